@@ -1,0 +1,116 @@
+/*
+ * t3d.h -- C ABI of libt3d.so: the B200 (sm_100a) reconstruction hot path of
+ * victorramirez952/tomography_3d_reconstructor.
+ *
+ * Boundary.  The reference is pure Python; its hot path is three classes (voxel_processor.py:27,
+ * surface_extractor.py:28, volume_calculator.py:10) whose arithmetic is delegated to numpy / scipy.ndimage /
+ * scikit-image.  This library replaces exactly those delegated calls.  The Python classes of the same names
+ * in tomography_3d_reconstructor_b200/ bind it through ctypes; every entry point below
+ * cites the reference line(s) it replaces.
+ *
+ * Conventions
+ *   - plain C, no torch types; `stream` is a cudaStream_t passed as void* (0 = default stream);
+ *   - pointers are DEVICE pointers unless the parameter name ends in `_host`;
+ *   - volumes are C-contiguous (Z, H, W); occupancy is bit-packed along x, LSB first, row stride
+ *     t3d_words_per_row(W) = ceil(W/32) uint32 words, bits at x >= W are zero;
+ *   - every function returns 0 on success; otherwise t3d_last_error() describes the failure
+ *     (1 = CUDA error, 2 = invalid argument).  Nothing here falls back to the CPU.
+ *   - variable-size outputs use count -> caller allocates -> emit.
+ */
+#ifndef T3D_H
+#define T3D_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+const char* t3d_last_error(void);
+int t3d_version(void);
+int64_t t3d_words_per_row(int W);
+
+/* ---- VoxelProcessor.create_voxel_data  (voxel_processor.py:36-54) -------------------------------------- */
+
+/* image_loader.py:108 `img >= threshold` + np.stack (voxel_processor.py:46).  masks: uint8 (Z,H,W); numpy bool
+ * masks use threshold = 1.  bits: (Z,H,wpr) uint32. */
+int t3d_pack_masks(const void* masks_u8, int Z, int H, int W, int threshold, void* bits, void* stream);
+
+/* inverse: numpy-bool view of a packed volume (the ndarray the reference API returns). out: uint8 (Z,H,W) 0/1 */
+int t3d_unpack_bits(const void* bits, int Z, int H, int W, void* out_u8, void* stream);
+
+/* scipy.ndimage.binary_fill_holes on 2-D planes, in place (voxel_processor.py:60-70).  Planes are
+ * plane_stride_words apart; scratch: t3d_fill_holes_scratch_bytes(n_planes, H, W) bytes. */
+int64_t t3d_fill_holes_scratch_bytes(int n_planes, int H, int W);
+int t3d_fill_holes_2d(void* bits, int n_planes, int64_t plane_stride_words, int H, int W, void* scratch, void* stream);
+
+/* z loop of _close_volume_ends (voxel_processor.py:72-75): out[z] = in[z] | (in[z-1] & in[z+1]), end planes
+ * copied.  lo_plane / hi_plane (may be NULL): neighbour planes of a z-slab (multi-GPU).  slice_counts_u64
+ * (may be NULL): Z per-slice popcounts of the result (np.sum, voxel_processor.py:51). */
+int t3d_gap_fill(const void* in_bits, void* out_bits, const void* lo_plane, const void* hi_plane, int Z, int H, int W,
+                 void* slice_counts_u64, void* stream);
+
+/* ---- VoxelProcessor.smooth_voxel_data  (voxel_processor.py:79-97) -------------------------------------- */
+
+/* n_stages (1..4) fused 6-connected erosions (bit s of erode_mask = 1; outside = True) / dilations (0; outside =
+ * False): skimage.morphology.binary_opening = stages {E,D}, binary_closing = {D,E}; opening then closing =
+ * {E,D,D,E} = n_stages 4, erode_mask 0b1001.  Out of place. */
+int t3d_morph(const void* in_bits, void* out_bits, int Z, int H, int W, int n_stages, unsigned erode_mask,
+              void* slice_counts_u64, void* stream);
+
+/* ---- VolumeCalculator  (volume_calculator.py:16-94) ----------------------------------------------------- */
+
+/* per-slice np.sum (volume_calculator.py:31-33) and np.where min/max (:39-44, :62-79).
+ * slice_counts_u64: Z uint64; bbox_i32x6: zmin,zmax,ymin,ymax,xmin,xmax (INT_MAX/-1 if empty). Either may be NULL. */
+int t3d_volume_stats(const void* bits, int Z, int H, int W, void* slice_counts_u64, void* bbox_i32x6, void* stream);
+
+/* ---- VoxelProcessor.generate_point_cloud  (voxel_processor.py:99-127) ----------------------------------- */
+int t3d_row_popcounts(const void* bits, int Z, int H, int W, void* row_counts_u32, void* stream);
+int t3d_point_cloud_emit(const void* bits, int Z, int H, int W, const void* row_base_u64, int subsample,
+                         const void* z_centre_mm_f64, double mm_per_pixel_y, double mm_per_pixel_x, void* out_f64,
+                         void* stream);
+
+/* generic exclusive scan of n_arrays uint32 arrays of length n (array k at in + k*n) */
+int64_t t3d_scan_workspace_bytes(int64_t n, int n_arrays);
+int t3d_exclusive_scan_u32(const void* in, void* out, int64_t n, int n_arrays, int out_is_u64, void* totals_u64,
+                           void* workspace, void* stream);
+
+/* ---- SurfaceExtractor.extract_manifold_surface  (surface_extractor.py:34-75) ---------------------------- */
+
+/* Sign of (float32(gaussian_filter(float64(pad(occ)), 0.5)) - 0.5) packed in padded coordinates
+ * (Z+2p, H+2p, wpr(W+2p)); surface_extractor.py:43-53 + the `> 0` test of marching cubes.  weights3_host: the three
+ * scipy kernel weights {centre, +-1, +-2} (NULL = the sigma 0.5 constants). */
+int t3d_field_sign(const void* occ_bits, int Z, int H, int W, int pad, const double* weights3_host, void* sign_bits,
+                   void* n_exact_u64, void* stream);
+
+/* marching cubes pass 1 on a sign volume (Zs,Hs,Ws): per voxel row counts of x/y/z cut edges and triangles,
+ * rowcnt_u32 = 4 arrays of Zs*Hs.  n_ambiguous_u64: cubes whose tiling Lewiner's tests could change. */
+int t3d_mc_count(const void* sign_bits, int Zs, int Hs, int Ws, void* rowcnt_u32, void* n_ambiguous_u64, void* stream);
+
+/* pass 2: vertices (z,y,x float32, after un-pad / variable-depth z map / mm scaling, surface_extractor.py:57-65,
+ * 82-113) and faces (int32, reference order, reversed winding). */
+int t3d_mc_emit(const void* sign_bits, const void* occ_bits, int Z, int H, int W, int pad, int gaussian,
+                const double* weights3_host, const void* rowbase_u32, uint32_t n_x, uint32_t n_y, int unpad_shift,
+                const void* cum_f64, const void* adj_f64, int n_cum, double mm_per_pixel_y, double mm_per_pixel_x,
+                int scale_in_f64, void* verts_f32, void* faces_i32, void* stream);
+
+/* test aids: the float32 field itself and the uint8 cube-case volume */
+int t3d_field_dense(const void* occ_bits, int Z, int H, int W, int pad, int gaussian, const double* weights3_host,
+                    void* out_f32, void* stream);
+int t3d_cube_cases(const void* sign_bits, int Zs, int Hs, int Ws, void* out_u8, void* stream);
+
+/* _ensure_manifold_mesh (surface_extractor.py:115-126): np.unique rows + degenerate-face drop.
+ * counts_u64[0] = V', [1] = F'. */
+int64_t t3d_canonicalize_workspace_bytes(int64_t V, int64_t F);
+int t3d_mesh_canonicalize(const void* verts_in, int64_t V, const void* faces_in, int64_t F, void* verts_out,
+                          void* faces_out_i64, void* faces_out_i32, void* counts_u64, void* workspace, void* stream);
+
+/* calculate_mesh_volume / calculate_surface_area (surface_extractor.py:128-148): out_f64 = {signed volume, area} */
+int64_t t3d_mesh_measure_workspace_bytes(void);
+int t3d_mesh_measure(const void* verts_f32, int64_t V, const void* faces, int64_t F, int faces_are_i64, void* out_f64,
+                     void* workspace, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* T3D_H */

@@ -1,0 +1,107 @@
+// t3d_common.cuh -- shared helpers for the sm_100a kernels behind include/t3d.h.
+//
+// Volume layout everywhere: C-contiguous (Z, H, W); occupancy is bit-packed along x, LSB first:
+//   word(z, y, w) bit i  <=>  voxel (z, y, x = 32*w + i),   row stride = words_per_row(W) = ceil(W/32).
+// Invariant: bits at x >= W in the last word of every row are zero.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#define T3D_NUM_SMS 148
+
+extern "C" void t3d_set_error(const char* fmt, ...);
+
+#define T3D_CHECK_LAUNCH(name)                                                                   \
+    do {                                                                                         \
+        cudaError_t e__ = cudaGetLastError();                                                    \
+        if (e__ != cudaSuccess) {                                                                \
+            t3d_set_error("%s: launch failed: %s", name, cudaGetErrorString(e__));               \
+            return 1;                                                                            \
+        }                                                                                        \
+    } while (0)
+
+#define T3D_CUDA(call)                                                                           \
+    do {                                                                                         \
+        cudaError_t e__ = (call);                                                                \
+        if (e__ != cudaSuccess) {                                                                \
+            t3d_set_error("%s failed: %s", #call, cudaGetErrorString(e__));                      \
+            return 1;                                                                            \
+        }                                                                                        \
+    } while (0)
+
+static inline int t3d_wpr(int W) { return (W + 31) >> 5; }
+
+__device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }
+
+// mask of valid bits (x < W) of word w in a row of width W
+__device__ __forceinline__ uint32_t valid_mask(int w, int W)
+{
+    const int rem = W - (w << 5);
+    if (rem >= 32) return 0xffffffffu;
+    if (rem <= 0) return 0u;
+    return (1u << rem) - 1u;
+}
+
+template <typename T>
+__device__ __forceinline__ T warp_sum(T v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__device__ __forceinline__ int warp_min(int v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ int warp_max(int v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// inclusive warp scan (Kogge-Stone over shuffles)
+__device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v)
+{
+    const uint32_t l = lane_id();
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, v, o);
+        if (l >= (uint32_t)o) v += t;
+    }
+    return v;
+}
+
+// streaming 128-bit loads/stores (no L1 allocation: every input byte is touched once)
+__device__ __forceinline__ uint4 ld_stream_u4(const void* p)
+{
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void st_stream_u4(void* p, uint4 v)
+{
+    asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y),
+                 "r"(v.z), "r"(v.w)
+                 : "memory");
+}
+
+// 4 bytes -> 4 bits: bit k = (byte k >= thr)
+__device__ __forceinline__ uint32_t ge4(uint32_t v, uint32_t thr4)
+{
+    const uint32_t m = __vcmpgeu4(v, thr4) & 0x80808080u;  // bit 7 of each byte
+    return (m * 0x00204081u) >> 28;
+}
+// 16 bytes -> 16 bits
+__device__ __forceinline__ uint32_t ge16(uint4 v, uint32_t thr4)
+{
+    return ge4(v.x, thr4) | (ge4(v.y, thr4) << 4) | (ge4(v.z, thr4) << 8) | (ge4(v.w, thr4) << 12);
+}
+// 4 bits -> 4 bytes of 0/1
+__device__ __forceinline__ uint32_t expand4(uint32_t nib) { return (nib * 0x00204081u) & 0x01010101u; }

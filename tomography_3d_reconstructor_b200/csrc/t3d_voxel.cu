@@ -1,0 +1,634 @@
+// t3d_voxel.cu -- VoxelProcessor / VolumeCalculator kernels (sm_100a).
+//
+// Reference semantics (file:line into the reference repository):
+//   pack        : image_loader.py:108 (`img >= threshold`) + np.stack, voxel_processor.py:46
+//   fill_holes  : scipy.ndimage.binary_fill_holes on slice 0 / Z-1, voxel_processor.py:60-70
+//   gap_fill    : the z loop of _close_volume_ends, voxel_processor.py:72-75 (== 3-point z stencil)
+//   morph       : skimage binary_opening / binary_closing, voxel_processor.py:87-91
+//   stats       : np.sum per slice (volume_calculator.py:31-33) and np.where min/max (:62-79)
+//   point cloud : np.where + subsample, voxel_processor.py:99-108
+//
+// All kernels are HBM/L2-bandwidth bound integer work on the bit-packed occupancy; no tensor cores.
+#include <stdarg.h>
+#include <string.h>
+
+#include "t3d_common.cuh"
+
+// ------------------------------------------------------------------------------------------------
+// error plumbing
+// ------------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+extern "C" void t3d_set_error(const char* fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+extern "C" const char* t3d_last_error(void) { return g_err; }
+extern "C" int t3d_version(void) { return 100; }
+extern "C" int64_t t3d_words_per_row(int W) { return t3d_wpr(W); }
+
+// ------------------------------------------------------------------------------------------------
+// pack: uint8 (Z,H,W) -> bits.  Fast path: W % 32 == 0 and 16-byte aligned input; each warp turns
+// 1024 contiguous bytes into 32 contiguous words per iteration with fully coalesced 128-bit loads.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_pack_flat(const uint8_t* __restrict__ src, uint32_t* __restrict__ dst,
+                                                   int64_t n_words, uint32_t thr4)
+{
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const uint32_t l = lane_id();
+    const int64_t n_chunks = n_words >> 5;  // chunks of 32 words = 1024 bytes
+    for (int64_t c = warp; c < n_chunks; c += n_warps) {
+        const uint8_t* p = src + (c << 10);
+        const uint4 a = ld_stream_u4(p + 16 * l);
+        const uint4 b = ld_stream_u4(p + 512 + 16 * l);
+        const uint32_t ha = ge16(a, thr4), hb = ge16(b, thr4);
+        const int s0 = (2 * l) & 31;
+        const uint32_t a0 = __shfl_sync(0xffffffffu, ha, s0), a1 = __shfl_sync(0xffffffffu, ha, s0 + 1);
+        const uint32_t b0 = __shfl_sync(0xffffffffu, hb, s0), b1 = __shfl_sync(0xffffffffu, hb, s0 + 1);
+        dst[(c << 5) + l] = (l < 16) ? (a0 | (a1 << 16)) : (b0 | (b1 << 16));
+    }
+    // tail words (n_words % 32): one thread per word
+    const int64_t tail0 = n_chunks << 5;
+    const int64_t t = tail0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n_words) {
+        const uint4* p = reinterpret_cast<const uint4*>(src + (t << 5));
+        dst[t] = ge16(p[0], thr4) | (ge16(p[1], thr4) << 16);
+    }
+}
+
+// generic path: any W, any alignment; one thread per output word
+__global__ void __launch_bounds__(256) k_pack_generic(const uint8_t* __restrict__ src, uint32_t* __restrict__ dst,
+                                                      int64_t n_rows, int W, int wpr, int thr)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_rows * wpr) return;
+    const int64_t row = i / wpr;
+    const int w = (int)(i - row * wpr);
+    const uint8_t* p = src + row * W + (w << 5);
+    const int n = min(32, W - (w << 5));
+    uint32_t v = 0;
+    for (int k = 0; k < n; ++k) v |= (uint32_t)(p[k] >= thr) << k;
+    dst[i] = v;
+}
+
+extern "C" int t3d_pack_masks(const void* masks_u8, int Z, int H, int W, int threshold, void* bits, void* stream)
+{
+    if (Z <= 0 || H <= 0 || W <= 0) { t3d_set_error("t3d_pack_masks: empty volume"); return 2; }
+    if (threshold < 0) threshold = 0;
+    if (threshold > 256) threshold = 256;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int wpr = t3d_wpr(W);
+    const int64_t rows = (int64_t)Z * H;
+    if ((W & 31) == 0 && ((uintptr_t)masks_u8 & 15) == 0 && threshold >= 1 && threshold <= 255) {
+        const int64_t n_words = rows * wpr;
+        const uint32_t thr4 = 0x01010101u * (uint32_t)threshold;
+        int64_t blocks = (n_words / 32 + 7) / 8;           // one warp-iteration per 32 words
+        const int64_t cap = (int64_t)T3D_NUM_SMS * 16;     // persistent-ish: 16 CTAs of 8 warps per SM
+        if (blocks > cap) blocks = cap;
+        if (blocks < 1) blocks = 1;
+        k_pack_flat<<<(unsigned)blocks, 256, 0, st>>>((const uint8_t*)masks_u8, (uint32_t*)bits, n_words, thr4);
+    } else {
+        const int64_t n = rows * wpr;
+        k_pack_generic<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const uint8_t*)masks_u8, (uint32_t*)bits, rows, W,
+                                                                    wpr, threshold);
+    }
+    T3D_CHECK_LAUNCH("t3d_pack_masks");
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// unpack: bits -> uint8 0/1 (numpy bool) for the API-visible volumes
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_unpack_flat(const uint32_t* __restrict__ src, uint8_t* __restrict__ dst,
+                                                     int64_t n_words)
+{
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const uint32_t l = lane_id();
+    const int64_t n_chunks = (n_words + 31) >> 5;
+    for (int64_t c = warp; c < n_chunks; c += n_warps) {
+        const int64_t wi = (c << 5) + l;
+        const uint32_t w = wi < n_words ? src[wi] : 0u;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            // lane writes 16 bytes at offset 16*l of this 512-byte half: bits of word (16*half + l/2), half-word l&1
+            const uint32_t ww = __shfl_sync(0xffffffffu, w, 16 * half + (l >> 1));
+            const uint32_t h = (ww >> (16 * (l & 1))) & 0xffffu;
+            uint4 o;
+            o.x = expand4(h & 15u); o.y = expand4((h >> 4) & 15u);
+            o.z = expand4((h >> 8) & 15u); o.w = expand4((h >> 12) & 15u);
+            const int64_t word_of_lane = (c << 5) + 16 * half + (l >> 1);
+            if (word_of_lane < n_words) st_stream_u4(dst + (c << 10) + 512 * half + 16 * l, o);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_unpack_generic(const uint32_t* __restrict__ src, uint8_t* __restrict__ dst,
+                                                        int64_t n_rows, int W, int wpr)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_rows * wpr) return;
+    const int64_t row = i / wpr;
+    const int w = (int)(i - row * wpr);
+    const uint32_t v = src[i];
+    uint8_t* p = dst + row * W + (w << 5);
+    const int n = min(32, W - (w << 5));
+    for (int k = 0; k < n; ++k) p[k] = (v >> k) & 1u;
+}
+
+extern "C" int t3d_unpack_bits(const void* bits, int Z, int H, int W, void* out_u8, void* stream)
+{
+    if (Z <= 0 || H <= 0 || W <= 0) { t3d_set_error("t3d_unpack_bits: empty volume"); return 2; }
+    cudaStream_t st = (cudaStream_t)stream;
+    const int wpr = t3d_wpr(W);
+    const int64_t rows = (int64_t)Z * H;
+    const int64_t n = rows * wpr;
+    if ((W & 31) == 0 && ((uintptr_t)out_u8 & 15) == 0) {
+        int64_t blocks = ((n + 31) / 32 + 7) / 8;
+        const int64_t cap = (int64_t)T3D_NUM_SMS * 16;
+        if (blocks > cap) blocks = cap;
+        if (blocks < 1) blocks = 1;
+        k_unpack_flat<<<(unsigned)blocks, 256, 0, st>>>((const uint32_t*)bits, (uint8_t*)out_u8, n);
+    } else {
+        k_unpack_generic<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const uint32_t*)bits, (uint8_t*)out_u8, rows, W, wpr);
+    }
+    T3D_CHECK_LAUNCH("t3d_unpack_bits");
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// 2-D hole filling of one bit plane (in place): complement of the 4-connected flood fill of the
+// background started from outside the image.  One CTA of 1024 threads per plane; every iteration
+// closes reachability along whole rows (carry-lookahead over words) and along whole columns
+// (segmented carry-lookahead over rows), so convex-ish objects converge in two iterations.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t fill_up(uint32_t m, uint32_t s)  // flood s within m towards bit 31
+{
+    s |= m & (s << 1);  m &= m << 1;
+    s |= m & (s << 2);  m &= m << 2;
+    s |= m & (s << 4);  m &= m << 4;
+    s |= m & (s << 8);  m &= m << 8;
+    s |= m & (s << 16);
+    return s;
+}
+__device__ __forceinline__ uint32_t fill_dn(uint32_t m, uint32_t s)  // towards bit 0
+{
+    s |= m & (s >> 1);  m &= m >> 1;
+    s |= m & (s >> 2);  m &= m >> 2;
+    s |= m & (s >> 4);  m &= m >> 4;
+    s |= m & (s >> 8);  m &= m >> 8;
+    s |= m & (s >> 16);
+    return s;
+}
+
+// closure of `reach` along one row, both directions.  One warp; lane owns words [l*k, (l+1)*k).
+__device__ bool row_closure(const uint32_t* mrow, uint32_t* rrow, int nw, int W)
+{
+    const uint32_t l = lane_id();
+    const int k = (nw + 31) >> 5;
+    const int w0 = l * k, w1 = min(nw, w0 + k);
+    bool changed = false;
+    // ---- towards +x
+    {
+        uint32_t carry = 0, P = 1;
+        for (int w = w0; w < w1; ++w) {
+            const uint32_t m = mrow[w];
+            const uint32_t f = fill_up(m, rrow[w] | (carry & m & 1u));
+            carry = f >> 31;
+            P &= (m == 0xffffffffu);
+        }
+        if (w0 >= w1) { carry = 0; P = 0; }
+        const uint32_t g = __ballot_sync(0xffffffffu, carry), p = __ballot_sync(0xffffffffu, P);
+        const uint32_t x = g | p;
+        const uint32_t cin = (((x + g) ^ x ^ g) >> l) & 1u;  // carry into lane l
+        carry = cin;
+        for (int w = w0; w < w1; ++w) {
+            const uint32_t m = mrow[w], r = rrow[w];
+            const uint32_t f = fill_up(m, r | (carry & m & 1u));
+            carry = f >> 31;
+            if (f != r) { rrow[w] = f; changed = true; }
+        }
+    }
+    __syncwarp();
+    // ---- towards -x
+    {
+        uint32_t carry = 0, P = 1;
+        for (int w = w1 - 1; w >= w0; --w) {
+            const uint32_t m = mrow[w];
+            const uint32_t f = fill_dn(m, rrow[w] | ((carry << 31) & m));
+            carry = f & 1u;
+            P &= (m == 0xffffffffu);
+        }
+        if (w0 >= w1) { carry = 0; P = 0; }
+        // lane order reversed: bit-reverse the ballots so that "carry into lane l" comes from lanes > l
+        const uint32_t g = __brev(__ballot_sync(0xffffffffu, carry)), p = __brev(__ballot_sync(0xffffffffu, P));
+        const uint32_t x = g | p;
+        const uint32_t cin = (((x + g) ^ x ^ g) >> (31 - l)) & 1u;
+        carry = cin;
+        for (int w = w1 - 1; w >= w0; --w) {
+            const uint32_t m = mrow[w], r = rrow[w];
+            const uint32_t f = fill_dn(m, r | ((carry << 31) & m));
+            carry = f & 1u;
+            if (f != r) { rrow[w] = f; changed = true; }
+        }
+    }
+    (void)W;
+    return changed;
+}
+
+#define FH_THREADS 1024
+#define FH_MAXSEG 64
+
+__global__ void __launch_bounds__(FH_THREADS) k_fill_holes(uint32_t* bits_planes, int64_t plane_stride_words,
+                                                           uint32_t* scratch, int H, int W, int nw)
+{
+    // plane handled by this CTA; scratch layout: [plane][0: mask m][1: reach r], each H*nw words
+    uint32_t* bits = bits_planes + (int64_t)blockIdx.x * plane_stride_words;
+    const int64_t pw = (int64_t)H * nw;
+    uint32_t* m = scratch + (int64_t)blockIdx.x * 2 * pw;
+    uint32_t* r = m + pw;
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, nwarps = FH_THREADS >> 5;
+
+    // background mask + seeds (background pixels on the image border touch the "outside")
+    for (int64_t i = tid; i < pw; i += FH_THREADS) {
+        const int y = (int)(i / nw), w = (int)(i - (int64_t)y * nw);
+        const uint32_t vm = valid_mask(w, W);
+        const uint32_t bg = ~bits[i] & vm;
+        uint32_t seed = 0;
+        if (y == 0 || y == H - 1) seed = bg;
+        if (w == 0) seed |= bg & 1u;
+        if (w == ((W - 1) >> 5)) seed |= bg & (1u << ((W - 1) & 31));
+        m[i] = bg;
+        r[i] = seed;
+    }
+    __syncthreads();
+
+    // column segments: thread (seg, col) sweeps rows [seg*L, seg*L+L)
+    __shared__ uint32_t sG[FH_MAXSEG][32];  // used in column tiles of 32 word-columns
+    __shared__ uint32_t sP[FH_MAXSEG][32];
+    const int nseg = min(FH_MAXSEG, min(FH_THREADS / 32, H));  // 32 segments
+    const int L = (H + nseg - 1) / nseg;
+
+    for (int iter = 0; iter < 4 * (H + W) + 8; ++iter) {
+        int changed = 0;
+        // ---- rows
+        for (int y = warp; y < H; y += nwarps)
+            changed |= row_closure(m + (int64_t)y * nw, r + (int64_t)y * nw, nw, W) ? 1 : 0;
+        __syncthreads();
+        // ---- columns, 32 word-columns at a time: thread = (seg = warp, col = lane)
+        for (int c0 = 0; c0 < nw; c0 += 32) {
+            const int c = c0 + (tid & 31), seg = warp;
+            const bool act = (c < nw) && (seg < nseg);
+            const int y0 = seg * L, y1 = min(H, y0 + L);
+            for (int dir = 0; dir < 2; ++dir) {
+                // pass 1: segment summary with zero carry-in
+                uint32_t G = 0, P = 0xffffffffu;
+                if (act && y0 < y1) {
+                    if (dir == 0) for (int y = y0; y < y1; ++y) { const uint32_t mm = m[(int64_t)y * nw + c]; G = r[(int64_t)y * nw + c] | (G & mm); P &= mm; }
+                    else          for (int y = y1 - 1; y >= y0; --y) { const uint32_t mm = m[(int64_t)y * nw + c]; G = r[(int64_t)y * nw + c] | (G & mm); P &= mm; }
+                } else { P = 0xffffffffu; G = 0; }
+                if (seg < FH_MAXSEG) { sG[seg][tid & 31] = G; sP[seg][tid & 31] = (act && y0 < y1) ? P : 0xffffffffu; }
+                __syncthreads();
+                // pass 2: carry into this segment
+                uint32_t cin = 0;
+                if (act) {
+                    if (dir == 0) for (int s = 0; s < seg; ++s) cin = sG[s][tid & 31] | (sP[s][tid & 31] & cin);
+                    else          for (int s = nseg - 1; s > seg; --s) cin = sG[s][tid & 31] | (sP[s][tid & 31] & cin);
+                }
+                // pass 3: final sweep
+                if (act && y0 < y1) {
+                    uint32_t carry = cin;
+                    if (dir == 0) {
+                        for (int y = y0; y < y1; ++y) {
+                            const int64_t i = (int64_t)y * nw + c;
+                            const uint32_t old = r[i], nv = old | (carry & m[i]);
+                            if (nv != old) { r[i] = nv; changed = 1; }
+                            carry = nv;
+                        }
+                    } else {
+                        for (int y = y1 - 1; y >= y0; --y) {
+                            const int64_t i = (int64_t)y * nw + c;
+                            const uint32_t old = r[i], nv = old | (carry & m[i]);
+                            if (nv != old) { r[i] = nv; changed = 1; }
+                            carry = nv;
+                        }
+                    }
+                }
+                __syncthreads();
+            }
+        }
+        if (!__syncthreads_or(changed)) break;
+    }
+    // holes = background never reached
+    for (int64_t i = tid; i < pw; i += FH_THREADS) bits[i] |= m[i] & ~r[i];
+}
+
+extern "C" int64_t t3d_fill_holes_scratch_bytes(int n_planes, int H, int W)
+{
+    return (int64_t)n_planes * 2 * H * t3d_wpr(W) * 4;
+}
+
+extern "C" int t3d_fill_holes_2d(void* bits, int n_planes, int64_t plane_stride_words, int H, int W, void* scratch,
+                                 void* stream)
+{
+    if (n_planes <= 0) return 0;
+    if (H <= 0 || W <= 0) { t3d_set_error("t3d_fill_holes_2d: empty plane"); return 2; }
+    k_fill_holes<<<n_planes, FH_THREADS, 0, (cudaStream_t)stream>>>((uint32_t*)bits, plane_stride_words,
+                                                                   (uint32_t*)scratch, H, W, t3d_wpr(W));
+    T3D_CHECK_LAUNCH("t3d_fill_holes_2d");
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// z gap fill: out[z] = f[z] | (f[z-1] & f[z+1]) for 1 <= z <= Z-2, copy for z = 0, Z-1
+// (voxel_processor.py:72-75; the np.any guards are redundant and the loop is not a recurrence,
+// SURVEY.md V3).  `lo` / `hi` are optional neighbour planes for z-slab sharding: when given, local
+// plane 0 / Z-1 is an interior plane of the global stack and uses them as f[-1] / f[Z].
+// Optionally accumulates per-slice popcounts of the result.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_gap_fill(const uint32_t* __restrict__ in, uint32_t* __restrict__ out,
+                                                  const uint32_t* __restrict__ lo, const uint32_t* __restrict__ hi,
+                                                  int Z, int64_t pw, unsigned long long* __restrict__ counts)
+{
+    const int z = blockIdx.y;
+    const uint32_t* c = in + (int64_t)z * pw;
+    const uint32_t* a = (z > 0) ? c - pw : lo;
+    const uint32_t* b = (z < Z - 1) ? c + pw : hi;
+    uint32_t* o = out + (int64_t)z * pw;
+    unsigned long long cnt = 0;
+    const bool fill = (a != nullptr) && (b != nullptr);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < pw; i += (int64_t)gridDim.x * blockDim.x) {
+        uint32_t v = c[i];
+        if (fill) v |= a[i] & b[i];
+        o[i] = v;
+        cnt += __popc(v);
+    }
+    if (counts) {
+        cnt = warp_sum(cnt);
+        __shared__ unsigned long long s[8];
+        if (lane_id() == 0) s[threadIdx.x >> 5] = cnt;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned long long t = 0;
+            for (int k = 0; k < (int)(blockDim.x >> 5); ++k) t += s[k];
+            if (t) atomicAdd(counts + z, t);
+        }
+    }
+}
+
+extern "C" int t3d_gap_fill(const void* in_bits, void* out_bits, const void* lo_plane, const void* hi_plane, int Z, int H,
+                            int W, void* slice_counts_u64, void* stream)
+{
+    if (Z <= 0 || H <= 0 || W <= 0) { t3d_set_error("t3d_gap_fill: empty volume"); return 2; }
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t pw = (int64_t)H * t3d_wpr(W);
+    if (slice_counts_u64) T3D_CUDA(cudaMemsetAsync(slice_counts_u64, 0, sizeof(unsigned long long) * Z, st));
+    int bx = (int)min((int64_t)64, (pw + 255) / 256);
+    dim3 grid(bx, Z);
+    k_gap_fill<<<grid, 256, 0, st>>>((const uint32_t*)in_bits, (uint32_t*)out_bits, (const uint32_t*)lo_plane,
+                                     (const uint32_t*)hi_plane, Z, pw, (unsigned long long*)slice_counts_u64);
+    T3D_CHECK_LAUNCH("t3d_gap_fill");
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// 6-connected binary morphology, up to 4 fused stages per launch through a shared-memory tile with a
+// halo of one voxel per stage.  Stage s is an erosion (bit s of erode_mask set; out-of-volume = 1) or
+// a dilation (out-of-volume = 0): exactly skimage's binary_erosion / binary_dilation with the default
+// cross footprint.  opening∘closing = stages E,D,D,E = erode_mask 0b1001.
+// ------------------------------------------------------------------------------------------------
+#define MT_Z 8
+#define MT_Y 16
+#define MT_XW 8
+#define MT_MAXR 4
+#define MT_SZ (MT_Z + 2 * MT_MAXR)
+#define MT_SY (MT_Y + 2 * MT_MAXR)
+#define MT_SX (MT_XW + 2)
+#define MT_THREADS 256
+
+__global__ void __launch_bounds__(MT_THREADS) k_morph(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, int Z,
+                                                      int H, int W, int nw, int nst, uint32_t erode_mask,
+                                                      unsigned long long* __restrict__ counts)
+{
+    __shared__ uint32_t buf[2][MT_SZ][MT_SY][MT_SX];
+    const int R = nst;
+    const int z0 = blockIdx.z * MT_Z - R, y0 = blockIdx.y * MT_Y - R, w0 = blockIdx.x * MT_XW - 1;
+    const int SZ = MT_Z + 2 * R, SY = MT_Y + 2 * R;
+    const int n_tile = SZ * SY * MT_SX;
+    const int tid = threadIdx.x;
+
+    for (int i = tid; i < n_tile; i += MT_THREADS) {
+        const int xw = i % MT_SX, t = i / MT_SX, yy = t % SY, zz = t / SY;
+        const int gz = z0 + zz, gy = y0 + yy, gw = w0 + xw;
+        uint32_t v = 0;
+        if (gz >= 0 && gz < Z && gy >= 0 && gy < H && gw >= 0 && gw < nw) v = in[((int64_t)gz * H + gy) * nw + gw];
+        buf[0][zz][yy][xw] = v;
+    }
+    __syncthreads();
+
+    int cur = 0;
+    for (int s = 0; s < nst; ++s) {
+        const bool er = (erode_mask >> s) & 1u;
+        const uint32_t B = er ? 0xffffffffu : 0u;
+        // positions computed by this stage: shrink by s+1 in z and y
+        const int lo = s + 1;
+        const int cz = SZ - 2 * lo, cy = SY - 2 * lo;
+        const int n = cz * cy * MT_SX;
+        for (int i = tid; i < n; i += MT_THREADS) {
+            const int xw = i % MT_SX, t = i / MT_SX, yy = lo + t % cy, zz = lo + t / cy;
+            const int gz = z0 + zz, gy = y0 + yy, gw = w0 + xw;
+            // source fetch with this stage's border value outside the volume
+            auto src = [&](int dz, int dy, int dxw) -> uint32_t {
+                const int az = gz + dz, ay = gy + dy, aw = gw + dxw;
+                if (az < 0 || az >= Z || ay < 0 || ay >= H || aw < 0 || aw >= nw) return B;
+                const int sx = xw + dxw;
+                if (sx < 0 || sx >= MT_SX) return B;  // outside the tile: only feeds halo garbage
+                const uint32_t vm = valid_mask(aw, W);
+                return (buf[cur][zz + dz][yy + dy][sx] & vm) | (B & ~vm);
+            };
+            const uint32_t c = src(0, 0, 0), l = src(0, 0, -1), r = src(0, 0, 1);
+            const uint32_t xm = (c << 1) | (l >> 31), xp = (c >> 1) | (r << 31);
+            const uint32_t zm = src(-1, 0, 0), zp = src(1, 0, 0), ym = src(0, -1, 0), yp = src(0, 1, 0);
+            uint32_t v = er ? (c & xm & xp & zm & zp & ym & yp) : (c | xm | xp | zm | zp | ym | yp);
+            buf[cur ^ 1][zz][yy][xw] = v;
+        }
+        __syncthreads();
+        cur ^= 1;
+    }
+
+    // write the central tile (a warp covers 32 consecutive words of one z plane: MT_Y*MT_XW = 128 per plane)
+    for (int i = tid; i < MT_Z * MT_Y * MT_XW; i += MT_THREADS) {
+        const int xw = i % MT_XW, t = i / MT_XW, yy = t % MT_Y, zz = t / MT_Y;
+        const int gz = z0 + R + zz, gy = y0 + R + yy, gw = w0 + 1 + xw;
+        uint32_t pc = 0;
+        if (gz < Z && gy < H && gw < nw) {
+            const uint32_t v = buf[cur][R + zz][R + yy][1 + xw] & valid_mask(gw, W);
+            out[((int64_t)gz * H + gy) * nw + gw] = v;
+            pc = __popc(v);
+        }
+        if (counts) {
+            pc = warp_sum(pc);
+            if (lane_id() == 0 && pc) atomicAdd(counts + gz, (unsigned long long)pc);
+        }
+    }
+}
+
+extern "C" int t3d_morph(const void* in_bits, void* out_bits, int Z, int H, int W, int n_stages, unsigned erode_mask,
+                         void* slice_counts_u64, void* stream)
+{
+    if (Z <= 0 || H <= 0 || W <= 0) { t3d_set_error("t3d_morph: empty volume"); return 2; }
+    if (n_stages < 1 || n_stages > MT_MAXR) { t3d_set_error("t3d_morph: n_stages must be 1..4"); return 2; }
+    if (in_bits == out_bits) { t3d_set_error("t3d_morph: in-place is not supported"); return 2; }
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nw = t3d_wpr(W);
+    if (slice_counts_u64) T3D_CUDA(cudaMemsetAsync(slice_counts_u64, 0, sizeof(unsigned long long) * Z, st));
+    dim3 grid((nw + MT_XW - 1) / MT_XW, (H + MT_Y - 1) / MT_Y, (Z + MT_Z - 1) / MT_Z);
+    k_morph<<<grid, MT_THREADS, 0, st>>>((const uint32_t*)in_bits, (uint32_t*)out_bits, Z, H, W, nw, n_stages, erode_mask,
+                                         (unsigned long long*)slice_counts_u64);
+    T3D_CHECK_LAUNCH("t3d_morph");
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-slice popcounts + bounding box of the set voxels (warp-shuffle tree reductions)
+// bbox = {zmin, zmax, ymin, ymax, xmin, xmax}; empty volume leaves {INT_MAX, -1, ...}
+// ------------------------------------------------------------------------------------------------
+__global__ void k_stats_init(unsigned long long* counts, int Z, int* bbox)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (counts && i < Z) counts[i] = 0;
+    if (bbox && i < 6) bbox[i] = (i & 1) ? -1 : 0x7fffffff;
+}
+
+__global__ void __launch_bounds__(256) k_stats(const uint32_t* __restrict__ bits, int H, int nw,
+                                               unsigned long long* __restrict__ counts, int* __restrict__ bbox)
+{
+    const int z = blockIdx.y;
+    const int64_t pw = (int64_t)H * nw;
+    const uint32_t* p = bits + (int64_t)z * pw;
+    unsigned long long cnt = 0;
+    int ymin = 0x7fffffff, ymax = -1, xmin = 0x7fffffff, xmax = -1;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < pw; i += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t v = p[i];
+        if (v) {
+            cnt += __popc(v);
+            const int y = (int)(i / nw), w = (int)(i - (int64_t)y * nw);
+            ymin = min(ymin, y); ymax = max(ymax, y);
+            xmin = min(xmin, (w << 5) + __ffs(v) - 1);
+            xmax = max(xmax, (w << 5) + 31 - __clz(v));
+        }
+    }
+    cnt = warp_sum(cnt);
+    ymin = warp_min(ymin); xmin = warp_min(xmin); ymax = warp_max(ymax); xmax = warp_max(xmax);
+    __shared__ unsigned long long sc[8];
+    __shared__ int sb[8][4];
+    const int wi = threadIdx.x >> 5;
+    if (lane_id() == 0) { sc[wi] = cnt; sb[wi][0] = ymin; sb[wi][1] = ymax; sb[wi][2] = xmin; sb[wi][3] = xmax; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 1; k < (int)(blockDim.x >> 5); ++k) {
+            cnt += sc[k]; ymin = min(ymin, sb[k][0]); ymax = max(ymax, sb[k][1]);
+            xmin = min(xmin, sb[k][2]); xmax = max(xmax, sb[k][3]);
+        }
+        if (cnt) {
+            if (counts) atomicAdd(counts + z, cnt);
+            if (bbox) {
+                atomicMin(bbox + 0, z); atomicMax(bbox + 1, z);
+                atomicMin(bbox + 2, ymin); atomicMax(bbox + 3, ymax);
+                atomicMin(bbox + 4, xmin); atomicMax(bbox + 5, xmax);
+            }
+        }
+    }
+}
+
+extern "C" int t3d_volume_stats(const void* bits, int Z, int H, int W, void* slice_counts_u64, void* bbox_i32x6,
+                                void* stream)
+{
+    if (Z <= 0 || H <= 0 || W <= 0) { t3d_set_error("t3d_volume_stats: empty volume"); return 2; }
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nw = t3d_wpr(W);
+    const int n_init = Z > 6 ? Z : 6;
+    k_stats_init<<<(n_init + 255) / 256, 256, 0, st>>>((unsigned long long*)slice_counts_u64, Z, (int*)bbox_i32x6);
+    const int64_t pw = (int64_t)H * nw;
+    int bx = (int)min((int64_t)32, (pw + 255) / 256);
+    dim3 grid(bx, Z);
+    k_stats<<<grid, 256, 0, st>>>((const uint32_t*)bits, H, nw, (unsigned long long*)slice_counts_u64, (int*)bbox_i32x6);
+    T3D_CHECK_LAUNCH("t3d_volume_stats");
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// point cloud (voxel_processor.py:99-127): np.where order (C order), every `sub`-th set voxel,
+// z -> cum[z] + depth[z]/2, y*mm_y, x*mm_x, float64 (N,3).
+// Two kernels: per-row popcounts (then an exclusive scan by the caller, t3d_scan_u32) and emission.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_row_popc(const uint32_t* __restrict__ bits, int64_t n_rows, int nw,
+                                                  uint32_t* __restrict__ row_counts)
+{
+    const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (row >= n_rows) return;
+    uint32_t c = 0;
+    for (int w = lane_id(); w < nw; w += 32) c += __popc(bits[row * nw + w]);
+    c = warp_sum(c);
+    if (lane_id() == 0) row_counts[row] = c;
+}
+
+__global__ void __launch_bounds__(256) k_point_cloud(const uint32_t* __restrict__ bits, int64_t n_rows, int H, int nw,
+                                                     const unsigned long long* __restrict__ row_base, int sub,
+                                                     const double* __restrict__ zc_mm, double mm_y, double mm_x,
+                                                     double* __restrict__ out)
+{
+    const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (row >= n_rows) return;
+    const int z = (int)(row / H), y = (int)(row - (int64_t)z * H);
+    unsigned long long base = row_base[row];
+    const uint32_t l = lane_id();
+    for (int w0 = 0; w0 < nw; w0 += 32) {
+        const int w = w0 + l;
+        uint32_t v = (w < nw) ? bits[row * nw + w] : 0u;
+        const uint32_t c = __popc(v);
+        const uint32_t incl = warp_incl_scan(c);
+        unsigned long long idx = base + incl - c;
+        while (v) {
+            const int b = __ffs(v) - 1;
+            v &= v - 1;
+            if (idx % (unsigned)sub == 0) {
+                double* o = out + 3 * (idx / (unsigned)sub);
+                o[0] = zc_mm[z];
+                o[1] = (double)y * mm_y;
+                o[2] = (double)((w << 5) + b) * mm_x;
+            }
+            ++idx;
+        }
+        base += __shfl_sync(0xffffffffu, incl, 31);
+    }
+}
+
+extern "C" int t3d_row_popcounts(const void* bits, int Z, int H, int W, void* row_counts_u32, void* stream)
+{
+    const int64_t rows = (int64_t)Z * H;
+    if (rows <= 0) return 0;
+    k_row_popc<<<(unsigned)((rows * 32 + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const uint32_t*)bits, rows,
+                                                                                      t3d_wpr(W), (uint32_t*)row_counts_u32);
+    T3D_CHECK_LAUNCH("t3d_row_popcounts");
+    return 0;
+}
+
+extern "C" int t3d_point_cloud_emit(const void* bits, int Z, int H, int W, const void* row_base_u64, int subsample,
+                                    const void* z_centre_mm_f64, double mm_per_pixel_y, double mm_per_pixel_x,
+                                    void* out_f64, void* stream)
+{
+    const int64_t rows = (int64_t)Z * H;
+    if (rows <= 0) return 0;
+    if (subsample < 1) subsample = 1;
+    k_point_cloud<<<(unsigned)((rows * 32 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        (const uint32_t*)bits, rows, H, t3d_wpr(W), (const unsigned long long*)row_base_u64, subsample,
+        (const double*)z_centre_mm_f64, mm_per_pixel_y, mm_per_pixel_x, (double*)out_f64);
+    T3D_CHECK_LAUNCH("t3d_point_cloud_emit");
+    return 0;
+}

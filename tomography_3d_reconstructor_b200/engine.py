@@ -1,0 +1,429 @@
+"""Device-side engine: thin Python over the C ABI (include/t3d.h).
+
+PyTorch is used only for device buffers, streams and host<->device copies; every arithmetic step is a
+kernel of libt3d.so.  Nothing in this module computes on the CPU and nothing falls back to it.
+"""
+from __future__ import annotations
+
+import ctypes
+import weakref
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import T3DError, check
+
+
+class T3DUnavailable(T3DError):
+    """libt3d.so or a CUDA device is missing.  Never swallowed by the reference-style `except Exception`."""
+
+
+def _require_cuda() -> torch.device:
+    if not torch.cuda.is_available():
+        raise T3DUnavailable("a CUDA device is required: this package has no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _L():
+    try:
+        return _lib.load()
+    except T3DError as e:  # missing shared object
+        raise T3DUnavailable(str(e)) from None
+
+
+def _stream() -> ctypes.c_void_p:
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t: Optional[torch.Tensor]) -> Optional[ctypes.c_void_p]:
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def words_per_row(W: int) -> int:
+    return (W + 31) // 32
+
+
+# scipy.ndimage._filters._gaussian_kernel1d(sigma=0.5, order=0, radius=2), restated with numpy so the three
+# weights are bit-identical to what gaussian_filter(sigma=0.5) uses (surface_extractor.py:50-51)
+def gaussian_weights_sigma_half() -> np.ndarray:
+    sigma, radius = 0.5, int(4.0 * 0.5 + 0.5)
+    x = np.arange(-radius, radius + 1)
+    phi = np.exp(-0.5 / (sigma * sigma) * x ** 2)
+    phi = phi / phi.sum()
+    return np.array([phi[2], phi[1], phi[0]], dtype=np.float64)  # centre, +-1, +-2
+
+
+_W3 = gaussian_weights_sigma_half()
+_W3_C = (ctypes.c_double * 3)(*_W3.tolist())
+
+
+# ----------------------------------------------------------------------------------------------------------
+# device containers
+# ----------------------------------------------------------------------------------------------------------
+class DeviceVolume:
+    """Bit-packed occupancy (Z, H, wpr) int32 on the device + lazily cached reductions."""
+
+    __slots__ = ("bits", "Z", "H", "W", "_counts", "_bbox", "__weakref__")
+
+    def __init__(self, bits: torch.Tensor, Z: int, H: int, W: int, counts: Optional[torch.Tensor] = None):
+        self.bits, self.Z, self.H, self.W = bits, Z, H, W
+        self._counts = counts  # device int64 (Z,) or host np.int64 once fetched
+        self._bbox = None
+
+    @property
+    def shape(self) -> Tuple[int, int, int]:
+        return (self.Z, self.H, self.W)
+
+    # per-slice np.sum(voxel_data[z]) (volume_calculator.py:31-33), exact integers
+    def slice_counts(self) -> np.ndarray:
+        if isinstance(self._counts, np.ndarray):
+            return self._counts
+        if self._counts is None:
+            self._run_stats()
+        c = self._counts.cpu().numpy().astype(np.int64)
+        self._counts = c
+        return c
+
+    def _run_stats(self) -> None:
+        dev = self.bits.device
+        counts = torch.empty(self.Z, dtype=torch.int64, device=dev)
+        bbox = torch.empty(6, dtype=torch.int32, device=dev)
+        check(_L().t3d_volume_stats(_p(self.bits), self.Z, self.H, self.W, _p(counts), _p(bbox), _stream()),
+              "t3d_volume_stats")
+        if self._counts is None:
+            self._counts = counts
+        self._bbox = bbox
+
+    def bbox(self) -> Optional[Tuple[int, int, int, int, int, int]]:
+        """(zmin, zmax, ymin, ymax, xmin, xmax) of the set voxels, None if the volume is empty."""
+        if self._bbox is None:
+            self._run_stats()
+        if isinstance(self._bbox, torch.Tensor):
+            b = tuple(int(v) for v in self._bbox.cpu().tolist())
+            self._bbox = b if b[1] >= 0 else ()
+        return self._bbox if self._bbox else None
+
+    def to_host(self) -> np.ndarray:
+        """numpy bool (Z, H, W): unpack on the device, copy through pinned memory."""
+        out = torch.empty((self.Z, self.H, self.W), dtype=torch.uint8, device=self.bits.device)
+        check(_L().t3d_unpack_bits(_p(self.bits), self.Z, self.H, self.W, _p(out), _stream()), "t3d_unpack_bits")
+        host = torch.empty((self.Z, self.H, self.W), dtype=torch.bool, pin_memory=True)
+        host.view(torch.uint8).copy_(out, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return host.numpy()
+
+
+class DeviceMesh:
+    __slots__ = ("verts", "faces", "n_ambiguous", "n_exact", "_measures", "__weakref__")
+
+    def __init__(self, verts: torch.Tensor, faces: torch.Tensor, n_ambiguous: int = 0, n_exact: int = 0):
+        self.verts, self.faces = verts, faces
+        self.n_ambiguous, self.n_exact = n_ambiguous, n_exact
+        self._measures = None
+
+    def measures(self) -> Tuple[float, float]:
+        """(signed volume, area), float64 accumulation on the device."""
+        if self._measures is None:
+            self._measures = mesh_measure(self.verts, self.faces)
+        return self._measures
+
+
+# ----------------------------------------------------------------------------------------------------------
+# identity registry: host ndarray handed to the caller -> device object it was materialised from
+# ----------------------------------------------------------------------------------------------------------
+class _Registry:
+    def __init__(self):
+        self._d = {}
+
+    def register(self, arr: np.ndarray, obj) -> None:
+        key = id(arr)
+
+        def _drop(_ref, key=key, d=self._d):
+            d.pop(key, None)
+
+        self._d[key] = (weakref.ref(arr, _drop), obj)
+
+    def lookup(self, arr):
+        e = self._d.get(id(arr))
+        if e is not None and e[0]() is arr:
+            return e[1]
+        return None
+
+
+volumes = _Registry()
+meshes = _Registry()
+
+
+# ----------------------------------------------------------------------------------------------------------
+# host -> device
+# ----------------------------------------------------------------------------------------------------------
+def _as_stack(mask_images) -> np.ndarray:
+    """Return a (Z,H,W) 1-byte array without copying when the slices already lie back to back in memory."""
+    if isinstance(mask_images, np.ndarray):
+        arr = mask_images
+        if arr.ndim != 3:
+            raise ValueError("expected a (Z,H,W) stack")
+    else:
+        first = np.asarray(mask_images[0])
+        n = len(mask_images)
+        contiguous = first.ndim == 2 and first.flags.c_contiguous and first.dtype.itemsize == 1
+        if contiguous:
+            step = first.nbytes
+            base = first.__array_interface__["data"][0]
+            for k, m in enumerate(mask_images):
+                if (not isinstance(m, np.ndarray) or m.shape != first.shape or m.dtype != first.dtype
+                        or not m.flags.c_contiguous or m.__array_interface__["data"][0] != base + k * step):
+                    contiguous = False
+                    break
+        if contiguous:
+            buf = (ctypes.c_uint8 * (first.nbytes * n)).from_address(first.__array_interface__["data"][0])
+            arr = np.frombuffer(buf, dtype=first.dtype).reshape((n,) + first.shape)
+        else:
+            arr = np.stack([np.asarray(m) for m in mask_images], axis=0)  # voxel_processor.py:46
+    if arr.dtype == np.bool_:
+        return arr.view(np.uint8)
+    if arr.dtype == np.uint8:
+        return arr
+    return (arr != 0).view(np.uint8)
+
+
+def upload_u8(stack_u8: np.ndarray) -> torch.Tensor:
+    dev = _require_cuda()
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", UserWarning)  # read-only ndarray -> tensor (we only read it)
+        t = torch.from_numpy(np.ascontiguousarray(stack_u8))
+    return t.to(dev, non_blocking=True)
+
+
+def pack(masks_u8_dev: torch.Tensor, threshold: int = 1) -> DeviceVolume:
+    """image_loader.py:108 + np.stack (voxel_processor.py:46) on the device."""
+    Z, H, W = (int(s) for s in masks_u8_dev.shape)
+    bits = torch.empty((Z, H, words_per_row(W)), dtype=torch.int32, device=masks_u8_dev.device)
+    check(_L().t3d_pack_masks(_p(masks_u8_dev), Z, H, W, int(threshold), _p(bits), _stream()), "t3d_pack_masks")
+    return DeviceVolume(bits, Z, H, W)
+
+
+def volume_from_host(voxel_data: np.ndarray) -> DeviceVolume:
+    dv = volumes.lookup(voxel_data)
+    if dv is not None:
+        return dv
+    arr = np.asarray(voxel_data)
+    if arr.ndim != 3:
+        raise ValueError("voxel data must be (Z,H,W)")
+    return pack(upload_u8(_as_stack(arr)), 1)
+
+
+# ----------------------------------------------------------------------------------------------------------
+# VoxelProcessor stages
+# ----------------------------------------------------------------------------------------------------------
+def close_volume_ends(dv: DeviceVolume, lo_plane: Optional[torch.Tensor] = None,
+                      hi_plane: Optional[torch.Tensor] = None, fill_first: bool = True,
+                      fill_last: bool = True, in_place: bool = True) -> DeviceVolume:
+    """voxel_processor.py:56-77.  lo/hi planes and fill_* flags exist for z-slab sharding."""
+    L = _L()
+    Z, H, W = dv.shape
+    wpr = words_per_row(W)
+    bits = dv.bits if in_place else dv.bits.clone()
+    planes: List[int] = []
+    if fill_first:
+        planes.append(0)
+    if fill_last and (Z - 1) not in planes:
+        planes.append(Z - 1)
+    if planes:
+        scratch = torch.empty(int(L.t3d_fill_holes_scratch_bytes(len(planes), H, W)) // 4, dtype=torch.int32,
+                              device=bits.device)
+        if len(planes) == 2:
+            check(L.t3d_fill_holes_2d(_p(bits), 2, (Z - 1) * H * wpr, H, W, _p(scratch), _stream()), "t3d_fill_holes_2d")
+        else:
+            check(L.t3d_fill_holes_2d(_p(bits[planes[0]]), 1, 0, H, W, _p(scratch), _stream()), "t3d_fill_holes_2d")
+    out = torch.empty_like(bits)
+    counts = torch.empty(Z, dtype=torch.int64, device=bits.device)
+    check(L.t3d_gap_fill(_p(bits), _p(out), _p(lo_plane), _p(hi_plane), Z, H, W, _p(counts), _stream()), "t3d_gap_fill")
+    return DeviceVolume(out, Z, H, W, counts)
+
+
+def morph_stages(iterations: int, create_manifold: bool) -> List[bool]:
+    """Stage list (True = erosion) of smooth_voxel_data, voxel_processor.py:86-91.  Closing is idempotent
+    (SURVEY.md V4), so iterations >= 1 closings collapse to one."""
+    stages: List[bool] = []
+    if create_manifold:
+        stages += [True, False]          # binary_opening = dilate(erode(x))
+    if iterations >= 1:
+        stages += [False, True]          # binary_closing = erode(dilate(x))
+    return stages
+
+
+def morph(dv: DeviceVolume, stages: Sequence[bool], want_counts: bool = True) -> DeviceVolume:
+    L = _L()
+    Z, H, W = dv.shape
+    cur = dv.bits
+    counts = None
+    if not stages:
+        return DeviceVolume(cur.clone(), Z, H, W, None)
+    i = 0
+    while i < len(stages):
+        chunk = list(stages[i:i + 4])
+        i += len(chunk)
+        mask = 0
+        for s, er in enumerate(chunk):
+            if er:
+                mask |= 1 << s
+        out = torch.empty_like(cur)
+        last = i >= len(stages)
+        if last and want_counts:
+            counts = torch.empty(Z, dtype=torch.int64, device=cur.device)
+        check(L.t3d_morph(_p(cur), _p(out), Z, H, W, len(chunk), mask, _p(counts) if last else None, _stream()), "t3d_morph")
+        cur = out
+    return DeviceVolume(cur, Z, H, W, counts)
+
+
+def smooth(dv: DeviceVolume, iterations: int = 3, create_manifold: bool = True) -> DeviceVolume:
+    return morph(dv, morph_stages(iterations, create_manifold))
+
+
+# ----------------------------------------------------------------------------------------------------------
+# SurfaceExtractor stages
+# ----------------------------------------------------------------------------------------------------------
+def z_map_arrays(slice_depths, add_padding: bool) -> Tuple[np.ndarray, np.ndarray]:
+    """cumulative / adjusted depths of _apply_variable_slice_depths (surface_extractor.py:84-95), host float64."""
+    sd = np.asarray(slice_depths, dtype=np.float64)
+    if len(sd) == 0:
+        return np.zeros(0), np.zeros(0)
+    adj = np.concatenate([[sd[0]], sd, [sd[-1]]]) if add_padding else sd
+    cum = np.cumsum(np.concatenate([[0], adj]))
+    return cum, adj
+
+
+def field_sign(dv: DeviceVolume, pad: int) -> Tuple[torch.Tensor, Tuple[int, int, int], torch.Tensor]:
+    Z, H, W = dv.shape
+    Zp, Hp, Wp = Z + 2 * pad, H + 2 * pad, W + 2 * pad
+    sign = torch.empty((Zp, Hp, words_per_row(Wp)), dtype=torch.int32, device=dv.bits.device)
+    n_exact = torch.empty(1, dtype=torch.int64, device=dv.bits.device)
+    check(_L().t3d_field_sign(_p(dv.bits), Z, H, W, pad, _W3_C, _p(sign), _p(n_exact), _stream()), "t3d_field_sign")
+    return sign, (Zp, Hp, Wp), n_exact
+
+
+def exclusive_scan_u32(x: torch.Tensor, n: int, n_arrays: int, out_u64: bool = False):
+    L = _L()
+    ws = torch.empty(int(L.t3d_scan_workspace_bytes(n, n_arrays)) // 8 + 1, dtype=torch.int64, device=x.device)
+    totals = torch.empty(n_arrays, dtype=torch.int64, device=x.device)
+    out = torch.empty(n * n_arrays, dtype=torch.int64 if out_u64 else torch.int32, device=x.device)
+    check(L.t3d_exclusive_scan_u32(_p(x), _p(out), n, n_arrays, 1 if out_u64 else 0, _p(totals), _p(ws), _stream()),
+          "t3d_exclusive_scan_u32")
+    return out, totals
+
+
+def extract_surface(dv: DeviceVolume, slice_depths, mm_per_pixel_y, mm_per_pixel_x, manifold: bool = True,
+                    add_padding: bool = True, canonical: Optional[bool] = None) -> DeviceMesh:
+    """surface_extractor.py:43-68 on the device.  Raises RuntimeError/ValueError where skimage would."""
+    L = _L()
+    Z, H, W = dv.shape
+    pad = 1 if (manifold and add_padding) else 0
+    gaussian = 1 if manifold else 0
+    if Z + 2 * pad < 2 or H + 2 * pad < 2 or W + 2 * pad < 2:
+        raise ValueError("Input array must be at least 2x2x2.")
+    dev = dv.bits.device
+    if gaussian:
+        sign, (Zs, Hs, Ws), n_exact_t = field_sign(dv, pad)
+    else:
+        sign, (Zs, Hs, Ws), n_exact_t = dv.bits, (Z, H, W), None
+    rows = Zs * Hs
+    rowcnt = torch.empty(4 * rows, dtype=torch.int32, device=dev)
+    n_amb = torch.empty(1, dtype=torch.int64, device=dev)
+    check(L.t3d_mc_count(_p(sign), Zs, Hs, Ws, _p(rowcnt), _p(n_amb), _stream()), "t3d_mc_count")
+    rowbase, totals = exclusive_scan_u32(rowcnt, rows, 4)
+    tail = torch.cat([totals, n_amb, n_exact_t if n_exact_t is not None else torch.zeros_like(n_amb)]).cpu().tolist()
+    nX, nY, nZ, nT, n_ambiguous, n_exact = (int(v) for v in tail)
+    V = nX + nY + nZ
+    if nT == 0 or V == 0:
+        # skimage: ValueError (level outside the data range) or RuntimeError (no surface)
+        raise RuntimeError("No surface found at the given iso value.")
+    if V >= 2 ** 31 or nT >= 2 ** 31:
+        raise T3DError("mesh too large for one device (V=%d, F=%d)" % (V, nT))
+    verts = torch.empty((V, 3), dtype=torch.float32, device=dev)
+    faces = torch.empty((nT, 3), dtype=torch.int32, device=dev)
+    cum, adj = z_map_arrays(slice_depths, add_padding)
+    n_cum = len(cum)
+    cum_d = torch.from_numpy(cum).to(dev) if n_cum else None
+    adj_d = torch.from_numpy(adj).to(dev) if n_cum else None
+    strong = isinstance(mm_per_pixel_y, np.floating) or isinstance(mm_per_pixel_x, np.floating)
+    check(L.t3d_mc_emit(_p(sign), _p(dv.bits), Z, H, W, pad, gaussian, _W3_C, _p(rowbase), nX, nY, 1 if manifold else 0,
+                        _p(cum_d), _p(adj_d), n_cum, float(mm_per_pixel_y), float(mm_per_pixel_x), 1 if strong else 0,
+                        _p(verts), _p(faces), _stream()), "t3d_mc_emit")
+    if canonical is None:
+        canonical = manifold
+    if not canonical:
+        return DeviceMesh(verts, faces, n_ambiguous, n_exact)
+    v2, f2 = canonicalize(verts, faces)
+    return DeviceMesh(v2, f2, n_ambiguous, n_exact)
+
+
+def canonicalize(verts: torch.Tensor, faces_i32: torch.Tensor, faces_i64: bool = True):
+    """_ensure_manifold_mesh (surface_extractor.py:115-126) on the device."""
+    L = _L()
+    V, F = int(verts.shape[0]), int(faces_i32.shape[0])
+    dev = verts.device
+    ws = torch.empty(int(L.t3d_canonicalize_workspace_bytes(V, F)) // 8 + 1, dtype=torch.int64, device=dev)
+    vout = torch.empty((V, 3), dtype=torch.float32, device=dev)
+    fout = torch.empty((F, 3), dtype=torch.int64 if faces_i64 else torch.int32, device=dev)
+    counts = torch.empty(2, dtype=torch.int64, device=dev)
+    check(L.t3d_mesh_canonicalize(_p(verts), V, _p(faces_i32), F, _p(vout), _p(fout) if faces_i64 else None,
+                                  None if faces_i64 else _p(fout), _p(counts), _p(ws), _stream()), "t3d_mesh_canonicalize")
+    v2, f2 = (int(c) for c in counts.cpu().tolist())
+    return vout[:v2], fout[:f2]
+
+
+def mesh_measure(verts: torch.Tensor, faces: torch.Tensor) -> Tuple[float, float]:
+    L = _L()
+    dev = verts.device
+    ws = torch.empty(int(L.t3d_mesh_measure_workspace_bytes()) // 8, dtype=torch.float64, device=dev)
+    out = torch.empty(2, dtype=torch.float64, device=dev)
+    verts = verts.contiguous()
+    faces = faces.contiguous()
+    check(L.t3d_mesh_measure(_p(verts), int(verts.shape[0]), _p(faces), int(faces.shape[0]),
+                             1 if faces.dtype == torch.int64 else 0, _p(out), _p(ws), _stream()), "t3d_mesh_measure")
+    v, a = out.cpu().tolist()
+    return float(v), float(a)
+
+
+def mesh_from_host(vertices: np.ndarray, faces: np.ndarray) -> DeviceMesh:
+    m = meshes.lookup(vertices)
+    if m is not None and meshes.lookup(faces) is m:
+        return m
+    dev = _require_cuda()
+    v = torch.from_numpy(np.ascontiguousarray(vertices, dtype=np.float32)).to(dev)
+    f = np.ascontiguousarray(faces)
+    if f.dtype not in (np.int32, np.int64):
+        f = f.astype(np.int64)
+    return DeviceMesh(v, torch.from_numpy(f).to(dev))
+
+
+# ----------------------------------------------------------------------------------------------------------
+# point cloud (voxel_processor.py:99-127)
+# ----------------------------------------------------------------------------------------------------------
+def point_cloud(dv: DeviceVolume, mm_per_pixel_x, mm_per_pixel_y, slice_depths, subsample_factor: int = 1) -> np.ndarray:
+    L = _L()
+    Z, H, W = dv.shape
+    dev = dv.bits.device
+    rows = Z * H
+    rc = torch.empty(rows, dtype=torch.int32, device=dev)
+    check(L.t3d_row_popcounts(_p(dv.bits), Z, H, W, _p(rc), _stream()), "t3d_row_popcounts")
+    base, total = exclusive_scan_u32(rc, rows, 1, out_u64=True)
+    n = int(total.cpu().item())
+    sub = subsample_factor if subsample_factor > 1 else 1
+    n_out = (n + sub - 1) // sub
+    sd = np.asarray(slice_depths, dtype=np.float64)
+    cum = np.cumsum(np.concatenate([[0], sd]))
+    zc = np.empty(Z, dtype=np.float64)
+    k = min(Z, len(sd))
+    zc[:k] = cum[:k] + sd[:k] / 2          # centre of slice (voxel_processor.py:116-117)
+    zc[k:] = cum[-1]                       # (:118-119)
+    out = torch.empty((n_out, 3), dtype=torch.float64, device=dev)
+    if n_out:
+        check(L.t3d_point_cloud_emit(_p(dv.bits), Z, H, W, _p(base), sub, _p(torch.from_numpy(zc).to(dev)),
+                                     float(mm_per_pixel_y), float(mm_per_pixel_x), _p(out), _stream()),
+              "t3d_point_cloud_emit")
+    return out.cpu().numpy()

@@ -1,0 +1,108 @@
+#!/usr/bin/env python3
+"""Drop-in `voxel_processor` module: the reference's VoxelProcessor (voxel_processor.py:27-163) with every
+array operation executed by sm_100a kernels (libt3d.so).  Class name, attributes, method names, parameter
+names/order, defaults, prints and error behaviour follow the reference; see INTEGRATION.md.
+
+Differences a caller can observe:
+  * returned voxel arrays are real `np.ndarray[bool]` but read-only (the device copy they mirror is cached by
+    array identity so smooth -> extract -> volume never re-uploads);
+  * with scikit-image absent the reference degrades to an identity smooth (voxel_processor.py:81-82); this
+    class always applies the skimage semantics (6-connected opening, then closing).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import engine
+
+
+class VoxelProcessor:
+    """Handles voxel data creation and processing operations (B200)."""
+
+    def __init__(self):
+        self.voxel_data = None
+        self.side_0_count = 0
+        self.side_1_count = 0
+        self.side_2_count = 0
+
+    # ------------------------------------------------------------------------------------------------
+    def _publish(self, dv: engine.DeviceVolume) -> np.ndarray:
+        host = dv.to_host()
+        host.setflags(write=False)
+        engine.volumes.register(host, dv)
+        return host
+
+    def create_voxel_data(self, mask_images: list, close_ends: bool = True,
+                          side_0_count: int = 0, side_1_count: int = 0, side_2_count: int = 0) -> np.ndarray:
+        """Create 3D voxel data from masks with side information (voxel_processor.py:36-54)."""
+        if mask_images is None or len(mask_images) == 0:
+            raise ValueError("Load masks first, hmm.")
+
+        self.side_0_count = side_0_count
+        self.side_1_count = side_1_count
+        self.side_2_count = side_2_count
+
+        dv = engine.pack(engine.upload_u8(engine._as_stack(mask_images)), 1)
+        if close_ends:
+            dv = engine.close_volume_ends(dv)
+        active = int(dv.slice_counts().sum())
+        self.voxel_data = self._publish(dv)
+        print(f"Voxels: {self.voxel_data.shape}, active: {active:,}")
+        return self.voxel_data
+
+    def create_voxel_data_from_u8(self, stack_u8, threshold: int = 200, close_ends: bool = True,
+                                  side_0_count: int = 0, side_1_count: int = 0, side_2_count: int = 0) -> np.ndarray:
+        """Additive fast path: grayscale uint8 (Z,H,W) stack (host ndarray or CUDA tensor) thresholded
+        on the device (`img >= threshold`, image_loader.py:108), skipping the host-side bool list."""
+        import torch
+        self.side_0_count, self.side_1_count, self.side_2_count = side_0_count, side_1_count, side_2_count
+        dev_u8 = stack_u8 if isinstance(stack_u8, torch.Tensor) else engine.upload_u8(np.asarray(stack_u8, dtype=np.uint8))
+        if dev_u8.numel() == 0:
+            raise ValueError("Load masks first, hmm.")
+        dv = engine.pack(dev_u8, threshold)
+        if close_ends:
+            dv = engine.close_volume_ends(dv)
+        active = int(dv.slice_counts().sum())
+        self.voxel_data = self._publish(dv)
+        print(f"Voxels: {self.voxel_data.shape}, active: {active:,}")
+        return self.voxel_data
+
+    def smooth_voxel_data(self, voxel_data: np.ndarray, iterations: int = 3, create_manifold: bool = True) -> np.ndarray:
+        """Smooth voxel data with morphological operations (voxel_processor.py:79-97)."""
+        dv = engine.volume_from_host(voxel_data)
+        return self._publish(engine.smooth(dv, iterations, create_manifold))
+
+    def generate_point_cloud(self, voxel_data: np.ndarray, mm_per_pixel_x: float,
+                             mm_per_pixel_y: float, slice_depths: np.ndarray, subsample_factor: int = 1) -> np.ndarray:
+        """Generate point cloud from voxels with variable slice depths (voxel_processor.py:99-127)."""
+        dv = engine.volume_from_host(voxel_data)
+        return engine.point_cloud(dv, mm_per_pixel_x, mm_per_pixel_y, slice_depths, subsample_factor)
+
+    def calculate_slice_depths(self, total_depth_mm: float) -> np.ndarray:
+        """Calculate depth per slice based on side structure (voxel_processor.py:129-163).  Host scalar code."""
+        total_slices = self.side_0_count + self.side_1_count + self.side_2_count
+
+        if self.side_1_count == 0 or total_slices == 0:
+            if total_slices == 0:
+                return np.array([])
+            return np.full(total_slices, total_depth_mm / total_slices)
+
+        side_1_depth_per_slice = total_depth_mm / self.side_1_count
+        side_0_2_total_depth = 2 * side_1_depth_per_slice
+        side_0_depth_per_slice = side_0_2_total_depth / self.side_0_count if self.side_0_count > 0 else 0
+        side_2_depth_per_slice = side_0_2_total_depth / self.side_2_count if self.side_2_count > 0 else 0
+
+        depths = ([side_0_depth_per_slice] * self.side_0_count + [side_1_depth_per_slice] * self.side_1_count
+                  + [side_2_depth_per_slice] * self.side_2_count)
+
+        print(f"Slice depth sequence: Side_0[0-{self.side_0_count-1}], Side_1[{self.side_0_count}-{self.side_0_count+self.side_1_count-1}], Side_2[{self.side_0_count+self.side_1_count}-{len(depths)-1}]")
+
+        return np.array(depths)
+
+    # ------------------------------------------------------------------------------------------------
+    # additive API (no reference counterpart)
+    def compute_sdf(self, voxel_data: np.ndarray, sampling=(1.0, 1.0, 1.0)) -> np.ndarray:
+        """Exact Euclidean signed distance (positive inside), float32 (Z,H,W)."""
+        from . import edt
+        dv = engine.volume_from_host(voxel_data)
+        return edt.signed_distance(dv, sampling).cpu().numpy()
