@@ -1,0 +1,375 @@
+#!/usr/bin/env python3
+"""bench.py -- headline benchmark: Gvoxels/s, mask stack -> stitched mesh + volumes (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--shape Z,H,W]
+
+One "step" = one pass of the whole hot path over one synthetic ellipsoid mask stack:
+uint8 masks -> threshold+bit-pack -> close ends -> opening/closing -> Gaussian field sign -> two-pass marching
+cubes -> canonical mesh -> mesh volume/area + voxel-count volumes.  N=1 workload = BASELINE.json configs[1]
+(512 slices of 1024x1024).  N>1: the stack grows with N (512*N slices), z-slab sharded with NCCL halo exchange and
+mesh stitching (weak scaling).  `value` has inputs resident in HBM; `e2e` goes through the reference-facing classes
+with host buffers (H2D + D2H inside the timed region).  `--impl reference` times the CPU oracle (the restated
+reference pipeline; the unmodified reference cannot run without scikit-image) on a bounded z-slab sample.
+"""
+from __future__ import annotations
+
+import argparse
+import contextlib
+import io
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "Gvoxels/s mask-stack->mesh+volume"
+PHYS = dict(x_length_mm=143.1, y_length_mm=95.03, total_depth_mm=6.0)  # config.py:12-14
+THRESHOLD = 200                                                        # config.py:27
+
+
+def side_counts(Z):
+    s0 = Z // 8
+    return (s0, Z - 2 * s0, s0)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# reference arm / CPU baseline: the oracle (CPU restatement of the reference pipeline) on a bounded z-slab sample
+# ----------------------------------------------------------------------------------------------------------------
+def _cpu_sample_job(args):
+    Z, H, W, z0, z1 = args
+    from oracle import cpu_ref
+    u8 = cpu_ref.ellipsoid_phantom_u8(Z, H, W, z0, z1)
+    t0 = time.perf_counter()
+    cpu_ref.reference_pipeline(u8, THRESHOLD, side_counts(z1 - z0), PHYS["total_depth_mm"], PHYS["x_length_mm"],
+                               PHYS["y_length_mm"])
+    return time.perf_counter() - t0, (z1 - z0) * H * W
+
+
+def cpu_sample(Z, H, W, n_slices, workers):
+    """Run the oracle on `workers` disjoint central z-slabs of n_slices each, in parallel processes.
+    Returns (seconds, voxels)."""
+    import multiprocessing as mp
+    n_slices = max(4, min(n_slices, Z // max(1, workers)))
+    zc = Z // 2 - (n_slices * workers) // 2
+    jobs = [(Z, H, W, zc + k * n_slices, zc + (k + 1) * n_slices) for k in range(workers)]
+    t0 = time.perf_counter()
+    if workers == 1:
+        res = [_cpu_sample_job(jobs[0])]
+    else:
+        with mp.get_context("spawn").Pool(workers) as pool:
+            res = pool.map(_cpu_sample_job, jobs)
+    wall = time.perf_counter() - t0
+    if workers > 1:
+        wall = max(r[0] for r in res)  # exclude process start-up
+    return wall, sum(r[1] for r in res), n_slices
+
+
+def run_reference(args, Z, H, W):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import cpu_ref
+    cpu_ref.build()
+    cores = os.cpu_count() or 1
+    workers = max(1, min(cores, 16))
+    budget_per_step = 150.0 / max(1, args.steps + args.warmup)
+    # measured oracle speed is ~2.5 Mvox/s per core (scipy.ndimage is single-threaded)
+    n_slices = int(max(4, min(32, budget_per_step * 2.5e6 / (H * W))))
+    for _ in range(args.warmup):
+        cpu_sample(Z, H, W, n_slices, workers)
+    secs, vox = 0.0, 0
+    for _ in range(args.steps):
+        s, v, n_slices = cpu_sample(Z, H, W, n_slices, workers)
+        secs += s
+        vox += v
+    value = vox / secs / 1e9
+    sample = "%d disjoint central z-slabs of %d slices x %dx%d per step (one per worker process)" % (workers, n_slices, H, W)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "Gvoxels/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / max(1, args.steps),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bool/f64 (numpy/scipy)",
+        "data": "synthetic",
+        "config": {"workload": "C1 ellipsoid stack %dx%dx%d (bounded sample per step)" % (Z, H, W), "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "Gvoxels/s", "cores": workers, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "Gvoxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.rows.append(ln.strip())
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for k, nm in enumerate(names):
+                if f[3 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_phantom_u8(Z_total, H, W, z0, z1, device):
+    """Analytic ellipsoid of SURVEY.md 8d, slices [z0, z1) of a Z_total stack, uint8 0/255, built on the device."""
+    import torch
+    cz, cy, cx = Z_total / 2 - 0.3, H / 2 + 0.2, W / 2 - 0.1
+    rz, ry, rx = 0.42 * Z_total, 0.33 * H, 0.45 * W
+    out = torch.empty((z1 - z0, H, W), dtype=torch.uint8, device=device)
+    y = ((torch.arange(H, dtype=torch.float64, device=device) - cy) / ry) ** 2
+    x = ((torch.arange(W, dtype=torch.float64, device=device) - cx) / rx) ** 2
+    yx = y[:, None] + x[None, :]
+    for a in range(z0, z1, 16):
+        b = min(z1, a + 16)
+        z = ((torch.arange(a, b, dtype=torch.float64, device=device) - cz) / rz) ** 2
+        out[a - z0:b - z0] = ((z[:, None, None] + yx[None]) <= 1.0).to(torch.uint8) * 255
+    return out
+
+
+STAGE_BYTES = {  # algorithmic bytes per voxel of each single-kernel stage
+    "pack": 1.0 + 0.125, "smooth": 0.25, "field_sign": 0.25, "mc_count": 0.125,
+}
+
+
+def run_ours(args, Z, H, W):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from tomography_3d_reconstructor_b200 import _lib, engine, pipeline
+    lib = _lib.load()
+
+    Zg = Z * world                       # weak scaling: the stack grows with the number of GPUs
+    sides = side_counts(Zg)
+    if world > 1:
+        from tomography_3d_reconstructor_b200 import sharded
+        z0, z1 = sharded.slab_range(Zg, rank, world)
+    else:
+        z0, z1 = 0, Zg
+    masks = make_phantom_u8(Zg, H, W, z0, z1, dev)
+
+    def step(mark=None):
+        if world > 1:
+            return sharded.reconstruct(masks, Zg, z0, THRESHOLD, sides, PHYS["total_depth_mm"], PHYS["x_length_mm"],
+                                       PHYS["y_length_mm"], mark=mark)
+        return pipeline.reconstruct(masks, THRESHOLD, sides, PHYS["total_depth_mm"], PHYS["x_length_mm"],
+                                    PHYS["y_length_mm"], mark=mark)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(3, args.warmup)):
+        res = step()
+    barrier()
+    l0 = lib.t3d_launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clocks:
+        barrier()
+        ev0.record()
+        for _ in range(args.steps):
+            res = step()
+        ev1.record()
+        barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = (lib.t3d_launch_count() - l0) // max(1, args.steps)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    voxels = Zg * H * W
+    value = voxels * args.steps / (ms * 1e-3) / 1e9
+
+    # ---- per-stage device times (one instrumented step, events on the launching stream)
+    marks = []
+
+    def mark(name):
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        marks.append((name, e))
+
+    stage_ms = {}
+    for _ in range(3):
+        marks.clear()
+        barrier()
+        mark("start")
+        step(mark)
+        barrier()
+        for (n0, e0), (n1, e1) in zip(marks[:-1], marks[1:]):
+            stage_ms.setdefault(n1, []).append(e0.elapsed_time(e1))
+    stage_ms = {k: float(np.min(v)) for k, v in stage_ms.items()}
+
+    # ---- e2e through the reference-facing classes, host buffers in pinned memory
+    e2e = None
+    if world == 1 and not args.no_e2e:
+        from tomography_3d_reconstructor_b200 import VoxelProcessor, SurfaceExtractor, VolumeCalculator
+        host_bool = torch.empty((Z, H, W), dtype=torch.bool, pin_memory=True)
+        host_bool.copy_(masks >= THRESHOLD)          # image_loader.py:108 happens upstream of the hot path
+        torch.cuda.synchronize()
+        hb = host_bool.numpy()
+        mask_list = [hb[z] for z in range(Z)]
+        mm_x, mm_y = PHYS["x_length_mm"] / W, PHYS["y_length_mm"] / H
+
+        def api_step():
+            vp, se, vc = VoxelProcessor(), SurfaceExtractor(), VolumeCalculator()
+            vox = vp.create_voxel_data(mask_list, True, *sides)
+            depths = vp.calculate_slice_depths(PHYS["total_depth_mm"])
+            sm = vp.smooth_voxel_data(vox, 3, True)
+            processed = vc.calculate_voxel_volume_variable_depth(sm, mm_x, mm_y, depths)
+            v, f = se.extract_manifold_surface(sm, depths, mm_y, mm_x, True, True, True)
+            mv = se.calculate_mesh_volume(v, f)
+            ar = se.calculate_surface_area(v, f)
+            props = vc.analyze_object_properties(vox, processed, mv, ar, mm_x, mm_y, depths, PHYS["x_length_mm"],
+                                                 PHYS["y_length_mm"], PHYS["total_depth_mm"])
+            return vox, sm, v, f, props
+
+        sink = io.StringIO()
+        with contextlib.redirect_stdout(sink):
+            for _ in range(2):
+                out = api_step()
+            n_e2e = max(2, min(args.steps, 5))
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(n_e2e):
+                out = api_step()
+            torch.cuda.synchronize()
+            e2e_s = (time.perf_counter() - t0) / n_e2e
+        vox, sm, v, f, props = out
+        e2e = {"value": voxels / e2e_s / 1e9, "unit": "Gvoxels/s", "h2d_bytes_per_step": int(hb.nbytes),
+               "d2h_bytes_per_step": int(vox.nbytes + sm.nbytes + v.nbytes + f.nbytes), "ms_per_step": 1e3 * e2e_s,
+               "steps": n_e2e, "api": "VoxelProcessor.create_voxel_data -> smooth_voxel_data -> "
+               "SurfaceExtractor.extract_manifold_surface -> calculate_mesh_volume/area -> VolumeCalculator.analyze_object_properties"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+    mesh = res["mesh"]
+    V, F = int(mesh.verts.shape[0]), int(mesh.faces.shape[0])
+    mesh_bytes = 12 * V + 12 * F
+    # dominant single kernel among the volume-sized stages
+    per_gpu_vox = (z1 - z0) * H * W
+    cand = {k: stage_ms[k] for k in STAGE_BYTES if k in stage_ms}
+    cand["mc_emit"] = stage_ms.get("mc_emit", 0.0)
+    dom = max(cand, key=cand.get)
+    if dom == "mc_emit":
+        dom_bytes = 0.125 * per_gpu_vox + mesh_bytes
+    else:
+        dom_bytes = STAGE_BYTES[dom] * per_gpu_vox
+    achieved = dom_bytes / (stage_ms[dom] * 1e-3) / 1e9
+    bytes_alg = 1.5 * voxels + mesh_bytes
+    line = {
+        "metric": METRIC, "value": value, "unit": "Gvoxels/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u8 -> bit-packed u32 (topology), f64 field taps -> f32 vertices", "data": "synthetic",
+        "config": {"workload": "C1 (BASELINE configs[1]): %d slices of %dx%d analytic ellipsoid masks (u8 0/255), threshold 200, "
+                   "close ends + opening/closing + Gaussian(0.5) marching cubes + volumes%s" %
+                   (Zg, H, W, "" if world == 1 else "; z-slab sharded over %d GPUs" % world),
+                   "shape": [Zg, H, W], "l2": "inputs larger than L2: %.0f MB of u8 masks per GPU per step" % (per_gpu_vox / 1e6),
+                   "mesh": {"vertices": V, "faces": F, "n_ambiguous_cubes": int(mesh.n_ambiguous)}},
+        "clocks": clocks.summary(),
+        "gpu_launches": int(launches),
+        "stages_ms": stage_ms,
+        "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": dom_bytes},
+        "pipeline_roofline": {"bytes_alg_per_step": bytes_alg, "achieved": bytes_alg * args.steps / (ms * 1e-3) / 1e9,
+                              "peak": peak * world, "unit": "GB/s",
+                              "frac": bytes_alg * args.steps / (ms * 1e-3) / 1e9 / (peak * world)},
+        "results": {"voxel_volume_mm3": float(res["voxel_volume_mm3"]), "mesh_volume_mm3": float(res["mesh_volume_mm3"]),
+                    "surface_area_mm2": float(res["surface_area_mm2"]), "active_voxels": int(res["active_voxels"])},
+    }
+    if e2e is not None:
+        line["e2e"] = e2e
+    if world == 1 and not args.no_cpu:
+        from oracle import cpu_ref
+        cpu_ref.build()
+        secs, vox_s, n_sl = cpu_sample(Z, H, W, 16, 1)
+        line["cpu_baseline"] = {"value": vox_s / secs / 1e9, "unit": "Gvoxels/s", "cores": 1, "kind": "port",
+                                "sample": "central z-slab of %d slices x %dx%d of the same phantom, oracle/cpu_ref.py "
+                                "(scipy.ndimage is single-threaded), %.1f s" % (n_sl, H, W, secs)}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--shape", default="512,1024,1024", help="Z,H,W per GPU")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    Z, H, W = (int(v) for v in args.shape.split(","))
+    if args.impl == "reference":
+        run_reference(args, Z, H, W)
+    else:
+        run_ours(args, Z, H, W)
+
+
+if __name__ == "__main__":
+    main()

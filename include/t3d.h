@@ -29,6 +29,9 @@ extern "C" {
 const char* t3d_last_error(void);
 int t3d_version(void);
 int64_t t3d_words_per_row(int W);
+/* number of kernels of this library launched so far by this process (bench.py gpu_launches) */
+int64_t t3d_launch_count(void);
+void t3d_count_launches(int n);
 
 /* ---- VoxelProcessor.create_voxel_data  (voxel_processor.py:36-54) -------------------------------------- */
 

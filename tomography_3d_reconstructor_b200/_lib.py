@@ -19,6 +19,8 @@ SIGNATURES = {
     "t3d_last_error": (_c.c_char_p, []),
     "t3d_version": (_i, []),
     "t3d_words_per_row": (_i64, [_i]),
+    "t3d_launch_count": (_i64, []),
+    "t3d_count_launches": (None, [_i]),
     "t3d_pack_masks": (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
     "t3d_unpack_bits": (_i, [_vp, _i, _i, _i, _vp, _vp]),
     "t3d_fill_holes_scratch_bytes": (_i64, [_i, _i, _i]),

@@ -11,6 +11,7 @@
 #define T3D_NUM_SMS 148
 
 extern "C" void t3d_set_error(const char* fmt, ...);
+extern "C" void t3d_count_launches(int n);  // bookkeeping for bench.py's gpu_launches (our kernels only)
 
 #define T3D_CHECK_LAUNCH(name)                                                                   \
     do {                                                                                         \

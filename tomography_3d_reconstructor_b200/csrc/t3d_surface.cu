@@ -408,6 +408,7 @@ extern "C" int t3d_exclusive_scan_u32(const void* in, void* out, int64_t n, int 
     else
         k_scan_final<uint32_t><<<grid, SC_THREADS, 0, st>>>((const uint32_t*)in, (uint32_t*)out, n, n, bs, (int)nb);
     T3D_CHECK_LAUNCH("t3d_exclusive_scan_u32");
+    t3d_count_launches(3);
     return 0;
 }
 
@@ -625,6 +626,7 @@ extern "C" int t3d_field_sign(const void* occ_bits, int Z, int H, int W, int pad
     T3D_CUDA(cudaMemsetAsync(n_exact_u64, 0, 8, st));
     k_field_sign<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(v, (uint32_t*)sign_bits, nwp, (unsigned long long*)n_exact_u64);
     T3D_CHECK_LAUNCH("t3d_field_sign");
+    t3d_count_launches(1);
     return 0;
 }
 
@@ -641,6 +643,7 @@ extern "C" int t3d_mc_count(const void* sign_bits, int Zs, int Hs, int Ws, void*
                                                                     (uint32_t*)rowcnt_u32, rows,
                                                                     (unsigned long long*)n_ambiguous_u64);
     T3D_CHECK_LAUNCH("t3d_mc_count");
+    t3d_count_launches(1);
     return 0;
 }
 
@@ -675,6 +678,7 @@ extern "C" int t3d_mc_emit(const void* sign_bits, const void* occ_bits, int Z, i
     p.faces = (int32_t*)faces_i32;
     k_mc_emit<<<(unsigned)((p.n_rows + EM_WARPS - 1) / EM_WARPS), EM_WARPS * 32, 0, (cudaStream_t)stream>>>(p);
     T3D_CHECK_LAUNCH("t3d_mc_emit");
+    t3d_count_launches(1);
     return 0;
 }
 
@@ -698,6 +702,7 @@ extern "C" int t3d_field_dense(const void* occ_bits, int Z, int H, int W, int pa
     const int64_t total = (int64_t)v.Zp * v.Hp * v.Wp;
     k_field_dense<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(v, (float*)out_f32);
     T3D_CHECK_LAUNCH("t3d_field_dense");
+    t3d_count_launches(1);
     return 0;
 }
 
@@ -726,6 +731,7 @@ extern "C" int t3d_cube_cases(const void* sign_bits, int Zs, int Hs, int Ws, voi
     k_cube_cases<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const uint32_t*)sign_bits, Zs, Hs, Ws,
                                                                                   t3d_wpr(Ws), (uint8_t*)out_u8);
     T3D_CHECK_LAUNCH("t3d_cube_cases");
+    t3d_count_launches(1);
     return 0;
 }
 
@@ -879,6 +885,7 @@ extern "C" int t3d_mesh_canonicalize(const void* verts_in, int64_t V, const void
         T3D_CUDA(cudaMemsetAsync(counts + 1, 0, 8, st));
     }
     T3D_CHECK_LAUNCH("t3d_mesh_canonicalize");
+    t3d_count_launches(F > 0 ? 7 : 5);
     return 0;
 }
 
@@ -947,5 +954,6 @@ extern "C" int t3d_mesh_measure(const void* verts_f32, int64_t V, const void* fa
         k_mesh_measure<int32_t><<<blocks, 256, 0, st>>>((const float*)verts_f32, (const int32_t*)faces, F, (double*)workspace);
     k_reduce_partials<<<1, 256, 0, st>>>((const double*)workspace, blocks, (double*)out_f64);
     T3D_CHECK_LAUNCH("t3d_mesh_measure");
+    t3d_count_launches(2);
     return 0;
 }

@@ -27,6 +27,9 @@ extern "C" void t3d_set_error(const char* fmt, ...)
     va_end(ap);
 }
 extern "C" const char* t3d_last_error(void) { return g_err; }
+static long long g_launches = 0;
+extern "C" void t3d_count_launches(int n) { g_launches += n; }
+extern "C" int64_t t3d_launch_count(void) { return g_launches; }
 extern "C" int t3d_version(void) { return 100; }
 extern "C" int64_t t3d_words_per_row(int W) { return t3d_wpr(W); }
 
@@ -97,6 +100,7 @@ extern "C" int t3d_pack_masks(const void* masks_u8, int Z, int H, int W, int thr
                                                                     wpr, threshold);
     }
     T3D_CHECK_LAUNCH("t3d_pack_masks");
+    t3d_count_launches(1);
     return 0;
 }
 
@@ -157,6 +161,7 @@ extern "C" int t3d_unpack_bits(const void* bits, int Z, int H, int W, void* out_
         k_unpack_generic<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const uint32_t*)bits, (uint8_t*)out_u8, rows, W, wpr);
     }
     T3D_CHECK_LAUNCH("t3d_unpack_bits");
+    t3d_count_launches(1);
     return 0;
 }
 
@@ -341,6 +346,7 @@ extern "C" int t3d_fill_holes_2d(void* bits, int n_planes, int64_t plane_stride_
     k_fill_holes<<<n_planes, FH_THREADS, 0, (cudaStream_t)stream>>>((uint32_t*)bits, plane_stride_words,
                                                                    (uint32_t*)scratch, H, W, t3d_wpr(W));
     T3D_CHECK_LAUNCH("t3d_fill_holes_2d");
+    t3d_count_launches(1);
     return 0;
 }
 
@@ -393,6 +399,7 @@ extern "C" int t3d_gap_fill(const void* in_bits, void* out_bits, const void* lo_
     k_gap_fill<<<grid, 256, 0, st>>>((const uint32_t*)in_bits, (uint32_t*)out_bits, (const uint32_t*)lo_plane,
                                      (const uint32_t*)hi_plane, Z, pw, (unsigned long long*)slice_counts_u64);
     T3D_CHECK_LAUNCH("t3d_gap_fill");
+    t3d_count_launches(1);
     return 0;
 }
 
@@ -491,6 +498,7 @@ extern "C" int t3d_morph(const void* in_bits, void* out_bits, int Z, int H, int 
     k_morph<<<grid, MT_THREADS, 0, st>>>((const uint32_t*)in_bits, (uint32_t*)out_bits, Z, H, W, nw, n_stages, erode_mask,
                                          (unsigned long long*)slice_counts_u64);
     T3D_CHECK_LAUNCH("t3d_morph");
+    t3d_count_launches(1);
     return 0;
 }
 
@@ -559,6 +567,7 @@ extern "C" int t3d_volume_stats(const void* bits, int Z, int H, int W, void* sli
     dim3 grid(bx, Z);
     k_stats<<<grid, 256, 0, st>>>((const uint32_t*)bits, H, nw, (unsigned long long*)slice_counts_u64, (int*)bbox_i32x6);
     T3D_CHECK_LAUNCH("t3d_volume_stats");
+    t3d_count_launches(2);
     return 0;
 }
 
@@ -616,6 +625,7 @@ extern "C" int t3d_row_popcounts(const void* bits, int Z, int H, int W, void* ro
     k_row_popc<<<(unsigned)((rows * 32 + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const uint32_t*)bits, rows,
                                                                                       t3d_wpr(W), (uint32_t*)row_counts_u32);
     T3D_CHECK_LAUNCH("t3d_row_popcounts");
+    t3d_count_launches(1);
     return 0;
 }
 
@@ -630,5 +640,6 @@ extern "C" int t3d_point_cloud_emit(const void* bits, int Z, int H, int W, const
         (const uint32_t*)bits, rows, H, t3d_wpr(W), (const unsigned long long*)row_base_u64, subsample,
         (const double*)z_centre_mm_f64, mm_per_pixel_y, mm_per_pixel_x, (double*)out_f64);
     T3D_CHECK_LAUNCH("t3d_point_cloud_emit");
+    t3d_count_launches(1);
     return 0;
 }

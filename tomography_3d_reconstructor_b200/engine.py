@@ -317,9 +317,10 @@ def exclusive_scan_u32(x: torch.Tensor, n: int, n_arrays: int, out_u64: bool = F
 
 
 def extract_surface(dv: DeviceVolume, slice_depths, mm_per_pixel_y, mm_per_pixel_x, manifold: bool = True,
-                    add_padding: bool = True, canonical: Optional[bool] = None) -> DeviceMesh:
+                    add_padding: bool = True, canonical: Optional[bool] = None, mark=None) -> DeviceMesh:
     """surface_extractor.py:43-68 on the device.  Raises RuntimeError/ValueError where skimage would."""
     L = _L()
+    mark = mark or (lambda _n: None)
     Z, H, W = dv.shape
     pad = 1 if (manifold and add_padding) else 0
     gaussian = 1 if manifold else 0
@@ -330,11 +331,14 @@ def extract_surface(dv: DeviceVolume, slice_depths, mm_per_pixel_y, mm_per_pixel
         sign, (Zs, Hs, Ws), n_exact_t = field_sign(dv, pad)
     else:
         sign, (Zs, Hs, Ws), n_exact_t = dv.bits, (Z, H, W), None
+    mark("field_sign")
     rows = Zs * Hs
     rowcnt = torch.empty(4 * rows, dtype=torch.int32, device=dev)
     n_amb = torch.empty(1, dtype=torch.int64, device=dev)
     check(L.t3d_mc_count(_p(sign), Zs, Hs, Ws, _p(rowcnt), _p(n_amb), _stream()), "t3d_mc_count")
+    mark("mc_count")
     rowbase, totals = exclusive_scan_u32(rowcnt, rows, 4)
+    mark("scan")
     tail = torch.cat([totals, n_amb, n_exact_t if n_exact_t is not None else torch.zeros_like(n_amb)]).cpu().tolist()
     nX, nY, nZ, nT, n_ambiguous, n_exact = (int(v) for v in tail)
     V = nX + nY + nZ
@@ -353,11 +357,13 @@ def extract_surface(dv: DeviceVolume, slice_depths, mm_per_pixel_y, mm_per_pixel
     check(L.t3d_mc_emit(_p(sign), _p(dv.bits), Z, H, W, pad, gaussian, _W3_C, _p(rowbase), nX, nY, 1 if manifold else 0,
                         _p(cum_d), _p(adj_d), n_cum, float(mm_per_pixel_y), float(mm_per_pixel_x), 1 if strong else 0,
                         _p(verts), _p(faces), _stream()), "t3d_mc_emit")
+    mark("mc_emit")
     if canonical is None:
         canonical = manifold
     if not canonical:
         return DeviceMesh(verts, faces, n_ambiguous, n_exact)
     v2, f2 = canonicalize(verts, faces)
+    mark("canonicalize")
     return DeviceMesh(v2, f2, n_ambiguous, n_exact)
 
 
