@@ -174,8 +174,8 @@ def make_phantom_u8(Z_total, H, W, z0, z1, device):
     return out
 
 
-STAGE_BYTES = {  # algorithmic bytes per voxel of each single-kernel stage
-    "pack": 1.0 + 0.125, "smooth": 0.25, "field_sign": 0.25, "mc_count": 0.125,
+STAGE_BYTES = {  # algorithmic bytes per voxel of each volume-sized stage
+    "pack": 1.0 + 0.125, "close_ends": 0.25, "smooth": 4 * 0.25, "field_sign": 0.25, "mc_flags": 0.125 + 1.0 / 256,
 }
 
 
@@ -312,12 +312,8 @@ def run_ours(args, Z, H, W):
     # dominant single kernel among the volume-sized stages
     per_gpu_vox = (z1 - z0) * H * W
     cand = {k: stage_ms[k] for k in STAGE_BYTES if k in stage_ms}
-    cand["mc_emit"] = stage_ms.get("mc_emit", 0.0)
     dom = max(cand, key=cand.get)
-    if dom == "mc_emit":
-        dom_bytes = 0.125 * per_gpu_vox + mesh_bytes
-    else:
-        dom_bytes = STAGE_BYTES[dom] * per_gpu_vox
+    dom_bytes = STAGE_BYTES[dom] * per_gpu_vox
     achieved = dom_bytes / (stage_ms[dom] * 1e-3) / 1e9
     bytes_alg = 1.5 * voxels + mesh_bytes
     line = {

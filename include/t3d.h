@@ -55,11 +55,12 @@ int t3d_gap_fill(const void* in_bits, void* out_bits, const void* lo_plane, cons
 
 /* ---- VoxelProcessor.smooth_voxel_data  (voxel_processor.py:79-97) -------------------------------------- */
 
-/* n_stages (1..4) fused 6-connected erosions (bit s of erode_mask = 1; outside = True) / dilations (0; outside =
- * False): skimage.morphology.binary_opening = stages {E,D}, binary_closing = {D,E}; opening then closing =
- * {E,D,D,E} = n_stages 4, erode_mask 0b1001.  Out of place. */
+/* n_stages 6-connected erosions (bit s of erode_mask = 1; outside = True) / dilations (0; outside = False), one
+ * launch per stage: skimage.morphology.binary_opening = stages {E,D}, binary_closing = {D,E}; opening then closing
+ * = {E,D,D,E} = n_stages 4, erode_mask 0b1001.  Out of place; scratch: t3d_morph_scratch_bytes(...) bytes. */
+int64_t t3d_morph_scratch_bytes(int Z, int H, int W, int n_stages);
 int t3d_morph(const void* in_bits, void* out_bits, int Z, int H, int W, int n_stages, unsigned erode_mask,
-              void* slice_counts_u64, void* stream);
+              void* slice_counts_u64, void* scratch, void* stream);
 
 /* ---- VolumeCalculator  (volume_calculator.py:16-94) ----------------------------------------------------- */
 
@@ -75,8 +76,8 @@ int t3d_point_cloud_emit(const void* bits, int Z, int H, int W, const void* row_
 
 /* generic exclusive scan of n_arrays uint32 arrays of length n (array k at in + k*n) */
 int64_t t3d_scan_workspace_bytes(int64_t n, int n_arrays);
-int t3d_exclusive_scan_u32(const void* in, void* out, int64_t n, int n_arrays, int out_is_u64, void* totals_u64,
-                           void* workspace, void* stream);
+int t3d_exclusive_scan_u32(const void* in, void* out, int64_t n, int n_arrays, int out_is_u64, int popcount_input,
+                           void* totals_u64, void* workspace, void* stream);
 
 /* ---- SurfaceExtractor.extract_manifold_surface  (surface_extractor.py:34-75) ---------------------------- */
 
@@ -86,16 +87,29 @@ int t3d_exclusive_scan_u32(const void* in, void* out, int64_t n, int n_arrays, i
 int t3d_field_sign(const void* occ_bits, int Z, int H, int W, int pad, const double* weights3_host, void* sign_bits,
                    void* n_exact_u64, void* stream);
 
-/* marching cubes pass 1 on a sign volume (Zs,Hs,Ws): per voxel row counts of x/y/z cut edges and triangles,
- * rowcnt_u32 = 4 arrays of Zs*Hs.  n_ambiguous_u64: cubes whose tiling Lewiner's tests could change. */
-int t3d_mc_count(const void* sign_bits, int Zs, int Hs, int Ws, void* rowcnt_u32, void* n_ambiguous_u64, void* stream);
-
-/* pass 2: vertices (z,y,x float32, after un-pad / variable-depth z map / mm scaling, surface_extractor.py:57-65,
- * 82-113) and faces (int32, reference order, reversed winding). */
-int t3d_mc_emit(const void* sign_bits, const void* occ_bits, int Z, int H, int W, int pad, int gaussian,
-                const double* weights3_host, const void* rowbase_u32, uint32_t n_x, uint32_t n_y, int unpad_shift,
-                const void* cum_f64, const void* adj_f64, int n_cum, double mm_per_pixel_y, double mm_per_pixel_x,
-                int scale_in_f64, void* verts_f32, void* faces_i32, void* stream);
+/* Two-pass marching cubes on a sign volume (Zs,Hs,Ws) = skimage.measure.marching_cubes(volume, 0.5), sparse after the
+ * first dense pass (see csrc/t3d_mc.cu):
+ *   t3d_mc_flags    -> ballots_u32[t3d_mc_num_chunks]: bit l of word c set iff sign word 32c+l owns a cut edge or an
+ *                      active cube origin
+ *   (caller) exclusive scan of popcount(ballots) -> chunkbase_u32, n_active
+ *   t3d_mc_words    -> aw_idx_u32[n_active] (flat word index) and aw_cnt_u32[4][n_active] (owned x/y/z cut edges,
+ *                      triangles); n_ambiguous_u64: cubes whose tiling Lewiner's extra tests could change
+ *   (caller) exclusive scan of aw_cnt -> aw_base_u32, totals n_x, n_y, n_z, n_t
+ *   t3d_mc_emit     -> vkeys_u64[n_x+n_y+n_z] (edge key per vertex) and faces_i32 (n_t,3): reference cube order,
+ *                      reversed winding (gradient_direction='descent')
+ *   t3d_mc_vertices -> verts_f32 (V,3) [z,y,x]: skimage's interpolation on the exact float64 field, then un-pad,
+ *                      variable-depth z map and mm scaling (surface_extractor.py:57-65, 82-113). */
+int64_t t3d_mc_num_chunks(int Zs, int Hs, int Ws);
+int t3d_mc_flags(const void* sign_bits, int Zs, int Hs, int Ws, void* ballots_u32, void* stream);
+int t3d_mc_words(const void* sign_bits, int Zs, int Hs, int Ws, const void* ballots_u32, const void* chunkbase_u32,
+                 uint32_t n_active, void* aw_idx_u32, void* aw_cnt_u32, void* n_ambiguous_u64, void* stream);
+int t3d_mc_emit(const void* sign_bits, int Zs, int Hs, int Ws, const void* ballots_u32, const void* chunkbase_u32,
+                const void* aw_idx_u32, const void* aw_base_u32, uint32_t n_active, uint32_t n_x, uint32_t n_y,
+                void* vkeys_u64, void* faces_i32, void* stream);
+int t3d_mc_vertices(const void* occ_bits, int Z, int H, int W, int pad, int gaussian, const double* weights3_host,
+                    const void* vkeys_u64, uint32_t n_x, uint32_t n_y, uint32_t n_z, int unpad_shift, const void* cum_f64,
+                    const void* adj_f64, int n_cum, double mm_per_pixel_y, double mm_per_pixel_x, int scale_in_f64,
+                    void* verts_f32, void* stream);
 
 /* test aids: the float32 field itself and the uint8 cube-case volume */
 int t3d_field_dense(const void* occ_bits, int Z, int H, int W, int pad, int gaussian, const double* weights3_host,

@@ -26,16 +26,20 @@ SIGNATURES = {
     "t3d_fill_holes_scratch_bytes": (_i64, [_i, _i, _i]),
     "t3d_fill_holes_2d": (_i, [_vp, _i, _i64, _i, _i, _vp, _vp]),
     "t3d_gap_fill": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
-    "t3d_morph": (_i, [_vp, _vp, _i, _i, _i, _i, _c.c_uint, _vp, _vp]),
+    "t3d_morph_scratch_bytes": (_i64, [_i, _i, _i, _i]),
+    "t3d_morph": (_i, [_vp, _vp, _i, _i, _i, _i, _c.c_uint, _vp, _vp, _vp]),
     "t3d_volume_stats": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp]),
     "t3d_row_popcounts": (_i, [_vp, _i, _i, _i, _vp, _vp]),
     "t3d_point_cloud_emit": (_i, [_vp, _i, _i, _i, _vp, _i, _vp, _dbl, _dbl, _vp, _vp]),
     "t3d_scan_workspace_bytes": (_i64, [_i64, _i]),
-    "t3d_exclusive_scan_u32": (_i, [_vp, _vp, _i64, _i, _i, _vp, _vp, _vp]),
+    "t3d_exclusive_scan_u32": (_i, [_vp, _vp, _i64, _i, _i, _i, _vp, _vp, _vp]),
     "t3d_field_sign": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
-    "t3d_mc_count": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp]),
-    "t3d_mc_emit": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _u32, _u32, _i, _vp, _vp, _i, _dbl, _dbl, _i,
-                         _vp, _vp, _vp]),
+    "t3d_mc_num_chunks": (_i64, [_i, _i, _i]),
+    "t3d_mc_flags": (_i, [_vp, _i, _i, _i, _vp, _vp]),
+    "t3d_mc_words": (_i, [_vp, _i, _i, _i, _vp, _vp, _u32, _vp, _vp, _vp, _vp]),
+    "t3d_mc_emit": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp, _u32, _u32, _u32, _vp, _vp, _vp]),
+    "t3d_mc_vertices": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _u32, _u32, _u32, _i, _vp, _vp, _i, _dbl, _dbl, _i,
+                             _vp, _vp]),
     "t3d_field_dense": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "t3d_cube_cases": (_i, [_vp, _i, _i, _i, _vp, _vp]),
     "t3d_canonicalize_workspace_bytes": (_i64, [_i64, _i64]),

@@ -1,8 +1,9 @@
 // t3d_common.cuh -- shared helpers for the sm_100a kernels behind include/t3d.h.
 //
 // Volume layout everywhere: C-contiguous (Z, H, W); occupancy is bit-packed along x, LSB first:
-//   word(z, y, w) bit i  <=>  voxel (z, y, x = 32*w + i),   row stride = words_per_row(W) = ceil(W/32).
-// Invariant: bits at x >= W in the last word of every row are zero.
+//   word(z, y, w) bit i  <=>  voxel (z, y, x = 32*w + i),   row stride = words_per_row(W) = ceil(W/32) rounded up
+//   to a multiple of 4 words, so every row starts 16-byte aligned and kernels move uint4 (128 voxels) per thread.
+// Invariant: bits at x >= W (tail of the last word and the padding words) are zero.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -31,7 +32,8 @@ extern "C" void t3d_count_launches(int n);  // bookkeeping for bench.py's gpu_la
         }                                                                                        \
     } while (0)
 
-static inline int t3d_wpr(int W) { return (W + 31) >> 5; }
+static inline int t3d_wpr(int W) { return (((W + 31) >> 5) + 3) & ~3; }
+static inline int t3d_wvalid(int W) { return (W + 31) >> 5; }  // words that hold at least one voxel
 
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }
 
@@ -106,3 +108,22 @@ __device__ __forceinline__ uint32_t ge16(uint4 v, uint32_t thr4)
 }
 // 4 bits -> 4 bytes of 0/1
 __device__ __forceinline__ uint32_t expand4(uint32_t nib) { return (nib * 0x00204081u) & 0x01010101u; }
+
+__device__ __forceinline__ uint4 and4(uint4 a, uint4 b) { return make_uint4(a.x & b.x, a.y & b.y, a.z & b.z, a.w & b.w); }
+__device__ __forceinline__ uint4 or4(uint4 a, uint4 b) { return make_uint4(a.x | b.x, a.y | b.y, a.z | b.z, a.w | b.w); }
+__device__ __forceinline__ uint4 splat4(uint32_t v) { return make_uint4(v, v, v, v); }
+__device__ __forceinline__ uint32_t popc4(uint4 a) { return __popc(a.x) + __popc(a.y) + __popc(a.z) + __popc(a.w); }
+// valid-bit masks of the four words of uint4 column w4 in a row of width W
+__device__ __forceinline__ uint4 valid_mask4(int w4, int W)
+{
+    return make_uint4(valid_mask(4 * w4, W), valid_mask(4 * w4 + 1, W), valid_mask(4 * w4 + 2, W), valid_mask(4 * w4 + 3, W));
+}
+// x-1 / x+1 neighbours of the 128 voxels of a uint4: l = word to the left of .x, r = word to the right of .w
+__device__ __forceinline__ uint4 shl1_4(uint4 c, uint32_t l)
+{
+    return make_uint4(__funnelshift_l(l, c.x, 1), __funnelshift_l(c.x, c.y, 1), __funnelshift_l(c.y, c.z, 1), __funnelshift_l(c.z, c.w, 1));
+}
+__device__ __forceinline__ uint4 shr1_4(uint4 c, uint32_t r)
+{
+    return make_uint4(__funnelshift_r(c.x, c.y, 1), __funnelshift_r(c.y, c.z, 1), __funnelshift_r(c.z, c.w, 1), __funnelshift_r(c.w, r, 1));
+}

@@ -1,0 +1,208 @@
+// t3d_field.cuh -- padded-occupancy view and exact evaluation of the marched field
+// (np.pad -> float64 -> scipy.ndimage.gaussian_filter(sigma=0.5) -> float32; surface_extractor.py:43-53).
+#pragma once
+#include "t3d_common.cuh"
+
+// ------------------------------------------------------------------------------------------------
+// padded-occupancy view + exact field evaluation
+// ------------------------------------------------------------------------------------------------
+struct OccView {
+    const uint32_t* bits;  // (Z, H, nw) packed occupancy
+    int Z, H, W, nw;
+    int pad;               // 0 or 1
+    int Zp, Hp, Wp;        // padded extents
+    int gaussian;          // 1: field = gaussian(sigma 0.5) of padded occupancy; 0: field = occupancy
+    double w0, w1, w2;     // scipy _gaussian_kernel1d(0.5, 0, 2): centre, +-1, +-2
+};
+
+// scipy 'reflect' (d c b a | a b c d | d c b a)
+__device__ __forceinline__ int reflect_idx(int i, int n)
+{
+    if (i >= 0 && i < n) return i;
+    if (n == 1) return 0;
+    const int period = 2 * n;
+    i %= period;
+    if (i < 0) i += period;
+    return i < n ? i : period - 1 - i;
+}
+
+// padded occupancy bit (coordinates already inside [0, Np))
+__device__ __forceinline__ uint32_t pbit(const OccView& v, int zp, int yp, int xp)
+{
+    const int z = zp - v.pad, y = yp - v.pad, x = xp - v.pad;
+    if (z < 0 || z >= v.Z || y < 0 || y >= v.H || x < 0 || x >= v.W) return 0u;
+    return (v.bits[((int64_t)z * v.H + y) * v.nw + (x >> 5)] >> (x & 31)) & 1u;
+}
+
+// bits of padded row (zp, yp) at padded x = xs .. xs+4 (x reflected at the padded border)
+__device__ __forceinline__ uint32_t get5(const OccView& v, int zp, int yp, int xs)
+{
+    const int z = zp - v.pad, y = yp - v.pad;
+    if (z < 0 || z >= v.Z || y < 0 || y >= v.H) return 0u;
+    const uint32_t* row = v.bits + ((int64_t)z * v.H + y) * v.nw;
+    if (xs >= 0 && xs + 4 < v.Wp) {
+        const int ox = xs - v.pad;
+        const int w = ox >> 5, sh = ox & 31;
+        const uint32_t lo = (w >= 0 && w < v.nw) ? row[w] : 0u;
+        const uint32_t hi = (w + 1 >= 0 && w + 1 < v.nw) ? row[w + 1] : 0u;
+        const unsigned long long win = (unsigned long long)lo | ((unsigned long long)hi << 32);
+        return (uint32_t)(win >> sh) & 31u;
+    }
+    uint32_t r = 0;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+        const int ox = reflect_idx(xs + k, v.Wp) - v.pad;
+        if (ox >= 0 && ox < v.W) r |= ((row[ox >> 5] >> (ox & 31)) & 1u) << k;
+    }
+    return r;
+}
+
+// one symmetric 5-tap correlation in scipy's order: c*w0 + (a_-2 + a_+2)*w2 + (a_-1 + a_+1)*w1, no FMA
+__device__ __forceinline__ double corr5(double m2, double m1, double c, double p1, double p2, double w0, double w1, double w2)
+{
+    double t = __dmul_rn(c, w0);
+    t = __dadd_rn(t, __dmul_rn(__dadd_rn(m2, p2), w2));
+    t = __dadd_rn(t, __dmul_rn(__dadd_rn(m1, p1), w1));
+    return t;
+}
+
+// float32(field) at padded voxel (zp, yp, xp): separable float64 passes along z, then y, then x,
+// each with reflect boundary, exactly like scipy.ndimage.gaussian_filter
+__device__ __forceinline__ float field_value(const OccView& v, int zp, int yp, int xp)
+{
+    if (!v.gaussian) return pbit(v, zp, yp, xp) ? 1.0f : 0.0f;
+    uint32_t b[5][5];
+#pragma unroll
+    for (int dz = 0; dz < 5; ++dz) {
+        const int zr = reflect_idx(zp - 2 + dz, v.Zp);
+#pragma unroll
+        for (int dy = 0; dy < 5; ++dy) b[dz][dy] = get5(v, zr, reflect_idx(yp - 2 + dy, v.Hp), xp - 2);
+    }
+    double Y[5];
+#pragma unroll
+    for (int dx = 0; dx < 5; ++dx) {
+        double A[5];
+#pragma unroll
+        for (int dy = 0; dy < 5; ++dy) {
+            const double c = (double)((b[2][dy] >> dx) & 1u);
+            const double n1 = (double)(((b[1][dy] >> dx) & 1u) + ((b[3][dy] >> dx) & 1u));
+            const double n2 = (double)(((b[0][dy] >> dx) & 1u) + ((b[4][dy] >> dx) & 1u));
+            double t = __dmul_rn(c, v.w0);
+            t = __dadd_rn(t, __dmul_rn(n2, v.w2));
+            t = __dadd_rn(t, __dmul_rn(n1, v.w1));
+            A[dy] = t;
+        }
+        Y[dx] = corr5(A[0], A[1], A[2], A[3], A[4], v.w0, v.w1, v.w2);
+    }
+    return __double2float_rn(corr5(Y[0], Y[1], Y[2], Y[3], Y[4], v.w0, v.w1, v.w2));
+}
+
+// padded occupancy word (zp, yp, wp) in padded x coordinates (no reflection; outside = 0)
+__device__ __forceinline__ uint32_t pword(const OccView& v, int zp, int yp, int wp)
+{
+    const int z = zp - v.pad, y = yp - v.pad;
+    if (z < 0 || z >= v.Z || y < 0 || y >= v.H || wp < 0) return 0u;
+    const uint32_t* row = v.bits + ((int64_t)z * v.H + y) * v.nw;
+    const uint32_t cur = (wp < v.nw) ? row[wp] : 0u;
+    if (!v.pad) return cur;
+    const uint32_t prev = (wp - 1 >= 0 && wp - 1 < v.nw) ? row[wp - 1] : 0u;
+    return (cur << 1) | (prev >> 31);
+}
+
+
+// bits of padded row (zp, yp) at padded x = xs .. xs+5 (x reflected at the padded border)
+__device__ __forceinline__ uint32_t get6(const OccView& v, int zp, int yp, int xs)
+{
+    const int z = zp - v.pad, y = yp - v.pad;
+    if (z < 0 || z >= v.Z || y < 0 || y >= v.H) return 0u;
+    const uint32_t* row = v.bits + ((int64_t)z * v.H + y) * v.nw;
+    if (xs >= 0 && xs + 5 < v.Wp) {
+        const int ox = xs - v.pad;
+        const int w = ox >> 5, sh = ox & 31;
+        const uint32_t lo = (w >= 0 && w < v.nw) ? row[w] : 0u;
+        const uint32_t hi = (sh > 26 && w + 1 >= 0 && w + 1 < v.nw) ? row[w + 1] : 0u;
+        const unsigned long long win = (unsigned long long)lo | ((unsigned long long)hi << 32);
+        return (uint32_t)(win >> sh) & 63u;
+    }
+    uint32_t r = 0;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+        const int ox = reflect_idx(xs + k, v.Wp) - v.pad;
+        if (ox >= 0 && ox < v.W) r |= ((row[ox >> 5] >> (ox & 31)) & 1u) << k;
+    }
+    return r;
+}
+
+// z-pass lookup: the first (z) pass of the separable filter sees only 0/1 samples, so its result is one of 18
+// values indexed by (centre c, n2 = a[-2]+a[+2], n1 = a[-1]+a[+1]):  c*w0 + n2*w2 + n1*w1 in scipy's order.
+__device__ __forceinline__ void fill_zlut(const OccView& v, double* zlut)  // zlut[18], one entry per calling thread
+{
+    const int i = threadIdx.x;
+    if (i < 18) {
+        const int c = i / 9, n2 = (i / 3) % 3, n1 = i % 3;
+        double t = __dmul_rn((double)c, v.w0);
+        t = __dadd_rn(t, __dmul_rn((double)n2, v.w2));
+        t = __dadd_rn(t, __dmul_rn((double)n1, v.w1));
+        zlut[i] = t;
+    }
+}
+
+// float32 field at both end points of the grid edge (z,y,x) -> +1 along AXIS (0 = z, 1 = y, 2 = x), sharing one
+// neighbourhood fetch: NY rows of (NZ planes x 6 x-bits) packed into one 64-bit word each.  Same arithmetic as
+// field_value() (the z pass comes from zlut, see fill_zlut).
+template <int AXIS>
+__device__ __forceinline__ void edge_field_values(const OccView& v, const double* __restrict__ zlut, int z, int y, int x,
+                                                  float& fa, float& fb)
+{
+    if (!v.gaussian) {
+        fa = pbit(v, z, y, x) ? 1.0f : 0.0f;
+        fb = pbit(v, z + (AXIS == 0), y + (AXIS == 1), x + (AXIS == 2)) ? 1.0f : 0.0f;
+        return;
+    }
+    constexpr int NZ = 5 + (AXIS == 0), NY = 5 + (AXIS == 1);
+    unsigned long long col[NY];
+#pragma unroll
+    for (int dy = 0; dy < NY; ++dy) {
+        const int yr = reflect_idx(y - 2 + dy, v.Hp);
+        unsigned long long c = 0;
+#pragma unroll
+        for (int dz = 0; dz < NZ; ++dz)
+            c |= (unsigned long long)get6(v, reflect_idx(z - 2 + dz, v.Zp), yr, x - 2) << (6 * dz);
+        col[dy] = c;
+    }
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+        const int oz = e * (AXIS == 0), oy = e * (AXIS == 1), ox = e * (AXIS == 2);
+        double Y[5];
+#pragma unroll
+        for (int dx = 0; dx < 5; ++dx) {
+            double A[5];
+#pragma unroll
+            for (int dy = 0; dy < 5; ++dy) {
+                const uint32_t q = (uint32_t)(col[oy + dy] >> (6 * oz + ox + dx));  // bit 6k = plane k of this column
+                const uint32_t c = (q >> 12) & 1u;
+                const uint32_t n1 = ((q >> 6) & 1u) + ((q >> 18) & 1u);
+                const uint32_t n2 = (q & 1u) + ((q >> 24) & 1u);
+                A[dy] = zlut[c * 9 + n2 * 3 + n1];
+            }
+            Y[dx] = corr5(A[0], A[1], A[2], A[3], A[4], v.w0, v.w1, v.w2);
+        }
+        const float f = __double2float_rn(corr5(Y[0], Y[1], Y[2], Y[3], Y[4], v.w0, v.w1, v.w2));
+        if (e == 0) fa = f; else fb = f;
+    }
+}
+
+static inline OccView t3d_make_view(const void* occ_bits, int Z, int H, int W, int pad, int gaussian, const double* w3)
+{
+    OccView v;
+    v.bits = (const uint32_t*)occ_bits;
+    v.Z = Z; v.H = H; v.W = W; v.nw = t3d_wpr(W);
+    v.pad = pad ? 1 : 0;
+    v.Zp = Z + 2 * v.pad; v.Hp = H + 2 * v.pad; v.Wp = W + 2 * v.pad;
+    v.gaussian = gaussian ? 1 : 0;
+    // scipy.ndimage._filters._gaussian_kernel1d(0.5, 0, 2)
+    v.w0 = w3 ? w3[0] : 0x1.92b965ef5aaeep-1;
+    v.w1 = w3 ? w3[1] : 0x1.b405b9842b206p-4;
+    v.w2 = w3 ? w3[2] : 0x1.14aebe6a24088p-12;
+    return v;
+}

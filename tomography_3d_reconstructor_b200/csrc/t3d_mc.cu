@@ -1,0 +1,506 @@
+// t3d_mc.cu -- two-pass marching cubes on the packed sign volume (sm_100a).
+//
+// Replaces skimage.measure.marching_cubes(volume, level=0.5) as called at surface_extractor.py:55, plus the vertex
+// post-transform of surface_extractor.py:57-65 / 82-113.  See SURVEY.md 8a-7, 8a-8.
+//
+// Work is proportional to the SURFACE, not the volume, after one cheap dense pass:
+//   1. t3d_mc_flags    dense, one thread per 32-voxel word of the sign volume: does this word own a cut edge or the
+//                      origin of an active cube?  -> one ballot word per warp (1 bit per word).
+//   2. exclusive scan  of the ballot popcounts  -> rank of every active word (order-preserving compaction).
+//   3. t3d_mc_words    active words only: packed counts of owned x/y/z cut edges and triangles -> compact arrays.
+//   4. exclusive scan  of those counts -> vertex / triangle bases per active word.
+//   5. t3d_mc_emit     one thread per active word: edge keys of the owned vertices, faces of its cubes
+//                      (ids of vertices owned by neighbouring words through ballot-rank lookups).
+//   6. t3d_mc_vertices one thread per vertex: exact float64 field at the two end points, skimage's interpolation,
+//                      un-pad, variable-depth z map, mm scaling.
+// Vertex ids: [x-edge vertices | y-edge | z-edge], each in raster order of the owning voxel (edge owned by its lower
+// corner).  Faces come out in the reference's order: cubes z-major, y, x fastest, table order inside a cube,
+// winding reversed (gradient_direction='descent').
+#include "mc_tables.h"
+#include "t3d_field.cuh"
+
+// ------------------------------------------------------------------------------------------------
+// tables
+// ------------------------------------------------------------------------------------------------
+__device__ __align__(16) const int8_t g_tri_table[256][T3D_MC_ROW] = {T3D_TRI_TABLE_ROWS};
+static const int8_t h_tri_table[256][T3D_MC_ROW] = {T3D_TRI_TABLE_ROWS};
+
+struct McLuts {
+    uint8_t ntri[256];
+    uint8_t amb[256];
+};
+__constant__ McLuts c_luts;
+static bool g_luts_ready = false;
+
+static int host_is_ambiguous(int idx)
+{
+    static const int FC[6][4] = {{0, 1, 2, 3}, {4, 5, 6, 7}, {0, 1, 5, 4}, {3, 2, 6, 7}, {0, 3, 7, 4}, {1, 2, 6, 5}};
+    for (int f = 0; f < 6; ++f) {
+        const int a = (idx >> FC[f][0]) & 1, b = (idx >> FC[f][1]) & 1, c = (idx >> FC[f][2]) & 1, d = (idx >> FC[f][3]) & 1;
+        if (a == c && b == d && a != b) return 1;
+    }
+    static const int DG[4][2] = {{0, 6}, {1, 7}, {2, 4}, {3, 5}};
+    for (int k = 0; k < 4; ++k) {
+        const int m = (1 << DG[k][0]) | (1 << DG[k][1]);
+        if (idx == m || idx == (255 ^ m)) return 1;
+    }
+    return 0;
+}
+
+static int ensure_luts()
+{
+    if (g_luts_ready) return 0;
+    McLuts l;
+    for (int i = 0; i < 256; ++i) {
+        int n = 0;
+        while (n < T3D_MC_ROW && h_tri_table[i][n] >= 0) n += 3;
+        l.ntri[i] = (uint8_t)(n / 3);
+        l.amb[i] = (uint8_t)host_is_ambiguous(i);
+    }
+    T3D_CUDA(cudaMemcpyToSymbol(c_luts, &l, sizeof(l)));
+    g_luts_ready = true;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-word bit arithmetic
+// ------------------------------------------------------------------------------------------------
+struct Grid {
+    const uint32_t* sign;
+    int Zs, Hs, Ws, nws;
+    int ncr;            // 32-word chunks per row = ceil(nws/32); one ballot word per (row, chunk)
+    uint32_t n_rows;    // Zs*Hs
+    int64_t n_words;    // n_rows*nws (flat word index i = row*nws + w)
+};
+
+struct WordMasks {
+    uint32_t s00, s01, s10, s11;  // rows (z,y) (z,y+1) (z+1,y) (z+1,y+1), word w
+    uint32_t a00, a01, a10, a11;  // the same rows shifted: value at x+1
+    uint32_t X00, X01, X10, X11;  // cut x-edges owned by each row's word
+    uint32_t Y0, Y1;              // cut y-edges owned by rows (z,y), (z+1,y)
+    uint32_t Z0, Z1;              // cut z-edges owned by rows (z,y), (z,y+1)
+    uint32_t act;                 // origins of active cubes
+};
+
+__device__ __forceinline__ uint32_t shr1(uint32_t s, uint32_t nbit) { return (s >> 1) | (nbit << 31); }
+
+// s*: words of the four rows, n*: bit 0 of the next word of each row
+__device__ __forceinline__ WordMasks make_masks(uint32_t s00, uint32_t s01, uint32_t s10, uint32_t s11, uint32_t n00,
+                                                uint32_t n01, uint32_t n10, uint32_t n11, bool hy, bool hz, int w, int Ws)
+{
+    WordMasks m;
+    const uint32_t vm = valid_mask(w, Ws), em = valid_mask(w, Ws - 1);  // em: x+1 still inside the grid
+    m.s00 = s00; m.s01 = s01; m.s10 = s10; m.s11 = s11;
+    m.a00 = shr1(s00, n00); m.a01 = shr1(s01, n01); m.a10 = shr1(s10, n10); m.a11 = shr1(s11, n11);
+    m.X00 = (s00 ^ m.a00) & em;
+    m.X01 = hy ? (s01 ^ m.a01) & em : 0u;
+    m.X10 = hz ? (s10 ^ m.a10) & em : 0u;
+    m.X11 = (hy && hz) ? (s11 ^ m.a11) & em : 0u;
+    m.Y0 = hy ? (s00 ^ s01) & vm : 0u;
+    m.Y1 = (hy && hz) ? (s10 ^ s11) & vm : 0u;
+    m.Z0 = hz ? (s00 ^ s10) & vm : 0u;
+    m.Z1 = (hy && hz) ? (s01 ^ s11) & vm : 0u;
+    m.act = 0u;
+    if (hy && hz) {
+        const uint32_t o = s00 | s01 | s10 | s11, a = s00 & s01 & s10 & s11;
+        const uint32_t oa = m.a00 | m.a01 | m.a10 | m.a11, aa = m.a00 & m.a01 & m.a10 & m.a11;
+        m.act = ((o | oa) & ~(a & aa)) & em;
+    }
+    return m;
+}
+
+__device__ __forceinline__ int cube_case(const WordMasks& m, int b)
+{
+    return (int)(((m.s00 >> b) & 1u) | (((m.a00 >> b) & 1u) << 1) | (((m.a01 >> b) & 1u) << 2) | (((m.s01 >> b) & 1u) << 3) |
+                 (((m.s10 >> b) & 1u) << 4) | (((m.a10 >> b) & 1u) << 5) | (((m.a11 >> b) & 1u) << 6) | (((m.s11 >> b) & 1u) << 7));
+}
+
+// masks of word w of voxel row `row`, loading everything from memory (sparse kernels)
+__device__ __forceinline__ WordMasks load_masks(const Grid& g, uint32_t row, int w, int& z, int& y)
+{
+    z = (int)(row / (uint32_t)g.Hs);
+    y = (int)(row - (uint32_t)z * (uint32_t)g.Hs);
+    const bool hy = (y + 1 < g.Hs), hz = (z + 1 < g.Zs), hx = (w + 1 < g.nws);
+    const uint32_t* p = g.sign + (int64_t)row * g.nws + w;
+    const int64_t dy = g.nws, dz = (int64_t)g.Hs * g.nws;
+    const uint32_t s00 = p[0], s01 = hy ? p[dy] : 0u, s10 = hz ? p[dz] : 0u, s11 = (hy && hz) ? p[dz + dy] : 0u;
+    uint32_t n00 = 0, n01 = 0, n10 = 0, n11 = 0;
+    if (hx) {
+        n00 = p[1] & 1u;
+        if (hy) n01 = p[dy + 1] & 1u;
+        if (hz) n10 = p[dz + 1] & 1u;
+        if (hy && hz) n11 = p[dz + dy + 1] & 1u;
+    }
+    return make_masks(s00, s01, s10, s11, n00, n01, n10, n11, hy, hz, w, g.Ws);
+}
+
+// ------------------------------------------------------------------------------------------------
+// 1. dense flags: a warp walks FR consecutive voxel rows, lane = word; one ballot per (row, 32-word chunk)
+// ------------------------------------------------------------------------------------------------
+#define FR 4
+
+__global__ void __launch_bounds__(256) k_mc_flags(Grid g, uint32_t* __restrict__ ballots)
+{
+    const uint32_t l = lane_id();
+    const uint32_t r0 = (blockIdx.x * 8u + (threadIdx.x >> 5)) * FR;
+    const int64_t dy = g.nws, dz = (int64_t)g.Hs * g.nws;
+    for (uint32_t row = r0; row < r0 + FR && row < g.n_rows; ++row) {
+        const int z = (int)(row / (uint32_t)g.Hs), y = (int)(row - (uint32_t)z * (uint32_t)g.Hs);
+        const bool hy = (y + 1 < g.Hs), hz = (z + 1 < g.Zs);
+        const uint32_t* p0 = g.sign + (int64_t)row * g.nws;
+        for (int c = 0; c < g.ncr; ++c) {
+            const int w = (c << 5) + l;
+            const bool in = w < g.nws;
+            const bool hx = (w + 1 < g.nws);
+            uint32_t s00 = 0, s01 = 0, s10 = 0, s11 = 0;
+            if (in) {
+                const uint32_t* p = p0 + w;
+                s00 = p[0];
+                if (hy) s01 = p[dy];
+                if (hz) s10 = p[dz];
+                if (hy && hz) s11 = p[dz + dy];
+            }
+            // bit 0 of the next word: from the next lane, lane 31 loads it
+            uint32_t n00 = __shfl_down_sync(0xffffffffu, s00, 1) & 1u, n01 = __shfl_down_sync(0xffffffffu, s01, 1) & 1u;
+            uint32_t n10 = __shfl_down_sync(0xffffffffu, s10, 1) & 1u, n11 = __shfl_down_sync(0xffffffffu, s11, 1) & 1u;
+            if (!hx) { n00 = n01 = n10 = n11 = 0u; }
+            else if (l == 31) {
+                const uint32_t* p = p0 + w + 1;
+                n00 = p[0] & 1u;
+                n01 = hy ? p[dy] & 1u : 0u;
+                n10 = hz ? p[dz] & 1u : 0u;
+                n11 = (hy && hz) ? p[dz + dy] & 1u : 0u;
+            }
+            bool active = false;
+            if (in) {
+                const WordMasks m = make_masks(s00, s01, s10, s11, n00, n01, n10, n11, hy, hz, w, g.Ws);
+                active = (m.X00 | m.Y0 | m.Z0 | m.act) != 0u;
+            }
+            const uint32_t bal = __ballot_sync(0xffffffffu, active);
+            if (l == 0) ballots[(int64_t)row * g.ncr + c] = bal;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// 3. counts of the active words (warp per ballot word; inactive chunks leave after one load)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_mc_words(Grid g, const uint32_t* __restrict__ ballots,
+                                                  const uint32_t* __restrict__ chunkbase, int64_t n_chunks, uint32_t n_active,
+                                                  uint32_t* __restrict__ aw_idx, uint32_t* __restrict__ aw_cnt,
+                                                  unsigned long long* __restrict__ n_ambiguous)
+{
+    const int64_t c = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (c >= n_chunks) return;
+    const uint32_t bal = ballots[c];
+    if (!bal) return;
+    const uint32_t l = lane_id();
+    if (!((bal >> l) & 1u)) return;
+    const uint32_t k = chunkbase[c] + __popc(bal & ((1u << l) - 1u));
+    const uint32_t row = (uint32_t)(c / g.ncr);
+    const int w = (int)((c - (int64_t)row * g.ncr) << 5) + (int)l;
+    int z, y;
+    const WordMasks m = load_masks(g, row, w, z, y);
+    uint32_t nt = 0, na = 0;
+    for (uint32_t a = m.act; a;) {
+        const int b = __ffs(a) - 1;
+        a &= a - 1;
+        const int cs = cube_case(m, b);
+        nt += c_luts.ntri[cs];
+        na += c_luts.amb[cs];
+    }
+    aw_idx[k] = row * (uint32_t)g.nws + (uint32_t)w;
+    aw_cnt[k] = __popc(m.X00);
+    aw_cnt[(int64_t)n_active + k] = __popc(m.Y0);
+    aw_cnt[2 * (int64_t)n_active + k] = __popc(m.Z0);
+    aw_cnt[3 * (int64_t)n_active + k] = nt;
+    if (na) atomicAdd(n_ambiguous, (unsigned long long)na);
+}
+
+// ------------------------------------------------------------------------------------------------
+// 5. emit: one thread per active word
+// ------------------------------------------------------------------------------------------------
+struct EmitArgs {
+    Grid g;
+    const uint32_t* ballots;
+    const uint32_t* chunkbase;
+    const uint32_t* aw_idx;
+    const uint32_t* aw_base;  // 4 arrays of n_active: X, Y, Z, T (exclusive scans)
+    uint32_t n_active;
+    uint32_t offY, offZ;      // offX = 0
+    unsigned long long* vkeys;  // per vertex: axis | x << 2 | y << 22 | z << 42
+    int32_t* faces;
+};
+
+// rank of word w of row `row` among the active words (the word must be active)
+__device__ __forceinline__ uint32_t active_rank(const EmitArgs& a, uint32_t row, int w)
+{
+    const int64_t c = (int64_t)row * a.g.ncr + (w >> 5);
+    return a.chunkbase[c] + __popc(a.ballots[c] & ((1u << (w & 31)) - 1u));
+}
+
+__device__ __forceinline__ uint32_t lt_mask(int b) { return b >= 32 ? 0xffffffffu : ((1u << b) - 1u); }
+
+__device__ __forceinline__ unsigned long long vkey(int axis, int z, int y, int x)
+{
+    return (unsigned long long)axis | ((unsigned long long)x << 2) | ((unsigned long long)y << 22) | ((unsigned long long)z << 42);
+}
+
+__global__ void __launch_bounds__(128) k_mc_emit(EmitArgs a)
+{
+    __shared__ __align__(16) int8_t s_tri[256][T3D_MC_ROW];
+    {
+        const int4* src = reinterpret_cast<const int4*>(&g_tri_table[0][0]);
+        int4* dst = reinterpret_cast<int4*>(&s_tri[0][0]);
+        for (int i = threadIdx.x; i < 256; i += blockDim.x) dst[i] = src[i];
+    }
+    __syncthreads();
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= a.n_active) return;
+    const uint32_t i = a.aw_idx[k];
+    const uint32_t row = i / (uint32_t)a.g.nws;
+    const int w = (int)(i - row * (uint32_t)a.g.nws);
+    int z, y;
+    const WordMasks m = load_masks(a.g, row, w, z, y);
+    const int64_t NA = a.n_active;
+    const uint32_t bX00 = a.aw_base[k], bY0 = a.offY + a.aw_base[NA + k], bZ0 = a.offZ + a.aw_base[2 * NA + k];
+    uint32_t pT = a.aw_base[3 * NA + k];
+    const int x0 = w << 5;
+
+    // ---- keys of the vertices this word owns
+    {
+        uint32_t id = bX00;
+        for (uint32_t q = m.X00; q;) { const int b = __ffs(q) - 1; q &= q - 1; a.vkeys[id++] = vkey(2, z, y, x0 + b); }
+        id = bY0;
+        for (uint32_t q = m.Y0; q;) { const int b = __ffs(q) - 1; q &= q - 1; a.vkeys[id++] = vkey(1, z, y, x0 + b); }
+        id = bZ0;
+        for (uint32_t q = m.Z0; q;) { const int b = __ffs(q) - 1; q &= q - 1; a.vkeys[id++] = vkey(0, z, y, x0 + b); }
+    }
+    if (!m.act) return;
+
+    // ---- bases of the neighbouring words whose vertices our cubes use (looked up only when they own any)
+    const uint32_t Hs = (uint32_t)a.g.Hs;
+    uint32_t bX01 = 0, bX10 = 0, bX11 = 0, bY1 = 0, bZ1 = 0;
+    if (m.X01 | m.Z1) {
+        const uint32_t r = active_rank(a, row + 1, w);
+        bX01 = a.aw_base[r];
+        bZ1 = a.offZ + a.aw_base[2 * NA + r];
+    }
+    if (m.X10 | m.Y1) {
+        const uint32_t r = active_rank(a, row + Hs, w);
+        bX10 = a.aw_base[r];
+        bY1 = a.offY + a.aw_base[NA + r];
+    }
+    if (m.X11) bX11 = a.aw_base[active_rank(a, row + Hs + 1, w)];
+    // y/z edges at x0+32 (bit 0 of the next word) are only used by the cube at bit 31
+    uint32_t nY0 = 0, nY1 = 0, nZ0 = 0, nZ1 = 0;
+    if ((m.act >> 31) & 1u) {
+        // cut y/z edges at x+1 for b = 31: corners a00.. are the next word's bit 0
+        const uint32_t v1 = (m.a00 >> 31) & 1u, v2 = (m.a01 >> 31) & 1u, v5 = (m.a10 >> 31) & 1u, v6 = (m.a11 >> 31) & 1u;
+        if (v1 != v2) nY0 = a.offY + a.aw_base[NA + active_rank(a, row, w + 1)];            // edge 1
+        if (v5 != v6) nY1 = a.offY + a.aw_base[NA + active_rank(a, row + Hs, w + 1)];       // edge 5
+        if (v1 != v5) nZ0 = a.offZ + a.aw_base[2 * NA + active_rank(a, row, w + 1)];        // edge 9
+        if (v2 != v6) nZ1 = a.offZ + a.aw_base[2 * NA + active_rank(a, row + 1, w + 1)];   // edge 10
+    }
+
+    for (uint32_t q = m.act; q;) {
+        const int b = __ffs(q) - 1;
+        q &= q - 1;
+        const int cs = cube_case(m, b);
+        const uint32_t lb = lt_mask(b), lb1 = lt_mask(b + 1);
+        const bool last = (b == 31);
+        const int8_t* rowt = s_tri[cs];
+        for (int t = 0; t < T3D_MC_ROW && rowt[t] >= 0; t += 3) {
+            uint32_t vid[3];
+#pragma unroll
+            for (int e = 0; e < 3; ++e) {
+                uint32_t id;
+                switch (rowt[t + e]) {
+                    case 0: id = bX00 + __popc(m.X00 & lb); break;
+                    case 1: id = last ? nY0 : bY0 + __popc(m.Y0 & lb1); break;
+                    case 2: id = bX01 + __popc(m.X01 & lb); break;
+                    case 3: id = bY0 + __popc(m.Y0 & lb); break;
+                    case 4: id = bX10 + __popc(m.X10 & lb); break;
+                    case 5: id = last ? nY1 : bY1 + __popc(m.Y1 & lb1); break;
+                    case 6: id = bX11 + __popc(m.X11 & lb); break;
+                    case 7: id = bY1 + __popc(m.Y1 & lb); break;
+                    case 8: id = bZ0 + __popc(m.Z0 & lb); break;
+                    case 9: id = last ? nZ0 : bZ0 + __popc(m.Z0 & lb1); break;
+                    case 10: id = last ? nZ1 : bZ1 + __popc(m.Z1 & lb1); break;
+                    default: id = bZ1 + __popc(m.Z1 & lb); break;  // 11
+                }
+                vid[e] = id;
+            }
+            int32_t* f = a.faces + 3 * (int64_t)pT;
+            f[0] = (int32_t)vid[2]; f[1] = (int32_t)vid[1]; f[2] = (int32_t)vid[0];
+            ++pT;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// 6. vertices: one thread per vertex of one axis block
+// ------------------------------------------------------------------------------------------------
+struct VertexArgs {
+    OccView occ;
+    const unsigned long long* vkeys;
+    uint32_t first, count;    // id range of this axis block
+    float shift;              // 1 if manifold else 0 (surface_extractor.py:57-60)
+    const double* cum;        // cumulative adjusted depths, n_cum entries (n_cum = 0: no z map)
+    const double* adj;        // adjusted depths, n_cum-1 entries
+    int n_cum;
+    double mm_y, mm_x;
+    int scale_f64;            // numpy float64 scalar operand: multiply in float64, then round
+    float* verts;             // (V, 3) z, y, x
+};
+
+template <int AXIS>
+__global__ void __launch_bounds__(128) k_mc_vertices(VertexArgs p)
+{
+    __shared__ double zlut[18];
+    fill_zlut(p.occ, zlut);
+    __syncthreads();
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= p.count) return;
+    const uint32_t id = p.first + t;
+    const unsigned long long key = p.vkeys[id];
+    const int x = (int)((key >> 2) & 0xfffffu), y = (int)((key >> 22) & 0xfffffu), z = (int)(key >> 42);
+    float fa, fb;
+    edge_field_values<AXIS>(p.occ, zlut, z, y, x, fa, fb);
+    // skimage: strength = 1/(FLT_EPSILON + |v - level|), centre of mass of the two corners, all in double
+    const double va = (double)fa - 0.5, vb = (double)fb - 0.5;
+    const double wa = __ddiv_rn(1.0, __dadd_rn(1.1920928955078125e-07, fabs(va)));
+    const double wb = __ddiv_rn(1.0, __dadd_rn(1.1920928955078125e-07, fabs(vb)));
+    const double frac = __ddiv_rn(wb, __dadd_rn(wa, wb));
+    double pz = (double)z, py = (double)y, px = (double)x;
+    if (AXIS == 0) pz = __dadd_rn(pz, frac); else if (AXIS == 1) py = __dadd_rn(py, frac); else px = __dadd_rn(px, frac);
+    float fz = __fsub_rn(__double2float_rn(pz), p.shift);
+    float fy = __fsub_rn(__double2float_rn(py), p.shift);
+    float fx = __fsub_rn(__double2float_rn(px), p.shift);
+    if (p.n_cum > 0) {
+        // surface_extractor.py:98-113, closed form verified bit-exact in SURVEY.md V8
+        if (fz < 0.0f) fz = 0.0f;
+        else if (fz >= (float)(p.n_cum - 1)) fz = __double2float_rn(p.cum[p.n_cum - 1]);
+        else {
+            const float fl = floorf(fz);
+            const int lo = (int)fl;
+            const float fr = __fsub_rn(fz, fl);
+            const int ai = min(lo, p.n_cum - 2);
+            fz = __double2float_rn(__dadd_rn(p.cum[lo], __dmul_rn((double)fr, p.adj[ai])));
+        }
+    }
+    if (p.scale_f64) {
+        fy = __double2float_rn(__dmul_rn((double)fy, p.mm_y));
+        fx = __double2float_rn(__dmul_rn((double)fx, p.mm_x));
+    } else {
+        fy = __fmul_rn(fy, __double2float_rn(p.mm_y));
+        fx = __fmul_rn(fx, __double2float_rn(p.mm_x));
+    }
+    float* o = p.verts + 3 * (int64_t)id;
+    o[0] = fz; o[1] = fy; o[2] = fx;
+}
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+static int make_grid(Grid& g, const void* sign_bits, int Zs, int Hs, int Ws, const char* who)
+{
+    if (Zs <= 0 || Hs <= 0 || Ws <= 0) { t3d_set_error("%s: empty volume", who); return 2; }
+    g.sign = (const uint32_t*)sign_bits;
+    g.Zs = Zs; g.Hs = Hs; g.Ws = Ws; g.nws = t3d_wpr(Ws);
+    g.ncr = (g.nws + 31) >> 5;
+    g.n_rows = (uint32_t)((int64_t)Zs * Hs);
+    g.n_words = (int64_t)Zs * Hs * g.nws;
+    if (g.n_words >= ((int64_t)1 << 32)) { t3d_set_error("%s: more than 2^32 words in one device slab", who); return 2; }
+    return 0;
+}
+
+extern "C" int64_t t3d_mc_num_chunks(int Zs, int Hs, int Ws) { return (int64_t)Zs * Hs * ((t3d_wpr(Ws) + 31) >> 5); }
+
+// ballots_u32: t3d_mc_num_chunks words, one per (voxel row, 32-word chunk): bit l = word 32*chunk+l of that row is active
+extern "C" int t3d_mc_flags(const void* sign_bits, int Zs, int Hs, int Ws, void* ballots_u32, void* stream)
+{
+    Grid g;
+    if (int rc = make_grid(g, sign_bits, Zs, Hs, Ws, "t3d_mc_flags")) return rc;
+    const int64_t n_warps = ((int64_t)g.n_rows + FR - 1) / FR;
+    k_mc_flags<<<(unsigned)((n_warps + 7) / 8), 256, 0, (cudaStream_t)stream>>>(g, (uint32_t*)ballots_u32);
+    T3D_CHECK_LAUNCH("t3d_mc_flags");
+    t3d_count_launches(1);
+    return 0;
+}
+
+// chunkbase_u32: exclusive scan of popcount(ballots); aw_idx_u32: n_active; aw_cnt_u32: 4 arrays of n_active
+extern "C" int t3d_mc_words(const void* sign_bits, int Zs, int Hs, int Ws, const void* ballots_u32, const void* chunkbase_u32,
+                            uint32_t n_active, void* aw_idx_u32, void* aw_cnt_u32, void* n_ambiguous_u64, void* stream)
+{
+    Grid g;
+    if (int rc = make_grid(g, sign_bits, Zs, Hs, Ws, "t3d_mc_words")) return rc;
+    if (ensure_luts()) return 1;
+    cudaStream_t st = (cudaStream_t)stream;
+    T3D_CUDA(cudaMemsetAsync(n_ambiguous_u64, 0, 8, st));
+    if (n_active == 0) return 0;
+    const int64_t n_chunks = (int64_t)g.n_rows * g.ncr;
+    k_mc_words<<<(unsigned)((n_chunks * 32 + 255) / 256), 256, 0, st>>>(g, (const uint32_t*)ballots_u32,
+                                                                        (const uint32_t*)chunkbase_u32, n_chunks, n_active,
+                                                                        (uint32_t*)aw_idx_u32, (uint32_t*)aw_cnt_u32,
+                                                                        (unsigned long long*)n_ambiguous_u64);
+    T3D_CHECK_LAUNCH("t3d_mc_words");
+    t3d_count_launches(1);
+    return 0;
+}
+
+// aw_base_u32: exclusive scans of aw_cnt; n_x / n_y: totals of the x- and y-edge counts.
+// vkeys_u64: one key per vertex (n_x + n_y + n_z); faces_i32: (n_t, 3).
+extern "C" int t3d_mc_emit(const void* sign_bits, int Zs, int Hs, int Ws, const void* ballots_u32, const void* chunkbase_u32,
+                           const void* aw_idx_u32, const void* aw_base_u32, uint32_t n_active, uint32_t n_x, uint32_t n_y,
+                           void* vkeys_u64, void* faces_i32, void* stream)
+{
+    EmitArgs a;
+    if (int rc = make_grid(a.g, sign_bits, Zs, Hs, Ws, "t3d_mc_emit")) return rc;
+    if (ensure_luts()) return 1;
+    if (n_active == 0) return 0;
+    a.ballots = (const uint32_t*)ballots_u32;
+    a.chunkbase = (const uint32_t*)chunkbase_u32;
+    a.aw_idx = (const uint32_t*)aw_idx_u32;
+    a.aw_base = (const uint32_t*)aw_base_u32;
+    a.n_active = n_active;
+    a.offY = n_x;
+    a.offZ = n_x + n_y;
+    a.vkeys = (unsigned long long*)vkeys_u64;
+    a.faces = (int32_t*)faces_i32;
+    k_mc_emit<<<(n_active + 127) / 128, 128, 0, (cudaStream_t)stream>>>(a);
+    T3D_CHECK_LAUNCH("t3d_mc_emit");
+    t3d_count_launches(1);
+    return 0;
+}
+
+// vertices from their keys.  occ_*: the occupancy the sign volume was derived from (pad / gaussian as in
+// t3d_field_sign; gaussian = 0: the sign volume IS the occupancy and pad must be 0).
+// cum/adj: device float64 arrays of the variable-slice-depth z map (n_cum = 0 disables it).
+extern "C" int t3d_mc_vertices(const void* occ_bits, int Z, int H, int W, int pad, int gaussian, const double* weights3_host,
+                               const void* vkeys_u64, uint32_t n_x, uint32_t n_y, uint32_t n_z, int unpad_shift,
+                               const void* cum_f64, const void* adj_f64, int n_cum, double mm_per_pixel_y,
+                               double mm_per_pixel_x, int scale_in_f64, void* verts_f32, void* stream)
+{
+    if (Z <= 0 || H <= 0 || W <= 0) { t3d_set_error("t3d_mc_vertices: empty volume"); return 2; }
+    if (!gaussian && pad) { t3d_set_error("t3d_mc_vertices: pad requires gaussian"); return 2; }
+    cudaStream_t st = (cudaStream_t)stream;
+    VertexArgs p;
+    p.occ = t3d_make_view(occ_bits, Z, H, W, pad, gaussian, weights3_host);
+    p.vkeys = (const unsigned long long*)vkeys_u64;
+    p.shift = unpad_shift ? 1.0f : 0.0f;
+    p.cum = (const double*)cum_f64;
+    p.adj = (const double*)adj_f64;
+    p.n_cum = n_cum;
+    p.mm_y = mm_per_pixel_y;
+    p.mm_x = mm_per_pixel_x;
+    p.scale_f64 = scale_in_f64 ? 1 : 0;
+    p.verts = (float*)verts_f32;
+    int launches = 0;
+    if (n_x) { p.first = 0; p.count = n_x; k_mc_vertices<2><<<(n_x + 127) / 128, 128, 0, st>>>(p); ++launches; }
+    if (n_y) { p.first = n_x; p.count = n_y; k_mc_vertices<1><<<(n_y + 127) / 128, 128, 0, st>>>(p); ++launches; }
+    if (n_z) { p.first = n_x + n_y; p.count = n_z; k_mc_vertices<0><<<(n_z + 127) / 128, 128, 0, st>>>(p); ++launches; }
+    T3D_CHECK_LAUNCH("t3d_mc_vertices");
+    t3d_count_launches(launches);
+    return 0;
+}

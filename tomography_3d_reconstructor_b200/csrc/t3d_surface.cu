@@ -17,271 +17,94 @@
 // exact summation order is spent only on the two end points of each cut edge (vertex interpolation).
 #include <cub/device/device_radix_sort.cuh>
 
-#include "mc_tables.h"
-#include "t3d_common.cuh"
+#include "t3d_field.cuh"
 
 // ------------------------------------------------------------------------------------------------
-// tables
+// sign volume: S(q) = float32(field(q)) > 0.5, packed in padded coordinates (Zp, Hp, nwp).
+// S equals the padded occupancy P except at voxels all of whose six (reflected) face neighbours disagree with
+// them (see the header comment); those few are evaluated exactly (slow path, not inlined).
+// Same shape as the morphology kernel: a thread owns one uint4 column of one padded plane and marches down FY
+// rows; the padded words are funnel-shifted out of the un-padded occupancy on the fly.
 // ------------------------------------------------------------------------------------------------
-__device__ __align__(16) const int8_t g_tri_table[256][T3D_MC_ROW] = {T3D_TRI_TABLE_ROWS};
-static const int8_t h_tri_table[256][T3D_MC_ROW] = {T3D_TRI_TABLE_ROWS};
+#define FY 16
 
-struct McLuts {
-    uint8_t ntri[256];
-    uint8_t amb[256];
-};
-__constant__ McLuts c_luts;
-static bool g_luts_ready = false;
-
-static int host_is_ambiguous(int idx)
+__device__ __noinline__ uint32_t exact_sign_bits(const OccView* v, int zp, int yp, int wp, uint32_t need, uint32_t s)
 {
-    static const int FC[6][4] = {{0, 1, 2, 3}, {4, 5, 6, 7}, {0, 1, 5, 4}, {3, 2, 6, 7}, {0, 3, 7, 4}, {1, 2, 6, 5}};
-    for (int f = 0; f < 6; ++f) {
-        const int a = (idx >> FC[f][0]) & 1, b = (idx >> FC[f][1]) & 1, c = (idx >> FC[f][2]) & 1, d = (idx >> FC[f][3]) & 1;
-        if (a == c && b == d && a != b) return 1;
+    while (need) {
+        const int b = __ffs(need) - 1;
+        need &= need - 1;
+        if (field_value(*v, zp, yp, (wp << 5) + b) > 0.5f) s |= 1u << b; else s &= ~(1u << b);
     }
-    static const int DG[4][2] = {{0, 6}, {1, 7}, {2, 4}, {3, 5}};
-    for (int k = 0; k < 4; ++k) {
-        const int m = (1 << DG[k][0]) | (1 << DG[k][1]);
-        if (idx == m || idx == (255 ^ m)) return 1;
-    }
-    return 0;
+    return s;
 }
 
-static int ensure_luts()
-{
-    if (g_luts_ready) return 0;
-    McLuts l;
-    for (int i = 0; i < 256; ++i) {
-        int n = 0;
-        while (n < T3D_MC_ROW && h_tri_table[i][n] >= 0) n += 3;
-        l.ntri[i] = (uint8_t)(n / 3);
-        l.amb[i] = (uint8_t)host_is_ambiguous(i);
-    }
-    T3D_CUDA(cudaMemcpyToSymbol(c_luts, &l, sizeof(l)));
-    g_luts_ready = true;
-    return 0;
-}
-
-// ------------------------------------------------------------------------------------------------
-// padded-occupancy view + exact field evaluation
-// ------------------------------------------------------------------------------------------------
-struct OccView {
-    const uint32_t* bits;  // (Z, H, nw) packed occupancy
-    int Z, H, W, nw;
-    int pad;               // 0 or 1
-    int Zp, Hp, Wp;        // padded extents
-    int gaussian;          // 1: field = gaussian(sigma 0.5) of padded occupancy; 0: field = occupancy
-    double w0, w1, w2;     // scipy _gaussian_kernel1d(0.5, 0, 2): centre, +-1, +-2
-};
-
-// scipy 'reflect' (d c b a | a b c d | d c b a)
-__device__ __forceinline__ int reflect_idx(int i, int n)
-{
-    if (i >= 0 && i < n) return i;
-    if (n == 1) return 0;
-    const int period = 2 * n;
-    i %= period;
-    if (i < 0) i += period;
-    return i < n ? i : period - 1 - i;
-}
-
-// padded occupancy bit (coordinates already inside [0, Np))
-__device__ __forceinline__ uint32_t pbit(const OccView& v, int zp, int yp, int xp)
-{
-    const int z = zp - v.pad, y = yp - v.pad, x = xp - v.pad;
-    if (z < 0 || z >= v.Z || y < 0 || y >= v.H || x < 0 || x >= v.W) return 0u;
-    return (v.bits[((int64_t)z * v.H + y) * v.nw + (x >> 5)] >> (x & 31)) & 1u;
-}
-
-// bits of padded row (zp, yp) at padded x = xs .. xs+4 (x reflected at the padded border)
-__device__ __forceinline__ uint32_t get5(const OccView& v, int zp, int yp, int xs)
+// four padded words wp = 4*wp4 .. 4*wp4+3 of padded row (zp, yp), plus the padded words to their left and right
+__device__ __forceinline__ uint4 prow4(const OccView& v, int zp, int yp, int wp4, uint32_t& left, uint32_t& right)
 {
     const int z = zp - v.pad, y = yp - v.pad;
-    if (z < 0 || z >= v.Z || y < 0 || y >= v.H) return 0u;
+    if (z < 0 || z >= v.Z || y < 0 || y >= v.H) { left = right = 0u; return make_uint4(0, 0, 0, 0); }
     const uint32_t* row = v.bits + ((int64_t)z * v.H + y) * v.nw;
-    if (xs >= 0 && xs + 4 < v.Wp) {
-        const int ox = xs - v.pad;
-        const int w = ox >> 5, sh = ox & 31;
-        const uint32_t lo = (w >= 0 && w < v.nw) ? row[w] : 0u;
-        const uint32_t hi = (w + 1 >= 0 && w + 1 < v.nw) ? row[w + 1] : 0u;
-        const unsigned long long win = (unsigned long long)lo | ((unsigned long long)hi << 32);
-        return (uint32_t)(win >> sh) & 31u;
-    }
-    uint32_t r = 0;
-#pragma unroll
-    for (int k = 0; k < 5; ++k) {
-        const int ox = reflect_idx(xs + k, v.Wp) - v.pad;
-        if (ox >= 0 && ox < v.W) r |= ((row[ox >> 5] >> (ox & 31)) & 1u) << k;
-    }
-    return r;
+    const int w0 = 4 * wp4;
+    const uint4 o = (w0 < v.nw) ? *reinterpret_cast<const uint4*>(row + w0) : make_uint4(0, 0, 0, 0);
+    const uint32_t om1 = (w0 >= 1 && w0 - 1 < v.nw) ? row[w0 - 1] : 0u;
+    const uint32_t o4 = (w0 + 4 < v.nw) ? row[w0 + 4] : 0u;
+    if (!v.pad) { left = om1; right = o4; return o; }
+    const uint32_t om2 = (w0 >= 2 && w0 - 2 < v.nw) ? row[w0 - 2] : 0u;
+    left = __funnelshift_l(om2, om1, 1);
+    right = __funnelshift_l(o.w, o4, 1);
+    return make_uint4(__funnelshift_l(om1, o.x, 1), __funnelshift_l(o.x, o.y, 1), __funnelshift_l(o.y, o.z, 1),
+                      __funnelshift_l(o.z, o.w, 1));
 }
 
-// one symmetric 5-tap correlation in scipy's order: c*w0 + (a_-2 + a_+2)*w2 + (a_-1 + a_+1)*w1, no FMA
-__device__ __forceinline__ double corr5(double m2, double m1, double c, double p1, double p2, double w0, double w1, double w2)
+__global__ void __launch_bounds__(256) k_field_sign(OccView v, uint32_t* __restrict__ sign, int nwp, int lanes_x,
+                                                    int pz_per_block, unsigned long long* __restrict__ n_exact)
 {
-    double t = __dmul_rn(c, w0);
-    t = __dadd_rn(t, __dmul_rn(__dadd_rn(m2, p2), w2));
-    t = __dadd_rn(t, __dmul_rn(__dadd_rn(m1, p1), w1));
-    return t;
-}
-
-// float32(field) at padded voxel (zp, yp, xp): separable float64 passes along z, then y, then x,
-// each with reflect boundary, exactly like scipy.ndimage.gaussian_filter
-__device__ float field_value(const OccView& v, int zp, int yp, int xp)
-{
-    if (!v.gaussian) return pbit(v, zp, yp, xp) ? 1.0f : 0.0f;
-    uint32_t b[5][5];
-#pragma unroll
-    for (int dz = 0; dz < 5; ++dz) {
-        const int zr = reflect_idx(zp - 2 + dz, v.Zp);
-#pragma unroll
-        for (int dy = 0; dy < 5; ++dy) b[dz][dy] = get5(v, zr, reflect_idx(yp - 2 + dy, v.Hp), xp - 2);
-    }
-    double Y[5];
-#pragma unroll
-    for (int dx = 0; dx < 5; ++dx) {
-        double A[5];
-#pragma unroll
-        for (int dy = 0; dy < 5; ++dy) {
-            const double c = (double)((b[2][dy] >> dx) & 1u);
-            const double n1 = (double)(((b[1][dy] >> dx) & 1u) + ((b[3][dy] >> dx) & 1u));
-            const double n2 = (double)(((b[0][dy] >> dx) & 1u) + ((b[4][dy] >> dx) & 1u));
-            double t = __dmul_rn(c, v.w0);
-            t = __dadd_rn(t, __dmul_rn(n2, v.w2));
-            t = __dadd_rn(t, __dmul_rn(n1, v.w1));
-            A[dy] = t;
+    __shared__ OccView sv;  // the rare exact path takes the view by pointer (keeps it out of registers / local memory)
+    if (threadIdx.x == 0) sv = v;
+    __syncthreads();
+    const int lx = threadIdx.x % lanes_x, pz = threadIdx.x / lanes_x;
+    const int nwp4 = nwp >> 2;
+    const int wp4 = blockIdx.x * lanes_x + lx, zp = blockIdx.z * pz_per_block + pz, y0 = blockIdx.y * FY;
+    if (pz >= pz_per_block || wp4 >= nwp4 || zp >= v.Zp) return;
+    const uint4 vm = valid_mask4(wp4, v.Wp);
+    const int zm_i = reflect_idx(zp - 1, v.Zp), zq_i = reflect_idx(zp + 1, v.Zp);
+    const int last = v.Wp - 1, last_w = last >> 5;
+    const uint32_t last_bit = 1u << (last & 31);
+    uint32_t l0, r0, lc, rc, ln, rn;
+    uint4 prev = prow4(v, zp, reflect_idx(y0 - 1, v.Hp), wp4, l0, r0);
+    uint4 cur = prow4(v, zp, y0, wp4, lc, rc);
+    const int y1 = min(v.Hp, y0 + FY);
+    for (int yp = y0; yp < y1; ++yp) {
+        const uint4 next = prow4(v, zp, reflect_idx(yp + 1, v.Hp), wp4, ln, rn);
+        uint32_t d0, d1;
+        const uint4 zm = prow4(v, zm_i, yp, wp4, d0, d1), zq = prow4(v, zq_i, yp, wp4, d0, d1);
+        uint4 xm = shl1_4(cur, lc), xq = shr1_4(cur, rc);
+        if (wp4 == 0) xm.x = (xm.x & ~1u) | (cur.x & 1u);  // reflect: x = -1 -> x = 0
+        if ((last_w >> 2) == wp4) {                        // reflect: x = Wp -> x = Wp-1
+            const int j = last_w & 3;
+            if (j == 0) xq.x = (xq.x & ~last_bit) | (cur.x & last_bit);
+            else if (j == 1) xq.y = (xq.y & ~last_bit) | (cur.y & last_bit);
+            else if (j == 2) xq.z = (xq.z & ~last_bit) | (cur.z & last_bit);
+            else xq.w = (xq.w & ~last_bit) | (cur.w & last_bit);
         }
-        Y[dx] = corr5(A[0], A[1], A[2], A[3], A[4], v.w0, v.w1, v.w2);
-    }
-    return __double2float_rn(corr5(Y[0], Y[1], Y[2], Y[3], Y[4], v.w0, v.w1, v.w2));
-}
-
-// padded occupancy word (zp, yp, wp) in padded x coordinates (no reflection; outside = 0)
-__device__ __forceinline__ uint32_t pword(const OccView& v, int zp, int yp, int wp)
-{
-    const int z = zp - v.pad, y = yp - v.pad;
-    if (z < 0 || z >= v.Z || y < 0 || y >= v.H || wp < 0) return 0u;
-    const uint32_t* row = v.bits + ((int64_t)z * v.H + y) * v.nw;
-    const uint32_t cur = (wp < v.nw) ? row[wp] : 0u;
-    if (!v.pad) return cur;
-    const uint32_t prev = (wp - 1 >= 0 && wp - 1 < v.nw) ? row[wp - 1] : 0u;
-    return (cur << 1) | (prev >> 31);
-}
-
-// ------------------------------------------------------------------------------------------------
-// sign volume: S(q) = float32(field(q)) > 0.5, packed in padded coordinates (Zp, Hp, nwp)
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_field_sign(OccView v, uint32_t* __restrict__ sign, int nwp,
-                                                    unsigned long long* __restrict__ n_exact)
-{
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t total = (int64_t)v.Zp * v.Hp * nwp;
-    if (i >= total) return;
-    const int wp = (int)(i % nwp);
-    const int64_t r = i / nwp;
-    const int yp = (int)(r % v.Hp), zp = (int)(r / v.Hp);
-    const uint32_t vm = valid_mask(wp, v.Wp);
-    const uint32_t c = pword(v, zp, yp, wp);
-    const uint32_t zm = pword(v, reflect_idx(zp - 1, v.Zp), yp, wp), zq = pword(v, reflect_idx(zp + 1, v.Zp), yp, wp);
-    const uint32_t ym = pword(v, zp, reflect_idx(yp - 1, v.Hp), wp), yq = pword(v, zp, reflect_idx(yp + 1, v.Hp), wp);
-    const uint32_t lw = pword(v, zp, yp, wp - 1), rw = pword(v, zp, yp, wp + 1);
-    uint32_t xm = (c << 1) | (lw >> 31);  // value at x-1
-    uint32_t xq = (c >> 1) | (rw << 31);  // value at x+1
-    if (wp == 0) xm = (xm & ~1u) | (c & 1u);  // reflect: x = -1 -> x = 0
-    {
-        const int last = v.Wp - 1;            // reflect: x = Wp -> x = Wp-1
-        if ((last >> 5) == wp) {
-            const uint32_t bit = 1u << (last & 31);
-            xq = (xq & ~bit) | (c & bit);
+        const uint4 any1 = or4(or4(or4(zm, zq), or4(prev, next)), or4(xm, xq));
+        const uint4 all1 = and4(and4(and4(zm, zq), and4(prev, next)), and4(xm, xq));
+        uint4 s = and4(cur, any1);
+        uint4 need;
+        need.x = ((cur.x & ~any1.x) | (~cur.x & all1.x)) & vm.x;
+        need.y = ((cur.y & ~any1.y) | (~cur.y & all1.y)) & vm.y;
+        need.z = ((cur.z & ~any1.z) | (~cur.z & all1.z)) & vm.z;
+        need.w = ((cur.w & ~any1.w) | (~cur.w & all1.w)) & vm.w;
+        if (need.x | need.y | need.z | need.w) {
+            atomicAdd(n_exact, (unsigned long long)popc4(need));
+            if (need.x) s.x = exact_sign_bits(&sv, zp, yp, 4 * wp4, need.x, s.x);
+            if (need.y) s.y = exact_sign_bits(&sv, zp, yp, 4 * wp4 + 1, need.y, s.y);
+            if (need.z) s.z = exact_sign_bits(&sv, zp, yp, 4 * wp4 + 2, need.z, s.z);
+            if (need.w) s.w = exact_sign_bits(&sv, zp, yp, 4 * wp4 + 3, need.w, s.w);
         }
-    }
-    const uint32_t any1 = zm | zq | ym | yq | xm | xq;
-    const uint32_t all1 = zm & zq & ym & yq & xm & xq;
-    uint32_t s = c & any1;
-    uint32_t need = ((c & ~any1) | (~c & all1)) & vm;
-    if (need) {
-        atomicAdd(n_exact, (unsigned long long)__popc(need));
-        while (need) {
-            const int b = __ffs(need) - 1;
-            need &= need - 1;
-            if (field_value(v, zp, yp, (wp << 5) + b) > 0.5f) s |= 1u << b; else s &= ~(1u << b);
-        }
-    }
-    sign[i] = s & vm;
-}
-
-// ------------------------------------------------------------------------------------------------
-// marching cubes pass 1: per voxel-row counts of owned cut edges (x, y, z) and triangles.
-// One warp per row (zp, yp) of the sign volume; lane = word.
-// ------------------------------------------------------------------------------------------------
-struct RowWords {
-    uint32_t s00, s01, s10, s11;  // rows (z,y) (z,y+1) (z+1,y) (z+1,y+1), word w
-    uint32_t n00, n01, n10, n11;  // bit 0 of word w+1 of each row (0/1)
-};
-
-__device__ __forceinline__ uint32_t ldw(const uint32_t* row, int w, int nwp) { return (row && w < nwp) ? row[w] : 0u; }
-
-__device__ __forceinline__ RowWords load_rows(const uint32_t* r00, const uint32_t* r01, const uint32_t* r10,
-                                              const uint32_t* r11, int w, int nwp)
-{
-    RowWords q;
-    q.s00 = ldw(r00, w, nwp); q.s01 = ldw(r01, w, nwp); q.s10 = ldw(r10, w, nwp); q.s11 = ldw(r11, w, nwp);
-    q.n00 = ldw(r00, w + 1, nwp) & 1u; q.n01 = ldw(r01, w + 1, nwp) & 1u;
-    q.n10 = ldw(r10, w + 1, nwp) & 1u; q.n11 = ldw(r11, w + 1, nwp) & 1u;
-    return q;
-}
-
-__device__ __forceinline__ uint32_t shr1(uint32_t s, uint32_t nbit) { return (s >> 1) | (nbit << 31); }  // value at x+1
-
-// 8-bit cube case of the cube whose origin is bit b of the current word
-__device__ __forceinline__ int cube_case(const RowWords& q, int b)
-{
-    const uint32_t a00 = shr1(q.s00, q.n00), a01 = shr1(q.s01, q.n01), a10 = shr1(q.s10, q.n10), a11 = shr1(q.s11, q.n11);
-    return (int)(((q.s00 >> b) & 1u) | (((a00 >> b) & 1u) << 1) | (((a01 >> b) & 1u) << 2) | (((q.s01 >> b) & 1u) << 3) |
-                 (((q.s10 >> b) & 1u) << 4) | (((a10 >> b) & 1u) << 5) | (((a11 >> b) & 1u) << 6) | (((q.s11 >> b) & 1u) << 7));
-}
-
-__global__ void __launch_bounds__(256) k_mc_count(const uint32_t* __restrict__ sign, int Zp, int Hp, int Wp, int nwp,
-                                                  uint32_t* __restrict__ rowcnt, int64_t n_rows,
-                                                  unsigned long long* __restrict__ n_ambiguous)
-{
-    const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (row >= n_rows) return;
-    const int y = (int)(row % Hp), z = (int)(row / Hp);
-    const uint32_t l = lane_id();
-    const bool hy = (y + 1 < Hp), hz = (z + 1 < Zp);
-    const uint32_t* r00 = sign + row * nwp;
-    const uint32_t* r01 = hy ? r00 + nwp : nullptr;
-    const uint32_t* r10 = hz ? r00 + (int64_t)Hp * nwp : nullptr;
-    const uint32_t* r11 = (hy && hz) ? r10 + nwp : nullptr;
-    uint32_t nX = 0, nY = 0, nZ = 0, nT = 0, nA = 0;
-    for (int w = l; w < nwp; w += 32) {
-        const RowWords q = load_rows(r00, r01, r10, r11, w, nwp);
-        const uint32_t vm = valid_mask(w, Wp), em = valid_mask(w, Wp - 1);  // em: x+1 still inside
-        nX += __popc((q.s00 ^ shr1(q.s00, q.n00)) & em);
-        if (hy) nY += __popc((q.s00 ^ q.s01) & vm);
-        if (hz) nZ += __popc((q.s00 ^ q.s10) & vm);
-        if (hy && hz) {
-            const uint32_t o = q.s00 | q.s01 | q.s10 | q.s11, a = q.s00 & q.s01 & q.s10 & q.s11;
-            const uint32_t on = (q.n00 | q.n01 | q.n10 | q.n11), an = (q.n00 & q.n01 & q.n10 & q.n11);
-            uint32_t act = ((o | shr1(o, on)) & ~(a & shr1(a, an))) & em;
-            while (act) {
-                const int b = __ffs(act) - 1;
-                act &= act - 1;
-                const int cs = cube_case(q, b);
-                nT += c_luts.ntri[cs];
-                nA += c_luts.amb[cs];
-            }
-        }
-    }
-    nX = warp_sum(nX); nY = warp_sum(nY); nZ = warp_sum(nZ); nT = warp_sum(nT); nA = warp_sum(nA);
-    if (l == 0) {
-        rowcnt[row] = nX;
-        rowcnt[n_rows + row] = nY;
-        rowcnt[2 * n_rows + row] = nZ;
-        rowcnt[3 * n_rows + row] = nT;
-        if (nA) atomicAdd(n_ambiguous, (unsigned long long)nA);
+        *reinterpret_cast<uint4*>(sign + ((int64_t)zp * v.Hp + yp) * nwp + 4 * wp4) = and4(s, vm);
+        prev = cur;
+        cur = next; lc = ln; rc = rn;
     }
 }
 
@@ -294,14 +117,14 @@ __global__ void __launch_bounds__(256) k_mc_count(const uint32_t* __restrict__ s
 #define SC_TILE (SC_THREADS * SC_ITEMS)
 
 __global__ void __launch_bounds__(SC_THREADS) k_scan_reduce(const uint32_t* __restrict__ in, int64_t n, int64_t stride,
-                                                            unsigned long long* __restrict__ block_sums, int n_blocks)
+                                                            unsigned long long* __restrict__ block_sums, int n_blocks, int popc_in)
 {
     const uint32_t* a = in + (int64_t)blockIdx.y * stride;
     const int64_t base = (int64_t)blockIdx.x * SC_TILE;
     unsigned long long s = 0;
     for (int k = 0; k < SC_ITEMS; ++k) {
         const int64_t i = base + (int64_t)k * SC_THREADS + threadIdx.x;
-        if (i < n) s += a[i];
+        if (i < n) s += popc_in ? (uint32_t)__popc(a[i]) : a[i];
     }
     s = warp_sum(s);
     __shared__ unsigned long long sh[SC_THREADS / 32];
@@ -355,7 +178,7 @@ __global__ void __launch_bounds__(1024) k_scan_block_sums(unsigned long long* __
 template <typename OutT>
 __global__ void __launch_bounds__(SC_THREADS) k_scan_final(const uint32_t* __restrict__ in, OutT* __restrict__ out, int64_t n,
                                                            int64_t stride, const unsigned long long* __restrict__ block_sums,
-                                                           int n_blocks)
+                                                           int n_blocks, int popc_in)
 {
     const uint32_t* a = in + (int64_t)blockIdx.y * stride;
     OutT* o = out + (int64_t)blockIdx.y * stride;
@@ -364,7 +187,7 @@ __global__ void __launch_bounds__(SC_THREADS) k_scan_final(const uint32_t* __res
     uint32_t s = 0;
 #pragma unroll
     for (int k = 0; k < SC_ITEMS; ++k) {
-        v[k] = (base + k < n) ? a[base + k] : 0u;
+        v[k] = (base + k < n) ? (popc_in ? (uint32_t)__popc(a[base + k]) : a[base + k]) : 0u;
         s += v[k];
     }
     const uint32_t incl = warp_incl_scan(s);
@@ -388,9 +211,10 @@ extern "C" int64_t t3d_scan_workspace_bytes(int64_t n, int n_arrays)
 }
 
 // in: n_arrays arrays of n uint32 (array k starts at in + k*n); out: same layout, uint32 (out_is_u64 = 0)
-// or uint64 (1); may alias `in` only for uint32 output.  totals: n_arrays uint64 (device).
-extern "C" int t3d_exclusive_scan_u32(const void* in, void* out, int64_t n, int n_arrays, int out_is_u64, void* totals_u64,
-                                      void* workspace, void* stream)
+// or uint64 (1); may alias `in` only for uint32 output.  popcount_input = 1 scans popcount(in[i]) instead of in[i].
+// totals: n_arrays uint64 (device).
+extern "C" int t3d_exclusive_scan_u32(const void* in, void* out, int64_t n, int n_arrays, int out_is_u64, int popcount_input,
+                                      void* totals_u64, void* workspace, void* stream)
 {
     cudaStream_t st = (cudaStream_t)stream;
     if (n <= 0 || n_arrays <= 0) {
@@ -401,218 +225,20 @@ extern "C" int t3d_exclusive_scan_u32(const void* in, void* out, int64_t n, int 
     if (nb > 0x7fffffff) { t3d_set_error("t3d_exclusive_scan_u32: too many elements"); return 2; }
     unsigned long long* bs = (unsigned long long*)workspace;
     dim3 grid((unsigned)nb, n_arrays);
-    k_scan_reduce<<<grid, SC_THREADS, 0, st>>>((const uint32_t*)in, n, n, bs, (int)nb);
+    k_scan_reduce<<<grid, SC_THREADS, 0, st>>>((const uint32_t*)in, n, n, bs, (int)nb, popcount_input);
     k_scan_block_sums<<<n_arrays, 1024, 0, st>>>(bs, (int)nb, (unsigned long long*)totals_u64);
     if (out_is_u64)
-        k_scan_final<unsigned long long><<<grid, SC_THREADS, 0, st>>>((const uint32_t*)in, (unsigned long long*)out, n, n, bs, (int)nb);
+        k_scan_final<unsigned long long><<<grid, SC_THREADS, 0, st>>>((const uint32_t*)in, (unsigned long long*)out, n, n, bs, (int)nb, popcount_input);
     else
-        k_scan_final<uint32_t><<<grid, SC_THREADS, 0, st>>>((const uint32_t*)in, (uint32_t*)out, n, n, bs, (int)nb);
+        k_scan_final<uint32_t><<<grid, SC_THREADS, 0, st>>>((const uint32_t*)in, (uint32_t*)out, n, n, bs, (int)nb, popcount_input);
     T3D_CHECK_LAUNCH("t3d_exclusive_scan_u32");
     t3d_count_launches(3);
     return 0;
 }
 
 // ------------------------------------------------------------------------------------------------
-// marching cubes pass 2: vertex + face emission.
-// Vertex ids: [all x-edge vertices | all y-edge vertices | all z-edge vertices], each block in raster
-// order of the owning voxel (edge owned by its lower corner) => id = block offset + row base + rank in row.
-// Faces are emitted in the reference's order (cubes z-major, y, x fastest; table order inside a cube)
-// with the winding reversed (gradient_direction='descent').
-// ------------------------------------------------------------------------------------------------
-struct EmitParams {
-    OccView occ;
-    const uint32_t* sign;
-    int nwp;
-    int64_t n_rows;
-    const uint32_t* rowbase;  // 4 arrays of n_rows (exclusive scans of the counts): X, Y, Z, T
-    uint32_t offY, offZ;      // offX = 0
-    // vertex transform
-    float shift;              // 1 if manifold else 0 (surface_extractor.py:57-60)
-    const double* cum;        // cumulative adjusted depths, n_cum entries (nullptr / 0: no z map)
-    const double* adj;        // adjusted depths, n_cum-1 entries
-    int n_cum;
-    double mm_y, mm_x;        // mm per pixel
-    int scale_f64;            // 1: multiply in float64 then round (numpy float64 scalar operand), 0: float32 multiply
-    float* verts;             // (V, 3) z, y, x
-    int32_t* faces;           // (F, 3)
-};
-
-__device__ __forceinline__ void emit_vertex(const EmitParams& p, uint32_t id, int axis, int z, int y, int x)
-{
-    // end points of the edge: (z,y,x) and +1 along `axis` (0 = z, 1 = y, 2 = x)
-    const double va = (double)field_value(p.occ, z, y, x) - 0.5;
-    const double vb = (double)field_value(p.occ, z + (axis == 0), y + (axis == 1), x + (axis == 2)) - 0.5;
-    const double wa = __ddiv_rn(1.0, __dadd_rn(1.1920928955078125e-07, fabs(va)));
-    const double wb = __ddiv_rn(1.0, __dadd_rn(1.1920928955078125e-07, fabs(vb)));
-    const double frac = __ddiv_rn(wb, __dadd_rn(wa, wb));
-    double pz = (double)z, py = (double)y, px = (double)x;
-    if (axis == 0) pz = __dadd_rn(pz, frac); else if (axis == 1) py = __dadd_rn(py, frac); else px = __dadd_rn(px, frac);
-    float fz = __fsub_rn(__double2float_rn(pz), p.shift);
-    float fy = __fsub_rn(__double2float_rn(py), p.shift);
-    float fx = __fsub_rn(__double2float_rn(px), p.shift);
-    if (p.n_cum > 0) {
-        // surface_extractor.py:98-113, closed form verified bit-exact in SURVEY.md V8
-        if (fz < 0.0f) fz = 0.0f;
-        else if (fz >= (float)(p.n_cum - 1)) fz = __double2float_rn(p.cum[p.n_cum - 1]);
-        else {
-            const float fl = floorf(fz);
-            const int lo = (int)fl;
-            const float fr = __fsub_rn(fz, fl);
-            const int ai = min(lo, p.n_cum - 2);
-            fz = __double2float_rn(__dadd_rn(p.cum[lo], __dmul_rn((double)fr, p.adj[ai])));
-        }
-    }
-    if (p.scale_f64) {
-        fy = __double2float_rn(__dmul_rn((double)fy, p.mm_y));
-        fx = __double2float_rn(__dmul_rn((double)fx, p.mm_x));
-    } else {
-        fy = __fmul_rn(fy, __double2float_rn(p.mm_y));
-        fx = __fmul_rn(fx, __double2float_rn(p.mm_x));
-    }
-    float* o = p.verts + 3 * (int64_t)id;
-    o[0] = fz; o[1] = fy; o[2] = fx;
-}
-
-__device__ __forceinline__ uint32_t lt_mask(int b) { return b >= 32 ? 0xffffffffu : ((1u << b) - 1u); }
-
-#define EM_WARPS 8
-
-__global__ void __launch_bounds__(EM_WARPS * 32) k_mc_emit(EmitParams p)
-{
-    __shared__ __align__(16) int8_t s_tri[256][T3D_MC_ROW];
-    {
-        const int4* src = reinterpret_cast<const int4*>(&g_tri_table[0][0]);
-        int4* dst = reinterpret_cast<int4*>(&s_tri[0][0]);
-        for (int i = threadIdx.x; i < 256; i += blockDim.x) dst[i] = src[i];
-    }
-    __syncthreads();
-    const int64_t row = (int64_t)blockIdx.x * EM_WARPS + (threadIdx.x >> 5);
-    if (row >= p.n_rows) return;
-    const int Zp = p.occ.Zp, Hp = p.occ.Hp, Wp = p.occ.Wp, nwp = p.nwp;
-    const int y = (int)(row % Hp), z = (int)(row / Hp);
-    const uint32_t l = lane_id();
-    const bool hy = (y + 1 < Hp), hz = (z + 1 < Zp);
-    const uint32_t* r00 = p.sign + row * nwp;
-    const uint32_t* r01 = hy ? r00 + nwp : nullptr;
-    const uint32_t* r10 = hz ? r00 + (int64_t)Hp * nwp : nullptr;
-    const uint32_t* r11 = (hy && hz) ? r10 + nwp : nullptr;
-    const int64_t N = p.n_rows;
-    // running bases (advance chunk by chunk)
-    uint32_t bX00 = p.rowbase[row];
-    uint32_t bX01 = hy ? p.rowbase[row + 1] : 0u;
-    uint32_t bX10 = hz ? p.rowbase[row + Hp] : 0u;
-    uint32_t bX11 = (hy && hz) ? p.rowbase[row + Hp + 1] : 0u;
-    uint32_t bY0 = p.offY + p.rowbase[N + row];
-    uint32_t bY1 = hz ? p.offY + p.rowbase[N + row + Hp] : 0u;
-    uint32_t bZ0 = p.offZ + p.rowbase[2 * N + row];
-    uint32_t bZ1 = hy ? p.offZ + p.rowbase[2 * N + row + 1] : 0u;
-    uint32_t bT = p.rowbase[3 * N + row];
-
-    for (int w0 = 0; w0 < nwp; w0 += 32) {
-        const int w = w0 + l;
-        const RowWords q = load_rows(r00, r01, r10, r11, w, nwp);
-        const uint32_t vm = valid_mask(w, Wp), em = valid_mask(w, Wp - 1);
-        const uint32_t X00 = (q.s00 ^ shr1(q.s00, q.n00)) & em;
-        const uint32_t X01 = hy ? (q.s01 ^ shr1(q.s01, q.n01)) & em : 0u;
-        const uint32_t X10 = hz ? (q.s10 ^ shr1(q.s10, q.n10)) & em : 0u;
-        const uint32_t X11 = (hy && hz) ? (q.s11 ^ shr1(q.s11, q.n11)) & em : 0u;
-        const uint32_t Y0 = hy ? (q.s00 ^ q.s01) & vm : 0u;
-        const uint32_t Y1 = (hy && hz) ? (q.s10 ^ q.s11) & vm : 0u;
-        const uint32_t Z0 = hz ? (q.s00 ^ q.s10) & vm : 0u;
-        const uint32_t Z1 = (hy && hz) ? (q.s01 ^ q.s11) & vm : 0u;
-        uint32_t act = 0;
-        if (hy && hz) {
-            const uint32_t o = q.s00 | q.s01 | q.s10 | q.s11, a = q.s00 & q.s01 & q.s10 & q.s11;
-            const uint32_t on = (q.n00 | q.n01 | q.n10 | q.n11), an = (q.n00 & q.n01 & q.n10 & q.n11);
-            act = ((o | shr1(o, on)) & ~(a & shr1(a, an))) & em;
-        }
-        uint32_t nt = 0;
-        for (uint32_t m = act; m;) {
-            const int b = __ffs(m) - 1;
-            m &= m - 1;
-            nt += c_luts.ntri[cube_case(q, b)];
-        }
-        // packed warp scans (two 16-bit fields per word; per-chunk sums <= 1024 and <= 5120 for triangles)
-        const uint32_t c0 = __popc(X00) | (__popc(X01) << 16), c1 = __popc(X10) | (__popc(X11) << 16);
-        const uint32_t c2 = __popc(Y0) | (__popc(Y1) << 16), c3 = __popc(Z0) | (__popc(Z1) << 16);
-        const uint32_t i0 = warp_incl_scan(c0), i1 = warp_incl_scan(c1), i2 = warp_incl_scan(c2), i3 = warp_incl_scan(c3);
-        const uint32_t it = warp_incl_scan(nt);
-        const uint32_t e0 = i0 - c0, e1 = i1 - c1, e2 = i2 - c2, e3 = i3 - c3;
-        const uint32_t pX00 = bX00 + (e0 & 0xffffu), pX01 = bX01 + (e0 >> 16);
-        const uint32_t pX10 = bX10 + (e1 & 0xffffu), pX11 = bX11 + (e1 >> 16);
-        const uint32_t pY0 = bY0 + (e2 & 0xffffu), pY1 = bY1 + (e2 >> 16);
-        const uint32_t pZ0 = bZ0 + (e3 & 0xffffu), pZ1 = bZ1 + (e3 >> 16);
-        uint32_t pT = bT + (it - nt);
-
-        // ---- vertices owned by this row
-        {
-            uint32_t id = pX00;
-            for (uint32_t m = X00; m;) { const int b = __ffs(m) - 1; m &= m - 1; emit_vertex(p, id++, 2, z, y, (w << 5) + b); }
-            id = pY0;
-            for (uint32_t m = Y0; m;) { const int b = __ffs(m) - 1; m &= m - 1; emit_vertex(p, id++, 1, z, y, (w << 5) + b); }
-            id = pZ0;
-            for (uint32_t m = Z0; m;) { const int b = __ffs(m) - 1; m &= m - 1; emit_vertex(p, id++, 0, z, y, (w << 5) + b); }
-        }
-        // ---- faces of the cubes of this row
-        for (uint32_t m = act; m;) {
-            const int b = __ffs(m) - 1;
-            m &= m - 1;
-            const int cs = cube_case(q, b);
-            const uint32_t lb = lt_mask(b), lb1 = lt_mask(b + 1);
-            const int8_t* rowt = s_tri[cs];
-            for (int t = 0; t < T3D_MC_ROW && rowt[t] >= 0; t += 3) {
-                uint32_t vid[3];
-#pragma unroll
-                for (int k = 0; k < 3; ++k) {
-                    uint32_t id;
-                    switch (rowt[t + k]) {
-                        case 0: id = pX00 + __popc(X00 & lb); break;
-                        case 1: id = pY0 + __popc(Y0 & lb1); break;
-                        case 2: id = pX01 + __popc(X01 & lb); break;
-                        case 3: id = pY0 + __popc(Y0 & lb); break;
-                        case 4: id = pX10 + __popc(X10 & lb); break;
-                        case 5: id = pY1 + __popc(Y1 & lb1); break;
-                        case 6: id = pX11 + __popc(X11 & lb); break;
-                        case 7: id = pY1 + __popc(Y1 & lb); break;
-                        case 8: id = pZ0 + __popc(Z0 & lb); break;
-                        case 9: id = pZ0 + __popc(Z0 & lb1); break;
-                        case 10: id = pZ1 + __popc(Z1 & lb1); break;
-                        default: id = pZ1 + __popc(Z1 & lb); break;  // 11
-                    }
-                    vid[k] = id;
-                }
-                int32_t* f = p.faces + 3 * (int64_t)pT;
-                f[0] = (int32_t)vid[2]; f[1] = (int32_t)vid[1]; f[2] = (int32_t)vid[0];
-                ++pT;
-            }
-        }
-        // ---- advance running bases by the chunk totals
-        const uint32_t t0 = __shfl_sync(0xffffffffu, i0, 31), t1 = __shfl_sync(0xffffffffu, i1, 31);
-        const uint32_t t2 = __shfl_sync(0xffffffffu, i2, 31), t3 = __shfl_sync(0xffffffffu, i3, 31);
-        bX00 += t0 & 0xffffu; bX01 += t0 >> 16; bX10 += t1 & 0xffffu; bX11 += t1 >> 16;
-        bY0 += t2 & 0xffffu; bY1 += t2 >> 16; bZ0 += t3 & 0xffffu; bZ1 += t3 >> 16;
-        bT += __shfl_sync(0xffffffffu, it, 31);
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
 // C ABI: field sign / count / emit
 // ------------------------------------------------------------------------------------------------
-static OccView make_view(const void* occ_bits, int Z, int H, int W, int pad, int gaussian, const double* w3)
-{
-    OccView v;
-    v.bits = (const uint32_t*)occ_bits;
-    v.Z = Z; v.H = H; v.W = W; v.nw = t3d_wpr(W);
-    v.pad = pad ? 1 : 0;
-    v.Zp = Z + 2 * v.pad; v.Hp = H + 2 * v.pad; v.Wp = W + 2 * v.pad;
-    v.gaussian = gaussian ? 1 : 0;
-    // scipy.ndimage._filters._gaussian_kernel1d(0.5, 0, 2)
-    v.w0 = w3 ? w3[0] : 0x1.92b965ef5aaeep-1;
-    v.w1 = w3 ? w3[1] : 0x1.b405b9842b206p-4;
-    v.w2 = w3 ? w3[2] : 0x1.14aebe6a24088p-12;
-    return v;
-}
-
 // sign volume dims: (Z+2p, H+2p, words_per_row(W+2p)).  n_exact_u64 (device, zeroed here) receives the
 // number of voxels that needed the exact float64 evaluation.
 extern "C" int t3d_field_sign(const void* occ_bits, int Z, int H, int W, int pad, const double* weights3, void* sign_bits,
@@ -620,68 +246,18 @@ extern "C" int t3d_field_sign(const void* occ_bits, int Z, int H, int W, int pad
 {
     if (Z <= 0 || H <= 0 || W <= 0) { t3d_set_error("t3d_field_sign: empty volume"); return 2; }
     cudaStream_t st = (cudaStream_t)stream;
-    const OccView v = make_view(occ_bits, Z, H, W, pad, 1, weights3);
+    const OccView v = t3d_make_view(occ_bits, Z, H, W, pad, 1, weights3);
     const int nwp = t3d_wpr(v.Wp);
-    const int64_t total = (int64_t)v.Zp * v.Hp * nwp;
     T3D_CUDA(cudaMemsetAsync(n_exact_u64, 0, 8, st));
-    k_field_sign<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(v, (uint32_t*)sign_bits, nwp, (unsigned long long*)n_exact_u64);
+    const int nwp4 = nwp / 4, lanes_x = nwp4 < 256 ? nwp4 : 256, pzb = 256 / lanes_x;
+    dim3 grid((nwp4 + lanes_x - 1) / lanes_x, (v.Hp + FY - 1) / FY, (v.Zp + pzb - 1) / pzb);
+    k_field_sign<<<grid, 256, 0, st>>>(v, (uint32_t*)sign_bits, nwp, lanes_x, pzb, (unsigned long long*)n_exact_u64);
     T3D_CHECK_LAUNCH("t3d_field_sign");
     t3d_count_launches(1);
     return 0;
 }
 
 // rowcnt: 4 * Zs*Hs uint32 (x-edge, y-edge, z-edge vertex counts and triangle counts per voxel row)
-extern "C" int t3d_mc_count(const void* sign_bits, int Zs, int Hs, int Ws, void* rowcnt_u32, void* n_ambiguous_u64,
-                            void* stream)
-{
-    if (Zs <= 0 || Hs <= 0 || Ws <= 0) { t3d_set_error("t3d_mc_count: empty volume"); return 2; }
-    if (ensure_luts()) return 1;
-    cudaStream_t st = (cudaStream_t)stream;
-    const int64_t rows = (int64_t)Zs * Hs;
-    T3D_CUDA(cudaMemsetAsync(n_ambiguous_u64, 0, 8, st));
-    k_mc_count<<<(unsigned)((rows * 32 + 255) / 256), 256, 0, st>>>((const uint32_t*)sign_bits, Zs, Hs, Ws, t3d_wpr(Ws),
-                                                                    (uint32_t*)rowcnt_u32, rows,
-                                                                    (unsigned long long*)n_ambiguous_u64);
-    T3D_CHECK_LAUNCH("t3d_mc_count");
-    t3d_count_launches(1);
-    return 0;
-}
-
-// rowbase: the exclusive scans of rowcnt (4 arrays); n_x / n_y: totals of the x- and y-edge counts.
-// occ_*: the occupancy the sign volume was derived from (pad/gaussian as in t3d_field_sign; gaussian = 0
-// means the sign volume IS the occupancy and pad must be 0).
-// cum/adj: device float64 arrays for the variable-slice-depth z map (n_cum = 0 disables it).
-extern "C" int t3d_mc_emit(const void* sign_bits, const void* occ_bits, int Z, int H, int W, int pad, int gaussian,
-                           const double* weights3, const void* rowbase_u32, uint32_t n_x, uint32_t n_y, int unpad_shift,
-                           const void* cum_f64, const void* adj_f64, int n_cum, double mm_per_pixel_y, double mm_per_pixel_x,
-                           int scale_in_f64, void* verts_f32, void* faces_i32, void* stream)
-{
-    if (Z <= 0 || H <= 0 || W <= 0) { t3d_set_error("t3d_mc_emit: empty volume"); return 2; }
-    if (!gaussian && pad) { t3d_set_error("t3d_mc_emit: pad requires gaussian"); return 2; }
-    if (ensure_luts()) return 1;
-    EmitParams p;
-    p.occ = make_view(occ_bits, Z, H, W, pad, gaussian, weights3);
-    p.sign = (const uint32_t*)sign_bits;
-    p.nwp = t3d_wpr(p.occ.Wp);
-    p.n_rows = (int64_t)p.occ.Zp * p.occ.Hp;
-    p.rowbase = (const uint32_t*)rowbase_u32;
-    p.offY = n_x;
-    p.offZ = n_x + n_y;
-    p.shift = unpad_shift ? 1.0f : 0.0f;
-    p.cum = (const double*)cum_f64;
-    p.adj = (const double*)adj_f64;
-    p.n_cum = n_cum;
-    p.mm_y = mm_per_pixel_y;
-    p.mm_x = mm_per_pixel_x;
-    p.scale_f64 = scale_in_f64 ? 1 : 0;
-    p.verts = (float*)verts_f32;
-    p.faces = (int32_t*)faces_i32;
-    k_mc_emit<<<(unsigned)((p.n_rows + EM_WARPS - 1) / EM_WARPS), EM_WARPS * 32, 0, (cudaStream_t)stream>>>(p);
-    T3D_CHECK_LAUNCH("t3d_mc_emit");
-    t3d_count_launches(1);
-    return 0;
-}
-
 // float32 field of the whole padded grid (test / debugging aid: lets the parity tests compare the field
 // itself with scipy bit for bit)
 __global__ void __launch_bounds__(256) k_field_dense(OccView v, float* __restrict__ out)
@@ -698,7 +274,7 @@ extern "C" int t3d_field_dense(const void* occ_bits, int Z, int H, int W, int pa
                                void* out_f32, void* stream)
 {
     if (Z <= 0 || H <= 0 || W <= 0) { t3d_set_error("t3d_field_dense: empty volume"); return 2; }
-    const OccView v = make_view(occ_bits, Z, H, W, pad, gaussian, weights3);
+    const OccView v = t3d_make_view(occ_bits, Z, H, W, pad, gaussian, weights3);
     const int64_t total = (int64_t)v.Zp * v.Hp * v.Wp;
     k_field_dense<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(v, (float*)out_f32);
     T3D_CHECK_LAUNCH("t3d_field_dense");
@@ -871,13 +447,13 @@ extern "C" int t3d_mesh_canonicalize(const void* verts_in, int64_t V, const void
     }
     const uint32_t* perm = pin;
     k_unique_heads<<<gv, 256, 0, st>>>(vin, perm, V, flags);
-    if (t3d_exclusive_scan_u32(flags, pos, V, 1, 0, totals, scan_ws, stream)) return 1;
+    if (t3d_exclusive_scan_u32(flags, pos, V, 1, 0, 0, totals, scan_ws, stream)) return 1;
     T3D_CUDA(cudaMemcpyAsync(counts, totals, 8, cudaMemcpyDeviceToDevice, st));
     k_scatter_unique<<<gv, 256, 0, st>>>(vin, perm, flags, pos, V, (float*)verts_out, newid);
     if (F > 0) {
         const unsigned gf = (unsigned)((F + 255) / 256);
         k_face_valid<<<gf, 256, 0, st>>>((const int32_t*)faces_in, F, newid, flags);
-        if (t3d_exclusive_scan_u32(flags, pos, F, 1, 0, totals, scan_ws, stream)) return 1;
+        if (t3d_exclusive_scan_u32(flags, pos, F, 1, 0, 0, totals, scan_ws, stream)) return 1;
         T3D_CUDA(cudaMemcpyAsync(counts + 1, totals, 8, cudaMemcpyDeviceToDevice, st));
         k_face_compact<<<gf, 256, 0, st>>>((const int32_t*)faces_in, F, newid, flags, pos, (long long*)faces_out_i64,
                                            (int32_t*)faces_out_i32);

@@ -86,7 +86,7 @@ extern "C" int t3d_pack_masks(const void* masks_u8, int Z, int H, int W, int thr
     cudaStream_t st = (cudaStream_t)stream;
     const int wpr = t3d_wpr(W);
     const int64_t rows = (int64_t)Z * H;
-    if ((W & 31) == 0 && ((uintptr_t)masks_u8 & 15) == 0 && threshold >= 1 && threshold <= 255) {
+    if ((W & 127) == 0 && ((uintptr_t)masks_u8 & 15) == 0 && threshold >= 1 && threshold <= 255) {
         const int64_t n_words = rows * wpr;
         const uint32_t thr4 = 0x01010101u * (uint32_t)threshold;
         int64_t blocks = (n_words / 32 + 7) / 8;           // one warp-iteration per 32 words
@@ -151,7 +151,7 @@ extern "C" int t3d_unpack_bits(const void* bits, int Z, int H, int W, void* out_
     const int wpr = t3d_wpr(W);
     const int64_t rows = (int64_t)Z * H;
     const int64_t n = rows * wpr;
-    if ((W & 31) == 0 && ((uintptr_t)out_u8 & 15) == 0) {
+    if ((W & 127) == 0 && ((uintptr_t)out_u8 & 15) == 0) {
         int64_t blocks = ((n + 31) / 32 + 7) / 8;
         const int64_t cap = (int64_t)T3D_NUM_SMS * 16;
         if (blocks > cap) blocks = cap;
@@ -355,33 +355,41 @@ extern "C" int t3d_fill_holes_2d(void* bits, int n_planes, int64_t plane_stride_
 // (voxel_processor.py:72-75; the np.any guards are redundant and the loop is not a recurrence,
 // SURVEY.md V3).  `lo` / `hi` are optional neighbour planes for z-slab sharding: when given, local
 // plane 0 / Z-1 is an interior plane of the global stack and uses them as f[-1] / f[Z].
-// Optionally accumulates per-slice popcounts of the result.
+// Optionally accumulates per-slice popcounts of the result.  128-bit accesses, two per thread in flight.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_gap_fill(const uint32_t* __restrict__ in, uint32_t* __restrict__ out,
-                                                  const uint32_t* __restrict__ lo, const uint32_t* __restrict__ hi,
-                                                  int Z, int64_t pw, unsigned long long* __restrict__ counts)
+__global__ void __launch_bounds__(256) k_gap_fill(const uint4* __restrict__ in, uint4* __restrict__ out,
+                                                  const uint4* __restrict__ lo, const uint4* __restrict__ hi, int Z,
+                                                  int64_t pw4, unsigned long long* __restrict__ counts)
 {
     const int z = blockIdx.y;
-    const uint32_t* c = in + (int64_t)z * pw;
-    const uint32_t* a = (z > 0) ? c - pw : lo;
-    const uint32_t* b = (z < Z - 1) ? c + pw : hi;
-    uint32_t* o = out + (int64_t)z * pw;
-    unsigned long long cnt = 0;
+    const uint4* c = in + (int64_t)z * pw4;
+    const uint4* a = (z > 0) ? c - pw4 : lo;
+    const uint4* b = (z < Z - 1) ? c + pw4 : hi;
+    uint4* o = out + (int64_t)z * pw4;
+    uint32_t cnt = 0;
     const bool fill = (a != nullptr) && (b != nullptr);
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < pw; i += (int64_t)gridDim.x * blockDim.x) {
-        uint32_t v = c[i];
-        if (fill) v |= a[i] & b[i];
-        o[i] = v;
-        cnt += __popc(v);
+    const int64_t stride = (int64_t)gridDim.x * 256;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < pw4; i += 2 * stride) {
+        const int64_t j = i + stride;
+        const bool two = j < pw4;
+        uint4 v0 = c[i], v1 = two ? c[j] : make_uint4(0, 0, 0, 0);
+        if (fill) {
+            const uint4 a0 = a[i], b0 = b[i];
+            v0 = or4(v0, and4(a0, b0));
+            if (two) { const uint4 a1 = a[j], b1 = b[j]; v1 = or4(v1, and4(a1, b1)); }
+        }
+        o[i] = v0;
+        if (two) o[j] = v1;
+        cnt += popc4(v0) + popc4(v1);
     }
     if (counts) {
         cnt = warp_sum(cnt);
-        __shared__ unsigned long long s[8];
+        __shared__ uint32_t s[8];
         if (lane_id() == 0) s[threadIdx.x >> 5] = cnt;
         __syncthreads();
         if (threadIdx.x == 0) {
             unsigned long long t = 0;
-            for (int k = 0; k < (int)(blockDim.x >> 5); ++k) t += s[k];
+            for (int k = 0; k < 8; ++k) t += s[k];
             if (t) atomicAdd(counts + z, t);
         }
     }
@@ -392,113 +400,120 @@ extern "C" int t3d_gap_fill(const void* in_bits, void* out_bits, const void* lo_
 {
     if (Z <= 0 || H <= 0 || W <= 0) { t3d_set_error("t3d_gap_fill: empty volume"); return 2; }
     cudaStream_t st = (cudaStream_t)stream;
-    const int64_t pw = (int64_t)H * t3d_wpr(W);
+    const int64_t pw4 = (int64_t)H * (t3d_wpr(W) / 4);
     if (slice_counts_u64) T3D_CUDA(cudaMemsetAsync(slice_counts_u64, 0, sizeof(unsigned long long) * Z, st));
-    int bx = (int)min((int64_t)64, (pw + 255) / 256);
+    int bx = (int)min((int64_t)32, (pw4 + 511) / 512);
     dim3 grid(bx, Z);
-    k_gap_fill<<<grid, 256, 0, st>>>((const uint32_t*)in_bits, (uint32_t*)out_bits, (const uint32_t*)lo_plane,
-                                     (const uint32_t*)hi_plane, Z, pw, (unsigned long long*)slice_counts_u64);
+    k_gap_fill<<<grid, 256, 0, st>>>((const uint4*)in_bits, (uint4*)out_bits, (const uint4*)lo_plane, (const uint4*)hi_plane, Z,
+                                     pw4, (unsigned long long*)slice_counts_u64);
     T3D_CHECK_LAUNCH("t3d_gap_fill");
     t3d_count_launches(1);
     return 0;
 }
 
 // ------------------------------------------------------------------------------------------------
-// 6-connected binary morphology, up to 4 fused stages per launch through a shared-memory tile with a
-// halo of one voxel per stage.  Stage s is an erosion (bit s of erode_mask set; out-of-volume = 1) or
-// a dilation (out-of-volume = 0): exactly skimage's binary_erosion / binary_dilation with the default
-// cross footprint.  opening∘closing = stages E,D,D,E = erode_mask 0b1001.
+// 6-connected binary morphology.  Stage s of a call is an erosion (bit s of erode_mask set; out-of-volume = 1)
+// or a dilation (out-of-volume = 0): exactly skimage's binary_erosion / binary_dilation with the default cross
+// footprint.  opening then closing = stages E,D,D,E = erode_mask 0b1001.
+//
+// One launch per stage.  The packed volume is 1/8 byte per voxel (67 MB at 512x1024x1024: L2 resident on a B200),
+// so a stage is bound by instruction issue and load latency, not HBM.  A thread owns one uint4 column (128 voxels)
+// of one plane and marches down MY rows with the y neighbours in a register window: per 128 output voxels it issues
+// 3 x 128-bit loads (next row, z-1, z+1) + 2 scalar loads (x neighbours, L1 hits), 8 funnel shifts and 12 LOP3.
 // ------------------------------------------------------------------------------------------------
-#define MT_Z 8
-#define MT_Y 16
-#define MT_XW 8
-#define MT_MAXR 4
-#define MT_SZ (MT_Z + 2 * MT_MAXR)
-#define MT_SY (MT_Y + 2 * MT_MAXR)
-#define MT_SX (MT_XW + 2)
-#define MT_THREADS 256
+#define MY 16
 
-__global__ void __launch_bounds__(MT_THREADS) k_morph(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, int Z,
-                                                      int H, int W, int nw, int nst, uint32_t erode_mask,
-                                                      unsigned long long* __restrict__ counts)
+template <bool ER>
+__global__ void __launch_bounds__(256) k_morph4(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, int Z, int H,
+                                                int W, int nw, int lanes_x, int pz_per_block,
+                                                unsigned long long* __restrict__ counts)
 {
-    __shared__ uint32_t buf[2][MT_SZ][MT_SY][MT_SX];
-    const int R = nst;
-    const int z0 = blockIdx.z * MT_Z - R, y0 = blockIdx.y * MT_Y - R, w0 = blockIdx.x * MT_XW - 1;
-    const int SZ = MT_Z + 2 * R, SY = MT_Y + 2 * R;
-    const int n_tile = SZ * SY * MT_SX;
-    const int tid = threadIdx.x;
-
-    for (int i = tid; i < n_tile; i += MT_THREADS) {
-        const int xw = i % MT_SX, t = i / MT_SX, yy = t % SY, zz = t / SY;
-        const int gz = z0 + zz, gy = y0 + yy, gw = w0 + xw;
-        uint32_t v = 0;
-        if (gz >= 0 && gz < Z && gy >= 0 && gy < H && gw >= 0 && gw < nw) v = in[((int64_t)gz * H + gy) * nw + gw];
-        buf[0][zz][yy][xw] = v;
-    }
-    __syncthreads();
-
-    int cur = 0;
-    for (int s = 0; s < nst; ++s) {
-        const bool er = (erode_mask >> s) & 1u;
-        const uint32_t B = er ? 0xffffffffu : 0u;
-        // positions computed by this stage: shrink by s+1 in z and y
-        const int lo = s + 1;
-        const int cz = SZ - 2 * lo, cy = SY - 2 * lo;
-        const int n = cz * cy * MT_SX;
-        for (int i = tid; i < n; i += MT_THREADS) {
-            const int xw = i % MT_SX, t = i / MT_SX, yy = lo + t % cy, zz = lo + t / cy;
-            const int gz = z0 + zz, gy = y0 + yy, gw = w0 + xw;
-            // source fetch with this stage's border value outside the volume
-            auto src = [&](int dz, int dy, int dxw) -> uint32_t {
-                const int az = gz + dz, ay = gy + dy, aw = gw + dxw;
-                if (az < 0 || az >= Z || ay < 0 || ay >= H || aw < 0 || aw >= nw) return B;
-                const int sx = xw + dxw;
-                if (sx < 0 || sx >= MT_SX) return B;  // outside the tile: only feeds halo garbage
-                const uint32_t vm = valid_mask(aw, W);
-                return (buf[cur][zz + dz][yy + dy][sx] & vm) | (B & ~vm);
-            };
-            const uint32_t c = src(0, 0, 0), l = src(0, 0, -1), r = src(0, 0, 1);
-            const uint32_t xm = (c << 1) | (l >> 31), xp = (c >> 1) | (r << 31);
-            const uint32_t zm = src(-1, 0, 0), zp = src(1, 0, 0), ym = src(0, -1, 0), yp = src(0, 1, 0);
-            uint32_t v = er ? (c & xm & xp & zm & zp & ym & yp) : (c | xm | xp | zm | zp | ym | yp);
-            buf[cur ^ 1][zz][yy][xw] = v;
-        }
+    constexpr uint32_t B = ER ? 0xffffffffu : 0u;
+    const int lx = threadIdx.x % lanes_x, pz = threadIdx.x / lanes_x;
+    const int nw4 = nw >> 2, nwv = (W + 31) >> 5;
+    const int w4 = blockIdx.x * lanes_x + lx, z = blockIdx.z * pz_per_block + pz, y0 = blockIdx.y * MY;
+    extern __shared__ unsigned int s_cnt[];
+    if (counts) {
+        if ((int)threadIdx.x < pz_per_block) s_cnt[threadIdx.x] = 0;
         __syncthreads();
-        cur ^= 1;
     }
-
-    // write the central tile (a warp covers 32 consecutive words of one z plane: MT_Y*MT_XW = 128 per plane)
-    for (int i = tid; i < MT_Z * MT_Y * MT_XW; i += MT_THREADS) {
-        const int xw = i % MT_XW, t = i / MT_XW, yy = t % MT_Y, zz = t / MT_Y;
-        const int gz = z0 + R + zz, gy = y0 + R + yy, gw = w0 + 1 + xw;
-        uint32_t pc = 0;
-        if (gz < Z && gy < H && gw < nw) {
-            const uint32_t v = buf[cur][R + zz][R + yy][1 + xw] & valid_mask(gw, W);
-            out[((int64_t)gz * H + gy) * nw + gw] = v;
-            pc = __popc(v);
+    uint32_t cnt = 0;
+    if (pz < pz_per_block && w4 < nw4 && z < Z) {
+        const uint4 vm = valid_mask4(w4, W);
+        // words beyond the volume (tail bits, padding words) read as the border value of this stage
+        const bool fix = ER && (4 * w4 + 4 > (W >> 5));
+        auto row4 = [&](int zz, int yy) -> uint4 {
+            uint4 v = *reinterpret_cast<const uint4*>(in + ((int64_t)zz * H + yy) * nw + 4 * w4);
+            if (fix) v = make_uint4(v.x | ~vm.x, v.y | ~vm.y, v.z | ~vm.z, v.w | ~vm.w);
+            return v;
+        };
+        const bool has_l = (w4 > 0), has_r = (4 * w4 + 4 < nwv);
+        const uint4 B4 = splat4(B);
+        uint4 prev = (y0 > 0) ? row4(z, y0 - 1) : B4;
+        uint4 cur = row4(z, y0);
+        const int y1 = min(H, y0 + MY);
+#pragma unroll 4
+        for (int y = y0; y < y1; ++y) {
+            const uint4 next = (y + 1 < H) ? row4(z, y + 1) : B4;
+            const uint4 zm = (z > 0) ? row4(z - 1, y) : B4;
+            const uint4 zp = (z + 1 < Z) ? row4(z + 1, y) : B4;
+            const uint32_t* rowp = in + ((int64_t)z * H + y) * nw + 4 * w4;
+            const uint32_t l = has_l ? rowp[-1] : B;
+            uint32_t r = has_r ? rowp[4] : B;
+            if (ER && has_r && 4 * w4 + 5 >= nwv) r |= ~valid_mask(4 * w4 + 4, W);  // right neighbour is the partial last word
+            const uint4 xm = shl1_4(cur, l), xp = shr1_4(cur, r);
+            uint4 v;
+            if (ER) v = and4(and4(and4(cur, xm), and4(xp, prev)), and4(and4(next, zm), zp));
+            else v = or4(or4(or4(cur, xm), or4(xp, prev)), or4(or4(next, zm), zp));
+            v = and4(v, vm);
+            *reinterpret_cast<uint4*>(out + ((int64_t)z * H + y) * nw + 4 * w4) = v;
+            cnt += popc4(v);
+            prev = cur;
+            cur = next;
         }
-        if (counts) {
-            pc = warp_sum(pc);
-            if (lane_id() == 0 && pc) atomicAdd(counts + gz, (unsigned long long)pc);
-        }
+        if (counts && cnt) atomicAdd(&s_cnt[pz], cnt);
+    }
+    if (counts) {
+        __syncthreads();
+        const int zz = blockIdx.z * pz_per_block + threadIdx.x;
+        if ((int)threadIdx.x < pz_per_block && zz < Z && s_cnt[threadIdx.x])
+            atomicAdd(counts + zz, (unsigned long long)s_cnt[threadIdx.x]);
     }
 }
 
+extern "C" int64_t t3d_morph_scratch_bytes(int Z, int H, int W, int n_stages)
+{
+    return n_stages > 1 ? (int64_t)Z * H * t3d_wpr(W) * 4 * (n_stages > 2 ? 2 : 1) : 0;
+}
+
+// scratch: t3d_morph_scratch_bytes (intermediate stages ping-pong there); in/out must not alias.
 extern "C" int t3d_morph(const void* in_bits, void* out_bits, int Z, int H, int W, int n_stages, unsigned erode_mask,
-                         void* slice_counts_u64, void* stream)
+                         void* slice_counts_u64, void* scratch, void* stream)
 {
     if (Z <= 0 || H <= 0 || W <= 0) { t3d_set_error("t3d_morph: empty volume"); return 2; }
-    if (n_stages < 1 || n_stages > MT_MAXR) { t3d_set_error("t3d_morph: n_stages must be 1..4"); return 2; }
+    if (n_stages < 1 || n_stages > 32) { t3d_set_error("t3d_morph: n_stages must be 1..32"); return 2; }
     if (in_bits == out_bits) { t3d_set_error("t3d_morph: in-place is not supported"); return 2; }
+    if (n_stages > 1 && !scratch) { t3d_set_error("t3d_morph: scratch required for more than one stage"); return 2; }
     cudaStream_t st = (cudaStream_t)stream;
-    const int nw = t3d_wpr(W);
+    const int nw = t3d_wpr(W), nw4 = nw / 4;
+    const int64_t vol_words = (int64_t)Z * H * nw;
     if (slice_counts_u64) T3D_CUDA(cudaMemsetAsync(slice_counts_u64, 0, sizeof(unsigned long long) * Z, st));
-    dim3 grid((nw + MT_XW - 1) / MT_XW, (H + MT_Y - 1) / MT_Y, (Z + MT_Z - 1) / MT_Z);
-    k_morph<<<grid, MT_THREADS, 0, st>>>((const uint32_t*)in_bits, (uint32_t*)out_bits, Z, H, W, nw, n_stages, erode_mask,
-                                         (unsigned long long*)slice_counts_u64);
+    const int lanes_x = nw4 < 256 ? nw4 : 256;
+    const int pzb = 256 / lanes_x;
+    dim3 grid((nw4 + lanes_x - 1) / lanes_x, (H + MY - 1) / MY, (Z + pzb - 1) / pzb);
+    const size_t smem = sizeof(unsigned int) * pzb;
+    uint32_t* tmp[2] = {(uint32_t*)scratch, (uint32_t*)scratch + vol_words};
+    const uint32_t* src = (const uint32_t*)in_bits;
+    for (int s = 0; s < n_stages; ++s) {
+        const bool last = (s == n_stages - 1);
+        uint32_t* dst = last ? (uint32_t*)out_bits : tmp[s & 1];
+        unsigned long long* cnt = last ? (unsigned long long*)slice_counts_u64 : nullptr;
+        if ((erode_mask >> s) & 1u) k_morph4<true><<<grid, 256, smem, st>>>(src, dst, Z, H, W, nw, lanes_x, pzb, cnt);
+        else k_morph4<false><<<grid, 256, smem, st>>>(src, dst, Z, H, W, nw, lanes_x, pzb, cnt);
+        src = dst;
+    }
     T3D_CHECK_LAUNCH("t3d_morph");
-    t3d_count_launches(1);
+    t3d_count_launches(n_stages);
     return 0;
 }
 
@@ -513,33 +528,38 @@ __global__ void k_stats_init(unsigned long long* counts, int Z, int* bbox)
     if (bbox && i < 6) bbox[i] = (i & 1) ? -1 : 0x7fffffff;
 }
 
+#define ST_YSPLIT 4
+
 __global__ void __launch_bounds__(256) k_stats(const uint32_t* __restrict__ bits, int H, int nw,
                                                unsigned long long* __restrict__ counts, int* __restrict__ bbox)
 {
-    const int z = blockIdx.y;
-    const int64_t pw = (int64_t)H * nw;
-    const uint32_t* p = bits + (int64_t)z * pw;
+    const int z = blockIdx.z;
+    const int w = blockIdx.x * 32 + threadIdx.x;
+    const int rows_per = (H + ST_YSPLIT - 1) / ST_YSPLIT;
+    const int ya = blockIdx.y * rows_per, yb = min(H, ya + rows_per);
+    const uint32_t* p = bits + (int64_t)z * H * nw;
     unsigned long long cnt = 0;
     int ymin = 0x7fffffff, ymax = -1, xmin = 0x7fffffff, xmax = -1;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < pw; i += (int64_t)gridDim.x * blockDim.x) {
-        const uint32_t v = p[i];
-        if (v) {
-            cnt += __popc(v);
-            const int y = (int)(i / nw), w = (int)(i - (int64_t)y * nw);
-            ymin = min(ymin, y); ymax = max(ymax, y);
-            xmin = min(xmin, (w << 5) + __ffs(v) - 1);
-            xmax = max(xmax, (w << 5) + 31 - __clz(v));
+    if (w < nw) {
+        for (int y = ya + threadIdx.y; y < yb; y += 8) {
+            const uint32_t v = p[(int64_t)y * nw + w];
+            if (v) {
+                cnt += __popc(v);
+                ymin = min(ymin, y); ymax = max(ymax, y);
+                xmin = min(xmin, (w << 5) + __ffs(v) - 1);
+                xmax = max(xmax, (w << 5) + 31 - __clz(v));
+            }
         }
     }
     cnt = warp_sum(cnt);
     ymin = warp_min(ymin); xmin = warp_min(xmin); ymax = warp_max(ymax); xmax = warp_max(xmax);
     __shared__ unsigned long long sc[8];
     __shared__ int sb[8][4];
-    const int wi = threadIdx.x >> 5;
-    if (lane_id() == 0) { sc[wi] = cnt; sb[wi][0] = ymin; sb[wi][1] = ymax; sb[wi][2] = xmin; sb[wi][3] = xmax; }
+    const int wi = threadIdx.y;
+    if (threadIdx.x == 0) { sc[wi] = cnt; sb[wi][0] = ymin; sb[wi][1] = ymax; sb[wi][2] = xmin; sb[wi][3] = xmax; }
     __syncthreads();
-    if (threadIdx.x == 0) {
-        for (int k = 1; k < (int)(blockDim.x >> 5); ++k) {
+    if (threadIdx.x == 0 && threadIdx.y == 0) {
+        for (int k = 1; k < 8; ++k) {
             cnt += sc[k]; ymin = min(ymin, sb[k][0]); ymax = max(ymax, sb[k][1]);
             xmin = min(xmin, sb[k][2]); xmax = max(xmax, sb[k][3]);
         }
@@ -562,10 +582,8 @@ extern "C" int t3d_volume_stats(const void* bits, int Z, int H, int W, void* sli
     const int nw = t3d_wpr(W);
     const int n_init = Z > 6 ? Z : 6;
     k_stats_init<<<(n_init + 255) / 256, 256, 0, st>>>((unsigned long long*)slice_counts_u64, Z, (int*)bbox_i32x6);
-    const int64_t pw = (int64_t)H * nw;
-    int bx = (int)min((int64_t)32, (pw + 255) / 256);
-    dim3 grid(bx, Z);
-    k_stats<<<grid, 256, 0, st>>>((const uint32_t*)bits, H, nw, (unsigned long long*)slice_counts_u64, (int*)bbox_i32x6);
+    dim3 grid((nw + 31) / 32, ST_YSPLIT, Z), block(32, 8);
+    k_stats<<<grid, block, 0, st>>>((const uint32_t*)bits, H, nw, (unsigned long long*)slice_counts_u64, (int*)bbox_i32x6);
     T3D_CHECK_LAUNCH("t3d_volume_stats");
     t3d_count_launches(2);
     return 0;

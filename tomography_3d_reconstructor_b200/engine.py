@@ -42,7 +42,8 @@ def _p(t: Optional[torch.Tensor]) -> Optional[ctypes.c_void_p]:
 
 
 def words_per_row(W: int) -> int:
-    return (W + 31) // 32
+    """Row stride in 32-bit words: ceil(W/32) rounded up to a multiple of 4 (16-byte aligned rows)."""
+    return (((W + 31) // 32) + 3) & ~3
 
 
 # scipy.ndimage._filters._gaussian_kernel1d(sigma=0.5, order=0, radius=2), restated with numpy so the three
@@ -259,25 +260,21 @@ def morph_stages(iterations: int, create_manifold: bool) -> List[bool]:
 def morph(dv: DeviceVolume, stages: Sequence[bool], want_counts: bool = True) -> DeviceVolume:
     L = _L()
     Z, H, W = dv.shape
-    cur = dv.bits
-    counts = None
+    stages = list(stages)
     if not stages:
-        return DeviceVolume(cur.clone(), Z, H, W, None)
-    i = 0
-    while i < len(stages):
-        chunk = list(stages[i:i + 4])
-        i += len(chunk)
-        mask = 0
-        for s, er in enumerate(chunk):
-            if er:
-                mask |= 1 << s
-        out = torch.empty_like(cur)
-        last = i >= len(stages)
-        if last and want_counts:
-            counts = torch.empty(Z, dtype=torch.int64, device=cur.device)
-        check(L.t3d_morph(_p(cur), _p(out), Z, H, W, len(chunk), mask, _p(counts) if last else None, _stream()), "t3d_morph")
-        cur = out
-    return DeviceVolume(cur, Z, H, W, counts)
+        return DeviceVolume(dv.bits.clone(), Z, H, W, None)
+    if len(stages) > 32:
+        raise ValueError("at most 32 morphology stages per call")
+    mask = 0
+    for s, er in enumerate(stages):
+        if er:
+            mask |= 1 << s
+    out = torch.empty_like(dv.bits)
+    counts = torch.empty(Z, dtype=torch.int64, device=out.device) if want_counts else None
+    nb = int(L.t3d_morph_scratch_bytes(Z, H, W, len(stages)))
+    scratch = torch.empty(nb // 4, dtype=torch.int32, device=out.device) if nb else None
+    check(L.t3d_morph(_p(dv.bits), _p(out), Z, H, W, len(stages), mask, _p(counts), _p(scratch), _stream()), "t3d_morph")
+    return DeviceVolume(out, Z, H, W, counts)
 
 
 def smooth(dv: DeviceVolume, iterations: int = 3, create_manifold: bool = True) -> DeviceVolume:
@@ -306,12 +303,13 @@ def field_sign(dv: DeviceVolume, pad: int) -> Tuple[torch.Tensor, Tuple[int, int
     return sign, (Zp, Hp, Wp), n_exact
 
 
-def exclusive_scan_u32(x: torch.Tensor, n: int, n_arrays: int, out_u64: bool = False):
+def exclusive_scan_u32(x: torch.Tensor, n: int, n_arrays: int, out_u64: bool = False, popcount_input: bool = False):
     L = _L()
     ws = torch.empty(int(L.t3d_scan_workspace_bytes(n, n_arrays)) // 8 + 1, dtype=torch.int64, device=x.device)
     totals = torch.empty(n_arrays, dtype=torch.int64, device=x.device)
     out = torch.empty(n * n_arrays, dtype=torch.int64 if out_u64 else torch.int32, device=x.device)
-    check(L.t3d_exclusive_scan_u32(_p(x), _p(out), n, n_arrays, 1 if out_u64 else 0, _p(totals), _p(ws), _stream()),
+    check(L.t3d_exclusive_scan_u32(_p(x), _p(out), n, n_arrays, 1 if out_u64 else 0, 1 if popcount_input else 0,
+                                   _p(totals), _p(ws), _stream()),
           "t3d_exclusive_scan_u32")
     return out, totals
 
@@ -332,32 +330,44 @@ def extract_surface(dv: DeviceVolume, slice_depths, mm_per_pixel_y, mm_per_pixel
     else:
         sign, (Zs, Hs, Ws), n_exact_t = dv.bits, (Z, H, W), None
     mark("field_sign")
-    rows = Zs * Hs
-    rowcnt = torch.empty(4 * rows, dtype=torch.int32, device=dev)
+    n_chunks = int(L.t3d_mc_num_chunks(Zs, Hs, Ws))
+    ballots = torch.empty(n_chunks, dtype=torch.int32, device=dev)
+    check(L.t3d_mc_flags(_p(sign), Zs, Hs, Ws, _p(ballots), _stream()), "t3d_mc_flags")
+    chunkbase, n_act_t = exclusive_scan_u32(ballots, n_chunks, 1, popcount_input=True)
+    mark("mc_flags")
+    n_active = int(n_act_t.cpu().item())
+    if n_active == 0:
+        # skimage: ValueError (level outside the data range) or RuntimeError (no surface)
+        raise RuntimeError("No surface found at the given iso value.")
+    aw_idx = torch.empty(n_active, dtype=torch.int32, device=dev)
+    aw_cnt = torch.empty(4 * n_active, dtype=torch.int32, device=dev)
     n_amb = torch.empty(1, dtype=torch.int64, device=dev)
-    check(L.t3d_mc_count(_p(sign), Zs, Hs, Ws, _p(rowcnt), _p(n_amb), _stream()), "t3d_mc_count")
-    mark("mc_count")
-    rowbase, totals = exclusive_scan_u32(rowcnt, rows, 4)
-    mark("scan")
+    check(L.t3d_mc_words(_p(sign), Zs, Hs, Ws, _p(ballots), _p(chunkbase), n_active, _p(aw_idx), _p(aw_cnt), _p(n_amb),
+                         _stream()), "t3d_mc_words")
+    aw_base, totals = exclusive_scan_u32(aw_cnt, n_active, 4)
+    mark("mc_words")
     tail = torch.cat([totals, n_amb, n_exact_t if n_exact_t is not None else torch.zeros_like(n_amb)]).cpu().tolist()
     nX, nY, nZ, nT, n_ambiguous, n_exact = (int(v) for v in tail)
     V = nX + nY + nZ
     if nT == 0 or V == 0:
-        # skimage: ValueError (level outside the data range) or RuntimeError (no surface)
         raise RuntimeError("No surface found at the given iso value.")
     if V >= 2 ** 31 or nT >= 2 ** 31:
         raise T3DError("mesh too large for one device (V=%d, F=%d)" % (V, nT))
     verts = torch.empty((V, 3), dtype=torch.float32, device=dev)
     faces = torch.empty((nT, 3), dtype=torch.int32, device=dev)
+    vkeys = torch.empty(V, dtype=torch.int64, device=dev)
     cum, adj = z_map_arrays(slice_depths, add_padding)
     n_cum = len(cum)
     cum_d = torch.from_numpy(cum).to(dev) if n_cum else None
     adj_d = torch.from_numpy(adj).to(dev) if n_cum else None
     strong = isinstance(mm_per_pixel_y, np.floating) or isinstance(mm_per_pixel_x, np.floating)
-    check(L.t3d_mc_emit(_p(sign), _p(dv.bits), Z, H, W, pad, gaussian, _W3_C, _p(rowbase), nX, nY, 1 if manifold else 0,
-                        _p(cum_d), _p(adj_d), n_cum, float(mm_per_pixel_y), float(mm_per_pixel_x), 1 if strong else 0,
-                        _p(verts), _p(faces), _stream()), "t3d_mc_emit")
+    check(L.t3d_mc_emit(_p(sign), Zs, Hs, Ws, _p(ballots), _p(chunkbase), _p(aw_idx), _p(aw_base), n_active, nX, nY,
+                        _p(vkeys), _p(faces), _stream()), "t3d_mc_emit")
     mark("mc_emit")
+    check(L.t3d_mc_vertices(_p(dv.bits), Z, H, W, pad, gaussian, _W3_C, _p(vkeys), nX, nY, nZ, 1 if manifold else 0,
+                            _p(cum_d), _p(adj_d), n_cum, float(mm_per_pixel_y), float(mm_per_pixel_x), 1 if strong else 0,
+                            _p(verts), _stream()), "t3d_mc_vertices")
+    mark("mc_vertices")
     if canonical is None:
         canonical = manifold
     if not canonical:
