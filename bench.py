@@ -175,7 +175,7 @@ def make_phantom_u8(Z_total, H, W, z0, z1, device):
 
 
 STAGE_BYTES = {  # algorithmic bytes per voxel of each volume-sized stage
-    "pack": 1.0 + 0.125, "close_ends": 0.25, "smooth": 4 * 0.25, "field_sign": 0.25, "mc_flags": 0.125 + 1.0 / 256,
+    "pack_close": 1.0 + 0.125 + 0.25, "smooth": 4 * 0.25, "field_sign": 0.25, "mc_flags": 0.125 + 1.0 / 256,
 }
 
 

@@ -238,3 +238,17 @@ def test_watertight_at_moderate_size(eng, oracle):
     analytic = 4.0 / 3.0 * np.pi * (0.42 * Z) * (0.33 * H) * (0.45 * W)
     assert abs(mv - analytic) / analytic < 5e-3
     assert abs(vc.calculate_voxel_volume(sm, 1.0, 1.0, 1.0) - analytic) / analytic < 5e-3
+
+
+def test_mm_scaling_follows_numpy_promotion(eng, oracle):
+    """`vertices[:, 1] *= mm`: float32 multiply for a python float, float64 multiply for a numpy float64 scalar."""
+    from tomography_3d_reconstructor_b200 import SurfaceExtractor
+    vol = oracle.smooth_voxel_data(oracle.ellipsoid_phantom_u8(20, 40, 60) >= 200, 3, True)
+    depths = oracle.calculate_slice_depths(6.0, 2, 16, 2)
+    se = SurfaceExtractor()
+    for mm_y, mm_x in ((95.03 / 40, 143.1 / 60), (np.float64(95.03 / 40), np.float64(143.1 / 60))):
+        got = se.extract_manifold_surface(vol, depths, mm_y, mm_x)
+        ref = oracle.extract_manifold_surface(vol, depths, mm_y, mm_x)
+        assert np.array_equal(got[0], ref[0]) or np.allclose(got[0], ref[0], rtol=1e-6, atol=0)
+        assert np.array_equal(got[0][:, 0], ref[0][:, 0])       # z map is bit-exact
+        assert np.array_equal(got[1], ref[1])

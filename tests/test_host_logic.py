@@ -1,0 +1,75 @@
+"""Host-side logic of the drop-in classes that needs no GPU, and the no-CPU-fallback guarantee."""
+import numpy as np
+import pytest
+import torch
+
+
+def test_slice_depths_match_reference_semantics(oracle):
+    from tomography_3d_reconstructor_b200 import VoxelProcessor
+    from tomography_3d_reconstructor_b200 import pipeline
+    for sides in ((20, 64, 20), (0, 10, 0), (3, 0, 3), (0, 0, 0), (5, 7, 0), (1, 1, 1)):
+        vp = VoxelProcessor()
+        vp.side_0_count, vp.side_1_count, vp.side_2_count = sides
+        d = vp.calculate_slice_depths(6.0)
+        assert np.array_equal(d, oracle.calculate_slice_depths(6.0, *sides))
+        assert np.array_equal(d, pipeline.slice_depths(6.0, *sides))
+
+
+def test_z_map_arrays_and_stage_lists():
+    from tomography_3d_reconstructor_b200 import engine
+    d = np.array([0.25, 0.5, 0.5, 0.25])
+    cum, adj = engine.z_map_arrays(d, True)
+    assert np.array_equal(adj, [0.25, 0.25, 0.5, 0.5, 0.25, 0.25]) and np.array_equal(cum, np.cumsum([0] + list(adj)))
+    cum, adj = engine.z_map_arrays(d, False)
+    assert np.array_equal(adj, d) and len(cum) == 5
+    assert engine.z_map_arrays([], True)[0].size == 0
+    assert engine.morph_stages(3, True) == [True, False, False, True]
+    assert engine.morph_stages(1, True) == [True, False, False, True]      # closing is idempotent
+    assert engine.morph_stages(0, True) == [True, False]
+    assert engine.morph_stages(3, False) == [False, True]
+    assert engine.morph_stages(0, False) == []
+    assert engine.words_per_row(1024) == 32 and engine.words_per_row(1026) == 36 and engine.words_per_row(5) == 4
+
+
+def test_stack_view_is_zero_copy_for_contiguous_slices():
+    from tomography_3d_reconstructor_b200 import engine
+    base = np.random.default_rng(0).random((6, 5, 8)) < 0.5
+    lst = [base[z] for z in range(6)]
+    st = engine._as_stack(lst)
+    assert st.dtype == np.uint8 and st.shape == (6, 5, 8) and np.array_equal(st.astype(bool), base)
+    assert st.__array_interface__["data"][0] == base.__array_interface__["data"][0]
+    scattered = [base[z].copy() for z in range(6)]
+    assert np.array_equal(engine._as_stack(scattered).astype(bool), base)
+    assert np.array_equal(engine._as_stack([m.astype(np.int32) * 7 for m in lst]).astype(bool), base)
+
+
+def test_variable_depth_volume_order(oracle):
+    from tomography_3d_reconstructor_b200 import pipeline
+    rng = np.random.default_rng(2)
+    vol = rng.random((30, 9, 9)) < 0.5
+    d = oracle.calculate_slice_depths(6.0, 5, 20, 5)
+    counts = vol.reshape(30, -1).sum(axis=1).astype(np.int64)
+    assert pipeline.variable_depth_volume(counts, 0.279, 0.186, d) == oracle.calculate_voxel_volume_variable_depth(vol, 0.279, 0.186, d)
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="only meaningful without a GPU")
+def test_no_cpu_fallback_without_cuda():
+    """The product path must fail loudly, never compute on the CPU."""
+    from tomography_3d_reconstructor_b200 import VoxelProcessor, SurfaceExtractor, VolumeCalculator, engine
+    masks = [np.ones((4, 4), bool)] * 3
+    with pytest.raises(engine.T3DUnavailable):
+        VoxelProcessor().create_voxel_data(masks)
+    with pytest.raises(ValueError, match="Load masks first"):
+        VoxelProcessor().create_voxel_data([])
+    with pytest.raises(engine.T3DUnavailable):   # not swallowed into `None` like ordinary extraction failures
+        SurfaceExtractor().extract_manifold_surface(np.ones((3, 4, 4), bool), np.ones(3), 1.0, 1.0)
+    with pytest.raises(engine.T3DUnavailable):
+        VolumeCalculator().calculate_voxel_volume(np.ones((3, 4, 4), bool), 1.0, 1.0, 1.0)
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    from tomography_3d_reconstructor_b200 import _lib
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(_lib.T3DError, match="no CPU fallback"):
+        _lib.load()

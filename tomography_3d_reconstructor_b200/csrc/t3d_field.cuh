@@ -161,14 +161,34 @@ __device__ __forceinline__ void edge_field_values(const OccView& v, const double
     }
     constexpr int NZ = 5 + (AXIS == 0), NY = 5 + (AXIS == 1);
     unsigned long long col[NY];
+    // un-padded coordinates of the first fetched voxel; interior = the whole fetch lies inside the occupancy volume
+    const int oz0 = z - 2 - v.pad, oy0 = y - 2 - v.pad, ox0 = x - 2 - v.pad;
+    if (oz0 >= 0 && oz0 + NZ <= v.Z && oy0 >= 0 && oy0 + NY <= v.H && ox0 >= 0 && ox0 + 6 <= v.W) {
+        const int w = ox0 >> 5, sh = ox0 & 31;
+        const bool two = sh > 26;  // the 6-bit window straddles two words
+        const uint32_t* p = v.bits + ((int64_t)oz0 * v.H + oy0) * v.nw + w;
+        const int64_t dzs = (int64_t)v.H * v.nw;
 #pragma unroll
-    for (int dy = 0; dy < NY; ++dy) {
-        const int yr = reflect_idx(y - 2 + dy, v.Hp);
-        unsigned long long c = 0;
+        for (int dy = 0; dy < NY; ++dy) {
+            unsigned long long c = 0;
 #pragma unroll
-        for (int dz = 0; dz < NZ; ++dz)
-            c |= (unsigned long long)get6(v, reflect_idx(z - 2 + dz, v.Zp), yr, x - 2) << (6 * dz);
-        col[dy] = c;
+            for (int dz = 0; dz < NZ; ++dz) {
+                const uint32_t* q = p + dz * dzs + dy * v.nw;
+                const uint32_t lo = q[0], hi = two ? q[1] : 0u;
+                c |= (unsigned long long)(__funnelshift_r(lo, hi, sh) & 63u) << (6 * dz);
+            }
+            col[dy] = c;
+        }
+    } else {
+#pragma unroll
+        for (int dy = 0; dy < NY; ++dy) {
+            const int yr = reflect_idx(y - 2 + dy, v.Hp);
+            unsigned long long c = 0;
+#pragma unroll
+            for (int dz = 0; dz < NZ; ++dz)
+                c |= (unsigned long long)get6(v, reflect_idx(z - 2 + dz, v.Zp), yr, x - 2) << (6 * dz);
+            col[dy] = c;
+        }
     }
 #pragma unroll
     for (int e = 0; e < 2; ++e) {

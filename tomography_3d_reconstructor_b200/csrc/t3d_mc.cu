@@ -135,70 +135,88 @@ __device__ __forceinline__ WordMasks load_masks(const Grid& g, uint32_t row, int
 }
 
 // ------------------------------------------------------------------------------------------------
-// 1. dense flags: a warp walks FR consecutive voxel rows, lane = word; one ballot per (row, 32-word chunk)
+// 1. dense flags.  Same shape as the morphology kernels: a thread owns one uint4 column (128 voxels) of one plane
+// and marches down GY rows, keeping the rows (z,y) and (z+1,y) in registers, so every sign word is loaded twice
+// (as plane z and as plane z+1).  Active words are rare (a few % of all words): each thread ORs its four flag bits
+// into the pre-zeroed bitmap (one bit per word, one 32-bit word per (row, 32-word chunk)) only when non-zero.
 // ------------------------------------------------------------------------------------------------
-#define FR 4
+#define GY 16
 
-__global__ void __launch_bounds__(256) k_mc_flags(Grid g, uint32_t* __restrict__ ballots)
+__global__ void __launch_bounds__(256) k_mc_flags(Grid g, uint32_t* __restrict__ ballots, int lanes_x, int pz_per_block)
 {
-    const uint32_t l = lane_id();
-    const uint32_t r0 = (blockIdx.x * 8u + (threadIdx.x >> 5)) * FR;
-    const int64_t dy = g.nws, dz = (int64_t)g.Hs * g.nws;
-    for (uint32_t row = r0; row < r0 + FR && row < g.n_rows; ++row) {
-        const int z = (int)(row / (uint32_t)g.Hs), y = (int)(row - (uint32_t)z * (uint32_t)g.Hs);
-        const bool hy = (y + 1 < g.Hs), hz = (z + 1 < g.Zs);
-        const uint32_t* p0 = g.sign + (int64_t)row * g.nws;
-        for (int c = 0; c < g.ncr; ++c) {
-            const int w = (c << 5) + l;
-            const bool in = w < g.nws;
-            const bool hx = (w + 1 < g.nws);
-            uint32_t s00 = 0, s01 = 0, s10 = 0, s11 = 0;
-            if (in) {
-                const uint32_t* p = p0 + w;
-                s00 = p[0];
-                if (hy) s01 = p[dy];
-                if (hz) s10 = p[dz];
-                if (hy && hz) s11 = p[dz + dy];
-            }
-            // bit 0 of the next word: from the next lane, lane 31 loads it
-            uint32_t n00 = __shfl_down_sync(0xffffffffu, s00, 1) & 1u, n01 = __shfl_down_sync(0xffffffffu, s01, 1) & 1u;
-            uint32_t n10 = __shfl_down_sync(0xffffffffu, s10, 1) & 1u, n11 = __shfl_down_sync(0xffffffffu, s11, 1) & 1u;
-            if (!hx) { n00 = n01 = n10 = n11 = 0u; }
-            else if (l == 31) {
-                const uint32_t* p = p0 + w + 1;
-                n00 = p[0] & 1u;
-                n01 = hy ? p[dy] & 1u : 0u;
-                n10 = hz ? p[dz] & 1u : 0u;
-                n11 = (hy && hz) ? p[dz + dy] & 1u : 0u;
-            }
-            bool active = false;
-            if (in) {
-                const WordMasks m = make_masks(s00, s01, s10, s11, n00, n01, n10, n11, hy, hz, w, g.Ws);
-                active = (m.X00 | m.Y0 | m.Z0 | m.act) != 0u;
-            }
-            const uint32_t bal = __ballot_sync(0xffffffffu, active);
-            if (l == 0) ballots[(int64_t)row * g.ncr + c] = bal;
+    const int lx = threadIdx.x % lanes_x, pz = threadIdx.x / lanes_x;
+    const int nws4 = g.nws >> 2;
+    const int w4 = blockIdx.x * lanes_x + lx, z = blockIdx.z * pz_per_block + pz, y0 = blockIdx.y * GY;
+    if (pz >= pz_per_block || w4 >= nws4 || z >= g.Zs) return;
+    const bool hz = (z + 1 < g.Zs);
+    const bool hx = (4 * w4 + 4 < g.nws);
+    const uint4 vm = valid_mask4(w4, g.Ws), em = valid_mask4(w4, g.Ws - 1);
+    const uint4 zero = make_uint4(0, 0, 0, 0);
+    auto row4 = [&](int zz, int yy, uint32_t& nxt) -> uint4 {
+        const uint32_t* p = g.sign + ((int64_t)zz * g.Hs + yy) * g.nws + 4 * w4;
+        nxt = hx ? p[4] : 0u;
+        return *reinterpret_cast<const uint4*>(p);
+    };
+    uint32_t n0, n1, m0 = 0, m1 = 0;
+    uint4 c0 = row4(z, y0, n0), c1 = hz ? row4(z + 1, y0, n1) : zero;  // rows (z,y), (z+1,y)
+    if (!hz) n1 = 0;
+    const int y1 = min(g.Hs, y0 + GY);
+    for (int y = y0; y < y1; ++y) {
+        const bool hy = (y + 1 < g.Hs);
+        const uint4 d0 = hy ? row4(z, y + 1, m0) : zero;                 // rows (z,y+1), (z+1,y+1)
+        const uint4 d1 = (hy && hz) ? row4(z + 1, y + 1, m1) : zero;
+        if (!hy) m0 = 0;
+        if (!(hy && hz)) m1 = 0;
+        // values at x+1
+        const uint4 a0 = shr1_4(c0, n0), a1 = shr1_4(c1, n1), b0 = shr1_4(d0, m0), b1 = shr1_4(d1, m1);
+        uint4 f;  // owned cut edges
+        f.x = ((c0.x ^ a0.x) & em.x); f.y = ((c0.y ^ a0.y) & em.y); f.z = ((c0.z ^ a0.z) & em.z); f.w = ((c0.w ^ a0.w) & em.w);
+        if (hy) { f.x |= (c0.x ^ d0.x) & vm.x; f.y |= (c0.y ^ d0.y) & vm.y; f.z |= (c0.z ^ d0.z) & vm.z; f.w |= (c0.w ^ d0.w) & vm.w; }
+        if (hz) { f.x |= (c0.x ^ c1.x) & vm.x; f.y |= (c0.y ^ c1.y) & vm.y; f.z |= (c0.z ^ c1.z) & vm.z; f.w |= (c0.w ^ c1.w) & vm.w; }
+        if (hy && hz) {  // active cube origins: the 8 corners are neither all set nor all clear
+            const uint4 o = or4(or4(or4(c0, c1), or4(d0, d1)), or4(or4(a0, a1), or4(b0, b1)));
+            const uint4 a = and4(and4(and4(c0, c1), and4(d0, d1)), and4(and4(a0, a1), and4(b0, b1)));
+            f.x |= (o.x & ~a.x) & em.x; f.y |= (o.y & ~a.y) & em.y; f.z |= (o.z & ~a.z) & em.z; f.w |= (o.w & ~a.w) & em.w;
         }
+        const uint32_t nib = (f.x ? 1u : 0u) | (f.y ? 2u : 0u) | (f.z ? 4u : 0u) | (f.w ? 8u : 0u);
+        if (nib) {
+            const int w = 4 * w4;
+            atomicOr(ballots + ((int64_t)z * g.Hs + y) * g.ncr + (w >> 5), nib << (w & 31));
+        }
+        c0 = d0; c1 = d1; n0 = m0; n1 = m1;
     }
 }
 
 // ------------------------------------------------------------------------------------------------
-// 3. counts of the active words (warp per ballot word; inactive chunks leave after one load)
+// 3a. compaction: flat index of every active word, in raster order (thread per bitmap word)
+// 3b. counts of the active words (thread per active word)
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_mc_words(Grid g, const uint32_t* __restrict__ ballots,
-                                                  const uint32_t* __restrict__ chunkbase, int64_t n_chunks, uint32_t n_active,
-                                                  uint32_t* __restrict__ aw_idx, uint32_t* __restrict__ aw_cnt,
-                                                  unsigned long long* __restrict__ n_ambiguous)
+__global__ void __launch_bounds__(256) k_mc_compact(Grid g, const uint32_t* __restrict__ ballots,
+                                                    const uint32_t* __restrict__ chunkbase, int64_t n_chunks,
+                                                    uint32_t* __restrict__ aw_idx)
 {
-    const int64_t c = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= n_chunks) return;
-    const uint32_t bal = ballots[c];
+    uint32_t bal = ballots[c];
     if (!bal) return;
-    const uint32_t l = lane_id();
-    if (!((bal >> l) & 1u)) return;
-    const uint32_t k = chunkbase[c] + __popc(bal & ((1u << l) - 1u));
+    uint32_t k = chunkbase[c];
     const uint32_t row = (uint32_t)(c / g.ncr);
-    const int w = (int)((c - (int64_t)row * g.ncr) << 5) + (int)l;
+    const uint32_t base = row * (uint32_t)g.nws + (uint32_t)((c - (int64_t)row * g.ncr) << 5);
+    while (bal) {
+        const int b = __ffs(bal) - 1;
+        bal &= bal - 1;
+        aw_idx[k++] = base + b;
+    }
+}
+
+__global__ void __launch_bounds__(128) k_mc_words(Grid g, const uint32_t* __restrict__ aw_idx, uint32_t n_active,
+                                                  uint32_t* __restrict__ aw_cnt, unsigned long long* __restrict__ n_ambiguous)
+{
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_active) return;
+    const uint32_t i = aw_idx[k];
+    const uint32_t row = i / (uint32_t)g.nws;
+    const int w = (int)(i - row * (uint32_t)g.nws);
     int z, y;
     const WordMasks m = load_masks(g, row, w, z, y);
     uint32_t nt = 0, na = 0;
@@ -209,7 +227,6 @@ __global__ void __launch_bounds__(256) k_mc_words(Grid g, const uint32_t* __rest
         nt += c_luts.ntri[cs];
         na += c_luts.amb[cs];
     }
-    aw_idx[k] = row * (uint32_t)g.nws + (uint32_t)w;
     aw_cnt[k] = __popc(m.X00);
     aw_cnt[(int64_t)n_active + k] = __popc(m.Y0);
     aw_cnt[2 * (int64_t)n_active + k] = __popc(m.Z0);
@@ -422,8 +439,11 @@ extern "C" int t3d_mc_flags(const void* sign_bits, int Zs, int Hs, int Ws, void*
 {
     Grid g;
     if (int rc = make_grid(g, sign_bits, Zs, Hs, Ws, "t3d_mc_flags")) return rc;
-    const int64_t n_warps = ((int64_t)g.n_rows + FR - 1) / FR;
-    k_mc_flags<<<(unsigned)((n_warps + 7) / 8), 256, 0, (cudaStream_t)stream>>>(g, (uint32_t*)ballots_u32);
+    cudaStream_t st = (cudaStream_t)stream;
+    T3D_CUDA(cudaMemsetAsync(ballots_u32, 0, sizeof(uint32_t) * (size_t)g.n_rows * g.ncr, st));
+    const int nws4 = g.nws / 4, lanes_x = nws4 < 256 ? nws4 : 256, pzb = 256 / lanes_x;
+    dim3 grid((nws4 + lanes_x - 1) / lanes_x, (Hs + GY - 1) / GY, (Zs + pzb - 1) / pzb);
+    k_mc_flags<<<grid, 256, 0, st>>>(g, (uint32_t*)ballots_u32, lanes_x, pzb);
     T3D_CHECK_LAUNCH("t3d_mc_flags");
     t3d_count_launches(1);
     return 0;
@@ -440,12 +460,13 @@ extern "C" int t3d_mc_words(const void* sign_bits, int Zs, int Hs, int Ws, const
     T3D_CUDA(cudaMemsetAsync(n_ambiguous_u64, 0, 8, st));
     if (n_active == 0) return 0;
     const int64_t n_chunks = (int64_t)g.n_rows * g.ncr;
-    k_mc_words<<<(unsigned)((n_chunks * 32 + 255) / 256), 256, 0, st>>>(g, (const uint32_t*)ballots_u32,
-                                                                        (const uint32_t*)chunkbase_u32, n_chunks, n_active,
-                                                                        (uint32_t*)aw_idx_u32, (uint32_t*)aw_cnt_u32,
-                                                                        (unsigned long long*)n_ambiguous_u64);
+    k_mc_compact<<<(unsigned)((n_chunks + 255) / 256), 256, 0, st>>>(g, (const uint32_t*)ballots_u32,
+                                                                      (const uint32_t*)chunkbase_u32, n_chunks,
+                                                                      (uint32_t*)aw_idx_u32);
+    k_mc_words<<<(n_active + 127) / 128, 128, 0, st>>>(g, (const uint32_t*)aw_idx_u32, n_active, (uint32_t*)aw_cnt_u32,
+                                                       (unsigned long long*)n_ambiguous_u64);
     T3D_CHECK_LAUNCH("t3d_mc_words");
-    t3d_count_launches(1);
+    t3d_count_launches(2);
     return 0;
 }
 

@@ -190,58 +190,36 @@ __device__ __forceinline__ uint32_t fill_dn(uint32_t m, uint32_t s)  // towards 
     return s;
 }
 
-// closure of `reach` along one row, both directions.  One warp; lane owns words [l*k, (l+1)*k).
-__device__ bool row_closure(const uint32_t* mrow, uint32_t* rrow, int nw, int W)
+// closure of `reach` along one row, both directions, by ONE thread (rows are independent, so the CTA closes
+// FH_THREADS rows at a time).  Words are fetched eight at a time BEFORE the carry chain runs, so the loads of a chunk
+// are all in flight together instead of being serialised behind the (possibly aliasing) stores.
+__device__ __forceinline__ bool row_closure(const uint32_t* mrow, uint32_t* rrow, int nwv)
 {
-    const uint32_t l = lane_id();
-    const int k = (nw + 31) >> 5;
-    const int w0 = l * k, w1 = min(nw, w0 + k);
     bool changed = false;
-    // ---- towards +x
-    {
-        uint32_t carry = 0, P = 1;
-        for (int w = w0; w < w1; ++w) {
-            const uint32_t m = mrow[w];
-            const uint32_t f = fill_up(m, rrow[w] | (carry & m & 1u));
+    uint32_t carry = 0;
+    for (int w0 = 0; w0 < nwv; w0 += 8) {            // towards +x
+        uint32_t m[8], r[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { const bool ok = w0 + k < nwv; m[k] = ok ? mrow[w0 + k] : 0u; r[k] = ok ? rrow[w0 + k] : 0u; }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const uint32_t f = fill_up(m[k], r[k] | (carry & m[k] & 1u));
             carry = f >> 31;
-            P &= (m == 0xffffffffu);
-        }
-        if (w0 >= w1) { carry = 0; P = 0; }
-        const uint32_t g = __ballot_sync(0xffffffffu, carry), p = __ballot_sync(0xffffffffu, P);
-        const uint32_t x = g | p;
-        const uint32_t cin = (((x + g) ^ x ^ g) >> l) & 1u;  // carry into lane l
-        carry = cin;
-        for (int w = w0; w < w1; ++w) {
-            const uint32_t m = mrow[w], r = rrow[w];
-            const uint32_t f = fill_up(m, r | (carry & m & 1u));
-            carry = f >> 31;
-            if (f != r) { rrow[w] = f; changed = true; }
+            if (f != r[k]) { rrow[w0 + k] = f; changed = true; }
         }
     }
-    __syncwarp();
-    // ---- towards -x
-    {
-        uint32_t carry = 0, P = 1;
-        for (int w = w1 - 1; w >= w0; --w) {
-            const uint32_t m = mrow[w];
-            const uint32_t f = fill_dn(m, rrow[w] | ((carry << 31) & m));
+    carry = 0;
+    for (int w0 = ((nwv - 1) >> 3) << 3; w0 >= 0; w0 -= 8) {   // towards -x
+        uint32_t m[8], r[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { const bool ok = w0 + k < nwv; m[k] = ok ? mrow[w0 + k] : 0u; r[k] = ok ? rrow[w0 + k] : 0u; }
+#pragma unroll
+        for (int k = 7; k >= 0; --k) {
+            const uint32_t f = fill_dn(m[k], r[k] | ((carry << 31) & m[k]));
             carry = f & 1u;
-            P &= (m == 0xffffffffu);
-        }
-        if (w0 >= w1) { carry = 0; P = 0; }
-        // lane order reversed: bit-reverse the ballots so that "carry into lane l" comes from lanes > l
-        const uint32_t g = __brev(__ballot_sync(0xffffffffu, carry)), p = __brev(__ballot_sync(0xffffffffu, P));
-        const uint32_t x = g | p;
-        const uint32_t cin = (((x + g) ^ x ^ g) >> (31 - l)) & 1u;
-        carry = cin;
-        for (int w = w1 - 1; w >= w0; --w) {
-            const uint32_t m = mrow[w], r = rrow[w];
-            const uint32_t f = fill_dn(m, r | ((carry << 31) & m));
-            carry = f & 1u;
-            if (f != r) { rrow[w] = f; changed = true; }
+            if (f != r[k]) { rrow[w0 + k] = f; changed = true; }
         }
     }
-    (void)W;
     return changed;
 }
 
@@ -257,7 +235,7 @@ __global__ void __launch_bounds__(FH_THREADS) k_fill_holes(uint32_t* bits_planes
     uint32_t* m = scratch + (int64_t)blockIdx.x * 2 * pw;
     uint32_t* r = m + pw;
     const int tid = threadIdx.x;
-    const int warp = tid >> 5, nwarps = FH_THREADS >> 5;
+    const int warp = tid >> 5;
 
     // background mask + seeds (background pixels on the image border touch the "outside")
     for (int64_t i = tid; i < pw; i += FH_THREADS) {
@@ -280,10 +258,12 @@ __global__ void __launch_bounds__(FH_THREADS) k_fill_holes(uint32_t* bits_planes
     const int L = (H + nseg - 1) / nseg;
 
     for (int iter = 0; iter < 4 * (H + W) + 8; ++iter) {
+        // A round = row closure then column closure.  The row closure is idempotent, so the fixpoint is reached as
+        // soon as a column closure changes nothing: only the column phase feeds `changed`.
         int changed = 0;
         // ---- rows
-        for (int y = warp; y < H; y += nwarps)
-            changed |= row_closure(m + (int64_t)y * nw, r + (int64_t)y * nw, nw, W) ? 1 : 0;
+        for (int y = tid; y < H; y += FH_THREADS)
+            row_closure(m + (int64_t)y * nw, r + (int64_t)y * nw, (W + 31) >> 5);
         __syncthreads();
         // ---- columns, 32 word-columns at a time: thread = (seg = warp, col = lane)
         for (int c0 = 0; c0 < nw; c0 += 32) {
@@ -305,22 +285,29 @@ __global__ void __launch_bounds__(FH_THREADS) k_fill_holes(uint32_t* bits_planes
                     if (dir == 0) for (int s = 0; s < seg; ++s) cin = sG[s][tid & 31] | (sP[s][tid & 31] & cin);
                     else          for (int s = nseg - 1; s > seg; --s) cin = sG[s][tid & 31] | (sP[s][tid & 31] & cin);
                 }
-                // pass 3: final sweep
+                // pass 3: final sweep (rows fetched eight at a time ahead of the dependent chain)
                 if (act && y0 < y1) {
                     uint32_t carry = cin;
-                    if (dir == 0) {
-                        for (int y = y0; y < y1; ++y) {
-                            const int64_t i = (int64_t)y * nw + c;
-                            const uint32_t old = r[i], nv = old | (carry & m[i]);
-                            if (nv != old) { r[i] = nv; changed = 1; }
-                            carry = nv;
+                    const int n = y1 - y0;
+                    for (int k0 = 0; k0 < n; k0 += 8) {
+                        uint32_t mm[8], rr[8];
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) {
+                            const int kk = k0 + k;
+                            const int y = dir == 0 ? y0 + kk : y1 - 1 - kk;
+                            const bool ok = kk < n;
+                            mm[k] = ok ? m[(int64_t)y * nw + c] : 0u;
+                            rr[k] = ok ? r[(int64_t)y * nw + c] : 0u;
                         }
-                    } else {
-                        for (int y = y1 - 1; y >= y0; --y) {
-                            const int64_t i = (int64_t)y * nw + c;
-                            const uint32_t old = r[i], nv = old | (carry & m[i]);
-                            if (nv != old) { r[i] = nv; changed = 1; }
-                            carry = nv;
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) {
+                            const int kk = k0 + k;
+                            if (kk < n) {
+                                const int y = dir == 0 ? y0 + kk : y1 - 1 - kk;
+                                const uint32_t nv = rr[k] | (carry & mm[k]);
+                                if (nv != rr[k]) { r[(int64_t)y * nw + c] = nv; changed = 1; }
+                                carry = nv;
+                            }
                         }
                     }
                 }
@@ -423,7 +410,7 @@ extern "C" int t3d_gap_fill(const void* in_bits, void* out_bits, const void* lo_
 // ------------------------------------------------------------------------------------------------
 #define MY 16
 
-template <bool ER>
+template <bool ER, bool FIX>
 __global__ void __launch_bounds__(256) k_morph4(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, int Z, int H,
                                                 int W, int nw, int lanes_x, int pz_per_block,
                                                 unsigned long long* __restrict__ counts)
@@ -441,7 +428,7 @@ __global__ void __launch_bounds__(256) k_morph4(const uint32_t* __restrict__ in,
     if (pz < pz_per_block && w4 < nw4 && z < Z) {
         const uint4 vm = valid_mask4(w4, W);
         // words beyond the volume (tail bits, padding words) read as the border value of this stage
-        const bool fix = ER && (4 * w4 + 4 > (W >> 5));
+        const bool fix = FIX && ER && (4 * w4 + 4 > (W >> 5));
         auto row4 = [&](int zz, int yy) -> uint4 {
             uint4 v = *reinterpret_cast<const uint4*>(in + ((int64_t)zz * H + yy) * nw + 4 * w4);
             if (fix) v = make_uint4(v.x | ~vm.x, v.y | ~vm.y, v.z | ~vm.z, v.w | ~vm.w);
@@ -460,7 +447,7 @@ __global__ void __launch_bounds__(256) k_morph4(const uint32_t* __restrict__ in,
             const uint32_t* rowp = in + ((int64_t)z * H + y) * nw + 4 * w4;
             const uint32_t l = has_l ? rowp[-1] : B;
             uint32_t r = has_r ? rowp[4] : B;
-            if (ER && has_r && 4 * w4 + 5 >= nwv) r |= ~valid_mask(4 * w4 + 4, W);  // right neighbour is the partial last word
+            if (FIX && ER && has_r && 4 * w4 + 5 >= nwv) r |= ~valid_mask(4 * w4 + 4, W);  // right neighbour is the partial last word
             const uint4 xm = shl1_4(cur, l), xp = shr1_4(cur, r);
             uint4 v;
             if (ER) v = and4(and4(and4(cur, xm), and4(xp, prev)), and4(and4(next, zm), zp));
@@ -508,8 +495,10 @@ extern "C" int t3d_morph(const void* in_bits, void* out_bits, int Z, int H, int 
         const bool last = (s == n_stages - 1);
         uint32_t* dst = last ? (uint32_t*)out_bits : tmp[s & 1];
         unsigned long long* cnt = last ? (unsigned long long*)slice_counts_u64 : nullptr;
-        if ((erode_mask >> s) & 1u) k_morph4<true><<<grid, 256, smem, st>>>(src, dst, Z, H, W, nw, lanes_x, pzb, cnt);
-        else k_morph4<false><<<grid, 256, smem, st>>>(src, dst, Z, H, W, nw, lanes_x, pzb, cnt);
+        const bool er = (erode_mask >> s) & 1u;
+        if (er && (W & 127)) k_morph4<true, true><<<grid, 256, smem, st>>>(src, dst, Z, H, W, nw, lanes_x, pzb, cnt);
+        else if (er) k_morph4<true, false><<<grid, 256, smem, st>>>(src, dst, Z, H, W, nw, lanes_x, pzb, cnt);
+        else k_morph4<false, false><<<grid, 256, smem, st>>>(src, dst, Z, H, W, nw, lanes_x, pzb, cnt);
         src = dst;
     }
     T3D_CHECK_LAUNCH("t3d_morph");

@@ -89,13 +89,35 @@ class DeviceVolume:
 
     def _run_stats(self) -> None:
         dev = self.bits.device
-        counts = torch.empty(self.Z, dtype=torch.int64, device=dev)
+        counts = torch.empty(self.Z, dtype=torch.int64, device=dev) if self._counts is None else None
         bbox = torch.empty(6, dtype=torch.int32, device=dev)
         check(_L().t3d_volume_stats(_p(self.bits), self.Z, self.H, self.W, _p(counts), _p(bbox), _stream()),
               "t3d_volume_stats")
         if self._counts is None:
             self._counts = counts
         self._bbox = bbox
+
+    # device-side handles (no synchronisation): used by pipeline.reconstruct to fetch everything in one copy
+    def counts_tensor(self) -> torch.Tensor:
+        if self._counts is None:
+            self._run_stats()
+        if isinstance(self._counts, np.ndarray):
+            return torch.from_numpy(self._counts).to(self.bits.device)
+        return self._counts
+
+    def bbox_tensor(self) -> torch.Tensor:
+        if self._bbox is None:
+            self._run_stats()
+        if isinstance(self._bbox, torch.Tensor):
+            return self._bbox
+        b = self._bbox if self._bbox else (0x7fffffff, -1) * 3
+        return torch.tensor(b, dtype=torch.int32, device=self.bits.device)
+
+    def set_host_stats(self, counts: np.ndarray, bbox) -> None:
+        self._counts = np.asarray(counts, dtype=np.int64)
+        if bbox is not None:
+            b = tuple(int(v) for v in bbox)
+            self._bbox = b if b[1] >= 0 else ()
 
     def bbox(self) -> Optional[Tuple[int, int, int, int, int, int]]:
         """(zmin, zmax, ymin, ymax, xmin, xmax) of the set voxels, None if the volume is empty."""
@@ -117,12 +139,35 @@ class DeviceVolume:
 
 
 class DeviceMesh:
-    __slots__ = ("verts", "faces", "n_ambiguous", "n_exact", "_measures", "__weakref__")
+    """Mesh on the device.  After an asynchronous canonicalisation the arrays are capacity-sized and the true sizes
+    live in `counts_dev` until resolve() (one D2H copy) or set_sizes() trims them."""
 
-    def __init__(self, verts: torch.Tensor, faces: torch.Tensor, n_ambiguous: int = 0, n_exact: int = 0):
-        self.verts, self.faces = verts, faces
+    __slots__ = ("_verts", "_faces", "counts_dev", "n_ambiguous", "n_exact", "_measures", "__weakref__")
+
+    def __init__(self, verts: torch.Tensor, faces: torch.Tensor, n_ambiguous: int = 0, n_exact: int = 0,
+                 counts_dev: Optional[torch.Tensor] = None):
+        self._verts, self._faces = verts, faces
+        self.counts_dev = counts_dev
         self.n_ambiguous, self.n_exact = n_ambiguous, n_exact
         self._measures = None
+
+    def set_sizes(self, n_verts: int, n_faces: int) -> None:
+        self._verts, self._faces = self._verts[:n_verts], self._faces[:n_faces]
+        self.counts_dev = None
+
+    def resolve(self) -> "DeviceMesh":
+        if self.counts_dev is not None:
+            v2, f2 = (int(c) for c in self.counts_dev.cpu().tolist())
+            self.set_sizes(v2, f2)
+        return self
+
+    @property
+    def verts(self) -> torch.Tensor:
+        return self.resolve()._verts
+
+    @property
+    def faces(self) -> torch.Tensor:
+        return self.resolve()._faces
 
     def measures(self) -> Tuple[float, float]:
         """(signed volume, area), float64 accumulation on the device."""
@@ -205,6 +250,50 @@ def pack(masks_u8_dev: torch.Tensor, threshold: int = 1) -> DeviceVolume:
     bits = torch.empty((Z, H, words_per_row(W)), dtype=torch.int32, device=masks_u8_dev.device)
     check(_L().t3d_pack_masks(_p(masks_u8_dev), Z, H, W, int(threshold), _p(bits), _stream()), "t3d_pack_masks")
     return DeviceVolume(bits, Z, H, W)
+
+
+_side_streams = {}
+
+
+def side_stream(dev: torch.device) -> torch.cuda.Stream:
+    """One auxiliary stream per device for work that is off the critical path (hole filling, bbox, measures)."""
+    key = (dev.type, dev.index)
+    st = _side_streams.get(key)
+    if st is None:
+        st = torch.cuda.Stream(device=dev)
+        _side_streams[key] = st
+    return st
+
+
+def pack_and_close(masks_u8_dev: torch.Tensor, threshold: int = 1, close_ends: bool = True) -> DeviceVolume:
+    """create_voxel_data on the device (voxel_processor.py:46-49).  The two end planes are packed first and their 2-D
+    hole filling runs on a side stream while the bulk of the stack is being packed; the z gap fill joins both."""
+    L = _L()
+    Z, H, W = (int(s) for s in masks_u8_dev.shape)
+    if not close_ends or Z < 3:
+        dv = pack(masks_u8_dev, threshold)
+        return close_volume_ends(dv) if close_ends else dv
+    dev = masks_u8_dev.device
+    wpr = words_per_row(W)
+    bits = torch.empty((Z, H, wpr), dtype=torch.int32, device=dev)
+    main = torch.cuda.current_stream()
+    check(L.t3d_pack_masks(_p(masks_u8_dev[0]), 1, H, W, int(threshold), _p(bits[0]), _stream()), "t3d_pack_masks")
+    check(L.t3d_pack_masks(_p(masks_u8_dev[Z - 1]), 1, H, W, int(threshold), _p(bits[Z - 1]), _stream()), "t3d_pack_masks")
+    scratch = torch.empty(int(L.t3d_fill_holes_scratch_bytes(2, H, W)) // 4, dtype=torch.int32, device=dev)
+    ends_packed = torch.cuda.Event()
+    ends_packed.record(main)
+    side = side_stream(dev)
+    filled = torch.cuda.Event()
+    with torch.cuda.stream(side):
+        side.wait_event(ends_packed)
+        check(L.t3d_fill_holes_2d(_p(bits), 2, (Z - 1) * H * wpr, H, W, _p(scratch), _stream()), "t3d_fill_holes_2d")
+        filled.record(side)
+    check(L.t3d_pack_masks(_p(masks_u8_dev[1]), Z - 2, H, W, int(threshold), _p(bits[1]), _stream()), "t3d_pack_masks")
+    main.wait_event(filled)
+    out = torch.empty_like(bits)
+    counts = torch.empty(Z, dtype=torch.int64, device=dev)
+    check(L.t3d_gap_fill(_p(bits), _p(out), None, None, Z, H, W, _p(counts), _stream()), "t3d_gap_fill")
+    return DeviceVolume(out, Z, H, W, counts)
 
 
 def volume_from_host(voxel_data: np.ndarray) -> DeviceVolume:
@@ -372,13 +461,20 @@ def extract_surface(dv: DeviceVolume, slice_depths, mm_per_pixel_y, mm_per_pixel
         canonical = manifold
     if not canonical:
         return DeviceMesh(verts, faces, n_ambiguous, n_exact)
+    if canonical == "async":
+        v2, f2, counts = canonicalize(verts, faces, sync=False)
+        mark("canonicalize")
+        m = DeviceMesh(v2, f2, n_ambiguous, n_exact, counts_dev=counts)
+        m._measures = (verts, faces)  # raw mesh, for pipeline.reconstruct (replaced by the numbers there)
+        return m
     v2, f2 = canonicalize(verts, faces)
     mark("canonicalize")
     return DeviceMesh(v2, f2, n_ambiguous, n_exact)
 
 
-def canonicalize(verts: torch.Tensor, faces_i32: torch.Tensor, faces_i64: bool = True):
-    """_ensure_manifold_mesh (surface_extractor.py:115-126) on the device."""
+def canonicalize(verts: torch.Tensor, faces_i32: torch.Tensor, faces_i64: bool = True, sync: bool = True):
+    """_ensure_manifold_mesh (surface_extractor.py:115-126) on the device.  sync=False returns capacity-sized
+    arrays plus the device tensor holding (V', F')."""
     L = _L()
     V, F = int(verts.shape[0]), int(faces_i32.shape[0])
     dev = verts.device
@@ -388,8 +484,23 @@ def canonicalize(verts: torch.Tensor, faces_i32: torch.Tensor, faces_i64: bool =
     counts = torch.empty(2, dtype=torch.int64, device=dev)
     check(L.t3d_mesh_canonicalize(_p(verts), V, _p(faces_i32), F, _p(vout), _p(fout) if faces_i64 else None,
                                   None if faces_i64 else _p(fout), _p(counts), _p(ws), _stream()), "t3d_mesh_canonicalize")
+    if not sync:
+        return vout, fout, counts
     v2, f2 = (int(c) for c in counts.cpu().tolist())
     return vout[:v2], fout[:f2]
+
+
+def mesh_measure_async(verts: torch.Tensor, faces: torch.Tensor) -> torch.Tensor:
+    """Device tensor {signed volume, area} (float64), no synchronisation."""
+    L = _L()
+    dev = verts.device
+    ws = torch.empty(int(L.t3d_mesh_measure_workspace_bytes()) // 8, dtype=torch.float64, device=dev)
+    out = torch.empty(2, dtype=torch.float64, device=dev)
+    verts = verts.contiguous()
+    faces = faces.contiguous()
+    check(L.t3d_mesh_measure(_p(verts), int(verts.shape[0]), _p(faces), int(faces.shape[0]),
+                             1 if faces.dtype == torch.int64 else 0, _p(out), _p(ws), _stream()), "t3d_mesh_measure")
+    return out
 
 
 def mesh_measure(verts: torch.Tensor, faces: torch.Tensor) -> Tuple[float, float]:

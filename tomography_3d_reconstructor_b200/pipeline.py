@@ -47,19 +47,42 @@ def reconstruct(masks_u8: torch.Tensor, threshold: int, side_counts, total_depth
     mm_x, mm_y = x_length_mm / W, y_length_mm / H
     depths = slice_depths(total_depth_mm, *side_counts)
 
-    dv = engine.pack(masks_u8, threshold)
-    mark("pack")
-    if close_ends:
-        dv = engine.close_volume_ends(dv)
-        mark("close_ends")
+    dv = engine.pack_and_close(masks_u8, threshold, close_ends)
+    mark("pack_close")
+    # bounding box of the raw grid: off the critical path
+    main = torch.cuda.current_stream()
+    side = engine.side_stream(masks_u8.device)
+    ready = torch.cuda.Event()
+    ready.record(main)
+    with torch.cuda.stream(side):
+        side.wait_event(ready)
+        bbox_t = dv.bbox_tensor()
+        bbox_done = torch.cuda.Event()
+        bbox_done.record(side)
     sm = engine.smooth(dv, iterations, True)
     mark("smooth")
-    mesh = engine.extract_surface(sm, depths, mm_y, mm_x, True, add_padding, mark=mark)
-    signed_volume, area = mesh.measures()
+    mesh = engine.extract_surface(sm, depths, mm_y, mm_x, True, add_padding, canonical="async", mark=mark)
+    # measures on the emitted (pre-canonical) mesh: merging exact duplicates and dropping zero-area faces changes
+    # neither the signed volume nor the area, and it removes a dependency on the canonical sizes
+    raw_verts, raw_faces = mesh._measures
+    mesh._measures = None
+    meas = engine.mesh_measure_async(raw_verts, raw_faces)
     mark("measure")
-    raw_counts, sm_counts = dv.slice_counts(), sm.slice_counts()
-    bbox = dv.bbox()
+    main.wait_event(bbox_done)
+    # one device->host copy for every scalar result of the step
+    Zc = dv.Z
+    packed = torch.cat([mesh.counts_dev, meas.view(torch.int64), dv.counts_tensor(), sm.counts_tensor(),
+                        bbox_t.to(torch.int64)]).cpu()
     mark("stats")
+    mesh.set_sizes(int(packed[0]), int(packed[1]))
+    signed_volume, area = (float(x) for x in packed[2:4].view(torch.float64).tolist())
+    mesh._measures = (signed_volume, area)
+    raw_counts = packed[4:4 + Zc].numpy().astype(np.int64)
+    sm_counts = packed[4 + Zc:4 + 2 * Zc].numpy().astype(np.int64)
+    bb = tuple(int(x) for x in packed[4 + 2 * Zc:].tolist())
+    dv.set_host_stats(raw_counts, bb)
+    sm.set_host_stats(sm_counts, None)
+    bbox = dv.bbox()
     return {
         "mesh": mesh,
         "voxel_volume_mm3": variable_depth_volume(raw_counts, mm_x, mm_y, depths),

@@ -42,9 +42,7 @@ class VoxelProcessor:
         self.side_1_count = side_1_count
         self.side_2_count = side_2_count
 
-        dv = engine.pack(engine.upload_u8(engine._as_stack(mask_images)), 1)
-        if close_ends:
-            dv = engine.close_volume_ends(dv)
+        dv = engine.pack_and_close(engine.upload_u8(engine._as_stack(mask_images)), 1, close_ends)
         active = int(dv.slice_counts().sum())
         self.voxel_data = self._publish(dv)
         print(f"Voxels: {self.voxel_data.shape}, active: {active:,}")
@@ -59,9 +57,7 @@ class VoxelProcessor:
         dev_u8 = stack_u8 if isinstance(stack_u8, torch.Tensor) else engine.upload_u8(np.asarray(stack_u8, dtype=np.uint8))
         if dev_u8.numel() == 0:
             raise ValueError("Load masks first, hmm.")
-        dv = engine.pack(dev_u8, threshold)
-        if close_ends:
-            dv = engine.close_volume_ends(dv)
+        dv = engine.pack_and_close(dev_u8, threshold, close_ends)
         active = int(dv.slice_counts().sum())
         self.voxel_data = self._publish(dv)
         print(f"Voxels: {self.voxel_data.shape}, active: {active:,}")
