@@ -307,7 +307,8 @@ def run_ours(args, Z, H, W):
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
     mesh = res["mesh"]
-    V, F = int(mesh.verts.shape[0]), int(mesh.faces.shape[0])
+    V = int(res.get("total_vertices", mesh.verts.shape[0]))
+    F = int(res.get("total_faces", mesh.faces.shape[0]))
     mesh_bytes = 12 * V + 12 * F
     # dominant single kernel among the volume-sized stages
     per_gpu_vox = (z1 - z0) * H * W

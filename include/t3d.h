@@ -98,16 +98,22 @@ int t3d_field_sign(const void* occ_bits, int Z, int H, int W, int pad, const dou
  *   t3d_mc_emit     -> vkeys_u64[n_x+n_y+n_z] (edge key per vertex) and faces_i32 (n_t,3): reference cube order,
  *                      reversed winding (gradient_direction='descent')
  *   t3d_mc_vertices -> verts_f32 (V,3) [z,y,x]: skimage's interpolation on the exact float64 field, then un-pad,
- *                      variable-depth z map and mm scaling (surface_extractor.py:57-65, 82-113). */
+ *                      variable-depth z map and mm scaling (surface_extractor.py:57-65, 82-113).
+ * z_begin/z_end: owned planes of the sign volume ([0, Zs) on one device; -1 = Zs).  With z-slab sharding a rank owns
+ * [z_begin, z_end) and additionally emits the x/y-edge vertices of ghost plane z_end; z_offset is the global padded
+ * plane index of local padded plane 0. */
 int64_t t3d_mc_num_chunks(int Zs, int Hs, int Ws);
-int t3d_mc_flags(const void* sign_bits, int Zs, int Hs, int Ws, void* ballots_u32, void* stream);
-int t3d_mc_words(const void* sign_bits, int Zs, int Hs, int Ws, const void* ballots_u32, const void* chunkbase_u32,
+int t3d_mc_flags(const void* sign_bits, int Zs, int Hs, int Ws, int z_begin, int z_end, void* ballots_u32, void* stream);
+int t3d_mc_words(const void* sign_bits, int Zs, int Hs, int Ws, int z_begin, int z_end, const void* ballots_u32,
+                 const void* chunkbase_u32,
                  uint32_t n_active, void* aw_idx_u32, void* aw_cnt_u32, void* n_ambiguous_u64, void* stream);
-int t3d_mc_emit(const void* sign_bits, int Zs, int Hs, int Ws, const void* ballots_u32, const void* chunkbase_u32,
+int t3d_mc_emit(const void* sign_bits, int Zs, int Hs, int Ws, int z_begin, int z_end, const void* ballots_u32,
+                const void* chunkbase_u32,
                 const void* aw_idx_u32, const void* aw_base_u32, uint32_t n_active, uint32_t n_x, uint32_t n_y,
                 void* vkeys_u64, void* faces_i32, void* stream);
 int t3d_mc_vertices(const void* occ_bits, int Z, int H, int W, int pad, int gaussian, const double* weights3_host,
-                    const void* vkeys_u64, uint32_t n_x, uint32_t n_y, uint32_t n_z, int unpad_shift, const void* cum_f64,
+                    const void* vkeys_u64, uint32_t n_x, uint32_t n_y, uint32_t n_z, int unpad_shift, int z_offset,
+                    const void* cum_f64,
                     const void* adj_f64, int n_cum, double mm_per_pixel_y, double mm_per_pixel_x, int scale_in_f64,
                     void* verts_f32, void* stream);
 

@@ -35,10 +35,10 @@ SIGNATURES = {
     "t3d_exclusive_scan_u32": (_i, [_vp, _vp, _i64, _i, _i, _i, _vp, _vp, _vp]),
     "t3d_field_sign": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "t3d_mc_num_chunks": (_i64, [_i, _i, _i]),
-    "t3d_mc_flags": (_i, [_vp, _i, _i, _i, _vp, _vp]),
-    "t3d_mc_words": (_i, [_vp, _i, _i, _i, _vp, _vp, _u32, _vp, _vp, _vp, _vp]),
-    "t3d_mc_emit": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp, _u32, _u32, _u32, _vp, _vp, _vp]),
-    "t3d_mc_vertices": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _u32, _u32, _u32, _i, _vp, _vp, _i, _dbl, _dbl, _i,
+    "t3d_mc_flags": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp]),
+    "t3d_mc_words": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _u32, _vp, _vp, _vp, _vp]),
+    "t3d_mc_emit": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _u32, _u32, _u32, _vp, _vp, _vp]),
+    "t3d_mc_vertices": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _u32, _u32, _u32, _i, _i, _vp, _vp, _i, _dbl, _dbl, _i,
                              _vp, _vp]),
     "t3d_field_dense": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "t3d_cube_cases": (_i, [_vp, _i, _i, _i, _vp, _vp]),

@@ -68,6 +68,9 @@ static int ensure_luts()
 struct Grid {
     const uint32_t* sign;
     int Zs, Hs, Ws, nws;
+    int z_begin, z_end; // planes [z_begin, z_end) are owned (vertices + cube layers); plane z_end, if it exists, is a
+                        // ghost plane: its x/y-edge vertices are emitted too (the cubes of layer z_end-1 use them) but
+                        // it owns no z-edges and no cubes.  Single device: [0, Zs).  z-slab sharding: see sharded.py.
     int ncr;            // 32-word chunks per row = ceil(nws/32); one ballot word per (row, chunk)
     uint32_t n_rows;    // Zs*Hs
     int64_t n_words;    // n_rows*nws (flat word index i = row*nws + w)
@@ -86,9 +89,11 @@ __device__ __forceinline__ uint32_t shr1(uint32_t s, uint32_t nbit) { return (s 
 
 // s*: words of the four rows, n*: bit 0 of the next word of each row
 __device__ __forceinline__ WordMasks make_masks(uint32_t s00, uint32_t s01, uint32_t s10, uint32_t s11, uint32_t n00,
-                                                uint32_t n01, uint32_t n10, uint32_t n11, bool hy, bool hz, int w, int Ws)
+                                                uint32_t n01, uint32_t n10, uint32_t n11, bool hy, bool hz, int w, int Ws,
+                                                bool own = true)
 {
     WordMasks m;
+    hz = hz && own;  // a ghost plane owns neither z-edges nor cubes
     const uint32_t vm = valid_mask(w, Ws), em = valid_mask(w, Ws - 1);  // em: x+1 still inside the grid
     m.s00 = s00; m.s01 = s01; m.s10 = s10; m.s11 = s11;
     m.a00 = shr1(s00, n00); m.a01 = shr1(s01, n01); m.a10 = shr1(s10, n10); m.a11 = shr1(s11, n11);
@@ -131,7 +136,7 @@ __device__ __forceinline__ WordMasks load_masks(const Grid& g, uint32_t row, int
         if (hz) n10 = p[dz + 1] & 1u;
         if (hy && hz) n11 = p[dz + dy + 1] & 1u;
     }
-    return make_masks(s00, s01, s10, s11, n00, n01, n10, n11, hy, hz, w, g.Ws);
+    return make_masks(s00, s01, s10, s11, n00, n01, n10, n11, hy, hz, w, g.Ws, z < g.z_end);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -146,9 +151,9 @@ __global__ void __launch_bounds__(256) k_mc_flags(Grid g, uint32_t* __restrict__
 {
     const int lx = threadIdx.x % lanes_x, pz = threadIdx.x / lanes_x;
     const int nws4 = g.nws >> 2;
-    const int w4 = blockIdx.x * lanes_x + lx, z = blockIdx.z * pz_per_block + pz, y0 = blockIdx.y * GY;
-    if (pz >= pz_per_block || w4 >= nws4 || z >= g.Zs) return;
-    const bool hz = (z + 1 < g.Zs);
+    const int w4 = blockIdx.x * lanes_x + lx, z = g.z_begin + blockIdx.z * pz_per_block + pz, y0 = blockIdx.y * GY;
+    if (pz >= pz_per_block || w4 >= nws4 || z >= g.Zs || z > g.z_end) return;
+    const bool hz = (z + 1 < g.Zs) && (z < g.z_end);  // ghost plane: x/y edges only
     const bool hx = (4 * w4 + 4 < g.nws);
     const uint4 vm = valid_mask4(w4, g.Ws), em = valid_mask4(w4, g.Ws - 1);
     const uint4 zero = make_uint4(0, 0, 0, 0);
@@ -362,6 +367,7 @@ struct VertexArgs {
     OccView occ;
     const unsigned long long* vkeys;
     uint32_t first, count;    // id range of this axis block
+    int z_offset;             // global padded plane of local padded plane 0 (z-slab sharding; 0 on a single device)
     float shift;              // 1 if manifold else 0 (surface_extractor.py:57-60)
     const double* cum;        // cumulative adjusted depths, n_cum entries (n_cum = 0: no z map)
     const double* adj;        // adjusted depths, n_cum-1 entries
@@ -389,7 +395,7 @@ __global__ void __launch_bounds__(128) k_mc_vertices(VertexArgs p)
     const double wa = __ddiv_rn(1.0, __dadd_rn(1.1920928955078125e-07, fabs(va)));
     const double wb = __ddiv_rn(1.0, __dadd_rn(1.1920928955078125e-07, fabs(vb)));
     const double frac = __ddiv_rn(wb, __dadd_rn(wa, wb));
-    double pz = (double)z, py = (double)y, px = (double)x;
+    double pz = (double)(z + p.z_offset), py = (double)y, px = (double)x;
     if (AXIS == 0) pz = __dadd_rn(pz, frac); else if (AXIS == 1) py = __dadd_rn(py, frac); else px = __dadd_rn(px, frac);
     float fz = __fsub_rn(__double2float_rn(pz), p.shift);
     float fy = __fsub_rn(__double2float_rn(py), p.shift);
@@ -420,9 +426,12 @@ __global__ void __launch_bounds__(128) k_mc_vertices(VertexArgs p)
 // ------------------------------------------------------------------------------------------------
 // C ABI
 // ------------------------------------------------------------------------------------------------
-static int make_grid(Grid& g, const void* sign_bits, int Zs, int Hs, int Ws, const char* who)
+static int make_grid(Grid& g, const void* sign_bits, int Zs, int Hs, int Ws, int z_begin, int z_end, const char* who)
 {
     if (Zs <= 0 || Hs <= 0 || Ws <= 0) { t3d_set_error("%s: empty volume", who); return 2; }
+    if (z_end < 0 || z_end > Zs) z_end = Zs;
+    if (z_begin < 0 || z_begin >= z_end) { t3d_set_error("%s: empty plane range", who); return 2; }
+    g.z_begin = z_begin; g.z_end = z_end;
     g.sign = (const uint32_t*)sign_bits;
     g.Zs = Zs; g.Hs = Hs; g.Ws = Ws; g.nws = t3d_wpr(Ws);
     g.ncr = (g.nws + 31) >> 5;
@@ -435,14 +444,16 @@ static int make_grid(Grid& g, const void* sign_bits, int Zs, int Hs, int Ws, con
 extern "C" int64_t t3d_mc_num_chunks(int Zs, int Hs, int Ws) { return (int64_t)Zs * Hs * ((t3d_wpr(Ws) + 31) >> 5); }
 
 // ballots_u32: t3d_mc_num_chunks words, one per (voxel row, 32-word chunk): bit l = word 32*chunk+l of that row is active
-extern "C" int t3d_mc_flags(const void* sign_bits, int Zs, int Hs, int Ws, void* ballots_u32, void* stream)
+extern "C" int t3d_mc_flags(const void* sign_bits, int Zs, int Hs, int Ws, int z_begin, int z_end, void* ballots_u32,
+                            void* stream)
 {
     Grid g;
-    if (int rc = make_grid(g, sign_bits, Zs, Hs, Ws, "t3d_mc_flags")) return rc;
+    if (int rc = make_grid(g, sign_bits, Zs, Hs, Ws, z_begin, z_end, "t3d_mc_flags")) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     T3D_CUDA(cudaMemsetAsync(ballots_u32, 0, sizeof(uint32_t) * (size_t)g.n_rows * g.ncr, st));
     const int nws4 = g.nws / 4, lanes_x = nws4 < 256 ? nws4 : 256, pzb = 256 / lanes_x;
-    dim3 grid((nws4 + lanes_x - 1) / lanes_x, (Hs + GY - 1) / GY, (Zs + pzb - 1) / pzb);
+    const int nz = (g.z_end < Zs ? g.z_end + 1 : Zs) - g.z_begin;
+    dim3 grid((nws4 + lanes_x - 1) / lanes_x, (Hs + GY - 1) / GY, (nz + pzb - 1) / pzb);
     k_mc_flags<<<grid, 256, 0, st>>>(g, (uint32_t*)ballots_u32, lanes_x, pzb);
     T3D_CHECK_LAUNCH("t3d_mc_flags");
     t3d_count_launches(1);
@@ -450,11 +461,12 @@ extern "C" int t3d_mc_flags(const void* sign_bits, int Zs, int Hs, int Ws, void*
 }
 
 // chunkbase_u32: exclusive scan of popcount(ballots); aw_idx_u32: n_active; aw_cnt_u32: 4 arrays of n_active
-extern "C" int t3d_mc_words(const void* sign_bits, int Zs, int Hs, int Ws, const void* ballots_u32, const void* chunkbase_u32,
+extern "C" int t3d_mc_words(const void* sign_bits, int Zs, int Hs, int Ws, int z_begin, int z_end, const void* ballots_u32,
+                            const void* chunkbase_u32,
                             uint32_t n_active, void* aw_idx_u32, void* aw_cnt_u32, void* n_ambiguous_u64, void* stream)
 {
     Grid g;
-    if (int rc = make_grid(g, sign_bits, Zs, Hs, Ws, "t3d_mc_words")) return rc;
+    if (int rc = make_grid(g, sign_bits, Zs, Hs, Ws, z_begin, z_end, "t3d_mc_words")) return rc;
     if (ensure_luts()) return 1;
     cudaStream_t st = (cudaStream_t)stream;
     T3D_CUDA(cudaMemsetAsync(n_ambiguous_u64, 0, 8, st));
@@ -472,12 +484,13 @@ extern "C" int t3d_mc_words(const void* sign_bits, int Zs, int Hs, int Ws, const
 
 // aw_base_u32: exclusive scans of aw_cnt; n_x / n_y: totals of the x- and y-edge counts.
 // vkeys_u64: one key per vertex (n_x + n_y + n_z); faces_i32: (n_t, 3).
-extern "C" int t3d_mc_emit(const void* sign_bits, int Zs, int Hs, int Ws, const void* ballots_u32, const void* chunkbase_u32,
+extern "C" int t3d_mc_emit(const void* sign_bits, int Zs, int Hs, int Ws, int z_begin, int z_end, const void* ballots_u32,
+                           const void* chunkbase_u32,
                            const void* aw_idx_u32, const void* aw_base_u32, uint32_t n_active, uint32_t n_x, uint32_t n_y,
                            void* vkeys_u64, void* faces_i32, void* stream)
 {
     EmitArgs a;
-    if (int rc = make_grid(a.g, sign_bits, Zs, Hs, Ws, "t3d_mc_emit")) return rc;
+    if (int rc = make_grid(a.g, sign_bits, Zs, Hs, Ws, z_begin, z_end, "t3d_mc_emit")) return rc;
     if (ensure_luts()) return 1;
     if (n_active == 0) return 0;
     a.ballots = (const uint32_t*)ballots_u32;
@@ -500,7 +513,7 @@ extern "C" int t3d_mc_emit(const void* sign_bits, int Zs, int Hs, int Ws, const 
 // cum/adj: device float64 arrays of the variable-slice-depth z map (n_cum = 0 disables it).
 extern "C" int t3d_mc_vertices(const void* occ_bits, int Z, int H, int W, int pad, int gaussian, const double* weights3_host,
                                const void* vkeys_u64, uint32_t n_x, uint32_t n_y, uint32_t n_z, int unpad_shift,
-                               const void* cum_f64, const void* adj_f64, int n_cum, double mm_per_pixel_y,
+                               int z_offset, const void* cum_f64, const void* adj_f64, int n_cum, double mm_per_pixel_y,
                                double mm_per_pixel_x, int scale_in_f64, void* verts_f32, void* stream)
 {
     if (Z <= 0 || H <= 0 || W <= 0) { t3d_set_error("t3d_mc_vertices: empty volume"); return 2; }
@@ -510,6 +523,7 @@ extern "C" int t3d_mc_vertices(const void* occ_bits, int Z, int H, int W, int pa
     p.occ = t3d_make_view(occ_bits, Z, H, W, pad, gaussian, weights3_host);
     p.vkeys = (const unsigned long long*)vkeys_u64;
     p.shift = unpad_shift ? 1.0f : 0.0f;
+    p.z_offset = z_offset;
     p.cum = (const double*)cum_f64;
     p.adj = (const double*)adj_f64;
     p.n_cum = n_cum;

@@ -404,8 +404,12 @@ def exclusive_scan_u32(x: torch.Tensor, n: int, n_arrays: int, out_u64: bool = F
 
 
 def extract_surface(dv: DeviceVolume, slice_depths, mm_per_pixel_y, mm_per_pixel_x, manifold: bool = True,
-                    add_padding: bool = True, canonical: Optional[bool] = None, mark=None) -> DeviceMesh:
-    """surface_extractor.py:43-68 on the device.  Raises RuntimeError/ValueError where skimage would."""
+                    add_padding: bool = True, canonical: Optional[bool] = None, mark=None,
+                    z_begin: int = 0, z_end: int = -1, z_offset: int = 0) -> DeviceMesh:
+    """surface_extractor.py:43-68 on the device.  Raises RuntimeError/ValueError where skimage would.
+
+    z_begin / z_end / z_offset: z-slab sharding (sharded.py): owned planes of the local sign volume and the global
+    padded plane index of local padded plane 0."""
     L = _L()
     mark = mark or (lambda _n: None)
     Z, H, W = dv.shape
@@ -421,7 +425,7 @@ def extract_surface(dv: DeviceVolume, slice_depths, mm_per_pixel_y, mm_per_pixel
     mark("field_sign")
     n_chunks = int(L.t3d_mc_num_chunks(Zs, Hs, Ws))
     ballots = torch.empty(n_chunks, dtype=torch.int32, device=dev)
-    check(L.t3d_mc_flags(_p(sign), Zs, Hs, Ws, _p(ballots), _stream()), "t3d_mc_flags")
+    check(L.t3d_mc_flags(_p(sign), Zs, Hs, Ws, z_begin, z_end, _p(ballots), _stream()), "t3d_mc_flags")
     chunkbase, n_act_t = exclusive_scan_u32(ballots, n_chunks, 1, popcount_input=True)
     mark("mc_flags")
     n_active = int(n_act_t.cpu().item())
@@ -431,7 +435,7 @@ def extract_surface(dv: DeviceVolume, slice_depths, mm_per_pixel_y, mm_per_pixel
     aw_idx = torch.empty(n_active, dtype=torch.int32, device=dev)
     aw_cnt = torch.empty(4 * n_active, dtype=torch.int32, device=dev)
     n_amb = torch.empty(1, dtype=torch.int64, device=dev)
-    check(L.t3d_mc_words(_p(sign), Zs, Hs, Ws, _p(ballots), _p(chunkbase), n_active, _p(aw_idx), _p(aw_cnt), _p(n_amb),
+    check(L.t3d_mc_words(_p(sign), Zs, Hs, Ws, z_begin, z_end, _p(ballots), _p(chunkbase), n_active, _p(aw_idx), _p(aw_cnt), _p(n_amb),
                          _stream()), "t3d_mc_words")
     aw_base, totals = exclusive_scan_u32(aw_cnt, n_active, 4)
     mark("mc_words")
@@ -450,11 +454,12 @@ def extract_surface(dv: DeviceVolume, slice_depths, mm_per_pixel_y, mm_per_pixel
     cum_d = torch.from_numpy(cum).to(dev) if n_cum else None
     adj_d = torch.from_numpy(adj).to(dev) if n_cum else None
     strong = isinstance(mm_per_pixel_y, np.floating) or isinstance(mm_per_pixel_x, np.floating)
-    check(L.t3d_mc_emit(_p(sign), Zs, Hs, Ws, _p(ballots), _p(chunkbase), _p(aw_idx), _p(aw_base), n_active, nX, nY,
+    check(L.t3d_mc_emit(_p(sign), Zs, Hs, Ws, z_begin, z_end, _p(ballots), _p(chunkbase), _p(aw_idx), _p(aw_base), n_active,
+                        nX, nY,
                         _p(vkeys), _p(faces), _stream()), "t3d_mc_emit")
     mark("mc_emit")
     check(L.t3d_mc_vertices(_p(dv.bits), Z, H, W, pad, gaussian, _W3_C, _p(vkeys), nX, nY, nZ, 1 if manifold else 0,
-                            _p(cum_d), _p(adj_d), n_cum, float(mm_per_pixel_y), float(mm_per_pixel_x), 1 if strong else 0,
+                            z_offset, _p(cum_d), _p(adj_d), n_cum, float(mm_per_pixel_y), float(mm_per_pixel_x), 1 if strong else 0,
                             _p(verts), _stream()), "t3d_mc_vertices")
     mark("mc_vertices")
     if canonical is None:
