@@ -188,6 +188,7 @@ def run_ours(args, Z, H, W):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        os.environ["NCCL_DEBUG"] = os.environ.get("T3D_NCCL_DEBUG", "WARN")  # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
     from tomography_3d_reconstructor_b200 import _lib, engine, pipeline
     lib = _lib.load()

@@ -133,6 +133,20 @@ int64_t t3d_mesh_measure_workspace_bytes(void);
 int t3d_mesh_measure(const void* verts_f32, int64_t V, const void* faces, int64_t F, int faces_are_i64, void* out_f64,
                      void* workspace, void* stream);
 
+/* ---- additive stages (no reference counterpart) ------------------------------------- */
+
+/* Exact Euclidean distance transform (oracle: scipy.ndimage.distance_transform_edt(occ, sampling)): dist_f32 (Z,H,W) =
+ * sign * distance between voxel centres from every foreground voxel (bit set; bit clear if invert) to the nearest
+ * voxel of the other kind, 0 there, inf if there is none; accumulate != 0 adds into dist_f32.  sampling_host = {sz, sy,
+ * sx} (NULL = 1,1,1).  sdf = t3d_edt(invert 0, sign +1) then t3d_edt(invert 1, sign -1, accumulate 1). */
+int64_t t3d_edt_workspace_bytes(int Z, int H, int W);
+int t3d_edt(const void* occ_bits, int Z, int H, int W, int invert, const double* sampling_host, float sign, int accumulate,
+            void* dist_f32, void* workspace, void* stream);
+
+/* area-weighted unit vertex normals (the reference discards skimage's normals, surface_extractor.py:55 vs :72) */
+int t3d_vertex_normals(const void* verts_f32, int64_t V, const void* faces, int64_t F, int faces_are_i64, void* normals_f32,
+                       void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,78 @@
+"""The drop-in boundary: the reference orchestrator imports the three classes BY MODULE NAME
+(tomography_3d_reconstruction.py:14-17).  This test puts tomography_3d_reconstructor_b200/dropin first on sys.path,
+imports them exactly that way and replays the orchestrator's analyze_object_properties / export call sequence
+(tomography_3d_reconstruction.py:194-229, 231-268) on a config-0-like stack, against the oracle."""
+import contextlib
+import importlib
+import io
+import os
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_orchestrator_call_sequence_through_dropin_modules(eng, oracle, tmp_path):
+    dropin = os.path.join(ROOT, "tomography_3d_reconstructor_b200", "dropin")
+    sys.path.insert(0, dropin)
+    try:
+        for m in ("voxel_processor", "surface_extractor", "volume_calculator"):
+            sys.modules.pop(m, None)
+        VoxelProcessor = importlib.import_module("voxel_processor").VoxelProcessor
+        SurfaceExtractor = importlib.import_module("surface_extractor").SurfaceExtractor
+        VolumeCalculator = importlib.import_module("volume_calculator").VolumeCalculator
+    finally:
+        sys.path.remove(dropin)
+    assert VoxelProcessor.__module__.startswith("tomography_3d_reconstructor_b200")
+
+    # config-0-like input: 512x512 would be slow for the oracle; same structure at 128x160, 6+20+6 slices
+    Z, H, W = 32, 128, 160
+    sides = (6, 20, 6)
+    u8 = oracle.ellipsoid_phantom_u8(Z, H, W)
+    masks = [u8[z] >= 200 for z in range(Z)]               # image_loader.py:108
+    x_mm, y_mm, depth_mm = 143.1, 95.03, 6.0                # config.py:12-14
+    mm_x, mm_y = x_mm / W, y_mm / H                         # tomography_3d_reconstruction.py:62-63
+    out = io.StringIO()
+    with contextlib.redirect_stdout(out):
+        vp, se, vc = VoxelProcessor(), SurfaceExtractor(), VolumeCalculator()
+        vox = vp.create_voxel_data(masks, True, *sides)                                    # :92-95
+        depths = vp.calculate_slice_depths(depth_mm)                                       # :98
+        voxel_volume = vc.calculate_voxel_volume_variable_depth(vp.voxel_data, mm_x, mm_y, depths)      # :116
+        sm1 = vp.smooth_voxel_data(vp.voxel_data, iterations=3, create_manifold=True)       # :106
+        processed = vc.calculate_voxel_volume_variable_depth(sm1, mm_x, mm_y, depths)
+        sm2 = vp.smooth_voxel_data(vp.voxel_data, iterations=3, create_manifold=True)       # :123
+        res = se.extract_manifold_surface(sm2, depths, mm_y, mm_x, smooth=True, manifold=True, add_padding=True)   # :131
+        vertices, faces = res
+        mesh_volume = se.calculate_mesh_volume(vertices, faces)                             # :140
+        sm3 = vp.smooth_voxel_data(vp.voxel_data, iterations=3, create_manifold=True)       # :209
+        v2, f2 = se.extract_manifold_surface(sm3, depths, mm_y, mm_x, smooth=True, manifold=True, add_padding=True)
+        area = se.calculate_surface_area(v2, f2)                                            # :220
+        props = vc.analyze_object_properties(vp.voxel_data, processed, mesh_volume, area, mm_x, mm_y, depths,
+                                             x_mm, y_mm, depth_mm)                          # :225-229
+    log = out.getvalue()
+    assert "Voxels: (32, 128, 160), active:" in log and "Slice depth sequence: Side_0[0-5], Side_1[6-25], Side_2[26-31]" in log
+    assert "Surface: %d vertices, %d faces" % (len(vertices), len(faces)) in log and "Density:" in log
+
+    ref = oracle.reference_pipeline(u8, 200, sides, depth_mm, x_mm, y_mm)
+    assert np.array_equal(vox, ref["voxel_data"]) and np.array_equal(sm1, ref["smoothed"])
+    assert np.array_equal(vertices, ref["vertices"]) and np.array_equal(faces, ref["faces"])
+    assert np.array_equal(v2, vertices) and np.array_equal(f2, faces)
+    assert voxel_volume == ref["voxel_volume"] and processed == ref["processed_volume"]
+    assert abs(mesh_volume - ref["mesh_volume"]) <= 1e-6 * ref["mesh_volume"]
+    assert set(props) == {"volume_mm3", "voxel_volume_mm3", "processed_voxel_volume_mm3", "mesh_volume_mm3", "bounding_box",
+                          "dimensions", "surface_area_mm2", "density"}                     # volume_calculator.py:123-131
+    assert props["voxel_volume_mm3"] == ref["voxel_volume"] and props["volume_mm3"] == mesh_volume
+    bb = ref["bbox"]
+    assert props["bounding_box"] == {"x": bb["x"], "y": bb["y"], "z": bb["z"]} and props["dimensions"] == bb["dimensions"]
+
+    # consumers downstream of the hot path take the arrays as they are: OBJ writer semantics (obj_exporter.py:25-31)
+    obj = tmp_path / "m.obj"
+    with open(obj, "w") as f:
+        for v in vertices[:5]:
+            f.write(f"v {v[0]:.6f} {v[1]:.6f} {v[2]:.6f}\n")
+        for t in faces[:5]:
+            f.write(f"f {t[0]+1} {t[1]+1} {t[2]+1}\n")
+    assert obj.read_text().count("\n") == 10

@@ -1,0 +1,62 @@
+"""GPU parity of the additive exact EDT / SDF stage against scipy.ndimage.distance_transform_edt."""
+import numpy as np
+import pytest
+import torch
+from scipy import ndimage
+
+from conftest import random_blobs
+
+pytestmark = pytest.mark.gpu
+
+
+def dev_volume(eng, vol_bool):
+    return eng.pack(eng.upload_u8(np.ascontiguousarray(vol_bool).view(np.uint8)), 1)
+
+
+@pytest.mark.parametrize("shape", [(1, 1, 1), (3, 4, 5), (9, 17, 33), (12, 40, 70), (20, 33, 130), (6, 5, 1100)])
+@pytest.mark.parametrize("sampling", [(1.0, 1.0, 1.0), (0.09375, 0.31, 0.28)])
+def test_edt_matches_scipy(eng, shape, sampling):
+    from tomography_3d_reconstructor_b200 import edt
+    rng = np.random.default_rng(shape[2])
+    for density in (0.3, 0.9):
+        vol = random_blobs(rng, shape, density, 1.5) if min(shape) > 2 else rng.random(shape) < density
+        if vol.all():
+            vol.flat[0] = False
+        got = edt.distance(dev_volume(eng, vol), sampling).cpu().numpy()
+        ref = ndimage.distance_transform_edt(vol, sampling=sampling)
+        if sampling == (1.0, 1.0, 1.0):
+            assert np.array_equal(got, ref.astype(np.float32))                 # exact integer squared distances
+        else:
+            assert np.allclose(got, ref, rtol=1e-6, atol=0)
+
+
+def test_sdf_and_degenerate_volumes(eng, oracle):
+    from tomography_3d_reconstructor_b200 import edt, VoxelProcessor
+    vol = oracle.smooth_voxel_data(oracle.ellipsoid_phantom_u8(24, 48, 80) >= 200, 3, True)
+    got = edt.signed_distance(dev_volume(eng, vol)).cpu().numpy()
+    assert np.array_equal(got, oracle.signed_distance(vol))
+    assert (got[vol] > 0).all() and (got[~vol] < 0).all()
+    ones = np.ones((3, 4, 5), bool)
+    assert np.isposinf(edt.signed_distance(dev_volume(eng, ones)).cpu().numpy()).all()
+    assert np.isneginf(edt.signed_distance(dev_volume(eng, ~ones)).cpu().numpy()).all()
+    vp = VoxelProcessor()
+    assert np.array_equal(vp.compute_sdf(vol, (0.5, 1.0, 2.0)), oracle.signed_distance(vol, (0.5, 1.0, 2.0)))
+
+
+def test_vertex_normals(eng, oracle):
+    from tomography_3d_reconstructor_b200 import SurfaceExtractor
+    vol = oracle.smooth_voxel_data(oracle.ellipsoid_phantom_u8(24, 48, 64) >= 200, 3, True)
+    se = SurfaceExtractor()
+    v, f = se.extract_manifold_surface(vol, np.ones(24), 1.0, 1.0)
+    n = se.vertex_normals(v, f)
+    assert n.shape == v.shape and np.allclose(np.linalg.norm(n, axis=1), 1.0, atol=1e-5)
+    vv = v.astype(np.float64)
+    fn = np.cross(vv[f[:, 1]] - vv[f[:, 0]], vv[f[:, 2]] - vv[f[:, 0]])
+    acc = np.zeros_like(vv)
+    for k in range(3):
+        np.add.at(acc, f[:, k], fn)
+    acc /= np.linalg.norm(acc, axis=1, keepdims=True)
+    assert np.allclose(n, acc, atol=1e-4)
+    centre = vv.mean(axis=0)                     # one consistent orientation relative to the centroid
+    s = np.sign(np.einsum("ij,ij->i", n, vv - centre))
+    assert abs(s.mean()) > 0.99

@@ -46,6 +46,9 @@ SIGNATURES = {
     "t3d_mesh_canonicalize": (_i, [_vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "t3d_mesh_measure_workspace_bytes": (_i64, []),
     "t3d_mesh_measure": (_i, [_vp, _i64, _vp, _i64, _i, _vp, _vp, _vp]),
+    "t3d_edt_workspace_bytes": (_i64, [_i, _i, _i]),
+    "t3d_edt": (_i, [_vp, _i, _i, _i, _i, _vp, _c.c_float, _i, _vp, _vp, _vp]),
+    "t3d_vertex_normals": (_i, [_vp, _i64, _vp, _i64, _i, _vp, _vp]),
 }
 
 
