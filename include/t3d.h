@@ -128,6 +128,12 @@ int64_t t3d_canonicalize_workspace_bytes(int64_t V, int64_t F);
 int t3d_mesh_canonicalize(const void* verts_in, int64_t V, const void* faces_in, int64_t F, void* verts_out,
                           void* faces_out_i64, void* faces_out_i32, void* counts_u64, void* workspace, void* stream);
 
+/* Same outputs for meshes in t3d_mc_emit's vertex order ([x|y|z]-edge blocks, raster order inside each): ONE stable
+ * 64-bit (z,y)-key sort; counts_u64 has 3 entries, [2] != 0 = ordering not verified, call t3d_mesh_canonicalize. */
+int64_t t3d_canonicalize_fast_workspace_bytes(int64_t V, int64_t F);
+int t3d_mesh_canonicalize_fast(const void* verts_in, int64_t V, const void* faces_in, int64_t F, void* verts_out,
+                               void* faces_out_i64, void* faces_out_i32, void* counts_u64, void* workspace, void* stream);
+
 /* calculate_mesh_volume / calculate_surface_area (surface_extractor.py:128-148): out_f64 = {signed volume, area} */
 int64_t t3d_mesh_measure_workspace_bytes(void);
 int t3d_mesh_measure(const void* verts_f32, int64_t V, const void* faces, int64_t F, int faces_are_i64, void* out_f64,

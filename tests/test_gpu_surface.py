@@ -252,3 +252,17 @@ def test_mm_scaling_follows_numpy_promotion(eng, oracle):
         assert np.array_equal(got[0], ref[0]) or np.allclose(got[0], ref[0], rtol=1e-6, atol=0)
         assert np.array_equal(got[0][:, 0], ref[0][:, 0])       # z map is bit-exact
         assert np.array_equal(got[1], ref[1])
+
+
+def test_fast_canonicalize_falls_back_when_order_cannot_be_verified(eng, oracle):
+    rng = np.random.default_rng(17)
+    V, F = 4000, 7000
+    base = rng.integers(-3, 4, size=(300, 3)).astype(np.float32) * np.float32(0.41)
+    verts = base[rng.integers(0, 300, V)]                      # arbitrary order: the (z,y)-key shortcut is invalid here
+    faces = rng.integers(0, V, size=(F, 3)).astype(np.int32)
+    tv, tf = torch.from_numpy(verts).cuda(), torch.from_numpy(faces).cuda()
+    _, _, counts = eng.canonicalize(tv, tf, sync=False, fast=True)
+    assert int(counts[2].item()) != 0                          # detected on the device ...
+    gv, gf = eng.canonicalize(tv, tf, fast=True)               # ... and the synchronous call falls back
+    rv, rf = oracle.ensure_manifold_mesh(verts, faces)
+    assert np.array_equal(gv.cpu().numpy(), rv) and np.array_equal(gf.cpu().numpy(), rf)

@@ -86,10 +86,10 @@ def _worker(rank, world, port, q):
         sharded.exchange_halos(ext, hl, n, hh, rank, world)
         ok_halo = bool(torch.equal(ext, glob[z0 - hl:z1 + hh]))
         # the small all-gather + stitch arithmetic
-        local = torch.tensor([100 + 10 * rank, 7, 3 if rank + 1 < world else 0, 3 if rank else 0], dtype=torch.int64)
+        local = torch.tensor([100 + 10 * rank, 7, 0, 3 if rank + 1 < world else 0, 3 if rank else 0], dtype=torch.int64)
         got = [torch.empty_like(local) for _ in range(world)]
         dist.all_gather(got, local)
-        per_rank = [(int(g[0]), int(g[2]), int(g[3])) for g in got]
+        per_rank = [(int(g[0]), int(g[3]), int(g[4])) for g in got]
         bases, ok = sharded.stitch_offsets(per_rank)
         # gather of per-rank mesh slabs
         res = {"verts": torch.full((2 + rank, 3), float(rank)), "faces": torch.full((3 + rank, 3), rank, dtype=torch.int64)}

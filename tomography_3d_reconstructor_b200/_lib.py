@@ -44,6 +44,8 @@ SIGNATURES = {
     "t3d_cube_cases": (_i, [_vp, _i, _i, _i, _vp, _vp]),
     "t3d_canonicalize_workspace_bytes": (_i64, [_i64, _i64]),
     "t3d_mesh_canonicalize": (_i, [_vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "t3d_canonicalize_fast_workspace_bytes": (_i64, [_i64, _i64]),
+    "t3d_mesh_canonicalize_fast": (_i, [_vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "t3d_mesh_measure_workspace_bytes": (_i64, []),
     "t3d_mesh_measure": (_i, [_vp, _i64, _vp, _i64, _i, _vp, _vp, _vp]),
     "t3d_edt_workspace_bytes": (_i64, [_i, _i, _i]),

@@ -466,6 +466,110 @@ extern "C" int t3d_mesh_canonicalize(const void* verts_in, int64_t V, const void
 }
 
 // ------------------------------------------------------------------------------------------------
+// fast canonical mesh for meshes emitted by t3d_mc_emit.  The raw vertex order is [x-edge | y-edge | z-edge] blocks,
+// each in raster order of the owning voxel, so among vertices with equal (z, y) float keys the x keys are already
+// ascending (equal (z,y) keys across blocks would need a vertex coordinate to round onto a grid plane).  One STABLE
+// radix sort on the 64-bit key (z key << 32 | y key) therefore yields np.unique's lexicographic order.  The result is
+// verified on the device: counts_u64[2] != 0 means an adjacent pair was out of order and the caller must fall back
+// to t3d_mesh_canonicalize (three-key sort, valid for any input).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_make_keys64(const float* __restrict__ verts, int64_t V, unsigned long long* __restrict__ keys,
+                                                     uint32_t* __restrict__ iota)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= V) return;
+    keys[i] = ((unsigned long long)float_key(verts[3 * i]) << 32) | float_key(verts[3 * i + 1]);
+    iota[i] = (uint32_t)i;
+}
+
+// head flags of the sorted sequence + strict lexicographic order check (z, y, x)
+__global__ void __launch_bounds__(256) k_heads_checked(const float* __restrict__ verts, const uint32_t* __restrict__ perm, int64_t V,
+                                                       uint32_t* __restrict__ head, unsigned long long* __restrict__ bad)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= V) return;
+    uint32_t h = 1;
+    if (i > 0) {
+        const float* a = verts + 3 * (int64_t)perm[i];
+        const float* b = verts + 3 * (int64_t)perm[i - 1];
+        const uint32_t az = float_key(a[0]), ay = float_key(a[1]), ax = float_key(a[2]);
+        const uint32_t bz = float_key(b[0]), by = float_key(b[1]), bx = float_key(b[2]);
+        h = (az != bz || ay != by || ax != bx) ? 1u : 0u;
+        const bool lt = (az < bz) || (az == bz && (ay < by || (ay == by && ax < bx)));  // current < previous
+        if (lt) atomicOr(bad, 1ull);
+    }
+    head[i] = h;
+}
+
+static size_t sort64_temp_bytes(int64_t V)
+{
+    size_t bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const unsigned long long*)nullptr, (unsigned long long*)nullptr,
+                                    (const uint32_t*)nullptr, (uint32_t*)nullptr, (int)V);
+    return bytes;
+}
+
+extern "C" int64_t t3d_canonicalize_fast_workspace_bytes(int64_t V, int64_t F)
+{
+    const int64_t n = V > F ? V : F;
+    int64_t b = 0;
+    b += 2 * align256(8 * V);                       // keys in/out
+    b += 2 * align256(4 * V);                       // iota, perm
+    b += 2 * align256(4 * n);                       // flags, positions
+    b += align256(4 * V);                           // newid
+    b += align256((int64_t)sort64_temp_bytes(V > 0 ? V : 1));
+    b += align256(t3d_scan_workspace_bytes(n, 1));
+    b += 256;
+    return b;
+}
+
+// same outputs as t3d_mesh_canonicalize; counts_u64[0] = V', [1] = F', [2] = 0 if the fast ordering was verified
+extern "C" int t3d_mesh_canonicalize_fast(const void* verts_in, int64_t V, const void* faces_in, int64_t F, void* verts_out,
+                                          void* faces_out_i64, void* faces_out_i32, void* counts_u64, void* workspace,
+                                          void* stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    if (V <= 0 || V > 0x7fffffff || F < 0) { t3d_set_error("t3d_mesh_canonicalize_fast: bad sizes"); return 2; }
+    const int64_t n = V > F ? V : F;
+    char* ws = (char*)workspace;
+    unsigned long long* keys_a = (unsigned long long*)ws; ws += align256(8 * V);
+    unsigned long long* keys_b = (unsigned long long*)ws; ws += align256(8 * V);
+    uint32_t* iota = (uint32_t*)ws; ws += align256(4 * V);
+    uint32_t* perm = (uint32_t*)ws; ws += align256(4 * V);
+    uint32_t* flags = (uint32_t*)ws; ws += align256(4 * n);
+    uint32_t* pos = (uint32_t*)ws; ws += align256(4 * n);
+    uint32_t* newid = (uint32_t*)ws; ws += align256(4 * V);
+    size_t temp_bytes = sort64_temp_bytes(V);
+    void* temp = ws; ws += align256((int64_t)temp_bytes);
+    void* scan_ws = ws; ws += align256(t3d_scan_workspace_bytes(n, 1));
+    unsigned long long* totals = (unsigned long long*)ws;
+    unsigned long long* counts = (unsigned long long*)counts_u64;
+    const unsigned gv = (unsigned)((V + 255) / 256);
+    const float* vin = (const float*)verts_in;
+    T3D_CUDA(cudaMemsetAsync(counts + 2, 0, 8, st));
+    k_make_keys64<<<gv, 256, 0, st>>>(vin, V, keys_a, iota);
+    T3D_CUDA(cub::DeviceRadixSort::SortPairs(temp, temp_bytes, (const unsigned long long*)keys_a, keys_b, (const uint32_t*)iota, perm,
+                                             (int)V, 0, 64, st));
+    k_heads_checked<<<gv, 256, 0, st>>>(vin, perm, V, flags, counts + 2);
+    if (t3d_exclusive_scan_u32(flags, pos, V, 1, 0, 0, totals, scan_ws, stream)) return 1;
+    T3D_CUDA(cudaMemcpyAsync(counts, totals, 8, cudaMemcpyDeviceToDevice, st));
+    k_scatter_unique<<<gv, 256, 0, st>>>(vin, perm, flags, pos, V, (float*)verts_out, newid);
+    if (F > 0) {
+        const unsigned gf = (unsigned)((F + 255) / 256);
+        k_face_valid<<<gf, 256, 0, st>>>((const int32_t*)faces_in, F, newid, flags);
+        if (t3d_exclusive_scan_u32(flags, pos, F, 1, 0, 0, totals, scan_ws, stream)) return 1;
+        T3D_CUDA(cudaMemcpyAsync(counts + 1, totals, 8, cudaMemcpyDeviceToDevice, st));
+        k_face_compact<<<gf, 256, 0, st>>>((const int32_t*)faces_in, F, newid, flags, pos, (long long*)faces_out_i64,
+                                           (int32_t*)faces_out_i32);
+    } else {
+        T3D_CUDA(cudaMemsetAsync(counts + 1, 0, 8, st));
+    }
+    T3D_CHECK_LAUNCH("t3d_mesh_canonicalize_fast");
+    t3d_count_launches(F > 0 ? 5 : 3);
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
 // mesh measures: signed volume sum_f v0.(v1 x v2)/6 and area sum_f 0.5|(v1-v0)x(v2-v0)|, float64 terms and
 // float64 accumulation, fixed reduction order (warp-shuffle trees, then one block over the block partials)
 // ------------------------------------------------------------------------------------------------

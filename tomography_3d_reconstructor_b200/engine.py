@@ -142,7 +142,7 @@ class DeviceMesh:
     """Mesh on the device.  After an asynchronous canonicalisation the arrays are capacity-sized and the true sizes
     live in `counts_dev` until resolve() (one D2H copy) or set_sizes() trims them."""
 
-    __slots__ = ("_verts", "_faces", "counts_dev", "n_ambiguous", "n_exact", "_measures", "__weakref__")
+    __slots__ = ("_verts", "_faces", "counts_dev", "n_ambiguous", "n_exact", "_measures", "raw", "__weakref__")
 
     def __init__(self, verts: torch.Tensor, faces: torch.Tensor, n_ambiguous: int = 0, n_exact: int = 0,
                  counts_dev: Optional[torch.Tensor] = None):
@@ -150,15 +150,22 @@ class DeviceMesh:
         self.counts_dev = counts_dev
         self.n_ambiguous, self.n_exact = n_ambiguous, n_exact
         self._measures = None
+        self.raw = None  # (raw verts, raw faces) of an asynchronous canonicalisation, until the sizes are known
 
-    def set_sizes(self, n_verts: int, n_faces: int) -> None:
-        self._verts, self._faces = self._verts[:n_verts], self._faces[:n_faces]
+    def set_sizes(self, n_verts: int, n_faces: int, unverified: int = 0) -> None:
+        """Trim the capacity-sized arrays.  unverified != 0: the fast ordering failed its device-side check, redo the
+        canonicalisation with the general three-key sort (degenerate inputs only)."""
+        if unverified and self.raw is not None:
+            self._verts, self._faces = canonicalize(self.raw[0], self.raw[1], self._faces.dtype == torch.int64, True, False)
+        else:
+            self._verts, self._faces = self._verts[:n_verts], self._faces[:n_faces]
         self.counts_dev = None
+        self.raw = None
 
     def resolve(self) -> "DeviceMesh":
         if self.counts_dev is not None:
-            v2, f2 = (int(c) for c in self.counts_dev.cpu().tolist())
-            self.set_sizes(v2, f2)
+            v2, f2, bad = (int(c) for c in self.counts_dev.cpu().tolist())
+            self.set_sizes(v2, f2, bad)
         return self
 
     @property
@@ -418,6 +425,11 @@ def extract_surface(dv: DeviceVolume, slice_depths, mm_per_pixel_y, mm_per_pixel
     if Z + 2 * pad < 2 or H + 2 * pad < 2 or W + 2 * pad < 2:
         raise ValueError("Input array must be at least 2x2x2.")
     dev = dv.bits.device
+    # host-side constants go up before the first synchronisation point
+    cum, adj = z_map_arrays(slice_depths, add_padding)
+    n_cum = len(cum)
+    cum_d = torch.from_numpy(cum).to(dev, non_blocking=True) if n_cum else None
+    adj_d = torch.from_numpy(adj).to(dev, non_blocking=True) if n_cum else None
     if gaussian:
         sign, (Zs, Hs, Ws), n_exact_t = field_sign(dv, pad)
     else:
@@ -449,10 +461,6 @@ def extract_surface(dv: DeviceVolume, slice_depths, mm_per_pixel_y, mm_per_pixel
     verts = torch.empty((V, 3), dtype=torch.float32, device=dev)
     faces = torch.empty((nT, 3), dtype=torch.int32, device=dev)
     vkeys = torch.empty(V, dtype=torch.int64, device=dev)
-    cum, adj = z_map_arrays(slice_depths, add_padding)
-    n_cum = len(cum)
-    cum_d = torch.from_numpy(cum).to(dev) if n_cum else None
-    adj_d = torch.from_numpy(adj).to(dev) if n_cum else None
     strong = isinstance(mm_per_pixel_y, np.floating) or isinstance(mm_per_pixel_x, np.floating)
     check(L.t3d_mc_emit(_p(sign), Zs, Hs, Ws, z_begin, z_end, _p(ballots), _p(chunkbase), _p(aw_idx), _p(aw_base), n_active,
                         nX, nY,
@@ -467,31 +475,43 @@ def extract_surface(dv: DeviceVolume, slice_depths, mm_per_pixel_y, mm_per_pixel
     if not canonical:
         return DeviceMesh(verts, faces, n_ambiguous, n_exact)
     if canonical == "async":
-        v2, f2, counts = canonicalize(verts, faces, sync=False)
+        v2, f2, counts = canonicalize(verts, faces, sync=False, fast=True)
         mark("canonicalize")
         m = DeviceMesh(v2, f2, n_ambiguous, n_exact, counts_dev=counts)
-        m._measures = (verts, faces)  # raw mesh, for pipeline.reconstruct (replaced by the numbers there)
+        m.raw = (verts, faces)
         return m
-    v2, f2 = canonicalize(verts, faces)
+    v2, f2 = canonicalize(verts, faces, fast=True)
     mark("canonicalize")
     return DeviceMesh(v2, f2, n_ambiguous, n_exact)
 
 
-def canonicalize(verts: torch.Tensor, faces_i32: torch.Tensor, faces_i64: bool = True, sync: bool = True):
-    """_ensure_manifold_mesh (surface_extractor.py:115-126) on the device.  sync=False returns capacity-sized
-    arrays plus the device tensor holding (V', F')."""
+def canonicalize(verts: torch.Tensor, faces_i32: torch.Tensor, faces_i64: bool = True, sync: bool = True,
+                 fast: bool = False):
+    """_ensure_manifold_mesh (surface_extractor.py:115-126) on the device.
+
+    fast=True (meshes in t3d_mc_emit's vertex order only): one stable 64-bit (z,y)-key sort, verified on the device;
+    if the verification fails the general three-key path runs instead (sync=True) or the caller must do so
+    (sync=False: returns capacity-sized arrays and the device tensor (V', F', unverified-flag))."""
     L = _L()
     V, F = int(verts.shape[0]), int(faces_i32.shape[0])
     dev = verts.device
-    ws = torch.empty(int(L.t3d_canonicalize_workspace_bytes(V, F)) // 8 + 1, dtype=torch.int64, device=dev)
     vout = torch.empty((V, 3), dtype=torch.float32, device=dev)
     fout = torch.empty((F, 3), dtype=torch.int64 if faces_i64 else torch.int32, device=dev)
-    counts = torch.empty(2, dtype=torch.int64, device=dev)
-    check(L.t3d_mesh_canonicalize(_p(verts), V, _p(faces_i32), F, _p(vout), _p(fout) if faces_i64 else None,
-                                  None if faces_i64 else _p(fout), _p(counts), _p(ws), _stream()), "t3d_mesh_canonicalize")
+    counts = torch.zeros(3, dtype=torch.int64, device=dev)
+    f64, f32 = (_p(fout), None) if faces_i64 else (None, _p(fout))
+    if fast:
+        ws = torch.empty(int(L.t3d_canonicalize_fast_workspace_bytes(V, F)) // 8 + 1, dtype=torch.int64, device=dev)
+        check(L.t3d_mesh_canonicalize_fast(_p(verts), V, _p(faces_i32), F, _p(vout), f64, f32, _p(counts), _p(ws), _stream()),
+              "t3d_mesh_canonicalize_fast")
+    else:
+        ws = torch.empty(int(L.t3d_canonicalize_workspace_bytes(V, F)) // 8 + 1, dtype=torch.int64, device=dev)
+        check(L.t3d_mesh_canonicalize(_p(verts), V, _p(faces_i32), F, _p(vout), f64, f32, _p(counts), _p(ws), _stream()),
+              "t3d_mesh_canonicalize")
     if not sync:
         return vout, fout, counts
-    v2, f2 = (int(c) for c in counts.cpu().tolist())
+    v2, f2, bad = (int(c) for c in counts.cpu().tolist())
+    if bad:
+        return canonicalize(verts, faces_i32, faces_i64, True, False)
     return vout[:v2], fout[:f2]
 
 

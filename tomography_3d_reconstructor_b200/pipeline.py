@@ -30,10 +30,13 @@ def variable_depth_volume(counts: np.ndarray, mm_x: float, mm_y: float, depths: 
     """volume_calculator.py:23-35 on exact per-slice counts, same float64 order."""
     if len(depths) == 0:
         return 0.0
-    total = 0.0
-    for z in range(min(len(counts), len(depths))):
-        total += counts[z] * (mm_x * mm_y * depths[z])
-    return total
+    n = min(len(counts), len(depths))
+    if n == 0:
+        return 0.0
+    # the reference's loop `total += count[z] * (mm_x * mm_y * depth[z])`, vectorised without changing a bit:
+    # the products are the same float64 operations and np.cumsum accumulates strictly left to right
+    prod = np.asarray(counts[:n], dtype=np.int64).astype(np.float64) * ((mm_x * mm_y) * np.asarray(depths[:n], dtype=np.float64))
+    return float(np.cumsum(prod)[-1])
 
 
 def reconstruct(masks_u8: torch.Tensor, threshold: int, side_counts, total_depth_mm: float, x_length_mm: float,
@@ -64,8 +67,7 @@ def reconstruct(masks_u8: torch.Tensor, threshold: int, side_counts, total_depth
     mesh = engine.extract_surface(sm, depths, mm_y, mm_x, True, add_padding, canonical="async", mark=mark)
     # measures on the emitted (pre-canonical) mesh: merging exact duplicates and dropping zero-area faces changes
     # neither the signed volume nor the area, and it removes a dependency on the canonical sizes
-    raw_verts, raw_faces = mesh._measures
-    mesh._measures = None
+    raw_verts, raw_faces = mesh.raw
     meas = engine.mesh_measure_async(raw_verts, raw_faces)
     mark("measure")
     main.wait_event(bbox_done)
@@ -74,12 +76,12 @@ def reconstruct(masks_u8: torch.Tensor, threshold: int, side_counts, total_depth
     packed = torch.cat([mesh.counts_dev, meas.view(torch.int64), dv.counts_tensor(), sm.counts_tensor(),
                         bbox_t.to(torch.int64)]).cpu()
     mark("stats")
-    mesh.set_sizes(int(packed[0]), int(packed[1]))
-    signed_volume, area = (float(x) for x in packed[2:4].view(torch.float64).tolist())
+    mesh.set_sizes(int(packed[0]), int(packed[1]), int(packed[2]))
+    signed_volume, area = (float(x) for x in packed[3:5].view(torch.float64).tolist())
     mesh._measures = (signed_volume, area)
-    raw_counts = packed[4:4 + Zc].numpy().astype(np.int64)
-    sm_counts = packed[4 + Zc:4 + 2 * Zc].numpy().astype(np.int64)
-    bb = tuple(int(x) for x in packed[4 + 2 * Zc:].tolist())
+    raw_counts = packed[5:5 + Zc].numpy().astype(np.int64)
+    sm_counts = packed[5 + Zc:5 + 2 * Zc].numpy().astype(np.int64)
+    bb = tuple(int(x) for x in packed[5 + 2 * Zc:].tolist())
     dv.set_host_stats(raw_counts, bb)
     sm.set_host_stats(sm_counts, None)
     bbox = dv.bbox()

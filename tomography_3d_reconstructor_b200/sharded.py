@@ -119,7 +119,7 @@ def slab_local(s: Slab, side_counts, total_depth_mm: float, x_length_mm: float, 
                add_padding: bool = True, mark=None) -> torch.Tensor:
     """Phases 3-4 (after the halo exchange): gap fill + smoothing on the extended buffer, surface of the owned cube
     layers, local canonical mesh.  Returns the int64 vector this rank contributes to the small all-gather:
-    [V' incl. ghosts, F', ghost tail, lead, signed volume bits, area bits, bbox(6, local z)]."""
+    [V' incl. ghosts, F', unverified-order flag, ghost tail, lead, signed volume bits, area bits, bbox(6, local z)]."""
     mark = mark or (lambda _n: None)
     L = engine._L()
     p, st = engine._p, engine._stream
@@ -143,13 +143,12 @@ def slab_local(s: Slab, side_counts, total_depth_mm: float, x_length_mm: float, 
     try:
         mesh = engine.extract_surface(loc, depths, mm_y, mm_x, True, add_padding, canonical="async", mark=mark,
                                       z_begin=a - z_offset, z_end=b - z_offset, z_offset=z_offset)
-        raw_verts, raw_faces = mesh._measures
-        mesh._measures = None
+        raw_verts, raw_faces = mesh.raw
         meas = engine.mesh_measure_async(raw_verts, raw_faces)
         counts_mesh = mesh.counts_dev
     except RuntimeError:       # this slab holds no surface
         mesh, meas = None, torch.zeros(2, dtype=torch.float64, device=dev)
-        counts_mesh = torch.zeros(2, dtype=torch.int64, device=dev)
+        counts_mesh = torch.zeros(3, dtype=torch.int64, device=dev)
     mark("measure")
     s.mesh = mesh
     # ghost tail / lead: canonical vertices lying exactly on the next rank's first plane / on our first plane
@@ -173,11 +172,12 @@ def finalize(s: Slab, rank: int, host: torch.Tensor, raw_counts: np.ndarray, sm_
     """Phase 5: host[r] = the vector of slab_local() of every rank; counts = global per-slice voxel counts."""
     mm_x, mm_y = x_length_mm / s.W, y_length_mm / s.H
     depths = pipeline.slice_depths(total_depth_mm, *side_counts)
-    per_rank = [(int(host[r, 0]), int(host[r, 2]), int(host[r, 3])) for r in range(host.shape[0])]
+    per_rank = [(int(host[r, 0]), int(host[r, 3]), int(host[r, 4])) for r in range(host.shape[0])]
     bases, consistent = stitch_offsets(per_rank)
-    meas_all = host[:, 4:6].contiguous().view(torch.float64)
+    consistent = consistent and not bool(host[:, 2].any())   # a rank whose fast ordering failed needs the general path
+    meas_all = host[:, 5:7].contiguous().view(torch.float64)
     signed_volume, area = float(meas_all[:, 0].sum()), float(meas_all[:, 1].sum())
-    bbs = host[:, 6:12].numpy().copy()
+    bbs = host[:, 7:13].numpy().copy()
     nonempty = bbs[:, 1] >= 0
     bbox = None
     if nonempty.any():
@@ -188,7 +188,7 @@ def finalize(s: Slab, rank: int, host: torch.Tensor, raw_counts: np.ndarray, sm_
                 int(q[:, 5].max()))
     v_own = per_rank[rank][0] - per_rank[rank][1]
     if s.mesh is not None:
-        s.mesh.set_sizes(per_rank[rank][0], int(host[rank, 1]))
+        s.mesh.set_sizes(per_rank[rank][0], int(host[rank, 1]), 0)
         verts_own = s.mesh._verts[:v_own]
         faces_global = s.mesh._faces + bases[rank]
     else:
