@@ -206,8 +206,12 @@ def run_ours(args, Z, H, W):
         if world > 1:
             return sharded.reconstruct(masks, Zg, z0, THRESHOLD, sides, PHYS["total_depth_mm"], PHYS["x_length_mm"],
                                        PHYS["y_length_mm"], mark=mark)
-        return pipeline.reconstruct(masks, THRESHOLD, sides, PHYS["total_depth_mm"], PHYS["x_length_mm"],
-                                    PHYS["y_length_mm"], mark=mark)
+        if mark is not None or args.staged:   # staged path: one library call per stage (per-stage event timing)
+            return pipeline.reconstruct(masks, THRESHOLD, sides, PHYS["total_depth_mm"], PHYS["x_length_mm"],
+                                        PHYS["y_length_mm"], mark=mark)
+        # fused path: the whole step is one t3d_reconstruct enqueue replayed from a CUDA graph + one D2H copy
+        return pipeline.reconstruct_fused(masks, THRESHOLD, sides, PHYS["total_depth_mm"], PHYS["x_length_mm"],
+                                          PHYS["y_length_mm"], use_graph=not args.no_graph)
 
     def barrier():
         if world > 1:
@@ -216,6 +220,15 @@ def run_ours(args, Z, H, W):
 
     for _ in range(max(3, args.warmup)):
         res = step()
+    barrier()
+    # kernels of this library per step: counted on one eager (non-graph) step, a graph replay launches the same ones
+    lc0 = lib.t3d_launch_count()
+    if world == 1 and not args.staged:
+        pipeline.reconstruct_fused(masks, THRESHOLD, sides, PHYS["total_depth_mm"], PHYS["x_length_mm"], PHYS["y_length_mm"],
+                                   use_graph=False)
+    else:
+        step()
+    launches_per_step = lib.t3d_launch_count() - lc0
     barrier()
     l0 = lib.t3d_launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -227,7 +240,7 @@ def run_ours(args, Z, H, W):
         ev1.record()
         barrier()
     ms = ev0.elapsed_time(ev1)
-    launches = (lib.t3d_launch_count() - l0) // max(1, args.steps)
+    launches = launches_per_step
     if world > 1:
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -326,7 +339,9 @@ def run_ours(args, Z, H, W):
                    "close ends + opening/closing + Gaussian(0.5) marching cubes + volumes%s" %
                    (Zg, H, W, "" if world == 1 else "; z-slab sharded over %d GPUs" % world),
                    "shape": [Zg, H, W], "l2": "inputs larger than L2: %.0f MB of u8 masks per GPU per step" % (per_gpu_vox / 1e6),
-                   "mesh": {"vertices": V, "faces": F, "n_ambiguous_cubes": int(mesh.n_ambiguous)}},
+                   "mesh": {"vertices": V, "faces": F, "n_ambiguous_cubes": int(mesh.n_ambiguous)},
+                   "execution": ("z-slab sharded, staged launches" if world > 1 else "staged launches" if args.staged else
+                                 "one t3d_reconstruct enqueue per step" + ("" if args.no_graph else ", replayed from a CUDA graph"))},
         "clocks": clocks.summary(),
         "gpu_launches": int(launches),
         "stages_ms": stage_ms,
@@ -361,6 +376,8 @@ def main():
     ap.add_argument("--shape", default="512,1024,1024", help="Z,H,W per GPU")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--staged", action="store_true", help="time the staged (one call per stage) path instead of the fused one")
+    ap.add_argument("--no-graph", action="store_true", help="fused path without CUDA-graph replay")
     args = ap.parse_args()
     Z, H, W = (int(v) for v in args.shape.split(","))
     if args.impl == "reference":

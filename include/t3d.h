@@ -139,6 +139,45 @@ int64_t t3d_mesh_measure_workspace_bytes(void);
 int t3d_mesh_measure(const void* verts_f32, int64_t V, const void* faces, int64_t F, int faces_are_i64, void* out_f64,
                      void* workspace, void* stream);
 
+/* ---- device-resident sizes: the whole path as one enqueue --------------------------------------------------
+ * Variants whose data-dependent sizes stay in device memory (sizes_u64 = {n_active, n_x, n_y, n_z, n_t}, or a single
+ * uint64): arrays are capacity-sized, nothing is written beyond a capacity, no host round trip => graph-capturable. */
+int t3d_exclusive_scan_u32_dev(const void* in, void* out, int64_t n_cap, int64_t stride, int n_arrays, int out_is_u64,
+                               int popcount_input, const void* n_dev_u64, void* totals_u64, void* workspace, void* stream);
+int t3d_mc_words_dev(const void* sign_bits, int Zs, int Hs, int Ws, int z_begin, int z_end, const void* ballots_u32,
+                     const void* chunkbase_u32, uint32_t cap_active, const void* sizes_u64, void* aw_idx_u32, void* aw_cnt_u32,
+                     void* n_ambiguous_u64, void* stream);
+int t3d_mc_emit_dev(const void* sign_bits, int Zs, int Hs, int Ws, int z_begin, int z_end, const void* ballots_u32,
+                    const void* chunkbase_u32, const void* aw_idx_u32, const void* aw_base_u32, uint32_t cap_active,
+                    const void* sizes_u64, uint32_t cap_verts, uint32_t cap_faces, void* vkeys_u64, void* faces_i32, void* stream);
+int t3d_mc_vertices_dev(const void* occ_bits, int Z, int H, int W, int pad, int gaussian, const double* weights3_host,
+                        const void* vkeys_u64, const void* sizes_u64, uint32_t cap_verts, int unpad_shift, int z_offset,
+                        const void* cum_f64, const void* adj_f64, int n_cum, double mm_per_pixel_y, double mm_per_pixel_x,
+                        int scale_in_f64, void* verts_f32, void* stream);
+int t3d_mesh_canonicalize_fast_dev(const void* verts_in, int64_t V_cap, const void* V_dev_u64, const void* faces_in, int64_t F_cap,
+                                   const void* F_dev_u64, void* verts_out, void* faces_out_i64, void* faces_out_i32,
+                                   void* counts_u64, void* workspace, void* stream);
+int t3d_mesh_measure_dev(const void* verts_f32, const void* faces, int64_t F_cap, const void* F_dev_u64, int faces_are_i64,
+                         void* out_f64, void* workspace, void* stream);
+
+/* The whole hot path in the order tomography_3d_reconstruction.py runs it (create_voxel_data :88-100, smooth + extract +
+ * mesh volume :120-140, surface area :207-223, analyze :225-229) as ONE enqueue on `stream` (plus an internal side stream,
+ * forked/joined with events): uint8 masks (Z,H,W) -> verts_out_f32 (cap_verts,3) / faces_out_i64 (cap_faces,3) in canonical
+ * order + the result block results_u64[t3d_reconstruct_results_len(Z)]:
+ *   [0] n_active [1] n_x [2] n_y [3] n_z [4] n_t (raw faces) [5] V' [6] F' [7] fast ordering unverified [8] overflow bits
+ *   (1: active words, 2: vertices, 4: faces exceeded their capacity -> retry larger) [9] ambiguous cubes [10] exact field
+ *   evaluations [11] signed mesh volume (f64) [12] area (f64) [13..15] bbox int32 x 6 [16] raw vertices
+ *   [32 .. 32+Z) per-slice voxel counts after close_ends, [32+Z .. 32+2Z) after smoothing.
+ * n_stages/erode_mask as t3d_morph (0 stages = no smoothing).  cum/adj: device float64 z-map arrays. */
+int64_t t3d_reconstruct_workspace_bytes(int Z, int H, int W, int add_padding, int n_stages, uint32_t cap_active,
+                                        uint32_t cap_verts, uint32_t cap_faces);
+int64_t t3d_reconstruct_results_len(int Z);
+int t3d_reconstruct(const void* masks_u8, int Z, int H, int W, int threshold, int close_ends, int n_stages, unsigned erode_mask,
+                    int add_padding, const double* weights3_host, const void* cum_f64, const void* adj_f64, int n_cum,
+                    double mm_per_pixel_y, double mm_per_pixel_x, int scale_in_f64, uint32_t cap_active, uint32_t cap_verts,
+                    uint32_t cap_faces, void* verts_out_f32, void* faces_out_i64, void* results_u64, void* workspace,
+                    void* stream);
+
 /* ---- additive stages (no reference counterpart) ------------------------------------- */
 
 /* Exact Euclidean distance transform (oracle: scipy.ndimage.distance_transform_edt(occ, sampling)): dist_f32 (Z,H,W) =

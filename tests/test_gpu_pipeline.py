@@ -71,3 +71,39 @@ def test_sharded_slabs_stitch_to_the_single_gpu_mesh(eng, oracle, shape, world):
     assert abs(o["mesh_volume_mm3"] - ref["mesh_volume_mm3"]) <= 1e-9 * ref["mesh_volume_mm3"]
     assert abs(o["surface_area_mm2"] - ref["surface_area_mm2"]) <= 1e-9 * ref["surface_area_mm2"]
     assert o["total_vertices"] == len(rv) and o["total_faces"] == len(rf)
+
+
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_fused_single_enqueue_path_matches_staged_path(eng, oracle, use_graph):
+    """t3d_reconstruct (one enqueue, device-resident sizes, optionally replayed from a CUDA graph) against the staged
+    path and the oracle, including capacity overflow -> fallback."""
+    from tomography_3d_reconstructor_b200 import pipeline
+    Z, H, W = 40, 96, 128
+    sides = (5, 30, 5)
+    args = (200, sides, 6.0, 143.1, 95.03)
+    u8 = oracle.ellipsoid_phantom_u8(Z, H, W)
+    u8[0, 46:50, 60:68] = 0
+    masks = torch.from_numpy(u8).cuda()
+    pipeline._plans.clear(); pipeline._hints.clear()
+    first = pipeline.reconstruct_fused(masks, *args, use_graph=use_graph)      # staged: learns the sizes
+    ref = oracle.reference_pipeline(u8, 200, sides, 6.0, 143.1, 95.03)
+    for rep in range(3):                                                      # fused (graph replayed on reps 2, 3)
+        out = pipeline.reconstruct_fused(masks, *args, use_graph=use_graph)
+        v, f = out["mesh"].verts.cpu().numpy(), out["mesh"].faces.cpu().numpy()
+        assert np.array_equal(v, ref["vertices"]) and np.array_equal(f, ref["faces"])
+        assert out["voxel_volume_mm3"] == ref["voxel_volume"] == first["voxel_volume_mm3"]
+        assert out["processed_voxel_volume_mm3"] == ref["processed_volume"]
+        assert abs(out["mesh_volume_mm3"] - ref["mesh_volume"]) <= 1e-6 * ref["mesh_volume"]
+        assert abs(out["surface_area_mm2"] - ref["surface_area"]) <= 1e-6 * ref["surface_area"]
+        assert out["bbox_index"] == first["bbox_index"] and out["active_voxels"] == first["active_voxels"]
+    assert len(pipeline._plans) == 1
+    # a much larger object in the same buffer overflows the capacities: detected on the device, staged fallback
+    big = oracle.ellipsoid_phantom_u8(Z, H, W).copy()
+    big[:, 4:-4, 4:-4] = 255
+    big[::2, ::3, ::5] = 0
+    masks.copy_(torch.from_numpy(big))
+    out = pipeline.reconstruct_fused(masks, *args, use_graph=use_graph)
+    ref2 = oracle.reference_pipeline(big, 200, sides, 6.0, 143.1, 95.03)
+    assert np.array_equal(out["mesh"].verts.cpu().numpy(), ref2["vertices"])
+    assert np.array_equal(out["mesh"].faces.cpu().numpy(), ref2["faces"])
+    assert out["voxel_volume_mm3"] == ref2["voxel_volume"]

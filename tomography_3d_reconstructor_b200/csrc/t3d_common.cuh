@@ -127,3 +127,13 @@ __device__ __forceinline__ uint4 shr1_4(uint4 c, uint32_t r)
 {
     return make_uint4(__funnelshift_r(c.x, c.y, 1), __funnelshift_r(c.y, c.z, 1), __funnelshift_r(c.z, c.w, 1), __funnelshift_r(c.w, r, 1));
 }
+
+// Sizes that only the device knows (number of active words, vertices, faces ...) are passed as a capacity plus an
+// optional pointer to the true value in device memory, so that a whole step can be enqueued (and graph-captured)
+// without a host round trip.  n = min(cap, *p) when p is given, else cap.
+__device__ __forceinline__ int64_t dev_n(int64_t cap, const unsigned long long* p)
+{
+    if (!p) return cap;
+    const unsigned long long v = *p;
+    return v < (unsigned long long)cap ? (int64_t)v : cap;
+}

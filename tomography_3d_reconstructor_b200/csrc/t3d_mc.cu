@@ -198,7 +198,7 @@ __global__ void __launch_bounds__(256) k_mc_flags(Grid g, uint32_t* __restrict__
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_mc_compact(Grid g, const uint32_t* __restrict__ ballots,
                                                     const uint32_t* __restrict__ chunkbase, int64_t n_chunks,
-                                                    uint32_t* __restrict__ aw_idx)
+                                                    uint32_t* __restrict__ aw_idx, uint32_t cap_active)
 {
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= n_chunks) return;
@@ -210,15 +210,18 @@ __global__ void __launch_bounds__(256) k_mc_compact(Grid g, const uint32_t* __re
     while (bal) {
         const int b = __ffs(bal) - 1;
         bal &= bal - 1;
-        aw_idx[k++] = base + b;
+        if (k < cap_active) aw_idx[k] = base + b;  // beyond the capacity: dropped, the caller sees n_active > capacity
+        ++k;
     }
 }
 
-__global__ void __launch_bounds__(128) k_mc_words(Grid g, const uint32_t* __restrict__ aw_idx, uint32_t n_active,
-                                                  uint32_t* __restrict__ aw_cnt, unsigned long long* __restrict__ n_ambiguous)
+__global__ void __launch_bounds__(128) k_mc_words(Grid g, const uint32_t* __restrict__ aw_idx, uint32_t cap_active,
+                                                  const unsigned long long* __restrict__ n_active_dev, uint32_t* __restrict__ aw_cnt,
+                                                  unsigned long long* __restrict__ n_ambiguous)
 {
+    const uint32_t n_active = cap_active;  // array stride
     const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n_active) return;
+    if ((int64_t)k >= dev_n(cap_active, n_active_dev)) return;
     const uint32_t i = aw_idx[k];
     const uint32_t row = i / (uint32_t)g.nws;
     const int w = (int)(i - row * (uint32_t)g.nws);
@@ -247,9 +250,11 @@ struct EmitArgs {
     const uint32_t* ballots;
     const uint32_t* chunkbase;
     const uint32_t* aw_idx;
-    const uint32_t* aw_base;  // 4 arrays of n_active: X, Y, Z, T (exclusive scans)
-    uint32_t n_active;
+    const uint32_t* aw_base;  // 4 arrays, `n_active` (= capacity) elements apart: X, Y, Z, T (exclusive scans)
+    uint32_t n_active;        // number of active words, or the capacity of the arrays when `sizes` is given
     uint32_t offY, offZ;      // offX = 0
+    const unsigned long long* sizes;  // optional device block {n_active, n_x, n_y, n_z, n_t}: overrides the three above
+    uint32_t cap_verts, cap_faces;    // with `sizes`: nothing is written beyond these
     unsigned long long* vkeys;  // per vertex: axis | x << 2 | y << 22 | z << 42
     int32_t* faces;
 };
@@ -278,6 +283,12 @@ __global__ void __launch_bounds__(128) k_mc_emit(EmitArgs a)
     }
     __syncthreads();
     const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a.sizes) {
+        if ((unsigned long long)k >= a.sizes[0]) return;
+        a.offY = (uint32_t)a.sizes[1];
+        a.offZ = (uint32_t)(a.sizes[1] + a.sizes[2]);
+        if (a.sizes[1] + a.sizes[2] + a.sizes[3] > a.cap_verts || a.sizes[4] > a.cap_faces) return;  // overflow: flagged by the caller
+    }
     if (k >= a.n_active) return;
     const uint32_t i = a.aw_idx[k];
     const uint32_t row = i / (uint32_t)a.g.nws;
@@ -378,14 +389,8 @@ struct VertexArgs {
 };
 
 template <int AXIS>
-__global__ void __launch_bounds__(128) k_mc_vertices(VertexArgs p)
+__device__ __forceinline__ void vertex_body(const VertexArgs& p, const double* zlut, uint32_t id)
 {
-    __shared__ double zlut[18];
-    fill_zlut(p.occ, zlut);
-    __syncthreads();
-    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= p.count) return;
-    const uint32_t id = p.first + t;
     const unsigned long long key = p.vkeys[id];
     const int x = (int)((key >> 2) & 0xfffffu), y = (int)((key >> 22) & 0xfffffu), z = (int)(key >> 42);
     float fa, fb;
@@ -421,6 +426,32 @@ __global__ void __launch_bounds__(128) k_mc_vertices(VertexArgs p)
     }
     float* o = p.verts + 3 * (int64_t)id;
     o[0] = fz; o[1] = fy; o[2] = fx;
+}
+
+
+template <int AXIS>
+__global__ void __launch_bounds__(128) k_mc_vertices(VertexArgs p)
+{
+    __shared__ double zlut[18];
+    fill_zlut(p.occ, zlut);
+    __syncthreads();
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= p.count) return;
+    vertex_body<AXIS>(p, zlut, p.first + t);
+}
+
+// all three axis blocks in one launch, block sizes read from device memory (sizes = {n_active, n_x, n_y, n_z, n_t})
+__global__ void __launch_bounds__(128) k_mc_vertices_all(VertexArgs p, const unsigned long long* __restrict__ sizes, uint32_t cap_verts)
+{
+    __shared__ double zlut[18];
+    fill_zlut(p.occ, zlut);
+    __syncthreads();
+    const unsigned long long nx = sizes[1], ny = sizes[2], nz = sizes[3];
+    if (nx + ny + nz > cap_verts) return;
+    const uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id < nx) vertex_body<2>(p, zlut, id);
+    else if (id < nx + ny) vertex_body<1>(p, zlut, id);
+    else if (id < nx + ny + nz) vertex_body<0>(p, zlut, id);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -474,9 +505,9 @@ extern "C" int t3d_mc_words(const void* sign_bits, int Zs, int Hs, int Ws, int z
     const int64_t n_chunks = (int64_t)g.n_rows * g.ncr;
     k_mc_compact<<<(unsigned)((n_chunks + 255) / 256), 256, 0, st>>>(g, (const uint32_t*)ballots_u32,
                                                                       (const uint32_t*)chunkbase_u32, n_chunks,
-                                                                      (uint32_t*)aw_idx_u32);
-    k_mc_words<<<(n_active + 127) / 128, 128, 0, st>>>(g, (const uint32_t*)aw_idx_u32, n_active, (uint32_t*)aw_cnt_u32,
-                                                       (unsigned long long*)n_ambiguous_u64);
+                                                                      (uint32_t*)aw_idx_u32, n_active);
+    k_mc_words<<<(n_active + 127) / 128, 128, 0, st>>>(g, (const uint32_t*)aw_idx_u32, n_active, nullptr,
+                                                       (uint32_t*)aw_cnt_u32, (unsigned long long*)n_ambiguous_u64);
     T3D_CHECK_LAUNCH("t3d_mc_words");
     t3d_count_launches(2);
     return 0;
@@ -502,6 +533,8 @@ extern "C" int t3d_mc_emit(const void* sign_bits, int Zs, int Hs, int Ws, int z_
     a.offZ = n_x + n_y;
     a.vkeys = (unsigned long long*)vkeys_u64;
     a.faces = (int32_t*)faces_i32;
+    a.sizes = nullptr;
+    a.cap_verts = a.cap_faces = 0xffffffffu;
     k_mc_emit<<<(n_active + 127) / 128, 128, 0, (cudaStream_t)stream>>>(a);
     T3D_CHECK_LAUNCH("t3d_mc_emit");
     t3d_count_launches(1);
@@ -537,5 +570,82 @@ extern "C" int t3d_mc_vertices(const void* occ_bits, int Z, int H, int W, int pa
     if (n_z) { p.first = n_x + n_y; p.count = n_z; k_mc_vertices<0><<<(n_z + 127) / 128, 128, 0, st>>>(p); ++launches; }
     T3D_CHECK_LAUNCH("t3d_mc_vertices");
     t3d_count_launches(launches);
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// device-size variants: every data-dependent size stays in device memory (sizes_u64 = {n_active, n_x, n_y, n_z, n_t}),
+// arrays are capacity-sized, nothing is written beyond the capacities.  No host round trip => graph-capturable.
+// ------------------------------------------------------------------------------------------------
+extern "C" int t3d_mc_words_dev(const void* sign_bits, int Zs, int Hs, int Ws, int z_begin, int z_end, const void* ballots_u32,
+                                const void* chunkbase_u32, uint32_t cap_active, const void* sizes_u64, void* aw_idx_u32,
+                                void* aw_cnt_u32, void* n_ambiguous_u64, void* stream)
+{
+    Grid g;
+    if (int rc = make_grid(g, sign_bits, Zs, Hs, Ws, z_begin, z_end, "t3d_mc_words_dev")) return rc;
+    if (ensure_luts()) return 1;
+    cudaStream_t st = (cudaStream_t)stream;
+    T3D_CUDA(cudaMemsetAsync(n_ambiguous_u64, 0, 8, st));
+    if (cap_active == 0) return 0;
+    const int64_t n_chunks = (int64_t)g.n_rows * g.ncr;
+    k_mc_compact<<<(unsigned)((n_chunks + 255) / 256), 256, 0, st>>>(g, (const uint32_t*)ballots_u32, (const uint32_t*)chunkbase_u32,
+                                                                      n_chunks, (uint32_t*)aw_idx_u32, cap_active);
+    k_mc_words<<<(cap_active + 127) / 128, 128, 0, st>>>(g, (const uint32_t*)aw_idx_u32, cap_active,
+                                                         (const unsigned long long*)sizes_u64, (uint32_t*)aw_cnt_u32,
+                                                         (unsigned long long*)n_ambiguous_u64);
+    T3D_CHECK_LAUNCH("t3d_mc_words_dev");
+    t3d_count_launches(2);
+    return 0;
+}
+
+extern "C" int t3d_mc_emit_dev(const void* sign_bits, int Zs, int Hs, int Ws, int z_begin, int z_end, const void* ballots_u32,
+                               const void* chunkbase_u32, const void* aw_idx_u32, const void* aw_base_u32, uint32_t cap_active,
+                               const void* sizes_u64, uint32_t cap_verts, uint32_t cap_faces, void* vkeys_u64, void* faces_i32,
+                               void* stream)
+{
+    EmitArgs a;
+    if (int rc = make_grid(a.g, sign_bits, Zs, Hs, Ws, z_begin, z_end, "t3d_mc_emit_dev")) return rc;
+    if (ensure_luts()) return 1;
+    if (cap_active == 0) return 0;
+    a.ballots = (const uint32_t*)ballots_u32;
+    a.chunkbase = (const uint32_t*)chunkbase_u32;
+    a.aw_idx = (const uint32_t*)aw_idx_u32;
+    a.aw_base = (const uint32_t*)aw_base_u32;
+    a.n_active = cap_active;
+    a.offY = a.offZ = 0;
+    a.sizes = (const unsigned long long*)sizes_u64;
+    a.cap_verts = cap_verts;
+    a.cap_faces = cap_faces;
+    a.vkeys = (unsigned long long*)vkeys_u64;
+    a.faces = (int32_t*)faces_i32;
+    k_mc_emit<<<(cap_active + 127) / 128, 128, 0, (cudaStream_t)stream>>>(a);
+    T3D_CHECK_LAUNCH("t3d_mc_emit_dev");
+    t3d_count_launches(1);
+    return 0;
+}
+
+extern "C" int t3d_mc_vertices_dev(const void* occ_bits, int Z, int H, int W, int pad, int gaussian, const double* weights3_host,
+                                   const void* vkeys_u64, const void* sizes_u64, uint32_t cap_verts, int unpad_shift, int z_offset,
+                                   const void* cum_f64, const void* adj_f64, int n_cum, double mm_per_pixel_y,
+                                   double mm_per_pixel_x, int scale_in_f64, void* verts_f32, void* stream)
+{
+    if (Z <= 0 || H <= 0 || W <= 0) { t3d_set_error("t3d_mc_vertices_dev: empty volume"); return 2; }
+    if (cap_verts == 0) return 0;
+    VertexArgs p;
+    p.occ = t3d_make_view(occ_bits, Z, H, W, pad, gaussian, weights3_host);
+    p.vkeys = (const unsigned long long*)vkeys_u64;
+    p.first = 0; p.count = cap_verts;
+    p.shift = unpad_shift ? 1.0f : 0.0f;
+    p.z_offset = z_offset;
+    p.cum = (const double*)cum_f64;
+    p.adj = (const double*)adj_f64;
+    p.n_cum = n_cum;
+    p.mm_y = mm_per_pixel_y;
+    p.mm_x = mm_per_pixel_x;
+    p.scale_f64 = scale_in_f64 ? 1 : 0;
+    p.verts = (float*)verts_f32;
+    k_mc_vertices_all<<<(cap_verts + 127) / 128, 128, 0, (cudaStream_t)stream>>>(p, (const unsigned long long*)sizes_u64, cap_verts);
+    T3D_CHECK_LAUNCH("t3d_mc_vertices_dev");
+    t3d_count_launches(1);
     return 0;
 }

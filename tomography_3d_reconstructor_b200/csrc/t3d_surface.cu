@@ -116,9 +116,11 @@ __global__ void __launch_bounds__(256) k_field_sign(OccView v, uint32_t* __restr
 #define SC_ITEMS 8
 #define SC_TILE (SC_THREADS * SC_ITEMS)
 
-__global__ void __launch_bounds__(SC_THREADS) k_scan_reduce(const uint32_t* __restrict__ in, int64_t n, int64_t stride,
-                                                            unsigned long long* __restrict__ block_sums, int n_blocks, int popc_in)
+__global__ void __launch_bounds__(SC_THREADS) k_scan_reduce(const uint32_t* __restrict__ in, int64_t n_cap, int64_t stride,
+                                                            unsigned long long* __restrict__ block_sums, int n_blocks, int popc_in,
+                                                            const unsigned long long* __restrict__ n_dev)
 {
+    const int64_t n = dev_n(n_cap, n_dev);
     const uint32_t* a = in + (int64_t)blockIdx.y * stride;
     const int64_t base = (int64_t)blockIdx.x * SC_TILE;
     unsigned long long s = 0;
@@ -176,10 +178,11 @@ __global__ void __launch_bounds__(1024) k_scan_block_sums(unsigned long long* __
 }
 
 template <typename OutT>
-__global__ void __launch_bounds__(SC_THREADS) k_scan_final(const uint32_t* __restrict__ in, OutT* __restrict__ out, int64_t n,
+__global__ void __launch_bounds__(SC_THREADS) k_scan_final(const uint32_t* __restrict__ in, OutT* __restrict__ out, int64_t n_cap,
                                                            int64_t stride, const unsigned long long* __restrict__ block_sums,
-                                                           int n_blocks, int popc_in)
+                                                           int n_blocks, int popc_in, const unsigned long long* __restrict__ n_dev)
 {
+    const int64_t n = dev_n(n_cap, n_dev);
     const uint32_t* a = in + (int64_t)blockIdx.y * stride;
     OutT* o = out + (int64_t)blockIdx.y * stride;
     const int64_t base = (int64_t)blockIdx.x * SC_TILE + (int64_t)threadIdx.x * SC_ITEMS;  // blocked arrangement
@@ -213,27 +216,35 @@ extern "C" int64_t t3d_scan_workspace_bytes(int64_t n, int n_arrays)
 // in: n_arrays arrays of n uint32 (array k starts at in + k*n); out: same layout, uint32 (out_is_u64 = 0)
 // or uint64 (1); may alias `in` only for uint32 output.  popcount_input = 1 scans popcount(in[i]) instead of in[i].
 // totals: n_arrays uint64 (device).
-extern "C" int t3d_exclusive_scan_u32(const void* in, void* out, int64_t n, int n_arrays, int out_is_u64, int popcount_input,
-                                      void* totals_u64, void* workspace, void* stream)
+// general form: arrays `stride` elements apart, at most n_cap elements each, true length optionally in device memory
+extern "C" int t3d_exclusive_scan_u32_dev(const void* in, void* out, int64_t n_cap, int64_t stride, int n_arrays, int out_is_u64,
+                                          int popcount_input, const void* n_dev_u64, void* totals_u64, void* workspace, void* stream)
 {
     cudaStream_t st = (cudaStream_t)stream;
-    if (n <= 0 || n_arrays <= 0) {
+    if (n_cap <= 0 || n_arrays <= 0) {
         if (n_arrays > 0) T3D_CUDA(cudaMemsetAsync(totals_u64, 0, 8 * n_arrays, st));
         return 0;
     }
-    const int64_t nb = (n + SC_TILE - 1) / SC_TILE;
+    const int64_t nb = (n_cap + SC_TILE - 1) / SC_TILE;
     if (nb > 0x7fffffff) { t3d_set_error("t3d_exclusive_scan_u32: too many elements"); return 2; }
     unsigned long long* bs = (unsigned long long*)workspace;
+    const unsigned long long* nd = (const unsigned long long*)n_dev_u64;
     dim3 grid((unsigned)nb, n_arrays);
-    k_scan_reduce<<<grid, SC_THREADS, 0, st>>>((const uint32_t*)in, n, n, bs, (int)nb, popcount_input);
+    k_scan_reduce<<<grid, SC_THREADS, 0, st>>>((const uint32_t*)in, n_cap, stride, bs, (int)nb, popcount_input, nd);
     k_scan_block_sums<<<n_arrays, 1024, 0, st>>>(bs, (int)nb, (unsigned long long*)totals_u64);
     if (out_is_u64)
-        k_scan_final<unsigned long long><<<grid, SC_THREADS, 0, st>>>((const uint32_t*)in, (unsigned long long*)out, n, n, bs, (int)nb, popcount_input);
+        k_scan_final<unsigned long long><<<grid, SC_THREADS, 0, st>>>((const uint32_t*)in, (unsigned long long*)out, n_cap, stride, bs, (int)nb, popcount_input, nd);
     else
-        k_scan_final<uint32_t><<<grid, SC_THREADS, 0, st>>>((const uint32_t*)in, (uint32_t*)out, n, n, bs, (int)nb, popcount_input);
+        k_scan_final<uint32_t><<<grid, SC_THREADS, 0, st>>>((const uint32_t*)in, (uint32_t*)out, n_cap, stride, bs, (int)nb, popcount_input, nd);
     T3D_CHECK_LAUNCH("t3d_exclusive_scan_u32");
     t3d_count_launches(3);
     return 0;
+}
+
+extern "C" int t3d_exclusive_scan_u32(const void* in, void* out, int64_t n, int n_arrays, int out_is_u64, int popcount_input,
+                                      void* totals_u64, void* workspace, void* stream)
+{
+    return t3d_exclusive_scan_u32_dev(in, out, n, n, n_arrays, out_is_u64, popcount_input, nullptr, totals_u64, workspace, stream);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -348,10 +359,11 @@ __global__ void __launch_bounds__(256) k_unique_heads(const float* __restrict__ 
 
 __global__ void __launch_bounds__(256) k_scatter_unique(const float* __restrict__ verts, const uint32_t* __restrict__ perm,
                                                         const uint32_t* __restrict__ head, const uint32_t* __restrict__ pos,
-                                                        int64_t V, float* __restrict__ out_verts, uint32_t* __restrict__ newid)
+                                                        int64_t V_cap, float* __restrict__ out_verts, uint32_t* __restrict__ newid,
+                                                        const unsigned long long* __restrict__ V_dev = nullptr)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= V) return;
+    if (i >= dev_n(V_cap, V_dev)) return;
     // pos = exclusive scan of head => unique index of element i is pos[i] + head[i] - 1
     const uint32_t u = pos[i] + head[i] - 1u;
     const uint32_t src = perm[i];
@@ -363,21 +375,22 @@ __global__ void __launch_bounds__(256) k_scatter_unique(const float* __restrict_
     }
 }
 
-__global__ void __launch_bounds__(256) k_face_valid(const int32_t* __restrict__ faces, int64_t F, const uint32_t* __restrict__ newid,
-                                                    uint32_t* __restrict__ valid)
+__global__ void __launch_bounds__(256) k_face_valid(const int32_t* __restrict__ faces, int64_t F_cap, const uint32_t* __restrict__ newid,
+                                                    uint32_t* __restrict__ valid, const unsigned long long* __restrict__ F_dev = nullptr)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= F) return;
+    if (i >= dev_n(F_cap, F_dev)) return;
     const uint32_t a = newid[faces[3 * i]], b = newid[faces[3 * i + 1]], c = newid[faces[3 * i + 2]];
     valid[i] = (a != b && b != c && a != c) ? 1u : 0u;
 }
 
-__global__ void __launch_bounds__(256) k_face_compact(const int32_t* __restrict__ faces, int64_t F, const uint32_t* __restrict__ newid,
+__global__ void __launch_bounds__(256) k_face_compact(const int32_t* __restrict__ faces, int64_t F_cap, const uint32_t* __restrict__ newid,
                                                       const uint32_t* __restrict__ valid, const uint32_t* __restrict__ pos,
-                                                      long long* __restrict__ out64, int32_t* __restrict__ out32)
+                                                      long long* __restrict__ out64, int32_t* __restrict__ out32,
+                                                      const unsigned long long* __restrict__ F_dev = nullptr)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= F || !valid[i]) return;
+    if (i >= dev_n(F_cap, F_dev) || !valid[i]) return;
     const uint32_t a = newid[faces[3 * i]], b = newid[faces[3 * i + 1]], c = newid[faces[3 * i + 2]];
     const int64_t o = 3 * (int64_t)pos[i];
     if (out64) { out64[o] = a; out64[o + 1] = b; out64[o + 2] = c; }
@@ -473,21 +486,24 @@ extern "C" int t3d_mesh_canonicalize(const void* verts_in, int64_t V, const void
 // verified on the device: counts_u64[2] != 0 means an adjacent pair was out of order and the caller must fall back
 // to t3d_mesh_canonicalize (three-key sort, valid for any input).
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_make_keys64(const float* __restrict__ verts, int64_t V, unsigned long long* __restrict__ keys,
-                                                     uint32_t* __restrict__ iota)
+__global__ void __launch_bounds__(256) k_make_keys64(const float* __restrict__ verts, int64_t V_cap, const unsigned long long* __restrict__ V_dev,
+                                                     unsigned long long* __restrict__ keys, uint32_t* __restrict__ iota)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= V) return;
-    keys[i] = ((unsigned long long)float_key(verts[3 * i]) << 32) | float_key(verts[3 * i + 1]);
+    if (i >= V_cap) return;
+    // slots beyond the true vertex count sort to the end
+    keys[i] = (i < dev_n(V_cap, V_dev)) ? (((unsigned long long)float_key(verts[3 * i]) << 32) | float_key(verts[3 * i + 1]))
+                                        : 0xffffffffffffffffull;
     iota[i] = (uint32_t)i;
 }
 
 // head flags of the sorted sequence + strict lexicographic order check (z, y, x)
-__global__ void __launch_bounds__(256) k_heads_checked(const float* __restrict__ verts, const uint32_t* __restrict__ perm, int64_t V,
-                                                       uint32_t* __restrict__ head, unsigned long long* __restrict__ bad)
+__global__ void __launch_bounds__(256) k_heads_checked(const float* __restrict__ verts, const uint32_t* __restrict__ perm, int64_t V_cap,
+                                                       const unsigned long long* __restrict__ V_dev, uint32_t* __restrict__ head,
+                                                       unsigned long long* __restrict__ bad)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= V) return;
+    if (i >= dev_n(V_cap, V_dev)) return;
     uint32_t h = 1;
     if (i > 0) {
         const float* a = verts + 3 * (int64_t)perm[i];
@@ -523,10 +539,11 @@ extern "C" int64_t t3d_canonicalize_fast_workspace_bytes(int64_t V, int64_t F)
     return b;
 }
 
-// same outputs as t3d_mesh_canonicalize; counts_u64[0] = V', [1] = F', [2] = 0 if the fast ordering was verified
-extern "C" int t3d_mesh_canonicalize_fast(const void* verts_in, int64_t V, const void* faces_in, int64_t F, void* verts_out,
-                                          void* faces_out_i64, void* faces_out_i32, void* counts_u64, void* workspace,
-                                          void* stream)
+// same outputs as t3d_mesh_canonicalize; counts_u64[0] = V', [1] = F', [2] = 0 if the fast ordering was verified.
+// V_dev / F_dev (optional, device uint64): true sizes when V / F are only capacities.
+static int canonicalize_fast_impl(const void* verts_in, int64_t V, const unsigned long long* V_dev, const void* faces_in, int64_t F,
+                                  const unsigned long long* F_dev, void* verts_out, void* faces_out_i64, void* faces_out_i32,
+                                  void* counts_u64, void* workspace, void* stream)
 {
     cudaStream_t st = (cudaStream_t)stream;
     if (V <= 0 || V > 0x7fffffff || F < 0) { t3d_set_error("t3d_mesh_canonicalize_fast: bad sizes"); return 2; }
@@ -547,20 +564,20 @@ extern "C" int t3d_mesh_canonicalize_fast(const void* verts_in, int64_t V, const
     const unsigned gv = (unsigned)((V + 255) / 256);
     const float* vin = (const float*)verts_in;
     T3D_CUDA(cudaMemsetAsync(counts + 2, 0, 8, st));
-    k_make_keys64<<<gv, 256, 0, st>>>(vin, V, keys_a, iota);
+    k_make_keys64<<<gv, 256, 0, st>>>(vin, V, V_dev, keys_a, iota);
     T3D_CUDA(cub::DeviceRadixSort::SortPairs(temp, temp_bytes, (const unsigned long long*)keys_a, keys_b, (const uint32_t*)iota, perm,
                                              (int)V, 0, 64, st));
-    k_heads_checked<<<gv, 256, 0, st>>>(vin, perm, V, flags, counts + 2);
-    if (t3d_exclusive_scan_u32(flags, pos, V, 1, 0, 0, totals, scan_ws, stream)) return 1;
+    k_heads_checked<<<gv, 256, 0, st>>>(vin, perm, V, V_dev, flags, counts + 2);
+    if (t3d_exclusive_scan_u32_dev(flags, pos, V, V, 1, 0, 0, V_dev, totals, scan_ws, stream)) return 1;
     T3D_CUDA(cudaMemcpyAsync(counts, totals, 8, cudaMemcpyDeviceToDevice, st));
-    k_scatter_unique<<<gv, 256, 0, st>>>(vin, perm, flags, pos, V, (float*)verts_out, newid);
+    k_scatter_unique<<<gv, 256, 0, st>>>(vin, perm, flags, pos, V, (float*)verts_out, newid, V_dev);
     if (F > 0) {
         const unsigned gf = (unsigned)((F + 255) / 256);
-        k_face_valid<<<gf, 256, 0, st>>>((const int32_t*)faces_in, F, newid, flags);
-        if (t3d_exclusive_scan_u32(flags, pos, F, 1, 0, 0, totals, scan_ws, stream)) return 1;
+        k_face_valid<<<gf, 256, 0, st>>>((const int32_t*)faces_in, F, newid, flags, F_dev);
+        if (t3d_exclusive_scan_u32_dev(flags, pos, F, F, 1, 0, 0, F_dev, totals, scan_ws, stream)) return 1;
         T3D_CUDA(cudaMemcpyAsync(counts + 1, totals, 8, cudaMemcpyDeviceToDevice, st));
         k_face_compact<<<gf, 256, 0, st>>>((const int32_t*)faces_in, F, newid, flags, pos, (long long*)faces_out_i64,
-                                           (int32_t*)faces_out_i32);
+                                           (int32_t*)faces_out_i32, F_dev);
     } else {
         T3D_CUDA(cudaMemsetAsync(counts + 1, 0, 8, st));
     }
@@ -569,14 +586,33 @@ extern "C" int t3d_mesh_canonicalize_fast(const void* verts_in, int64_t V, const
     return 0;
 }
 
+extern "C" int t3d_mesh_canonicalize_fast(const void* verts_in, int64_t V, const void* faces_in, int64_t F, void* verts_out,
+                                          void* faces_out_i64, void* faces_out_i32, void* counts_u64, void* workspace,
+                                          void* stream)
+{
+    return canonicalize_fast_impl(verts_in, V, nullptr, faces_in, F, nullptr, verts_out, faces_out_i64, faces_out_i32, counts_u64,
+                                  workspace, stream);
+}
+
+// capacity-sized inputs, true sizes in device memory (graph-capturable)
+extern "C" int t3d_mesh_canonicalize_fast_dev(const void* verts_in, int64_t V_cap, const void* V_dev_u64, const void* faces_in,
+                                              int64_t F_cap, const void* F_dev_u64, void* verts_out, void* faces_out_i64,
+                                              void* faces_out_i32, void* counts_u64, void* workspace, void* stream)
+{
+    return canonicalize_fast_impl(verts_in, V_cap, (const unsigned long long*)V_dev_u64, faces_in, F_cap,
+                                  (const unsigned long long*)F_dev_u64, verts_out, faces_out_i64, faces_out_i32, counts_u64, workspace,
+                                  stream);
+}
+
 // ------------------------------------------------------------------------------------------------
 // mesh measures: signed volume sum_f v0.(v1 x v2)/6 and area sum_f 0.5|(v1-v0)x(v2-v0)|, float64 terms and
 // float64 accumulation, fixed reduction order (warp-shuffle trees, then one block over the block partials)
 // ------------------------------------------------------------------------------------------------
 template <typename IdxT>
-__global__ void __launch_bounds__(256) k_mesh_measure(const float* __restrict__ verts, const IdxT* __restrict__ faces, int64_t F,
-                                                      double* __restrict__ partials)
+__global__ void __launch_bounds__(256) k_mesh_measure(const float* __restrict__ verts, const IdxT* __restrict__ faces, int64_t F_cap,
+                                                      double* __restrict__ partials, const unsigned long long* __restrict__ F_dev = nullptr)
 {
+    const int64_t F = dev_n(F_cap, F_dev);
     double vol = 0.0, area = 0.0;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < F; i += (int64_t)gridDim.x * blockDim.x) {
         const float* a = verts + 3 * (int64_t)faces[3 * i];
@@ -620,18 +656,34 @@ __global__ void __launch_bounds__(256) k_reduce_partials(const double* __restric
 extern "C" int64_t t3d_mesh_measure_workspace_bytes(void) { return (int64_t)MM_BLOCKS * 2 * 8; }
 
 // out_f64[0] = signed volume, out_f64[1] = area (device)
+static int mesh_measure_impl(const void* verts_f32, const void* faces, int64_t F, const unsigned long long* F_dev, int faces_are_i64,
+                             void* out_f64, void* workspace, void* stream);
+
 extern "C" int t3d_mesh_measure(const void* verts_f32, int64_t V, const void* faces, int64_t F, int faces_are_i64, void* out_f64,
                                 void* workspace, void* stream)
 {
-    cudaStream_t st = (cudaStream_t)stream;
     (void)V;
+    return mesh_measure_impl(verts_f32, faces, F, nullptr, faces_are_i64, out_f64, workspace, stream);
+}
+
+// F is a capacity, the true face count is read from device memory
+extern "C" int t3d_mesh_measure_dev(const void* verts_f32, const void* faces, int64_t F_cap, const void* F_dev_u64, int faces_are_i64,
+                                    void* out_f64, void* workspace, void* stream)
+{
+    return mesh_measure_impl(verts_f32, faces, F_cap, (const unsigned long long*)F_dev_u64, faces_are_i64, out_f64, workspace, stream);
+}
+
+static int mesh_measure_impl(const void* verts_f32, const void* faces, int64_t F, const unsigned long long* F_dev, int faces_are_i64,
+                             void* out_f64, void* workspace, void* stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
     if (F <= 0) { T3D_CUDA(cudaMemsetAsync(out_f64, 0, 16, st)); return 0; }
     int blocks = (int)((F + 255) / 256);
     if (blocks > MM_BLOCKS) blocks = MM_BLOCKS;
     if (faces_are_i64)
-        k_mesh_measure<long long><<<blocks, 256, 0, st>>>((const float*)verts_f32, (const long long*)faces, F, (double*)workspace);
+        k_mesh_measure<long long><<<blocks, 256, 0, st>>>((const float*)verts_f32, (const long long*)faces, F, (double*)workspace, F_dev);
     else
-        k_mesh_measure<int32_t><<<blocks, 256, 0, st>>>((const float*)verts_f32, (const int32_t*)faces, F, (double*)workspace);
+        k_mesh_measure<int32_t><<<blocks, 256, 0, st>>>((const float*)verts_f32, (const int32_t*)faces, F, (double*)workspace, F_dev);
     k_reduce_partials<<<1, 256, 0, st>>>((const double*)workspace, blocks, (double*)out_f64);
     T3D_CHECK_LAUNCH("t3d_mesh_measure");
     t3d_count_launches(2);

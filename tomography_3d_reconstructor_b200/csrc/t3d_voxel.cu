@@ -190,37 +190,60 @@ __device__ __forceinline__ uint32_t fill_dn(uint32_t m, uint32_t s)  // towards 
     return s;
 }
 
-// closure of `reach` along one row, both directions, by ONE thread (rows are independent, so the CTA closes
-// FH_THREADS rows at a time).  Words are fetched eight at a time BEFORE the carry chain runs, so the loads of a chunk
-// are all in flight together instead of being serialised behind the (possibly aliasing) stores.
-__device__ __forceinline__ bool row_closure(const uint32_t* mrow, uint32_t* rrow, int nwv)
+// closure of `reach` along rows, both directions.  A warp owns 32 consecutive rows: it stages a 32-row x 16-word tile
+// of the mask and of `reach` in shared memory with coalesced loads (row pitch 17 words: conflict-free when lane = row),
+// every lane then runs the carry chain of ITS row over the 16 words, and the tile is written back coalesced.  The
+// carry of each row crosses tiles in a register.
+#define FH_TW 16
+#define FH_PITCH 17
+
+__device__ __forceinline__ void rows_closure_tile(const uint32_t* __restrict__ m, uint32_t* __restrict__ r, int nw, int nwv,
+                                                  int y0, int H, uint32_t* tm, uint32_t* tr)
 {
-    bool changed = false;
-    uint32_t carry = 0;
-    for (int w0 = 0; w0 < nwv; w0 += 8) {            // towards +x
-        uint32_t m[8], r[8];
+    const uint32_t l = lane_id();
+    const int rsub = l >> 4, wsub = l & 15;
+    const int n_tiles = (nwv + FH_TW - 1) / FH_TW;
+    for (int dir = 0; dir < 2; ++dir) {
+        uint32_t carry = 0;
+        for (int t = 0; t < n_tiles; ++t) {
+            const int c = dir == 0 ? t : n_tiles - 1 - t;
+            const int w = c * FH_TW + wsub;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) { const bool ok = w0 + k < nwv; m[k] = ok ? mrow[w0 + k] : 0u; r[k] = ok ? rrow[w0 + k] : 0u; }
+            for (int j = 0; j < 16; ++j) {
+                const int rr = 2 * j + rsub, y = y0 + rr;
+                const bool ok = (y < H) && (w < nwv);
+                tm[rr * FH_PITCH + wsub] = ok ? m[(int64_t)y * nw + w] : 0u;
+                tr[rr * FH_PITCH + wsub] = ok ? r[(int64_t)y * nw + w] : 0u;
+            }
+            __syncwarp();
+            uint32_t* mr = tm + l * FH_PITCH;
+            uint32_t* rr_ = tr + l * FH_PITCH;
+            if (dir == 0) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const uint32_t f = fill_up(m[k], r[k] | (carry & m[k] & 1u));
-            carry = f >> 31;
-            if (f != r[k]) { rrow[w0 + k] = f; changed = true; }
+                for (int k = 0; k < FH_TW; ++k) {
+                    const uint32_t mm = mr[k];
+                    const uint32_t f = fill_up(mm, rr_[k] | (carry & mm & 1u));
+                    carry = f >> 31;
+                    rr_[k] = f;
+                }
+            } else {
+#pragma unroll
+                for (int k = FH_TW - 1; k >= 0; --k) {
+                    const uint32_t mm = mr[k];
+                    const uint32_t f = fill_dn(mm, rr_[k] | ((carry << 31) & mm));
+                    carry = f & 1u;
+                    rr_[k] = f;
+                }
+            }
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const int rr = 2 * j + rsub, y = y0 + rr;
+                if (y < H && w < nwv) r[(int64_t)y * nw + w] = tr[rr * FH_PITCH + wsub];
+            }
+            __syncwarp();
         }
     }
-    carry = 0;
-    for (int w0 = ((nwv - 1) >> 3) << 3; w0 >= 0; w0 -= 8) {   // towards -x
-        uint32_t m[8], r[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) { const bool ok = w0 + k < nwv; m[k] = ok ? mrow[w0 + k] : 0u; r[k] = ok ? rrow[w0 + k] : 0u; }
-#pragma unroll
-        for (int k = 7; k >= 0; --k) {
-            const uint32_t f = fill_dn(m[k], r[k] | ((carry << 31) & m[k]));
-            carry = f & 1u;
-            if (f != r[k]) { rrow[w0 + k] = f; changed = true; }
-        }
-    }
-    return changed;
 }
 
 #define FH_THREADS 1024
@@ -251,6 +274,7 @@ __global__ void __launch_bounds__(FH_THREADS) k_fill_holes(uint32_t* bits_planes
     }
     __syncthreads();
 
+    extern __shared__ uint32_t tile[];  // per warp: mask tile + reach tile, 32 rows x FH_PITCH words each
     // column segments: thread (seg, col) sweeps rows [seg*L, seg*L+L)
     __shared__ uint32_t sG[FH_MAXSEG][32];  // used in column tiles of 32 word-columns
     __shared__ uint32_t sP[FH_MAXSEG][32];
@@ -262,8 +286,9 @@ __global__ void __launch_bounds__(FH_THREADS) k_fill_holes(uint32_t* bits_planes
         // soon as a column closure changes nothing: only the column phase feeds `changed`.
         int changed = 0;
         // ---- rows
-        for (int y = tid; y < H; y += FH_THREADS)
-            row_closure(m + (int64_t)y * nw, r + (int64_t)y * nw, (W + 31) >> 5);
+        for (int y0 = warp * 32; y0 < H; y0 += (FH_THREADS / 32) * 32)
+            rows_closure_tile(m, r, nw, (W + 31) >> 5, y0, H, tile + warp * 2 * 32 * FH_PITCH,
+                              tile + warp * 2 * 32 * FH_PITCH + 32 * FH_PITCH);
         __syncthreads();
         // ---- columns, 32 word-columns at a time: thread = (seg = warp, col = lane)
         for (int c0 = 0; c0 < nw; c0 += 32) {
@@ -330,8 +355,14 @@ extern "C" int t3d_fill_holes_2d(void* bits, int n_planes, int64_t plane_stride_
 {
     if (n_planes <= 0) return 0;
     if (H <= 0 || W <= 0) { t3d_set_error("t3d_fill_holes_2d: empty plane"); return 2; }
-    k_fill_holes<<<n_planes, FH_THREADS, 0, (cudaStream_t)stream>>>((uint32_t*)bits, plane_stride_words,
-                                                                   (uint32_t*)scratch, H, W, t3d_wpr(W));
+    const size_t smem = (size_t)(FH_THREADS / 32) * 2 * 32 * FH_PITCH * sizeof(uint32_t);  // 136 KB
+    static bool attr_set = false;
+    if (!attr_set) {
+        T3D_CUDA(cudaFuncSetAttribute(k_fill_holes, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    k_fill_holes<<<n_planes, FH_THREADS, smem, (cudaStream_t)stream>>>((uint32_t*)bits, plane_stride_words,
+                                                                      (uint32_t*)scratch, H, W, t3d_wpr(W));
     T3D_CHECK_LAUNCH("t3d_fill_holes_2d");
     t3d_count_launches(1);
     return 0;

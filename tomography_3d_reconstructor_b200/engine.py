@@ -142,7 +142,8 @@ class DeviceMesh:
     """Mesh on the device.  After an asynchronous canonicalisation the arrays are capacity-sized and the true sizes
     live in `counts_dev` until resolve() (one D2H copy) or set_sizes() trims them."""
 
-    __slots__ = ("_verts", "_faces", "counts_dev", "n_ambiguous", "n_exact", "_measures", "raw", "__weakref__")
+    __slots__ = ("_verts", "_faces", "counts_dev", "n_ambiguous", "n_exact", "_measures", "raw", "n_active", "n_raw",
+                 "__weakref__")
 
     def __init__(self, verts: torch.Tensor, faces: torch.Tensor, n_ambiguous: int = 0, n_exact: int = 0,
                  counts_dev: Optional[torch.Tensor] = None):
@@ -151,6 +152,8 @@ class DeviceMesh:
         self.n_ambiguous, self.n_exact = n_ambiguous, n_exact
         self._measures = None
         self.raw = None  # (raw verts, raw faces) of an asynchronous canonicalisation, until the sizes are known
+        self.n_active = 0        # active 32-voxel words / raw (vertices, faces): capacity hints for the fused path
+        self.n_raw = (0, 0)
 
     def set_sizes(self, n_verts: int, n_faces: int, unverified: int = 0) -> None:
         """Trim the capacity-sized arrays.  unverified != 0: the fast ordering failed its device-side check, redo the
@@ -479,10 +482,13 @@ def extract_surface(dv: DeviceVolume, slice_depths, mm_per_pixel_y, mm_per_pixel
         mark("canonicalize")
         m = DeviceMesh(v2, f2, n_ambiguous, n_exact, counts_dev=counts)
         m.raw = (verts, faces)
+        m.n_active, m.n_raw = n_active, (V, nT)
         return m
     v2, f2 = canonicalize(verts, faces, fast=True)
     mark("canonicalize")
-    return DeviceMesh(v2, f2, n_ambiguous, n_exact)
+    m = DeviceMesh(v2, f2, n_ambiguous, n_exact)
+    m.n_active, m.n_raw = n_active, (V, nT)
+    return m
 
 
 def canonicalize(verts: torch.Tensor, faces_i32: torch.Tensor, faces_i64: bool = True, sync: bool = True,

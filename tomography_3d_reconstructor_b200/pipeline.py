@@ -95,3 +95,133 @@ def reconstruct(masks_u8: torch.Tensor, threshold: int, side_counts, total_depth
         "active_voxels": int(raw_counts.sum()),
         "slice_depths": depths,
     }
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# fused path: the whole step as ONE enqueue (t3d_reconstruct), captured in a CUDA graph
+# ----------------------------------------------------------------------------------------------------------------
+R_NACTIVE, R_NX, R_NY, R_NZ, R_NT, R_VCANON, R_FCANON, R_UNVERIFIED, R_OVERFLOW = range(9)
+R_NAMBIGUOUS, R_NEXACT, R_VOLUME, R_AREA, R_BBOX, R_VRAW, R_COUNTS = 9, 10, 11, 12, 13, 16, 32
+
+
+class FusedPlan:
+    """Buffers + (optionally) a captured CUDA graph for one problem shape.  Data-dependent sizes stay on the device;
+    buffers are capacity-sized from hints (a previous run of the same input) and the result block reports overflow.
+    The mesh returned by run() lives in the plan's output buffers: valid until the next run()."""
+
+    def __init__(self, shape, threshold, side_counts, total_depth_mm, x_length_mm, y_length_mm, iterations, close_ends,
+                 add_padding, caps, device):
+        import ctypes
+        L = engine._L()
+        self.shape = Z, H, W = tuple(int(v) for v in shape)
+        self.threshold, self.close_ends, self.add_padding = int(threshold), bool(close_ends), bool(add_padding)
+        self.mm_x, self.mm_y = x_length_mm / W, y_length_mm / H
+        self.depths = slice_depths(total_depth_mm, *side_counts)
+        stages = engine.morph_stages(iterations, True)
+        self.n_stages = len(stages)
+        self.erode_mask = sum(1 << k for k, er in enumerate(stages) if er)
+        self.caps = tuple(int(c) for c in caps)
+        cum, adj = engine.z_map_arrays(self.depths, add_padding)
+        self.n_cum = len(cum)
+        self.cum_d = torch.from_numpy(cum).to(device) if self.n_cum else None
+        self.adj_d = torch.from_numpy(adj).to(device) if self.n_cum else None
+        nbytes = int(L.t3d_reconstruct_workspace_bytes(Z, H, W, 1 if add_padding else 0, self.n_stages, *self.caps))
+        self.ws = torch.empty(nbytes // 8 + 1, dtype=torch.int64, device=device)
+        self.verts = torch.empty((self.caps[1], 3), dtype=torch.float32, device=device)
+        self.faces = torch.empty((self.caps[2], 3), dtype=torch.int64, device=device)
+        self.n_res = int(L.t3d_reconstruct_results_len(Z))
+        self.res = torch.zeros(self.n_res, dtype=torch.int64, device=device)
+        self.res_host = torch.zeros(self.n_res, dtype=torch.int64, pin_memory=True)
+        self.graph, self.graph_ptr = None, None
+        self._ctypes = ctypes
+
+    def enqueue(self, masks_u8: torch.Tensor) -> None:
+        Z, H, W = self.shape
+        p = engine._p
+        engine.check(engine._L().t3d_reconstruct(
+            p(masks_u8), Z, H, W, self.threshold, 1 if self.close_ends else 0, self.n_stages, self.erode_mask,
+            1 if self.add_padding else 0, engine._W3_C, p(self.cum_d), p(self.adj_d), self.n_cum, float(self.mm_y),
+            float(self.mm_x), 0, self.caps[0], self.caps[1], self.caps[2], p(self.verts), p(self.faces), p(self.res),
+            p(self.ws), engine._stream()), "t3d_reconstruct")
+
+    def capture(self, masks_u8: torch.Tensor) -> None:
+        """Record the step for this input buffer into a CUDA graph (after one eager warm-up run)."""
+        self.enqueue(masks_u8)
+        torch.cuda.current_stream().synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self.enqueue(masks_u8)
+        self.graph, self.graph_ptr = g, masks_u8.data_ptr()
+
+    def run(self, masks_u8: torch.Tensor, use_graph: bool = True):
+        """Returns the host result block (numpy int64 view) after one synchronisation."""
+        if use_graph and self.graph is not None and self.graph_ptr == masks_u8.data_ptr():
+            self.graph.replay()
+        else:
+            self.enqueue(masks_u8)
+        self.res_host.copy_(self.res, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return self.res_host.numpy()
+
+
+_plans: Dict = {}
+_hints: Dict = {}
+
+
+def _caps_from(n_active: int, v_raw: int, f_raw: int):
+    grow = lambda n: int(n * 1.02) + 4096
+    return grow(n_active), grow(v_raw), grow(f_raw)
+
+
+def reconstruct_fused(masks_u8: torch.Tensor, threshold: int, side_counts, total_depth_mm: float, x_length_mm: float,
+                      y_length_mm: float, iterations: int = 3, close_ends: bool = True, add_padding: bool = True,
+                      use_graph: bool = True) -> Dict:
+    """Same contract as reconstruct(), executed as one graph launch + one device->host copy.
+
+    The first call for a given (shape, parameters) runs the staged path to learn the mesh size; later calls reuse a
+    FusedPlan.  If the input changes so much that a capacity overflows (or the fast vertex ordering cannot be
+    verified) the staged path runs instead and the hints are refreshed."""
+    Z, H, W = (int(s) for s in masks_u8.shape)
+    key = (Z, H, W, int(threshold), tuple(side_counts), float(total_depth_mm), float(x_length_mm), float(y_length_mm),
+           int(iterations), bool(close_ends), bool(add_padding), masks_u8.device.index)
+
+    def staged():
+        out = reconstruct(masks_u8, threshold, side_counts, total_depth_mm, x_length_mm, y_length_mm, iterations, close_ends,
+                          add_padding)
+        m = out["mesh"]
+        _hints[key] = _caps_from(m.n_active, *m.n_raw)
+        return out
+
+    if key not in _hints:
+        return staged()
+    plan = _plans.get(key)
+    if plan is None or any(c < h for c, h in zip(plan.caps, _hints[key])):
+        plan = FusedPlan((Z, H, W), threshold, side_counts, total_depth_mm, x_length_mm, y_length_mm, iterations,
+                         close_ends, add_padding, _hints[key], masks_u8.device)
+        _plans[key] = plan
+    if use_graph and plan.graph_ptr != masks_u8.data_ptr():
+        plan.capture(masks_u8)
+    r = plan.run(masks_u8, use_graph)
+    if r[R_OVERFLOW] or r[R_UNVERIFIED] or r[R_NT] == 0:
+        _plans.pop(key, None)
+        _hints.pop(key, None)
+        return staged()
+    # every later call with a slightly larger mesh still fits thanks to the margin; refresh the hints if it grew
+    _hints[key] = tuple(max(a, b) for a, b in zip(_hints[key], _caps_from(int(r[R_NACTIVE]), int(r[R_VRAW]), int(r[R_NT]))))
+    mesh = engine.DeviceMesh(plan.verts[:int(r[R_VCANON])], plan.faces[:int(r[R_FCANON])], int(r[R_NAMBIGUOUS]), int(r[R_NEXACT]))
+    vol_area = r[R_VOLUME:R_VOLUME + 2].view(np.float64)
+    mesh._measures = (float(vol_area[0]), float(vol_area[1]))
+    mesh.n_active, mesh.n_raw = int(r[R_NACTIVE]), (int(r[R_VRAW]), int(r[R_NT]))
+    raw_counts = r[R_COUNTS:R_COUNTS + Z].astype(np.int64)
+    sm_counts = r[R_COUNTS + Z:R_COUNTS + 2 * Z].astype(np.int64)
+    bb = tuple(int(v) for v in r[R_BBOX:R_BBOX + 3].view(np.int32))
+    return {
+        "mesh": mesh,
+        "voxel_volume_mm3": variable_depth_volume(raw_counts, plan.mm_x, plan.mm_y, plan.depths),
+        "processed_voxel_volume_mm3": variable_depth_volume(sm_counts, plan.mm_x, plan.mm_y, plan.depths),
+        "mesh_volume_mm3": abs(float(vol_area[0])),
+        "surface_area_mm2": float(vol_area[1]),
+        "bbox_index": bb if bb[1] >= 0 else None,
+        "active_voxels": int(raw_counts.sum()),
+        "slice_depths": plan.depths,
+    }
