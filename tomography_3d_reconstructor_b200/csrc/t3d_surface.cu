@@ -109,97 +109,83 @@ __global__ void __launch_bounds__(256) k_field_sign(OccView v, uint32_t* __restr
 }
 
 // ------------------------------------------------------------------------------------------------
-// exclusive scan of n_arrays independent uint32 arrays of length n (in place), totals -> totals[k]
-// three kernels: block reduce, scan of block sums (one block per array), block scan + offset
+// exclusive scan of n_arrays independent uint32 arrays (in place allowed for uint32 output), totals -> totals[k].
+// Single pass with decoupled look-back (Merrill & Garland): a tile of SC_TILE items per CTA, tiles ordered by an
+// atomic ticket, each tile publishes (status | value) in one 64-bit word; a tile's exclusive prefix is found by a
+// warp walking back over its predecessors until it meets an inclusive prefix.  One launch, data read once.
 // ------------------------------------------------------------------------------------------------
 #define SC_THREADS 256
 #define SC_ITEMS 8
 #define SC_TILE (SC_THREADS * SC_ITEMS)
-
-__global__ void __launch_bounds__(SC_THREADS) k_scan_reduce(const uint32_t* __restrict__ in, int64_t n_cap, int64_t stride,
-                                                            unsigned long long* __restrict__ block_sums, int n_blocks, int popc_in,
-                                                            const unsigned long long* __restrict__ n_dev)
-{
-    const int64_t n = dev_n(n_cap, n_dev);
-    const uint32_t* a = in + (int64_t)blockIdx.y * stride;
-    const int64_t base = (int64_t)blockIdx.x * SC_TILE;
-    unsigned long long s = 0;
-    for (int k = 0; k < SC_ITEMS; ++k) {
-        const int64_t i = base + (int64_t)k * SC_THREADS + threadIdx.x;
-        if (i < n) s += popc_in ? (uint32_t)__popc(a[i]) : a[i];
-    }
-    s = warp_sum(s);
-    __shared__ unsigned long long sh[SC_THREADS / 32];
-    if (lane_id() == 0) sh[threadIdx.x >> 5] = s;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        unsigned long long t = 0;
-        for (int k = 0; k < SC_THREADS / 32; ++k) t += sh[k];
-        block_sums[(int64_t)blockIdx.y * n_blocks + blockIdx.x] = t;
-    }
-}
-
-__global__ void __launch_bounds__(1024) k_scan_block_sums(unsigned long long* __restrict__ block_sums, int n_blocks,
-                                                          unsigned long long* __restrict__ totals)
-{
-    unsigned long long* a = block_sums + (int64_t)blockIdx.x * n_blocks;
-    __shared__ unsigned long long sh[32];
-    __shared__ unsigned long long carry_s;
-    if (threadIdx.x == 0) carry_s = 0;
-    __syncthreads();
-    for (int base = 0; base < n_blocks; base += 1024) {
-        const int i = base + threadIdx.x;
-        const unsigned long long v = (i < n_blocks) ? a[i] : 0ull;
-        unsigned long long x = v;
-        const uint32_t l = lane_id();
-        for (int o = 1; o < 32; o <<= 1) {
-            const unsigned long long t = __shfl_up_sync(0xffffffffu, x, o);
-            if (l >= (uint32_t)o) x += t;
-        }
-        if (l == 31) sh[threadIdx.x >> 5] = x;
-        __syncthreads();
-        if (threadIdx.x < 32) {
-            unsigned long long y = sh[threadIdx.x];
-            for (int o = 1; o < 32; o <<= 1) {
-                const unsigned long long t = __shfl_up_sync(0xffffffffu, y, o);
-                if (l >= (uint32_t)o) y += t;
-            }
-            sh[threadIdx.x] = y;
-        }
-        __syncthreads();
-        const unsigned long long warp_off = (threadIdx.x >> 5) ? sh[(threadIdx.x >> 5) - 1] : 0ull;
-        const unsigned long long carry = carry_s;
-        if (i < n_blocks) a[i] = carry + warp_off + x - v;  // exclusive
-        __syncthreads();
-        if (threadIdx.x == 1023) carry_s = carry + warp_off + x;
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) totals[blockIdx.x] = carry_s;
-}
+#define SC_FLAG_A (1ull << 62)   // aggregate of this tile available
+#define SC_FLAG_P (2ull << 62)   // inclusive prefix available
+#define SC_VALUE_MASK ((1ull << 62) - 1)
 
 template <typename OutT>
-__global__ void __launch_bounds__(SC_THREADS) k_scan_final(const uint32_t* __restrict__ in, OutT* __restrict__ out, int64_t n_cap,
-                                                           int64_t stride, const unsigned long long* __restrict__ block_sums,
-                                                           int n_blocks, int popc_in, const unsigned long long* __restrict__ n_dev)
+__global__ void __launch_bounds__(SC_THREADS) k_scan_lookback(const uint32_t* __restrict__ in, OutT* __restrict__ out, int64_t n_cap,
+                                                              int64_t stride, unsigned long long* __restrict__ desc, int n_tiles,
+                                                              unsigned int* __restrict__ tickets, int popc_in,
+                                                              const unsigned long long* __restrict__ n_dev,
+                                                              unsigned long long* __restrict__ totals)
 {
     const int64_t n = dev_n(n_cap, n_dev);
     const uint32_t* a = in + (int64_t)blockIdx.y * stride;
     OutT* o = out + (int64_t)blockIdx.y * stride;
-    const int64_t base = (int64_t)blockIdx.x * SC_TILE + (int64_t)threadIdx.x * SC_ITEMS;  // blocked arrangement
+    volatile unsigned long long* d = desc + (int64_t)blockIdx.y * n_tiles;
+    __shared__ int s_tile;
+    __shared__ uint32_t sh[SC_THREADS / 32];
+    __shared__ unsigned long long s_prefix;
+    if (threadIdx.x == 0) s_tile = (int)atomicAdd(tickets + blockIdx.y, 1u);
+    __syncthreads();
+    const int tile = s_tile;
+    const int64_t base = (int64_t)tile * SC_TILE + (int64_t)threadIdx.x * SC_ITEMS;  // blocked arrangement
     uint32_t v[SC_ITEMS];
-    uint32_t s = 0;
+    uint32_t sum = 0;
 #pragma unroll
     for (int k = 0; k < SC_ITEMS; ++k) {
         v[k] = (base + k < n) ? (popc_in ? (uint32_t)__popc(a[base + k]) : a[base + k]) : 0u;
-        s += v[k];
+        sum += v[k];
     }
-    const uint32_t incl = warp_incl_scan(s);
-    __shared__ uint32_t sh[SC_THREADS / 32];
+    const uint32_t incl = warp_incl_scan(sum);
     if (lane_id() == 31) sh[threadIdx.x >> 5] = incl;
     __syncthreads();
-    uint32_t woff = 0;
-    for (int k = 0; k < (int)(threadIdx.x >> 5); ++k) woff += sh[k];
-    unsigned long long run = block_sums[(int64_t)blockIdx.y * n_blocks + blockIdx.x] + woff + (incl - s);
+    uint32_t woff = 0, agg = 0;
+#pragma unroll
+    for (int k = 0; k < SC_THREADS / 32; ++k) {
+        if (k < (int)(threadIdx.x >> 5)) woff += sh[k];
+        agg += sh[k];
+    }
+    // publish the aggregate, look back for the exclusive prefix of this tile (warp 0)
+    if (threadIdx.x < 32) {
+        unsigned long long prefix = 0;
+        if (tile == 0) {
+            if (threadIdx.x == 0) { d[0] = SC_FLAG_P | (unsigned long long)agg; }
+        } else {
+            if (threadIdx.x == 0) { d[tile] = SC_FLAG_A | (unsigned long long)agg; }
+            int idx = tile - 1 - (int)threadIdx.x;
+            while (true) {
+                unsigned long long w = (idx >= 0) ? d[idx] : SC_FLAG_P;  // before tile 0: an (empty) inclusive prefix
+                while (__any_sync(0xffffffffu, (w >> 62) == 0)) {        // spin until the 32 predecessors have published
+                    if ((w >> 62) == 0) w = (idx >= 0) ? d[idx] : SC_FLAG_P;
+                }
+                const uint32_t is_p = __ballot_sync(0xffffffffu, (w >> 62) == 2);
+                const int first_p = is_p ? (__ffs(is_p) - 1) : 32;       // nearest predecessor holding an inclusive prefix
+                unsigned long long val = ((int)threadIdx.x <= first_p) ? (w & SC_VALUE_MASK) : 0ull;
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) val += __shfl_xor_sync(0xffffffffu, val, off);
+                prefix += val;
+                if (is_p) break;
+                idx -= 32;
+            }
+            if (threadIdx.x == 0) { d[tile] = SC_FLAG_P | ((prefix + agg) & SC_VALUE_MASK); }
+        }
+        if (threadIdx.x == 0) {
+            s_prefix = prefix;
+            if (tile == n_tiles - 1) totals[blockIdx.y] = prefix + agg;
+        }
+    }
+    __syncthreads();
+    unsigned long long run = s_prefix + woff + (incl - sum);
 #pragma unroll
     for (int k = 0; k < SC_ITEMS; ++k) {
         if (base + k < n) o[base + k] = (OutT)run;
@@ -210,7 +196,7 @@ __global__ void __launch_bounds__(SC_THREADS) k_scan_final(const uint32_t* __res
 extern "C" int64_t t3d_scan_workspace_bytes(int64_t n, int n_arrays)
 {
     const int64_t nb = (n + SC_TILE - 1) / SC_TILE;
-    return (nb * n_arrays + 16) * 8;
+    return (nb * n_arrays + 16) * 8 + 256;
 }
 
 // in: n_arrays arrays of n uint32 (array k starts at in + k*n); out: same layout, uint32 (out_is_u64 = 0)
@@ -225,19 +211,25 @@ extern "C" int t3d_exclusive_scan_u32_dev(const void* in, void* out, int64_t n_c
         if (n_arrays > 0) T3D_CUDA(cudaMemsetAsync(totals_u64, 0, 8 * n_arrays, st));
         return 0;
     }
+    if (n_arrays > 16) { t3d_set_error("t3d_exclusive_scan_u32: at most 16 arrays per call"); return 2; }
     const int64_t nb = (n_cap + SC_TILE - 1) / SC_TILE;
     if (nb > 0x7fffffff) { t3d_set_error("t3d_exclusive_scan_u32: too many elements"); return 2; }
-    unsigned long long* bs = (unsigned long long*)workspace;
+    // workspace: [tile descriptors: nb * n_arrays u64][tickets: 16 u32], zeroed for every scan
+    const size_t desc_bytes = (size_t)nb * n_arrays * 8;
+    T3D_CUDA(cudaMemsetAsync(workspace, 0, desc_bytes + 64, st));
+    unsigned long long* desc = (unsigned long long*)workspace;
+    unsigned int* tickets = (unsigned int*)((char*)workspace + desc_bytes);
     const unsigned long long* nd = (const unsigned long long*)n_dev_u64;
     dim3 grid((unsigned)nb, n_arrays);
-    k_scan_reduce<<<grid, SC_THREADS, 0, st>>>((const uint32_t*)in, n_cap, stride, bs, (int)nb, popcount_input, nd);
-    k_scan_block_sums<<<n_arrays, 1024, 0, st>>>(bs, (int)nb, (unsigned long long*)totals_u64);
     if (out_is_u64)
-        k_scan_final<unsigned long long><<<grid, SC_THREADS, 0, st>>>((const uint32_t*)in, (unsigned long long*)out, n_cap, stride, bs, (int)nb, popcount_input, nd);
+        k_scan_lookback<unsigned long long><<<grid, SC_THREADS, 0, st>>>((const uint32_t*)in, (unsigned long long*)out, n_cap, stride, desc,
+                                                                         (int)nb, tickets, popcount_input, nd,
+                                                                         (unsigned long long*)totals_u64);
     else
-        k_scan_final<uint32_t><<<grid, SC_THREADS, 0, st>>>((const uint32_t*)in, (uint32_t*)out, n_cap, stride, bs, (int)nb, popcount_input, nd);
+        k_scan_lookback<uint32_t><<<grid, SC_THREADS, 0, st>>>((const uint32_t*)in, (uint32_t*)out, n_cap, stride, desc, (int)nb, tickets,
+                                                               popcount_input, nd, (unsigned long long*)totals_u64);
     T3D_CHECK_LAUNCH("t3d_exclusive_scan_u32");
-    t3d_count_launches(3);
+    t3d_count_launches(1);
     return 0;
 }
 

@@ -138,6 +138,16 @@ class DeviceVolume:
         return host.numpy()
 
 
+def download(t: torch.Tensor) -> np.ndarray:
+    """Device tensor -> numpy array backed by pinned host memory (DMA at PCIe speed; torch's caching host allocator
+    recycles the pinned blocks).  A plain `.cpu()` goes through pageable memory at a fraction of the bandwidth."""
+    t = t.contiguous()
+    host = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+    host.copy_(t, non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    return host.numpy()
+
+
 class DeviceMesh:
     """Mesh on the device.  After an asynchronous canonicalisation the arrays are capacity-sized and the true sizes
     live in `counts_dev` until resolve() (one D2H copy) or set_sizes() trims them."""
@@ -304,6 +314,85 @@ def pack_and_close(masks_u8_dev: torch.Tensor, threshold: int = 1, close_ends: b
     counts = torch.empty(Z, dtype=torch.int64, device=dev)
     check(L.t3d_gap_fill(_p(bits), _p(out), None, None, Z, H, W, _p(counts), _stream()), "t3d_gap_fill")
     return DeviceVolume(out, Z, H, W, counts)
+
+
+_copy_streams = {}
+
+
+def _copy_stream_pair(dev: torch.device):
+    key = (dev.type, dev.index)
+    st = _copy_streams.get(key)
+    if st is None:
+        st = (torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev))
+        _copy_streams[key] = st
+    return st
+
+
+def create_voxel_data_from_host(stack_u8: np.ndarray, threshold: int = 1, close_ends: bool = True, chunk_planes: int = 32):
+    """create_voxel_data (voxel_processor.py:36-54) for a host stack, pipelined in z-chunks so that the upload of the
+    masks (H2D), the kernels and the download of the resulting bool grid (D2H) overlap: PCIe is full duplex and the
+    two directions use different copy engines.  Returns (DeviceVolume, numpy bool array in pinned memory).
+
+    Chunk c is uploaded and packed while chunk c-1 is gap-filled (it needs one packed plane of chunk c), unpacked and
+    downloaded.  Global slices 0 / Z-1 are hole-filled right after their chunk is packed, i.e. before any gap fill
+    reads them, so the result is identical to the unpipelined path."""
+    L = _L()
+    dev = _require_cuda()
+    Z, H, W = (int(v) for v in stack_u8.shape)
+    wpr = words_per_row(W)
+    src = torch.from_numpy(np.ascontiguousarray(stack_u8)) if not isinstance(stack_u8, torch.Tensor) else stack_u8
+    masks_dev = torch.empty((Z, H, W), dtype=torch.uint8, device=dev)
+    bits = torch.empty((Z, H, wpr), dtype=torch.int32, device=dev)
+    out_bits = torch.empty_like(bits)
+    out_u8 = torch.empty((Z, H, W), dtype=torch.uint8, device=dev)
+    counts = torch.empty(Z, dtype=torch.int64, device=dev)
+    host = torch.empty((Z, H, W), dtype=torch.bool, pin_memory=True)
+    host_u8 = host.view(torch.uint8)
+    scratch = torch.empty(int(L.t3d_fill_holes_scratch_bytes(1, H, W)) // 4, dtype=torch.int32, device=dev)
+    main = torch.cuda.current_stream()
+    s_in, s_out = _copy_stream_pair(dev)
+    start = torch.cuda.Event()
+    start.record(main)
+    s_in.wait_event(start)
+    s_out.wait_event(start)
+    bounds = [(a, min(Z, a + chunk_planes)) for a in range(0, Z, chunk_planes)]
+    n_chunks = len(bounds)
+
+    def finish(c):  # gap fill (or copy) + unpack + download of chunk c; needs chunk c+1 packed when it exists
+        a, b = bounds[c]
+        if close_ends:
+            lo = bits[a - 1] if a > 0 else None
+            hi = bits[b] if b < Z else None
+            check(L.t3d_gap_fill(_p(bits[a]), _p(out_bits[a]), _p(lo), _p(hi), b - a, H, W, _p(counts[a:]), _stream()), "t3d_gap_fill")
+        check(L.t3d_unpack_bits(_p(out_bits[a]), b - a, H, W, _p(out_u8[a]), _stream()), "t3d_unpack_bits")
+        ev = torch.cuda.Event()
+        ev.record(main)
+        s_out.wait_event(ev)
+        with torch.cuda.stream(s_out):
+            host_u8[a:b].copy_(out_u8[a:b], non_blocking=True)
+
+    for c, (a, b) in enumerate(bounds):
+        with torch.cuda.stream(s_in):
+            masks_dev[a:b].copy_(src[a:b], non_blocking=True)
+            up = torch.cuda.Event()
+            up.record(s_in)
+        main.wait_event(up)
+        dst = bits if close_ends else out_bits
+        check(L.t3d_pack_masks(_p(masks_dev[a]), b - a, H, W, int(threshold), _p(dst[a]), _stream()), "t3d_pack_masks")
+        if close_ends:
+            if a == 0:
+                check(L.t3d_fill_holes_2d(_p(bits[0]), 1, 0, H, W, _p(scratch), _stream()), "t3d_fill_holes_2d")
+            if b == Z and Z > 1:
+                check(L.t3d_fill_holes_2d(_p(bits[Z - 1]), 1, 0, H, W, _p(scratch), _stream()), "t3d_fill_holes_2d")
+        if c > 0:
+            finish(c - 1)
+    finish(n_chunks - 1)
+    done = torch.cuda.Event()
+    done.record(s_out)
+    main.wait_event(done)
+    main.synchronize()
+    dv = DeviceVolume(out_bits, Z, H, W, counts if close_ends else None)
+    return dv, host.numpy()
 
 
 def volume_from_host(voxel_data: np.ndarray) -> DeviceVolume:

@@ -33,8 +33,8 @@ class SurfaceExtractor:
         try:
             dv = engine.volume_from_host(volume_data)
             mesh = engine.extract_surface(dv, slice_depths, mm_per_pixel_y, mm_per_pixel_x, manifold, add_padding)
-            vertices = mesh.verts.cpu().numpy()
-            faces = mesh.faces.cpu().numpy()
+            vertices = engine.download(mesh.verts)
+            faces = engine.download(mesh.faces)
             engine.meshes.register(vertices, mesh)
             engine.meshes.register(faces, mesh)
             self.last_mesh = mesh

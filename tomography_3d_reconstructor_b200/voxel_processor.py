@@ -42,9 +42,12 @@ class VoxelProcessor:
         self.side_1_count = side_1_count
         self.side_2_count = side_2_count
 
-        dv = engine.pack_and_close(engine.upload_u8(engine._as_stack(mask_images)), 1, close_ends)
+        # upload, pack/close and download pipelined in z-chunks (H2D and D2H overlap)
+        dv, host = engine.create_voxel_data_from_host(engine._as_stack(mask_images), 1, close_ends)
+        host.setflags(write=False)
+        engine.volumes.register(host, dv)
         active = int(dv.slice_counts().sum())
-        self.voxel_data = self._publish(dv)
+        self.voxel_data = host
         print(f"Voxels: {self.voxel_data.shape}, active: {active:,}")
         return self.voxel_data
 
