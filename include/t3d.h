@@ -87,6 +87,12 @@ int t3d_exclusive_scan_u32(const void* in, void* out, int64_t n, int n_arrays, i
 int t3d_field_sign(const void* occ_bits, int Z, int H, int W, int pad, const double* weights3_host, void* sign_bits,
                    void* n_exact_u64, void* stream);
 
+/* Same sign volume through a leaner kernel: the (rare) words that need the exact evaluation are recorded in
+ * exc_list_u64 (exc_cap entries) and patched by a second small kernel.  exc_count_u64 (device) = recorded words; if it
+ * exceeds exc_cap the result is incomplete and t3d_field_sign must be run instead. */
+int t3d_field_sign_lean(const void* occ_bits, int Z, int H, int W, int pad, const double* weights3_host, void* sign_bits,
+                        void* n_exact_u64, void* exc_list_u64, uint32_t exc_cap, void* exc_count_u64, void* stream);
+
 /* Two-pass marching cubes on a sign volume (Zs,Hs,Ws) = skimage.measure.marching_cubes(volume, 0.5), sparse after the
  * first dense pass (see csrc/t3d_mc.cu):
  *   t3d_mc_flags    -> ballots_u32[t3d_mc_num_chunks]: bit l of word c set iff sign word 32c+l owns a cut edge or an
@@ -166,7 +172,8 @@ int t3d_mesh_measure_dev(const void* verts_f32, const void* faces, int64_t F_cap
  * order + the result block results_u64[t3d_reconstruct_results_len(Z)]:
  *   [0] n_active [1] n_x [2] n_y [3] n_z [4] n_t (raw faces) [5] V' [6] F' [7] fast ordering unverified [8] overflow bits
  *   (1: active words, 2: vertices, 4: faces exceeded their capacity -> retry larger) [9] ambiguous cubes [10] exact field
- *   evaluations [11] signed mesh volume (f64) [12] area (f64) [13..15] bbox int32 x 6 [16] raw vertices
+ *   evaluations [11] signed mesh volume (f64) [12] area (f64) [13..15] bbox int32 x 6 [16] raw vertices [17] recorded
+ *   exact-evaluation words (overflow bit 8 if above the internal list capacity)
  *   [32 .. 32+Z) per-slice voxel counts after close_ends, [32+Z .. 32+2Z) after smoothing.
  * n_stages/erode_mask as t3d_morph (0 stages = no smoothing).  cum/adj: device float64 z-map arrays. */
 int64_t t3d_reconstruct_workspace_bytes(int Z, int H, int W, int add_padding, int n_stages, uint32_t cap_active,
@@ -187,6 +194,13 @@ int t3d_reconstruct(const void* masks_u8, int Z, int H, int W, int threshold, in
 int64_t t3d_edt_workspace_bytes(int Z, int H, int W);
 int t3d_edt(const void* occ_bits, int Z, int H, int W, int invert, const double* sampling_host, float sign, int accumulate,
             void* dist_f32, void* workspace, void* stream);
+
+/* Marching a dense float32 field directly (e.g. the SDF): sign bits = (field > level) packed like an occupancy volume,
+ * then t3d_mc_flags/words/emit on them, and vertices interpolated on the field itself. */
+int t3d_sign_from_f32(const void* field_f32, int Z, int H, int W, double level, void* sign_bits, void* stream);
+int t3d_mc_vertices_f32(const void* field_f32, int Z, int H, int W, double level, const void* vkeys_u64, uint32_t n_x, uint32_t n_y,
+                        uint32_t n_z, int unpad_shift, int z_offset, const void* cum_f64, const void* adj_f64, int n_cum,
+                        double mm_per_pixel_y, double mm_per_pixel_x, int scale_in_f64, void* verts_f32, void* stream);
 
 /* area-weighted unit vertex normals (the reference discards skimage's normals, surface_extractor.py:55 vs :72) */
 int t3d_vertex_normals(const void* verts_f32, int64_t V, const void* faces, int64_t F, int faces_are_i64, void* normals_f32,

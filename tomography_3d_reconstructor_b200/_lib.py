@@ -34,6 +34,7 @@ SIGNATURES = {
     "t3d_scan_workspace_bytes": (_i64, [_i64, _i]),
     "t3d_exclusive_scan_u32": (_i, [_vp, _vp, _i64, _i, _i, _i, _vp, _vp, _vp]),
     "t3d_field_sign": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "t3d_field_sign_lean": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _u32, _vp, _vp]),
     "t3d_mc_num_chunks": (_i64, [_i, _i, _i]),
     "t3d_mc_flags": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "t3d_mc_words": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _u32, _vp, _vp, _vp, _vp]),
@@ -60,6 +61,8 @@ SIGNATURES = {
                              _vp, _vp, _vp, _vp, _vp]),
     "t3d_edt_workspace_bytes": (_i64, [_i, _i, _i]),
     "t3d_edt": (_i, [_vp, _i, _i, _i, _i, _vp, _c.c_float, _i, _vp, _vp, _vp]),
+    "t3d_sign_from_f32": (_i, [_vp, _i, _i, _i, _dbl, _vp, _vp]),
+    "t3d_mc_vertices_f32": (_i, [_vp, _i, _i, _i, _dbl, _vp, _u32, _u32, _u32, _i, _i, _vp, _vp, _i, _dbl, _dbl, _i, _vp, _vp]),
     "t3d_vertex_normals": (_i, [_vp, _i64, _vp, _i64, _i, _vp, _vp]),
 }
 

@@ -137,3 +137,6 @@ __device__ __forceinline__ int64_t dev_n(int64_t cap, const unsigned long long* 
     const unsigned long long v = *p;
     return v < (unsigned long long)cap ? (int64_t)v : cap;
 }
+
+// rows each thread of the y-marching stencil kernels walks (tunable through the environment for experiments)
+int t3d_rows_per_thread(const char* env_name, int dflt);

@@ -147,11 +147,11 @@ __device__ __forceinline__ WordMasks load_masks(const Grid& g, uint32_t row, int
 // ------------------------------------------------------------------------------------------------
 #define GY 16
 
-__global__ void __launch_bounds__(256) k_mc_flags(Grid g, uint32_t* __restrict__ ballots, int lanes_x, int pz_per_block)
+__global__ void __launch_bounds__(256) k_mc_flags(Grid g, uint32_t* __restrict__ ballots, int lanes_x, int pz_per_block, int gy)
 {
     const int lx = threadIdx.x % lanes_x, pz = threadIdx.x / lanes_x;
     const int nws4 = g.nws >> 2;
-    const int w4 = blockIdx.x * lanes_x + lx, z = g.z_begin + blockIdx.z * pz_per_block + pz, y0 = blockIdx.y * GY;
+    const int w4 = blockIdx.x * lanes_x + lx, z = g.z_begin + blockIdx.z * pz_per_block + pz, y0 = blockIdx.y * gy;
     if (pz >= pz_per_block || w4 >= nws4 || z >= g.Zs || z > g.z_end) return;
     const bool hz = (z + 1 < g.Zs) && (z < g.z_end);  // ghost plane: x/y edges only
     const bool hx = (4 * w4 + 4 < g.nws);
@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(256) k_mc_flags(Grid g, uint32_t* __restrict__
     uint32_t n0, n1, m0 = 0, m1 = 0;
     uint4 c0 = row4(z, y0, n0), c1 = hz ? row4(z + 1, y0, n1) : zero;  // rows (z,y), (z+1,y)
     if (!hz) n1 = 0;
-    const int y1 = min(g.Hs, y0 + GY);
+    const int y1 = min(g.Hs, y0 + gy);
     for (int y = y0; y < y1; ++y) {
         const bool hy = (y + 1 < g.Hs);
         const uint4 d0 = hy ? row4(z, y + 1, m0) : zero;                 // rows (z,y+1), (z+1,y+1)
@@ -376,6 +376,8 @@ __global__ void __launch_bounds__(128) k_mc_emit(EmitArgs a)
 // ------------------------------------------------------------------------------------------------
 struct VertexArgs {
     OccView occ;
+    const float* field;       // optional dense float32 field (Z,H,W): marched directly at `level` (SDF path)
+    double level;             // iso level (0.5 for the Gaussian occupancy field)
     const unsigned long long* vkeys;
     uint32_t first, count;    // id range of this axis block
     int z_offset;             // global padded plane of local padded plane 0 (z-slab sharding; 0 on a single device)
@@ -394,9 +396,15 @@ __device__ __forceinline__ void vertex_body(const VertexArgs& p, const double* z
     const unsigned long long key = p.vkeys[id];
     const int x = (int)((key >> 2) & 0xfffffu), y = (int)((key >> 22) & 0xfffffu), z = (int)(key >> 42);
     float fa, fb;
-    edge_field_values<AXIS>(p.occ, zlut, z, y, x, fa, fb);
+    if (p.field) {
+        const int64_t i = ((int64_t)z * p.occ.H + y) * p.occ.W + x;
+        fa = p.field[i];
+        fb = p.field[i + (AXIS == 0 ? (int64_t)p.occ.H * p.occ.W : AXIS == 1 ? p.occ.W : 1)];
+    } else {
+        edge_field_values<AXIS>(p.occ, zlut, z, y, x, fa, fb);
+    }
     // skimage: strength = 1/(FLT_EPSILON + |v - level|), centre of mass of the two corners, all in double
-    const double va = (double)fa - 0.5, vb = (double)fb - 0.5;
+    const double va = (double)fa - p.level, vb = (double)fb - p.level;
     const double wa = __ddiv_rn(1.0, __dadd_rn(1.1920928955078125e-07, fabs(va)));
     const double wb = __ddiv_rn(1.0, __dadd_rn(1.1920928955078125e-07, fabs(vb)));
     const double frac = __ddiv_rn(wb, __dadd_rn(wa, wb));
@@ -484,8 +492,9 @@ extern "C" int t3d_mc_flags(const void* sign_bits, int Zs, int Hs, int Ws, int z
     T3D_CUDA(cudaMemsetAsync(ballots_u32, 0, sizeof(uint32_t) * (size_t)g.n_rows * g.ncr, st));
     const int nws4 = g.nws / 4, lanes_x = nws4 < 256 ? nws4 : 256, pzb = 256 / lanes_x;
     const int nz = (g.z_end < Zs ? g.z_end + 1 : Zs) - g.z_begin;
-    dim3 grid((nws4 + lanes_x - 1) / lanes_x, (Hs + GY - 1) / GY, (nz + pzb - 1) / pzb);
-    k_mc_flags<<<grid, 256, 0, st>>>(g, (uint32_t*)ballots_u32, lanes_x, pzb);
+    static const int gy = t3d_rows_per_thread("T3D_FLAGS_ROWS", GY);
+    dim3 grid((nws4 + lanes_x - 1) / lanes_x, (Hs + gy - 1) / gy, (nz + pzb - 1) / pzb);
+    k_mc_flags<<<grid, 256, 0, st>>>(g, (uint32_t*)ballots_u32, lanes_x, pzb, gy);
     T3D_CHECK_LAUNCH("t3d_mc_flags");
     t3d_count_launches(1);
     return 0;
@@ -555,6 +564,8 @@ extern "C" int t3d_mc_vertices(const void* occ_bits, int Z, int H, int W, int pa
     VertexArgs p;
     p.occ = t3d_make_view(occ_bits, Z, H, W, pad, gaussian, weights3_host);
     p.vkeys = (const unsigned long long*)vkeys_u64;
+    p.field = nullptr;
+    p.level = 0.5;
     p.shift = unpad_shift ? 1.0f : 0.0f;
     p.z_offset = z_offset;
     p.cum = (const double*)cum_f64;
@@ -634,6 +645,8 @@ extern "C" int t3d_mc_vertices_dev(const void* occ_bits, int Z, int H, int W, in
     VertexArgs p;
     p.occ = t3d_make_view(occ_bits, Z, H, W, pad, gaussian, weights3_host);
     p.vkeys = (const unsigned long long*)vkeys_u64;
+    p.field = nullptr;
+    p.level = 0.5;
     p.first = 0; p.count = cap_verts;
     p.shift = unpad_shift ? 1.0f : 0.0f;
     p.z_offset = z_offset;
@@ -647,5 +660,66 @@ extern "C" int t3d_mc_vertices_dev(const void* occ_bits, int Z, int H, int W, in
     k_mc_vertices_all<<<(cap_verts + 127) / 128, 128, 0, (cudaStream_t)stream>>>(p, (const unsigned long long*)sizes_u64, cap_verts);
     T3D_CHECK_LAUNCH("t3d_mc_vertices_dev");
     t3d_count_launches(1);
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// marching a dense float32 field (additive SDF path): sign bits and vertices straight from it
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_sign_from_f32(const float* __restrict__ field, int64_t n_rows, int W, int nw, double level,
+                                                       uint32_t* __restrict__ bits)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_rows * nw) return;
+    const int64_t row = i / nw;
+    const int w = (int)(i - row * nw);
+    const float* p = field + row * W + (w << 5);
+    const int n = min(32, W - (w << 5));
+    uint32_t v = 0;
+    for (int k = 0; k < n; ++k) v |= (uint32_t)(((double)p[k] - level) > 0.0) << k;
+    bits[i] = v;
+}
+
+// bit = (field > level), packed like an occupancy volume (Z,H,wpr(W))
+extern "C" int t3d_sign_from_f32(const void* field_f32, int Z, int H, int W, double level, void* sign_bits, void* stream)
+{
+    if (Z <= 0 || H <= 0 || W <= 0) { t3d_set_error("t3d_sign_from_f32: empty volume"); return 2; }
+    const int nw = t3d_wpr(W);
+    const int64_t rows = (int64_t)Z * H, n = rows * nw;
+    k_sign_from_f32<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const float*)field_f32, rows, W, nw, level,
+                                                                                 (uint32_t*)sign_bits);
+    T3D_CHECK_LAUNCH("t3d_sign_from_f32");
+    t3d_count_launches(1);
+    return 0;
+}
+
+// vertices of a mesh marched on the float field itself (no padding, no Gaussian): skimage's interpolation at `level`
+extern "C" int t3d_mc_vertices_f32(const void* field_f32, int Z, int H, int W, double level, const void* vkeys_u64, uint32_t n_x,
+                                   uint32_t n_y, uint32_t n_z, int unpad_shift, int z_offset, const void* cum_f64,
+                                   const void* adj_f64, int n_cum, double mm_per_pixel_y, double mm_per_pixel_x, int scale_in_f64,
+                                   void* verts_f32, void* stream)
+{
+    if (Z <= 0 || H <= 0 || W <= 0) { t3d_set_error("t3d_mc_vertices_f32: empty volume"); return 2; }
+    cudaStream_t st = (cudaStream_t)stream;
+    VertexArgs p;
+    p.occ = t3d_make_view(nullptr, Z, H, W, 0, 0, nullptr);
+    p.field = (const float*)field_f32;
+    p.level = level;
+    p.vkeys = (const unsigned long long*)vkeys_u64;
+    p.shift = unpad_shift ? 1.0f : 0.0f;
+    p.z_offset = z_offset;
+    p.cum = (const double*)cum_f64;
+    p.adj = (const double*)adj_f64;
+    p.n_cum = n_cum;
+    p.mm_y = mm_per_pixel_y;
+    p.mm_x = mm_per_pixel_x;
+    p.scale_f64 = scale_in_f64 ? 1 : 0;
+    p.verts = (float*)verts_f32;
+    int launches = 0;
+    if (n_x) { p.first = 0; p.count = n_x; k_mc_vertices<2><<<(n_x + 127) / 128, 128, 0, st>>>(p); ++launches; }
+    if (n_y) { p.first = n_x; p.count = n_y; k_mc_vertices<1><<<(n_y + 127) / 128, 128, 0, st>>>(p); ++launches; }
+    if (n_z) { p.first = n_x + n_y; p.count = n_z; k_mc_vertices<0><<<(n_z + 127) / 128, 128, 0, st>>>(p); ++launches; }
+    T3D_CHECK_LAUNCH("t3d_mc_vertices_f32");
+    t3d_count_launches(launches);
     return 0;
 }

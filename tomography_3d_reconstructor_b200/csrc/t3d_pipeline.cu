@@ -12,14 +12,16 @@
 // result block (uint64 slots); keep in sync with include/t3d.h and pipeline.py
 enum {
     R_NACTIVE = 0, R_NX = 1, R_NY = 2, R_NZ = 3, R_NT = 4, R_VCANON = 5, R_FCANON = 6, R_UNVERIFIED = 7, R_OVERFLOW = 8,
-    R_NAMBIGUOUS = 9, R_NEXACT = 10, R_VOLUME_F64 = 11, R_AREA_F64 = 12, R_BBOX_I32X6 = 13 /* 3 slots */, R_VRAW = 16,
+    R_NAMBIGUOUS = 9, R_NEXACT = 10, R_VOLUME_F64 = 11, R_AREA_F64 = 12, R_BBOX_I32X6 = 13 /* 3 slots */, R_VRAW = 16, R_NEXC = 17,
     R_COUNTS = 32  /* Z raw per-slice counts, then Z smoothed per-slice counts */
 };
+
+#define EXC_CAP (1u << 20)  // capacity of the list of sign words that need the exact field evaluation
 
 static inline int64_t al(int64_t x) { return (x + 255) & ~(int64_t)255; }
 
 struct Layout {
-    int64_t bitsA, bitsB, bitsC, morph, fill, sign, ballots, chunkbase, scan1, aw_idx, aw_cnt, aw_base, scan2, vkeys, verts_raw,
+    int64_t bitsA, bitsB, bitsC, morph, fill, sign, exc, ballots, chunkbase, scan1, aw_idx, aw_cnt, aw_base, scan2, vkeys, verts_raw,
         faces_raw, canon, measure, total;
 };
 
@@ -36,6 +38,7 @@ static Layout make_layout(int Z, int H, int W, int pad, uint32_t capNA, uint32_t
     L.morph = o; o += al(t3d_morph_scratch_bytes(Z, H, W, n_stages));
     L.fill = o; o += al(t3d_fill_holes_scratch_bytes(2, H, W));
     L.sign = o; o += al((int64_t)Zp * Hp * nwp * 4);
+    L.exc = o; o += al((int64_t)EXC_CAP * 8);
     L.ballots = o; o += al(n_chunks * 4);
     L.chunkbase = o; o += al(n_chunks * 4);
     L.scan1 = o; o += al(t3d_scan_workspace_bytes(n_chunks, 1));
@@ -62,13 +65,14 @@ extern "C" int64_t t3d_reconstruct_results_len(int Z) { return R_COUNTS + 2 * (i
 
 __global__ void k_finalize_sizes(unsigned long long* r, unsigned long long capNA, unsigned long long capV, unsigned long long capF)
 {
+    unsigned long long of8 = (r[R_NEXC] > EXC_CAP) ? 8ull : 0ull;
     const unsigned long long v = r[R_NX] + r[R_NY] + r[R_NZ];
     r[R_VRAW] = v;
     unsigned long long of = 0;
     if (r[R_NACTIVE] > capNA) of |= 1;
     if (v > capV) of |= 2;
     if (r[R_NT] > capF) of |= 4;
-    r[R_OVERFLOW] = of;
+    r[R_OVERFLOW] = of | of8;
 }
 
 struct SideStream {
@@ -152,7 +156,7 @@ extern "C" int t3d_reconstruct(const void* masks_u8, int Z, int H, int W, int th
     }
 
     // ---- extract_manifold_surface: field sign, two-pass marching cubes, vertices
-    RUN(t3d_field_sign(smoothed, Z, H, W, pad, weights3_host, ws + L.sign, R + R_NEXACT, st));
+    RUN(t3d_field_sign_lean(smoothed, Z, H, W, pad, weights3_host, ws + L.sign, R + R_NEXACT, ws + L.exc, EXC_CAP, R + R_NEXC, st));
     RUN(t3d_mc_flags(ws + L.sign, Zp, Hp, Wp, 0, -1, ws + L.ballots, st));
     RUN(t3d_exclusive_scan_u32(ws + L.ballots, ws + L.chunkbase, n_chunks, 1, 0, 1, R + R_NACTIVE, ws + L.scan1, st));
     RUN(t3d_mc_words_dev(ws + L.sign, Zp, Hp, Wp, 0, -1, ws + L.ballots, ws + L.chunkbase, cap_active, R + R_NACTIVE, ws + L.aw_idx,

@@ -56,15 +56,23 @@ __device__ __forceinline__ uint4 prow4(const OccView& v, int zp, int yp, int wp4
                       __funnelshift_l(o.z, o.w, 1));
 }
 
+// LEAN: words that need the exact evaluation are only RECORDED (flat word index << 32 | bit mask) and patched by
+// k_field_sign_fix afterwards; the kernel then carries no call and half the registers.  If more than exc_cap words are
+// recorded the caller must rerun the robust (LEAN = false) variant.
+template <bool LEAN>
 __global__ void __launch_bounds__(256) k_field_sign(OccView v, uint32_t* __restrict__ sign, int nwp, int lanes_x,
-                                                    int pz_per_block, unsigned long long* __restrict__ n_exact)
+                                                    int pz_per_block, int fy, unsigned long long* __restrict__ n_exact,
+                                                    unsigned long long* __restrict__ exc, unsigned long long exc_cap,
+                                                    unsigned long long* __restrict__ exc_count)
 {
     __shared__ OccView sv;  // the rare exact path takes the view by pointer (keeps it out of registers / local memory)
-    if (threadIdx.x == 0) sv = v;
-    __syncthreads();
+    if (!LEAN) {
+        if (threadIdx.x == 0) sv = v;
+        __syncthreads();
+    }
     const int lx = threadIdx.x % lanes_x, pz = threadIdx.x / lanes_x;
     const int nwp4 = nwp >> 2;
-    const int wp4 = blockIdx.x * lanes_x + lx, zp = blockIdx.z * pz_per_block + pz, y0 = blockIdx.y * FY;
+    const int wp4 = blockIdx.x * lanes_x + lx, zp = blockIdx.z * pz_per_block + pz, y0 = blockIdx.y * fy;
     if (pz >= pz_per_block || wp4 >= nwp4 || zp >= v.Zp) return;
     const uint4 vm = valid_mask4(wp4, v.Wp);
     const int zm_i = reflect_idx(zp - 1, v.Zp), zq_i = reflect_idx(zp + 1, v.Zp);
@@ -73,7 +81,7 @@ __global__ void __launch_bounds__(256) k_field_sign(OccView v, uint32_t* __restr
     uint32_t l0, r0, lc, rc, ln, rn;
     uint4 prev = prow4(v, zp, reflect_idx(y0 - 1, v.Hp), wp4, l0, r0);
     uint4 cur = prow4(v, zp, y0, wp4, lc, rc);
-    const int y1 = min(v.Hp, y0 + FY);
+    const int y1 = min(v.Hp, y0 + fy);
     for (int yp = y0; yp < y1; ++yp) {
         const uint4 next = prow4(v, zp, reflect_idx(yp + 1, v.Hp), wp4, ln, rn);
         uint32_t d0, d1;
@@ -97,14 +105,49 @@ __global__ void __launch_bounds__(256) k_field_sign(OccView v, uint32_t* __restr
         need.w = ((cur.w & ~any1.w) | (~cur.w & all1.w)) & vm.w;
         if (need.x | need.y | need.z | need.w) {
             atomicAdd(n_exact, (unsigned long long)popc4(need));
-            if (need.x) s.x = exact_sign_bits(&sv, zp, yp, 4 * wp4, need.x, s.x);
-            if (need.y) s.y = exact_sign_bits(&sv, zp, yp, 4 * wp4 + 1, need.y, s.y);
-            if (need.z) s.z = exact_sign_bits(&sv, zp, yp, 4 * wp4 + 2, need.z, s.z);
-            if (need.w) s.w = exact_sign_bits(&sv, zp, yp, 4 * wp4 + 3, need.w, s.w);
+            if (LEAN) {
+                const unsigned long long flat = ((unsigned long long)zp * v.Hp + yp) * nwp + 4 * wp4;
+                const uint32_t nd[4] = {need.x, need.y, need.z, need.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (nd[j]) {
+                        const unsigned long long k = atomicAdd(exc_count, 1ull);
+                        if (k < exc_cap) exc[k] = ((flat + j) << 32) | nd[j];
+                    }
+                }
+            } else {
+                if (need.x) s.x = exact_sign_bits(&sv, zp, yp, 4 * wp4, need.x, s.x);
+                if (need.y) s.y = exact_sign_bits(&sv, zp, yp, 4 * wp4 + 1, need.y, s.y);
+                if (need.z) s.z = exact_sign_bits(&sv, zp, yp, 4 * wp4 + 2, need.z, s.z);
+                if (need.w) s.w = exact_sign_bits(&sv, zp, yp, 4 * wp4 + 3, need.w, s.w);
+            }
         }
         *reinterpret_cast<uint4*>(sign + ((int64_t)zp * v.Hp + yp) * nwp + 4 * wp4) = and4(s, vm);
         prev = cur;
         cur = next; lc = ln; rc = rn;
+    }
+}
+
+// patch the recorded words: exact float64 evaluation of the flagged voxels (one thread per word)
+__global__ void __launch_bounds__(128) k_field_sign_fix(OccView v, uint32_t* __restrict__ sign, int nwp,
+                                                        const unsigned long long* __restrict__ exc, unsigned long long exc_cap,
+                                                        const unsigned long long* __restrict__ exc_count)
+{
+    const unsigned long long n = min(*exc_count, exc_cap);
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned long long e = exc[i];
+        const unsigned long long flat = e >> 32;
+        uint32_t need = (uint32_t)e;
+        const int wp = (int)(flat % nwp);
+        const unsigned long long row = flat / nwp;
+        const int yp = (int)(row % v.Hp), zp = (int)(row / v.Hp);
+        uint32_t s = sign[flat];
+        while (need) {
+            const int b = __ffs(need) - 1;
+            need &= need - 1;
+            if (field_value(v, zp, yp, (wp << 5) + b) > 0.5f) s |= 1u << b; else s &= ~(1u << b);
+        }
+        sign[flat] = s;
     }
 }
 
@@ -253,10 +296,36 @@ extern "C" int t3d_field_sign(const void* occ_bits, int Z, int H, int W, int pad
     const int nwp = t3d_wpr(v.Wp);
     T3D_CUDA(cudaMemsetAsync(n_exact_u64, 0, 8, st));
     const int nwp4 = nwp / 4, lanes_x = nwp4 < 256 ? nwp4 : 256, pzb = 256 / lanes_x;
-    dim3 grid((nwp4 + lanes_x - 1) / lanes_x, (v.Hp + FY - 1) / FY, (v.Zp + pzb - 1) / pzb);
-    k_field_sign<<<grid, 256, 0, st>>>(v, (uint32_t*)sign_bits, nwp, lanes_x, pzb, (unsigned long long*)n_exact_u64);
+    static const int fy = t3d_rows_per_thread("T3D_SIGN_ROWS", FY);
+    dim3 grid((nwp4 + lanes_x - 1) / lanes_x, (v.Hp + fy - 1) / fy, (v.Zp + pzb - 1) / pzb);
+    k_field_sign<false><<<grid, 256, 0, st>>>(v, (uint32_t*)sign_bits, nwp, lanes_x, pzb, fy, (unsigned long long*)n_exact_u64, nullptr, 0,
+                                              nullptr);
     T3D_CHECK_LAUNCH("t3d_field_sign");
     t3d_count_launches(1);
+    return 0;
+}
+
+// Same result through the lean kernel: the (rare) words needing the exact evaluation are recorded in exc_list_u64
+// (exc_cap entries) and patched by a second small kernel.  exc_count_u64 (device) receives the number of recorded
+// words: if it exceeds exc_cap the sign volume is incomplete and the caller must run t3d_field_sign instead.
+extern "C" int t3d_field_sign_lean(const void* occ_bits, int Z, int H, int W, int pad, const double* weights3, void* sign_bits,
+                                   void* n_exact_u64, void* exc_list_u64, uint32_t exc_cap, void* exc_count_u64, void* stream)
+{
+    if (Z <= 0 || H <= 0 || W <= 0) { t3d_set_error("t3d_field_sign_lean: empty volume"); return 2; }
+    cudaStream_t st = (cudaStream_t)stream;
+    const OccView v = t3d_make_view(occ_bits, Z, H, W, pad, 1, weights3);
+    const int nwp = t3d_wpr(v.Wp);
+    T3D_CUDA(cudaMemsetAsync(n_exact_u64, 0, 8, st));
+    T3D_CUDA(cudaMemsetAsync(exc_count_u64, 0, 8, st));
+    const int nwp4 = nwp / 4, lanes_x = nwp4 < 256 ? nwp4 : 256, pzb = 256 / lanes_x;
+    static const int fy = t3d_rows_per_thread("T3D_SIGN_ROWS", FY);
+    dim3 grid((nwp4 + lanes_x - 1) / lanes_x, (v.Hp + fy - 1) / fy, (v.Zp + pzb - 1) / pzb);
+    k_field_sign<true><<<grid, 256, 0, st>>>(v, (uint32_t*)sign_bits, nwp, lanes_x, pzb, fy, (unsigned long long*)n_exact_u64,
+                                             (unsigned long long*)exc_list_u64, exc_cap, (unsigned long long*)exc_count_u64);
+    k_field_sign_fix<<<T3D_NUM_SMS, 128, 0, st>>>(v, (uint32_t*)sign_bits, nwp, (const unsigned long long*)exc_list_u64, exc_cap,
+                                                  (const unsigned long long*)exc_count_u64);
+    T3D_CHECK_LAUNCH("t3d_field_sign_lean");
+    t3d_count_launches(2);
     return 0;
 }
 
@@ -387,6 +456,35 @@ __global__ void __launch_bounds__(256) k_face_compact(const int32_t* __restrict_
     const int64_t o = 3 * (int64_t)pos[i];
     if (out64) { out64[o] = a; out64[o + 1] = b; out64[o + 2] = c; }
     if (out32) { out32[o] = (int32_t)a; out32[o + 1] = (int32_t)b; out32[o + 2] = (int32_t)c; }
+}
+
+// faces through newid straight into the output (degenerate faces are rare): counts the invalid ones; the compaction
+// below runs only when there are any.  meta[0] = number of invalid faces.
+__global__ void __launch_bounds__(256) k_face_remap(const int32_t* __restrict__ faces, int64_t F_cap, const uint32_t* __restrict__ newid,
+                                                    uint32_t* __restrict__ valid, long long* __restrict__ out64, int32_t* __restrict__ out32,
+                                                    unsigned long long* __restrict__ n_invalid, const unsigned long long* __restrict__ F_dev)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t F = dev_n(F_cap, F_dev);
+    bool bad = false;
+    if (i < F) {
+        const uint32_t a = newid[faces[3 * i]], b = newid[faces[3 * i + 1]], c = newid[faces[3 * i + 2]];
+        bad = !(a != b && b != c && a != c);
+        valid[i] = bad ? 0u : 1u;
+        if (out64) { out64[3 * i] = a; out64[3 * i + 1] = b; out64[3 * i + 2] = c; }
+        if (out32) { out32[3 * i] = (int32_t)a; out32[3 * i + 1] = (int32_t)b; out32[3 * i + 2] = (int32_t)c; }
+    }
+    const uint32_t nb = __popc(__ballot_sync(0xffffffffu, bad));
+    if (lane_id() == 0 && nb) atomicAdd(n_invalid, (unsigned long long)nb);
+}
+
+// after k_face_remap: F' = F - invalid; the scan/compaction that follow see n = F only if something has to move
+__global__ void k_face_plan(const unsigned long long* __restrict__ n_invalid, int64_t F_cap, const unsigned long long* __restrict__ F_dev,
+                            unsigned long long* __restrict__ n_to_compact, unsigned long long* __restrict__ f_out)
+{
+    const unsigned long long F = (unsigned long long)dev_n(F_cap, F_dev);
+    *n_to_compact = (*n_invalid) ? F : 0ull;
+    *f_out = F - *n_invalid;
 }
 
 static size_t sort_temp_bytes(int64_t V)
@@ -564,12 +662,15 @@ static int canonicalize_fast_impl(const void* verts_in, int64_t V, const unsigne
     T3D_CUDA(cudaMemcpyAsync(counts, totals, 8, cudaMemcpyDeviceToDevice, st));
     k_scatter_unique<<<gv, 256, 0, st>>>(vin, perm, flags, pos, V, (float*)verts_out, newid, V_dev);
     if (F > 0) {
+        // totals[1] = invalid faces, totals[2] = faces the compaction has to look at (0 when nothing is invalid)
         const unsigned gf = (unsigned)((F + 255) / 256);
-        k_face_valid<<<gf, 256, 0, st>>>((const int32_t*)faces_in, F, newid, flags, F_dev);
-        if (t3d_exclusive_scan_u32_dev(flags, pos, F, F, 1, 0, 0, F_dev, totals, scan_ws, stream)) return 1;
-        T3D_CUDA(cudaMemcpyAsync(counts + 1, totals, 8, cudaMemcpyDeviceToDevice, st));
+        T3D_CUDA(cudaMemsetAsync(totals + 1, 0, 16, st));
+        k_face_remap<<<gf, 256, 0, st>>>((const int32_t*)faces_in, F, newid, flags, (long long*)faces_out_i64, (int32_t*)faces_out_i32,
+                                         totals + 1, F_dev);
+        k_face_plan<<<1, 1, 0, st>>>(totals + 1, F, F_dev, totals + 2, counts + 1);
+        if (t3d_exclusive_scan_u32_dev(flags, pos, F, F, 1, 0, 0, totals + 2, totals + 3, scan_ws, stream)) return 1;
         k_face_compact<<<gf, 256, 0, st>>>((const int32_t*)faces_in, F, newid, flags, pos, (long long*)faces_out_i64,
-                                           (int32_t*)faces_out_i32, F_dev);
+                                           (int32_t*)faces_out_i32, totals + 2);
     } else {
         T3D_CUDA(cudaMemsetAsync(counts + 1, 0, 8, st));
     }

@@ -10,6 +10,7 @@
 //
 // All kernels are HBM/L2-bandwidth bound integer work on the bit-packed occupancy; no tensor cores.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "t3d_common.cuh"
@@ -30,6 +31,14 @@ extern "C" const char* t3d_last_error(void) { return g_err; }
 static long long g_launches = 0;
 extern "C" void t3d_count_launches(int n) { g_launches += n; }
 extern "C" int64_t t3d_launch_count(void) { return g_launches; }
+
+int t3d_rows_per_thread(const char* env_name, int dflt)
+{
+    const char* e = getenv(env_name);
+    if (!e) return dflt;
+    const int v = atoi(e);
+    return (v >= 1 && v <= 4096) ? v : dflt;
+}
 extern "C" int t3d_version(void) { return 100; }
 extern "C" int64_t t3d_words_per_row(int W) { return t3d_wpr(W); }
 
@@ -443,13 +452,13 @@ extern "C" int t3d_gap_fill(const void* in_bits, void* out_bits, const void* lo_
 
 template <bool ER, bool FIX>
 __global__ void __launch_bounds__(256) k_morph4(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, int Z, int H,
-                                                int W, int nw, int lanes_x, int pz_per_block,
+                                                int W, int nw, int lanes_x, int pz_per_block, int my,
                                                 unsigned long long* __restrict__ counts)
 {
     constexpr uint32_t B = ER ? 0xffffffffu : 0u;
     const int lx = threadIdx.x % lanes_x, pz = threadIdx.x / lanes_x;
     const int nw4 = nw >> 2, nwv = (W + 31) >> 5;
-    const int w4 = blockIdx.x * lanes_x + lx, z = blockIdx.z * pz_per_block + pz, y0 = blockIdx.y * MY;
+    const int w4 = blockIdx.x * lanes_x + lx, z = blockIdx.z * pz_per_block + pz, y0 = blockIdx.y * my;
     extern __shared__ unsigned int s_cnt[];
     if (counts) {
         if ((int)threadIdx.x < pz_per_block) s_cnt[threadIdx.x] = 0;
@@ -469,7 +478,7 @@ __global__ void __launch_bounds__(256) k_morph4(const uint32_t* __restrict__ in,
         const uint4 B4 = splat4(B);
         uint4 prev = (y0 > 0) ? row4(z, y0 - 1) : B4;
         uint4 cur = row4(z, y0);
-        const int y1 = min(H, y0 + MY);
+        const int y1 = min(H, y0 + my);
 #pragma unroll 4
         for (int y = y0; y < y1; ++y) {
             const uint4 next = (y + 1 < H) ? row4(z, y + 1) : B4;
@@ -518,7 +527,8 @@ extern "C" int t3d_morph(const void* in_bits, void* out_bits, int Z, int H, int 
     if (slice_counts_u64) T3D_CUDA(cudaMemsetAsync(slice_counts_u64, 0, sizeof(unsigned long long) * Z, st));
     const int lanes_x = nw4 < 256 ? nw4 : 256;
     const int pzb = 256 / lanes_x;
-    dim3 grid((nw4 + lanes_x - 1) / lanes_x, (H + MY - 1) / MY, (Z + pzb - 1) / pzb);
+    static const int my = t3d_rows_per_thread("T3D_MORPH_ROWS", MY);
+    dim3 grid((nw4 + lanes_x - 1) / lanes_x, (H + my - 1) / my, (Z + pzb - 1) / pzb);
     const size_t smem = sizeof(unsigned int) * pzb;
     uint32_t* tmp[2] = {(uint32_t*)scratch, (uint32_t*)scratch + vol_words};
     const uint32_t* src = (const uint32_t*)in_bits;
@@ -527,9 +537,9 @@ extern "C" int t3d_morph(const void* in_bits, void* out_bits, int Z, int H, int 
         uint32_t* dst = last ? (uint32_t*)out_bits : tmp[s & 1];
         unsigned long long* cnt = last ? (unsigned long long*)slice_counts_u64 : nullptr;
         const bool er = (erode_mask >> s) & 1u;
-        if (er && (W & 127)) k_morph4<true, true><<<grid, 256, smem, st>>>(src, dst, Z, H, W, nw, lanes_x, pzb, cnt);
-        else if (er) k_morph4<true, false><<<grid, 256, smem, st>>>(src, dst, Z, H, W, nw, lanes_x, pzb, cnt);
-        else k_morph4<false, false><<<grid, 256, smem, st>>>(src, dst, Z, H, W, nw, lanes_x, pzb, cnt);
+        if (er && (W & 127)) k_morph4<true, true><<<grid, 256, smem, st>>>(src, dst, Z, H, W, nw, lanes_x, pzb, my, cnt);
+        else if (er) k_morph4<true, false><<<grid, 256, smem, st>>>(src, dst, Z, H, W, nw, lanes_x, pzb, my, cnt);
+        else k_morph4<false, false><<<grid, 256, smem, st>>>(src, dst, Z, H, W, nw, lanes_x, pzb, my, cnt);
         src = dst;
     }
     T3D_CHECK_LAUNCH("t3d_morph");

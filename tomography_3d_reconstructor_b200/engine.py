@@ -66,12 +66,13 @@ _W3_C = (ctypes.c_double * 3)(*_W3.tolist())
 class DeviceVolume:
     """Bit-packed occupancy (Z, H, wpr) int32 on the device + lazily cached reductions."""
 
-    __slots__ = ("bits", "Z", "H", "W", "_counts", "_bbox", "__weakref__")
+    __slots__ = ("bits", "Z", "H", "W", "_counts", "_bbox", "memo", "__weakref__")
 
     def __init__(self, bits: torch.Tensor, Z: int, H: int, W: int, counts: Optional[torch.Tensor] = None):
         self.bits, self.Z, self.H, self.W = bits, Z, H, W
         self._counts = counts  # device int64 (Z,) or host np.int64 once fetched
         self._bbox = None
+        self.memo = {}         # results derived from this (immutable) volume: smoothing, extraction (SURVEY.md 8f-2)
 
     @property
     def shape(self) -> Tuple[int, int, int]:
@@ -482,13 +483,25 @@ def z_map_arrays(slice_depths, add_padding: bool) -> Tuple[np.ndarray, np.ndarra
     return cum, adj
 
 
-def field_sign(dv: DeviceVolume, pad: int) -> Tuple[torch.Tensor, Tuple[int, int, int], torch.Tensor]:
+EXC_CAP = 1 << 18  # list capacity of the lean field-sign kernel (words needing the exact float64 evaluation)
+
+
+def field_sign(dv: DeviceVolume, pad: int, lean: bool = False):
+    """Sign volume of the marched field.  lean=True uses the two-kernel variant and additionally returns the device
+    counter of recorded exception words: above EXC_CAP the caller must call again with lean=False."""
     Z, H, W = dv.shape
     Zp, Hp, Wp = Z + 2 * pad, H + 2 * pad, W + 2 * pad
-    sign = torch.empty((Zp, Hp, words_per_row(Wp)), dtype=torch.int32, device=dv.bits.device)
-    n_exact = torch.empty(1, dtype=torch.int64, device=dv.bits.device)
-    check(_L().t3d_field_sign(_p(dv.bits), Z, H, W, pad, _W3_C, _p(sign), _p(n_exact), _stream()), "t3d_field_sign")
-    return sign, (Zp, Hp, Wp), n_exact
+    dev = dv.bits.device
+    sign = torch.empty((Zp, Hp, words_per_row(Wp)), dtype=torch.int32, device=dev)
+    n_exact = torch.empty(1, dtype=torch.int64, device=dev)
+    if not lean:
+        check(_L().t3d_field_sign(_p(dv.bits), Z, H, W, pad, _W3_C, _p(sign), _p(n_exact), _stream()), "t3d_field_sign")
+        return sign, (Zp, Hp, Wp), n_exact
+    exc = torch.empty(EXC_CAP, dtype=torch.int64, device=dev)
+    n_exc = torch.empty(1, dtype=torch.int64, device=dev)
+    check(_L().t3d_field_sign_lean(_p(dv.bits), Z, H, W, pad, _W3_C, _p(sign), _p(n_exact), _p(exc), EXC_CAP, _p(n_exc),
+                                   _stream()), "t3d_field_sign_lean")
+    return sign, (Zp, Hp, Wp), n_exact, n_exc
 
 
 def exclusive_scan_u32(x: torch.Tensor, n: int, n_arrays: int, out_u64: bool = False, popcount_input: bool = False):
@@ -504,13 +517,20 @@ def exclusive_scan_u32(x: torch.Tensor, n: int, n_arrays: int, out_u64: bool = F
 
 def extract_surface(dv: DeviceVolume, slice_depths, mm_per_pixel_y, mm_per_pixel_x, manifold: bool = True,
                     add_padding: bool = True, canonical: Optional[bool] = None, mark=None,
-                    z_begin: int = 0, z_end: int = -1, z_offset: int = 0) -> DeviceMesh:
+                    z_begin: int = 0, z_end: int = -1, z_offset: int = 0, field: Optional[torch.Tensor] = None,
+                    level: float = 0.5) -> DeviceMesh:
     """surface_extractor.py:43-68 on the device.  Raises RuntimeError/ValueError where skimage would.
 
     z_begin / z_end / z_offset: z-slab sharding (sharded.py): owned planes of the local sign volume and the global
     padded plane index of local padded plane 0."""
     L = _L()
     mark = mark or (lambda _n: None)
+    if field is not None:     # march a dense float32 field (SDF path): dv is ignored
+        Z, H, W = (int(v) for v in field.shape)
+        sbits = torch.empty((Z, H, words_per_row(W)), dtype=torch.int32, device=field.device)
+        check(L.t3d_sign_from_f32(_p(field), Z, H, W, float(level), _p(sbits), _stream()), "t3d_sign_from_f32")
+        dv, manifold_shift = DeviceVolume(sbits, Z, H, W), manifold
+        manifold = False
     Z, H, W = dv.shape
     pad = 1 if (manifold and add_padding) else 0
     gaussian = 1 if manifold else 0
@@ -522,17 +542,29 @@ def extract_surface(dv: DeviceVolume, slice_depths, mm_per_pixel_y, mm_per_pixel
     n_cum = len(cum)
     cum_d = torch.from_numpy(cum).to(dev, non_blocking=True) if n_cum else None
     adj_d = torch.from_numpy(adj).to(dev, non_blocking=True) if n_cum else None
+    n_exc_t = None
     if gaussian:
-        sign, (Zs, Hs, Ws), n_exact_t = field_sign(dv, pad)
+        sign, (Zs, Hs, Ws), n_exact_t, n_exc_t = field_sign(dv, pad, lean=True)
     else:
         sign, (Zs, Hs, Ws), n_exact_t = dv.bits, (Z, H, W), None
     mark("field_sign")
     n_chunks = int(L.t3d_mc_num_chunks(Zs, Hs, Ws))
     ballots = torch.empty(n_chunks, dtype=torch.int32, device=dev)
-    check(L.t3d_mc_flags(_p(sign), Zs, Hs, Ws, z_begin, z_end, _p(ballots), _stream()), "t3d_mc_flags")
-    chunkbase, n_act_t = exclusive_scan_u32(ballots, n_chunks, 1, popcount_input=True)
+
+    def flag_and_rank():
+        check(L.t3d_mc_flags(_p(sign), Zs, Hs, Ws, z_begin, z_end, _p(ballots), _stream()), "t3d_mc_flags")
+        return exclusive_scan_u32(ballots, n_chunks, 1, popcount_input=True)
+
+    chunkbase, n_act_t = flag_and_rank()
     mark("mc_flags")
-    n_active = int(n_act_t.cpu().item())
+    if n_exc_t is not None:
+        n_active, n_exc = (int(v) for v in torch.cat([n_act_t, n_exc_t]).cpu().tolist())
+        if n_exc > EXC_CAP:  # too many isolated voxels for the exception list: robust single-kernel variant
+            sign, _, n_exact_t = field_sign(dv, pad, lean=False)
+            chunkbase, n_act_t = flag_and_rank()
+            n_active = int(n_act_t.cpu().item())
+    else:
+        n_active = int(n_act_t.cpu().item())
     if n_active == 0:
         # skimage: ValueError (level outside the data range) or RuntimeError (no surface)
         raise RuntimeError("No surface found at the given iso value.")
@@ -558,12 +590,17 @@ def extract_surface(dv: DeviceVolume, slice_depths, mm_per_pixel_y, mm_per_pixel
                         nX, nY,
                         _p(vkeys), _p(faces), _stream()), "t3d_mc_emit")
     mark("mc_emit")
-    check(L.t3d_mc_vertices(_p(dv.bits), Z, H, W, pad, gaussian, _W3_C, _p(vkeys), nX, nY, nZ, 1 if manifold else 0,
-                            z_offset, _p(cum_d), _p(adj_d), n_cum, float(mm_per_pixel_y), float(mm_per_pixel_x), 1 if strong else 0,
-                            _p(verts), _stream()), "t3d_mc_vertices")
+    if field is not None:
+        check(L.t3d_mc_vertices_f32(_p(field), Z, H, W, float(level), _p(vkeys), nX, nY, nZ, 0, z_offset, _p(cum_d), _p(adj_d),
+                                    n_cum, float(mm_per_pixel_y), float(mm_per_pixel_x), 1 if strong else 0, _p(verts),
+                                    _stream()), "t3d_mc_vertices_f32")
+    else:
+        check(L.t3d_mc_vertices(_p(dv.bits), Z, H, W, pad, gaussian, _W3_C, _p(vkeys), nX, nY, nZ, 1 if manifold else 0,
+                                z_offset, _p(cum_d), _p(adj_d), n_cum, float(mm_per_pixel_y), float(mm_per_pixel_x),
+                                1 if strong else 0, _p(verts), _stream()), "t3d_mc_vertices")
     mark("mc_vertices")
     if canonical is None:
-        canonical = manifold
+        canonical = manifold or field is not None
     if not canonical:
         return DeviceMesh(verts, faces, n_ambiguous, n_exact)
     if canonical == "async":

@@ -32,8 +32,18 @@ class SurfaceExtractor:
         self.last_error = None
         try:
             dv = engine.volume_from_host(volume_data)
-            mesh = engine.extract_surface(dv, slice_depths, mm_per_pixel_y, mm_per_pixel_x, manifold, add_padding)
-            vertices = engine.download(mesh.verts)
+            # the orchestrator extracts the same surface four times (tomography_3d_reconstruction.py:131,153,177,213,243):
+            # memoise on the device volume (only volumes published by this package, which are read-only, can hit)
+            sd = np.asarray(slice_depths, dtype=np.float64)
+            key = ("extract", sd.tobytes(), repr(mm_per_pixel_y), repr(mm_per_pixel_x), type(mm_per_pixel_y).__name__,
+                   type(mm_per_pixel_x).__name__, bool(manifold), bool(add_padding))
+            cacheable = engine.volumes.lookup(volume_data) is dv
+            mesh = dv.memo.get(key) if cacheable else None
+            if mesh is None:
+                mesh = engine.extract_surface(dv, slice_depths, mm_per_pixel_y, mm_per_pixel_x, manifold, add_padding)
+                if cacheable:
+                    dv.memo[key] = mesh
+            vertices = engine.download(mesh.verts)      # fresh, writable host arrays on every call
             faces = engine.download(mesh.faces)
             engine.meshes.register(vertices, mesh)
             engine.meshes.register(faces, mesh)
@@ -67,6 +77,30 @@ class SurfaceExtractor:
     # ------------------------------------------------------------------------------------------------
     # additive API: the reference drops skimage's normals (surface_extractor.py:55 vs :72); they are exposed
     # here without widening the (vertices, faces) tuple
+    def extract_surface_from_sdf(self, sdf, slice_depths: np.ndarray, mm_per_pixel_y: float, mm_per_pixel_x: float,
+                                 level: float = 0.0) -> Optional[Tuple[np.ndarray, np.ndarray]]:
+        """Marching cubes on a signed distance field (positive inside, e.g. VoxelProcessor.compute_sdf) at `level`:
+        vertices float32 [z_mm, y_mm, x_mm] (z through the variable slice depths, no padding), np.unique order, faces
+        int64.  `sdf`: numpy float32 (Z,H,W) or a CUDA tensor."""
+        import torch
+        self.last_error = None
+        try:
+            f = sdf if isinstance(sdf, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(sdf, dtype=np.float32)).to(engine._require_cuda())
+            mesh = engine.extract_surface(None, slice_depths, mm_per_pixel_y, mm_per_pixel_x, False, False, field=f.contiguous(),
+                                          level=level)
+            vertices, faces = engine.download(mesh.verts), engine.download(mesh.faces)
+            engine.meshes.register(vertices, mesh)
+            engine.meshes.register(faces, mesh)
+            self.last_mesh, self.last_n_ambiguous = mesh, mesh.n_ambiguous
+            return vertices, faces
+        except engine.T3DUnavailable:
+            raise
+        except Exception as e:
+            self.last_error = e
+            if os.environ.get("T3D_RAISE"):
+                raise
+            return None
+
     def vertex_normals(self, vertices: np.ndarray, faces: np.ndarray) -> np.ndarray:
         """Area-weighted unit vertex normals, float32 (V,3) [z,y,x]."""
         from . import normals
