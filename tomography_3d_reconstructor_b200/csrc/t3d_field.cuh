@@ -190,25 +190,46 @@ __device__ __forceinline__ void edge_field_values(const OccView& v, const double
             col[dy] = c;
         }
     }
+    // z pass of column (dy, k): bit 6*plane + k of col[dy]; `oz` selects which five planes are the taps
+    auto zpass = [&](int dy, int k, int oz) -> double {
+        const uint32_t q = (uint32_t)(col[dy] >> (6 * oz + k));  // bit 6j = plane j of this column
+        const uint32_t c = (q >> 12) & 1u;
+        const uint32_t n1 = ((q >> 6) & 1u) + ((q >> 18) & 1u);
+        const uint32_t n2 = (q & 1u) + ((q >> 24) & 1u);
+        return zlut[c * 9 + n2 * 3 + n1];
+    };
+    if (AXIS == 2) {
+        // end points differ by one in x: the z and y passes of the six x columns are shared
+        double Y[6];
 #pragma unroll
-    for (int e = 0; e < 2; ++e) {
-        const int oz = e * (AXIS == 0), oy = e * (AXIS == 1), ox = e * (AXIS == 2);
-        double Y[5];
+        for (int k = 0; k < 6; ++k)
+            Y[k] = corr5(zpass(0, k, 0), zpass(1, k, 0), zpass(2, k, 0), zpass(3, k, 0), zpass(4, k, 0), v.w0, v.w1, v.w2);
+        fa = __double2float_rn(corr5(Y[0], Y[1], Y[2], Y[3], Y[4], v.w0, v.w1, v.w2));
+        fb = __double2float_rn(corr5(Y[1], Y[2], Y[3], Y[4], Y[5], v.w0, v.w1, v.w2));
+    } else if (AXIS == 1) {
+        // end points differ by one in y: the z pass of the six rows is shared
+        double Ya[5], Yb[5];
 #pragma unroll
-        for (int dx = 0; dx < 5; ++dx) {
-            double A[5];
+        for (int k = 0; k < 5; ++k) {
+            double A[6];
 #pragma unroll
-            for (int dy = 0; dy < 5; ++dy) {
-                const uint32_t q = (uint32_t)(col[oy + dy] >> (6 * oz + ox + dx));  // bit 6k = plane k of this column
-                const uint32_t c = (q >> 12) & 1u;
-                const uint32_t n1 = ((q >> 6) & 1u) + ((q >> 18) & 1u);
-                const uint32_t n2 = (q & 1u) + ((q >> 24) & 1u);
-                A[dy] = zlut[c * 9 + n2 * 3 + n1];
-            }
-            Y[dx] = corr5(A[0], A[1], A[2], A[3], A[4], v.w0, v.w1, v.w2);
+            for (int dy = 0; dy < 6; ++dy) A[dy] = zpass(dy, k, 0);
+            Ya[k] = corr5(A[0], A[1], A[2], A[3], A[4], v.w0, v.w1, v.w2);
+            Yb[k] = corr5(A[1], A[2], A[3], A[4], A[5], v.w0, v.w1, v.w2);
         }
-        const float f = __double2float_rn(corr5(Y[0], Y[1], Y[2], Y[3], Y[4], v.w0, v.w1, v.w2));
-        if (e == 0) fa = f; else fb = f;
+        fa = __double2float_rn(corr5(Ya[0], Ya[1], Ya[2], Ya[3], Ya[4], v.w0, v.w1, v.w2));
+        fb = __double2float_rn(corr5(Yb[0], Yb[1], Yb[2], Yb[3], Yb[4], v.w0, v.w1, v.w2));
+    } else {
+        // end points differ by one in z: different taps in every column
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            double Y[5];
+#pragma unroll
+            for (int k = 0; k < 5; ++k)
+                Y[k] = corr5(zpass(0, k, e), zpass(1, k, e), zpass(2, k, e), zpass(3, k, e), zpass(4, k, e), v.w0, v.w1, v.w2);
+            const float f = __double2float_rn(corr5(Y[0], Y[1], Y[2], Y[3], Y[4], v.w0, v.w1, v.w2));
+            if (e == 0) fa = f; else fb = f;
+        }
     }
 }
 

@@ -147,7 +147,7 @@ __device__ __forceinline__ WordMasks load_masks(const Grid& g, uint32_t row, int
 // ------------------------------------------------------------------------------------------------
 #define GY 16
 
-__global__ void __launch_bounds__(256) k_mc_flags(Grid g, uint32_t* __restrict__ ballots, int lanes_x, int pz_per_block, int gy)
+__global__ void __launch_bounds__(256, 5) k_mc_flags(Grid g, uint32_t* __restrict__ ballots, int lanes_x, int pz_per_block, int gy)
 {
     const int lx = threadIdx.x % lanes_x, pz = threadIdx.x / lanes_x;
     const int nws4 = g.nws >> 2;

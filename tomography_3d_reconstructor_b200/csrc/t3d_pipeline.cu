@@ -77,7 +77,7 @@ __global__ void k_finalize_sizes(unsigned long long* r, unsigned long long capNA
 
 struct SideStream {
     cudaStream_t s = nullptr;
-    cudaEvent_t e[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t e[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 static SideStream g_side[64];
 
@@ -88,7 +88,7 @@ static int side_for_current_device(SideStream** out)
     SideStream& s = g_side[dev & 63];
     if (!s.s) {
         T3D_CUDA(cudaStreamCreateWithFlags(&s.s, cudaStreamNonBlocking));
-        for (int k = 0; k < 4; ++k) T3D_CUDA(cudaEventCreateWithFlags(&s.e[k], cudaEventDisableTiming));
+        for (int k = 0; k < 6; ++k) T3D_CUDA(cudaEventCreateWithFlags(&s.e[k], cudaEventDisableTiming));
     }
     *out = &s;
     return 0;
@@ -168,11 +168,15 @@ extern "C" int t3d_reconstruct(const void* masks_u8, int Z, int H, int W, int th
                         R + R_NACTIVE, cap_verts, cap_faces, ws + L.vkeys, ws + L.faces_raw, st));
     RUN(t3d_mc_vertices_dev(smoothed, Z, H, W, pad, 1, weights3_host, ws + L.vkeys, R + R_NACTIVE, cap_verts, 1, 0, cum_f64, adj_f64,
                             n_cum, mm_per_pixel_y, mm_per_pixel_x, scale_in_f64, ws + L.verts_raw, st));
-    // ---- mesh volume / area on the emitted mesh, canonical mesh
-    RUN(t3d_mesh_measure_dev(ws + L.verts_raw, ws + L.faces_raw, cap_faces, R + R_NT, 0, R + R_VOLUME_F64, ws + L.measure, st));
+    // ---- mesh volume / area on the emitted mesh (side stream, concurrent with the canonical sort), canonical mesh
+    T3D_CUDA(cudaStreamWaitEvent(st, side->e[3], 0));   // the bbox reduction is done with the side stream
+    T3D_CUDA(cudaEventRecord(side->e[4], st));
+    T3D_CUDA(cudaStreamWaitEvent(side->s, side->e[4], 0));
+    RUN(t3d_mesh_measure_dev(ws + L.verts_raw, ws + L.faces_raw, cap_faces, R + R_NT, 0, R + R_VOLUME_F64, ws + L.measure, side->s));
+    T3D_CUDA(cudaEventRecord(side->e[5], side->s));
     RUN(t3d_mesh_canonicalize_fast_dev(ws + L.verts_raw, cap_verts, R + R_VRAW, ws + L.faces_raw, cap_faces, R + R_NT, verts_out_f32,
                                        faces_out_i64, nullptr, R + R_VCANON, ws + L.canon, st));
-    T3D_CUDA(cudaStreamWaitEvent(st, side->e[3], 0));
+    T3D_CUDA(cudaStreamWaitEvent(st, side->e[5], 0));
     T3D_CHECK_LAUNCH("t3d_reconstruct");
     t3d_count_launches(1);
     return 0;

@@ -26,7 +26,7 @@
 // Same shape as the morphology kernel: a thread owns one uint4 column of one padded plane and marches down FY
 // rows; the padded words are funnel-shifted out of the un-padded occupancy on the fly.
 // ------------------------------------------------------------------------------------------------
-#define FY 16
+#define FY 8
 
 __device__ __noinline__ uint32_t exact_sign_bits(const OccView* v, int zp, int yp, int wp, uint32_t need, uint32_t s)
 {
@@ -60,7 +60,7 @@ __device__ __forceinline__ uint4 prow4(const OccView& v, int zp, int yp, int wp4
 // k_field_sign_fix afterwards; the kernel then carries no call and half the registers.  If more than exc_cap words are
 // recorded the caller must rerun the robust (LEAN = false) variant.
 template <bool LEAN>
-__global__ void __launch_bounds__(256) k_field_sign(OccView v, uint32_t* __restrict__ sign, int nwp, int lanes_x,
+__global__ void __launch_bounds__(256, LEAN ? 4 : 2) k_field_sign(OccView v, uint32_t* __restrict__ sign, int nwp, int lanes_x,
                                                     int pz_per_block, int fy, unsigned long long* __restrict__ n_exact,
                                                     unsigned long long* __restrict__ exc, unsigned long long exc_cap,
                                                     unsigned long long* __restrict__ exc_count)

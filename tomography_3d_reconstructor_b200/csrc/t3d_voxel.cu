@@ -448,10 +448,10 @@ extern "C" int t3d_gap_fill(const void* in_bits, void* out_bits, const void* lo_
 // of one plane and marches down MY rows with the y neighbours in a register window: per 128 output voxels it issues
 // 3 x 128-bit loads (next row, z-1, z+1) + 2 scalar loads (x neighbours, L1 hits), 8 funnel shifts and 12 LOP3.
 // ------------------------------------------------------------------------------------------------
-#define MY 16
+#define MY 8
 
 template <bool ER, bool FIX>
-__global__ void __launch_bounds__(256) k_morph4(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, int Z, int H,
+__global__ void __launch_bounds__(256, 5) k_morph4(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, int Z, int H,
                                                 int W, int nw, int lanes_x, int pz_per_block, int my,
                                                 unsigned long long* __restrict__ counts)
 {
@@ -508,6 +508,173 @@ __global__ void __launch_bounds__(256) k_morph4(const uint32_t* __restrict__ in,
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Fused multi-stage morphology (up to 4 stages, e.g. opening then closing = E,D,D,E) in ONE pass over the volume.
+// A CTA owns a band of full-width rows and marches through a chunk of planes.  Level 0 = input, level k = output of
+// stage k-1; levels 0..NST-1 live in shared memory as rings of 4 planes, the last level goes to global memory.  Level k
+// lags level k-1 by two planes, so everything a step reads was written in an earlier step: one __syncthreads per
+// plane.  Cells outside the volume (rows, planes, tail bits) hold the border value of the stage that will READ them
+// (1 for an erosion, 0 for a dilation), which makes the inner loop branch-free.
+// The halo is nst rows / planes on each side (recomputed by neighbouring CTAs); band and chunk sizes are chosen so
+// that the grid is about one wave of the 148 SMs.
+// ------------------------------------------------------------------------------------------------
+struct FusedMorph {
+    const uint32_t* in;
+    uint32_t* out;
+    int Z, H, W, nw, nw4;
+    int nst;
+    uint32_t erode_mask;
+    int BY, BZ, RB;            // output rows per band, output planes per chunk, rows held in shared memory
+    unsigned long long* counts;
+};
+
+__global__ void __launch_bounds__(1024, 1) k_morph_fused(FusedMorph p)
+{
+    extern __shared__ uint4 ring[];  // [level][slot 0..3][row 0..RB)[w4]
+    __shared__ unsigned int s_cnt[2];
+    const int R = p.nst, RB = p.RB, nw4 = p.nw4;
+    const int yb0 = blockIdx.y * p.BY, yb1 = min(p.H, yb0 + p.BY);
+    const int zc0 = blockIdx.z * p.BZ, zc1 = min(p.Z, zc0 + p.BZ);
+    const int plane4 = RB * nw4;                  // uint4 per ring plane
+    const int nwv = (p.W + 31) >> 5;
+    const int T = (zc1 - zc0) + R + 2 * p.nst;
+    const int tid = threadIdx.x, nthreads = blockDim.x;
+    auto border = [&](int stage) -> uint32_t { return ((p.erode_mask >> stage) & 1u) ? 0xffffffffu : 0u; };
+    // items of one step: level 0 loads RB rows; level k (1..nst) computes rows [k, RB-k)
+    int first[6];
+    first[0] = 0;
+    first[1] = RB * nw4;
+    for (int k = 1; k <= p.nst; ++k) first[k + 1] = first[k] + (RB - 2 * k) * nw4;
+    const int n_items = first[p.nst + 1];
+    if (tid < 2) s_cnt[tid] = 0;
+    __syncthreads();
+
+    // input staging: every thread owns up to two uint4 of a plane; the global loads for plane zi+1 are issued at the
+    // start of step t and land in shared memory at the start of step t+1, so their latency hides behind the compute
+    const int n_in = first[1];
+    const uint32_t B0 = border(0);
+    auto load_in = [&](int zi, int j) -> uint4 {
+        const int r = j / nw4, w4 = j - r * nw4;
+        const int y = yb0 - R + r;
+        uint4 v = splat4(B0);
+        if (zi >= 0 && zi < p.Z && y >= 0 && y < p.H && zi < zc1 + R) {
+            v = *reinterpret_cast<const uint4*>(p.in + ((int64_t)zi * p.H + y) * p.nw + 4 * w4);
+            if (B0 && 4 * w4 + 4 > (p.W >> 5)) { const uint4 vm = valid_mask4(w4, p.W); v = make_uint4(v.x | ~vm.x, v.y | ~vm.y, v.z | ~vm.z, v.w | ~vm.w); }
+        }
+        return v;
+    };
+    uint4 pre0 = splat4(B0), pre1 = splat4(B0);
+    if (tid < n_in) pre0 = load_in(zc0 - R, tid);
+    if (tid + nthreads < n_in) pre1 = load_in(zc0 - R, tid + nthreads);
+
+    for (int t = 0; t < T; ++t) {
+        const int zi = zc0 - R + t;   // input plane of this step
+        // ---- level 0: plane zi (prefetched) -> ring, then prefetch plane zi + 1
+        {
+            uint4* dst = ring + ((zi + 64) & 3) * plane4;
+            if (tid < n_in) dst[tid] = pre0;
+            if (tid + nthreads < n_in) dst[tid + nthreads] = pre1;
+            if (tid < n_in) pre0 = load_in(zi + 1, tid);
+            if (tid + nthreads < n_in) pre1 = load_in(zi + 1, tid + nthreads);
+        }
+        uint32_t pc = 0;
+        for (int i = n_in + tid; i < n_items; i += nthreads) {
+            int k = 1;
+            while (i >= first[k + 1]) ++k;
+            const int j = i - first[k];
+            {
+                // ---- level k = stage k-1 applied to level k-1, plane z = zi - 2k
+                const int z = zi - 2 * k;
+                const int halo = R - k;
+                if (z < zc0 - halo || z >= zc1 + halo) continue;
+                const int rr = j / nw4, w4 = j - rr * nw4;
+                const int r = k + rr;
+                const int y = yb0 - R + r;
+                const bool er = (p.erode_mask >> (k - 1)) & 1u;
+                const uint32_t B = er ? 0xffffffffu : 0u;
+                const uint4* L = ring + (k - 1) * 4 * plane4;
+                const uint4* pc0 = L + ((z + 64) & 3) * plane4 + r * nw4 + w4;
+                const uint4 c = pc0[0], ym = pc0[-nw4], yp = pc0[nw4];
+                const uint4 zm = L[((z - 1 + 64) & 3) * plane4 + r * nw4 + w4], zq = L[((z + 1 + 64) & 3) * plane4 + r * nw4 + w4];
+                const uint32_t l = (w4 > 0) ? pc0[-1].w : B;
+                const uint32_t rgt = (4 * w4 + 4 < nwv) ? pc0[1].x : B;
+                const uint4 xm = shl1_4(c, l), xp = shr1_4(c, rgt);
+                uint4 v = er ? and4(and4(and4(c, xm), and4(xp, ym)), and4(and4(yp, zm), zq))
+                             : or4(or4(or4(c, xm), or4(xp, ym)), or4(or4(yp, zm), zq));
+                const uint4 vm = valid_mask4(w4, p.W);
+                const bool inside = (z >= 0 && z < p.Z && y >= 0 && y < p.H);
+                if (k < p.nst) {
+                    const uint32_t Bn = border(k);   // what the next stage must see outside the volume / beyond W
+                    if (!inside) v = splat4(Bn);
+                    else v = make_uint4((v.x & vm.x) | (Bn & ~vm.x), (v.y & vm.y) | (Bn & ~vm.y), (v.z & vm.z) | (Bn & ~vm.z), (v.w & vm.w) | (Bn & ~vm.w));
+                    ring[(k * 4 + ((z + 64) & 3)) * plane4 + r * nw4 + w4] = v;
+                } else if (inside && y >= yb0 && y < yb1) {
+                    v = and4(v, vm);
+                    *reinterpret_cast<uint4*>(p.out + ((int64_t)z * p.H + y) * p.nw + 4 * w4) = v;
+                    pc += popc4(v);
+                }
+            }
+        }
+        if (p.counts) {
+            pc = warp_sum(pc);
+            if ((tid & 31) == 0 && pc) atomicAdd(&s_cnt[t & 1], pc);
+        }
+        __syncthreads();
+        if (p.counts && tid == 0) {
+            const int zf = zi - 2 * p.nst;
+            const unsigned int c = s_cnt[t & 1];
+            if (c && zf >= zc0 && zf < zc1) atomicAdd(p.counts + zf, (unsigned long long)c);
+            s_cnt[t & 1] = 0;   // reused at step t+2, after the barrier of step t+1
+        }
+    }
+}
+
+// returns 1 if the fused kernel was launched, 0 if the shape does not fit (caller falls back to one launch per stage)
+static int launch_morph_fused(const uint32_t* in, uint32_t* out, int Z, int H, int W, int n_stages, unsigned erode_mask,
+                              unsigned long long* counts, cudaStream_t st, int* rc)
+{
+    *rc = 0;
+    if (n_stages < 2 || n_stages > 4) return 0;
+    // Correct but shared-memory-bandwidth bound (5 LDS.128 per 128 voxels and stage): 243 us vs 4 x 38 us for the
+    // per-stage kernels at 512x1024x1024, so it is opt-in until the z neighbours are kept in registers.
+    if (!getenv("T3D_FUSED_MORPH")) return 0;
+    const int nw = t3d_wpr(W), nw4 = nw / 4;
+    const int smem_budget = 200 * 1024;
+    const int row_bytes = nw * 4;
+    int RB = smem_budget / (n_stages * 4 * row_bytes);
+    if (RB > 64) RB = 64;
+    if (RB * nw4 > 2048) RB = 2048 / nw4;   // the input plane is staged by at most two uint4 per thread
+    int BY = RB - 2 * n_stages;
+    if (BY < 8) return 0;
+    if (BY > H) { BY = H; RB = BY + 2 * n_stages; }
+    const int n_bands = (H + BY - 1) / BY;
+    // even out the bands, then choose the chunk count so that bands * chunks is about one wave
+    BY = (H + n_bands - 1) / n_bands;
+    RB = BY + 2 * n_stages;
+    int n_chunks = T3D_NUM_SMS / n_bands;
+    if (n_chunks < 1) n_chunks = 1;
+    int BZ = (Z + n_chunks - 1) / n_chunks;
+    if (BZ < 4 * n_stages) BZ = Z < 4 * n_stages ? Z : 4 * n_stages;   // keep the redundant halo work bounded
+    n_chunks = (Z + BZ - 1) / BZ;
+    FusedMorph p;
+    p.in = in; p.out = out; p.Z = Z; p.H = H; p.W = W; p.nw = nw; p.nw4 = nw4; p.nst = n_stages; p.erode_mask = erode_mask;
+    p.BY = BY; p.BZ = BZ; p.RB = RB; p.counts = counts;
+    const size_t smem = (size_t)n_stages * 4 * RB * row_bytes;
+    static size_t attr = 0;
+    if (smem > attr) {
+        if (cudaFuncSetAttribute(k_morph_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+            cudaGetLastError();
+            return 0;
+        }
+        attr = smem;
+    }
+    dim3 grid(1, n_bands, n_chunks);
+    k_morph_fused<<<grid, 1024, smem, st>>>(p);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { t3d_set_error("t3d_morph (fused): launch failed: %s", cudaGetErrorString(e)); *rc = 1; }
+    return 1;
+}
+
 extern "C" int64_t t3d_morph_scratch_bytes(int Z, int H, int W, int n_stages)
 {
     return n_stages > 1 ? (int64_t)Z * H * t3d_wpr(W) * 4 * (n_stages > 2 ? 2 : 1) : 0;
@@ -525,6 +692,15 @@ extern "C" int t3d_morph(const void* in_bits, void* out_bits, int Z, int H, int 
     const int nw = t3d_wpr(W), nw4 = nw / 4;
     const int64_t vol_words = (int64_t)Z * H * nw;
     if (slice_counts_u64) T3D_CUDA(cudaMemsetAsync(slice_counts_u64, 0, sizeof(unsigned long long) * Z, st));
+    {   // all stages in one pass when they fit in shared memory
+        int rc = 0;
+        if (launch_morph_fused((const uint32_t*)in_bits, (uint32_t*)out_bits, Z, H, W, n_stages, erode_mask,
+                               (unsigned long long*)slice_counts_u64, st, &rc)) {
+            if (rc) return rc;
+            t3d_count_launches(1);
+            return 0;
+        }
+    }
     const int lanes_x = nw4 < 256 ? nw4 : 256;
     const int pzb = 256 / lanes_x;
     static const int my = t3d_rows_per_thread("T3D_MORPH_ROWS", MY);
