@@ -220,16 +220,18 @@ def reconstruct(masks_u8: torch.Tensor, Zg: int, z0: int, threshold: int, side_c
     local = slab_local(s, side_counts, total_depth_mm, x_length_mm, y_length_mm, iterations, add_padding, mark)
     sizes = [slab_range(Zg, r, world) for r in range(world)]
     if world > 1:
-        gathered = [torch.empty_like(local) for _ in range(world)]
-        dist.all_gather(gathered, local, group=group)
+        # ONE small all-gather: [local result vector | raw per-slice counts | smoothed per-slice counts] (padded)
         nmax = max(e - b for b, e in sizes)
-        pad_counts = torch.zeros(2 * nmax, dtype=torch.int64, device=s.dev)
-        pad_counts[:s.n] = s.cnt_raw
-        pad_counts[nmax:nmax + s.n] = s.cnt_sm
-        all_counts = [torch.empty_like(pad_counts) for _ in range(world)]
-        dist.all_gather(all_counts, pad_counts, group=group)
-        host = torch.stack(gathered).cpu()
-        hc = torch.stack(all_counts).cpu().numpy()
+        nl = int(local.numel())
+        msg = torch.zeros(nl + 2 * nmax, dtype=torch.int64, device=s.dev)
+        msg[:nl] = local
+        msg[nl:nl + s.n] = s.cnt_raw
+        msg[nl + nmax:nl + nmax + s.n] = s.cnt_sm
+        allmsg = torch.empty((world, nl + 2 * nmax), dtype=torch.int64, device=s.dev)
+        dist.all_gather_into_tensor(allmsg, msg, group=group)
+        hm = allmsg.cpu()
+        host = hm[:, :nl].contiguous()
+        hc = hm[:, nl:].numpy()
         raw_counts = np.concatenate([hc[r, :e - b] for r, (b, e) in enumerate(sizes)]).astype(np.int64)
         sm_counts = np.concatenate([hc[r, nmax:nmax + e - b] for r, (b, e) in enumerate(sizes)]).astype(np.int64)
     else:
