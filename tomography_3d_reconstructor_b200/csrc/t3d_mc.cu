@@ -275,13 +275,19 @@ __device__ __forceinline__ unsigned long long vkey(int axis, int z, int y, int x
 
 __global__ void __launch_bounds__(128) k_mc_emit(EmitArgs a)
 {
+    // per-thread tables indexed by cube edge (0..11), thread-major => bank-conflict free; the corner -> vertex id
+    // computation below is a table look-up instead of a 12-way switch (which diverged to ~4 active lanes)
     __shared__ __align__(16) int8_t s_tri[256][T3D_MC_ROW];
+    __shared__ uint32_t s_base[12][128];
+    __shared__ uint32_t s_mask[12][128];
+    __shared__ uint32_t s_next[4][128];   // ids of the y/z-edge vertices at bit 0 of the next word (edges 1, 5, 9, 10 at b = 31)
     {
         const int4* src = reinterpret_cast<const int4*>(&g_tri_table[0][0]);
         int4* dst = reinterpret_cast<int4*>(&s_tri[0][0]);
         for (int i = threadIdx.x; i < 256; i += blockDim.x) dst[i] = src[i];
     }
     __syncthreads();
+    const uint32_t tid = threadIdx.x;
     const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     if (a.sizes) {
         if ((unsigned long long)k >= a.sizes[0]) return;
@@ -328,13 +334,27 @@ __global__ void __launch_bounds__(128) k_mc_emit(EmitArgs a)
     // y/z edges at x0+32 (bit 0 of the next word) are only used by the cube at bit 31
     uint32_t nY0 = 0, nY1 = 0, nZ0 = 0, nZ1 = 0;
     if ((m.act >> 31) & 1u) {
-        // cut y/z edges at x+1 for b = 31: corners a00.. are the next word's bit 0
         const uint32_t v1 = (m.a00 >> 31) & 1u, v2 = (m.a01 >> 31) & 1u, v5 = (m.a10 >> 31) & 1u, v6 = (m.a11 >> 31) & 1u;
         if (v1 != v2) nY0 = a.offY + a.aw_base[NA + active_rank(a, row, w + 1)];            // edge 1
         if (v5 != v6) nY1 = a.offY + a.aw_base[NA + active_rank(a, row + Hs, w + 1)];       // edge 5
         if (v1 != v5) nZ0 = a.offZ + a.aw_base[2 * NA + active_rank(a, row, w + 1)];        // edge 9
-        if (v2 != v6) nZ1 = a.offZ + a.aw_base[2 * NA + active_rank(a, row + 1, w + 1)];   // edge 10
+        if (v2 != v6) nZ1 = a.offZ + a.aw_base[2 * NA + active_rank(a, row + 1, w + 1)];    // edge 10
     }
+    // edge -> (base id of the owning word's block, cut mask of that block)
+    s_base[0][tid] = bX00; s_mask[0][tid] = m.X00;
+    s_base[1][tid] = bY0;  s_mask[1][tid] = m.Y0;
+    s_base[2][tid] = bX01; s_mask[2][tid] = m.X01;
+    s_base[3][tid] = bY0;  s_mask[3][tid] = m.Y0;
+    s_base[4][tid] = bX10; s_mask[4][tid] = m.X10;
+    s_base[5][tid] = bY1;  s_mask[5][tid] = m.Y1;
+    s_base[6][tid] = bX11; s_mask[6][tid] = m.X11;
+    s_base[7][tid] = bY1;  s_mask[7][tid] = m.Y1;
+    s_base[8][tid] = bZ0;  s_mask[8][tid] = m.Z0;
+    s_base[9][tid] = bZ0;  s_mask[9][tid] = m.Z0;
+    s_base[10][tid] = bZ1; s_mask[10][tid] = m.Z1;
+    s_base[11][tid] = bZ1; s_mask[11][tid] = m.Z1;
+    s_next[0][tid] = nY0; s_next[1][tid] = nY1; s_next[2][tid] = nZ0; s_next[3][tid] = nZ1;
+    // (each thread reads back only its own column: no barrier needed)
 
     for (uint32_t q = m.act; q;) {
         const int b = __ffs(q) - 1;
@@ -342,27 +362,20 @@ __global__ void __launch_bounds__(128) k_mc_emit(EmitArgs a)
         const int cs = cube_case(m, b);
         const uint32_t lb = lt_mask(b), lb1 = lt_mask(b + 1);
         const bool last = (b == 31);
-        const int8_t* rowt = s_tri[cs];
-        for (int t = 0; t < T3D_MC_ROW && rowt[t] >= 0; t += 3) {
+        const int4 trow = *reinterpret_cast<const int4*>(s_tri[cs]);   // 16 edge ids, -1 terminated
+        const uint32_t tw[4] = {(uint32_t)trow.x, (uint32_t)trow.y, (uint32_t)trow.z, (uint32_t)trow.w};
+        auto edge_at = [&](int t) -> int { return (int)(int8_t)((tw[t >> 2] >> ((t & 3) * 8)) & 0xffu); };
+        for (int t = 0; t < 15; t += 3) {
+            const int e0 = edge_at(t);
+            if (e0 < 0) break;
             uint32_t vid[3];
 #pragma unroll
-            for (int e = 0; e < 3; ++e) {
-                uint32_t id;
-                switch (rowt[t + e]) {
-                    case 0: id = bX00 + __popc(m.X00 & lb); break;
-                    case 1: id = last ? nY0 : bY0 + __popc(m.Y0 & lb1); break;
-                    case 2: id = bX01 + __popc(m.X01 & lb); break;
-                    case 3: id = bY0 + __popc(m.Y0 & lb); break;
-                    case 4: id = bX10 + __popc(m.X10 & lb); break;
-                    case 5: id = last ? nY1 : bY1 + __popc(m.Y1 & lb1); break;
-                    case 6: id = bX11 + __popc(m.X11 & lb); break;
-                    case 7: id = bY1 + __popc(m.Y1 & lb); break;
-                    case 8: id = bZ0 + __popc(m.Z0 & lb); break;
-                    case 9: id = last ? nZ0 : bZ0 + __popc(m.Z0 & lb1); break;
-                    case 10: id = last ? nZ1 : bZ1 + __popc(m.Z1 & lb1); break;
-                    default: id = bZ1 + __popc(m.Z1 & lb); break;  // 11
-                }
-                vid[e] = id;
+            for (int c = 0; c < 3; ++c) {
+                const int e = (c == 0) ? e0 : edge_at(t + c);
+                const uint32_t at_next = (0x622u >> e) & 1u;           // edges 1, 5, 9, 10 sit at x + 1
+                uint32_t id = s_base[e][tid] + __popc(s_mask[e][tid] & (at_next ? lb1 : lb));
+                if (last && at_next) id = s_next[((e >> 2) & 1) + 2 * ((e >> 3) & 1) + ((e >> 3) & 1) * ((e >> 1) & 1)][tid];
+                vid[c] = id;
             }
             int32_t* f = a.faces + 3 * (int64_t)pT;
             f[0] = (int32_t)vid[2]; f[1] = (int32_t)vid[1]; f[2] = (int32_t)vid[0];
