@@ -204,8 +204,12 @@ def run_ours(args, Z, H, W):
 
     def step(mark=None):
         if world > 1:
-            return sharded.reconstruct(masks, Zg, z0, THRESHOLD, sides, PHYS["total_depth_mm"], PHYS["x_length_mm"],
-                                       PHYS["y_length_mm"], mark=mark)
+            if mark is not None or args.staged:
+                return sharded.reconstruct(masks, Zg, z0, THRESHOLD, sides, PHYS["total_depth_mm"], PHYS["x_length_mm"],
+                                           PHYS["y_length_mm"], mark=mark)
+            # fused: pack -> NCCL halo exchange -> one t3d_reconstruct_slab enqueue -> all-gather -> stitch, one sync
+            return sharded.reconstruct_fused(masks, Zg, z0, THRESHOLD, sides, PHYS["total_depth_mm"], PHYS["x_length_mm"],
+                                             PHYS["y_length_mm"])
         if mark is not None or args.staged:   # staged path: one library call per stage (per-stage event timing)
             return pipeline.reconstruct(masks, THRESHOLD, sides, PHYS["total_depth_mm"], PHYS["x_length_mm"],
                                         PHYS["y_length_mm"], mark=mark)
@@ -340,7 +344,9 @@ def run_ours(args, Z, H, W):
                    (Zg, H, W, "" if world == 1 else "; z-slab sharded over %d GPUs" % world),
                    "shape": [Zg, H, W], "l2": "inputs larger than L2: %.0f MB of u8 masks per GPU per step" % (per_gpu_vox / 1e6),
                    "mesh": {"vertices": V, "faces": F, "n_ambiguous_cubes": int(mesh.n_ambiguous)},
-                   "execution": ("z-slab sharded, staged launches" if world > 1 else "staged launches" if args.staged else
+                   "execution": ("z-slab sharded, staged launches" if world > 1 and args.staged else
+                                 "z-slab sharded: pack, NCCL halo exchange, one t3d_reconstruct_slab enqueue, result all-gather, "
+                                 "face stitching; one host sync per step" if world > 1 else "staged launches" if args.staged else
                                  "one t3d_reconstruct enqueue per step" + ("" if args.no_graph else ", replayed from a CUDA graph"))},
         "clocks": clocks.summary(),
         "gpu_launches": int(launches),

@@ -173,7 +173,8 @@ int t3d_mesh_measure_dev(const void* verts_f32, const void* faces, int64_t F_cap
  *   [0] n_active [1] n_x [2] n_y [3] n_z [4] n_t (raw faces) [5] V' [6] F' [7] fast ordering unverified [8] overflow bits
  *   (1: active words, 2: vertices, 4: faces exceeded their capacity -> retry larger) [9] ambiguous cubes [10] exact field
  *   evaluations [11] signed mesh volume (f64) [12] area (f64) [13..15] bbox int32 x 6 [16] raw vertices [17] recorded
- *   exact-evaluation words (overflow bit 8 if above the internal list capacity)
+ *   exact-evaluation words (overflow bit 8 if above the internal list capacity).  On overflow nothing is emitted: slots
+ *   [0..4] and [16] read 0 and the sizes that did not fit are kept in [20..24].
  *   [32 .. 32+Z) per-slice voxel counts after close_ends, [32+Z .. 32+2Z) after smoothing.
  * n_stages/erode_mask as t3d_morph (0 stages = no smoothing).  cum/adj: device float64 z-map arrays. */
 int64_t t3d_reconstruct_workspace_bytes(int Z, int H, int W, int add_padding, int n_stages, uint32_t cap_active,
@@ -184,6 +185,27 @@ int t3d_reconstruct(const void* masks_u8, int Z, int H, int W, int threshold, in
                     double mm_per_pixel_y, double mm_per_pixel_x, int scale_in_f64, uint32_t cap_active, uint32_t cap_verts,
                     uint32_t cap_faces, void* verts_out_f32, void* faces_out_i64, void* results_u64, void* workspace,
                     void* stream);
+
+/* z-slab variant of t3d_reconstruct for one rank of a sharded run (host side: sharded.py).  ext_bits holds
+ * halo_lo + n_own + halo_hi bit-planes: the rank's own packed slices (global end slices already hole-filled) between the
+ * planes received from its z-neighbours.  Gap fill and morphology are recomputed on the halo; the surface is marched on
+ * min(3, halo) planes either side with z_begin/z_end (owned planes of the local padded sign volume, as t3d_mc_flags) and
+ * z_offset (global plane index of local surface plane 0, as t3d_mc_vertices).  The result block is t3d_reconstruct's with
+ * Zx = halo_lo + n_own + halo_hi per-plane counts twice from slot 32 (bbox is over the own planes, local z), plus
+ *   [18] ghost tail: canonical vertices with z == z_ghost (the next rank's first plane), if want_ghost
+ *   [19] lead: canonical vertices with z == z_lead (this rank's first plane), if want_lead. */
+int64_t t3d_reconstruct_slab_workspace_bytes(int halo_lo, int n_own, int halo_hi, int H, int W, int add_padding, int n_stages,
+                                             uint32_t cap_active, uint32_t cap_verts, uint32_t cap_faces);
+int t3d_reconstruct_slab(const void* ext_bits, int halo_lo, int n_own, int halo_hi, int H, int W, int n_stages,
+                         unsigned erode_mask, int add_padding, int z_begin, int z_end, int z_offset, int want_ghost, float z_ghost,
+                         int want_lead, float z_lead, const double* weights3_host, const void* cum_f64, const void* adj_f64,
+                         int n_cum, double mm_per_pixel_y, double mm_per_pixel_x, int scale_in_f64, uint32_t cap_active,
+                         uint32_t cap_verts, uint32_t cap_faces, void* verts_out_f32, void* faces_out_i64, void* results_u64,
+                         void* workspace, void* stream);
+/* faces_i64[0 .. 3*F'[rank]) += sum over lower ranks of (V' - ghost tail), read from the all-gathered result blocks
+ * (world x stride_u64 uint64 on the device): local vertex ids -> ids in the stitched mesh. */
+int t3d_slab_stitch_faces(void* faces_i64, int64_t cap_faces, const void* gathered_results_u64, int64_t stride_u64, int rank,
+                          void* stream);
 
 /* ---- additive stages (no reference counterpart) ------------------------------------- */
 

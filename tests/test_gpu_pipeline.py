@@ -73,6 +73,56 @@ def test_sharded_slabs_stitch_to_the_single_gpu_mesh(eng, oracle, shape, world):
     assert o["total_vertices"] == len(rv) and o["total_faces"] == len(rf)
 
 
+@pytest.mark.parametrize("world", [1, 2, 3])
+@pytest.mark.parametrize("shape", [(40, 64, 96), (53, 70, 130)])
+def test_fused_slab_path_stitches_to_the_single_gpu_mesh(eng, oracle, shape, world):
+    """t3d_reconstruct_slab + t3d_slab_stitch_faces (the sharded step without host synchronisation), all ranks emulated on
+    ONE GPU: device copies stand in for the NCCL halo exchange and the all-gather of the result blocks."""
+    from tomography_3d_reconstructor_b200 import pipeline, sharded
+    Z, H, W = shape
+    u8 = oracle.ellipsoid_phantom_u8(Z, H, W)
+    u8[0, H // 2 - 2:H // 2 + 2, W // 2 - 3:W // 2 + 3] = 0
+    sides = (Z // 8, Z - 2 * (Z // 8), Z // 8)
+    full = torch.from_numpy(u8).cuda()
+    ref = pipeline.reconstruct(full, 200, sides, 6.0, 143.1, 95.03)
+    rm = ref["mesh"]
+    caps = pipeline._caps_from(rm.n_active, *rm.n_raw)           # generous: the whole mesh per rank
+    ranges = [sharded.slab_range(Z, r, world) for r in range(world)]
+    plans = [sharded.FusedSlabPlan(b - a, H, W, Z, a, 200, sides, 6.0, 143.1, 95.03, 3, True, caps, full.device, r, world)
+             for r, (a, b) in enumerate(ranges)]
+    for pl, (a, b) in zip(plans, ranges):
+        pl.pack(full[a:b].contiguous())
+    for r, s in enumerate(plans):
+        if s.hl:
+            lo = plans[r - 1]
+            s.ext[:s.hl] = lo.ext[lo.hl + lo.n - s.hl:lo.hl + lo.n]
+        if s.hh:
+            hi = plans[r + 1]
+            s.ext[s.hl + s.n:] = hi.ext[hi.hl:hi.hl + s.hh]
+    for pl in plans:
+        pl.compute()
+    gathered = torch.stack([pl.res for pl in plans])
+    for pl in plans:
+        pl.gathered.copy_(gathered)
+        pl.stitch()
+    h = gathered.cpu().numpy()
+    assert not h[:, pipeline.R_OVERFLOW].any() and not h[:, pipeline.R_UNVERIFIED].any()
+    outs = [sharded.assemble(pl, h) for pl in plans]
+    assert all(o["stitch_consistent"] for o in outs)
+    v = torch.cat([o["verts"] for o in outs]).cpu().numpy()
+    f = torch.cat([o["faces"] for o in outs]).cpu().numpy()
+    rv, rf = rm.verts.cpu().numpy(), rm.faces.cpu().numpy()
+    assert np.array_equal(v.view(np.uint32), rv.view(np.uint32))
+    assert np.array_equal(f, rf)
+    o = outs[-1]
+    assert o["voxel_volume_mm3"] == ref["voxel_volume_mm3"]
+    assert o["processed_voxel_volume_mm3"] == ref["processed_voxel_volume_mm3"]
+    assert o["bbox_index"] == ref["bbox_index"] and o["active_voxels"] == ref["active_voxels"]
+    assert abs(o["mesh_volume_mm3"] - ref["mesh_volume_mm3"]) <= 1e-9 * ref["mesh_volume_mm3"]
+    assert abs(o["surface_area_mm2"] - ref["surface_area_mm2"]) <= 1e-9 * ref["surface_area_mm2"]
+    assert o["total_vertices"] == len(rv) and o["total_faces"] == len(rf)
+
+
 @pytest.mark.parametrize("use_graph", [False, True])
 def test_fused_single_enqueue_path_matches_staged_path(eng, oracle, use_graph):
     """t3d_reconstruct (one enqueue, device-resident sizes, optionally replayed from a CUDA graph) against the staged

@@ -13,10 +13,12 @@
 enum {
     R_NACTIVE = 0, R_NX = 1, R_NY = 2, R_NZ = 3, R_NT = 4, R_VCANON = 5, R_FCANON = 6, R_UNVERIFIED = 7, R_OVERFLOW = 8,
     R_NAMBIGUOUS = 9, R_NEXACT = 10, R_VOLUME_F64 = 11, R_AREA_F64 = 12, R_BBOX_I32X6 = 13 /* 3 slots */, R_VRAW = 16, R_NEXC = 17,
-    R_COUNTS = 32  /* Z raw per-slice counts, then Z smoothed per-slice counts */
+    R_NGHOST = 18, R_NLEAD = 19,
+    R_COUNTS = 32  /* Zx raw per-slice counts, then Zx smoothed per-slice counts */
 };
 
 #define EXC_CAP (1u << 20)  // capacity of the list of sign words that need the exact field evaluation
+#define SURF_HALO 3         // smoothed planes the surface stage reads beyond the owned ones (Gaussian radius 2 + upper cube corner)
 
 static inline int64_t al(int64_t x) { return (x + 255) & ~(int64_t)255; }
 
@@ -25,17 +27,19 @@ struct Layout {
         faces_raw, canon, measure, total;
 };
 
-static Layout make_layout(int Z, int H, int W, int pad, uint32_t capNA, uint32_t capV, uint32_t capF, int n_stages)
+// Zx: planes of the voxel buffers (own slices + halos); Zl: planes the surface stage reads
+static Layout make_layout(int Zx, int Zl, int H, int W, int pad, uint32_t capNA, uint32_t capV, uint32_t capF, int n_stages,
+                          bool own_bitsA)
 {
     Layout L;
-    const int64_t nw = t3d_words_per_row(W), vol = (int64_t)Z * H * nw * 4;
-    const int Zp = Z + 2 * pad, Hp = H + 2 * pad, Wp = W + 2 * pad;
+    const int64_t nw = t3d_words_per_row(W), vol = (int64_t)Zx * H * nw * 4;
+    const int Zp = Zl + 2 * pad, Hp = H + 2 * pad, Wp = W + 2 * pad;
     const int64_t nwp = t3d_words_per_row(Wp), n_chunks = t3d_mc_num_chunks(Zp, Hp, Wp);
     int64_t o = 0;
-    L.bitsA = o; o += al(vol);
+    L.bitsA = o; o += own_bitsA ? al(vol) : 0;
     L.bitsB = o; o += al(vol);
     L.bitsC = o; o += al(vol);
-    L.morph = o; o += al(t3d_morph_scratch_bytes(Z, H, W, n_stages));
+    L.morph = o; o += al(t3d_morph_scratch_bytes(Zx, H, W, n_stages));
     L.fill = o; o += al(t3d_fill_holes_scratch_bytes(2, H, W));
     L.sign = o; o += al((int64_t)Zp * Hp * nwp * 4);
     L.exc = o; o += al((int64_t)EXC_CAP * 8);
@@ -58,10 +62,19 @@ static Layout make_layout(int Z, int H, int W, int pad, uint32_t capNA, uint32_t
 extern "C" int64_t t3d_reconstruct_workspace_bytes(int Z, int H, int W, int add_padding, int n_stages, uint32_t cap_active,
                                                    uint32_t cap_verts, uint32_t cap_faces)
 {
-    return make_layout(Z, H, W, add_padding ? 1 : 0, cap_active, cap_verts, cap_faces, n_stages).total;
+    return make_layout(Z, Z, H, W, add_padding ? 1 : 0, cap_active, cap_verts, cap_faces, n_stages, true).total;
 }
 
 extern "C" int64_t t3d_reconstruct_results_len(int Z) { return R_COUNTS + 2 * (int64_t)Z; }
+
+static inline int imin(int a, int b) { return a < b ? a : b; }
+
+extern "C" int64_t t3d_reconstruct_slab_workspace_bytes(int halo_lo, int n_own, int halo_hi, int H, int W, int add_padding,
+                                                        int n_stages, uint32_t cap_active, uint32_t cap_verts, uint32_t cap_faces)
+{
+    const int Zx = halo_lo + n_own + halo_hi, Zl = imin(SURF_HALO, halo_lo) + n_own + imin(SURF_HALO, halo_hi);
+    return make_layout(Zx, Zl, H, W, add_padding ? 1 : 0, cap_active, cap_verts, cap_faces, n_stages, false).total;
+}
 
 __global__ void k_finalize_sizes(unsigned long long* r, unsigned long long capNA, unsigned long long capV, unsigned long long capF)
 {
@@ -73,6 +86,51 @@ __global__ void k_finalize_sizes(unsigned long long* r, unsigned long long capNA
     if (v > capV) of |= 2;
     if (r[R_NT] > capF) of |= 4;
     r[R_OVERFLOW] = of | of8;
+    if (of | of8) {
+        // the emit kernel writes nothing on overflow: make every later stage see an empty mesh instead of stale indices
+        // (the sizes that did not fit are kept in slots 20..24 for the caller's next capacity guess)
+        for (int k = 0; k < 5; ++k) { r[20 + k] = r[R_NACTIVE + k]; r[R_NACTIVE + k] = 0; }
+        r[R_VRAW] = 0;
+    }
+}
+
+// Number of canonical vertices whose z equals zq[w] (warp w): the list is sorted by z first, so this is
+// upper_bound - lower_bound, found by a 32-ary search (one probe per lane and step).
+__global__ void k_count_plane_vertices(const float* __restrict__ verts, const unsigned long long* n_dev, float z_ghost, float z_lead,
+                                       int want_ghost, int want_lead, unsigned long long* out_ghost, unsigned long long* out_lead)
+{
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool want = w == 0 ? want_ghost != 0 : want_lead != 0;
+    unsigned long long* out = w == 0 ? out_ghost : out_lead;
+    if (!want) {
+        if (lane == 0) *out = 0;
+        return;
+    }
+    const float zq = w == 0 ? z_ghost : z_lead;
+    const long long n = (long long)*n_dev;
+    long long bound[2];
+    for (int upper = 0; upper < 2; ++upper) {
+        // smallest i with z[i] >= zq (lower) / z[i] > zq (upper)
+        long long lo = 0, hi = n;   // answer in [lo, hi]
+        while (hi - lo > 0) {
+            const long long span = hi - lo, step = (span + 31) / 32;
+            const long long i = lo + (long long)lane * step;
+            bool before = false;     // element i is before the answer
+            if (i < hi) {
+                const float z = verts[3 * i];
+                before = upper ? (z <= zq) : (z < zq);
+            }
+            const unsigned b = __ballot_sync(0xffffffffu, before);
+            const int k = __popc(b);   // lanes 0..k-1 are before (monotone)
+            if (k == 0) { hi = lo; break; }
+            const long long last_before = lo + (long long)(k - 1) * step;
+            const long long nlo = last_before + 1;
+            const long long nhi = (k < 32 && lo + (long long)k * step < hi) ? lo + (long long)k * step : hi;
+            lo = nlo; hi = nhi;
+        }
+        bound[upper] = lo;
+    }
+    if (lane == 0) *out = (unsigned long long)(bound[1] - bound[0]);
 }
 
 struct SideStream {
@@ -96,6 +154,73 @@ static int side_for_current_device(SideStream** out)
 
 #define RUN(call) do { if (int rc__ = (call)) return rc__; } while (0)
 
+struct SlabGeom {
+    int hl, n, hh;        // halo planes below / own planes / halo planes above in the voxel buffers
+    int z_begin, z_end;   // owned planes of the local padded sign volume (-1 = to the end)
+    int z_offset;         // global un-padded plane index of local surface plane 0
+    int want_ghost, want_lead;
+    float z_ghost, z_lead;
+};
+
+// Everything after the voxel grid exists: smoothing, surface, canonical mesh, measures.  `grid` = bit volume of
+// Zx = hl + n + hh planes after close_ends (bitsB of the layout), counts already in R[R_COUNTS .. +Zx).
+static int reconstruct_core(const uint32_t* grid, const SlabGeom& g, int H, int W, int n_stages, unsigned erode_mask, int pad,
+                            const double* weights3_host, const void* cum_f64, const void* adj_f64, int n_cum, double mm_y,
+                            double mm_x, int scale_in_f64, uint32_t cap_active, uint32_t cap_verts, uint32_t cap_faces,
+                            void* verts_out_f32, void* faces_out_i64, unsigned long long* R, char* ws, const Layout& L,
+                            SideStream* side, cudaStream_t st)
+{
+    const int Zx = g.hl + g.n + g.hh;
+    const int64_t nw = t3d_words_per_row(W), plane_words = (int64_t)H * nw;
+    const int sl = imin(SURF_HALO, g.hl), sh = imin(SURF_HALO, g.hh), Zl = sl + g.n + sh;
+    const int Zp = Zl + 2 * pad, Hp = H + 2 * pad, Wp = W + 2 * pad;
+    const int64_t n_chunks = t3d_mc_num_chunks(Zp, Hp, Wp);
+    uint32_t* bitsC = (uint32_t*)(ws + L.bitsC);
+
+    // bounding box of the owned planes of the raw grid: side stream, joined before the measures
+    T3D_CUDA(cudaEventRecord(side->e[2], st));
+    T3D_CUDA(cudaStreamWaitEvent(side->s, side->e[2], 0));
+    RUN(t3d_volume_stats(grid + (int64_t)g.hl * plane_words, g.n, H, W, nullptr, R + R_BBOX_I32X6, side->s));
+    T3D_CUDA(cudaEventRecord(side->e[3], side->s));
+
+    // ---- smooth_voxel_data
+    const uint32_t* smoothed = grid;
+    if (n_stages > 0) {
+        RUN(t3d_morph(grid, bitsC, Zx, H, W, n_stages, erode_mask, R + R_COUNTS + Zx, ws + L.morph, st));
+        smoothed = bitsC;
+    } else {
+        T3D_CUDA(cudaMemcpyAsync(R + R_COUNTS + Zx, R + R_COUNTS, sizeof(unsigned long long) * Zx, cudaMemcpyDeviceToDevice, st));
+    }
+    const uint32_t* surf = smoothed + (int64_t)(g.hl - sl) * plane_words;
+
+    // ---- extract_manifold_surface: field sign, two-pass marching cubes, vertices
+    RUN(t3d_field_sign_lean(surf, Zl, H, W, pad, weights3_host, ws + L.sign, R + R_NEXACT, ws + L.exc, EXC_CAP, R + R_NEXC, st));
+    RUN(t3d_mc_flags(ws + L.sign, Zp, Hp, Wp, g.z_begin, g.z_end, ws + L.ballots, st));
+    RUN(t3d_exclusive_scan_u32(ws + L.ballots, ws + L.chunkbase, n_chunks, 1, 0, 1, R + R_NACTIVE, ws + L.scan1, st));
+    RUN(t3d_mc_words_dev(ws + L.sign, Zp, Hp, Wp, g.z_begin, g.z_end, ws + L.ballots, ws + L.chunkbase, cap_active, R + R_NACTIVE,
+                         ws + L.aw_idx, ws + L.aw_cnt, R + R_NAMBIGUOUS, st));
+    RUN(t3d_exclusive_scan_u32_dev(ws + L.aw_cnt, ws + L.aw_base, cap_active, cap_active, 4, 0, 0, R + R_NACTIVE, R + R_NX,
+                                   ws + L.scan2, st));
+    k_finalize_sizes<<<1, 1, 0, st>>>(R, cap_active, cap_verts, cap_faces);
+    RUN(t3d_mc_emit_dev(ws + L.sign, Zp, Hp, Wp, g.z_begin, g.z_end, ws + L.ballots, ws + L.chunkbase, ws + L.aw_idx, ws + L.aw_base,
+                        cap_active, R + R_NACTIVE, cap_verts, cap_faces, ws + L.vkeys, ws + L.faces_raw, st));
+    RUN(t3d_mc_vertices_dev(surf, Zl, H, W, pad, 1, weights3_host, ws + L.vkeys, R + R_NACTIVE, cap_verts, 1, g.z_offset, cum_f64,
+                            adj_f64, n_cum, mm_y, mm_x, scale_in_f64, ws + L.verts_raw, st));
+    // ---- mesh volume / area on the emitted mesh (side stream, concurrent with the canonical sort), canonical mesh
+    T3D_CUDA(cudaStreamWaitEvent(st, side->e[3], 0));   // the bbox reduction is done with the side stream
+    T3D_CUDA(cudaEventRecord(side->e[4], st));
+    T3D_CUDA(cudaStreamWaitEvent(side->s, side->e[4], 0));
+    RUN(t3d_mesh_measure_dev(ws + L.verts_raw, ws + L.faces_raw, cap_faces, R + R_NT, 0, R + R_VOLUME_F64, ws + L.measure, side->s));
+    T3D_CUDA(cudaEventRecord(side->e[5], side->s));
+    RUN(t3d_mesh_canonicalize_fast_dev(ws + L.verts_raw, cap_verts, R + R_VRAW, ws + L.faces_raw, cap_faces, R + R_NT, verts_out_f32,
+                                       faces_out_i64, nullptr, R + R_VCANON, ws + L.canon, st));
+    if (g.want_ghost || g.want_lead)
+        k_count_plane_vertices<<<1, 64, 0, st>>>((const float*)verts_out_f32, R + R_VCANON, g.z_ghost, g.z_lead, g.want_ghost,
+                                                 g.want_lead, R + R_NGHOST, R + R_NLEAD);
+    T3D_CUDA(cudaStreamWaitEvent(st, side->e[5], 0));
+    return 0;
+}
+
 extern "C" int t3d_reconstruct(const void* masks_u8, int Z, int H, int W, int threshold, int close_ends, int n_stages,
                                unsigned erode_mask, int add_padding, const double* weights3_host, const void* cum_f64,
                                const void* adj_f64, int n_cum, double mm_per_pixel_y, double mm_per_pixel_x, int scale_in_f64,
@@ -106,15 +231,12 @@ extern "C" int t3d_reconstruct(const void* masks_u8, int Z, int H, int W, int th
     if (cap_active == 0 || cap_verts == 0 || cap_faces == 0) { t3d_set_error("t3d_reconstruct: zero capacity"); return 2; }
     cudaStream_t st = (cudaStream_t)stream;
     const int pad = add_padding ? 1 : 0;
-    const Layout L = make_layout(Z, H, W, pad, cap_active, cap_verts, cap_faces, n_stages);
+    const Layout L = make_layout(Z, Z, H, W, pad, cap_active, cap_verts, cap_faces, n_stages, true);
     char* ws = (char*)workspace;
     unsigned long long* R = (unsigned long long*)results_u64;
     const int64_t nw = t3d_words_per_row(W), plane_words = (int64_t)H * nw, plane_bytes = (int64_t)H * W;
-    const int Zp = Z + 2 * pad, Hp = H + 2 * pad, Wp = W + 2 * pad;
-    const int64_t n_chunks = t3d_mc_num_chunks(Zp, Hp, Wp);
     uint32_t* bitsA = (uint32_t*)(ws + L.bitsA);
     uint32_t* bitsB = (uint32_t*)(ws + L.bitsB);
-    uint32_t* bitsC = (uint32_t*)(ws + L.bitsC);
     const uint8_t* m = (const uint8_t*)masks_u8;
     SideStream* side;
     RUN(side_for_current_device(&side));
@@ -140,44 +262,66 @@ extern "C" int t3d_reconstruct(const void* masks_u8, int Z, int H, int W, int th
         RUN(t3d_pack_masks(m, Z, H, W, threshold, bitsB, st));
         RUN(t3d_volume_stats(bitsB, Z, H, W, R + R_COUNTS, nullptr, st));
     }
-    // bounding box of the raw grid: side stream, joined at the end
-    T3D_CUDA(cudaEventRecord(side->e[2], st));
-    T3D_CUDA(cudaStreamWaitEvent(side->s, side->e[2], 0));
-    RUN(t3d_volume_stats(bitsB, Z, H, W, nullptr, R + R_BBOX_I32X6, side->s));
-    T3D_CUDA(cudaEventRecord(side->e[3], side->s));
-
-    // ---- smooth_voxel_data
-    const uint32_t* smoothed = bitsB;
-    if (n_stages > 0) {
-        RUN(t3d_morph(bitsB, bitsC, Z, H, W, n_stages, erode_mask, R + R_COUNTS + Z, ws + L.morph, st));
-        smoothed = bitsC;
-    } else {
-        T3D_CUDA(cudaMemcpyAsync(R + R_COUNTS + Z, R + R_COUNTS, sizeof(unsigned long long) * Z, cudaMemcpyDeviceToDevice, st));
-    }
-
-    // ---- extract_manifold_surface: field sign, two-pass marching cubes, vertices
-    RUN(t3d_field_sign_lean(smoothed, Z, H, W, pad, weights3_host, ws + L.sign, R + R_NEXACT, ws + L.exc, EXC_CAP, R + R_NEXC, st));
-    RUN(t3d_mc_flags(ws + L.sign, Zp, Hp, Wp, 0, -1, ws + L.ballots, st));
-    RUN(t3d_exclusive_scan_u32(ws + L.ballots, ws + L.chunkbase, n_chunks, 1, 0, 1, R + R_NACTIVE, ws + L.scan1, st));
-    RUN(t3d_mc_words_dev(ws + L.sign, Zp, Hp, Wp, 0, -1, ws + L.ballots, ws + L.chunkbase, cap_active, R + R_NACTIVE, ws + L.aw_idx,
-                         ws + L.aw_cnt, R + R_NAMBIGUOUS, st));
-    RUN(t3d_exclusive_scan_u32_dev(ws + L.aw_cnt, ws + L.aw_base, cap_active, cap_active, 4, 0, 0, R + R_NACTIVE, R + R_NX,
-                                   ws + L.scan2, st));
-    k_finalize_sizes<<<1, 1, 0, st>>>(R, cap_active, cap_verts, cap_faces);
-    RUN(t3d_mc_emit_dev(ws + L.sign, Zp, Hp, Wp, 0, -1, ws + L.ballots, ws + L.chunkbase, ws + L.aw_idx, ws + L.aw_base, cap_active,
-                        R + R_NACTIVE, cap_verts, cap_faces, ws + L.vkeys, ws + L.faces_raw, st));
-    RUN(t3d_mc_vertices_dev(smoothed, Z, H, W, pad, 1, weights3_host, ws + L.vkeys, R + R_NACTIVE, cap_verts, 1, 0, cum_f64, adj_f64,
-                            n_cum, mm_per_pixel_y, mm_per_pixel_x, scale_in_f64, ws + L.verts_raw, st));
-    // ---- mesh volume / area on the emitted mesh (side stream, concurrent with the canonical sort), canonical mesh
-    T3D_CUDA(cudaStreamWaitEvent(st, side->e[3], 0));   // the bbox reduction is done with the side stream
-    T3D_CUDA(cudaEventRecord(side->e[4], st));
-    T3D_CUDA(cudaStreamWaitEvent(side->s, side->e[4], 0));
-    RUN(t3d_mesh_measure_dev(ws + L.verts_raw, ws + L.faces_raw, cap_faces, R + R_NT, 0, R + R_VOLUME_F64, ws + L.measure, side->s));
-    T3D_CUDA(cudaEventRecord(side->e[5], side->s));
-    RUN(t3d_mesh_canonicalize_fast_dev(ws + L.verts_raw, cap_verts, R + R_VRAW, ws + L.faces_raw, cap_faces, R + R_NT, verts_out_f32,
-                                       faces_out_i64, nullptr, R + R_VCANON, ws + L.canon, st));
-    T3D_CUDA(cudaStreamWaitEvent(st, side->e[5], 0));
+    SlabGeom g = {0, Z, 0, 0, -1, 0, 0, 0, 0.f, 0.f};
+    RUN(reconstruct_core(bitsB, g, H, W, n_stages, erode_mask, pad, weights3_host, cum_f64, adj_f64, n_cum, mm_per_pixel_y,
+                         mm_per_pixel_x, scale_in_f64, cap_active, cap_verts, cap_faces, verts_out_f32, faces_out_i64, R, ws, L, side,
+                         st));
     T3D_CHECK_LAUNCH("t3d_reconstruct");
+    t3d_count_launches(1);
+    return 0;
+}
+
+// ---- z-slab variant (sharded.py): the caller has packed its own slices into planes [halo_lo, halo_lo + n_own) of
+// `ext_bits`, filled the holes of the global end slices and received the halo planes from its z-neighbours.
+extern "C" int t3d_reconstruct_slab(const void* ext_bits, int halo_lo, int n_own, int halo_hi, int H, int W, int n_stages,
+                                    unsigned erode_mask, int add_padding, int z_begin, int z_end, int z_offset, int want_ghost,
+                                    float z_ghost, int want_lead, float z_lead, const double* weights3_host, const void* cum_f64,
+                                    const void* adj_f64, int n_cum, double mm_per_pixel_y, double mm_per_pixel_x, int scale_in_f64,
+                                    uint32_t cap_active, uint32_t cap_verts, uint32_t cap_faces, void* verts_out_f32,
+                                    void* faces_out_i64, void* results_u64, void* workspace, void* stream)
+{
+    if (n_own <= 0 || H <= 0 || W <= 0 || halo_lo < 0 || halo_hi < 0) { t3d_set_error("t3d_reconstruct_slab: bad slab"); return 2; }
+    if (cap_active == 0 || cap_verts == 0 || cap_faces == 0) { t3d_set_error("t3d_reconstruct_slab: zero capacity"); return 2; }
+    cudaStream_t st = (cudaStream_t)stream;
+    const int pad = add_padding ? 1 : 0, Zx = halo_lo + n_own + halo_hi;
+    const int Zl = imin(SURF_HALO, halo_lo) + n_own + imin(SURF_HALO, halo_hi);
+    const Layout L = make_layout(Zx, Zl, H, W, pad, cap_active, cap_verts, cap_faces, n_stages, false);
+    char* ws = (char*)workspace;
+    unsigned long long* R = (unsigned long long*)results_u64;
+    SideStream* side;
+    RUN(side_for_current_device(&side));
+    T3D_CUDA(cudaMemsetAsync(R, 0, sizeof(unsigned long long) * R_COUNTS, st));
+    RUN(t3d_gap_fill(ext_bits, ws + L.bitsB, nullptr, nullptr, Zx, H, W, R + R_COUNTS, st));
+    SlabGeom g = {halo_lo, n_own, halo_hi, z_begin, z_end, z_offset, want_ghost, want_lead, z_ghost, z_lead};
+    RUN(reconstruct_core((const uint32_t*)(ws + L.bitsB), g, H, W, n_stages, erode_mask, pad, weights3_host, cum_f64, adj_f64, n_cum,
+                         mm_per_pixel_y, mm_per_pixel_x, scale_in_f64, cap_active, cap_verts, cap_faces, verts_out_f32, faces_out_i64,
+                         R, ws, L, side, st));
+    T3D_CHECK_LAUNCH("t3d_reconstruct_slab");
+    t3d_count_launches(1);
+    return 0;
+}
+
+// Stitching: global face ids = local ids + the number of owned unique vertices of the lower ranks.  `gathered` = the
+// all-gathered result blocks (world x stride uint64); only slots R_VCANON / R_NGHOST / R_FCANON are read.
+__global__ void k_add_vertex_base(long long* __restrict__ faces, const unsigned long long* __restrict__ gathered, int64_t stride, int rank,
+                                  int64_t cap3)
+{
+    long long base = 0;
+    for (int r = 0; r < rank; ++r) base += (long long)(gathered[r * stride + R_VCANON] - gathered[r * stride + R_NGHOST]);
+    const int64_t n3 = 3 * (int64_t)gathered[rank * stride + R_FCANON];
+    const int64_t n = n3 < cap3 ? n3 : cap3;
+    if (base == 0) return;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) faces[i] += base;
+}
+
+extern "C" int t3d_slab_stitch_faces(void* faces_i64, int64_t cap_faces, const void* gathered_results_u64, int64_t stride_u64,
+                                     int rank, void* stream)
+{
+    if (rank < 0 || cap_faces < 0) { t3d_set_error("t3d_slab_stitch_faces: bad arguments"); return 2; }
+    if (rank == 0 || cap_faces == 0) return 0;
+    k_add_vertex_base<<<148 * 8, 256, 0, (cudaStream_t)stream>>>((long long*)faces_i64, (const unsigned long long*)gathered_results_u64,
+                                                               stride_u64, rank, 3 * cap_faces);
+    T3D_CHECK_LAUNCH("t3d_slab_stitch_faces");
     t3d_count_launches(1);
     return 0;
 }

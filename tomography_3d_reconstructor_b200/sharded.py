@@ -160,16 +160,17 @@ def slab_local(s: Slab, side_counts, total_depth_mm: float, x_length_mm: float, 
         vz = mesh._verts[:, 0]
         valid = torch.arange(vz.shape[0], device=dev) < counts_mesh[0]
         if s.z1 < s.Zg:
-            n_ghost = ((vz == float(z_map_value(b - 1, cum, adj))) & valid).sum()
+            n_ghost = ((vz == float(z_map_value(b - pad, cum, adj))) & valid).sum()
         if s.z0 > 0:
-            n_lead = ((vz == float(z_map_value(a - 1, cum, adj))) & valid).sum()
+            n_lead = ((vz == float(z_map_value(a - pad, cum, adj))) & valid).sum()
     s.local = torch.cat([counts_mesh, n_ghost.reshape(1), n_lead.reshape(1), meas.view(torch.int64), bbox_t.to(torch.int64)])
     return s.local
 
 
 def finalize(s: Slab, rank: int, host: torch.Tensor, raw_counts: np.ndarray, sm_counts: np.ndarray, slab_starts: List[int],
-             side_counts, total_depth_mm: float, x_length_mm: float, y_length_mm: float) -> Dict:
-    """Phase 5: host[r] = the vector of slab_local() of every rank; counts = global per-slice voxel counts."""
+             side_counts, total_depth_mm: float, x_length_mm: float, y_length_mm: float, stitched=None) -> Dict:
+    """Phase 5: host[r] = the vector of slab_local() of every rank; counts = global per-slice voxel counts.
+    stitched = (capacity-sized canonical verts, faces already carrying global ids) from the fused path."""
     mm_x, mm_y = x_length_mm / s.W, y_length_mm / s.H
     depths = pipeline.slice_depths(total_depth_mm, *side_counts)
     per_rank = [(int(host[r, 0]), int(host[r, 3]), int(host[r, 4])) for r in range(host.shape[0])]
@@ -187,7 +188,9 @@ def finalize(s: Slab, rank: int, host: torch.Tensor, raw_counts: np.ndarray, sm_
         bbox = (int(q[:, 0].min()), int(q[:, 1].max()), int(q[:, 2].min()), int(q[:, 3].max()), int(q[:, 4].min()),
                 int(q[:, 5].max()))
     v_own = per_rank[rank][0] - per_rank[rank][1]
-    if s.mesh is not None:
+    if stitched is not None:
+        verts_own, faces_global = stitched[0][:v_own], stitched[1][:int(host[rank, 1])]
+    elif s.mesh is not None:
         s.mesh.set_sizes(per_rank[rank][0], int(host[rank, 1]), 0)
         verts_own = s.mesh._verts[:v_own]
         faces_global = s.mesh._faces + bases[rank]
@@ -202,7 +205,7 @@ def finalize(s: Slab, rank: int, host: torch.Tensor, raw_counts: np.ndarray, sm_
         "processed_voxel_volume_mm3": pipeline.variable_depth_volume(sm_counts, mm_x, mm_y, depths),
         "mesh_volume_mm3": abs(signed_volume), "surface_area_mm2": area, "bbox_index": bbox,
         "active_voxels": int(raw_counts.sum()), "slice_depths": depths,
-        "mesh": _MeshView(verts_own, faces_global, total_v, total_f),
+        "mesh": _MeshView(verts_own, faces_global, total_v, total_f), "local_mesh": s.mesh,
     }
 
 
@@ -241,6 +244,169 @@ def reconstruct(masks_u8: torch.Tensor, Zg: int, z0: int, threshold: int, side_c
     mark("stats")
     return finalize(s, rank, host, raw_counts, sm_counts, [b for b, _ in sizes], side_counts, total_depth_mm,
                     x_length_mm, y_length_mm)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# fused sharded step: pack -> halo exchange -> ONE t3d_reconstruct_slab enqueue -> all-gather of the result blocks ->
+# face stitching -> one device->host copy.  No host synchronisation before the end of the step.
+# ----------------------------------------------------------------------------------------------------------------
+class FusedSlabPlan:
+    """Per-rank buffers for one (slab shape, parameters); capacities from a previous staged step of the same input.
+    The returned mesh slab lives in the plan's buffers: valid until the next run()."""
+
+    def __init__(self, n, H, W, Zg, z0, threshold, side_counts, total_depth_mm, x_length_mm, y_length_mm, iterations,
+                 add_padding, caps, device, rank, world, group=None):
+        L = engine._L()
+        self.n, self.H, self.W, self.Zg, self.z0, self.z1 = int(n), int(H), int(W), int(Zg), int(z0), int(z0) + int(n)
+        self.rank, self.world, self.group, self.dev = rank, world, group, device
+        if world > 1 and self.n < HALO:
+            raise ValueError("z-slabs must be at least %d slices thick" % HALO)
+        self.threshold, self.add_padding = int(threshold), bool(add_padding)
+        self.side_counts, self.phys = tuple(side_counts), (float(total_depth_mm), float(x_length_mm), float(y_length_mm))
+        self.mm_x, self.mm_y = x_length_mm / W, y_length_mm / H
+        self.depths = pipeline.slice_depths(total_depth_mm, *side_counts)
+        stages = engine.morph_stages(iterations, True)
+        self.n_stages = len(stages)
+        self.erode_mask = sum(1 << k for k, er in enumerate(stages) if er)
+        self.caps = tuple(int(c) for c in caps)
+        self.hl, self.hh = (HALO if self.z0 > 0 else 0), (HALO if self.z1 < Zg else 0)
+        pad = 1 if add_padding else 0
+        sl = min(SURF_HALO, self.hl)
+        self.z_offset = self.z0 - sl
+        a, b = owned_padded_planes(Zg, self.z0, self.z1, pad)
+        self.z_begin, self.z_end = a - self.z_offset, b - self.z_offset
+        cum, adj = engine.z_map_arrays(self.depths, add_padding)
+        self.n_cum = len(cum)
+        self.cum_d = torch.from_numpy(cum).to(device) if self.n_cum else None
+        self.adj_d = torch.from_numpy(adj).to(device) if self.n_cum else None
+        # the vertex transform subtracts `pad` from the padded plane index before the z map (surface_extractor.py:57-60)
+        self.want_ghost, self.want_lead = int(self.z1 < Zg), int(self.z0 > 0)
+        self.z_ghost = float(z_map_value(b - pad, cum, adj)) if self.want_ghost else 0.0
+        self.z_lead = float(z_map_value(a - pad, cum, adj)) if self.want_lead else 0.0
+        wpr = engine.words_per_row(W)
+        Zx = self.hl + self.n + self.hh
+        self.ext = torch.zeros((Zx, H, wpr), dtype=torch.int32, device=device)
+        self.fill = torch.empty(int(L.t3d_fill_holes_scratch_bytes(1, H, W)) // 4 + 1, dtype=torch.int32, device=device)
+        nbytes = int(L.t3d_reconstruct_slab_workspace_bytes(self.hl, self.n, self.hh, H, W, pad, self.n_stages, *self.caps))
+        self.ws = torch.empty(nbytes // 8 + 1, dtype=torch.int64, device=device)
+        self.verts = torch.empty((self.caps[1], 3), dtype=torch.float32, device=device)
+        self.faces = torch.empty((self.caps[2], 3), dtype=torch.int64, device=device)
+        self.sizes = [slab_range(Zg, r, world) for r in range(world)]
+        nmax = max(e - b_ for b_, e in self.sizes)
+        self.stride = pipeline.R_COUNTS + 2 * (nmax + 2 * HALO)
+        self.res = torch.zeros(self.stride, dtype=torch.int64, device=device)
+        self.gathered = torch.zeros((world, self.stride), dtype=torch.int64, device=device)
+        self.host = torch.zeros((world, self.stride), dtype=torch.int64, pin_memory=True)
+
+    def pack(self, masks_u8: torch.Tensor) -> None:
+        """Own slices -> planes [hl, hl+n) of the extended buffer; holes of the global end slices filled."""
+        L = engine._L()
+        p, st = engine._p, engine._stream
+        hl, n, H, W = self.hl, self.n, self.H, self.W
+        engine.check(L.t3d_pack_masks(p(masks_u8), n, H, W, self.threshold, p(self.ext[hl]), st()), "t3d_pack_masks")
+        ends = ([hl] if self.z0 == 0 else []) + ([hl + n - 1] if self.z1 == self.Zg and not (self.z0 == 0 and n == 1) else [])
+        for e in ends:
+            engine.check(L.t3d_fill_holes_2d(p(self.ext[e]), 1, 0, H, W, p(self.fill), st()), "t3d_fill_holes_2d")
+
+    def compute(self) -> None:
+        """Everything between the halo exchange and the result gather: one t3d_reconstruct_slab enqueue."""
+        p = engine._p
+        engine.check(engine._L().t3d_reconstruct_slab(
+            p(self.ext), self.hl, self.n, self.hh, self.H, self.W, self.n_stages, self.erode_mask, 1 if self.add_padding else 0,
+            self.z_begin, self.z_end, self.z_offset, self.want_ghost, self.z_ghost, self.want_lead, self.z_lead, engine._W3_C,
+            p(self.cum_d), p(self.adj_d), self.n_cum, float(self.mm_y), float(self.mm_x), 0, self.caps[0], self.caps[1],
+            self.caps[2], p(self.verts), p(self.faces), p(self.res), p(self.ws), engine._stream()), "t3d_reconstruct_slab")
+
+    def stitch(self) -> None:
+        """Local face ids -> ids in the stitched mesh, from the gathered result blocks (device side)."""
+        engine.check(engine._L().t3d_slab_stitch_faces(engine._p(self.faces), self.caps[2], engine._p(self.gathered), self.stride,
+                                                      self.rank, engine._stream()), "t3d_slab_stitch_faces")
+
+    def enqueue(self, masks_u8: torch.Tensor) -> None:
+        self.pack(masks_u8)
+        if self.world > 1:
+            exchange_halos(self.ext, self.hl, self.n, self.hh, self.rank, self.world, self.group)
+        self.compute()
+        if self.world > 1:
+            dist.all_gather_into_tensor(self.gathered, self.res, group=self.group)
+            self.stitch()
+        else:
+            self.gathered[0].copy_(self.res)
+
+    def run(self, masks_u8: torch.Tensor) -> np.ndarray:
+        self.enqueue(masks_u8)
+        self.host.copy_(self.gathered, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return self.host.numpy()
+
+
+_slab_plans: Dict = {}
+_slab_hints: Dict = {}
+
+
+def reconstruct_fused(masks_u8: torch.Tensor, Zg: int, z0: int, threshold: int, side_counts, total_depth_mm: float,
+                      x_length_mm: float, y_length_mm: float, iterations: int = 3, add_padding: bool = True, group=None) -> Dict:
+    """Same contract and results as reconstruct(); the step is enqueued without any host synchronisation.
+
+    The first call for a given (slab, parameters) runs the staged path to learn the mesh sizes; if any rank reports a
+    capacity overflow, an unverifiable fast ordering or an empty slab, every rank re-runs the staged path."""
+    R = pipeline
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    n, H, W = (int(v) for v in masks_u8.shape)
+    key = (n, H, W, int(Zg), int(z0), int(threshold), tuple(side_counts), float(total_depth_mm), float(x_length_mm),
+           float(y_length_mm), int(iterations), bool(add_padding), masks_u8.device.index, world)
+
+    def staged():
+        out = reconstruct(masks_u8, Zg, z0, threshold, side_counts, total_depth_mm, x_length_mm, y_length_mm, iterations,
+                          add_padding, group=group)
+        m = out.get("local_mesh")
+        _slab_hints[key] = pipeline._caps_from(m.n_active, *m.n_raw) if m is not None else (4096, 4096, 4096)
+        return out
+
+    if key not in _slab_hints:
+        return staged()
+    plan = _slab_plans.get(key)
+    if plan is None or any(c < h for c, h in zip(plan.caps, _slab_hints[key])):
+        plan = FusedSlabPlan(n, H, W, Zg, z0, threshold, side_counts, total_depth_mm, x_length_mm, y_length_mm, iterations,
+                             add_padding, _slab_hints[key], masks_u8.device, rank, world, group)
+        _slab_plans[key] = plan
+    h = plan.run(masks_u8)
+    if (h[:, R.R_OVERFLOW] != 0).any() or (h[:, R.R_UNVERIFIED] != 0).any() or (h[:, R.R_NT] == 0).any():
+        _slab_plans.pop(key, None)
+        _slab_hints.pop(key, None)
+        return staged()
+    me = h[rank]
+    _slab_hints[key] = tuple(max(a, b) for a, b in zip(_slab_hints[key], pipeline._caps_from(int(me[R.R_NACTIVE]), int(me[R.R_VRAW]),
+                                                                                             int(me[R.R_NT]))))
+    return assemble(plan, h)
+
+
+R_NGHOST, R_NLEAD = 18, 19
+
+
+def assemble(plan: FusedSlabPlan, h: np.ndarray) -> Dict:
+    """Result dict of reconstruct() from the gathered result blocks h (world x stride int64, host)."""
+    R = pipeline
+    Zg, world = plan.Zg, plan.world
+    # the small table finalize() works on: [V', F', unverified, ghost, lead, volume bits, area bits, bbox x 6]
+    table = np.zeros((world, 13), dtype=np.int64)
+    raw_parts, sm_parts = [], []
+    for r, (b, e) in enumerate(plan.sizes):
+        hl_r, hh_r = (HALO if b > 0 else 0), (HALO if e < Zg else 0)
+        Zx_r = hl_r + (e - b) + hh_r
+        row = h[r]
+        table[r, :5] = (row[R.R_VCANON], row[R.R_FCANON], row[R.R_UNVERIFIED], row[R_NGHOST], row[R_NLEAD])
+        table[r, 5:7] = row[R.R_VOLUME:R.R_VOLUME + 2]
+        table[r, 7:13] = row[R.R_BBOX:R.R_BBOX + 3].view(np.int32)
+        raw_parts.append(row[R.R_COUNTS + hl_r:R.R_COUNTS + hl_r + (e - b)])
+        sm_parts.append(row[R.R_COUNTS + Zx_r + hl_r:R.R_COUNTS + Zx_r + hl_r + (e - b)])
+    s = Slab()
+    s.H, s.W, s.dev, s.mesh = plan.H, plan.W, plan.dev, None
+    out = finalize(s, plan.rank, torch.from_numpy(table), np.concatenate(raw_parts).astype(np.int64),
+                   np.concatenate(sm_parts).astype(np.int64), [b for b, _ in plan.sizes], plan.side_counts, *plan.phys,
+                   stitched=(plan.verts, plan.faces))
+    out["n_ambiguous"] = out["mesh"].n_ambiguous = int(h[:, R.R_NAMBIGUOUS].sum())
+    return out
 
 
 class _MeshView:
