@@ -189,6 +189,7 @@ def run_ours(args, Z, H, W):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ["NCCL_DEBUG"] = os.environ.get("T3D_NCCL_DEBUG", "WARN")  # keep stdout to the one JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/t3d_nccl.%h.%p.log")
         dist.init_process_group("nccl", device_id=dev)
     from tomography_3d_reconstructor_b200 import _lib, engine, pipeline
     lib = _lib.load()
@@ -209,7 +210,7 @@ def run_ours(args, Z, H, W):
                                            PHYS["y_length_mm"], mark=mark)
             # fused: pack -> NCCL halo exchange -> one t3d_reconstruct_slab enqueue -> all-gather -> stitch, one sync
             return sharded.reconstruct_fused(masks, Zg, z0, THRESHOLD, sides, PHYS["total_depth_mm"], PHYS["x_length_mm"],
-                                             PHYS["y_length_mm"])
+                                             PHYS["y_length_mm"], use_graph=not args.no_graph)
         if mark is not None or args.staged:   # staged path: one library call per stage (per-stage event timing)
             return pipeline.reconstruct(masks, THRESHOLD, sides, PHYS["total_depth_mm"], PHYS["x_length_mm"],
                                         PHYS["y_length_mm"], mark=mark)
@@ -230,6 +231,9 @@ def run_ours(args, Z, H, W):
     if world == 1 and not args.staged:
         pipeline.reconstruct_fused(masks, THRESHOLD, sides, PHYS["total_depth_mm"], PHYS["x_length_mm"], PHYS["y_length_mm"],
                                    use_graph=False)
+    elif world > 1 and not args.staged:
+        sharded.reconstruct_fused(masks, Zg, z0, THRESHOLD, sides, PHYS["total_depth_mm"], PHYS["x_length_mm"], PHYS["y_length_mm"],
+                                  use_graph=False)
     else:
         step()
     launches_per_step = lib.t3d_launch_count() - lc0
@@ -312,9 +316,18 @@ def run_ours(args, Z, H, W):
                "steps": n_e2e, "api": "VoxelProcessor.create_voxel_data -> smooth_voxel_data -> "
                "SurfaceExtractor.extract_manifold_surface -> calculate_mesh_volume/area -> VolumeCalculator.analyze_object_properties"}
 
-    if rank != 0:
+    def teardown():
         if world > 1:
+            # captured graphs hold NCCL work: release them before the communicator goes away
+            sharded._slab_plans.clear()
+            import gc
+            gc.collect()
+            torch.cuda.synchronize()
+            dist.barrier()
             dist.destroy_process_group()
+
+    if rank != 0:
+        teardown()
         return
 
     peaks = {}
@@ -346,7 +359,8 @@ def run_ours(args, Z, H, W):
                    "mesh": {"vertices": V, "faces": F, "n_ambiguous_cubes": int(mesh.n_ambiguous)},
                    "execution": ("z-slab sharded, staged launches" if world > 1 and args.staged else
                                  "z-slab sharded: pack, NCCL halo exchange, one t3d_reconstruct_slab enqueue, result all-gather, "
-                                 "face stitching; one host sync per step" if world > 1 else "staged launches" if args.staged else
+                                 "face stitching; one host sync per step" + ("" if args.no_graph else ", replayed from a CUDA graph (NCCL included)")
+                                 if world > 1 else "staged launches" if args.staged else
                                  "one t3d_reconstruct enqueue per step" + ("" if args.no_graph else ", replayed from a CUDA graph"))},
         "clocks": clocks.summary(),
         "gpu_launches": int(launches),
@@ -369,8 +383,7 @@ def run_ours(args, Z, H, W):
                                 "sample": "central z-slab of %d slices x %dx%d of the same phantom, oracle/cpu_ref.py "
                                 "(scipy.ndimage is single-threaded), %.1f s" % (n_sl, H, W, secs)}
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    teardown()
 
 
 def main():

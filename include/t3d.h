@@ -193,12 +193,17 @@ int t3d_reconstruct(const void* masks_u8, int Z, int H, int W, int threshold, in
  * z_offset (global plane index of local surface plane 0, as t3d_mc_vertices).  The result block is t3d_reconstruct's with
  * Zx = halo_lo + n_own + halo_hi per-plane counts twice from slot 32 (bbox is over the own planes, local z), plus
  *   [18] ghost tail: canonical vertices with z == z_ghost (the next rank's first plane), if want_ghost
- *   [19] lead: canonical vertices with z == z_lead (this rank's first plane), if want_lead. */
+ *   [19] lead: canonical vertices with z == z_lead (this rank's first plane), if want_lead.
+ * t3d_slab_pack packs the own slices (uint8, n_own x H x W) into ext_bits and fills the holes of the global end slices
+ * (fill_first / fill_last; fill_scratch = t3d_fill_holes_scratch_bytes(2, H, W)) on an internal side stream, which
+ * t3d_reconstruct_slab joins when join_fill != 0 -- the halo exchange in between does not wait for it. */
+int t3d_slab_pack(const void* masks_u8, int n_own, int H, int W, int threshold, int halo_lo, int halo_hi, int fill_first,
+                  int fill_last, void* ext_bits, void* fill_scratch, void* stream);
 int64_t t3d_reconstruct_slab_workspace_bytes(int halo_lo, int n_own, int halo_hi, int H, int W, int add_padding, int n_stages,
                                              uint32_t cap_active, uint32_t cap_verts, uint32_t cap_faces);
 int t3d_reconstruct_slab(const void* ext_bits, int halo_lo, int n_own, int halo_hi, int H, int W, int n_stages,
                          unsigned erode_mask, int add_padding, int z_begin, int z_end, int z_offset, int want_ghost, float z_ghost,
-                         int want_lead, float z_lead, const double* weights3_host, const void* cum_f64, const void* adj_f64,
+                         int want_lead, float z_lead, int join_fill, const double* weights3_host, const void* cum_f64, const void* adj_f64,
                          int n_cum, double mm_per_pixel_y, double mm_per_pixel_x, int scale_in_f64, uint32_t cap_active,
                          uint32_t cap_verts, uint32_t cap_faces, void* verts_out_f32, void* faces_out_i64, void* results_u64,
                          void* workspace, void* stream);

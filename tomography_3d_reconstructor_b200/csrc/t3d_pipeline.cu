@@ -271,11 +271,45 @@ extern "C" int t3d_reconstruct(const void* masks_u8, int Z, int H, int W, int th
     return 0;
 }
 
+// ---- z-slab packing: own slices -> planes [halo_lo, halo_lo + n_own) of ext_bits.  The global end slices (fill_first /
+// fill_last) are packed first and hole-filled on the side stream while the other slices are packed; t3d_reconstruct_slab
+// joins the side stream (join_fill), so the halo exchange in between does not wait for the fill.  (The filled slice is
+// part of a halo only if the slab is thinner than the halo; then the fill is joined here.)
+extern "C" int t3d_slab_pack(const void* masks_u8, int n_own, int H, int W, int threshold, int halo_lo, int halo_hi, int fill_first,
+                             int fill_last, void* ext_bits, void* fill_scratch, void* stream)
+{
+    if (n_own <= 0 || H <= 0 || W <= 0 || halo_lo < 0) { t3d_set_error("t3d_slab_pack: bad slab"); return 2; }
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t nw = t3d_words_per_row(W), plane_words = (int64_t)H * nw, plane_bytes = (int64_t)H * W;
+    const uint8_t* m = (const uint8_t*)masks_u8;
+    uint32_t* own = (uint32_t*)ext_bits + (int64_t)halo_lo * plane_words;
+    if (fill_last && n_own == 1 && fill_first) fill_last = 0;   // one slice: filled once
+    if (!fill_first && !fill_last) return t3d_pack_masks(m, n_own, H, W, threshold, own, st);
+    SideStream* side;
+    RUN(side_for_current_device(&side));
+    const int lo = fill_first ? 1 : 0, hi = fill_last ? n_own - 1 : n_own;   // [lo, hi) = slices that are not filled
+    if (fill_first) RUN(t3d_pack_masks(m, 1, H, W, threshold, own, st));
+    if (fill_last) RUN(t3d_pack_masks(m + (int64_t)(n_own - 1) * plane_bytes, 1, H, W, threshold, own + (int64_t)(n_own - 1) * plane_words, st));
+    T3D_CUDA(cudaEventRecord(side->e[0], st));
+    T3D_CUDA(cudaStreamWaitEvent(side->s, side->e[0], 0));
+    char* scratch = (char*)fill_scratch;
+    if (fill_first && fill_last) {
+        RUN(t3d_fill_holes_2d(own, 2, (int64_t)(n_own - 1) * plane_words, H, W, scratch, side->s));
+    } else {
+        RUN(t3d_fill_holes_2d(fill_first ? own : own + (int64_t)(n_own - 1) * plane_words, 1, 0, H, W, scratch, side->s));
+    }
+    T3D_CUDA(cudaEventRecord(side->e[1], side->s));
+    if (hi > lo) RUN(t3d_pack_masks(m + (int64_t)lo * plane_bytes, hi - lo, H, W, threshold, own + (int64_t)lo * plane_words, st));
+    const int halo = halo_lo > halo_hi ? halo_lo : halo_hi;
+    if (n_own <= halo) T3D_CUDA(cudaStreamWaitEvent(st, side->e[1], 0));
+    return 0;
+}
+
 // ---- z-slab variant (sharded.py): the caller has packed its own slices into planes [halo_lo, halo_lo + n_own) of
 // `ext_bits`, filled the holes of the global end slices and received the halo planes from its z-neighbours.
 extern "C" int t3d_reconstruct_slab(const void* ext_bits, int halo_lo, int n_own, int halo_hi, int H, int W, int n_stages,
                                     unsigned erode_mask, int add_padding, int z_begin, int z_end, int z_offset, int want_ghost,
-                                    float z_ghost, int want_lead, float z_lead, const double* weights3_host, const void* cum_f64,
+                                    float z_ghost, int want_lead, float z_lead, int join_fill, const double* weights3_host, const void* cum_f64,
                                     const void* adj_f64, int n_cum, double mm_per_pixel_y, double mm_per_pixel_x, int scale_in_f64,
                                     uint32_t cap_active, uint32_t cap_verts, uint32_t cap_faces, void* verts_out_f32,
                                     void* faces_out_i64, void* results_u64, void* workspace, void* stream)
@@ -291,6 +325,7 @@ extern "C" int t3d_reconstruct_slab(const void* ext_bits, int halo_lo, int n_own
     SideStream* side;
     RUN(side_for_current_device(&side));
     T3D_CUDA(cudaMemsetAsync(R, 0, sizeof(unsigned long long) * R_COUNTS, st));
+    if (join_fill) T3D_CUDA(cudaStreamWaitEvent(st, side->e[1], 0));   // hole filling started by t3d_slab_pack
     RUN(t3d_gap_fill(ext_bits, ws + L.bitsB, nullptr, nullptr, Zx, H, W, R + R_COUNTS, st));
     SlabGeom g = {halo_lo, n_own, halo_hi, z_begin, z_end, z_offset, want_ghost, want_lead, z_ghost, z_lead};
     RUN(reconstruct_core((const uint32_t*)(ws + L.bitsB), g, H, W, n_stages, erode_mask, pad, weights3_host, cum_f64, adj_f64, n_cum,

@@ -286,7 +286,7 @@ class FusedSlabPlan:
         wpr = engine.words_per_row(W)
         Zx = self.hl + self.n + self.hh
         self.ext = torch.zeros((Zx, H, wpr), dtype=torch.int32, device=device)
-        self.fill = torch.empty(int(L.t3d_fill_holes_scratch_bytes(1, H, W)) // 4 + 1, dtype=torch.int32, device=device)
+        self.fill = torch.empty(int(L.t3d_fill_holes_scratch_bytes(2, H, W)) // 4 + 1, dtype=torch.int32, device=device)
         nbytes = int(L.t3d_reconstruct_slab_workspace_bytes(self.hl, self.n, self.hh, H, W, pad, self.n_stages, *self.caps))
         self.ws = torch.empty(nbytes // 8 + 1, dtype=torch.int64, device=device)
         self.verts = torch.empty((self.caps[1], 3), dtype=torch.float32, device=device)
@@ -297,23 +297,23 @@ class FusedSlabPlan:
         self.res = torch.zeros(self.stride, dtype=torch.int64, device=device)
         self.gathered = torch.zeros((world, self.stride), dtype=torch.int64, device=device)
         self.host = torch.zeros((world, self.stride), dtype=torch.int64, pin_memory=True)
+        self.graph, self.graph_ptr = None, None
 
     def pack(self, masks_u8: torch.Tensor) -> None:
-        """Own slices -> planes [hl, hl+n) of the extended buffer; holes of the global end slices filled."""
-        L = engine._L()
-        p, st = engine._p, engine._stream
-        hl, n, H, W = self.hl, self.n, self.H, self.W
-        engine.check(L.t3d_pack_masks(p(masks_u8), n, H, W, self.threshold, p(self.ext[hl]), st()), "t3d_pack_masks")
-        ends = ([hl] if self.z0 == 0 else []) + ([hl + n - 1] if self.z1 == self.Zg and not (self.z0 == 0 and n == 1) else [])
-        for e in ends:
-            engine.check(L.t3d_fill_holes_2d(p(self.ext[e]), 1, 0, H, W, p(self.fill), st()), "t3d_fill_holes_2d")
+        """Own slices -> planes [hl, hl+n) of the extended buffer; the holes of the global end slices are filled on the
+        library's side stream (joined by compute())."""
+        p = engine._p
+        engine.check(engine._L().t3d_slab_pack(p(masks_u8), self.n, self.H, self.W, self.threshold, self.hl, self.hh,
+                                               int(self.z0 == 0), int(self.z1 == self.Zg), p(self.ext), p(self.fill),
+                                               engine._stream()), "t3d_slab_pack")
 
     def compute(self) -> None:
         """Everything between the halo exchange and the result gather: one t3d_reconstruct_slab enqueue."""
         p = engine._p
         engine.check(engine._L().t3d_reconstruct_slab(
             p(self.ext), self.hl, self.n, self.hh, self.H, self.W, self.n_stages, self.erode_mask, 1 if self.add_padding else 0,
-            self.z_begin, self.z_end, self.z_offset, self.want_ghost, self.z_ghost, self.want_lead, self.z_lead, engine._W3_C,
+            self.z_begin, self.z_end, self.z_offset, self.want_ghost, self.z_ghost, self.want_lead, self.z_lead,
+            int(self.z0 == 0 or self.z1 == self.Zg), engine._W3_C,
             p(self.cum_d), p(self.adj_d), self.n_cum, float(self.mm_y), float(self.mm_x), 0, self.caps[0], self.caps[1],
             self.caps[2], p(self.verts), p(self.faces), p(self.res), p(self.ws), engine._stream()), "t3d_reconstruct_slab")
 
@@ -333,8 +333,21 @@ class FusedSlabPlan:
         else:
             self.gathered[0].copy_(self.res)
 
-    def run(self, masks_u8: torch.Tensor) -> np.ndarray:
+    def capture(self, masks_u8: torch.Tensor) -> None:
+        """Record the whole step (NCCL halo exchange and result all-gather included) for this input buffer into a CUDA
+        graph; every rank must capture, and replay, in the same step."""
         self.enqueue(masks_u8)
+        torch.cuda.current_stream().synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self.enqueue(masks_u8)
+        self.graph, self.graph_ptr = g, masks_u8.data_ptr()
+
+    def run(self, masks_u8: torch.Tensor, use_graph: bool = False) -> np.ndarray:
+        if use_graph and self.graph is not None and self.graph_ptr == masks_u8.data_ptr():
+            self.graph.replay()
+        else:
+            self.enqueue(masks_u8)
         self.host.copy_(self.gathered, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         return self.host.numpy()
@@ -345,8 +358,10 @@ _slab_hints: Dict = {}
 
 
 def reconstruct_fused(masks_u8: torch.Tensor, Zg: int, z0: int, threshold: int, side_counts, total_depth_mm: float,
-                      x_length_mm: float, y_length_mm: float, iterations: int = 3, add_padding: bool = True, group=None) -> Dict:
-    """Same contract and results as reconstruct(); the step is enqueued without any host synchronisation.
+                      x_length_mm: float, y_length_mm: float, iterations: int = 3, add_padding: bool = True, group=None,
+                      use_graph: bool = False) -> Dict:
+    """Same contract and results as reconstruct(); the step is enqueued without any host synchronisation (use_graph:
+    replayed from a CUDA graph that includes the NCCL operations; all ranks must pass the same value).
 
     The first call for a given (slab, parameters) runs the staged path to learn the mesh sizes; if any rank reports a
     capacity overflow, an unverifiable fast ordering or an empty slab, every rank re-runs the staged path."""
@@ -370,7 +385,9 @@ def reconstruct_fused(masks_u8: torch.Tensor, Zg: int, z0: int, threshold: int, 
         plan = FusedSlabPlan(n, H, W, Zg, z0, threshold, side_counts, total_depth_mm, x_length_mm, y_length_mm, iterations,
                              add_padding, _slab_hints[key], masks_u8.device, rank, world, group)
         _slab_plans[key] = plan
-    h = plan.run(masks_u8)
+    if use_graph and plan.graph_ptr != masks_u8.data_ptr():
+        plan.capture(masks_u8)
+    h = plan.run(masks_u8, use_graph)
     if (h[:, R.R_OVERFLOW] != 0).any() or (h[:, R.R_UNVERIFIED] != 0).any() or (h[:, R.R_NT] == 0).any():
         _slab_plans.pop(key, None)
         _slab_hints.pop(key, None)
