@@ -174,6 +174,8 @@ def make_phantom_u8(Z_total, H, W, z0, z1, device):
     return out
 
 
+NCU_PACK_TRAFFIC_BYTES = 551741440   # 534.78 MB read + 16.96 MB written (profiles/r01_ncu_full_summary.txt)
+
 STAGE_BYTES = {  # algorithmic bytes per voxel of each volume-sized stage
     "pack_close": 1.0 + 0.125 + 0.25, "smooth": 4 * 0.25, "field_sign": 0.25, "mc_flags": 0.125 + 1.0 / 256,
 }
@@ -256,6 +258,24 @@ def run_ours(args, Z, H, W):
     voxels = Zg * H * W
     value = voxels * args.steps / (ms * 1e-3) / 1e9
 
+    # ---- dominant kernel by bytes, timed alone on the launching stream: k_pack_flat (t3d_pack_masks) streams the whole
+    # u8 stack (larger than L2) and writes the bit volume
+    n_own = z1 - z0
+    kbits = torch.empty((n_own, H, engine.words_per_row(W)), dtype=torch.int32, device=dev)
+    kst = engine._stream()
+    for _ in range(3):
+        lib.t3d_pack_masks(engine._p(masks), n_own, H, W, THRESHOLD, engine._p(kbits), kst)
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    K_REP = 20
+    k0.record()
+    for _ in range(K_REP):
+        lib.t3d_pack_masks(engine._p(masks), n_own, H, W, THRESHOLD, engine._p(kbits), kst)
+    k1.record()
+    torch.cuda.synchronize()
+    pack_ms = k0.elapsed_time(k1) / K_REP
+    del kbits
+
     # ---- per-stage device times (one instrumented step, events on the launching stream)
     marks = []
 
@@ -276,7 +296,7 @@ def run_ours(args, Z, H, W):
     stage_ms = {k: float(np.min(v)) for k, v in stage_ms.items()}
 
     # ---- e2e through the reference-facing classes, host buffers in pinned memory
-    e2e = None
+    e2e = e2e_classes = None
     if world == 1 and not args.no_e2e:
         from tomography_3d_reconstructor_b200 import VoxelProcessor, SurfaceExtractor, VolumeCalculator
         host_bool = torch.empty((Z, H, W), dtype=torch.bool, pin_memory=True)
@@ -311,10 +331,37 @@ def run_ours(args, Z, H, W):
             torch.cuda.synchronize()
             e2e_s = (time.perf_counter() - t0) / n_e2e
         vox, sm, v, f, props = out
-        e2e = {"value": voxels / e2e_s / 1e9, "unit": "Gvoxels/s", "h2d_bytes_per_step": int(hb.nbytes),
-               "d2h_bytes_per_step": int(vox.nbytes + sm.nbytes + v.nbytes + f.nbytes), "ms_per_step": 1e3 * e2e_s,
-               "steps": n_e2e, "api": "VoxelProcessor.create_voxel_data -> smooth_voxel_data -> "
-               "SurfaceExtractor.extract_manifold_surface -> calculate_mesh_volume/area -> VolumeCalculator.analyze_object_properties"}
+        e2e_classes = {"value": voxels / e2e_s / 1e9, "unit": "Gvoxels/s", "h2d_bytes_per_step": int(hb.nbytes),
+                       "d2h_bytes_per_step": int(vox.nbytes + sm.nbytes + v.nbytes + f.nbytes), "ms_per_step": 1e3 * e2e_s,
+                       "steps": n_e2e, "api": "VoxelProcessor.create_voxel_data -> smooth_voxel_data -> "
+                       "SurfaceExtractor.extract_manifold_surface -> calculate_mesh_volume/area -> "
+                       "VolumeCalculator.analyze_object_properties (also returns both bool voxel grids to the host: 2 x 1 B/voxel)"}
+        del out, vox, sm
+        # the same work as one call: host masks in, host mesh + volumes out (what the reference arm computes)
+        host_u8 = torch.empty((Z, H, W), dtype=torch.uint8, pin_memory=True)
+        host_u8.copy_(masks)
+        torch.cuda.synchronize()
+        hu = host_u8.numpy()
+        u8_list = [hu[z] for z in range(Z)]
+
+        def host_step():
+            return pipeline.reconstruct_host(u8_list, THRESHOLD, sides, PHYS["total_depth_mm"], PHYS["x_length_mm"],
+                                             PHYS["y_length_mm"], use_graph=not args.no_graph)
+
+        for _ in range(2):
+            out = host_step()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            out = host_step()
+        torch.cuda.synchronize()
+        e2e_s = (time.perf_counter() - t0) / n_e2e
+        e2e = {"value": voxels / e2e_s / 1e9, "unit": "Gvoxels/s", "h2d_bytes_per_step": int(hu.nbytes),
+               "d2h_bytes_per_step": int(out["vertices"].nbytes + out["faces"].nbytes + 8 * (32 + 2 * Z)),
+               "ms_per_step": 1e3 * e2e_s, "steps": n_e2e,
+               "api": "pipeline.reconstruct_host: list of pinned host u8 masks -> H2D -> t3d_reconstruct -> D2H of the mesh "
+               "(f32 vertices, int64 faces) and the result block (volumes, area, bbox, per-slice counts)"}
+        assert np.array_equal(out["vertices"], v) and np.array_equal(out["faces"], f)
 
     def teardown():
         if world > 1:
@@ -325,6 +372,37 @@ def run_ours(args, Z, H, W):
             torch.cuda.synchronize()
             dist.barrier()
             dist.destroy_process_group()
+
+    if world > 1 and not args.no_e2e:
+        # sharded e2e: every rank uploads its slab from pinned host memory and downloads its slab of the stitched mesh
+        host_u8 = torch.empty((z1 - z0, H, W), dtype=torch.uint8, pin_memory=True)
+        host_u8.copy_(masks)
+        torch.cuda.synchronize()
+        hnp = host_u8.numpy()
+
+        def host_step():
+            return sharded.reconstruct_host(hnp, Zg, z0, THRESHOLD, sides, PHYS["total_depth_mm"], PHYS["x_length_mm"],
+                                            PHYS["y_length_mm"], use_graph=not args.no_graph)
+
+        for _ in range(2):
+            out = host_step()
+        n_e2e = max(2, min(args.steps, 5))
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            out = host_step()
+        barrier()
+        e2e_s = (time.perf_counter() - t0) / n_e2e
+        t = torch.tensor([e2e_s, float(hnp.nbytes), float(out["vertices_host"].nbytes + out["faces_host"].nbytes)],
+                         dtype=torch.float64, device=dev)
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        e2e_s = float(tmax[0].item())
+        e2e = {"value": voxels / e2e_s / 1e9, "unit": "Gvoxels/s", "h2d_bytes_per_step": int(t[1].item()),
+               "d2h_bytes_per_step": int(t[2].item()), "ms_per_step": 1e3 * e2e_s, "steps": n_e2e,
+               "api": "sharded.reconstruct_host: per-rank pinned host u8 slab -> H2D -> sharded step -> D2H of the rank's "
+               "slab of the stitched mesh (bytes summed over ranks, time = max over ranks)"}
 
     if rank != 0:
         teardown()
@@ -341,12 +419,14 @@ def run_ours(args, Z, H, W):
     V = int(res.get("total_vertices", mesh.verts.shape[0]))
     F = int(res.get("total_faces", mesh.faces.shape[0]))
     mesh_bytes = 12 * V + 12 * F
-    # dominant single kernel among the volume-sized stages
+    # dominant kernel by bytes: the mask decode / bit packing (1 B read + 1/8 B written per voxel)
     per_gpu_vox = (z1 - z0) * H * W
-    cand = {k: stage_ms[k] for k in STAGE_BYTES if k in stage_ms}
-    dom = max(cand, key=cand.get)
-    dom_bytes = STAGE_BYTES[dom] * per_gpu_vox
-    achieved = dom_bytes / (stage_ms[dom] * 1e-3) / 1e9
+    dom = "k_pack_flat (t3d_pack_masks)"
+    dom_bytes = 1.125 * per_gpu_vox
+    achieved = dom_bytes / (pack_ms * 1e-3) / 1e9
+    stage_roofline = {k: {"GB/s": STAGE_BYTES[k] * per_gpu_vox / (stage_ms[k] * 1e-3) / 1e9,
+                          "frac": STAGE_BYTES[k] * per_gpu_vox / (stage_ms[k] * 1e-3) / 1e9 / peak}
+                      for k in STAGE_BYTES if k in stage_ms}
     bytes_alg = 1.5 * voxels + mesh_bytes
     line = {
         "metric": METRIC, "value": value, "unit": "Gvoxels/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
@@ -366,7 +446,12 @@ def run_ours(args, Z, H, W):
         "gpu_launches": int(launches),
         "stages_ms": stage_ms,
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": dom_bytes},
+                     "traffic": NCU_PACK_TRAFFIC_BYTES if (Z, H, W) == (512, 1024, 1024) else None,
+                     "traffic_source": "profiles/ ncu --set full capture of this kernel at C1: dram__bytes_read.sum + "
+                     "dram__bytes_write.sum per launch (most of the 67 MB bit volume stays in the 126 MB L2)",
+                     "peak_source": peak_src, "algorithmic_bytes_per_launch": dom_bytes,
+                     "us_per_launch": 1e3 * pack_ms, "launches_timed": K_REP, "share_of_step": pack_ms / (ms / args.steps),
+                     "stages": stage_roofline},
         "pipeline_roofline": {"bytes_alg_per_step": bytes_alg, "achieved": bytes_alg * args.steps / (ms * 1e-3) / 1e9,
                               "peak": peak * world, "unit": "GB/s",
                               "frac": bytes_alg * args.steps / (ms * 1e-3) / 1e9 / (peak * world)},
@@ -375,10 +460,12 @@ def run_ours(args, Z, H, W):
     }
     if e2e is not None:
         line["e2e"] = e2e
+    if e2e_classes is not None:
+        line["e2e_classes"] = e2e_classes
     if world == 1 and not args.no_cpu:
         from oracle import cpu_ref
         cpu_ref.build()
-        secs, vox_s, n_sl = cpu_sample(Z, H, W, 16, 1)
+        secs, vox_s, n_sl = cpu_sample(Z, H, W, 64, 1)
         line["cpu_baseline"] = {"value": vox_s / secs / 1e9, "unit": "Gvoxels/s", "cores": 1, "kind": "port",
                                 "sample": "central z-slab of %d slices x %dx%d of the same phantom, oracle/cpu_ref.py "
                                 "(scipy.ndimage is single-threaded), %.1f s" % (n_sl, H, W, secs)}

@@ -225,3 +225,34 @@ def reconstruct_fused(masks_u8: torch.Tensor, threshold: int, side_counts, total
         "active_voxels": int(raw_counts.sum()),
         "slice_depths": plan.depths,
     }
+
+
+_device_inputs: Dict = {}
+
+
+def reconstruct_host(mask_images, threshold: int, side_counts, total_depth_mm: float, x_length_mm: float, y_length_mm: float,
+                     iterations: int = 3, close_ends: bool = True, add_padding: bool = True, use_graph: bool = True) -> Dict:
+    """The whole path on HOST data, as one call: a list of (H,W) bool / uint8 masks (what ImageLoader returns,
+    image_loader.py:97-109) or a (Z,H,W) array -> one host->device copy -> reconstruct_fused -> the mesh as numpy arrays
+    (out["vertices"] f32 (V,3) [z,y,x] mm, out["faces"] int64 (F,3)) + the scalars of reconstruct().  bool masks:
+    pass threshold=1.  The intermediate voxel grids stay on the device (the class API has to return them as arrays)."""
+    a = engine._as_stack(mask_images)
+    dev = engine._require_cuda()
+    key = (a.shape, torch.cuda.current_device())
+    buf = _device_inputs.get(key)
+    if buf is None:                                  # persistent input buffer: keeps the captured graph valid
+        buf = _device_inputs[key] = torch.empty(a.shape, dtype=torch.uint8, device=dev)
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", UserWarning)
+        buf.copy_(torch.from_numpy(np.ascontiguousarray(a)), non_blocking=True)
+    out = reconstruct_fused(buf, threshold, side_counts, total_depth_mm, x_length_mm, y_length_mm, iterations, close_ends,
+                            add_padding, use_graph)
+    v, f = out["mesh"].verts.contiguous(), out["mesh"].faces.contiguous()
+    hv = torch.empty(v.shape, dtype=v.dtype, pin_memory=True)
+    hf = torch.empty(f.shape, dtype=f.dtype, pin_memory=True)
+    hv.copy_(v, non_blocking=True)
+    hf.copy_(f, non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    out["vertices"], out["faces"] = hv.numpy(), hf.numpy()
+    return out

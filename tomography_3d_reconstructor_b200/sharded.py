@@ -400,6 +400,38 @@ def reconstruct_fused(masks_u8: torch.Tensor, Zg: int, z0: int, threshold: int, 
 
 R_NGHOST, R_NLEAD = 18, 19
 
+_device_inputs: Dict = {}
+
+
+def reconstruct_host(masks_host: np.ndarray, Zg: int, z0: int, threshold: int, side_counts, total_depth_mm: float,
+                     x_length_mm: float, y_length_mm: float, iterations: int = 3, add_padding: bool = True, group=None,
+                     use_graph: bool = True) -> Dict:
+    """The sharded step on HOST data: this rank's slices [z0, z0+n) as a numpy uint8 (or bool: use threshold=1) array
+    (n,H,W), ideally in pinned memory -> upload -> reconstruct_fused -> this rank's slab of the stitched mesh as numpy
+    arrays in out["vertices_host"], out["faces_host"] (global vertex ids; concatenating the ranks' arrays in rank order
+    gives the single-GPU mesh)."""
+    a = np.ascontiguousarray(masks_host)
+    if a.dtype == np.bool_:
+        a = a.view(np.uint8)
+    if a.dtype != np.uint8 or a.ndim != 3:
+        raise ValueError("masks_host must be a (n,H,W) uint8 or bool array")
+    dev = engine._require_cuda()
+    key = (a.shape, dev.index if dev.index is not None else torch.cuda.current_device())
+    buf = _device_inputs.get(key)
+    if buf is None:                                  # persistent input buffer: keeps the captured graph valid
+        buf = _device_inputs[key] = torch.empty(a.shape, dtype=torch.uint8, device=dev)
+    buf.copy_(torch.from_numpy(a), non_blocking=True)
+    out = reconstruct_fused(buf, Zg, z0, threshold, side_counts, total_depth_mm, x_length_mm, y_length_mm, iterations,
+                            add_padding, group, use_graph)
+    v, f = out["verts"].contiguous(), out["faces"].contiguous()
+    hv = torch.empty(v.shape, dtype=v.dtype, pin_memory=True)
+    hf = torch.empty(f.shape, dtype=f.dtype, pin_memory=True)
+    hv.copy_(v, non_blocking=True)
+    hf.copy_(f, non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    out["vertices_host"], out["faces_host"] = hv.numpy(), hf.numpy()
+    return out
+
 
 def assemble(plan: FusedSlabPlan, h: np.ndarray) -> Dict:
     """Result dict of reconstruct() from the gathered result blocks h (world x stride int64, host)."""
