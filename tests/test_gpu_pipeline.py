@@ -86,7 +86,7 @@ def test_fused_slab_path_stitches_to_the_single_gpu_mesh(eng, oracle, shape, wor
     full = torch.from_numpy(u8).cuda()
     ref = pipeline.reconstruct(full, 200, sides, 6.0, 143.1, 95.03)
     rm = ref["mesh"]
-    caps = pipeline._caps_from(rm.n_active, *rm.n_raw)           # generous: the whole mesh per rank
+    caps = pipeline._caps_from(rm.n_active, *rm.n_raw, rm.n_z, rm.n_raw[0])   # generous: the whole mesh per rank
     ranges = [sharded.slab_range(Z, r, world) for r in range(world)]
     plans = [sharded.FusedSlabPlan(b - a, H, W, Z, a, 200, sides, 6.0, 143.1, 95.03, 3, True, caps, full.device, r, world)
              for r, (a, b) in enumerate(ranges)]
@@ -157,3 +157,45 @@ def test_fused_single_enqueue_path_matches_staged_path(eng, oracle, use_graph):
     assert np.array_equal(out["mesh"].verts.cpu().numpy(), ref2["vertices"])
     assert np.array_equal(out["mesh"].faces.cpu().numpy(), ref2["faces"])
     assert out["voxel_volume_mm3"] == ref2["voxel_volume"]
+
+
+@pytest.mark.parametrize("case", ["blobs_touching_everything", "box_on_slice0", "noise", "plate", "no_depths_like"])
+def test_fused_structured_vertex_order_on_awkward_volumes(eng, oracle, case):
+    """The structured canonical ordering (t3d_mesh_canonicalize_structured_dev: y-edge ranking, one z-edge sort, clamp-group
+    sort) must give exactly the mesh of the staged path on volumes that touch slice 0 / the image border, flat faces
+    and noise; the capacities tune themselves (clamp group provisioned on demand)."""
+    from conftest import random_blobs
+    from tomography_3d_reconstructor_b200 import pipeline
+    rng = np.random.default_rng(7)
+    Z, H, W = 24, 70, 100
+    if case == "blobs_touching_everything":
+        occ = random_blobs(rng, (Z, H, W), 0.5, 2.0)
+    elif case == "box_on_slice0":
+        occ = np.zeros((Z, H, W), bool)
+        occ[0:14, 10:50, 0:80] = True            # touches slice 0 and the x = 0 border: flat cap under slice 0
+    elif case == "noise":
+        occ = rng.random((Z, H, W)) < 0.55
+    elif case == "plate":
+        occ = np.zeros((Z, H, W), bool)
+        occ[8:12, :, :] = True                   # spans the whole image: long y-edge / z-edge runs with equal keys
+    else:
+        occ = random_blobs(rng, (Z, H, W), 0.3, 3.0)
+        occ[:2] = False
+    u8 = (occ * 255).astype(np.uint8)
+    masks = torch.from_numpy(u8).cuda()
+    sides = (4, 16, 4)
+    args = (200, sides, 6.0, 143.1, 95.03)
+    pipeline._plans.clear(); pipeline._hints.clear(); pipeline._g0_caps.clear(); pipeline._generic_sort.clear()
+    ref = pipeline.reconstruct(masks, *args)
+    rv, rf = ref["mesh"].verts.cpu().numpy(), ref["mesh"].faces.cpu().numpy()
+    for rep in range(4):          # 1: staged (learns), 2: fused, maybe re-tuned, 3-4: steady state
+        out = pipeline.reconstruct_fused(masks, *args, use_graph=False)
+        v, f = out["mesh"].verts.cpu().numpy(), out["mesh"].faces.cpu().numpy()
+        assert np.array_equal(v.view(np.uint32), rv.view(np.uint32)) and np.array_equal(f, rf)
+        assert out["voxel_volume_mm3"] == ref["voxel_volume_mm3"]
+    assert len(pipeline._plans) == 1, "steady state must be the fused path"
+    plan = next(iter(pipeline._plans.values()))
+    if case in ("blobs_touching_everything", "box_on_slice0"):
+        assert plan.caps[3] > 0 and plan.caps[4] > 0, "clamp group must be handled by the structured path, not a fallback"
+    if case in ("plate", "no_depths_like"):
+        assert plan.caps[3] > 0 and plan.caps[4] == 0

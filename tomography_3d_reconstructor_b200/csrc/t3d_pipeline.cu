@@ -13,7 +13,7 @@
 enum {
     R_NACTIVE = 0, R_NX = 1, R_NY = 2, R_NZ = 3, R_NT = 4, R_VCANON = 5, R_FCANON = 6, R_UNVERIFIED = 7, R_OVERFLOW = 8,
     R_NAMBIGUOUS = 9, R_NEXACT = 10, R_VOLUME_F64 = 11, R_AREA_F64 = 12, R_BBOX_I32X6 = 13 /* 3 slots */, R_VRAW = 16, R_NEXC = 17,
-    R_NGHOST = 18, R_NLEAD = 19,
+    R_NGHOST = 18, R_NLEAD = 19, R_NG0 = 25,
     R_COUNTS = 32  /* Zx raw per-slice counts, then Zx smoothed per-slice counts */
 };
 
@@ -28,8 +28,8 @@ struct Layout {
 };
 
 // Zx: planes of the voxel buffers (own slices + halos); Zl: planes the surface stage reads
-static Layout make_layout(int Zx, int Zl, int H, int W, int pad, uint32_t capNA, uint32_t capV, uint32_t capF, int n_stages,
-                          bool own_bitsA)
+static Layout make_layout(int Zx, int Zl, int H, int W, int pad, uint32_t capNA, uint32_t capV, uint32_t capF, uint32_t capZ,
+                          uint32_t capG0, int n_stages, bool own_bitsA)
 {
     Layout L;
     const int64_t nw = t3d_words_per_row(W), vol = (int64_t)Zx * H * nw * 4;
@@ -53,16 +53,17 @@ static Layout make_layout(int Zx, int Zl, int H, int W, int pad, uint32_t capNA,
     L.vkeys = o; o += al((int64_t)capV * 8);
     L.verts_raw = o; o += al((int64_t)capV * 12);
     L.faces_raw = o; o += al((int64_t)capF * 12);
-    L.canon = o; o += al(t3d_canonicalize_fast_workspace_bytes(capV, capF));
+    L.canon = o; o += al(capZ ? t3d_canonicalize_structured_workspace_bytes(capV, capF, capZ, capG0, Zp)
+                              : t3d_canonicalize_fast_workspace_bytes(capV, capF));
     L.measure = o; o += al(t3d_mesh_measure_workspace_bytes());
     L.total = o;
     return L;
 }
 
 extern "C" int64_t t3d_reconstruct_workspace_bytes(int Z, int H, int W, int add_padding, int n_stages, uint32_t cap_active,
-                                                   uint32_t cap_verts, uint32_t cap_faces)
+                                                   uint32_t cap_verts, uint32_t cap_faces, uint32_t cap_zverts, uint32_t cap_g0)
 {
-    return make_layout(Z, Z, H, W, add_padding ? 1 : 0, cap_active, cap_verts, cap_faces, n_stages, true).total;
+    return make_layout(Z, Z, H, W, add_padding ? 1 : 0, cap_active, cap_verts, cap_faces, cap_zverts, cap_g0, n_stages, true).total;
 }
 
 extern "C" int64_t t3d_reconstruct_results_len(int Z) { return R_COUNTS + 2 * (int64_t)Z; }
@@ -70,10 +71,11 @@ extern "C" int64_t t3d_reconstruct_results_len(int Z) { return R_COUNTS + 2 * (i
 static inline int imin(int a, int b) { return a < b ? a : b; }
 
 extern "C" int64_t t3d_reconstruct_slab_workspace_bytes(int halo_lo, int n_own, int halo_hi, int H, int W, int add_padding,
-                                                        int n_stages, uint32_t cap_active, uint32_t cap_verts, uint32_t cap_faces)
+                                                        int n_stages, uint32_t cap_active, uint32_t cap_verts, uint32_t cap_faces,
+                                                        uint32_t cap_zverts, uint32_t cap_g0)
 {
     const int Zx = halo_lo + n_own + halo_hi, Zl = imin(SURF_HALO, halo_lo) + n_own + imin(SURF_HALO, halo_hi);
-    return make_layout(Zx, Zl, H, W, add_padding ? 1 : 0, cap_active, cap_verts, cap_faces, n_stages, false).total;
+    return make_layout(Zx, Zl, H, W, add_padding ? 1 : 0, cap_active, cap_verts, cap_faces, cap_zverts, cap_g0, n_stages, false).total;
 }
 
 __global__ void k_finalize_sizes(unsigned long long* r, unsigned long long capNA, unsigned long long capV, unsigned long long capF)
@@ -167,8 +169,8 @@ struct SlabGeom {
 static int reconstruct_core(const uint32_t* grid, const SlabGeom& g, int H, int W, int n_stages, unsigned erode_mask, int pad,
                             const double* weights3_host, const void* cum_f64, const void* adj_f64, int n_cum, double mm_y,
                             double mm_x, int scale_in_f64, uint32_t cap_active, uint32_t cap_verts, uint32_t cap_faces,
-                            void* verts_out_f32, void* faces_out_i64, unsigned long long* R, char* ws, const Layout& L,
-                            SideStream* side, cudaStream_t st)
+                            uint32_t cap_zverts, uint32_t cap_g0, void* verts_out_f32, void* faces_out_i64, unsigned long long* R,
+                            char* ws, const Layout& L, SideStream* side, cudaStream_t st)
 {
     const int Zx = g.hl + g.n + g.hh;
     const int64_t nw = t3d_words_per_row(W), plane_words = (int64_t)H * nw;
@@ -212,8 +214,13 @@ static int reconstruct_core(const uint32_t* grid, const SlabGeom& g, int H, int 
     T3D_CUDA(cudaStreamWaitEvent(side->s, side->e[4], 0));
     RUN(t3d_mesh_measure_dev(ws + L.verts_raw, ws + L.faces_raw, cap_faces, R + R_NT, 0, R + R_VOLUME_F64, ws + L.measure, side->s));
     T3D_CUDA(cudaEventRecord(side->e[5], side->s));
-    RUN(t3d_mesh_canonicalize_fast_dev(ws + L.verts_raw, cap_verts, R + R_VRAW, ws + L.faces_raw, cap_faces, R + R_NT, verts_out_f32,
-                                       faces_out_i64, nullptr, R + R_VCANON, ws + L.canon, st));
+    if (cap_zverts)
+        RUN(t3d_mesh_canonicalize_structured_dev(ws + L.verts_raw, ws + L.vkeys, cap_verts, R + R_NACTIVE, R + R_VRAW, Zp, Hp, Wp,
+                                                 ws + L.chunkbase, ws + L.aw_base, cap_active, g.z_offset, 1, n_cum, cap_zverts, cap_g0, ws + L.faces_raw, cap_faces, R + R_NT, verts_out_f32,
+                                                 faces_out_i64, nullptr, R + R_VCANON, R + R_NG0, ws + L.canon, st));
+    else
+        RUN(t3d_mesh_canonicalize_fast_dev(ws + L.verts_raw, cap_verts, R + R_VRAW, ws + L.faces_raw, cap_faces, R + R_NT,
+                                           verts_out_f32, faces_out_i64, nullptr, R + R_VCANON, ws + L.canon, st));
     if (g.want_ghost || g.want_lead)
         k_count_plane_vertices<<<1, 64, 0, st>>>((const float*)verts_out_f32, R + R_VCANON, g.z_ghost, g.z_lead, g.want_ghost,
                                                  g.want_lead, R + R_NGHOST, R + R_NLEAD);
@@ -224,14 +231,14 @@ static int reconstruct_core(const uint32_t* grid, const SlabGeom& g, int H, int 
 extern "C" int t3d_reconstruct(const void* masks_u8, int Z, int H, int W, int threshold, int close_ends, int n_stages,
                                unsigned erode_mask, int add_padding, const double* weights3_host, const void* cum_f64,
                                const void* adj_f64, int n_cum, double mm_per_pixel_y, double mm_per_pixel_x, int scale_in_f64,
-                               uint32_t cap_active, uint32_t cap_verts, uint32_t cap_faces, void* verts_out_f32, void* faces_out_i64,
-                               void* results_u64, void* workspace, void* stream)
+                               uint32_t cap_active, uint32_t cap_verts, uint32_t cap_faces, uint32_t cap_zverts, uint32_t cap_g0,
+                               void* verts_out_f32, void* faces_out_i64, void* results_u64, void* workspace, void* stream)
 {
     if (Z <= 0 || H <= 0 || W <= 0) { t3d_set_error("t3d_reconstruct: empty volume"); return 2; }
     if (cap_active == 0 || cap_verts == 0 || cap_faces == 0) { t3d_set_error("t3d_reconstruct: zero capacity"); return 2; }
     cudaStream_t st = (cudaStream_t)stream;
     const int pad = add_padding ? 1 : 0;
-    const Layout L = make_layout(Z, Z, H, W, pad, cap_active, cap_verts, cap_faces, n_stages, true);
+    const Layout L = make_layout(Z, Z, H, W, pad, cap_active, cap_verts, cap_faces, cap_zverts, cap_g0, n_stages, true);
     char* ws = (char*)workspace;
     unsigned long long* R = (unsigned long long*)results_u64;
     const int64_t nw = t3d_words_per_row(W), plane_words = (int64_t)H * nw, plane_bytes = (int64_t)H * W;
@@ -264,8 +271,8 @@ extern "C" int t3d_reconstruct(const void* masks_u8, int Z, int H, int W, int th
     }
     SlabGeom g = {0, Z, 0, 0, -1, 0, 0, 0, 0.f, 0.f};
     RUN(reconstruct_core(bitsB, g, H, W, n_stages, erode_mask, pad, weights3_host, cum_f64, adj_f64, n_cum, mm_per_pixel_y,
-                         mm_per_pixel_x, scale_in_f64, cap_active, cap_verts, cap_faces, verts_out_f32, faces_out_i64, R, ws, L, side,
-                         st));
+                         mm_per_pixel_x, scale_in_f64, cap_active, cap_verts, cap_faces, cap_zverts, cap_g0, verts_out_f32, faces_out_i64,
+                         R, ws, L, side, st));
     T3D_CHECK_LAUNCH("t3d_reconstruct");
     t3d_count_launches(1);
     return 0;
@@ -311,15 +318,15 @@ extern "C" int t3d_reconstruct_slab(const void* ext_bits, int halo_lo, int n_own
                                     unsigned erode_mask, int add_padding, int z_begin, int z_end, int z_offset, int want_ghost,
                                     float z_ghost, int want_lead, float z_lead, int join_fill, const double* weights3_host, const void* cum_f64,
                                     const void* adj_f64, int n_cum, double mm_per_pixel_y, double mm_per_pixel_x, int scale_in_f64,
-                                    uint32_t cap_active, uint32_t cap_verts, uint32_t cap_faces, void* verts_out_f32,
-                                    void* faces_out_i64, void* results_u64, void* workspace, void* stream)
+                                    uint32_t cap_active, uint32_t cap_verts, uint32_t cap_faces, uint32_t cap_zverts, uint32_t cap_g0,
+                                    void* verts_out_f32, void* faces_out_i64, void* results_u64, void* workspace, void* stream)
 {
     if (n_own <= 0 || H <= 0 || W <= 0 || halo_lo < 0 || halo_hi < 0) { t3d_set_error("t3d_reconstruct_slab: bad slab"); return 2; }
     if (cap_active == 0 || cap_verts == 0 || cap_faces == 0) { t3d_set_error("t3d_reconstruct_slab: zero capacity"); return 2; }
     cudaStream_t st = (cudaStream_t)stream;
     const int pad = add_padding ? 1 : 0, Zx = halo_lo + n_own + halo_hi;
     const int Zl = imin(SURF_HALO, halo_lo) + n_own + imin(SURF_HALO, halo_hi);
-    const Layout L = make_layout(Zx, Zl, H, W, pad, cap_active, cap_verts, cap_faces, n_stages, false);
+    const Layout L = make_layout(Zx, Zl, H, W, pad, cap_active, cap_verts, cap_faces, cap_zverts, cap_g0, n_stages, false);
     char* ws = (char*)workspace;
     unsigned long long* R = (unsigned long long*)results_u64;
     SideStream* side;
@@ -329,8 +336,8 @@ extern "C" int t3d_reconstruct_slab(const void* ext_bits, int halo_lo, int n_own
     RUN(t3d_gap_fill(ext_bits, ws + L.bitsB, nullptr, nullptr, Zx, H, W, R + R_COUNTS, st));
     SlabGeom g = {halo_lo, n_own, halo_hi, z_begin, z_end, z_offset, want_ghost, want_lead, z_ghost, z_lead};
     RUN(reconstruct_core((const uint32_t*)(ws + L.bitsB), g, H, W, n_stages, erode_mask, pad, weights3_host, cum_f64, adj_f64, n_cum,
-                         mm_per_pixel_y, mm_per_pixel_x, scale_in_f64, cap_active, cap_verts, cap_faces, verts_out_f32, faces_out_i64,
-                         R, ws, L, side, st));
+                         mm_per_pixel_y, mm_per_pixel_x, scale_in_f64, cap_active, cap_verts, cap_faces, cap_zverts, cap_g0, verts_out_f32,
+                         faces_out_i64, R, ws, L, side, st));
     T3D_CHECK_LAUNCH("t3d_reconstruct_slab");
     t3d_count_launches(1);
     return 0;

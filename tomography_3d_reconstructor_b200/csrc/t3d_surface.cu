@@ -174,13 +174,17 @@ __global__ void __launch_bounds__(SC_THREADS) k_scan_lookback(const uint32_t* __
     const int64_t n = dev_n(n_cap, n_dev);
     const uint32_t* a = in + (int64_t)blockIdx.y * stride;
     OutT* o = out + (int64_t)blockIdx.y * stride;
-    volatile unsigned long long* d = desc + (int64_t)blockIdx.y * n_tiles;
+    volatile unsigned long long* d = desc + (int64_t)blockIdx.y * n_tiles;   // (stride of the launch, before clamping below)
     __shared__ int s_tile;
     __shared__ uint32_t sh[SC_THREADS / 32];
     __shared__ unsigned long long s_prefix;
     if (threadIdx.x == 0) s_tile = (int)atomicAdd(tickets + blockIdx.y, 1u);
     __syncthreads();
     const int tile = s_tile;
+    // only the tiles that hold data take part (capacity-sized launches with a small device-side n)
+    const int64_t need = (n + SC_TILE - 1) / SC_TILE;
+    n_tiles = (int)(need < 1 ? 1 : (need < n_tiles ? need : n_tiles));
+    if (tile >= n_tiles) return;
     const int64_t base = (int64_t)tile * SC_TILE + (int64_t)threadIdx.x * SC_ITEMS;  // blocked arrangement
     uint32_t v[SC_ITEMS];
     uint32_t sum = 0;
@@ -450,12 +454,14 @@ __global__ void __launch_bounds__(256) k_face_compact(const int32_t* __restrict_
                                                       long long* __restrict__ out64, int32_t* __restrict__ out32,
                                                       const unsigned long long* __restrict__ F_dev = nullptr)
 {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= dev_n(F_cap, F_dev) || !valid[i]) return;
-    const uint32_t a = newid[faces[3 * i]], b = newid[faces[3 * i + 1]], c = newid[faces[3 * i + 2]];
-    const int64_t o = 3 * (int64_t)pos[i];
-    if (out64) { out64[o] = a; out64[o + 1] = b; out64[o + 2] = c; }
-    if (out32) { out32[o] = (int32_t)a; out32[o + 1] = (int32_t)b; out32[o + 2] = (int32_t)c; }
+    const int64_t F = dev_n(F_cap, F_dev);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < F; i += (int64_t)gridDim.x * blockDim.x) {
+        if (!valid[i]) continue;
+        const uint32_t a = newid[faces[3 * i]], b = newid[faces[3 * i + 1]], c = newid[faces[3 * i + 2]];
+        const int64_t o = 3 * (int64_t)pos[i];
+        if (out64) { out64[o] = a; out64[o + 1] = b; out64[o + 2] = c; }
+        if (out32) { out32[o] = (int32_t)a; out32[o + 1] = (int32_t)b; out32[o + 2] = (int32_t)c; }
+    }
 }
 
 // faces through newid straight into the output (degenerate faces are rare): counts the invalid ones; the compaction
@@ -629,6 +635,35 @@ extern "C" int64_t t3d_canonicalize_fast_workspace_bytes(int64_t V, int64_t F)
     return b;
 }
 
+// everything after the sorted permutation is known: head flags + order check, unique scatter, face remap
+static int canonical_tail(const float* vin, const uint32_t* perm, int64_t V, const unsigned long long* V_dev, const void* faces_in,
+                          int64_t F, const unsigned long long* F_dev, void* verts_out, void* faces_out_i64, void* faces_out_i32,
+                          unsigned long long* counts, uint32_t* flags, uint32_t* pos, uint32_t* newid, void* scan_ws,
+                          unsigned long long* totals, cudaStream_t st)
+{
+    void* stream = (void*)st;
+    const unsigned gv = (unsigned)((V + 255) / 256);
+    k_heads_checked<<<gv, 256, 0, st>>>(vin, perm, V, V_dev, flags, counts + 2);
+    if (t3d_exclusive_scan_u32_dev(flags, pos, V, V, 1, 0, 0, V_dev, totals, scan_ws, stream)) return 1;
+    T3D_CUDA(cudaMemcpyAsync(counts, totals, 8, cudaMemcpyDeviceToDevice, st));
+    k_scatter_unique<<<gv, 256, 0, st>>>(vin, perm, flags, pos, V, (float*)verts_out, newid, V_dev);
+    if (F > 0) {
+        // totals[1] = invalid faces, totals[2] = faces the compaction has to look at (0 when nothing is invalid)
+        const unsigned gf = (unsigned)((F + 255) / 256);
+        T3D_CUDA(cudaMemsetAsync(totals + 1, 0, 16, st));
+        k_face_remap<<<gf, 256, 0, st>>>((const int32_t*)faces_in, F, newid, flags, (long long*)faces_out_i64, (int32_t*)faces_out_i32,
+                                         totals + 1, F_dev);
+        k_face_plan<<<1, 1, 0, st>>>(totals + 1, F, F_dev, totals + 2, counts + 1);
+        if (t3d_exclusive_scan_u32_dev(flags, pos, F, F, 1, 0, 0, totals + 2, totals + 3, scan_ws, stream)) return 1;
+        const unsigned gc = gf < (unsigned)(T3D_NUM_SMS * 8) ? gf : (unsigned)(T3D_NUM_SMS * 8);
+        k_face_compact<<<gc, 256, 0, st>>>((const int32_t*)faces_in, F, newid, flags, pos, (long long*)faces_out_i64,
+                                           (int32_t*)faces_out_i32, totals + 2);
+    } else {
+        T3D_CUDA(cudaMemsetAsync(counts + 1, 0, 8, st));
+    }
+    return 0;
+}
+
 // same outputs as t3d_mesh_canonicalize; counts_u64[0] = V', [1] = F', [2] = 0 if the fast ordering was verified.
 // V_dev / F_dev (optional, device uint64): true sizes when V / F are only capacities.
 static int canonicalize_fast_impl(const void* verts_in, int64_t V, const unsigned long long* V_dev, const void* faces_in, int64_t F,
@@ -657,23 +692,8 @@ static int canonicalize_fast_impl(const void* verts_in, int64_t V, const unsigne
     k_make_keys64<<<gv, 256, 0, st>>>(vin, V, V_dev, keys_a, iota);
     T3D_CUDA(cub::DeviceRadixSort::SortPairs(temp, temp_bytes, (const unsigned long long*)keys_a, keys_b, (const uint32_t*)iota, perm,
                                              (int)V, 0, 64, st));
-    k_heads_checked<<<gv, 256, 0, st>>>(vin, perm, V, V_dev, flags, counts + 2);
-    if (t3d_exclusive_scan_u32_dev(flags, pos, V, V, 1, 0, 0, V_dev, totals, scan_ws, stream)) return 1;
-    T3D_CUDA(cudaMemcpyAsync(counts, totals, 8, cudaMemcpyDeviceToDevice, st));
-    k_scatter_unique<<<gv, 256, 0, st>>>(vin, perm, flags, pos, V, (float*)verts_out, newid, V_dev);
-    if (F > 0) {
-        // totals[1] = invalid faces, totals[2] = faces the compaction has to look at (0 when nothing is invalid)
-        const unsigned gf = (unsigned)((F + 255) / 256);
-        T3D_CUDA(cudaMemsetAsync(totals + 1, 0, 16, st));
-        k_face_remap<<<gf, 256, 0, st>>>((const int32_t*)faces_in, F, newid, flags, (long long*)faces_out_i64, (int32_t*)faces_out_i32,
-                                         totals + 1, F_dev);
-        k_face_plan<<<1, 1, 0, st>>>(totals + 1, F, F_dev, totals + 2, counts + 1);
-        if (t3d_exclusive_scan_u32_dev(flags, pos, F, F, 1, 0, 0, totals + 2, totals + 3, scan_ws, stream)) return 1;
-        k_face_compact<<<gf, 256, 0, st>>>((const int32_t*)faces_in, F, newid, flags, pos, (long long*)faces_out_i64,
-                                           (int32_t*)faces_out_i32, totals + 2);
-    } else {
-        T3D_CUDA(cudaMemsetAsync(counts + 1, 0, 8, st));
-    }
+    if (canonical_tail(vin, perm, V, V_dev, faces_in, F, F_dev, verts_out, faces_out_i64, faces_out_i32, counts, flags, pos, newid,
+                       scan_ws, totals, st)) return 1;
     T3D_CHECK_LAUNCH("t3d_mesh_canonicalize_fast");
     t3d_count_launches(F > 0 ? 5 : 3);
     return 0;
@@ -695,6 +715,233 @@ extern "C" int t3d_mesh_canonicalize_fast_dev(const void* verts_in, int64_t V_ca
     return canonicalize_fast_impl(verts_in, V_cap, (const unsigned long long*)V_dev_u64, faces_in, F_cap,
                                   (const unsigned long long*)F_dev_u64, verts_out, faces_out_i64, faces_out_i32, counts_u64, workspace,
                                   stream);
+}
+
+// ------------------------------------------------------------------------------------------------
+// structured canonical order for meshes emitted by t3d_mc_emit (vertex keys available).
+//
+// Raw order = [x-edge | y-edge | z-edge] blocks, each in raster order of the owning grid point (zc, yc, xc).  A vertex
+// has one fractional coordinate; give every coordinate a level (2c on a grid line, 2c+1 strictly inside cell c).
+// np.unique's order (z, y, x floats) is the order by (z level, z float, y level, y float, x level) as long as the
+// coordinate transform is monotone, which fixes almost everything without sorting:
+//   * x-edge vertices are already in canonical order among themselves;
+//   * y-edge vertices only need ordering inside their (plane, row gap) segment (a handful of vertices): ranked by counting;
+//   * z-edge vertices need ONE stable radix sort by (layer, z float) -- a third of the vertices, 42-bit keys;
+//   * the final position of a vertex = its rank in its own block + how many vertices of the other two blocks precede it;
+//     those counts are per-row / per-plane prefix counts, read from the scanned per-active-word counts of the emit pass.
+// Exception G0: with the z map's clamp (surface_extractor.py:100-103) every vertex at or below un-padded plane 0 gets
+// z = 0, so the vertices of the closing cap under slice 0 interleave with those of plane 0 by (y, x): that group (empty
+// unless the object touches slice 0) is ordered by one small generic (y,x)-key sort of its own (cap_g0 entries).
+// As with the fast path the result is verified on the device (counts[2]): rounding that breaks the level model, a
+// group larger than cap_g0 or more z-edge vertices than cap_z leave counts[2] != 0 and the caller falls back.
+// ------------------------------------------------------------------------------------------------
+struct CanonS {
+    const float* verts;
+    const unsigned long long* vkeys;
+    const unsigned long long* sizes;   // {n_active, n_x, n_y, n_z, n_t}
+    uint32_t cap_verts, cap_z, cap_g0;
+    int Zs, Hs;                        // planes / rows per plane of the (local, padded) sign volume
+    int ncr;                           // bitmap chunks per row (t3d_mc_flags)
+    const uint32_t* chunkbase;         // active words before each chunk
+    const uint32_t* aw_base;           // 4 arrays (x, y, z vertices, triangles before each active word), `stride` apart
+    uint32_t stride;
+    int g_plane;                       // local plane index of un-padded plane 0 (= shift - z_offset); < 0: no clamp group here
+    unsigned long long* zkeys;
+    uint32_t* zval;
+    const uint32_t* zperm;             // z block sorted by (layer, z float)
+    unsigned long long* gkeys;
+    uint32_t* gval;
+    const uint32_t* gperm;             // clamp group sorted by (y, x)
+    uint32_t* perm;                    // out: sorted position -> raw vertex id
+    unsigned long long* n_g0_out;
+};
+
+// Number of x- / y- / z-edge vertices (AX = 0 / 1 / 2) owned by grid rows before `row` (rows in raster order, row =
+// plane * Hs + y): the emit order is row-major over active words, so this is the scanned count at the first active word
+// at or after the start of the row.
+template <int AX>
+__device__ __forceinline__ uint32_t before_row(const CanonS& c, int64_t row)
+{
+    const uint32_t na = (uint32_t)c.sizes[0];
+    const uint32_t r = row >= (int64_t)c.Zs * c.Hs ? na : c.chunkbase[row * c.ncr];
+    return r >= na ? (uint32_t)c.sizes[1 + AX] : c.aw_base[(int64_t)AX * c.stride + r];
+}
+
+// sizes of the clamp group per block (0 when the group needs no merging)
+__device__ __forceinline__ void g0_sizes(const CanonS& c, uint32_t& gX, uint32_t& gY, uint32_t& gZ)
+{
+    gX = gY = gZ = 0;
+    if (c.g_plane < 0) return;
+    const int64_t r_plane = (int64_t)min(c.g_plane, c.Zs) * c.Hs, r_next = (int64_t)min(c.g_plane + 1, c.Zs) * c.Hs;
+    const uint32_t z_below = before_row<2>(c, r_plane);                               // z-edge vertices in layers below plane g_plane
+    const uint32_t xy_below = before_row<0>(c, r_plane) + before_row<1>(c, r_plane);  // x/y-edge vertices on planes below it
+    if (z_below == 0 && xy_below == 0) return;                                        // only plane g_plane itself: the level model holds
+    gX = before_row<0>(c, r_next); gY = before_row<1>(c, r_next); gZ = z_below;
+}
+
+__global__ void __launch_bounds__(256) k_canon_zkeys(CanonS c)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= c.cap_z) return;
+    const uint32_t nx = (uint32_t)c.sizes[1], ny = (uint32_t)c.sizes[2], nz = (uint32_t)c.sizes[3];
+    unsigned long long key = 0xffffffffffffffffull;
+    if ((unsigned long long)nx + ny + nz <= c.cap_verts && i < nz) {
+        uint32_t gX, gY, gZ;
+        g0_sizes(c, gX, gY, gZ);
+        const uint32_t raw = nx + ny + i;
+        key = (i < gZ) ? 0ull : (((c.vkeys[raw] >> 42) + 1ull) << 32) | float_key(c.verts[3 * (int64_t)raw]);
+    }
+    c.zkeys[i] = key;
+    c.zval[i] = i;
+}
+
+__global__ void __launch_bounds__(256) k_canon_gkeys(CanonS c)
+{
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= c.cap_g0) return;
+    const uint32_t nx = (uint32_t)c.sizes[1], ny = (uint32_t)c.sizes[2], nz = (uint32_t)c.sizes[3];
+    unsigned long long key = 0xffffffffffffffffull;
+    uint32_t raw = 0;
+    if ((unsigned long long)nx + ny + nz <= c.cap_verts) {
+        uint32_t gX, gY, gZ;
+        g0_sizes(c, gX, gY, gZ);
+        if (t < gX + gY + gZ) {
+            raw = t < gX ? t : t < gX + gY ? nx + (t - gX) : nx + ny + (t - gX - gY);
+            const float* v = c.verts + 3 * (int64_t)raw;
+            key = ((unsigned long long)float_key(v[1]) << 32) | float_key(v[2]);
+        }
+    }
+    c.gkeys[t] = key;
+    c.gval[t] = raw;
+}
+
+__global__ void __launch_bounds__(256) k_canon_positions(CanonS c)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t nx = (uint32_t)c.sizes[1], ny = (uint32_t)c.sizes[2], nz = (uint32_t)c.sizes[3];
+    const unsigned long long V64 = (unsigned long long)nx + ny + nz;
+    if (V64 > c.cap_verts || i >= (uint32_t)V64) return;
+    if (nz > c.cap_z) { c.perm[i] = i; return; }       // no z order available: identity, the order check will fail
+    uint32_t gX, gY, gZ;
+    g0_sizes(c, gX, gY, gZ);
+    const uint32_t nG = gX + gY + gZ;
+    if (i == 0 && c.n_g0_out) *c.n_g0_out = nG;
+    // positions [0, nG): the clamp group in (y, x) order (block order when its sort was not provisioned)
+    if (i < nG) c.perm[i] = (nG <= c.cap_g0) ? c.gperm[i] : (i < gX ? i : i < gX + gY ? nx + (i - gX) : nx + ny + (i - gX - gY));
+    if (i < nx) {                                       // x-edge vertex: after the y-edge vertices of earlier rows and the z-edge
+        if (i < gX) return;                             // vertices of lower layers
+        const unsigned long long key = c.vkeys[i];
+        const int k = (int)(key >> 42), j = (int)((key >> 22) & 0xfffffu);
+        c.perm[i + before_row<1>(c, (int64_t)k * c.Hs + j) + before_row<2>(c, (int64_t)k * c.Hs)] = i;
+    } else if (i < nx + ny) {                           // y-edge vertex: rank inside its (plane, row gap) segment by counting
+        const uint32_t iy = i - nx;
+        if (iy < gY) return;
+        const unsigned long long key = c.vkeys[i];
+        const int k = (int)(key >> 42), j = (int)((key >> 22) & 0xfffffu);
+        const int64_t row = (int64_t)k * c.Hs + j;
+        const uint32_t lo = before_row<1>(c, row), hi = before_row<1>(c, row + 1);
+        const uint32_t mine = float_key(c.verts[3 * (int64_t)i + 1]);
+        uint32_t r = 0;
+        for (uint32_t e = lo; e < hi; ++e) {
+            const uint32_t ke = float_key(c.verts[3 * (int64_t)(nx + e) + 1]);
+            r += (ke < mine || (ke == mine && e < iy)) ? 1u : 0u;
+        }
+        c.perm[before_row<0>(c, row + 1) + lo + r + before_row<2>(c, (int64_t)k * c.Hs)] = i;
+    } else {                                            // z block: this thread takes sorted rank R
+        const uint32_t R = i - nx - ny;
+        if (R < gZ) return;
+        const uint32_t raw = nx + ny + c.zperm[R];
+        const int64_t next_plane = ((int64_t)(c.vkeys[raw] >> 42) + 1) * c.Hs;
+        c.perm[before_row<0>(c, next_plane) + before_row<1>(c, next_plane) + R] = raw;
+    }
+}
+
+static int bits_for(unsigned v) { int b = 0; while ((1u << b) <= v) ++b; return b; }   // bits needed to hold values 0..v
+
+static size_t sort64_temp_bytes(int64_t V);
+
+extern "C" int64_t t3d_canonicalize_structured_workspace_bytes(int64_t V, int64_t F, uint32_t cap_z, uint32_t cap_g0, int Zs)
+{
+    const int64_t n = V > F ? V : F;
+    int64_t b = 0;
+    b += 2 * align256(8 * (int64_t)cap_z) + 2 * align256(4 * (int64_t)cap_z);      // z keys in/out, values in/out
+    b += 2 * align256(8 * (int64_t)cap_g0) + 2 * align256(4 * (int64_t)cap_g0);    // clamp group keys / values
+    b += align256(4 * V);                                                          // perm
+    b += 2 * align256(4 * n);                                                      // flags, positions
+    b += align256(4 * V);                                                          // newid
+    const int64_t tz = (int64_t)sort64_temp_bytes(cap_z > 0 ? cap_z : 1), tg = (int64_t)sort64_temp_bytes(cap_g0 > 0 ? cap_g0 : 1);
+    b += align256(tz > tg ? tz : tg);
+    b += align256(t3d_scan_workspace_bytes(n, 1));
+    b += 256;
+    return b;
+}
+
+// verts_in / vkeys: capacity V_cap, true block sizes in sizes_u64 = {n_active, n_x, n_y, n_z, n_t} (device); V_dev_u64 = n_x+n_y+n_z
+// and F_dev_u64 = n_t (device).  Zs: planes of the marched (local) sign volume; z_offset / unpad_shift / n_cum as passed to
+// t3d_mc_vertices.  counts_u64: [0] V' [1] F' [2] != 0: order not verified, fall back; n_g0_u64 (optional): size of the
+// clamp group (a caller seeing [2] != 0 with *n_g0 > cap_g0 retries with a larger cap_g0).
+extern "C" int t3d_mesh_canonicalize_structured_dev(const void* verts_in, const void* vkeys_u64, int64_t V_cap, const void* sizes_u64,
+                                                    const void* V_dev_u64, int Zs, int Hs, int Ws, const void* chunkbase_u32,
+                                                    const void* aw_base_u32, uint32_t aw_stride, int z_offset, int unpad_shift, int n_cum,
+                                                    uint32_t cap_z, uint32_t cap_g0, const void* faces_in, int64_t F_cap,
+                                                    const void* F_dev_u64, void* verts_out, void* faces_out_i64, void* faces_out_i32,
+                                                    void* counts_u64, void* n_g0_u64, void* workspace, void* stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    if (V_cap <= 0 || V_cap > 0x7fffffff || F_cap < 0 || Zs <= 0 || Hs <= 0 || Ws <= 0 || cap_z == 0) {
+        t3d_set_error("t3d_mesh_canonicalize_structured: bad sizes");
+        return 2;
+    }
+    const int64_t V = V_cap, F = F_cap, n = V > F ? V : F;
+    char* ws = (char*)workspace;
+    CanonS c;
+    c.verts = (const float*)verts_in;
+    c.vkeys = (const unsigned long long*)vkeys_u64;
+    c.sizes = (const unsigned long long*)sizes_u64;
+    c.cap_verts = (uint32_t)V; c.cap_z = cap_z; c.cap_g0 = cap_g0;
+    c.Zs = Zs; c.Hs = Hs;
+    c.ncr = (t3d_wpr(Ws) + 31) >> 5;
+    c.chunkbase = (const uint32_t*)chunkbase_u32;
+    c.aw_base = (const uint32_t*)aw_base_u32;
+    c.stride = aw_stride;
+    c.g_plane = (n_cum > 0 && unpad_shift > 0) ? unpad_shift - z_offset : -1;
+    unsigned long long* zkeys_b; uint32_t* zperm; unsigned long long* gkeys_b; uint32_t* gperm;
+    c.zkeys = (unsigned long long*)ws; ws += align256(8 * (int64_t)cap_z);
+    zkeys_b = (unsigned long long*)ws; ws += align256(8 * (int64_t)cap_z);
+    c.zval = (uint32_t*)ws; ws += align256(4 * (int64_t)cap_z);
+    zperm = (uint32_t*)ws; ws += align256(4 * (int64_t)cap_z);
+    c.gkeys = (unsigned long long*)ws; ws += align256(8 * (int64_t)cap_g0);
+    gkeys_b = (unsigned long long*)ws; ws += align256(8 * (int64_t)cap_g0);
+    c.gval = (uint32_t*)ws; ws += align256(4 * (int64_t)cap_g0);
+    gperm = (uint32_t*)ws; ws += align256(4 * (int64_t)cap_g0);
+    c.perm = (uint32_t*)ws; ws += align256(4 * V);
+    uint32_t* flags = (uint32_t*)ws; ws += align256(4 * n);
+    uint32_t* pos = (uint32_t*)ws; ws += align256(4 * n);
+    uint32_t* newid = (uint32_t*)ws; ws += align256(4 * V);
+    const size_t tz = sort64_temp_bytes(cap_z), tg = sort64_temp_bytes(cap_g0 > 0 ? cap_g0 : 1);
+    void* temp = ws; ws += align256((int64_t)(tz > tg ? tz : tg));
+    void* scan_ws = ws; ws += align256(t3d_scan_workspace_bytes(n, 1));
+    unsigned long long* totals = (unsigned long long*)ws;
+    unsigned long long* counts = (unsigned long long*)counts_u64;
+    c.zperm = zperm; c.gperm = gperm;
+    c.n_g0_out = (unsigned long long*)n_g0_u64;
+    T3D_CUDA(cudaMemsetAsync(counts + 2, 0, 8, st));
+    k_canon_zkeys<<<(cap_z + 255) / 256, 256, 0, st>>>(c);
+    size_t tb = tz;
+    T3D_CUDA(cub::DeviceRadixSort::SortPairs(temp, tb, (const unsigned long long*)c.zkeys, zkeys_b, (const uint32_t*)c.zval, zperm,
+                                             (int)cap_z, 0, 32 + bits_for((unsigned)Zs + 1), st));
+    if (cap_g0 > 0) {
+        k_canon_gkeys<<<(cap_g0 + 255) / 256, 256, 0, st>>>(c);
+        tb = tg;
+        T3D_CUDA(cub::DeviceRadixSort::SortPairs(temp, tb, (const unsigned long long*)c.gkeys, gkeys_b, (const uint32_t*)c.gval, gperm,
+                                                 (int)cap_g0, 0, 64, st));
+    }
+    k_canon_positions<<<(unsigned)((V + 255) / 256), 256, 0, st>>>(c);
+    if (canonical_tail(c.verts, c.perm, V, (const unsigned long long*)V_dev_u64, faces_in, F, (const unsigned long long*)F_dev_u64,
+                       verts_out, faces_out_i64, faces_out_i32, counts, flags, pos, newid, scan_ws, totals, st)) return 1;
+    T3D_CHECK_LAUNCH("t3d_mesh_canonicalize_structured");
+    t3d_count_launches((F > 0 ? 5 : 3) + 2 + (cap_g0 > 0 ? 1 : 0));
+    return 0;
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -153,7 +153,7 @@ class DeviceMesh:
     """Mesh on the device.  After an asynchronous canonicalisation the arrays are capacity-sized and the true sizes
     live in `counts_dev` until resolve() (one D2H copy) or set_sizes() trims them."""
 
-    __slots__ = ("_verts", "_faces", "counts_dev", "n_ambiguous", "n_exact", "_measures", "raw", "n_active", "n_raw",
+    __slots__ = ("_verts", "_faces", "counts_dev", "n_ambiguous", "n_exact", "_measures", "raw", "n_active", "n_raw", "n_z",
                  "__weakref__")
 
     def __init__(self, verts: torch.Tensor, faces: torch.Tensor, n_ambiguous: int = 0, n_exact: int = 0,
@@ -608,12 +608,12 @@ def extract_surface(dv: DeviceVolume, slice_depths, mm_per_pixel_y, mm_per_pixel
         mark("canonicalize")
         m = DeviceMesh(v2, f2, n_ambiguous, n_exact, counts_dev=counts)
         m.raw = (verts, faces)
-        m.n_active, m.n_raw = n_active, (V, nT)
+        m.n_active, m.n_raw, m.n_z = n_active, (V, nT), nZ
         return m
     v2, f2 = canonicalize(verts, faces, fast=True)
     mark("canonicalize")
     m = DeviceMesh(v2, f2, n_ambiguous, n_exact)
-    m.n_active, m.n_raw = n_active, (V, nT)
+    m.n_active, m.n_raw, m.n_z = n_active, (V, nT), nZ
     return m
 
 

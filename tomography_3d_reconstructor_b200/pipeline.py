@@ -101,7 +101,7 @@ def reconstruct(masks_u8: torch.Tensor, threshold: int, side_counts, total_depth
 # fused path: the whole step as ONE enqueue (t3d_reconstruct), captured in a CUDA graph
 # ----------------------------------------------------------------------------------------------------------------
 R_NACTIVE, R_NX, R_NY, R_NZ, R_NT, R_VCANON, R_FCANON, R_UNVERIFIED, R_OVERFLOW = range(9)
-R_NAMBIGUOUS, R_NEXACT, R_VOLUME, R_AREA, R_BBOX, R_VRAW, R_COUNTS = 9, 10, 11, 12, 13, 16, 32
+R_NAMBIGUOUS, R_NEXACT, R_VOLUME, R_AREA, R_BBOX, R_VRAW, R_NG0, R_COUNTS = 9, 10, 11, 12, 13, 16, 25, 32
 
 
 class FusedPlan:
@@ -125,6 +125,8 @@ class FusedPlan:
         self.n_cum = len(cum)
         self.cum_d = torch.from_numpy(cum).to(device) if self.n_cum else None
         self.adj_d = torch.from_numpy(adj).to(device) if self.n_cum else None
+        if len(self.caps) != 5:
+            raise ValueError("caps = (active words, vertices, faces, z-edge vertices, clamp group)")
         nbytes = int(L.t3d_reconstruct_workspace_bytes(Z, H, W, 1 if add_padding else 0, self.n_stages, *self.caps))
         self.ws = torch.empty(nbytes // 8 + 1, dtype=torch.int64, device=device)
         self.verts = torch.empty((self.caps[1], 3), dtype=torch.float32, device=device)
@@ -141,8 +143,8 @@ class FusedPlan:
         engine.check(engine._L().t3d_reconstruct(
             p(masks_u8), Z, H, W, self.threshold, 1 if self.close_ends else 0, self.n_stages, self.erode_mask,
             1 if self.add_padding else 0, engine._W3_C, p(self.cum_d), p(self.adj_d), self.n_cum, float(self.mm_y),
-            float(self.mm_x), 0, self.caps[0], self.caps[1], self.caps[2], p(self.verts), p(self.faces), p(self.res),
-            p(self.ws), engine._stream()), "t3d_reconstruct")
+            float(self.mm_x), 0, self.caps[0], self.caps[1], self.caps[2], self.caps[3], self.caps[4], p(self.verts),
+            p(self.faces), p(self.res), p(self.ws), engine._stream()), "t3d_reconstruct")
 
     def capture(self, masks_u8: torch.Tensor) -> None:
         """Record the step for this input buffer into a CUDA graph (after one eager warm-up run)."""
@@ -166,11 +168,34 @@ class FusedPlan:
 
 _plans: Dict = {}
 _hints: Dict = {}
+_g0_caps: Dict = {}       # key -> capacity of the z-clamp group sort (survives re-learning of the other capacities)
+_generic_sort: Dict = {}  # key -> True: the structured vertex ordering could not be verified on this input, use the 64-bit sort
 
 
-def _caps_from(n_active: int, v_raw: int, f_raw: int):
-    grow = lambda n: int(n * 1.02) + 4096
-    return grow(n_active), grow(v_raw), grow(f_raw)
+def _tuned_caps(key, caps):
+    caps = tuple(caps)
+    g0 = max(caps[4], _g0_caps.get(key, 0))
+    return caps[:3] + ((0, 0) if _generic_sort.get(key) else (caps[3], g0))
+
+
+def _retune(key, n_g0: int, cap_g0: int) -> bool:
+    """After an unverified structured ordering: provision the clamp-group sort if that was missing, else switch this
+    problem to the generic 64-bit sort.  Returns True if the step should be run again."""
+    if n_g0 > cap_g0:
+        _g0_caps[key] = _grow(n_g0)
+    else:
+        _generic_sort[key] = True
+    return True
+
+
+def _grow(n: int) -> int:
+    return int(n * 1.02) + 4096
+
+
+def _caps_from(n_active: int, v_raw: int, f_raw: int, n_z: int, n_g0: int = 0):
+    """Capacities (active words, vertices, faces, z-edge vertices, z-clamp group) with a small margin; the clamp group
+    (vertices under slice 0, see t3d_mesh_canonicalize_structured_dev) stays unprovisioned while it is empty."""
+    return _grow(n_active), _grow(v_raw), _grow(f_raw), _grow(n_z), (_grow(n_g0) if n_g0 > 0 else 0)
 
 
 def reconstruct_fused(masks_u8: torch.Tensor, threshold: int, side_counts, total_depth_mm: float, x_length_mm: float,
@@ -189,25 +214,31 @@ def reconstruct_fused(masks_u8: torch.Tensor, threshold: int, side_counts, total
         out = reconstruct(masks_u8, threshold, side_counts, total_depth_mm, x_length_mm, y_length_mm, iterations, close_ends,
                           add_padding)
         m = out["mesh"]
-        _hints[key] = _caps_from(m.n_active, *m.n_raw)
+        _hints[key] = _caps_from(m.n_active, *m.n_raw, m.n_z)
         return out
 
     if key not in _hints:
         return staged()
+    caps = _tuned_caps(key, _hints[key])
     plan = _plans.get(key)
-    if plan is None or any(c < h for c, h in zip(plan.caps, _hints[key])):
+    if plan is None or any(c < h for c, h in zip(plan.caps, caps)) or (plan.caps[3] == 0) != (caps[3] == 0):
         plan = FusedPlan((Z, H, W), threshold, side_counts, total_depth_mm, x_length_mm, y_length_mm, iterations,
-                         close_ends, add_padding, _hints[key], masks_u8.device)
+                         close_ends, add_padding, caps, masks_u8.device)
         _plans[key] = plan
     if use_graph and plan.graph_ptr != masks_u8.data_ptr():
         plan.capture(masks_u8)
     r = plan.run(masks_u8, use_graph)
+    if r[R_UNVERIFIED] and not r[R_OVERFLOW] and plan.caps[3] and _retune(key, int(r[R_NG0]), plan.caps[4]):
+        _plans.pop(key, None)
+        return reconstruct_fused(masks_u8, threshold, side_counts, total_depth_mm, x_length_mm, y_length_mm, iterations,
+                                 close_ends, add_padding, use_graph)
     if r[R_OVERFLOW] or r[R_UNVERIFIED] or r[R_NT] == 0:
         _plans.pop(key, None)
         _hints.pop(key, None)
         return staged()
     # every later call with a slightly larger mesh still fits thanks to the margin; refresh the hints if it grew
-    _hints[key] = tuple(max(a, b) for a, b in zip(_hints[key], _caps_from(int(r[R_NACTIVE]), int(r[R_VRAW]), int(r[R_NT]))))
+    _hints[key] = tuple(max(a, b) for a, b in zip(_hints[key], _caps_from(int(r[R_NACTIVE]), int(r[R_VRAW]), int(r[R_NT]),
+                                                                         int(r[R_NZ]), int(r[R_NG0]))))
     mesh = engine.DeviceMesh(plan.verts[:int(r[R_VCANON])], plan.faces[:int(r[R_FCANON])], int(r[R_NAMBIGUOUS]), int(r[R_NEXACT]))
     vol_area = r[R_VOLUME:R_VOLUME + 2].view(np.float64)
     mesh._measures = (float(vol_area[0]), float(vol_area[1]))

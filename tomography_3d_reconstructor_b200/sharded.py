@@ -269,6 +269,8 @@ class FusedSlabPlan:
         self.n_stages = len(stages)
         self.erode_mask = sum(1 << k for k, er in enumerate(stages) if er)
         self.caps = tuple(int(c) for c in caps)
+        if len(self.caps) != 5:
+            raise ValueError("caps = (active words, vertices, faces, z-edge vertices, clamp group)")
         self.hl, self.hh = (HALO if self.z0 > 0 else 0), (HALO if self.z1 < Zg else 0)
         pad = 1 if add_padding else 0
         sl = min(SURF_HALO, self.hl)
@@ -315,7 +317,7 @@ class FusedSlabPlan:
             self.z_begin, self.z_end, self.z_offset, self.want_ghost, self.z_ghost, self.want_lead, self.z_lead,
             int(self.z0 == 0 or self.z1 == self.Zg), engine._W3_C,
             p(self.cum_d), p(self.adj_d), self.n_cum, float(self.mm_y), float(self.mm_x), 0, self.caps[0], self.caps[1],
-            self.caps[2], p(self.verts), p(self.faces), p(self.res), p(self.ws), engine._stream()), "t3d_reconstruct_slab")
+            self.caps[2], self.caps[3], self.caps[4], p(self.verts), p(self.faces), p(self.res), p(self.ws), engine._stream()), "t3d_reconstruct_slab")
 
     def stitch(self) -> None:
         """Local face ids -> ids in the stitched mesh, from the gathered result blocks (device side)."""
@@ -355,6 +357,7 @@ class FusedSlabPlan:
 
 _slab_plans: Dict = {}
 _slab_hints: Dict = {}
+_slab_retuned: Dict = {}
 
 
 def reconstruct_fused(masks_u8: torch.Tensor, Zg: int, z0: int, threshold: int, side_counts, total_depth_mm: float,
@@ -375,26 +378,37 @@ def reconstruct_fused(masks_u8: torch.Tensor, Zg: int, z0: int, threshold: int, 
         out = reconstruct(masks_u8, Zg, z0, threshold, side_counts, total_depth_mm, x_length_mm, y_length_mm, iterations,
                           add_padding, group=group)
         m = out.get("local_mesh")
-        _slab_hints[key] = pipeline._caps_from(m.n_active, *m.n_raw) if m is not None else (4096, 4096, 4096)
+        _slab_hints[key] = pipeline._caps_from(m.n_active, *m.n_raw, m.n_z) if m is not None else (4096, 4096, 4096, 4096, 0)
         return out
 
     if key not in _slab_hints:
         return staged()
+    caps = pipeline._tuned_caps(("slab",) + key, _slab_hints[key])
     plan = _slab_plans.get(key)
-    if plan is None or any(c < h for c, h in zip(plan.caps, _slab_hints[key])):
+    if plan is None:      # plans are (re)built by all ranks in the same call: building one runs the step's collectives once more
         plan = FusedSlabPlan(n, H, W, Zg, z0, threshold, side_counts, total_depth_mm, x_length_mm, y_length_mm, iterations,
-                             add_padding, _slab_hints[key], masks_u8.device, rank, world, group)
+                             add_padding, caps, masks_u8.device, rank, world, group)
         _slab_plans[key] = plan
     if use_graph and plan.graph_ptr != masks_u8.data_ptr():
         plan.capture(masks_u8)
     h = plan.run(masks_u8, use_graph)
-    if (h[:, R.R_OVERFLOW] != 0).any() or (h[:, R.R_UNVERIFIED] != 0).any() or (h[:, R.R_NT] == 0).any():
+    me = h[rank]
+    bad = h[:, R.R_UNVERIFIED] != 0
+    if bad.any() and not (h[:, R.R_OVERFLOW] != 0).any() and not _slab_retuned.get(key, 0) >= 2:
+        # every rank takes this branch together (the decision only uses gathered data); a rank whose own ordering was
+        # not verified provisions its clamp-group sort or switches to the generic 64-bit sort
+        _slab_retuned[key] = _slab_retuned.get(key, 0) + 1
+        if bad[rank] and plan.caps[3]:
+            pipeline._retune(("slab",) + key, int(me[R.R_NG0]), plan.caps[4])
+        _slab_plans.pop(key, None)
+        return reconstruct_fused(masks_u8, Zg, z0, threshold, side_counts, total_depth_mm, x_length_mm, y_length_mm, iterations,
+                                 add_padding, group, use_graph)
+    if (h[:, R.R_OVERFLOW] != 0).any() or bad.any() or (h[:, R.R_NT] == 0).any():
         _slab_plans.pop(key, None)
         _slab_hints.pop(key, None)
         return staged()
-    me = h[rank]
-    _slab_hints[key] = tuple(max(a, b) for a, b in zip(_slab_hints[key], pipeline._caps_from(int(me[R.R_NACTIVE]), int(me[R.R_VRAW]),
-                                                                                             int(me[R.R_NT]))))
+    _slab_hints[key] = tuple(max(a, b) for a, b in zip(_slab_hints[key], pipeline._caps_from(
+        int(me[R.R_NACTIVE]), int(me[R.R_VRAW]), int(me[R.R_NT]), int(me[R.R_NZ]), int(me[R.R_NG0]))))
     return assemble(plan, h)
 
 
