@@ -635,6 +635,122 @@ extern "C" int64_t t3d_canonicalize_fast_workspace_bytes(int64_t V, int64_t F)
     return b;
 }
 
+// np.unique on the sorted sequence in ONE pass: head flags + strict order check, exclusive scan of the heads (decoupled
+// look-back, same tile protocol as k_scan_lookback), scatter of the unique vertices and of the old -> new id map.
+// n_unique_out receives V'.
+__global__ void __launch_bounds__(SC_THREADS) k_unique_fused(const float* __restrict__ verts, const uint32_t* __restrict__ perm, int64_t V_cap,
+                                                             const unsigned long long* __restrict__ V_dev, float* __restrict__ out_verts,
+                                                             uint32_t* __restrict__ newid, unsigned long long* __restrict__ desc, int n_tiles,
+                                                             unsigned int* __restrict__ ticket, unsigned long long* __restrict__ bad,
+                                                             unsigned long long* __restrict__ n_unique_out)
+{
+    // striped arrangement: element e = k * SC_THREADS + tid of the tile, so a warp always touches 32 consecutive sorted
+    // positions (coalesced perm reads, neighbouring vertices); keys go through shared memory for the neighbour compare
+    const int64_t n = dev_n(V_cap, V_dev);
+    volatile unsigned long long* d = desc;
+    __shared__ int s_tile;
+    __shared__ uint32_t s_kz[SC_TILE + 1], s_ky[SC_TILE + 1], s_kx[SC_TILE + 1];   // [0] = last element of the previous tile
+    __shared__ uint32_t s_part[SC_ITEMS * (SC_THREADS / 32)];                     // heads per (k, warp), then their exclusive scan
+    __shared__ unsigned long long s_prefix;
+    if (threadIdx.x == 0) s_tile = (int)atomicAdd(ticket, 1u);
+    __syncthreads();
+    const int tile = s_tile;
+    const int64_t need = (n + SC_TILE - 1) / SC_TILE;
+    n_tiles = (int)(need < 1 ? 1 : (need < n_tiles ? need : n_tiles));
+    if (tile >= n_tiles) return;
+    const int64_t base = (int64_t)tile * SC_TILE;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint32_t src[SC_ITEMS];
+    float vz[SC_ITEMS], vy[SC_ITEMS], vx[SC_ITEMS];
+#pragma unroll
+    for (int k = 0; k < SC_ITEMS; ++k) {
+        const int e = k * SC_THREADS + tid;
+        if (base + e < n) {
+            src[k] = perm[base + e];
+            const float* a = verts + 3 * (int64_t)src[k];
+            vz[k] = a[0]; vy[k] = a[1]; vx[k] = a[2];
+            s_kz[e + 1] = float_key(vz[k]); s_ky[e + 1] = float_key(vy[k]); s_kx[e + 1] = float_key(vx[k]);
+        }
+    }
+    if (tid == 0 && base > 0) {
+        const float* b = verts + 3 * (int64_t)perm[base - 1];
+        s_kz[0] = float_key(b[0]); s_ky[0] = float_key(b[1]); s_kx[0] = float_key(b[2]);
+    }
+    __syncthreads();
+    uint32_t ball[SC_ITEMS];
+    uint32_t myhead = 0;
+    bool out_of_order = false;
+#pragma unroll
+    for (int k = 0; k < SC_ITEMS; ++k) {
+        const int e = k * SC_THREADS + tid;
+        bool h = false;
+        if (base + e < n) {
+            h = true;
+            if (base + e > 0) {
+                const uint32_t az = s_kz[e + 1], ay = s_ky[e + 1], ax = s_kx[e + 1], pz = s_kz[e], py = s_ky[e], px = s_kx[e];
+                h = (az != pz || ay != py || ax != px);
+                out_of_order |= (az < pz) || (az == pz && (ay < py || (ay == py && ax < px)));
+            }
+        }
+        ball[k] = __ballot_sync(0xffffffffu, h);
+        myhead |= (h ? 1u : 0u) << k;
+        if (lane == 0) s_part[k * (SC_THREADS / 32) + warp] = __popc(ball[k]);
+    }
+    if (out_of_order) atomicOr(bad, 1ull);
+    __syncthreads();
+    if (tid < 32) {
+        // exclusive scan of the 64 partial counts (two per lane), tile aggregate, look-back
+        const uint32_t p0 = s_part[2 * lane], p1 = s_part[2 * lane + 1];
+        const uint32_t incl = warp_incl_scan(p0 + p1);
+        const uint32_t agg = __shfl_sync(0xffffffffu, incl, 31);
+        s_part[2 * lane] = incl - p0 - p1;
+        s_part[2 * lane + 1] = incl - p1;
+        unsigned long long prefix = 0;
+        if (tile == 0) {
+            if (tid == 0) { d[0] = SC_FLAG_P | (unsigned long long)agg; }
+        } else {
+            if (tid == 0) { d[tile] = SC_FLAG_A | (unsigned long long)agg; }
+            int idx = tile - 1 - tid;
+            while (true) {
+                unsigned long long w = (idx >= 0) ? d[idx] : SC_FLAG_P;
+                while (__any_sync(0xffffffffu, (w >> 62) == 0)) {
+                    if ((w >> 62) == 0) w = (idx >= 0) ? d[idx] : SC_FLAG_P;
+                }
+                const uint32_t is_p = __ballot_sync(0xffffffffu, (w >> 62) == 2);
+                const int first_p = is_p ? (__ffs(is_p) - 1) : 32;
+                unsigned long long val = (tid <= first_p) ? (w & SC_VALUE_MASK) : 0ull;
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) val += __shfl_xor_sync(0xffffffffu, val, off);
+                prefix += val;
+                if (is_p) break;
+                idx -= 32;
+            }
+            if (tid == 0) { d[tile] = SC_FLAG_P | ((prefix + agg) & SC_VALUE_MASK); }
+        }
+        if (tid == 0) {
+            s_prefix = prefix;
+            if (tile == n_tiles - 1) *n_unique_out = prefix + agg;
+        }
+    }
+    __syncthreads();
+    const uint32_t tile_prefix = (uint32_t)s_prefix;
+    const uint32_t lt = (1u << lane) - 1u;
+#pragma unroll
+    for (int k = 0; k < SC_ITEMS; ++k) {
+        const int e = k * SC_THREADS + tid;
+        if (base + e < n) {
+            const uint32_t h = (myhead >> k) & 1u;
+            // unique index = (heads up to and including this element) - 1
+            const uint32_t u = tile_prefix + s_part[k * (SC_THREADS / 32) + warp] + __popc(ball[k] & lt) + h - 1u;
+            newid[src[k]] = u;
+            if (h) {
+                float* o = out_verts + 3 * (int64_t)u;
+                o[0] = vz[k]; o[1] = vy[k]; o[2] = vx[k];
+            }
+        }
+    }
+}
+
 // everything after the sorted permutation is known: head flags + order check, unique scatter, face remap
 static int canonical_tail(const float* vin, const uint32_t* perm, int64_t V, const unsigned long long* V_dev, const void* faces_in,
                           int64_t F, const unsigned long long* F_dev, void* verts_out, void* faces_out_i64, void* faces_out_i32,
@@ -642,11 +758,14 @@ static int canonical_tail(const float* vin, const uint32_t* perm, int64_t V, con
                           unsigned long long* totals, cudaStream_t st)
 {
     void* stream = (void*)st;
-    const unsigned gv = (unsigned)((V + 255) / 256);
-    k_heads_checked<<<gv, 256, 0, st>>>(vin, perm, V, V_dev, flags, counts + 2);
-    if (t3d_exclusive_scan_u32_dev(flags, pos, V, V, 1, 0, 0, V_dev, totals, scan_ws, stream)) return 1;
-    T3D_CUDA(cudaMemcpyAsync(counts, totals, 8, cudaMemcpyDeviceToDevice, st));
-    k_scatter_unique<<<gv, 256, 0, st>>>(vin, perm, flags, pos, V, (float*)verts_out, newid, V_dev);
+    {
+        // workspace as in t3d_exclusive_scan_u32_dev: [tile descriptors][ticket], zeroed per use
+        const int64_t nb = (V + SC_TILE - 1) / SC_TILE;
+        const size_t desc_bytes = (size_t)nb * 8;
+        T3D_CUDA(cudaMemsetAsync(scan_ws, 0, desc_bytes + 64, st));
+        k_unique_fused<<<(unsigned)nb, SC_THREADS, 0, st>>>(vin, perm, V, V_dev, (float*)verts_out, newid, (unsigned long long*)scan_ws,
+                                                           (int)nb, (unsigned int*)((char*)scan_ws + desc_bytes), counts + 2, counts);
+    }
     if (F > 0) {
         // totals[1] = invalid faces, totals[2] = faces the compaction has to look at (0 when nothing is invalid)
         const unsigned gf = (unsigned)((F + 255) / 256);
@@ -817,13 +936,16 @@ __global__ void __launch_bounds__(256) k_canon_gkeys(CanonS c)
 
 __global__ void __launch_bounds__(256) k_canon_positions(CanonS c)
 {
+    __shared__ uint32_t s_g[3];
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t nx = (uint32_t)c.sizes[1], ny = (uint32_t)c.sizes[2], nz = (uint32_t)c.sizes[3];
     const unsigned long long V64 = (unsigned long long)nx + ny + nz;
-    if (V64 > c.cap_verts || i >= (uint32_t)V64) return;
+    if (V64 > c.cap_verts) return;
+    if (threadIdx.x == 0) g0_sizes(c, s_g[0], s_g[1], s_g[2]);
+    __syncthreads();
+    if (i >= (uint32_t)V64) return;
     if (nz > c.cap_z) { c.perm[i] = i; return; }       // no z order available: identity, the order check will fail
-    uint32_t gX, gY, gZ;
-    g0_sizes(c, gX, gY, gZ);
+    const uint32_t gX = s_g[0], gY = s_g[1], gZ = s_g[2];
     const uint32_t nG = gX + gY + gZ;
     if (i == 0 && c.n_g0_out) *c.n_g0_out = nG;
     // positions [0, nG): the clamp group in (y, x) order (block order when its sort was not provisioned)
