@@ -238,6 +238,16 @@ int t3d_slab_stitch_faces(void* faces_i64, int64_t cap_faces, const void* gather
  * voxel of the other kind, 0 there, inf if there is none; accumulate != 0 adds into dist_f32.  sampling_host = {sz, sy,
  * sx} (NULL = 1,1,1).  sdf = t3d_edt(invert 0, sign +1) then t3d_edt(invert 1, sign -1, accumulate 1). */
 int64_t t3d_edt_workspace_bytes(int Z, int H, int W);
+/* The two halves of t3d_edt, for z-slab sharding: the x and y passes never look across planes, so every
+ * rank runs t3d_edt_xy on its own slices (dyx_i16 = two (Z,H,W) int16 arrays back to back: y offset, then x offset of
+ * the nearest site in the plane); after the all-to-all transpose z-slabs -> y-slabs, t3d_edt_z runs the z pass and the
+ * final distance on full z columns (Z = all slices, H = rows of the rank's y-slab). */
+int64_t t3d_edt_xy_workspace_bytes(int Z, int H, int W);
+int t3d_edt_xy(const void* occ_bits, int Z, int H, int W, int invert, const double* sampling_host, void* dyx_i16, void* workspace,
+               void* stream);
+int64_t t3d_edt_z_workspace_bytes(int Z, int H, int W);
+int t3d_edt_z(const void* dy_i16, const void* dx_i16, int Z, int H, int W, const double* sampling_host, float sign, int accumulate,
+              void* dist_f32, void* workspace, void* stream);
 int t3d_edt(const void* occ_bits, int Z, int H, int W, int invert, const double* sampling_host, float sign, int accumulate,
             void* dist_f32, void* workspace, void* stream);
 

@@ -83,3 +83,39 @@ def test_surface_from_sdf(eng, oracle):
     if namb == 0:
         key = e[:, 0] * (len(uv) + 1) + e[:, 1]
         assert np.array_equal(np.sort(key), np.sort(e[:, 1] * (len(uv) + 1) + e[:, 0]))   # closed, oriented
+
+
+def _emulated_all_to_all(sends, send_sizes, recvs, recv_sizes):
+    """What edt._exchange does over NCCL, for all ranks living in this process: chunk q of rank r -> chunk r of rank q."""
+    world = len(sends)
+    for r in range(world):
+        so = np.concatenate([[0], np.cumsum(send_sizes[r])])
+        for q in range(world):
+            ro = np.concatenate([[0], np.cumsum(recv_sizes[q])])
+            assert send_sizes[r][q] == recv_sizes[q][r]
+            recvs[q][ro[r]:ro[r + 1]] = sends[r][so[q]:so[q + 1]]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world", [2, 3])
+@pytest.mark.parametrize("shape,sampling", [((19, 23, 40), (1.0, 1.0, 1.0)), ((24, 17, 70), (0.7, 1.3, 0.45))])
+def test_sharded_edt_matches_single_device(eng, shape, sampling, world):
+    """z-slab sharded signed distance (x/y passes per slab, all-to-all transpose, z pass per y-slab, transpose back), all
+    ranks emulated on ONE GPU, must equal the single-device transform bit for bit."""
+    from tomography_3d_reconstructor_b200 import edt, sharded
+    rng = np.random.default_rng(5)
+    Z, H, W = shape
+    vol = random_blobs(rng, shape, 0.45, 1.5)
+    dv = dev_volume(eng, vol)
+    ref = edt.signed_distance(dv, sampling).cpu().numpy()
+    ranges = [sharded.slab_range(Z, r, world) for r in range(world)]
+    ts = [edt.SlabTransform(dv.bits[a:b].contiguous(), Z, a, H, W, sampling, r, world) for r, (a, b) in enumerate(ranges)]
+    for k, invert in enumerate((0, 1)):
+        sends = [t.xy_pass(invert) for t in ts]
+        for c in range(2):
+            _emulated_all_to_all([s[c] for s in sends], [t.send_sizes for t in ts], [t.cols[c] for t in ts], [t.recv_sizes for t in ts])
+        for t in ts:
+            t.z_pass(invert, k)
+    _emulated_all_to_all([t.dist_cols for t in ts], [t.recv_sizes for t in ts], [t.back for t in ts], [t.send_sizes for t in ts])
+    out = torch.cat([t.result() for t in ts]).cpu().numpy()
+    assert np.array_equal(out.view(np.uint32), ref.view(np.uint32))

@@ -99,7 +99,20 @@ def _worker(rank, world, port, q):
             v, f = m
             ok_gather = v.shape[0] == sum(2 + r for r in range(world)) and f.shape[0] == sum(3 + r for r in range(world)) \
                 and float(v[-1, 0]) == world - 1 and int(f[-1, 0]) == world - 1
-        q.put((rank, ok_halo, bases, ok, ok_gather))
+        # the EDT's all-to-all transpose z-slabs -> y-slabs and back (edt.py), on CPU tensors
+        from tomography_3d_reconstructor_b200 import edt
+        Zt, Ht, Wt = 11, 7, 5
+        g16 = (torch.arange(Zt * Ht * Wt, dtype=torch.int32) % 30000).to(torch.int16).reshape(Zt, Ht, Wt)
+        zr, yr, send_sizes, recv_sizes = edt.transpose_plan(Zt, Ht, Wt, rank, world)
+        a, b = zr[rank]
+        ya, yb = yr[rank]
+        cols = torch.empty(Zt * (yb - ya) * Wt, dtype=torch.int16)
+        edt._exchange(edt.pack_rows(g16[a:b], yr), send_sizes, cols, recv_sizes, rank, world, None)
+        ok_fwd = bool(torch.equal(cols.view(Zt, yb - ya, Wt), g16[:, ya:yb, :]))
+        back = torch.empty((b - a) * Ht * Wt, dtype=torch.int16)
+        edt._exchange(cols, recv_sizes, back, send_sizes, rank, world, None)
+        ok_back = bool(torch.equal(edt.unpack_rows(back, b - a, Ht, Wt, yr), g16[a:b]))
+        q.put((rank, ok_halo, bases, ok, ok_gather and ok_fwd and ok_back))
     finally:
         dist.destroy_process_group()
 

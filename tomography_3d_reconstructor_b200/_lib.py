@@ -68,6 +68,10 @@ SIGNATURES = {
                                   _vp, _i, _dbl, _dbl, _i, _u32, _u32, _u32, _u32, _u32, _vp, _vp, _vp, _vp, _vp]),
     "t3d_slab_stitch_faces": (_i, [_vp, _i64, _vp, _i64, _i, _vp]),
     "t3d_edt_workspace_bytes": (_i64, [_i, _i, _i]),
+    "t3d_edt_xy_workspace_bytes": (_i64, [_i, _i, _i]),
+    "t3d_edt_xy": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "t3d_edt_z_workspace_bytes": (_i64, [_i, _i, _i]),
+    "t3d_edt_z": (_i, [_vp, _vp, _i, _i, _i, _vp, _c.c_float, _i, _vp, _vp, _vp]),
     "t3d_edt": (_i, [_vp, _i, _i, _i, _i, _vp, _c.c_float, _i, _vp, _vp, _vp]),
     "t3d_sign_from_f32": (_i, [_vp, _i, _i, _i, _dbl, _vp, _vp]),
     "t3d_mc_vertices_f32": (_i, [_vp, _i, _i, _i, _dbl, _vp, _u32, _u32, _u32, _i, _i, _vp, _vp, _i, _dbl, _dbl, _i, _vp, _vp]),

@@ -94,7 +94,8 @@ __global__ void __launch_bounds__(256) k_edt_x(const uint32_t* __restrict__ bits
 // out: ncomp_in + 1 components (new component first), or the final float distance
 // ------------------------------------------------------------------------------------------------
 struct EdtPass {
-    const int16_t* in;
+    const int16_t* in;  // first existing component
+    const int16_t* in1; // second existing component (ncomp_in > 1)
     int16_t* out;      // (ncomp_in + 1) component arrays, may be null when dist_out is set
     float* dist_out;   // final float32 distance (z pass)
     int64_t vol;       // elements per component array
@@ -114,7 +115,7 @@ __device__ __forceinline__ double site_cost(const EdtPass& p, int64_t idx)
     if (a == EDT_NONE) return INFINITY;
     double f = (double)a * (double)a * p.w0;
     if (p.ncomp_in > 1) {
-        const int b = p.in[p.vol + idx];
+        const int b = p.in1[idx];
         f += (double)b * (double)b * p.w1;
     }
     return f;
@@ -161,7 +162,7 @@ __global__ void __launch_bounds__(128) k_edt_envelope(EdtPass p)
         const int v = sv[(int64_t)j * L];
         const int64_t sidx = base + v * p.stride;
         const int a = p.in[sidx];
-        const int b = p.ncomp_in > 1 ? p.in[p.vol + sidx] : 0;
+        const int b = p.ncomp_in > 1 ? p.in1[sidx] : 0;
         const int dnew = v - q;
         if (p.dist_out) {
             // scipy: dt = (ft - indices) * sampling; sqrt(add.reduce(dt*dt, axis=0)) -- axis order z, y, x
@@ -177,46 +178,99 @@ __global__ void __launch_bounds__(128) k_edt_envelope(EdtPass p)
     }
 }
 
-extern "C" int64_t t3d_edt_workspace_bytes(int Z, int H, int W)
+static inline int64_t a256(int64_t x) { return (x + 255) & ~(int64_t)255; }
+
+static int edt_check(int Z, int H, int W, const char* who)
 {
-    const int64_t vol = (int64_t)Z * H * W;
-    // int16 x offsets (1 comp) + int16 (y,x) offsets (2 comps) + stacks (int32 + double per voxel)
-    return vol * 2 + vol * 4 + vol * 12 + 1024;
+    if (Z <= 0 || H <= 0 || W <= 0) { t3d_set_error("%s: empty volume", who); return 2; }
+    if (Z > 32766 || H > 32766 || W > 32766) { t3d_set_error("%s: extent above 32766", who); return 2; }
+    return 0;
 }
 
-// dist_f32 (Z,H,W): sign * distance from every foreground voxel (bit set; bit clear if invert) to the nearest voxel of
-// the other kind, 0 at the other kind, inf if there is none; accumulate != 0 adds to dist_f32 instead of overwriting.
-// sampling_host: {sz, sy, sx}.  Extents up to 32766 per axis.
-extern "C" int t3d_edt(const void* occ_bits, int Z, int H, int W, int invert, const double* sampling_host, float sign,
-                       int accumulate, void* dist_f32, void* workspace, void* stream)
+// x and y passes: dyx_i16 = two (Z,H,W) int16 arrays back to back, [0] = y offset, [1] = x offset of the nearest site
+// within the voxel's own z plane (EDT_NONE in [0] if the plane has no site).  These passes never look across planes, so
+// a z-slab can run them on its own slices.  workspace: t3d_edt_xy_workspace_bytes.
+extern "C" int64_t t3d_edt_xy_workspace_bytes(int Z, int H, int W)
 {
-    if (Z <= 0 || H <= 0 || W <= 0) { t3d_set_error("t3d_edt: empty volume"); return 2; }
-    if (Z > 32766 || H > 32766 || W > 32766) { t3d_set_error("t3d_edt: extent above 32766"); return 2; }
+    const int64_t vol = (int64_t)Z * H * W;
+    return a256(vol * 2) + a256(vol * 4) + vol * 8 + 1024;   // x offsets, stack sites, stack boundaries
+}
+
+extern "C" int t3d_edt_xy(const void* occ_bits, int Z, int H, int W, int invert, const double* sampling_host, void* dyx_i16,
+                          void* workspace, void* stream)
+{
+    if (int rc = edt_check(Z, H, W, "t3d_edt_xy")) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t vol = (int64_t)Z * H * W;
-    const double sz = sampling_host ? sampling_host[0] : 1.0, sy = sampling_host ? sampling_host[1] : 1.0,
-                 sx = sampling_host ? sampling_host[2] : 1.0;
+    const double sy = sampling_host ? sampling_host[1] : 1.0, sx = sampling_host ? sampling_host[2] : 1.0;
     char* ws = (char*)workspace;
-    int16_t* dx = (int16_t*)ws; ws += (vol * 2 + 255) & ~(int64_t)255;
-    int16_t* dyx = (int16_t*)ws; ws += (vol * 4 + 255) & ~(int64_t)255;
-    int32_t* st_v = (int32_t*)ws; ws += (vol * 4 + 255) & ~(int64_t)255;
+    int16_t* dx = (int16_t*)ws; ws += a256(vol * 2);
+    int32_t* st_v = (int32_t*)ws; ws += a256(vol * 4);
     double* st_z = (double*)ws;
     const int64_t rows = (int64_t)Z * H;
     k_edt_x<<<(unsigned)((rows * 32 + 255) / 256), 256, 0, st>>>((const uint32_t*)occ_bits, rows, W, t3d_wpr(W), invert ? 1 : 0, dx);
     EdtPass p;
     // y pass: lines = (z, x); samples stride W
-    p.in = dx; p.out = dyx; p.dist_out = nullptr; p.vol = vol;
+    p.in = dx; p.in1 = nullptr; p.out = (int16_t*)dyx_i16; p.dist_out = nullptr; p.vol = vol;
     p.n_lines = (int64_t)Z * W; p.inner = W; p.outer_stride = (int64_t)H * W; p.stride = W; p.n = H; p.ncomp_in = 1;
-    p.w_new = sy * sy; p.w0 = sx * sx; p.w1 = 0.0; p.s_new = sy; p.s0 = sx; p.s1 = 0.0; p.st_v = st_v; p.st_z = st_z; p.sign = sign; p.accumulate = 0;
+    p.w_new = sy * sy; p.w0 = sx * sx; p.w1 = 0.0; p.s_new = sy; p.s0 = sx; p.s1 = 0.0; p.st_v = st_v; p.st_z = st_z; p.sign = 1.f;
+    p.accumulate = 0;
     k_edt_envelope<<<(unsigned)((p.n_lines + 127) / 128), 128, 0, st>>>(p);
-    // z pass: lines = (y, x); samples stride H*W; input components (dy, dx)
-    p.in = dyx; p.out = nullptr; p.dist_out = (float*)dist_f32;
-    p.n_lines = (int64_t)H * W; p.inner = (int64_t)H * W; p.outer_stride = 0; p.stride = (int64_t)H * W; p.n = Z; p.ncomp_in = 2;
-    p.w_new = sz * sz; p.w0 = sy * sy; p.w1 = sx * sx; p.s_new = sz; p.s0 = sy; p.s1 = sx; p.accumulate = accumulate ? 1 : 0;
-    k_edt_envelope<<<(unsigned)((p.n_lines + 127) / 128), 128, 0, st>>>(p);
-    T3D_CHECK_LAUNCH("t3d_edt");
-    t3d_count_launches(3);
+    T3D_CHECK_LAUNCH("t3d_edt_xy");
+    t3d_count_launches(2);
     return 0;
+}
+
+// z pass + final distance on full z columns: dy_i16 / dx_i16 (Z,H,W) from t3d_edt_xy (for a sharded run: the y-slab this
+// rank received in the all-to-all transpose, H = rows of that y-slab).  dist_f32 (Z,H,W) = or += sign * distance.
+extern "C" int64_t t3d_edt_z_workspace_bytes(int Z, int H, int W)
+{
+    const int64_t vol = (int64_t)Z * H * W;
+    return a256(vol * 4) + vol * 8 + 1024;
+}
+
+extern "C" int t3d_edt_z(const void* dy_i16, const void* dx_i16, int Z, int H, int W, const double* sampling_host, float sign,
+                         int accumulate, void* dist_f32, void* workspace, void* stream)
+{
+    if (int rc = edt_check(Z, H, W, "t3d_edt_z")) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t vol = (int64_t)Z * H * W;
+    const double sz = sampling_host ? sampling_host[0] : 1.0, sy = sampling_host ? sampling_host[1] : 1.0,
+                 sx = sampling_host ? sampling_host[2] : 1.0;
+    char* ws = (char*)workspace;
+    int32_t* st_v = (int32_t*)ws; ws += a256(vol * 4);
+    double* st_z = (double*)ws;
+    EdtPass p;
+    // lines = (y, x); samples stride H*W; input components (dy, dx)
+    p.in = (const int16_t*)dy_i16; p.in1 = (const int16_t*)dx_i16; p.out = nullptr; p.dist_out = (float*)dist_f32; p.vol = vol;
+    p.n_lines = (int64_t)H * W; p.inner = (int64_t)H * W; p.outer_stride = 0; p.stride = (int64_t)H * W; p.n = Z; p.ncomp_in = 2;
+    p.w_new = sz * sz; p.w0 = sy * sy; p.w1 = sx * sx; p.s_new = sz; p.s0 = sy; p.s1 = sx; p.st_v = st_v; p.st_z = st_z; p.sign = sign;
+    p.accumulate = accumulate ? 1 : 0;
+    k_edt_envelope<<<(unsigned)((p.n_lines + 127) / 128), 128, 0, st>>>(p);
+    T3D_CHECK_LAUNCH("t3d_edt_z");
+    t3d_count_launches(1);
+    return 0;
+}
+
+// dist_f32 (Z,H,W): sign * distance from every foreground voxel (bit set; bit clear if invert) to the nearest voxel of
+// the other kind, 0 at the other kind, inf if there is none; accumulate != 0 adds to dist_f32 instead of overwriting.
+// sampling_host: {sz, sy, sx}.  Extents up to 32766 per axis.
+extern "C" int64_t t3d_edt_workspace_bytes(int Z, int H, int W)
+{
+    const int64_t vol = (int64_t)Z * H * W;
+    const int64_t a = t3d_edt_xy_workspace_bytes(Z, H, W), b = t3d_edt_z_workspace_bytes(Z, H, W);
+    return a256(vol * 4) + (a > b ? a : b);     // (dy, dx) + the larger of the two passes' scratch
+}
+
+extern "C" int t3d_edt(const void* occ_bits, int Z, int H, int W, int invert, const double* sampling_host, float sign,
+                       int accumulate, void* dist_f32, void* workspace, void* stream)
+{
+    if (int rc = edt_check(Z, H, W, "t3d_edt")) return rc;
+    const int64_t vol = (int64_t)Z * H * W;
+    int16_t* dyx = (int16_t*)workspace;
+    char* scratch = (char*)workspace + a256(vol * 4);
+    if (int rc = t3d_edt_xy(occ_bits, Z, H, W, invert, sampling_host, dyx, scratch, stream)) return rc;
+    return t3d_edt_z(dyx, dyx + vol, Z, H, W, sampling_host, sign, accumulate, dist_f32, scratch, stream);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -41,3 +41,124 @@ def signed_distance(dv: engine.DeviceVolume, sampling=(1.0, 1.0, 1.0)) -> torch.
     check(L.t3d_edt(engine._p(dv.bits), Z, H, W, 0, s3, 1.0, 0, engine._p(out), engine._p(ws), engine._stream()), "t3d_edt")
     check(L.t3d_edt(engine._p(dv.bits), Z, H, W, 1, s3, -1.0, 1, engine._p(out), engine._p(ws), engine._stream()), "t3d_edt")
     return out
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# z-slab sharded transform: x/y passes on the own slices, ONE all-to-all transpose z-slabs -> y-slabs,
+# z pass on full columns, all-to-all back.  NVLink traffic: 4 B/voxel per transform forward (two int16 offsets), and
+# 4 B/voxel back for the float32 result -- edt(occ) and edt(~occ) of a signed distance share the way back.
+# ----------------------------------------------------------------------------------------------------------------
+def _ranges(n: int, world: int):
+    from .sharded import slab_range
+    return [slab_range(n, r, world) for r in range(world)]
+
+
+def transpose_plan(Zg: int, H: int, W: int, rank: int, world: int):
+    """Split sizes (in elements) of the z-slab -> y-slab all-to-all for one (n,H,W) array.
+
+    send chunk q = own slices x rows of y-slab q;  recv chunk r = slices of rank r x own rows.  Because ranks own
+    contiguous slice ranges in rank order, the receive buffer IS the (Zg, Hq, W) array of the own y-slab."""
+    zr, yr = _ranges(Zg, world), _ranges(H, world)
+    n = zr[rank][1] - zr[rank][0]
+    hq = yr[rank][1] - yr[rank][0]
+    send = [n * (b - a) * W for a, b in yr]
+    recv = [(b - a) * hq * W for a, b in zr]
+    return zr, yr, send, recv
+
+
+def _exchange(send_buf, send_sizes, recv_buf, recv_sizes, rank, world, group):
+    """All-to-all of variable-sized contiguous chunks as one grouped batch of point-to-point operations (what NCCL's
+    all-to-all is; also works on gloo)."""
+    import torch.distributed as dist
+    so = [0]
+    for s in send_sizes:
+        so.append(so[-1] + s)
+    ro = [0]
+    for s in recv_sizes:
+        ro.append(ro[-1] + s)
+    recv_buf[ro[rank]:ro[rank + 1]].copy_(send_buf[so[rank]:so[rank + 1]])
+    ops = []
+    for q in range(world):
+        if q == rank:
+            continue
+        if recv_sizes[q]:
+            ops.append(dist.P2POp(dist.irecv, recv_buf[ro[q]:ro[q + 1]], q, group))
+        if send_sizes[q]:
+            ops.append(dist.P2POp(dist.isend, send_buf[so[q]:so[q + 1]], q, group))
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+
+
+def pack_rows(arr, yr):
+    """(n,H,W) -> flat [q][z][y in y-slab q][x] (the send layout of the forward transpose)."""
+    return torch.cat([arr[:, a:b, :].reshape(-1) for a, b in yr])
+
+
+def unpack_rows(flat, n: int, H: int, W: int, yr):
+    """Inverse of pack_rows (the receive layout of the backward transpose)."""
+    out = torch.empty((n, H, W), dtype=flat.dtype, device=flat.device)
+    o = 0
+    for a, b in yr:
+        m = n * (b - a) * W
+        out[:, a:b, :] = flat[o:o + m].view(n, b - a, W)
+        o += m
+    return out
+
+
+class SlabTransform:
+    """Per-rank state of the sharded transform, split into the phases between the collectives (so that tests can run
+    all ranks of a job in one process and move the chunks themselves)."""
+
+    def __init__(self, bits_slab: torch.Tensor, Zg: int, z0: int, H: int, W: int, sampling, rank: int, world: int):
+        L = engine._L()
+        self.bits, self.Zg, self.H, self.W, self.rank, self.world = bits_slab, Zg, H, W, rank, world
+        self.n = n = int(bits_slab.shape[0])
+        dev = bits_slab.device
+        self.zr, self.yr, self.send_sizes, self.recv_sizes = transpose_plan(Zg, H, W, rank, world)
+        if self.zr[rank] != (z0, z0 + n):
+            raise ValueError("slab [%d,%d) is not slab_range(%d, %d, %d)" % (z0, z0 + n, Zg, rank, world))
+        self.hq = hq = self.yr[rank][1] - self.yr[rank][0]
+        self.s3 = _sampling(sampling)
+        self.dyx = torch.empty((2, n, H, W), dtype=torch.int16, device=dev)
+        self.ws1 = torch.empty(int(L.t3d_edt_xy_workspace_bytes(n, H, W)) // 8 + 1, dtype=torch.int64, device=dev)
+        self.cols = [torch.empty(Zg * hq * W, dtype=torch.int16, device=dev) for _ in range(2)]
+        self.dist_cols = torch.zeros(Zg * hq * W, dtype=torch.float32, device=dev)
+        self.ws2 = torch.empty(int(L.t3d_edt_z_workspace_bytes(Zg, max(hq, 1), W)) // 8 + 1, dtype=torch.int64, device=dev)
+        self.back = torch.empty(n * H * W, dtype=torch.float32, device=dev)
+
+    def xy_pass(self, invert: int):
+        """x and y passes on the own slices; returns the two send buffers (y offsets, x offsets) of the forward transpose."""
+        p = engine._p
+        check(engine._L().t3d_edt_xy(p(self.bits), self.n, self.H, self.W, invert, self.s3, p(self.dyx), p(self.ws1),
+                                     engine._stream()), "t3d_edt_xy")
+        return [pack_rows(self.dyx[c], self.yr) for c in range(2)]
+
+    def z_pass(self, invert: int, accumulate: int) -> None:
+        """z pass + final distance on the received full columns of the own y-slab."""
+        if not self.hq:
+            return
+        p = engine._p
+        check(engine._L().t3d_edt_z(p(self.cols[0]), p(self.cols[1]), self.Zg, self.hq, self.W, self.s3, -1.0 if invert else 1.0,
+                                    accumulate, p(self.dist_cols), p(self.ws2), engine._stream()), "t3d_edt_z")
+
+    def result(self) -> torch.Tensor:
+        return unpack_rows(self.back, self.n, self.H, self.W, self.yr)
+
+
+def signed_distance_sharded(bits_slab: torch.Tensor, Zg: int, z0: int, H: int, W: int, sampling=(1.0, 1.0, 1.0), group=None,
+                            signed: bool = True) -> torch.Tensor:
+    """bits_slab: this rank's packed slices [z0, z0+n) (n, H, words) of the global (Zg,H,W) occupancy.
+    Returns float32 (n,H,W): this rank's slices of edt(occ) - edt(~occ) (signed) or of edt(occ), bit-identical to the
+    single-device transform of the whole volume."""
+    import torch.distributed as dist
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    t = SlabTransform(bits_slab, Zg, z0, H, W, sampling, rank, world)
+    for k, invert in enumerate((0, 1) if signed else (0,)):
+        sends = t.xy_pass(invert)
+        for c in range(2):   # forward transpose of the y and x offsets
+            _exchange(sends[c], t.send_sizes, t.cols[c], t.recv_sizes, rank, world, group)
+        t.z_pass(invert, k)
+    # backward transpose: chunk r of the y-slab result = slices of rank r (contiguous), received as [q][z][y in q][x]
+    _exchange(t.dist_cols, t.recv_sizes, t.back, t.send_sizes, rank, world, group)
+    return t.result()
