@@ -70,12 +70,16 @@ def _exchange(send_buf, send_sizes, recv_buf, recv_sizes, rank, world, group):
     """All-to-all of variable-sized contiguous chunks as one grouped batch of point-to-point operations (what NCCL's
     all-to-all is; also works on gloo)."""
     import torch.distributed as dist
+    # as raw bytes: NCCL has no 16-bit integer type
+    isz = send_buf.element_size()
+    send_buf, recv_buf = send_buf.view(torch.uint8), recv_buf.view(torch.uint8)
     so = [0]
     for s in send_sizes:
-        so.append(so[-1] + s)
+        so.append(so[-1] + s * isz)
     ro = [0]
     for s in recv_sizes:
-        ro.append(ro[-1] + s)
+        ro.append(ro[-1] + s * isz)
+    send_sizes, recv_sizes = [s * isz for s in send_sizes], [s * isz for s in recv_sizes]
     recv_buf[ro[rank]:ro[rank + 1]].copy_(send_buf[so[rank]:so[rank + 1]])
     ops = []
     for q in range(world):

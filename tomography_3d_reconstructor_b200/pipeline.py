@@ -97,6 +97,38 @@ def reconstruct(masks_u8: torch.Tensor, threshold: int, side_counts, total_depth
     }
 
 
+def sdf_sampling(depths: np.ndarray, mm_y: float, mm_x: float):
+    """Voxel pitch (z, y, x) in mm used for the distance transform: the mean slice depth along z (the separable transform
+    needs one pitch per axis; the z coordinates of the vertices still go through the exact variable-depth map)."""
+    dz = float(np.mean(depths)) if len(depths) else 1.0
+    return (dz if dz > 0 else 1.0, float(mm_y), float(mm_x))
+
+
+def reconstruct_sdf(masks_u8: torch.Tensor, threshold: int, side_counts, total_depth_mm: float, x_length_mm: float,
+                    y_length_mm: float, iterations: int = 3, close_ends: bool = True, level: float = 0.0,
+                    sampling=None) -> Dict:
+    """SDF variant of reconstruct() (BASELINE configs 3/4; additive): voxel grid -> smoothing -> exact
+    signed Euclidean distance (mm, positive inside) -> marching cubes on the distance field at `level` -> mesh + volumes.
+    Returns reconstruct()'s dict plus "sdf" (float32 CUDA tensor)."""
+    from . import edt
+    Z, H, W = (int(s) for s in masks_u8.shape)
+    mm_x, mm_y = x_length_mm / W, y_length_mm / H
+    depths = slice_depths(total_depth_mm, *side_counts)
+    dv = engine.pack_and_close(masks_u8, threshold, close_ends)
+    sm = engine.smooth(dv, iterations, True)
+    sdf = edt.signed_distance(sm, sampling or sdf_sampling(depths, mm_y, mm_x))
+    mesh = engine.extract_surface(None, depths, mm_y, mm_x, False, False, field=sdf, level=level)
+    signed_volume, area = mesh.measures()
+    raw_counts, sm_counts = dv.slice_counts(), sm.slice_counts()
+    return {
+        "mesh": mesh, "sdf": sdf,
+        "voxel_volume_mm3": variable_depth_volume(raw_counts, mm_x, mm_y, depths),
+        "processed_voxel_volume_mm3": variable_depth_volume(sm_counts, mm_x, mm_y, depths),
+        "mesh_volume_mm3": abs(signed_volume), "surface_area_mm2": area, "bbox_index": dv.bbox(),
+        "active_voxels": int(raw_counts.sum()), "slice_depths": depths,
+    }
+
+
 # ----------------------------------------------------------------------------------------------------------------
 # fused path: the whole step as ONE enqueue (t3d_reconstruct), captured in a CUDA graph
 # ----------------------------------------------------------------------------------------------------------------

@@ -472,6 +472,112 @@ def assemble(plan: FusedSlabPlan, h: np.ndarray) -> Dict:
     return out
 
 
+# ----------------------------------------------------------------------------------------------------------------
+# SDF variant (BASELINE configs 3/4): smoothing on z-slabs as above, exact signed distance through the all-to-all
+# transpose of edt.py, marching cubes on the distance field with ONE float32 halo plane from the next rank, the same
+# ghost-plane stitching.  Written as phases so that tests can run every rank of a job in one process.
+# ----------------------------------------------------------------------------------------------------------------
+def sdf_slab_smooth(s: Slab, iterations: int = 3):
+    """After slab_pack + the halo exchange: gap fill and smoothing on the extended buffer.  Returns the own smoothed
+    planes as a DeviceVolume and sets the per-slice counts / bbox tensor on the slab."""
+    L = engine._L()
+    p, st = engine._p, engine._stream
+    hl, n, hh, H, W = s.hl, s.n, s.hh, s.H, s.W
+    Zx = hl + n + hh
+    gf = torch.empty_like(s.ext)
+    cnt_raw = torch.empty(Zx, dtype=torch.int64, device=s.dev)
+    engine.check(L.t3d_gap_fill(p(s.ext), p(gf), None, None, Zx, H, W, p(cnt_raw), st()), "t3d_gap_fill")
+    smx = engine.smooth(engine.DeviceVolume(gf, Zx, H, W, cnt_raw), iterations, True)
+    s.cnt_raw, s.cnt_sm = cnt_raw[hl:hl + n], smx.counts_tensor()[hl:hl + n]
+    s.local = engine.DeviceVolume(gf[hl:hl + n], n, H, W, s.cnt_raw).bbox_tensor()     # kept for sdf_slab_surface
+    return engine.DeviceVolume(smx.bits[hl:hl + n].contiguous(), n, H, W)
+
+
+def exchange_sdf_plane(sdf_own: torch.Tensor, rank: int, world: int, group=None) -> Optional[torch.Tensor]:
+    """First own plane -> previous rank; returns the next rank's first plane (None on the last rank)."""
+    nxt = torch.empty_like(sdf_own[0]) if rank + 1 < world else None
+    ops = []
+    if nxt is not None:
+        ops.append(dist.P2POp(dist.irecv, nxt, rank + 1, group))
+    if rank > 0:
+        ops.append(dist.P2POp(dist.isend, sdf_own[0].contiguous(), rank - 1, group))
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+    return nxt
+
+
+def sdf_slab_surface(s: Slab, sdf_own: torch.Tensor, sdf_next: Optional[torch.Tensor], side_counts, total_depth_mm: float,
+                     x_length_mm: float, y_length_mm: float, level: float = 0.0) -> torch.Tensor:
+    """Marching cubes on the own planes of the distance field (+ the next rank's first plane as ghost plane), local
+    canonical mesh.  Returns the vector of slab_local()."""
+    n, H, W, dev = s.n, s.H, s.W, s.dev
+    mm_x, mm_y = x_length_mm / W, y_length_mm / H
+    depths = pipeline.slice_depths(total_depth_mm, *side_counts)
+    field = torch.cat([sdf_own, sdf_next[None]]) if sdf_next is not None else sdf_own
+    bbox_t = s.local
+    try:
+        mesh = engine.extract_surface(None, depths, mm_y, mm_x, False, False, canonical="async", z_begin=0,
+                                      z_end=n if sdf_next is not None else -1, z_offset=s.z0, field=field.contiguous(), level=level)
+        meas = engine.mesh_measure_async(*mesh.raw)
+        counts_mesh = mesh.counts_dev
+    except RuntimeError:       # this slab holds no surface
+        mesh, meas = None, torch.zeros(2, dtype=torch.float64, device=dev)
+        counts_mesh = torch.zeros(3, dtype=torch.int64, device=dev)
+    s.mesh = mesh
+    cum, adj = engine.z_map_arrays(depths, False)
+    zero = torch.zeros((), dtype=torch.int64, device=dev)
+    n_ghost = n_lead = zero
+    if mesh is not None:
+        vz = mesh._verts[:, 0]
+        valid = torch.arange(vz.shape[0], device=dev) < counts_mesh[0]
+        if s.z1 < s.Zg:
+            n_ghost = ((vz == float(z_map_value(s.z1, cum, adj))) & valid).sum()
+        if s.z0 > 0:
+            n_lead = ((vz == float(z_map_value(s.z0, cum, adj))) & valid).sum()
+    s.local = torch.cat([counts_mesh, n_ghost.reshape(1), n_lead.reshape(1), meas.view(torch.int64), bbox_t.to(torch.int64)])
+    return s.local
+
+
+def reconstruct_sdf(masks_u8: torch.Tensor, Zg: int, z0: int, threshold: int, side_counts, total_depth_mm: float,
+                    x_length_mm: float, y_length_mm: float, iterations: int = 3, level: float = 0.0, sampling=None,
+                    group=None) -> Dict:
+    """z-slab sharded pipeline.reconstruct_sdf: every rank passes its slices [z0, z0+n) of the global stack and gets its
+    slab of the stitched mesh (+ "sdf": its slices of the distance field)."""
+    from . import edt
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    s = slab_pack(masks_u8, Zg, z0, threshold, world)
+    if world > 1:
+        exchange_halos(s.ext, s.hl, s.n, s.hh, rank, world, group)
+    sm = sdf_slab_smooth(s, iterations)
+    depths = pipeline.slice_depths(total_depth_mm, *side_counts)
+    samp = sampling or pipeline.sdf_sampling(depths, y_length_mm / s.H, x_length_mm / s.W)
+    sdf = edt.signed_distance_sharded(sm.bits, Zg, z0, s.H, s.W, samp, group) if world > 1 else edt.signed_distance(sm, samp)
+    nxt = exchange_sdf_plane(sdf, rank, world, group) if world > 1 else None
+    local = sdf_slab_surface(s, sdf, nxt, side_counts, total_depth_mm, x_length_mm, y_length_mm, level)
+    sizes = [slab_range(Zg, r, world) for r in range(world)]
+    nmax = max(e - b for b, e in sizes)
+    nl = int(local.numel())
+    msg = torch.zeros(nl + 2 * nmax, dtype=torch.int64, device=s.dev)
+    msg[:nl] = local
+    msg[nl:nl + s.n] = s.cnt_raw
+    msg[nl + nmax:nl + nmax + s.n] = s.cnt_sm
+    if world > 1:
+        allmsg = torch.empty((world, nl + 2 * nmax), dtype=torch.int64, device=s.dev)
+        dist.all_gather_into_tensor(allmsg, msg, group=group)
+    else:
+        allmsg = msg[None]
+    hm = allmsg.cpu()
+    host = hm[:, :nl].contiguous()
+    hc = hm[:, nl:].numpy()
+    raw_counts = np.concatenate([hc[r, :e - b] for r, (b, e) in enumerate(sizes)]).astype(np.int64)
+    sm_counts = np.concatenate([hc[r, nmax:nmax + e - b] for r, (b, e) in enumerate(sizes)]).astype(np.int64)
+    out = finalize(s, rank, host, raw_counts, sm_counts, [b for b, _ in sizes], side_counts, total_depth_mm, x_length_mm,
+                   y_length_mm)
+    out["sdf"] = sdf
+    return out
+
+
 class _MeshView:
     """Shape-compatible stand-in for engine.DeviceMesh in bench.py: this rank's slab of the stitched mesh."""
 
