@@ -254,3 +254,25 @@ def test_sharded_sdf_pipeline_stitches_to_the_single_gpu_mesh(eng, oracle, world
     assert abs(o["mesh_volume_mm3"] - ref["mesh_volume_mm3"]) <= 1e-9 * ref["mesh_volume_mm3"]
     # the distance-field surface encloses about the same volume as the voxel count (sanity of the whole SDF path)
     assert abs(ref["mesh_volume_mm3"] - ref["processed_voxel_volume_mm3"]) < 0.05 * ref["processed_voxel_volume_mm3"]
+
+
+def test_batch_of_independent_phantoms_matches_the_oracle(eng, oracle):
+    """BASELINE configs[2] in miniature: independent random ellipsoid phantoms through batch.reconstruct_batch (one shared
+    plan + CUDA graph, items copied into its input buffer) against the oracle, item by item; two 'ranks' cover the batch."""
+    from tomography_3d_reconstructor_b200 import batch, pipeline
+    n, count = 40, 5
+    radii, centres = batch.phantom_params(count, n)
+    dev = torch.device("cuda", 0)
+    stacks = [batch.phantom_u8(n, radii[i], centres[i], dev) for i in range(count)]
+    sides = (5, 30, 5)
+    phys = (6.0, 143.1, 95.03)
+    pipeline._plans.clear(); pipeline._hints.clear()
+    got = {}
+    for rank in range(2):
+        got.update(batch.reconstruct_batch(stacks, 200, sides, *phys, rank=rank, world=2))
+    assert sorted(got) == list(range(count))
+    for i in range(count):
+        ref = oracle.reference_pipeline(stacks[i].cpu().numpy(), 200, sides, *phys)
+        assert np.array_equal(got[i]["vertices"], ref["vertices"]) and np.array_equal(got[i]["faces"], ref["faces"])
+        assert got[i]["voxel_volume_mm3"] == ref["voxel_volume"] and got[i]["processed_voxel_volume_mm3"] == ref["processed_volume"]
+        assert abs(got[i]["mesh_volume_mm3"] - ref["mesh_volume"]) <= 1e-6 * ref["mesh_volume"]

@@ -73,3 +73,17 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
     with pytest.raises(_lib.T3DError, match="no CPU fallback"):
         _lib.load()
+
+
+def test_batch_assignment_partitions_the_items():
+    from tomography_3d_reconstructor_b200 import batch
+    for count in (0, 1, 7, 256):
+        for world in (1, 2, 3, 8):
+            parts = [batch.my_items(count, r, world) for r in range(world)]
+            assert sorted(i for p in parts for i in p) == list(range(count))
+            assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
+    radii, centres = batch.phantom_params(256, 256)
+    assert radii.shape == (256, 3) and radii.min() >= 0.2 * 256 and radii.max() <= 0.45 * 256
+    assert np.abs(centres - 128).max() <= 0.05 * 256
+    r2, c2 = batch.phantom_params(256, 256)
+    assert np.array_equal(radii, r2) and np.array_equal(centres, c2)      # deterministic (rng 1234)
