@@ -26,16 +26,24 @@ def slice_depths(total_depth_mm: float, side_0: int, side_1: int, side_2: int) -
     return np.array([d0] * side_0 + [d1] * side_1 + [d2] * side_2)
 
 
-def variable_depth_volume(counts: np.ndarray, mm_x: float, mm_y: float, depths: np.ndarray) -> float:
-    """volume_calculator.py:23-35 on exact per-slice counts, same float64 order."""
+def volume_weights(mm_x: float, mm_y: float, depths: np.ndarray) -> np.ndarray:
+    """Per-slice voxel volume `mm_x * mm_y * depth[z]` exactly as volume_calculator.py:31-33 forms it."""
+    return (mm_x * mm_y) * np.asarray(depths, dtype=np.float64)
+
+
+def variable_depth_volume(counts: np.ndarray, mm_x: float, mm_y: float, depths: np.ndarray, weights: np.ndarray = None) -> float:
+    """volume_calculator.py:23-35 on exact per-slice counts, same float64 order.  `weights` = volume_weights(...) cached
+    by the caller (the fused plans call this between two steps, with the GPU idle)."""
     if len(depths) == 0:
         return 0.0
     n = min(len(counts), len(depths))
     if n == 0:
         return 0.0
+    if weights is None:
+        weights = volume_weights(mm_x, mm_y, depths)
     # the reference's loop `total += count[z] * (mm_x * mm_y * depth[z])`, vectorised without changing a bit:
     # the products are the same float64 operations and np.cumsum accumulates strictly left to right
-    prod = np.asarray(counts[:n], dtype=np.int64).astype(np.float64) * ((mm_x * mm_y) * np.asarray(depths[:n], dtype=np.float64))
+    prod = np.asarray(counts[:n]).astype(np.float64) * weights[:n]
     return float(np.cumsum(prod)[-1])
 
 
@@ -149,6 +157,7 @@ class FusedPlan:
         self.threshold, self.close_ends, self.add_padding = int(threshold), bool(close_ends), bool(add_padding)
         self.mm_x, self.mm_y = x_length_mm / W, y_length_mm / H
         self.depths = slice_depths(total_depth_mm, *side_counts)
+        self.vol_weights = volume_weights(self.mm_x, self.mm_y, self.depths)
         stages = engine.morph_stages(iterations, True)
         self.n_stages = len(stages)
         self.erode_mask = sum(1 << k for k, er in enumerate(stages) if er)
@@ -275,13 +284,13 @@ def reconstruct_fused(masks_u8: torch.Tensor, threshold: int, side_counts, total
     vol_area = r[R_VOLUME:R_VOLUME + 2].view(np.float64)
     mesh._measures = (float(vol_area[0]), float(vol_area[1]))
     mesh.n_active, mesh.n_raw = int(r[R_NACTIVE]), (int(r[R_VRAW]), int(r[R_NT]))
-    raw_counts = r[R_COUNTS:R_COUNTS + Z].astype(np.int64)
-    sm_counts = r[R_COUNTS + Z:R_COUNTS + 2 * Z].astype(np.int64)
+    raw_counts = r[R_COUNTS:R_COUNTS + Z]
+    sm_counts = r[R_COUNTS + Z:R_COUNTS + 2 * Z]
     bb = tuple(int(v) for v in r[R_BBOX:R_BBOX + 3].view(np.int32))
     return {
         "mesh": mesh,
-        "voxel_volume_mm3": variable_depth_volume(raw_counts, plan.mm_x, plan.mm_y, plan.depths),
-        "processed_voxel_volume_mm3": variable_depth_volume(sm_counts, plan.mm_x, plan.mm_y, plan.depths),
+        "voxel_volume_mm3": variable_depth_volume(raw_counts, plan.mm_x, plan.mm_y, plan.depths, plan.vol_weights),
+        "processed_voxel_volume_mm3": variable_depth_volume(sm_counts, plan.mm_x, plan.mm_y, plan.depths, plan.vol_weights),
         "mesh_volume_mm3": abs(float(vol_area[0])),
         "surface_area_mm2": float(vol_area[1]),
         "bbox_index": bb if bb[1] >= 0 else None,

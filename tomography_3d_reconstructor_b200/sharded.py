@@ -167,42 +167,45 @@ def slab_local(s: Slab, side_counts, total_depth_mm: float, x_length_mm: float, 
     return s.local
 
 
-def finalize(s: Slab, rank: int, host: torch.Tensor, raw_counts: np.ndarray, sm_counts: np.ndarray, slab_starts: List[int],
-             side_counts, total_depth_mm: float, x_length_mm: float, y_length_mm: float, stitched=None) -> Dict:
-    """Phase 5: host[r] = the vector of slab_local() of every rank; counts = global per-slice voxel counts.
-    stitched = (capacity-sized canonical verts, faces already carrying global ids) from the fused path."""
+def finalize(s: Slab, rank: int, host, raw_counts: np.ndarray, sm_counts: np.ndarray, slab_starts: List[int],
+             side_counts, total_depth_mm: float, x_length_mm: float, y_length_mm: float, stitched=None, depths=None,
+             vol_weights=None) -> Dict:
+    """Phase 5: host[r] = the vector of slab_local() of every rank (int64, torch or numpy); counts = global per-slice
+    voxel counts.  stitched = (capacity-sized canonical verts, faces already carrying global ids) from the fused path.
+    Plain numpy / Python on purpose: this runs on the host between two steps, with the GPU idle."""
     mm_x, mm_y = x_length_mm / s.W, y_length_mm / s.H
-    depths = pipeline.slice_depths(total_depth_mm, *side_counts)
-    per_rank = [(int(host[r, 0]), int(host[r, 3]), int(host[r, 4])) for r in range(host.shape[0])]
+    if depths is None:
+        depths = pipeline.slice_depths(total_depth_mm, *side_counts)
+    h = host.numpy() if isinstance(host, torch.Tensor) else np.asarray(host)
+    rows = h.tolist()
+    per_rank = [(row[0], row[3], row[4]) for row in rows]
     bases, consistent = stitch_offsets(per_rank)
-    consistent = consistent and not bool(host[:, 2].any())   # a rank whose fast ordering failed needs the general path
-    meas_all = host[:, 5:7].contiguous().view(torch.float64)
+    consistent = consistent and not any(row[2] for row in rows)   # a rank whose fast ordering failed needs the general path
+    meas_all = np.ascontiguousarray(h[:, 5:7]).view(np.float64)
     signed_volume, area = float(meas_all[:, 0].sum()), float(meas_all[:, 1].sum())
-    bbs = host[:, 7:13].numpy().copy()
-    nonempty = bbs[:, 1] >= 0
     bbox = None
-    if nonempty.any():
-        bbs[:, 0] += np.asarray(slab_starts)
-        bbs[:, 1] += np.asarray(slab_starts)
-        q = bbs[nonempty]
-        bbox = (int(q[:, 0].min()), int(q[:, 1].max()), int(q[:, 2].min()), int(q[:, 3].max()), int(q[:, 4].min()),
-                int(q[:, 5].max()))
+    nonempty = [r for r, row in enumerate(rows) if row[8] >= 0]
+    if nonempty:
+        bbox = (min(rows[r][7] + slab_starts[r] for r in nonempty), max(rows[r][8] + slab_starts[r] for r in nonempty),
+                min(rows[r][9] for r in nonempty), max(rows[r][10] for r in nonempty),
+                min(rows[r][11] for r in nonempty), max(rows[r][12] for r in nonempty))
     v_own = per_rank[rank][0] - per_rank[rank][1]
+    n_faces = rows[rank][1]
     if stitched is not None:
-        verts_own, faces_global = stitched[0][:v_own], stitched[1][:int(host[rank, 1])]
+        verts_own, faces_global = stitched[0][:v_own], stitched[1][:n_faces]
     elif s.mesh is not None:
-        s.mesh.set_sizes(per_rank[rank][0], int(host[rank, 1]), 0)
+        s.mesh.set_sizes(per_rank[rank][0], n_faces, 0)
         verts_own = s.mesh._verts[:v_own]
         faces_global = s.mesh._faces + bases[rank]
     else:
         verts_own = torch.empty((0, 3), dtype=torch.float32, device=s.dev)
         faces_global = torch.empty((0, 3), dtype=torch.int64, device=s.dev)
-    total_v, total_f = sum(v - g for v, g, _ in per_rank), int(host[:, 1].sum())
+    total_v, total_f = sum(v - g for v, g, _ in per_rank), sum(row[1] for row in rows)
     return {
         "verts": verts_own, "faces": faces_global, "vertex_base": bases[rank], "stitch_consistent": consistent,
         "total_vertices": total_v, "total_faces": total_f,
-        "voxel_volume_mm3": pipeline.variable_depth_volume(raw_counts, mm_x, mm_y, depths),
-        "processed_voxel_volume_mm3": pipeline.variable_depth_volume(sm_counts, mm_x, mm_y, depths),
+        "voxel_volume_mm3": pipeline.variable_depth_volume(raw_counts, mm_x, mm_y, depths, vol_weights),
+        "processed_voxel_volume_mm3": pipeline.variable_depth_volume(sm_counts, mm_x, mm_y, depths, vol_weights),
         "mesh_volume_mm3": abs(signed_volume), "surface_area_mm2": area, "bbox_index": bbox,
         "active_voxels": int(raw_counts.sum()), "slice_depths": depths,
         "mesh": _MeshView(verts_own, faces_global, total_v, total_f), "local_mesh": s.mesh,
@@ -265,6 +268,7 @@ class FusedSlabPlan:
         self.side_counts, self.phys = tuple(side_counts), (float(total_depth_mm), float(x_length_mm), float(y_length_mm))
         self.mm_x, self.mm_y = x_length_mm / W, y_length_mm / H
         self.depths = pipeline.slice_depths(total_depth_mm, *side_counts)
+        self.vol_weights = pipeline.volume_weights(self.mm_x, self.mm_y, self.depths)
         stages = engine.morph_stages(iterations, True)
         self.n_stages = len(stages)
         self.erode_mask = sum(1 << k for k, er in enumerate(stages) if er)
@@ -300,6 +304,17 @@ class FusedSlabPlan:
         self.gathered = torch.zeros((world, self.stride), dtype=torch.int64, device=device)
         self.host = torch.zeros((world, self.stride), dtype=torch.int64, pin_memory=True)
         self.graph, self.graph_ptr = None, None
+        # where every rank's own per-slice counts sit in its result block (raw, then smoothed)
+        self.raw_spans, self.sm_spans = [], []
+        for b_, e in self.sizes:
+            hl_r, hh_r = (HALO if b_ > 0 else 0), (HALO if e < Zg else 0)
+            zx_r = hl_r + (e - b_) + hh_r
+            c0 = pipeline.R_COUNTS
+            self.raw_spans.append((c0 + hl_r, c0 + hl_r + (e - b_)))
+            self.sm_spans.append((c0 + zx_r + hl_r, c0 + zx_r + hl_r + (e - b_)))
+        self.slab_starts = [b_ for b_, _ in self.sizes]
+        self.slab_stub = Slab()
+        self.slab_stub.H, self.slab_stub.W, self.slab_stub.dev, self.slab_stub.mesh = self.H, self.W, device, None
 
     def pack(self, masks_u8: torch.Tensor) -> None:
         """Own slices -> planes [hl, hl+n) of the extended buffer; the holes of the global end slices are filled on the
@@ -450,24 +465,17 @@ def reconstruct_host(masks_host: np.ndarray, Zg: int, z0: int, threshold: int, s
 def assemble(plan: FusedSlabPlan, h: np.ndarray) -> Dict:
     """Result dict of reconstruct() from the gathered result blocks h (world x stride int64, host)."""
     R = pipeline
-    Zg, world = plan.Zg, plan.world
+    world = plan.world
     # the small table finalize() works on: [V', F', unverified, ghost, lead, volume bits, area bits, bbox x 6]
-    table = np.zeros((world, 13), dtype=np.int64)
-    raw_parts, sm_parts = [], []
-    for r, (b, e) in enumerate(plan.sizes):
-        hl_r, hh_r = (HALO if b > 0 else 0), (HALO if e < Zg else 0)
-        Zx_r = hl_r + (e - b) + hh_r
-        row = h[r]
-        table[r, :5] = (row[R.R_VCANON], row[R.R_FCANON], row[R.R_UNVERIFIED], row[R_NGHOST], row[R_NLEAD])
-        table[r, 5:7] = row[R.R_VOLUME:R.R_VOLUME + 2]
-        table[r, 7:13] = row[R.R_BBOX:R.R_BBOX + 3].view(np.int32)
-        raw_parts.append(row[R.R_COUNTS + hl_r:R.R_COUNTS + hl_r + (e - b)])
-        sm_parts.append(row[R.R_COUNTS + Zx_r + hl_r:R.R_COUNTS + Zx_r + hl_r + (e - b)])
-    s = Slab()
-    s.H, s.W, s.dev, s.mesh = plan.H, plan.W, plan.dev, None
-    out = finalize(s, plan.rank, torch.from_numpy(table), np.concatenate(raw_parts).astype(np.int64),
-                   np.concatenate(sm_parts).astype(np.int64), [b for b, _ in plan.sizes], plan.side_counts, *plan.phys,
-                   stitched=(plan.verts, plan.faces))
+    table = np.empty((world, 13), dtype=np.int64)
+    table[:, 0] = h[:, R.R_VCANON]; table[:, 1] = h[:, R.R_FCANON]; table[:, 2] = h[:, R.R_UNVERIFIED]
+    table[:, 3] = h[:, R_NGHOST]; table[:, 4] = h[:, R_NLEAD]
+    table[:, 5:7] = h[:, R.R_VOLUME:R.R_VOLUME + 2]
+    table[:, 7:13] = np.ascontiguousarray(h[:, R.R_BBOX:R.R_BBOX + 3]).view(np.int32)
+    raw_counts = np.concatenate([h[r, a:b] for r, (a, b) in enumerate(plan.raw_spans)])
+    sm_counts = np.concatenate([h[r, a:b] for r, (a, b) in enumerate(plan.sm_spans)])
+    out = finalize(plan.slab_stub, plan.rank, table, raw_counts, sm_counts, plan.slab_starts, plan.side_counts, *plan.phys,
+                   stitched=(plan.verts, plan.faces), depths=plan.depths, vol_weights=plan.vol_weights)
     out["n_ambiguous"] = out["mesh"].n_ambiguous = int(h[:, R.R_NAMBIGUOUS].sum())
     return out
 
