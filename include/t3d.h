@@ -159,7 +159,8 @@ int t3d_mc_emit_dev(const void* sign_bits, int Zs, int Hs, int Ws, int z_begin, 
 int t3d_mc_vertices_dev(const void* occ_bits, int Z, int H, int W, int pad, int gaussian, const double* weights3_host,
                         const void* vkeys_u64, const void* sizes_u64, uint32_t cap_verts, int unpad_shift, int z_offset,
                         const void* cum_f64, const void* adj_f64, int n_cum, double mm_per_pixel_y, double mm_per_pixel_x,
-                        int scale_in_f64, void* verts_f32, void* stream);
+                        int scale_in_f64, int which_blocks /* 1: x-edge, 2: y-edge, 4: z-edge vertices */, void* verts_f32,
+                        void* stream);
 int t3d_mesh_canonicalize_fast_dev(const void* verts_in, int64_t V_cap, const void* V_dev_u64, const void* faces_in, int64_t F_cap,
                                    const void* F_dev_u64, void* verts_out, void* faces_out_i64, void* faces_out_i32,
                                    void* counts_u64, void* workspace, void* stream);
@@ -170,14 +171,19 @@ int t3d_mesh_canonicalize_fast_dev(const void* verts_in, int64_t V_cap, const vo
  * t3d_mc_emit_dev; Zs,Hs,Ws = the marched sign volume).  The vertices the z map clamps onto z = 0 (surface_extractor.py:100-103;
  * non-empty only when the object touches slice 0) are ordered by a generic (y,x) sort over cap_g0 entries (0 = not
  * provisioned).  sizes_u64 = {n_active, n_x, n_y, n_z, n_t}; Zs / z_offset / unpad_shift / n_cum as for t3d_mc_vertices.
- * counts_u64[2] != 0: order not verified (level model broken by rounding, cap_z or cap_g0 too small) -> fall back. */
+ * counts_u64[2] != 0: order not verified (level model broken by rounding, cap_z or cap_g0 too small) -> fall back.
+ * zkey_bits (0 = 32): the z keys are sorted as (layer, key(z) - key(z of the layer's lower plane)) truncated to that many
+ * bits -- the caller bounds the span of one layer from the z map (fewer radix passes); a wrong bound only fails the
+ * verification.  phases: 1 = only the z-edge sort (needs only the z-edge vertices; can run on another stream while the
+ * other vertices are still being computed), 2 = everything after it, 3 = both. */
 int64_t t3d_canonicalize_structured_workspace_bytes(int64_t V, int64_t F, uint32_t cap_z, uint32_t cap_g0, int Zs);
 int t3d_mesh_canonicalize_structured_dev(const void* verts_in, const void* vkeys_u64, int64_t V_cap, const void* sizes_u64,
                                          const void* V_dev_u64, int Zs, int Hs, int Ws, const void* chunkbase_u32,
-                                         const void* aw_base_u32, uint32_t aw_stride, int z_offset, int unpad_shift, int n_cum,
-                                         uint32_t cap_z, uint32_t cap_g0, const void* faces_in, int64_t F_cap, const void* F_dev_u64,
+                                         const void* aw_base_u32, uint32_t aw_stride, int z_offset, int unpad_shift,
+                                         const void* cum_f64, const void* adj_f64, int n_cum, int zkey_bits, uint32_t cap_z,
+                                         uint32_t cap_g0, const void* faces_in, int64_t F_cap, const void* F_dev_u64,
                                          void* verts_out, void* faces_out_i64, void* faces_out_i32, void* counts_u64,
-                                         void* n_g0_u64, void* workspace, void* stream);
+                                         void* n_g0_u64, void* workspace, int phases, void* stream);
 int t3d_mesh_measure_dev(const void* verts_f32, const void* faces, int64_t F_cap, const void* F_dev_u64, int faces_are_i64,
                          void* out_f64, void* workspace, void* stream);
 
@@ -192,7 +198,8 @@ int t3d_mesh_measure_dev(const void* verts_f32, const void* faces, int64_t F_cap
  *   [0..4] and [16] read 0 and the sizes that did not fit are kept in [20..24].  [25] size of the z-clamp group of the
  *   canonical ordering (t3d_mesh_canonicalize_structured_dev): [7] != 0 with [25] > cap_g0 -> retry with a larger cap_g0.
  * cap_zverts: capacity for the z-edge vertices ([3]); cap_zverts = 0 selects the generic 64-bit sort
- * (t3d_mesh_canonicalize_fast_dev) instead of the structured ordering.
+ * (t3d_mesh_canonicalize_fast_dev) instead of the structured ordering; zkey_bits as for
+ * t3d_mesh_canonicalize_structured_dev (0 = no bound known).
  *   [32 .. 32+Z) per-slice voxel counts after close_ends, [32+Z .. 32+2Z) after smoothing.
  * n_stages/erode_mask as t3d_morph (0 stages = no smoothing).  cum/adj: device float64 z-map arrays. */
 int64_t t3d_reconstruct_workspace_bytes(int Z, int H, int W, int add_padding, int n_stages, uint32_t cap_active,
@@ -201,8 +208,8 @@ int64_t t3d_reconstruct_results_len(int Z);
 int t3d_reconstruct(const void* masks_u8, int Z, int H, int W, int threshold, int close_ends, int n_stages, unsigned erode_mask,
                     int add_padding, const double* weights3_host, const void* cum_f64, const void* adj_f64, int n_cum,
                     double mm_per_pixel_y, double mm_per_pixel_x, int scale_in_f64, uint32_t cap_active, uint32_t cap_verts,
-                    uint32_t cap_faces, uint32_t cap_zverts, uint32_t cap_g0, void* verts_out_f32, void* faces_out_i64,
-                    void* results_u64, void* workspace, void* stream);
+                    uint32_t cap_faces, uint32_t cap_zverts, uint32_t cap_g0, int zkey_bits, void* verts_out_f32,
+                    void* faces_out_i64, void* results_u64, void* workspace, void* stream);
 
 /* z-slab variant of t3d_reconstruct for one rank of a sharded run (host side: sharded.py).  ext_bits holds
  * halo_lo + n_own + halo_hi bit-planes: the rank's own packed slices (global end slices already hole-filled) between the
@@ -224,8 +231,8 @@ int t3d_reconstruct_slab(const void* ext_bits, int halo_lo, int n_own, int halo_
                          unsigned erode_mask, int add_padding, int z_begin, int z_end, int z_offset, int want_ghost, float z_ghost,
                          int want_lead, float z_lead, int join_fill, const double* weights3_host, const void* cum_f64, const void* adj_f64,
                          int n_cum, double mm_per_pixel_y, double mm_per_pixel_x, int scale_in_f64, uint32_t cap_active,
-                         uint32_t cap_verts, uint32_t cap_faces, uint32_t cap_zverts, uint32_t cap_g0, void* verts_out_f32,
-                         void* faces_out_i64, void* results_u64, void* workspace, void* stream);
+                         uint32_t cap_verts, uint32_t cap_faces, uint32_t cap_zverts, uint32_t cap_g0, int zkey_bits,
+                         void* verts_out_f32, void* faces_out_i64, void* results_u64, void* workspace, void* stream);
 /* faces_i64[0 .. 3*F'[rank]) += sum over lower ranks of (V' - ghost tail), read from the all-gathered result blocks
  * (world x stride_u64 uint64 on the device): local vertex ids -> ids in the stitched mesh. */
 int t3d_slab_stitch_faces(void* faces_i64, int64_t cap_faces, const void* gathered_results_u64, int64_t stride_u64, int rank,

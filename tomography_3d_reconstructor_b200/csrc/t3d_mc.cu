@@ -461,18 +461,26 @@ __global__ void __launch_bounds__(128) k_mc_vertices(VertexArgs p)
     vertex_body<AXIS>(p, zlut, p.first + t);
 }
 
-// all three axis blocks in one launch, block sizes read from device memory (sizes = {n_active, n_x, n_y, n_z, n_t})
-__global__ void __launch_bounds__(128) k_mc_vertices_all(VertexArgs p, const unsigned long long* __restrict__ sizes, uint32_t cap_verts)
+// axis blocks selected by `which` (1: x-edge, 2: y-edge, 4: z-edge vertices) in one launch, block sizes read from device
+// memory (sizes = {n_active, n_x, n_y, n_z, n_t}).  Thread t handles the t-th vertex of the selected blocks.
+__global__ void __launch_bounds__(128) k_mc_vertices_all(VertexArgs p, const unsigned long long* __restrict__ sizes, uint32_t cap_verts,
+                                                         int which)
 {
     __shared__ double zlut[18];
     fill_zlut(p.occ, zlut);
     __syncthreads();
     const unsigned long long nx = sizes[1], ny = sizes[2], nz = sizes[3];
     if (nx + ny + nz > cap_verts) return;
-    const uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
-    if (id < nx) vertex_body<2>(p, zlut, id);
-    else if (id < nx + ny) vertex_body<1>(p, zlut, id);
-    else if (id < nx + ny + nz) vertex_body<0>(p, zlut, id);
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (which & 1) {
+        if (t < nx) { vertex_body<2>(p, zlut, t); return; }
+        t -= (uint32_t)nx;
+    }
+    if (which & 2) {
+        if (t < ny) { vertex_body<1>(p, zlut, (uint32_t)nx + t); return; }
+        t -= (uint32_t)ny;
+    }
+    if ((which & 4) && t < nz) vertex_body<0>(p, zlut, (uint32_t)(nx + ny) + t);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -651,9 +659,10 @@ extern "C" int t3d_mc_emit_dev(const void* sign_bits, int Zs, int Hs, int Ws, in
 extern "C" int t3d_mc_vertices_dev(const void* occ_bits, int Z, int H, int W, int pad, int gaussian, const double* weights3_host,
                                    const void* vkeys_u64, const void* sizes_u64, uint32_t cap_verts, int unpad_shift, int z_offset,
                                    const void* cum_f64, const void* adj_f64, int n_cum, double mm_per_pixel_y,
-                                   double mm_per_pixel_x, int scale_in_f64, void* verts_f32, void* stream)
+                                   double mm_per_pixel_x, int scale_in_f64, int which_blocks, void* verts_f32, void* stream)
 {
     if (Z <= 0 || H <= 0 || W <= 0) { t3d_set_error("t3d_mc_vertices_dev: empty volume"); return 2; }
+    if ((which_blocks & 7) == 0) return 0;
     if (cap_verts == 0) return 0;
     VertexArgs p;
     p.occ = t3d_make_view(occ_bits, Z, H, W, pad, gaussian, weights3_host);
@@ -670,7 +679,8 @@ extern "C" int t3d_mc_vertices_dev(const void* occ_bits, int Z, int H, int W, in
     p.mm_x = mm_per_pixel_x;
     p.scale_f64 = scale_in_f64 ? 1 : 0;
     p.verts = (float*)verts_f32;
-    k_mc_vertices_all<<<(cap_verts + 127) / 128, 128, 0, (cudaStream_t)stream>>>(p, (const unsigned long long*)sizes_u64, cap_verts);
+    k_mc_vertices_all<<<(cap_verts + 127) / 128, 128, 0, (cudaStream_t)stream>>>(p, (const unsigned long long*)sizes_u64, cap_verts,
+                                                                               which_blocks & 7);
     T3D_CHECK_LAUNCH("t3d_mc_vertices_dev");
     t3d_count_launches(1);
     return 0;

@@ -135,9 +135,10 @@ __global__ void k_count_plane_vertices(const float* __restrict__ verts, const un
     if (lane == 0) *out = (unsigned long long)(bound[1] - bound[0]);
 }
 
+#define N_SIDE_EVENTS 8
 struct SideStream {
     cudaStream_t s = nullptr;
-    cudaEvent_t e[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t e[N_SIDE_EVENTS] = {};
 };
 static SideStream g_side[64];
 
@@ -147,8 +148,12 @@ static int side_for_current_device(SideStream** out)
     T3D_CUDA(cudaGetDevice(&dev));
     SideStream& s = g_side[dev & 63];
     if (!s.s) {
-        T3D_CUDA(cudaStreamCreateWithFlags(&s.s, cudaStreamNonBlocking));
-        for (int k = 0; k < 6; ++k) T3D_CUDA(cudaEventCreateWithFlags(&s.e[k], cudaEventDisableTiming));
+        // highest priority: the side stream carries short dependent chains (hole filling, the z-edge sort) that must not
+        // queue behind the large grids of the main stream
+        int prio_lo = 0, prio_hi = 0;
+        T3D_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        T3D_CUDA(cudaStreamCreateWithPriority(&s.s, cudaStreamNonBlocking, prio_hi));
+        for (int k = 0; k < N_SIDE_EVENTS; ++k) T3D_CUDA(cudaEventCreateWithFlags(&s.e[k], cudaEventDisableTiming));
     }
     *out = &s;
     return 0;
@@ -169,8 +174,8 @@ struct SlabGeom {
 static int reconstruct_core(const uint32_t* grid, const SlabGeom& g, int H, int W, int n_stages, unsigned erode_mask, int pad,
                             const double* weights3_host, const void* cum_f64, const void* adj_f64, int n_cum, double mm_y,
                             double mm_x, int scale_in_f64, uint32_t cap_active, uint32_t cap_verts, uint32_t cap_faces,
-                            uint32_t cap_zverts, uint32_t cap_g0, void* verts_out_f32, void* faces_out_i64, unsigned long long* R,
-                            char* ws, const Layout& L, SideStream* side, cudaStream_t st)
+                            uint32_t cap_zverts, uint32_t cap_g0, int zkey_bits, void* verts_out_f32, void* faces_out_i64,
+                            unsigned long long* R, char* ws, const Layout& L, SideStream* side, cudaStream_t st)
 {
     const int Zx = g.hl + g.n + g.hh;
     const int64_t nw = t3d_words_per_row(W), plane_words = (int64_t)H * nw;
@@ -206,21 +211,33 @@ static int reconstruct_core(const uint32_t* grid, const SlabGeom& g, int H, int 
     k_finalize_sizes<<<1, 1, 0, st>>>(R, cap_active, cap_verts, cap_faces);
     RUN(t3d_mc_emit_dev(ws + L.sign, Zp, Hp, Wp, g.z_begin, g.z_end, ws + L.ballots, ws + L.chunkbase, ws + L.aw_idx, ws + L.aw_base,
                         cap_active, R + R_NACTIVE, cap_verts, cap_faces, ws + L.vkeys, ws + L.faces_raw, st));
-    RUN(t3d_mc_vertices_dev(surf, Zl, H, W, pad, 1, weights3_host, ws + L.vkeys, R + R_NACTIVE, cap_verts, 1, g.z_offset, cum_f64,
-                            adj_f64, n_cum, mm_y, mm_x, scale_in_f64, ws + L.verts_raw, st));
-    // ---- mesh volume / area on the emitted mesh (side stream, concurrent with the canonical sort), canonical mesh
-    T3D_CUDA(cudaStreamWaitEvent(st, side->e[3], 0));   // the bbox reduction is done with the side stream
-    T3D_CUDA(cudaEventRecord(side->e[4], st));
-    T3D_CUDA(cudaStreamWaitEvent(side->s, side->e[4], 0));
-    RUN(t3d_mesh_measure_dev(ws + L.verts_raw, ws + L.faces_raw, cap_faces, R + R_NT, 0, R + R_VOLUME_F64, ws + L.measure, side->s));
-    T3D_CUDA(cudaEventRecord(side->e[5], side->s));
-    if (cap_zverts)
+    // (running the z-edge sort of the structured ordering on the side stream, under the evaluation of the x/y-edge
+    // vertices, was measured: no gain -- the two compete for the same issue slots -- so the flow stays serial)
+    if (cap_zverts) {
+        RUN(t3d_mc_vertices_dev(surf, Zl, H, W, pad, 1, weights3_host, ws + L.vkeys, R + R_NACTIVE, cap_verts, 1, g.z_offset, cum_f64,
+                                adj_f64, n_cum, mm_y, mm_x, scale_in_f64, 7, ws + L.verts_raw, st));
+        // ---- mesh volume / area on the emitted mesh (side stream, concurrent with the canonical ordering), canonical mesh
+        T3D_CUDA(cudaStreamWaitEvent(st, side->e[3], 0));   // the bbox reduction is done with the side stream
+        T3D_CUDA(cudaEventRecord(side->e[4], st));
+        T3D_CUDA(cudaStreamWaitEvent(side->s, side->e[4], 0));
+        RUN(t3d_mesh_measure_dev(ws + L.verts_raw, ws + L.faces_raw, cap_faces, R + R_NT, 0, R + R_VOLUME_F64, ws + L.measure, side->s));
+        T3D_CUDA(cudaEventRecord(side->e[5], side->s));
         RUN(t3d_mesh_canonicalize_structured_dev(ws + L.verts_raw, ws + L.vkeys, cap_verts, R + R_NACTIVE, R + R_VRAW, Zp, Hp, Wp,
-                                                 ws + L.chunkbase, ws + L.aw_base, cap_active, g.z_offset, 1, n_cum, cap_zverts, cap_g0, ws + L.faces_raw, cap_faces, R + R_NT, verts_out_f32,
-                                                 faces_out_i64, nullptr, R + R_VCANON, R + R_NG0, ws + L.canon, st));
-    else
+                                                 ws + L.chunkbase, ws + L.aw_base, cap_active, g.z_offset, 1, cum_f64, adj_f64, n_cum,
+                                                 zkey_bits, cap_zverts, cap_g0, ws + L.faces_raw, cap_faces, R + R_NT, verts_out_f32,
+                                                 faces_out_i64, nullptr, R + R_VCANON, R + R_NG0, ws + L.canon, 3, st));
+    } else {
+        RUN(t3d_mc_vertices_dev(surf, Zl, H, W, pad, 1, weights3_host, ws + L.vkeys, R + R_NACTIVE, cap_verts, 1, g.z_offset, cum_f64,
+                                adj_f64, n_cum, mm_y, mm_x, scale_in_f64, 7, ws + L.verts_raw, st));
+        // ---- mesh volume / area on the emitted mesh (side stream, concurrent with the canonical sort), canonical mesh
+        T3D_CUDA(cudaStreamWaitEvent(st, side->e[3], 0));   // the bbox reduction is done with the side stream
+        T3D_CUDA(cudaEventRecord(side->e[4], st));
+        T3D_CUDA(cudaStreamWaitEvent(side->s, side->e[4], 0));
+        RUN(t3d_mesh_measure_dev(ws + L.verts_raw, ws + L.faces_raw, cap_faces, R + R_NT, 0, R + R_VOLUME_F64, ws + L.measure, side->s));
+        T3D_CUDA(cudaEventRecord(side->e[5], side->s));
         RUN(t3d_mesh_canonicalize_fast_dev(ws + L.verts_raw, cap_verts, R + R_VRAW, ws + L.faces_raw, cap_faces, R + R_NT,
                                            verts_out_f32, faces_out_i64, nullptr, R + R_VCANON, ws + L.canon, st));
+    }
     if (g.want_ghost || g.want_lead)
         k_count_plane_vertices<<<1, 64, 0, st>>>((const float*)verts_out_f32, R + R_VCANON, g.z_ghost, g.z_lead, g.want_ghost,
                                                  g.want_lead, R + R_NGHOST, R + R_NLEAD);
@@ -232,7 +249,8 @@ extern "C" int t3d_reconstruct(const void* masks_u8, int Z, int H, int W, int th
                                unsigned erode_mask, int add_padding, const double* weights3_host, const void* cum_f64,
                                const void* adj_f64, int n_cum, double mm_per_pixel_y, double mm_per_pixel_x, int scale_in_f64,
                                uint32_t cap_active, uint32_t cap_verts, uint32_t cap_faces, uint32_t cap_zverts, uint32_t cap_g0,
-                               void* verts_out_f32, void* faces_out_i64, void* results_u64, void* workspace, void* stream)
+                               int zkey_bits, void* verts_out_f32, void* faces_out_i64, void* results_u64, void* workspace,
+                               void* stream)
 {
     if (Z <= 0 || H <= 0 || W <= 0) { t3d_set_error("t3d_reconstruct: empty volume"); return 2; }
     if (cap_active == 0 || cap_verts == 0 || cap_faces == 0) { t3d_set_error("t3d_reconstruct: zero capacity"); return 2; }
@@ -271,8 +289,8 @@ extern "C" int t3d_reconstruct(const void* masks_u8, int Z, int H, int W, int th
     }
     SlabGeom g = {0, Z, 0, 0, -1, 0, 0, 0, 0.f, 0.f};
     RUN(reconstruct_core(bitsB, g, H, W, n_stages, erode_mask, pad, weights3_host, cum_f64, adj_f64, n_cum, mm_per_pixel_y,
-                         mm_per_pixel_x, scale_in_f64, cap_active, cap_verts, cap_faces, cap_zverts, cap_g0, verts_out_f32, faces_out_i64,
-                         R, ws, L, side, st));
+                         mm_per_pixel_x, scale_in_f64, cap_active, cap_verts, cap_faces, cap_zverts, cap_g0, zkey_bits, verts_out_f32,
+                         faces_out_i64, R, ws, L, side, st));
     T3D_CHECK_LAUNCH("t3d_reconstruct");
     t3d_count_launches(1);
     return 0;
@@ -319,7 +337,8 @@ extern "C" int t3d_reconstruct_slab(const void* ext_bits, int halo_lo, int n_own
                                     float z_ghost, int want_lead, float z_lead, int join_fill, const double* weights3_host, const void* cum_f64,
                                     const void* adj_f64, int n_cum, double mm_per_pixel_y, double mm_per_pixel_x, int scale_in_f64,
                                     uint32_t cap_active, uint32_t cap_verts, uint32_t cap_faces, uint32_t cap_zverts, uint32_t cap_g0,
-                                    void* verts_out_f32, void* faces_out_i64, void* results_u64, void* workspace, void* stream)
+                                    int zkey_bits, void* verts_out_f32, void* faces_out_i64, void* results_u64, void* workspace,
+                                    void* stream)
 {
     if (n_own <= 0 || H <= 0 || W <= 0 || halo_lo < 0 || halo_hi < 0) { t3d_set_error("t3d_reconstruct_slab: bad slab"); return 2; }
     if (cap_active == 0 || cap_verts == 0 || cap_faces == 0) { t3d_set_error("t3d_reconstruct_slab: zero capacity"); return 2; }
@@ -336,8 +355,8 @@ extern "C" int t3d_reconstruct_slab(const void* ext_bits, int halo_lo, int n_own
     RUN(t3d_gap_fill(ext_bits, ws + L.bitsB, nullptr, nullptr, Zx, H, W, R + R_COUNTS, st));
     SlabGeom g = {halo_lo, n_own, halo_hi, z_begin, z_end, z_offset, want_ghost, want_lead, z_ghost, z_lead};
     RUN(reconstruct_core((const uint32_t*)(ws + L.bitsB), g, H, W, n_stages, erode_mask, pad, weights3_host, cum_f64, adj_f64, n_cum,
-                         mm_per_pixel_y, mm_per_pixel_x, scale_in_f64, cap_active, cap_verts, cap_faces, cap_zverts, cap_g0, verts_out_f32,
-                         faces_out_i64, R, ws, L, side, st));
+                         mm_per_pixel_y, mm_per_pixel_x, scale_in_f64, cap_active, cap_verts, cap_faces, cap_zverts, cap_g0, zkey_bits,
+                         verts_out_f32, faces_out_i64, R, ws, L, side, st));
     T3D_CHECK_LAUNCH("t3d_reconstruct_slab");
     t3d_count_launches(1);
     return 0;

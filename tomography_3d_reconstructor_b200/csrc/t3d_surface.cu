@@ -865,6 +865,9 @@ struct CanonS {
     const uint32_t* aw_base;           // 4 arrays (x, y, z vertices, triangles before each active word), `stride` apart
     uint32_t stride;
     int g_plane;                       // local plane index of un-padded plane 0 (= shift - z_offset); < 0: no clamp group here
+    int z_offset; float shift;         // as in t3d_mc_vertices: global plane of local plane 0, un-pad shift
+    const double* cum; const double* adj; int n_cum;
+    int zkey_bits;                     // 32: absolute z keys; less: key relative to the layer's lower plane, that many bits
     unsigned long long* zkeys;
     uint32_t* zval;
     const uint32_t* zperm;             // z block sorted by (layer, z float)
@@ -898,6 +901,23 @@ __device__ __forceinline__ void g0_sizes(const CanonS& c, uint32_t& gX, uint32_t
     gX = before_row<0>(c, r_next); gY = before_row<1>(c, r_next); gZ = z_below;
 }
 
+// z coordinate the vertex transform gives to a vertex lying exactly on local plane k (same arithmetic as vertex_body)
+__device__ __forceinline__ float plane_z(const CanonS& c, int k)
+{
+    float fz = __fsub_rn(__double2float_rn((double)(k + c.z_offset)), c.shift);
+    if (c.n_cum > 0) {
+        if (fz < 0.0f) fz = 0.0f;
+        else if (fz >= (float)(c.n_cum - 1)) fz = __double2float_rn(c.cum[c.n_cum - 1]);
+        else {
+            const float fl = floorf(fz);
+            const int lo = (int)fl;
+            const float fr = __fsub_rn(fz, fl);
+            fz = __double2float_rn(__dadd_rn(c.cum[lo], __dmul_rn((double)fr, c.adj[min(lo, c.n_cum - 2)])));
+        }
+    }
+    return fz;
+}
+
 __global__ void __launch_bounds__(256) k_canon_zkeys(CanonS c)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -908,7 +928,19 @@ __global__ void __launch_bounds__(256) k_canon_zkeys(CanonS c)
         uint32_t gX, gY, gZ;
         g0_sizes(c, gX, gY, gZ);
         const uint32_t raw = nx + ny + i;
-        key = (i < gZ) ? 0ull : (((c.vkeys[raw] >> 42) + 1ull) << 32) | float_key(c.verts[3 * (int64_t)raw]);
+        if (i < gZ) key = 0ull;
+        else {
+            const int k = (int)(c.vkeys[raw] >> 42);
+            uint32_t zk = float_key(c.verts[3 * (int64_t)raw]);
+            if (c.zkey_bits < 32) {
+                // relative to the layer's lower plane; anything outside the promised span saturates (and fails the check)
+                const uint32_t base = float_key(plane_z(c, k));
+                zk = zk >= base ? zk - base : 0u;
+                const uint32_t lim = (1u << c.zkey_bits) - 1u;
+                zk = zk > lim ? lim : zk;
+            }
+            key = ((unsigned long long)(k + 1) << c.zkey_bits) | zk;
+        }
     }
     c.zkeys[i] = key;
     c.zval[i] = i;
@@ -1004,13 +1036,15 @@ extern "C" int64_t t3d_canonicalize_structured_workspace_bytes(int64_t V, int64_
 // clamp group (a caller seeing [2] != 0 with *n_g0 > cap_g0 retries with a larger cap_g0).
 extern "C" int t3d_mesh_canonicalize_structured_dev(const void* verts_in, const void* vkeys_u64, int64_t V_cap, const void* sizes_u64,
                                                     const void* V_dev_u64, int Zs, int Hs, int Ws, const void* chunkbase_u32,
-                                                    const void* aw_base_u32, uint32_t aw_stride, int z_offset, int unpad_shift, int n_cum,
+                                                    const void* aw_base_u32, uint32_t aw_stride, int z_offset, int unpad_shift,
+                                                    const void* cum_f64, const void* adj_f64, int n_cum, int zkey_bits,
                                                     uint32_t cap_z, uint32_t cap_g0, const void* faces_in, int64_t F_cap,
                                                     const void* F_dev_u64, void* verts_out, void* faces_out_i64, void* faces_out_i32,
-                                                    void* counts_u64, void* n_g0_u64, void* workspace, void* stream)
+                                                    void* counts_u64, void* n_g0_u64, void* workspace, int phases, void* stream)
 {
     cudaStream_t st = (cudaStream_t)stream;
-    if (V_cap <= 0 || V_cap > 0x7fffffff || F_cap < 0 || Zs <= 0 || Hs <= 0 || Ws <= 0 || cap_z == 0) {
+    if (zkey_bits <= 0 || zkey_bits > 32) zkey_bits = 32;
+    if (V_cap <= 0 || V_cap > 0x7fffffff || F_cap < 0 || Zs <= 0 || Hs <= 0 || Ws <= 0 || cap_z == 0 || (phases & 3) == 0) {
         t3d_set_error("t3d_mesh_canonicalize_structured: bad sizes");
         return 2;
     }
@@ -1027,6 +1061,9 @@ extern "C" int t3d_mesh_canonicalize_structured_dev(const void* verts_in, const 
     c.aw_base = (const uint32_t*)aw_base_u32;
     c.stride = aw_stride;
     c.g_plane = (n_cum > 0 && unpad_shift > 0) ? unpad_shift - z_offset : -1;
+    c.z_offset = z_offset; c.shift = unpad_shift ? 1.0f : 0.0f;
+    c.cum = (const double*)cum_f64; c.adj = (const double*)adj_f64; c.n_cum = n_cum;
+    c.zkey_bits = zkey_bits;
     unsigned long long* zkeys_b; uint32_t* zperm; unsigned long long* gkeys_b; uint32_t* gperm;
     c.zkeys = (unsigned long long*)ws; ws += align256(8 * (int64_t)cap_z);
     zkeys_b = (unsigned long long*)ws; ws += align256(8 * (int64_t)cap_z);
@@ -1047,22 +1084,28 @@ extern "C" int t3d_mesh_canonicalize_structured_dev(const void* verts_in, const 
     unsigned long long* counts = (unsigned long long*)counts_u64;
     c.zperm = zperm; c.gperm = gperm;
     c.n_g0_out = (unsigned long long*)n_g0_u64;
-    T3D_CUDA(cudaMemsetAsync(counts + 2, 0, 8, st));
-    k_canon_zkeys<<<(cap_z + 255) / 256, 256, 0, st>>>(c);
-    size_t tb = tz;
-    T3D_CUDA(cub::DeviceRadixSort::SortPairs(temp, tb, (const unsigned long long*)c.zkeys, zkeys_b, (const uint32_t*)c.zval, zperm,
-                                             (int)cap_z, 0, 32 + bits_for((unsigned)Zs + 1), st));
-    if (cap_g0 > 0) {
-        k_canon_gkeys<<<(cap_g0 + 255) / 256, 256, 0, st>>>(c);
-        tb = tg;
-        T3D_CUDA(cub::DeviceRadixSort::SortPairs(temp, tb, (const unsigned long long*)c.gkeys, gkeys_b, (const uint32_t*)c.gval, gperm,
-                                                 (int)cap_g0, 0, 64, st));
+    if (phases & 1) {
+        k_canon_zkeys<<<(cap_z + 255) / 256, 256, 0, st>>>(c);
+        size_t tb = tz;
+        T3D_CUDA(cub::DeviceRadixSort::SortPairs(temp, tb, (const unsigned long long*)c.zkeys, zkeys_b, (const uint32_t*)c.zval, zperm,
+                                                 (int)cap_z, 0, zkey_bits + bits_for((unsigned)Zs + 1), st));
+        t3d_count_launches(2);
     }
-    k_canon_positions<<<(unsigned)((V + 255) / 256), 256, 0, st>>>(c);
-    if (canonical_tail(c.verts, c.perm, V, (const unsigned long long*)V_dev_u64, faces_in, F, (const unsigned long long*)F_dev_u64,
-                       verts_out, faces_out_i64, faces_out_i32, counts, flags, pos, newid, scan_ws, totals, st)) return 1;
+    if (phases & 2) {
+        T3D_CUDA(cudaMemsetAsync(counts + 2, 0, 8, st));
+        if (cap_g0 > 0) {
+            // (shares the radix sort's temporary storage with the z sort: phase 2 must be ordered after phase 1)
+            k_canon_gkeys<<<(cap_g0 + 255) / 256, 256, 0, st>>>(c);
+            size_t tb = tg;
+            T3D_CUDA(cub::DeviceRadixSort::SortPairs(temp, tb, (const unsigned long long*)c.gkeys, gkeys_b, (const uint32_t*)c.gval, gperm,
+                                                     (int)cap_g0, 0, 64, st));
+        }
+        k_canon_positions<<<(unsigned)((V + 255) / 256), 256, 0, st>>>(c);
+        if (canonical_tail(c.verts, c.perm, V, (const unsigned long long*)V_dev_u64, faces_in, F, (const unsigned long long*)F_dev_u64,
+                           verts_out, faces_out_i64, faces_out_i32, counts, flags, pos, newid, scan_ws, totals, st)) return 1;
+        t3d_count_launches((F > 0 ? 5 : 3) + (cap_g0 > 0 ? 1 : 0));
+    }
     T3D_CHECK_LAUNCH("t3d_mesh_canonicalize_structured");
-    t3d_count_launches((F > 0 ? 5 : 3) + 2 + (cap_g0 > 0 ? 1 : 0));
     return 0;
 }
 

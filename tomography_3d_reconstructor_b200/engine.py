@@ -483,6 +483,35 @@ def z_map_arrays(slice_depths, add_padding: bool) -> Tuple[np.ndarray, np.ndarra
     return cum, adj
 
 
+def z_map_value(plane_unpadded: float, cum: np.ndarray, adj: np.ndarray) -> np.float32:
+    """float32 z coordinate the vertex transform gives to a vertex lying exactly on un-padded plane index `plane`
+    (surface_extractor.py:98-113; same arithmetic as the kernel and SURVEY.md V8)."""
+    z = np.float32(plane_unpadded)
+    if len(cum) == 0:
+        return z
+    if z < 0:
+        return np.float32(0)
+    if z >= len(cum) - 1:
+        return np.float32(cum[-1])
+    lo = int(np.floor(z))
+    fr = np.float32(z - np.float32(lo))
+    return np.float32(cum[lo] + np.float64(fr) * adj[min(lo, len(adj) - 1)])
+
+
+def zkey_bits(slice_depths, add_padding: bool, n_planes: int, z_offset: int = 0, shift: int = 1) -> int:
+    """Bits needed for `float key(z) - float key(z of the layer's lower plane)` over the cube layers of a sign volume of
+    n_planes planes: the bound t3d_mesh_canonicalize_structured_dev uses to shorten its radix sort (32 = no bound)."""
+    cum, adj = z_map_arrays(slice_depths, add_padding)
+    if len(cum) == 0:
+        return 32
+    z = np.array([z_map_value(k + z_offset - shift, cum, adj) for k in range(n_planes + 1)], dtype=np.float32)
+    if (z < 0).any() or (np.diff(z) < 0).any():
+        return 32
+    span = int(np.diff(z.view(np.uint32).astype(np.int64)).max()) if len(z) > 1 else 0
+    nb = max(1, span.bit_length())
+    return nb if nb < 31 else 32
+
+
 EXC_CAP = 1 << 18  # list capacity of the lean field-sign kernel (words needing the exact float64 evaluation)
 
 

@@ -164,6 +164,7 @@ class FusedPlan:
         self.caps = tuple(int(c) for c in caps)
         cum, adj = engine.z_map_arrays(self.depths, add_padding)
         self.n_cum = len(cum)
+        self.zkey_bits = engine.zkey_bits(self.depths, add_padding, Z + 2 * (1 if add_padding else 0), 0, 1)
         self.cum_d = torch.from_numpy(cum).to(device) if self.n_cum else None
         self.adj_d = torch.from_numpy(adj).to(device) if self.n_cum else None
         if len(self.caps) != 5:
@@ -184,7 +185,7 @@ class FusedPlan:
         engine.check(engine._L().t3d_reconstruct(
             p(masks_u8), Z, H, W, self.threshold, 1 if self.close_ends else 0, self.n_stages, self.erode_mask,
             1 if self.add_padding else 0, engine._W3_C, p(self.cum_d), p(self.adj_d), self.n_cum, float(self.mm_y),
-            float(self.mm_x), 0, self.caps[0], self.caps[1], self.caps[2], self.caps[3], self.caps[4], p(self.verts),
+            float(self.mm_x), 0, self.caps[0], self.caps[1], self.caps[2], self.caps[3], self.caps[4], self.zkey_bits, p(self.verts),
             p(self.faces), p(self.res), p(self.ws), engine._stream()), "t3d_reconstruct")
 
     def capture(self, masks_u8: torch.Tensor) -> None:

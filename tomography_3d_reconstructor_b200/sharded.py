@@ -46,19 +46,7 @@ def owned_padded_planes(Zg: int, z0: int, z1: int, pad: int = 1) -> Tuple[int, i
     return a, b
 
 
-def z_map_value(plane_unpadded: float, cum: np.ndarray, adj: np.ndarray) -> np.float32:
-    """float32 z coordinate the vertex transform gives to a vertex lying exactly on un-padded plane index `plane`
-    (surface_extractor.py:98-113; same arithmetic as the kernel and SURVEY.md V8)."""
-    z = np.float32(plane_unpadded)
-    if len(cum) == 0:
-        return z
-    if z < 0:
-        return np.float32(0)
-    if z >= len(cum) - 1:
-        return np.float32(cum[-1])
-    lo = int(np.floor(z))
-    fr = np.float32(z - np.float32(lo))
-    return np.float32(cum[lo] + np.float64(fr) * adj[min(lo, len(adj) - 1)])
+z_map_value = engine.z_map_value
 
 
 def exchange_halos(ext: torch.Tensor, hl: int, n: int, hh: int, rank: int, world: int, group=None) -> None:
@@ -289,6 +277,8 @@ class FusedSlabPlan:
         self.want_ghost, self.want_lead = int(self.z1 < Zg), int(self.z0 > 0)
         self.z_ghost = float(z_map_value(b - pad, cum, adj)) if self.want_ghost else 0.0
         self.z_lead = float(z_map_value(a - pad, cum, adj)) if self.want_lead else 0.0
+        n_surf = min(SURF_HALO, self.hl) + self.n + min(SURF_HALO, self.hh) + 2 * pad
+        self.zkey_bits = engine.zkey_bits(self.depths, add_padding, n_surf, self.z_offset, 1)
         wpr = engine.words_per_row(W)
         Zx = self.hl + self.n + self.hh
         self.ext = torch.zeros((Zx, H, wpr), dtype=torch.int32, device=device)
@@ -332,7 +322,7 @@ class FusedSlabPlan:
             self.z_begin, self.z_end, self.z_offset, self.want_ghost, self.z_ghost, self.want_lead, self.z_lead,
             int(self.z0 == 0 or self.z1 == self.Zg), engine._W3_C,
             p(self.cum_d), p(self.adj_d), self.n_cum, float(self.mm_y), float(self.mm_x), 0, self.caps[0], self.caps[1],
-            self.caps[2], self.caps[3], self.caps[4], p(self.verts), p(self.faces), p(self.res), p(self.ws), engine._stream()), "t3d_reconstruct_slab")
+            self.caps[2], self.caps[3], self.caps[4], self.zkey_bits, p(self.verts), p(self.faces), p(self.res), p(self.ws), engine._stream()), "t3d_reconstruct_slab")
 
     def stitch(self) -> None:
         """Local face ids -> ids in the stitched mesh, from the gathered result blocks (device side)."""
