@@ -103,8 +103,7 @@ struct EdtPass {
     int n, ncomp_in;
     double w_new, w0, w1;  // squared sampling of the new axis and of the existing components
     double s_new, s0, s1;  // the samplings themselves (final distance, scipy's arithmetic)
-    int32_t* st_v;     // stacks [n][n_lines]
-    double* st_z;
+    uint32_t* stack;   // [n][n_lines] entries (site | first sample it serves << 16)
     float sign;        // +1 / -1 applied to dist_out
     int accumulate;    // dist_out += instead of =
 };
@@ -121,36 +120,53 @@ __device__ __forceinline__ double site_cost(const EdtPass& p, int64_t idx)
     return f;
 }
 
+// Lower envelope of the parabolas f(j) + ((q-j)*s)^2 along one line per thread (Felzenszwalb & Huttenlocher).  Only
+// integer positions are ever queried, so a stack entry keeps the FIRST SAMPLE its site serves instead of the real
+// intersection abscissa: entry = site | start << 16 (4 bytes instead of 12), the top of the stack lives in registers,
+// and "pop while the new site takes over at or before the top's start" is equivalent to the real-valued test for every
+// integer query (a site whose interval contains no integer can be dropped).  A tie at an integer position stays with the
+// earlier site, as in the real-valued sweep (`boundary < q` to advance).
 __global__ void __launch_bounds__(128) k_edt_envelope(EdtPass p)
 {
     const int64_t line = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (line >= p.n_lines) return;
     const int64_t base = (line / p.inner) * p.outer_stride + (line % p.inner);
-    int32_t* sv = p.st_v + line;
-    double* sz = p.st_z + line;
+    uint32_t* st = p.stack + line;
     const int64_t L = p.n_lines;
-    int k = -1;
-    double fk = 0.0;  // cost of the site on top of the stack
-    int vk = 0;
+    int k = -1;            // index of the top entry; entries below the top are in st[], the top is (vk, bk, fk)
+    int vk = 0, bk = 0;
+    double fk = 0.0;
     for (int q = 0; q < p.n; ++q) {
         const double fq = site_cost(p, base + q * p.stride);
         if (isinf(fq)) continue;
-        double s = -INFINITY;
+        int b = 0;
         while (k >= 0) {
-            // abscissa where parabola q overtakes parabola vk
-            s = ((fq + (double)q * q * p.w_new) - (fk + (double)vk * vk * p.w_new)) / (2.0 * p.w_new * (double)(q - vk));
-            if (s <= sz[(int64_t)k * L]) {
+            // abscissa where parabola q overtakes parabola vk; q serves the samples > s
+            const double s = ((fq + (double)q * q * p.w_new) - (fk + (double)vk * vk * p.w_new)) / (2.0 * p.w_new * (double)(q - vk));
+            b = s >= (double)p.n ? p.n : (s < 0.0 ? 0 : (int)floor(s) + 1);
+            if (b <= bk) {   // the top serves no sample any more
                 --k;
-                if (k >= 0) { vk = sv[(int64_t)k * L]; fk = site_cost(p, base + vk * p.stride); }
+                if (k >= 0) {
+                    const uint32_t e = st[(int64_t)k * L];
+                    vk = (int)(e & 0xffffu); bk = (int)(e >> 16);
+                    fk = site_cost(p, base + vk * p.stride);
+                }
             } else break;
         }
+        if (k >= 0) st[(int64_t)k * L] = (uint32_t)vk | ((uint32_t)bk << 16);   // spill the old top
+        else b = 0;
         ++k;
-        sv[(int64_t)k * L] = q;
-        sz[(int64_t)k * L] = (k == 0) ? -INFINITY : s;
-        vk = q; fk = fq;
+        vk = q; bk = b; fk = fq;
     }
+    if (k >= 0) st[(int64_t)k * L] = (uint32_t)vk | ((uint32_t)bk << 16);
     // evaluation sweep
-    int j = 0;
+    int j = 0, v = 0, next_start = p.n;
+    if (k >= 0) {
+        v = (int)(st[0] & 0xffffu);
+        next_start = k >= 1 ? (int)(st[L] >> 16) : p.n;
+    }
+    int a = 0, bcomp = 0;
+    bool have = false;
     for (int q = 0; q < p.n; ++q) {
         const int64_t idx = base + q * p.stride;
         if (k < 0) {  // no site anywhere on this line
@@ -158,22 +174,29 @@ __global__ void __launch_bounds__(128) k_edt_envelope(EdtPass p)
             else { p.out[idx] = EDT_NONE; }
             continue;
         }
-        while (j < k && sz[(int64_t)(j + 1) * L] < (double)q) ++j;
-        const int v = sv[(int64_t)j * L];
-        const int64_t sidx = base + v * p.stride;
-        const int a = p.in[sidx];
-        const int b = p.ncomp_in > 1 ? p.in1[sidx] : 0;
+        while (q >= next_start) {
+            ++j;
+            v = (int)(st[(int64_t)j * L] & 0xffffu);
+            next_start = j < k ? (int)(st[(int64_t)(j + 1) * L] >> 16) : p.n;
+            have = false;
+        }
+        if (!have) {
+            const int64_t sidx = base + v * p.stride;
+            a = p.in[sidx];
+            bcomp = p.ncomp_in > 1 ? p.in1[sidx] : 0;
+            have = true;
+        }
         const int dnew = v - q;
         if (p.dist_out) {
             // scipy: dt = (ft - indices) * sampling; sqrt(add.reduce(dt*dt, axis=0)) -- axis order z, y, x
-            const double t0 = __dmul_rn((double)dnew, p.s_new), t1 = __dmul_rn((double)a, p.s0), t2 = __dmul_rn((double)b, p.s1);
+            const double t0 = __dmul_rn((double)dnew, p.s_new), t1 = __dmul_rn((double)a, p.s0), t2 = __dmul_rn((double)bcomp, p.s1);
             const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(t0, t0), __dmul_rn(t1, t1)), __dmul_rn(t2, t2));
             const float d = p.sign * (float)sqrt(d2);
             p.dist_out[idx] = p.accumulate ? p.dist_out[idx] + d : d;
         } else {
             p.out[idx] = (int16_t)dnew;
             p.out[p.vol + idx] = (int16_t)a;
-            if (p.ncomp_in > 1) p.out[2 * p.vol + idx] = (int16_t)b;
+            if (p.ncomp_in > 1) p.out[2 * p.vol + idx] = (int16_t)bcomp;
         }
     }
 }
@@ -193,7 +216,7 @@ static int edt_check(int Z, int H, int W, const char* who)
 extern "C" int64_t t3d_edt_xy_workspace_bytes(int Z, int H, int W)
 {
     const int64_t vol = (int64_t)Z * H * W;
-    return a256(vol * 2) + a256(vol * 4) + vol * 8 + 1024;   // x offsets, stack sites, stack boundaries
+    return a256(vol * 2) + a256(vol * 4) + 1024;   // x offsets, envelope stacks
 }
 
 extern "C" int t3d_edt_xy(const void* occ_bits, int Z, int H, int W, int invert, const double* sampling_host, void* dyx_i16,
@@ -205,15 +228,14 @@ extern "C" int t3d_edt_xy(const void* occ_bits, int Z, int H, int W, int invert,
     const double sy = sampling_host ? sampling_host[1] : 1.0, sx = sampling_host ? sampling_host[2] : 1.0;
     char* ws = (char*)workspace;
     int16_t* dx = (int16_t*)ws; ws += a256(vol * 2);
-    int32_t* st_v = (int32_t*)ws; ws += a256(vol * 4);
-    double* st_z = (double*)ws;
+    uint32_t* stack = (uint32_t*)ws;
     const int64_t rows = (int64_t)Z * H;
     k_edt_x<<<(unsigned)((rows * 32 + 255) / 256), 256, 0, st>>>((const uint32_t*)occ_bits, rows, W, t3d_wpr(W), invert ? 1 : 0, dx);
     EdtPass p;
     // y pass: lines = (z, x); samples stride W
     p.in = dx; p.in1 = nullptr; p.out = (int16_t*)dyx_i16; p.dist_out = nullptr; p.vol = vol;
     p.n_lines = (int64_t)Z * W; p.inner = W; p.outer_stride = (int64_t)H * W; p.stride = W; p.n = H; p.ncomp_in = 1;
-    p.w_new = sy * sy; p.w0 = sx * sx; p.w1 = 0.0; p.s_new = sy; p.s0 = sx; p.s1 = 0.0; p.st_v = st_v; p.st_z = st_z; p.sign = 1.f;
+    p.w_new = sy * sy; p.w0 = sx * sx; p.w1 = 0.0; p.s_new = sy; p.s0 = sx; p.s1 = 0.0; p.stack = stack; p.sign = 1.f;
     p.accumulate = 0;
     k_edt_envelope<<<(unsigned)((p.n_lines + 127) / 128), 128, 0, st>>>(p);
     T3D_CHECK_LAUNCH("t3d_edt_xy");
@@ -226,7 +248,7 @@ extern "C" int t3d_edt_xy(const void* occ_bits, int Z, int H, int W, int invert,
 extern "C" int64_t t3d_edt_z_workspace_bytes(int Z, int H, int W)
 {
     const int64_t vol = (int64_t)Z * H * W;
-    return a256(vol * 4) + vol * 8 + 1024;
+    return a256(vol * 4) + 1024;
 }
 
 extern "C" int t3d_edt_z(const void* dy_i16, const void* dx_i16, int Z, int H, int W, const double* sampling_host, float sign,
@@ -237,14 +259,11 @@ extern "C" int t3d_edt_z(const void* dy_i16, const void* dx_i16, int Z, int H, i
     const int64_t vol = (int64_t)Z * H * W;
     const double sz = sampling_host ? sampling_host[0] : 1.0, sy = sampling_host ? sampling_host[1] : 1.0,
                  sx = sampling_host ? sampling_host[2] : 1.0;
-    char* ws = (char*)workspace;
-    int32_t* st_v = (int32_t*)ws; ws += a256(vol * 4);
-    double* st_z = (double*)ws;
     EdtPass p;
     // lines = (y, x); samples stride H*W; input components (dy, dx)
     p.in = (const int16_t*)dy_i16; p.in1 = (const int16_t*)dx_i16; p.out = nullptr; p.dist_out = (float*)dist_f32; p.vol = vol;
     p.n_lines = (int64_t)H * W; p.inner = (int64_t)H * W; p.outer_stride = 0; p.stride = (int64_t)H * W; p.n = Z; p.ncomp_in = 2;
-    p.w_new = sz * sz; p.w0 = sy * sy; p.w1 = sx * sx; p.s_new = sz; p.s0 = sy; p.s1 = sx; p.st_v = st_v; p.st_z = st_z; p.sign = sign;
+    p.w_new = sz * sz; p.w0 = sy * sy; p.w1 = sx * sx; p.s_new = sz; p.s0 = sy; p.s1 = sx; p.stack = (uint32_t*)workspace; p.sign = sign;
     p.accumulate = accumulate ? 1 : 0;
     k_edt_envelope<<<(unsigned)((p.n_lines + 127) / 128), 128, 0, st>>>(p);
     T3D_CHECK_LAUNCH("t3d_edt_z");
