@@ -269,6 +269,24 @@ int t3d_mc_vertices_f32(const void* field_f32, int Z, int H, int W, double level
 int t3d_vertex_normals(const void* verts_f32, int64_t V, const void* faces, int64_t F, int faces_are_i64, void* normals_f32,
                        void* stream);
 
+/* ---- device-side mesh consumers: the step right after the path ----------------------------- */
+
+/* glb_exporter.py:52-91 create_layer_colors: rgba_u8 (V,4) = grey (200,200,200,255); red where first_start <= z <=
+ * first_end (if has_first); blue where last_start <= z <= last_end (if has_last; blue wins), z = vertex column 0 compared
+ * in float64 as numpy does. */
+int t3d_layer_colors(const void* verts_f32, int64_t V, int has_first, double first_start, double first_end, int has_last,
+                     double last_start, double last_end, void* rgba_u8, void* stream);
+
+/* obj_exporter.py:25-31 as text formatting on the device, two-phase: t3d_obj_measure computes every line's length and
+ * their scan into `workspace` and the total (device uint64); the caller allocates total + 1 bytes; t3d_obj_emit writes
+ * "v %.6f %.6f %.6f\n" per vertex, one blank line, "f a b c\n" (1-based) per face -- byte-identical to the reference's
+ * loop (the two comment lines and the blank line in front of the body stay with the host). */
+int64_t t3d_obj_workspace_bytes(int64_t V, int64_t F);
+int t3d_obj_measure(const void* verts_f32, int64_t V, const void* faces, int64_t F, int faces_are_i64, void* total_len_u64,
+                    void* workspace, void* stream);
+int t3d_obj_emit(const void* verts_f32, int64_t V, const void* faces, int64_t F, int faces_are_i64, const void* total_len_u64,
+                 const void* workspace, void* out_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -99,9 +99,13 @@ def test_repeated_orchestrator_calls_are_memoised(eng, oracle):
         v2, f2 = se.extract_manifold_surface(sm1, depths, 95.03 / H, 143.1 / W)
         assert lib.t3d_launch_count() == n1                  # no kernel ran: served from the device cache
         assert v2 is not v1 and np.array_equal(v1, v2) and np.array_equal(f1, f2)
-        v2[:, 0] += 1.0                                      # callers may scribble on their copy ...
+        with pytest.raises(ValueError):                       # returned arrays are read-only (identity-cached device mesh) ...
+            v2[:, 0] += 1.0
+        mine_v = v2.copy()                                    # ... an edited copy is a different array: measured as given
+        mine_v[:, 0] *= 2.0
+        assert abs(se.calculate_mesh_volume(mine_v, f2) - 2.0 * se.calculate_mesh_volume(v2, f2)) <= 1e-9 * se.calculate_mesh_volume(mine_v, f2)
         v3, _ = se.extract_manifold_surface(sm1, depths, 95.03 / H, 143.1 / W)
-        assert np.array_equal(v3, v1)                        # ... the cache stays pristine
+        assert np.array_equal(v3, v1)
         v4, _ = se.extract_manifold_surface(sm1, depths, 95.03 / H, 143.1 / W, add_padding=False)
         assert lib.t3d_launch_count() > n1 and not np.array_equal(v4[:100], v1[:100])
         # a caller-owned copy of the grid is a different array: no stale hits

@@ -707,11 +707,14 @@ def mesh_from_host(vertices: np.ndarray, faces: np.ndarray) -> DeviceMesh:
     if m is not None and meshes.lookup(faces) is m:
         return m
     dev = _require_cuda()
-    v = torch.from_numpy(np.ascontiguousarray(vertices, dtype=np.float32)).to(dev)
     f = np.ascontiguousarray(faces)
     if f.dtype not in (np.int32, np.int64):
         f = f.astype(np.int64)
-    return DeviceMesh(v, torch.from_numpy(f).to(dev))
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", UserWarning)  # read-only ndarray -> tensor (we only read it)
+        v = torch.from_numpy(np.ascontiguousarray(vertices, dtype=np.float32)).to(dev)
+        return DeviceMesh(v, torch.from_numpy(f).to(dev))
 
 
 # ----------------------------------------------------------------------------------------------------------

@@ -4,7 +4,9 @@ kernels.  Same class / method names, parameter names/order and defaults, same pr
 failure (surface_extractor.py:74-75) -- except that a missing libt3d.so / CUDA device raises (no CPU fallback).
 
 Returned vertices are float32 (V,3) [z_mm, y_mm, x_mm], lexicographically sorted and de-duplicated exactly like
-np.unique(axis=0); faces are int64 (F,3) in the reference's cube order with degenerate faces dropped.
+np.unique(axis=0); faces are int64 (F,3) in the reference's cube order with degenerate faces dropped.  Both arrays
+are READ-ONLY (copy them to edit): the device mesh they came from is recognised by array identity, so
+calculate_mesh_volume / calculate_surface_area / the exporters do not upload them again.
 """
 from __future__ import annotations
 
@@ -43,8 +45,10 @@ class SurfaceExtractor:
                 mesh = engine.extract_surface(dv, slice_depths, mm_per_pixel_y, mm_per_pixel_x, manifold, add_padding)
                 if cacheable:
                     dv.memo[key] = mesh
-            vertices = engine.download(mesh.verts)      # fresh, writable host arrays on every call
-            faces = engine.download(mesh.faces)
+            vertices = engine.download(mesh.verts)      # fresh host arrays on every call, read-only: the device copy
+            faces = engine.download(mesh.faces)         # is recognised by array identity (volume / area / export)
+            vertices.flags.writeable = False
+            faces.flags.writeable = False
             engine.meshes.register(vertices, mesh)
             engine.meshes.register(faces, mesh)
             self.last_mesh = mesh
@@ -89,6 +93,8 @@ class SurfaceExtractor:
             mesh = engine.extract_surface(None, slice_depths, mm_per_pixel_y, mm_per_pixel_x, False, False, field=f.contiguous(),
                                           level=level)
             vertices, faces = engine.download(mesh.verts), engine.download(mesh.faces)
+            vertices.flags.writeable = False
+            faces.flags.writeable = False
             engine.meshes.register(vertices, mesh)
             engine.meshes.register(faces, mesh)
             self.last_mesh, self.last_n_ambiguous = mesh, mesh.n_ambiguous
