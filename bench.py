@@ -465,7 +465,7 @@ def run_ours(args, Z, H, W):
     if world == 1 and not args.no_cpu:
         from oracle import cpu_ref
         cpu_ref.build()
-        secs, vox_s, n_sl = cpu_sample(Z, H, W, 64, 1)
+        secs, vox_s, n_sl = cpu_sample(Z, H, W, 96, 1)
         line["cpu_baseline"] = {"value": vox_s / secs / 1e9, "unit": "Gvoxels/s", "cores": 1, "kind": "port",
                                 "sample": "central z-slab of %d slices x %dx%d of the same phantom, oracle/cpu_ref.py "
                                 "(scipy.ndimage is single-threaded), %.1f s" % (n_sl, H, W, secs)}
