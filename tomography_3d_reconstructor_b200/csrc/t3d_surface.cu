@@ -242,7 +242,8 @@ __global__ void __launch_bounds__(SC_THREADS) k_scan_lookback(const uint32_t* __
 
 extern "C" int64_t t3d_scan_workspace_bytes(int64_t n, int n_arrays)
 {
-    const int64_t nb = (n + SC_TILE - 1) / SC_TILE;
+    // sized for the smallest tile any scan-like kernel of this file uses (k_unique_fused: SC_THREADS * 4 items)
+    const int64_t nb = (n + SC_THREADS * 4 - 1) / (SC_THREADS * 4);
     return (nb * n_arrays + 16) * 8 + 256;
 }
 
@@ -638,6 +639,8 @@ extern "C" int64_t t3d_canonicalize_fast_workspace_bytes(int64_t V, int64_t F)
 // np.unique on the sorted sequence in ONE pass: head flags + strict order check, exclusive scan of the heads (decoupled
 // look-back, same tile protocol as k_scan_lookback), scatter of the unique vertices and of the old -> new id map.
 // n_unique_out receives V'.
+#define UQ_ITEMS 4   // fewer items per thread than the plain scan: three floats + an index per item live in registers
+#define UQ_TILE (SC_THREADS * UQ_ITEMS)
 __global__ void __launch_bounds__(SC_THREADS) k_unique_fused(const float* __restrict__ verts, const uint32_t* __restrict__ perm, int64_t V_cap,
                                                              const unsigned long long* __restrict__ V_dev, float* __restrict__ out_verts,
                                                              uint32_t* __restrict__ newid, unsigned long long* __restrict__ desc, int n_tiles,
@@ -649,21 +652,21 @@ __global__ void __launch_bounds__(SC_THREADS) k_unique_fused(const float* __rest
     const int64_t n = dev_n(V_cap, V_dev);
     volatile unsigned long long* d = desc;
     __shared__ int s_tile;
-    __shared__ uint32_t s_kz[SC_TILE + 1], s_ky[SC_TILE + 1], s_kx[SC_TILE + 1];   // [0] = last element of the previous tile
-    __shared__ uint32_t s_part[SC_ITEMS * (SC_THREADS / 32)];                     // heads per (k, warp), then their exclusive scan
+    __shared__ uint32_t s_kz[UQ_TILE + 1], s_ky[UQ_TILE + 1], s_kx[UQ_TILE + 1];   // [0] = last element of the previous tile
+    __shared__ uint32_t s_part[UQ_ITEMS * (SC_THREADS / 32)];                     // heads per (k, warp), then their exclusive scan
     __shared__ unsigned long long s_prefix;
     if (threadIdx.x == 0) s_tile = (int)atomicAdd(ticket, 1u);
     __syncthreads();
     const int tile = s_tile;
-    const int64_t need = (n + SC_TILE - 1) / SC_TILE;
+    const int64_t need = (n + UQ_TILE - 1) / UQ_TILE;
     n_tiles = (int)(need < 1 ? 1 : (need < n_tiles ? need : n_tiles));
     if (tile >= n_tiles) return;
-    const int64_t base = (int64_t)tile * SC_TILE;
+    const int64_t base = (int64_t)tile * UQ_TILE;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    uint32_t src[SC_ITEMS];
-    float vz[SC_ITEMS], vy[SC_ITEMS], vx[SC_ITEMS];
+    uint32_t src[UQ_ITEMS];
+    float vz[UQ_ITEMS], vy[UQ_ITEMS], vx[UQ_ITEMS];
 #pragma unroll
-    for (int k = 0; k < SC_ITEMS; ++k) {
+    for (int k = 0; k < UQ_ITEMS; ++k) {
         const int e = k * SC_THREADS + tid;
         if (base + e < n) {
             src[k] = perm[base + e];
@@ -677,11 +680,11 @@ __global__ void __launch_bounds__(SC_THREADS) k_unique_fused(const float* __rest
         s_kz[0] = float_key(b[0]); s_ky[0] = float_key(b[1]); s_kx[0] = float_key(b[2]);
     }
     __syncthreads();
-    uint32_t ball[SC_ITEMS];
+    uint32_t ball[UQ_ITEMS];
     uint32_t myhead = 0;
     bool out_of_order = false;
 #pragma unroll
-    for (int k = 0; k < SC_ITEMS; ++k) {
+    for (int k = 0; k < UQ_ITEMS; ++k) {
         const int e = k * SC_THREADS + tid;
         bool h = false;
         if (base + e < n) {
@@ -699,12 +702,17 @@ __global__ void __launch_bounds__(SC_THREADS) k_unique_fused(const float* __rest
     if (out_of_order) atomicOr(bad, 1ull);
     __syncthreads();
     if (tid < 32) {
-        // exclusive scan of the 64 partial counts (two per lane), tile aggregate, look-back
-        const uint32_t p0 = s_part[2 * lane], p1 = s_part[2 * lane + 1];
-        const uint32_t incl = warp_incl_scan(p0 + p1);
+        // exclusive scan of the partial counts (UQ_ITEMS * 8 of them, spread over the lanes), tile aggregate, look-back
+        constexpr int PER_LANE = UQ_ITEMS * (SC_THREADS / 32) / 32;
+        static_assert(PER_LANE >= 1 && PER_LANE * 32 == UQ_ITEMS * (SC_THREADS / 32), "partials must spread evenly over a warp");
+        uint32_t pv[PER_LANE], psum = 0;
+#pragma unroll
+        for (int t = 0; t < PER_LANE; ++t) { pv[t] = s_part[PER_LANE * lane + t]; psum += pv[t]; }
+        const uint32_t incl = warp_incl_scan(psum);
         const uint32_t agg = __shfl_sync(0xffffffffu, incl, 31);
-        s_part[2 * lane] = incl - p0 - p1;
-        s_part[2 * lane + 1] = incl - p1;
+        uint32_t runp = incl - psum;
+#pragma unroll
+        for (int t = 0; t < PER_LANE; ++t) { s_part[PER_LANE * lane + t] = runp; runp += pv[t]; }
         unsigned long long prefix = 0;
         if (tile == 0) {
             if (tid == 0) { d[0] = SC_FLAG_P | (unsigned long long)agg; }
@@ -736,7 +744,7 @@ __global__ void __launch_bounds__(SC_THREADS) k_unique_fused(const float* __rest
     const uint32_t tile_prefix = (uint32_t)s_prefix;
     const uint32_t lt = (1u << lane) - 1u;
 #pragma unroll
-    for (int k = 0; k < SC_ITEMS; ++k) {
+    for (int k = 0; k < UQ_ITEMS; ++k) {
         const int e = k * SC_THREADS + tid;
         if (base + e < n) {
             const uint32_t h = (myhead >> k) & 1u;
@@ -760,7 +768,7 @@ static int canonical_tail(const float* vin, const uint32_t* perm, int64_t V, con
     void* stream = (void*)st;
     {
         // workspace as in t3d_exclusive_scan_u32_dev: [tile descriptors][ticket], zeroed per use
-        const int64_t nb = (V + SC_TILE - 1) / SC_TILE;
+        const int64_t nb = (V + UQ_TILE - 1) / UQ_TILE;
         const size_t desc_bytes = (size_t)nb * 8;
         T3D_CUDA(cudaMemsetAsync(scan_ws, 0, desc_bytes + 64, st));
         k_unique_fused<<<(unsigned)nb, SC_THREADS, 0, st>>>(vin, perm, V, V_dev, (float*)verts_out, newid, (unsigned long long*)scan_ws,
