@@ -114,3 +114,36 @@ def test_repeated_orchestrator_calls_are_memoised(eng, oracle):
         v5, f5 = se.extract_manifold_surface(mine, depths, 95.03 / H, 143.1 / W)
         ref = oracle.extract_manifold_surface(mine, depths, 95.03 / H, 143.1 / W)
         assert np.array_equal(v5, ref[0]) and np.array_equal(f5, ref[1])
+
+
+def test_config0_real_generator_stack_through_the_classes(eng, oracle):
+    """BASELINE configs[0]: the 104-slice stack the reference's own generator + loader produce (golden fixture) through
+    the drop-in classes: grid, depths and voxel volume equal the REFERENCE's outputs; mesh and volumes equal the oracle's."""
+    import contextlib
+    import io
+    import os
+    from tomography_3d_reconstructor_b200 import SurfaceExtractor, VolumeCalculator, VoxelProcessor
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "config0_stack.npz"))
+    shape = tuple(int(v) for v in g["shape"])
+    n = int(np.prod(shape))
+    masks = np.unpackbits(g["masks_bits"])[:n].reshape(shape).astype(bool)
+    sides = tuple(int(s) for s in g["sides"])
+    mm_x, mm_y = 143.1 / 512, 95.03 / 512
+    with contextlib.redirect_stdout(io.StringIO()):
+        vp, se, vc = VoxelProcessor(), SurfaceExtractor(), VolumeCalculator()
+        vox = vp.create_voxel_data([m for m in masks], True, *sides)
+        depths = vp.calculate_slice_depths(6.0)
+        vol = vc.calculate_voxel_volume_variable_depth(vox, mm_x, mm_y, depths)
+        bb = vc.calculate_bounding_box_variable_depth(vox, mm_x, mm_y, depths)
+        sm = vp.smooth_voxel_data(vox, 3, True)
+        v, f = se.extract_manifold_surface(sm, depths, mm_y, mm_x)
+        mv = se.calculate_mesh_volume(v, f)
+    assert np.array_equal(np.packbits(vox), g["voxel_bits"]) and int(vox.sum()) == 8030338
+    assert np.array_equal(depths, g["slice_depths"])
+    assert vol == float(g["volume"]) == 28658.498565015263
+    assert np.array_equal(np.array([bb["x"], bb["y"], bb["z"]], dtype=np.float64), g["bbox"])
+    ref = oracle.reference_pipeline((masks * np.uint8(255)), 200, sides, 6.0, 143.1, 95.03)
+    assert np.array_equal(sm, ref["smoothed"])
+    assert np.array_equal(v, ref["vertices"]) and np.array_equal(f, ref["faces"])
+    assert abs(mv - ref["mesh_volume"]) <= 1e-6 * ref["mesh_volume"]
+    assert se.last_n_ambiguous == ref["n_ambiguous"]

@@ -179,3 +179,20 @@ def test_edt_oracle(oracle):
     assert sdf[3, 4, 6] > 0 and sdf[0, 0, 0] < 0
     assert sdf[2, 3, 4] == 1.0 and sdf[1, 3, 4] == -1.0
     assert np.array_equal(oracle.squared_edt_index(vol)[3, 4:6, 6], [4, 4])
+
+
+def test_config0_real_generator_stack_known_answer(oracle):
+    """BASELINE configs[0] from the reference's OWN generator + loader (tools/make_golden_config0.py):
+    the oracle's voxel path must reproduce the reference's grid, slice depths and voxel volume bit for bit."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "config0_stack.npz"))
+    shape = tuple(int(v) for v in g["shape"])
+    n = int(np.prod(shape))
+    masks = np.unpackbits(g["masks_bits"])[:n].reshape(shape).astype(bool)
+    vox = oracle.create_voxel_data([m for m in masks], True)
+    assert np.array_equal(np.packbits(vox), g["voxel_bits"])
+    assert int(vox.sum()) == int(g["active"]) == 8030338
+    depths = oracle.calculate_slice_depths(6.0, *(int(s) for s in g["sides"]))
+    assert np.array_equal(depths, g["slice_depths"])
+    vol = oracle.calculate_voxel_volume_variable_depth(vox, 143.1 / 512, 95.03 / 512, depths)
+    assert vol == float(g["volume"]) == 28658.498565015263
