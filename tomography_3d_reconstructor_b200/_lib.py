@@ -51,7 +51,7 @@ SIGNATURES = {
     "t3d_mesh_measure": (_i, [_vp, _i64, _vp, _i64, _i, _vp, _vp, _vp]),
     "t3d_exclusive_scan_u32_dev": (_i, [_vp, _vp, _i64, _i64, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "t3d_mc_words_dev": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _u32, _vp, _vp, _vp, _vp, _vp]),
-    "t3d_mc_emit_dev": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _u32, _vp, _u32, _u32, _vp, _vp, _vp]),
+    "t3d_mc_emit_dev": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _u32, _vp, _u32, _u32, _vp, _vp, _i, _vp]),
     "t3d_mc_vertices_dev": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _u32, _i, _i, _vp, _vp, _i, _dbl, _dbl, _i, _i, _vp, _vp]),
     "t3d_mesh_canonicalize_fast_dev": (_i, [_vp, _i64, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "t3d_mesh_measure_dev": (_i, [_vp, _vp, _i64, _vp, _i, _vp, _vp, _vp]),

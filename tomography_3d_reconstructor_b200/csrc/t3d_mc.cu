@@ -273,6 +273,9 @@ __device__ __forceinline__ unsigned long long vkey(int axis, int z, int y, int x
     return (unsigned long long)axis | ((unsigned long long)x << 2) | ((unsigned long long)y << 22) | ((unsigned long long)z << 42);
 }
 
+// PARTS: 1 = vertex keys only, 2 = faces only, 3 = both (the keys are all the vertex kernel needs, so the faces can be
+// emitted concurrently with it on another stream)
+template <int PARTS>
 __global__ void __launch_bounds__(128) k_mc_emit(EmitArgs a)
 {
     // per-thread tables indexed by cube edge (0..11), thread-major => bank-conflict free; the corner -> vertex id
@@ -281,12 +284,12 @@ __global__ void __launch_bounds__(128) k_mc_emit(EmitArgs a)
     __shared__ uint32_t s_base[12][128];
     __shared__ uint32_t s_mask[12][128];
     __shared__ uint32_t s_next[4][128];   // ids of the y/z-edge vertices at bit 0 of the next word (edges 1, 5, 9, 10 at b = 31)
-    {
+    if (PARTS & 2) {
         const int4* src = reinterpret_cast<const int4*>(&g_tri_table[0][0]);
         int4* dst = reinterpret_cast<int4*>(&s_tri[0][0]);
         for (int i = threadIdx.x; i < 256; i += blockDim.x) dst[i] = src[i];
+        __syncthreads();
     }
-    __syncthreads();
     const uint32_t tid = threadIdx.x;
     const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     if (a.sizes) {
@@ -307,7 +310,7 @@ __global__ void __launch_bounds__(128) k_mc_emit(EmitArgs a)
     const int x0 = w << 5;
 
     // ---- keys of the vertices this word owns
-    {
+    if (PARTS & 1) {
         uint32_t id = bX00;
         for (uint32_t q = m.X00; q;) { const int b = __ffs(q) - 1; q &= q - 1; a.vkeys[id++] = vkey(2, z, y, x0 + b); }
         id = bY0;
@@ -315,7 +318,7 @@ __global__ void __launch_bounds__(128) k_mc_emit(EmitArgs a)
         id = bZ0;
         for (uint32_t q = m.Z0; q;) { const int b = __ffs(q) - 1; q &= q - 1; a.vkeys[id++] = vkey(0, z, y, x0 + b); }
     }
-    if (!m.act) return;
+    if (!(PARTS & 2) || !m.act) return;
 
     // ---- bases of the neighbouring words whose vertices our cubes use (looked up only when they own any)
     const uint32_t Hs = (uint32_t)a.g.Hs;
@@ -565,7 +568,7 @@ extern "C" int t3d_mc_emit(const void* sign_bits, int Zs, int Hs, int Ws, int z_
     a.faces = (int32_t*)faces_i32;
     a.sizes = nullptr;
     a.cap_verts = a.cap_faces = 0xffffffffu;
-    k_mc_emit<<<(n_active + 127) / 128, 128, 0, (cudaStream_t)stream>>>(a);
+    k_mc_emit<3><<<(n_active + 127) / 128, 128, 0, (cudaStream_t)stream>>>(a);
     T3D_CHECK_LAUNCH("t3d_mc_emit");
     t3d_count_launches(1);
     return 0;
@@ -633,7 +636,7 @@ extern "C" int t3d_mc_words_dev(const void* sign_bits, int Zs, int Hs, int Ws, i
 extern "C" int t3d_mc_emit_dev(const void* sign_bits, int Zs, int Hs, int Ws, int z_begin, int z_end, const void* ballots_u32,
                                const void* chunkbase_u32, const void* aw_idx_u32, const void* aw_base_u32, uint32_t cap_active,
                                const void* sizes_u64, uint32_t cap_verts, uint32_t cap_faces, void* vkeys_u64, void* faces_i32,
-                               void* stream)
+                               int parts, void* stream)
 {
     EmitArgs a;
     if (int rc = make_grid(a.g, sign_bits, Zs, Hs, Ws, z_begin, z_end, "t3d_mc_emit_dev")) return rc;
@@ -650,7 +653,10 @@ extern "C" int t3d_mc_emit_dev(const void* sign_bits, int Zs, int Hs, int Ws, in
     a.cap_faces = cap_faces;
     a.vkeys = (unsigned long long*)vkeys_u64;
     a.faces = (int32_t*)faces_i32;
-    k_mc_emit<<<(cap_active + 127) / 128, 128, 0, (cudaStream_t)stream>>>(a);
+    const unsigned ge = (cap_active + 127) / 128;
+    if ((parts & 3) == 1) k_mc_emit<1><<<ge, 128, 0, (cudaStream_t)stream>>>(a);
+    else if ((parts & 3) == 2) k_mc_emit<2><<<ge, 128, 0, (cudaStream_t)stream>>>(a);
+    else k_mc_emit<3><<<ge, 128, 0, (cudaStream_t)stream>>>(a);
     T3D_CHECK_LAUNCH("t3d_mc_emit_dev");
     t3d_count_launches(1);
     return 0;

@@ -209,35 +209,31 @@ static int reconstruct_core(const uint32_t* grid, const SlabGeom& g, int H, int 
     RUN(t3d_exclusive_scan_u32_dev(ws + L.aw_cnt, ws + L.aw_base, cap_active, cap_active, 4, 0, 0, R + R_NACTIVE, R + R_NX,
                                    ws + L.scan2, st));
     k_finalize_sizes<<<1, 1, 0, st>>>(R, cap_active, cap_verts, cap_faces);
+    // The vertex kernel only needs the keys: the faces are emitted on the side stream at the same time (the two kernels
+    // have different bottlenecks: dependent loads vs. float64 issue), then the measures run there as before.
     RUN(t3d_mc_emit_dev(ws + L.sign, Zp, Hp, Wp, g.z_begin, g.z_end, ws + L.ballots, ws + L.chunkbase, ws + L.aw_idx, ws + L.aw_base,
-                        cap_active, R + R_NACTIVE, cap_verts, cap_faces, ws + L.vkeys, ws + L.faces_raw, st));
-    // (running the z-edge sort of the structured ordering on the side stream, under the evaluation of the x/y-edge
-    // vertices, was measured: no gain -- the two compete for the same issue slots -- so the flow stays serial)
-    if (cap_zverts) {
-        RUN(t3d_mc_vertices_dev(surf, Zl, H, W, pad, 1, weights3_host, ws + L.vkeys, R + R_NACTIVE, cap_verts, 1, g.z_offset, cum_f64,
-                                adj_f64, n_cum, mm_y, mm_x, scale_in_f64, 7, ws + L.verts_raw, st));
-        // ---- mesh volume / area on the emitted mesh (side stream, concurrent with the canonical ordering), canonical mesh
-        T3D_CUDA(cudaStreamWaitEvent(st, side->e[3], 0));   // the bbox reduction is done with the side stream
-        T3D_CUDA(cudaEventRecord(side->e[4], st));
-        T3D_CUDA(cudaStreamWaitEvent(side->s, side->e[4], 0));
-        RUN(t3d_mesh_measure_dev(ws + L.verts_raw, ws + L.faces_raw, cap_faces, R + R_NT, 0, R + R_VOLUME_F64, ws + L.measure, side->s));
-        T3D_CUDA(cudaEventRecord(side->e[5], side->s));
+                        cap_active, R + R_NACTIVE, cap_verts, cap_faces, ws + L.vkeys, ws + L.faces_raw, 1, st));
+    T3D_CUDA(cudaEventRecord(side->e[4], st));
+    T3D_CUDA(cudaStreamWaitEvent(side->s, side->e[4], 0));
+    RUN(t3d_mc_emit_dev(ws + L.sign, Zp, Hp, Wp, g.z_begin, g.z_end, ws + L.ballots, ws + L.chunkbase, ws + L.aw_idx, ws + L.aw_base,
+                        cap_active, R + R_NACTIVE, cap_verts, cap_faces, ws + L.vkeys, ws + L.faces_raw, 2, side->s));
+    T3D_CUDA(cudaEventRecord(side->e[6], side->s));
+    RUN(t3d_mc_vertices_dev(surf, Zl, H, W, pad, 1, weights3_host, ws + L.vkeys, R + R_NACTIVE, cap_verts, 1, g.z_offset, cum_f64,
+                            adj_f64, n_cum, mm_y, mm_x, scale_in_f64, 7, ws + L.verts_raw, st));
+    // ---- mesh volume / area on the emitted mesh (side stream, concurrent with the canonical ordering), canonical mesh
+    T3D_CUDA(cudaEventRecord(side->e[7], st));
+    T3D_CUDA(cudaStreamWaitEvent(side->s, side->e[7], 0));
+    RUN(t3d_mesh_measure_dev(ws + L.verts_raw, ws + L.faces_raw, cap_faces, R + R_NT, 0, R + R_VOLUME_F64, ws + L.measure, side->s));
+    T3D_CUDA(cudaEventRecord(side->e[5], side->s));
+    T3D_CUDA(cudaStreamWaitEvent(st, side->e[6], 0));   // faces emitted (and, earlier on that stream, the bbox reduction)
+    if (cap_zverts)
         RUN(t3d_mesh_canonicalize_structured_dev(ws + L.verts_raw, ws + L.vkeys, cap_verts, R + R_NACTIVE, R + R_VRAW, Zp, Hp, Wp,
                                                  ws + L.chunkbase, ws + L.aw_base, cap_active, g.z_offset, 1, cum_f64, adj_f64, n_cum,
                                                  zkey_bits, cap_zverts, cap_g0, ws + L.faces_raw, cap_faces, R + R_NT, verts_out_f32,
                                                  faces_out_i64, nullptr, R + R_VCANON, R + R_NG0, ws + L.canon, 3, st));
-    } else {
-        RUN(t3d_mc_vertices_dev(surf, Zl, H, W, pad, 1, weights3_host, ws + L.vkeys, R + R_NACTIVE, cap_verts, 1, g.z_offset, cum_f64,
-                                adj_f64, n_cum, mm_y, mm_x, scale_in_f64, 7, ws + L.verts_raw, st));
-        // ---- mesh volume / area on the emitted mesh (side stream, concurrent with the canonical sort), canonical mesh
-        T3D_CUDA(cudaStreamWaitEvent(st, side->e[3], 0));   // the bbox reduction is done with the side stream
-        T3D_CUDA(cudaEventRecord(side->e[4], st));
-        T3D_CUDA(cudaStreamWaitEvent(side->s, side->e[4], 0));
-        RUN(t3d_mesh_measure_dev(ws + L.verts_raw, ws + L.faces_raw, cap_faces, R + R_NT, 0, R + R_VOLUME_F64, ws + L.measure, side->s));
-        T3D_CUDA(cudaEventRecord(side->e[5], side->s));
+    else
         RUN(t3d_mesh_canonicalize_fast_dev(ws + L.verts_raw, cap_verts, R + R_VRAW, ws + L.faces_raw, cap_faces, R + R_NT,
                                            verts_out_f32, faces_out_i64, nullptr, R + R_VCANON, ws + L.canon, st));
-    }
     if (g.want_ghost || g.want_lead)
         k_count_plane_vertices<<<1, 64, 0, st>>>((const float*)verts_out_f32, R + R_VCANON, g.z_ghost, g.z_lead, g.want_ghost,
                                                  g.want_lead, R + R_NGHOST, R + R_NLEAD);
