@@ -140,7 +140,7 @@ def reconstruct_sdf(masks_u8: torch.Tensor, threshold: int, side_counts, total_d
 # ----------------------------------------------------------------------------------------------------------------
 # fused path: the whole step as ONE enqueue (t3d_reconstruct), captured in a CUDA graph
 # ----------------------------------------------------------------------------------------------------------------
-R_NACTIVE, R_NX, R_NY, R_NZ, R_NT, R_VCANON, R_FCANON, R_UNVERIFIED, R_OVERFLOW = range(9)
+R_NACTIVE, R_NX, R_NY, R_NZ, R_NT, R_VCANON, R_FCANON, R_UNVERIFIED, R_OVERFLOW = range(9)   # keep in sync with t3d_pipeline.cu
 R_NAMBIGUOUS, R_NEXACT, R_VOLUME, R_AREA, R_BBOX, R_VRAW, R_NG0, R_COUNTS = 9, 10, 11, 12, 13, 16, 25, 32
 
 
@@ -176,7 +176,9 @@ class FusedPlan:
         self.n_res = int(L.t3d_reconstruct_results_len(Z))
         self.res = torch.zeros(self.n_res, dtype=torch.int64, device=device)
         self.res_host = torch.zeros(self.n_res, dtype=torch.int64, pin_memory=True)
+        self.res_np = self.res_host.numpy()
         self.graph, self.graph_ptr = None, None
+        self.last_sizes, self.last_canon, self.last_mesh = None, None, None
         self._ctypes = ctypes
 
     def enqueue(self, masks_u8: torch.Tensor) -> None:
@@ -195,7 +197,9 @@ class FusedPlan:
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
             self.enqueue(masks_u8)
+            self.res_host.copy_(self.res, non_blocking=True)      # the read-back of the result block is a node of the graph
         self.graph, self.graph_ptr = g, masks_u8.data_ptr()
+        self.res_np = self.res_host.numpy()
 
     def run(self, masks_u8: torch.Tensor, use_graph: bool = True):
         """Returns the host result block (numpy int64 view) after one synchronisation."""
@@ -203,9 +207,9 @@ class FusedPlan:
             self.graph.replay()
         else:
             self.enqueue(masks_u8)
-        self.res_host.copy_(self.res, non_blocking=True)
+            self.res_host.copy_(self.res, non_blocking=True)
         torch.cuda.current_stream().synchronize()
-        return self.res_host.numpy()
+        return self.res_np
 
 
 _plans: Dict = {}
@@ -270,32 +274,43 @@ def reconstruct_fused(masks_u8: torch.Tensor, threshold: int, side_counts, total
     if use_graph and plan.graph_ptr != masks_u8.data_ptr():
         plan.capture(masks_u8)
     r = plan.run(masks_u8, use_graph)
-    if r[R_UNVERIFIED] and not r[R_OVERFLOW] and plan.caps[3] and _retune(key, int(r[R_NG0]), plan.caps[4]):
+    # (from here on: plain Python on one .tolist() of the header -- this runs between two steps, with the GPU idle)
+    h = r[:R_COUNTS].tolist()
+    if h[R_UNVERIFIED] and not h[R_OVERFLOW] and plan.caps[3] and _retune(key, h[R_NG0], plan.caps[4]):
         _plans.pop(key, None)
         return reconstruct_fused(masks_u8, threshold, side_counts, total_depth_mm, x_length_mm, y_length_mm, iterations,
                                  close_ends, add_padding, use_graph)
-    if r[R_OVERFLOW] or r[R_UNVERIFIED] or r[R_NT] == 0:
+    if h[R_OVERFLOW] or h[R_UNVERIFIED] or h[R_NT] == 0:
         _plans.pop(key, None)
         _hints.pop(key, None)
         return staged()
-    # every later call with a slightly larger mesh still fits thanks to the margin; refresh the hints if it grew
-    _hints[key] = tuple(max(a, b) for a, b in zip(_hints[key], _caps_from(int(r[R_NACTIVE]), int(r[R_VRAW]), int(r[R_NT]),
-                                                                         int(r[R_NZ]), int(r[R_NG0]))))
-    mesh = engine.DeviceMesh(plan.verts[:int(r[R_VCANON])], plan.faces[:int(r[R_FCANON])], int(r[R_NAMBIGUOUS]), int(r[R_NEXACT]))
-    vol_area = r[R_VOLUME:R_VOLUME + 2].view(np.float64)
-    mesh._measures = (float(vol_area[0]), float(vol_area[1]))
-    mesh.n_active, mesh.n_raw = int(r[R_NACTIVE]), (int(r[R_VRAW]), int(r[R_NT]))
-    raw_counts = r[R_COUNTS:R_COUNTS + Z]
-    sm_counts = r[R_COUNTS + Z:R_COUNTS + 2 * Z]
-    bb = tuple(int(v) for v in r[R_BBOX:R_BBOX + 3].view(np.int32))
+    sizes = (h[R_NACTIVE], h[R_VRAW], h[R_NT], h[R_NZ], h[R_NG0])
+    if sizes != plan.last_sizes:
+        # every later call with a slightly larger mesh still fits thanks to the margin; refresh the hints if it grew
+        _hints[key] = tuple(max(a, b) for a, b in zip(_hints[key], _caps_from(*sizes)))
+        plan.last_sizes = sizes
+    canon = (h[R_VCANON], h[R_FCANON])
+    if plan.last_mesh is None or plan.last_canon != canon:
+        plan.last_mesh = engine.DeviceMesh(plan.verts[:canon[0]], plan.faces[:canon[1]])
+        plan.last_canon = canon
+    mesh = plan.last_mesh                       # views of the plan's output buffers: valid until the next run
+    mesh.n_ambiguous, mesh.n_exact = h[R_NAMBIGUOUS], h[R_NEXACT]
+    vol_area = r[R_VOLUME:R_VOLUME + 2].view(np.float64).tolist()
+    mesh._measures = (vol_area[0], vol_area[1])
+    mesh.n_active, mesh.n_raw, mesh.n_z = sizes[0], (sizes[1], sizes[2]), sizes[3]
+    # both voxel volumes in one pass: rows = raw / smoothed per-slice counts (volume_calculator.py:23-35, same order)
+    counts2 = r[R_COUNTS:R_COUNTS + 2 * Z].reshape(2, Z)
+    n = min(Z, len(plan.depths))
+    vols = np.cumsum(counts2[:, :n].astype(np.float64) * plan.vol_weights[:n], axis=1)[:, -1].tolist() if n else [0.0, 0.0]
+    bb = r[R_BBOX:R_BBOX + 3].view(np.int32).tolist()
     return {
         "mesh": mesh,
-        "voxel_volume_mm3": variable_depth_volume(raw_counts, plan.mm_x, plan.mm_y, plan.depths, plan.vol_weights),
-        "processed_voxel_volume_mm3": variable_depth_volume(sm_counts, plan.mm_x, plan.mm_y, plan.depths, plan.vol_weights),
-        "mesh_volume_mm3": abs(float(vol_area[0])),
-        "surface_area_mm2": float(vol_area[1]),
-        "bbox_index": bb if bb[1] >= 0 else None,
-        "active_voxels": int(raw_counts.sum()),
+        "voxel_volume_mm3": vols[0],
+        "processed_voxel_volume_mm3": vols[1],
+        "mesh_volume_mm3": abs(vol_area[0]),
+        "surface_area_mm2": vol_area[1],
+        "bbox_index": tuple(bb) if bb[1] >= 0 else None,
+        "active_voxels": int(counts2[0].sum()),
         "slice_depths": plan.depths,
     }
 

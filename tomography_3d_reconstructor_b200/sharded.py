@@ -293,6 +293,7 @@ class FusedSlabPlan:
         self.res = torch.zeros(self.stride, dtype=torch.int64, device=device)
         self.gathered = torch.zeros((world, self.stride), dtype=torch.int64, device=device)
         self.host = torch.zeros((world, self.stride), dtype=torch.int64, pin_memory=True)
+        self.host_np = self.host.numpy()
         self.graph, self.graph_ptr = None, None
         # where every rank's own per-slice counts sit in its result block (raw, then smoothed)
         self.raw_spans, self.sm_spans = [], []
@@ -348,6 +349,7 @@ class FusedSlabPlan:
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
             self.enqueue(masks_u8)
+            self.host.copy_(self.gathered, non_blocking=True)     # the read-back of the result blocks is a node of the graph
         self.graph, self.graph_ptr = g, masks_u8.data_ptr()
 
     def run(self, masks_u8: torch.Tensor, use_graph: bool = False) -> np.ndarray:
@@ -355,9 +357,9 @@ class FusedSlabPlan:
             self.graph.replay()
         else:
             self.enqueue(masks_u8)
-        self.host.copy_(self.gathered, non_blocking=True)
+            self.host.copy_(self.gathered, non_blocking=True)
         torch.cuda.current_stream().synchronize()
-        return self.host.numpy()
+        return self.host_np
 
 
 _slab_plans: Dict = {}
