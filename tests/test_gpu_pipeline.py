@@ -276,3 +276,29 @@ def test_batch_of_independent_phantoms_matches_the_oracle(eng, oracle):
         assert np.array_equal(got[i]["vertices"], ref["vertices"]) and np.array_equal(got[i]["faces"], ref["faces"])
         assert got[i]["voxel_volume_mm3"] == ref["voxel_volume"] and got[i]["processed_voxel_volume_mm3"] == ref["processed_volume"]
         assert abs(got[i]["mesh_volume_mm3"] - ref["mesh_volume"]) <= 1e-6 * ref["mesh_volume"]
+
+
+@pytest.mark.parametrize("shape", [(1, 9, 33), (2, 5, 7), (3, 64, 31), (4, 3, 257), (5, 33, 130), (9, 40, 1)])
+def test_fused_path_on_degenerate_shapes(eng, oracle, shape):
+    """Tiny / ragged stacks (one or two slices, rows narrower or slightly wider than a machine word, W = 1) through the
+    single-enqueue path against the oracle, bit for bit; also when nothing is left to mesh."""
+    from conftest import random_blobs
+    from tomography_3d_reconstructor_b200 import pipeline
+    rng = np.random.default_rng(sum(shape))
+    Z, H, W = shape
+    occ = random_blobs(rng, shape, 0.6, 1.0) if min(shape) > 1 else rng.random(shape) < 0.7
+    u8 = (occ * 255).astype(np.uint8)
+    sides = (0, Z, 0)
+    args = (200, sides, 6.0, 143.1, 95.03)
+    masks = torch.from_numpy(u8).cuda()
+    pipeline._plans.clear(); pipeline._hints.clear(); pipeline._g0_caps.clear(); pipeline._generic_sort.clear()
+    ref = oracle.reference_pipeline(u8, 200, sides, 6.0, 143.1, 95.03)
+    for rep in range(3):
+        if ref["vertices"] is None:
+            with pytest.raises((RuntimeError, ValueError)):
+                pipeline.reconstruct_fused(masks, *args, use_graph=False)
+            continue
+        out = pipeline.reconstruct_fused(masks, *args, use_graph=(rep == 2))
+        v, f = out["mesh"].verts.cpu().numpy(), out["mesh"].faces.cpu().numpy()
+        assert np.array_equal(v.view(np.uint32), ref["vertices"].view(np.uint32)) and np.array_equal(f, ref["faces"]), rep
+        assert out["voxel_volume_mm3"] == ref["voxel_volume"] and out["processed_voxel_volume_mm3"] == ref["processed_volume"]
