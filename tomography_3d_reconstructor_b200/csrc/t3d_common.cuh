@@ -13,6 +13,14 @@
 
 extern "C" void t3d_set_error(const char* fmt, ...);
 extern "C" void t3d_count_launches(int n);  // bookkeeping for bench.py's gpu_launches (our kernels only)
+// Zeroing of small counters / scan descriptors / bitmaps.  The single-enqueue entry points (t3d_pipeline.cu) zero every
+// such buffer of a step with ONE kernel up front and register the ranges; t3d_zero_async then skips the ranges it finds
+// registered (each memset would be its own node on the critical path of the captured graph) and memsets anything else.
+int t3d_zero_async(void* p, size_t n, cudaStream_t st);
+void t3d_prezero_register(const void* p, size_t n);
+void t3d_prezero_clear(void);
+void t3d_canonicalize_structured_zero_range(int64_t V, int64_t F, uint32_t cap_z, uint32_t cap_g0, int Zs, int64_t* offset,
+                                            int64_t* size);
 
 #define T3D_CHECK_LAUNCH(name)                                                                   \
     do {                                                                                         \

@@ -513,7 +513,7 @@ extern "C" int t3d_mc_flags(const void* sign_bits, int Zs, int Hs, int Ws, int z
     Grid g;
     if (int rc = make_grid(g, sign_bits, Zs, Hs, Ws, z_begin, z_end, "t3d_mc_flags")) return rc;
     cudaStream_t st = (cudaStream_t)stream;
-    T3D_CUDA(cudaMemsetAsync(ballots_u32, 0, sizeof(uint32_t) * (size_t)g.n_rows * g.ncr, st));
+    if (t3d_zero_async(ballots_u32, sizeof(uint32_t) * (size_t)g.n_rows * g.ncr, st)) return 1;
     const int nws4 = g.nws / 4, lanes_x = nws4 < 256 ? nws4 : 256, pzb = 256 / lanes_x;
     const int nz = (g.z_end < Zs ? g.z_end + 1 : Zs) - g.z_begin;
     static const int gy = t3d_rows_per_thread("T3D_FLAGS_ROWS", GY);
@@ -533,7 +533,7 @@ extern "C" int t3d_mc_words(const void* sign_bits, int Zs, int Hs, int Ws, int z
     if (int rc = make_grid(g, sign_bits, Zs, Hs, Ws, z_begin, z_end, "t3d_mc_words")) return rc;
     if (ensure_luts()) return 1;
     cudaStream_t st = (cudaStream_t)stream;
-    T3D_CUDA(cudaMemsetAsync(n_ambiguous_u64, 0, 8, st));
+    if (t3d_zero_async(n_ambiguous_u64, 8, st)) return 1;
     if (n_active == 0) return 0;
     const int64_t n_chunks = (int64_t)g.n_rows * g.ncr;
     k_mc_compact<<<(unsigned)((n_chunks + 255) / 256), 256, 0, st>>>(g, (const uint32_t*)ballots_u32,
@@ -620,7 +620,7 @@ extern "C" int t3d_mc_words_dev(const void* sign_bits, int Zs, int Hs, int Ws, i
     if (int rc = make_grid(g, sign_bits, Zs, Hs, Ws, z_begin, z_end, "t3d_mc_words_dev")) return rc;
     if (ensure_luts()) return 1;
     cudaStream_t st = (cudaStream_t)stream;
-    T3D_CUDA(cudaMemsetAsync(n_ambiguous_u64, 0, 8, st));
+    if (t3d_zero_async(n_ambiguous_u64, 8, st)) return 1;
     if (cap_active == 0) return 0;
     const int64_t n_chunks = (int64_t)g.n_rows * g.ncr;
     k_mc_compact<<<(unsigned)((n_chunks + 255) / 256), 256, 0, st>>>(g, (const uint32_t*)ballots_u32, (const uint32_t*)chunkbase_u32,

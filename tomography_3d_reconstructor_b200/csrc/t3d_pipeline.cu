@@ -6,6 +6,8 @@
 // capacity (the overflow flags in the result block tell the caller to retry with larger capacities).  The call can
 // therefore be captured in a CUDA graph and replayed with a single launch; hole filling of the two end slices and the
 // bounding-box reduction run on an internal side stream, forked and joined with events (also capturable).
+#include <stdint.h>
+
 #include "t3d.h"
 #include "t3d_common.cuh"
 
@@ -161,6 +163,40 @@ static int side_for_current_device(SideStream** out)
 
 #define RUN(call) do { if (int rc__ = (call)) return rc__; } while (0)
 
+// every counter / scan descriptor / bitmap a step needs zeroed, in one node of the graph (see t3d_zero_async)
+struct ZeroSet {
+    uint4* p[6];
+    unsigned long long n16[6];   // sizes in 16-byte units
+    int n;
+};
+__global__ void __launch_bounds__(256) k_zero_ranges(ZeroSet z)
+{
+    for (int k = 0; k < z.n; ++k)
+        for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < z.n16[k];
+             i += (unsigned long long)gridDim.x * blockDim.x)
+            z.p[k][i] = make_uint4(0, 0, 0, 0);
+}
+struct PrezeroGuard {
+    PrezeroGuard() { t3d_prezero_clear(); }
+    ~PrezeroGuard() { t3d_prezero_clear(); }
+    ZeroSet z{};
+    void add(void* p, size_t bytes)
+    {
+        const size_t n16 = bytes / 16;       // ranges are 16-byte aligned; a tail that is not a multiple stays a memset
+        if (!n16 || z.n >= 6 || ((uintptr_t)p & 15)) return;
+        z.p[z.n] = (uint4*)p; z.n16[z.n] = n16; ++z.n;
+        t3d_prezero_register(p, n16 * 16);
+    }
+    int launch(cudaStream_t st)
+    {
+        if (!z.n) return 0;
+        k_zero_ranges<<<T3D_NUM_SMS * 2, 256, 0, st>>>(z);
+        T3D_CHECK_LAUNCH("k_zero_ranges");
+        t3d_count_launches(1);
+        return 0;
+    }
+};
+
 struct SlabGeom {
     int hl, n, hh;        // halo planes below / own planes / halo planes above in the voxel buffers
     int z_begin, z_end;   // owned planes of the local padded sign volume (-1 = to the end)
@@ -261,7 +297,21 @@ extern "C" int t3d_reconstruct(const void* masks_u8, int Z, int H, int W, int th
     const uint8_t* m = (const uint8_t*)masks_u8;
     SideStream* side;
     RUN(side_for_current_device(&side));
-    T3D_CUDA(cudaMemsetAsync(R, 0, sizeof(unsigned long long) * R_COUNTS, st));
+    PrezeroGuard zg;
+    {
+        const int Zp = Z + 2 * pad, Hp = H + 2 * pad, Wp = W + 2 * pad;
+        const int64_t n_chunks = t3d_mc_num_chunks(Zp, Hp, Wp);
+        zg.add(R, sizeof(unsigned long long) * (R_COUNTS + 2 * (size_t)Z));
+        zg.add(ws + L.ballots, (size_t)al(n_chunks * 4));
+        zg.add(ws + L.scan1, (size_t)al(t3d_scan_workspace_bytes(n_chunks, 1)));
+        zg.add(ws + L.scan2, (size_t)al(t3d_scan_workspace_bytes(cap_active, 4)));
+        if (cap_zverts) {
+            int64_t off = 0, size = 0;
+            t3d_canonicalize_structured_zero_range(cap_verts, cap_faces, cap_zverts, cap_g0, Zp, &off, &size);
+            zg.add(ws + L.canon + off, (size_t)size);
+        }
+        RUN(zg.launch(st));
+    }
 
     // ---- create_voxel_data: pack, fill the holes of the end slices (side stream), z gap fill + per-slice counts
     if (close_ends && Z >= 3) {
@@ -346,7 +396,21 @@ extern "C" int t3d_reconstruct_slab(const void* ext_bits, int halo_lo, int n_own
     unsigned long long* R = (unsigned long long*)results_u64;
     SideStream* side;
     RUN(side_for_current_device(&side));
-    T3D_CUDA(cudaMemsetAsync(R, 0, sizeof(unsigned long long) * R_COUNTS, st));
+    PrezeroGuard zg;
+    {
+        const int Zp = Zl + 2 * pad, Hp = H + 2 * pad, Wp = W + 2 * pad;
+        const int64_t n_chunks = t3d_mc_num_chunks(Zp, Hp, Wp);
+        zg.add(R, sizeof(unsigned long long) * (R_COUNTS + 2 * (size_t)Zx));
+        zg.add(ws + L.ballots, (size_t)al(n_chunks * 4));
+        zg.add(ws + L.scan1, (size_t)al(t3d_scan_workspace_bytes(n_chunks, 1)));
+        zg.add(ws + L.scan2, (size_t)al(t3d_scan_workspace_bytes(cap_active, 4)));
+        if (cap_zverts) {
+            int64_t off = 0, size = 0;
+            t3d_canonicalize_structured_zero_range(cap_verts, cap_faces, cap_zverts, cap_g0, Zp, &off, &size);
+            zg.add(ws + L.canon + off, (size_t)size);
+        }
+        RUN(zg.launch(st));
+    }
     if (join_fill) T3D_CUDA(cudaStreamWaitEvent(st, side->e[1], 0));   // hole filling started by t3d_slab_pack
     RUN(t3d_gap_fill(ext_bits, ws + L.bitsB, nullptr, nullptr, Zx, H, W, R + R_COUNTS, st));
     SlabGeom g = {halo_lo, n_own, halo_hi, z_begin, z_end, z_offset, want_ghost, want_lead, z_ghost, z_lead};

@@ -264,7 +264,7 @@ extern "C" int t3d_exclusive_scan_u32_dev(const void* in, void* out, int64_t n_c
     if (nb > 0x7fffffff) { t3d_set_error("t3d_exclusive_scan_u32: too many elements"); return 2; }
     // workspace: [tile descriptors: nb * n_arrays u64][tickets: 16 u32], zeroed for every scan
     const size_t desc_bytes = (size_t)nb * n_arrays * 8;
-    T3D_CUDA(cudaMemsetAsync(workspace, 0, desc_bytes + 64, st));
+    if (t3d_zero_async(workspace, desc_bytes + 64, st)) return 1;
     unsigned long long* desc = (unsigned long long*)workspace;
     unsigned int* tickets = (unsigned int*)((char*)workspace + desc_bytes);
     const unsigned long long* nd = (const unsigned long long*)n_dev_u64;
@@ -320,8 +320,7 @@ extern "C" int t3d_field_sign_lean(const void* occ_bits, int Z, int H, int W, in
     cudaStream_t st = (cudaStream_t)stream;
     const OccView v = t3d_make_view(occ_bits, Z, H, W, pad, 1, weights3);
     const int nwp = t3d_wpr(v.Wp);
-    T3D_CUDA(cudaMemsetAsync(n_exact_u64, 0, 8, st));
-    T3D_CUDA(cudaMemsetAsync(exc_count_u64, 0, 8, st));
+    if (t3d_zero_async(n_exact_u64, 8, st) || t3d_zero_async(exc_count_u64, 8, st)) return 1;
     const int nwp4 = nwp / 4, lanes_x = nwp4 < 256 ? nwp4 : 256, pzb = 256 / lanes_x;
     static const int fy = t3d_rows_per_thread("T3D_SIGN_ROWS", FY);
     dim3 grid((nwp4 + lanes_x - 1) / lanes_x, (v.Hp + fy - 1) / fy, (v.Zp + pzb - 1) / pzb);
@@ -763,25 +762,25 @@ __global__ void __launch_bounds__(SC_THREADS) k_unique_fused(const float* __rest
 static int canonical_tail(const float* vin, const uint32_t* perm, int64_t V, const unsigned long long* V_dev, const void* faces_in,
                           int64_t F, const unsigned long long* F_dev, void* verts_out, void* faces_out_i64, void* faces_out_i32,
                           unsigned long long* counts, uint32_t* flags, uint32_t* pos, uint32_t* newid, void* scan_ws,
-                          unsigned long long* totals, cudaStream_t st)
+                          void* scan_ws_faces, unsigned long long* totals, cudaStream_t st)
 {
     void* stream = (void*)st;
     {
         // workspace as in t3d_exclusive_scan_u32_dev: [tile descriptors][ticket], zeroed per use
         const int64_t nb = (V + UQ_TILE - 1) / UQ_TILE;
         const size_t desc_bytes = (size_t)nb * 8;
-        T3D_CUDA(cudaMemsetAsync(scan_ws, 0, desc_bytes + 64, st));
+        if (t3d_zero_async(scan_ws, desc_bytes + 64, st)) return 1;
         k_unique_fused<<<(unsigned)nb, SC_THREADS, 0, st>>>(vin, perm, V, V_dev, (float*)verts_out, newid, (unsigned long long*)scan_ws,
                                                            (int)nb, (unsigned int*)((char*)scan_ws + desc_bytes), counts + 2, counts);
     }
     if (F > 0) {
         // totals[1] = invalid faces, totals[2] = faces the compaction has to look at (0 when nothing is invalid)
         const unsigned gf = (unsigned)((F + 255) / 256);
-        T3D_CUDA(cudaMemsetAsync(totals + 1, 0, 16, st));
+        if (t3d_zero_async(totals + 1, 16, st)) return 1;
         k_face_remap<<<gf, 256, 0, st>>>((const int32_t*)faces_in, F, newid, flags, (long long*)faces_out_i64, (int32_t*)faces_out_i32,
                                          totals + 1, F_dev);
         k_face_plan<<<1, 1, 0, st>>>(totals + 1, F, F_dev, totals + 2, counts + 1);
-        if (t3d_exclusive_scan_u32_dev(flags, pos, F, F, 1, 0, 0, totals + 2, totals + 3, scan_ws, stream)) return 1;
+        if (t3d_exclusive_scan_u32_dev(flags, pos, F, F, 1, 0, 0, totals + 2, totals + 3, scan_ws_faces, stream)) return 1;
         const unsigned gc = gf < (unsigned)(T3D_NUM_SMS * 8) ? gf : (unsigned)(T3D_NUM_SMS * 8);
         k_face_compact<<<gc, 256, 0, st>>>((const int32_t*)faces_in, F, newid, flags, pos, (long long*)faces_out_i64,
                                            (int32_t*)faces_out_i32, totals + 2);
@@ -820,7 +819,7 @@ static int canonicalize_fast_impl(const void* verts_in, int64_t V, const unsigne
     T3D_CUDA(cub::DeviceRadixSort::SortPairs(temp, temp_bytes, (const unsigned long long*)keys_a, keys_b, (const uint32_t*)iota, perm,
                                              (int)V, 0, 64, st));
     if (canonical_tail(vin, perm, V, V_dev, faces_in, F, F_dev, verts_out, faces_out_i64, faces_out_i32, counts, flags, pos, newid,
-                       scan_ws, totals, st)) return 1;
+                       scan_ws, scan_ws, totals, st)) return 1;
     T3D_CHECK_LAUNCH("t3d_mesh_canonicalize_fast");
     t3d_count_launches(F > 0 ? 5 : 3);
     return 0;
@@ -1033,9 +1032,18 @@ extern "C" int64_t t3d_canonicalize_structured_workspace_bytes(int64_t V, int64_
     b += align256(4 * V);                                                          // newid
     const int64_t tz = (int64_t)sort64_temp_bytes(cap_z > 0 ? cap_z : 1), tg = (int64_t)sort64_temp_bytes(cap_g0 > 0 ? cap_g0 : 1);
     b += align256(tz > tg ? tz : tg);
-    b += align256(t3d_scan_workspace_bytes(n, 1));
-    b += 256;
+    b += 2 * align256(t3d_scan_workspace_bytes(n, 1)) + 256;   // zero tail: unique descriptors, face-scan workspace, totals
     return b;
+}
+
+// the part of the workspace the call needs zeroed on entry (it does so itself unless the range was zeroed up front and
+// registered, see t3d_zero_async): [offset, offset + size) from the start of the workspace
+void t3d_canonicalize_structured_zero_range(int64_t V, int64_t F, uint32_t cap_z, uint32_t cap_g0, int Zs, int64_t* offset,
+                                            int64_t* size)
+{
+    const int64_t n = V > F ? V : F;
+    *size = 2 * align256(t3d_scan_workspace_bytes(n, 1)) + 256;
+    *offset = t3d_canonicalize_structured_workspace_bytes(V, F, cap_z, cap_g0, Zs) - *size;
 }
 
 // verts_in / vkeys: capacity V_cap, true block sizes in sizes_u64 = {n_active, n_x, n_y, n_z, n_t} (device); V_dev_u64 = n_x+n_y+n_z
@@ -1088,6 +1096,7 @@ extern "C" int t3d_mesh_canonicalize_structured_dev(const void* verts_in, const 
     const size_t tz = sort64_temp_bytes(cap_z), tg = sort64_temp_bytes(cap_g0 > 0 ? cap_g0 : 1);
     void* temp = ws; ws += align256((int64_t)(tz > tg ? tz : tg));
     void* scan_ws = ws; ws += align256(t3d_scan_workspace_bytes(n, 1));
+    void* scan_ws_f = ws; ws += align256(t3d_scan_workspace_bytes(n, 1));
     unsigned long long* totals = (unsigned long long*)ws;
     unsigned long long* counts = (unsigned long long*)counts_u64;
     c.zperm = zperm; c.gperm = gperm;
@@ -1100,7 +1109,7 @@ extern "C" int t3d_mesh_canonicalize_structured_dev(const void* verts_in, const 
         t3d_count_launches(2);
     }
     if (phases & 2) {
-        T3D_CUDA(cudaMemsetAsync(counts + 2, 0, 8, st));
+        if (t3d_zero_async(counts + 2, 8, st)) return 1;
         if (cap_g0 > 0) {
             // (shares the radix sort's temporary storage with the z sort: phase 2 must be ordered after phase 1)
             k_canon_gkeys<<<(cap_g0 + 255) / 256, 256, 0, st>>>(c);
@@ -1110,7 +1119,7 @@ extern "C" int t3d_mesh_canonicalize_structured_dev(const void* verts_in, const 
         }
         k_canon_positions<<<(unsigned)((V + 255) / 256), 256, 0, st>>>(c);
         if (canonical_tail(c.verts, c.perm, V, (const unsigned long long*)V_dev_u64, faces_in, F, (const unsigned long long*)F_dev_u64,
-                           verts_out, faces_out_i64, faces_out_i32, counts, flags, pos, newid, scan_ws, totals, st)) return 1;
+                           verts_out, faces_out_i64, faces_out_i32, counts, flags, pos, newid, scan_ws, scan_ws_f, totals, st)) return 1;
         t3d_count_launches((F > 0 ? 5 : 3) + (cap_g0 > 0 ? 1 : 0));
     }
     T3D_CHECK_LAUNCH("t3d_mesh_canonicalize_structured");

@@ -32,6 +32,19 @@ static long long g_launches = 0;
 extern "C" void t3d_count_launches(int n) { g_launches += n; }
 extern "C" int64_t t3d_launch_count(void) { return g_launches; }
 
+struct ZeroRange { const char* p; size_t n; };
+static thread_local ZeroRange g_zero[8];
+static thread_local int g_nzero = 0;
+void t3d_prezero_register(const void* p, size_t n) { if (g_nzero < 8) g_zero[g_nzero++] = {(const char*)p, n}; }
+void t3d_prezero_clear(void) { g_nzero = 0; }
+int t3d_zero_async(void* p, size_t n, cudaStream_t st)
+{
+    for (int k = 0; k < g_nzero; ++k)
+        if ((const char*)p >= g_zero[k].p && (const char*)p + n <= g_zero[k].p + g_zero[k].n) return 0;   // zeroed up front
+    T3D_CUDA(cudaMemsetAsync(p, 0, n, st));
+    return 0;
+}
+
 int t3d_rows_per_thread(const char* env_name, int dflt)
 {
     const char* e = getenv(env_name);
@@ -428,7 +441,7 @@ extern "C" int t3d_gap_fill(const void* in_bits, void* out_bits, const void* lo_
     if (Z <= 0 || H <= 0 || W <= 0) { t3d_set_error("t3d_gap_fill: empty volume"); return 2; }
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t pw4 = (int64_t)H * (t3d_wpr(W) / 4);
-    if (slice_counts_u64) T3D_CUDA(cudaMemsetAsync(slice_counts_u64, 0, sizeof(unsigned long long) * Z, st));
+    if (slice_counts_u64 && t3d_zero_async(slice_counts_u64, sizeof(unsigned long long) * Z, st)) return 1;
     int bx = (int)min((int64_t)32, (pw4 + 511) / 512);
     dim3 grid(bx, Z);
     k_gap_fill<<<grid, 256, 0, st>>>((const uint4*)in_bits, (uint4*)out_bits, (const uint4*)lo_plane, (const uint4*)hi_plane, Z,
@@ -778,7 +791,7 @@ extern "C" int t3d_morph(const void* in_bits, void* out_bits, int Z, int H, int 
     cudaStream_t st = (cudaStream_t)stream;
     const int nw = t3d_wpr(W), nw4 = nw / 4;
     const int64_t vol_words = (int64_t)Z * H * nw;
-    if (slice_counts_u64) T3D_CUDA(cudaMemsetAsync(slice_counts_u64, 0, sizeof(unsigned long long) * Z, st));
+    if (slice_counts_u64 && t3d_zero_async(slice_counts_u64, sizeof(unsigned long long) * Z, st)) return 1;
     {   // all stages in one pass when they fit in shared memory
         int rc = 0;
         if (launch_morph_fused((const uint32_t*)in_bits, (uint32_t*)out_bits, Z, H, W, n_stages, erode_mask,
