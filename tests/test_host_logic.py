@@ -87,3 +87,25 @@ def test_batch_assignment_partitions_the_items():
     assert np.abs(centres - 128).max() <= 0.05 * 256
     r2, c2 = batch.phantom_params(256, 256)
     assert np.array_equal(radii, r2) and np.array_equal(centres, c2)      # deterministic (rng 1234)
+
+
+def test_z_map_value_and_zkey_bits_follow_the_reference_z_map(oracle):
+    """engine.z_map_value = the reference's _apply_variable_slice_depths on grid planes (bit for bit, both padding modes);
+    engine.zkey_bits bounds the float-key span of every cube layer (the bound the structured vertex ordering relies on)."""
+    from tomography_3d_reconstructor_b200 import engine, pipeline
+    for sides, pad in (((20, 64, 20), True), ((3, 18, 3), False), ((0, 7, 0), True), ((64, 384, 64), True)):
+        depths = pipeline.slice_depths(6.0, *sides)
+        cum, adj = engine.z_map_arrays(depths, pad)
+        Zs = sum(sides) + (2 if pad else 0)
+        planes = np.arange(-1, Zs + 1, dtype=np.float32)
+        v = np.zeros((len(planes), 3), dtype=np.float32)
+        v[:, 0] = planes
+        oracle.apply_variable_slice_depths(v, depths, pad)
+        mine = np.array([engine.z_map_value(float(p), cum, adj) for p in planes], dtype=np.float32)
+        assert np.array_equal(mine.view(np.uint32), v[:, 0].view(np.uint32))
+        for z_offset in (0, min(17, Zs - 3)):
+            nb = engine.zkey_bits(depths, pad, Zs - z_offset, z_offset, 1)
+            z = np.array([engine.z_map_value(k + z_offset - 1, cum, adj) for k in range(Zs - z_offset + 1)], dtype=np.float32)
+            span = int(np.diff(z.view(np.uint32).astype(np.int64)).max())
+            assert nb == 32 or span < (1 << nb)
+    assert engine.zkey_bits(np.array([]), True, 10) == 32

@@ -198,7 +198,7 @@ __global__ void __launch_bounds__(EDT_THREADS) k_edt_envelope(EdtPass p)
     const uint32_t* nxt = st + L;
     if (k >= 1) { e_next = *nxt; next_start = (int)(e_next >> 16); }
     int a = 0, bcomp = 0;
-    double rest2 = 0.0;    // (a*s0)^2 + (b*s1)^2 of the current site, in scipy's association order below
+    double a2 = 0.0, b2 = 0.0;   // (a*s0)^2 and (b*s1)^2 of the current site (added in scipy's order below)
     bool have = false;
     off = 0;
     for (int q = 0; q < n; ++q, off += stride) {
@@ -215,10 +215,9 @@ __global__ void __launch_bounds__(EDT_THREADS) k_edt_envelope(EdtPass p)
             a = in0[soff];
             bcomp = NCOMP > 1 ? in1[soff] : 0;
             if (FINAL) {
-                const double t1 = __dmul_rn((double)a, s0), t2 = __dmul_rn((double)bcomp, s1);
-                rest2 = 0.0; (void)rest2;
                 // kept as two products: the sum order below must stay ((t0^2 + t1^2) + t2^2)
-                gk = __dmul_rn(t1, t1); vkd = __dmul_rn(t2, t2);
+                const double t1 = __dmul_rn((double)a, s0), t2 = __dmul_rn((double)bcomp, s1);
+                a2 = __dmul_rn(t1, t1); b2 = __dmul_rn(t2, t2);
             }
             have = true;
         }
@@ -226,7 +225,7 @@ __global__ void __launch_bounds__(EDT_THREADS) k_edt_envelope(EdtPass p)
         if (FINAL) {
             // scipy: dt = (ft - indices) * sampling; sqrt(add.reduce(dt*dt, axis=0)) -- axis order z, y, x
             const double t0 = __dmul_rn((double)dnew, s_new);
-            const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(t0, t0), gk), vkd);
+            const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(t0, t0), a2), b2);
             const float d = sign * (float)sqrt(d2);
             dout[off] = acc ? dout[off] + d : d;
         } else {

@@ -245,6 +245,7 @@ static int reconstruct_core(const uint32_t* grid, const SlabGeom& g, int H, int 
     RUN(t3d_exclusive_scan_u32_dev(ws + L.aw_cnt, ws + L.aw_base, cap_active, cap_active, 4, 0, 0, R + R_NACTIVE, R + R_NX,
                                    ws + L.scan2, st));
     k_finalize_sizes<<<1, 1, 0, st>>>(R, cap_active, cap_verts, cap_faces);
+    t3d_count_launches(1);
     // The vertex kernel only needs the keys: the faces are emitted on the side stream at the same time (the two kernels
     // have different bottlenecks: dependent loads vs. float64 issue), then the measures run there as before.
     RUN(t3d_mc_emit_dev(ws + L.sign, Zp, Hp, Wp, g.z_begin, g.z_end, ws + L.ballots, ws + L.chunkbase, ws + L.aw_idx, ws + L.aw_base,
@@ -273,6 +274,7 @@ static int reconstruct_core(const uint32_t* grid, const SlabGeom& g, int H, int 
     if (g.want_ghost || g.want_lead)
         k_count_plane_vertices<<<1, 64, 0, st>>>((const float*)verts_out_f32, R + R_VCANON, g.z_ghost, g.z_lead, g.want_ghost,
                                                  g.want_lead, R + R_NGHOST, R + R_NLEAD);
+    if (g.want_ghost || g.want_lead) t3d_count_launches(1);
     T3D_CUDA(cudaStreamWaitEvent(st, side->e[5], 0));
     return 0;
 }
