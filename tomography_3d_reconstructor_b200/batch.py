@@ -6,7 +6,7 @@ is copied into the plan's persistent input buffer and the captured CUDA graph is
 device-to-device copy + one graph launch + the download of its mesh."""
 from __future__ import annotations
 
-from typing import Dict, Iterable, List, Sequence, Tuple
+from typing import Dict, Iterable, List, Tuple
 
 import numpy as np
 import torch

@@ -179,7 +179,6 @@ class FusedPlan:
         self.res_np = self.res_host.numpy()
         self.graph, self.graph_ptr = None, None
         self.last_sizes, self.last_canon, self.last_mesh = None, None, None
-        self._ctypes = ctypes
 
     def enqueue(self, masks_u8: torch.Tensor) -> None:
         Z, H, W = self.shape

@@ -10,7 +10,6 @@ Prints one line per check and exits non-zero on a mismatch."""
 import os
 import sys
 
-import numpy as np
 import torch
 import torch.distributed as dist
 
