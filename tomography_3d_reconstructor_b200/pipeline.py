@@ -151,7 +151,6 @@ class FusedPlan:
 
     def __init__(self, shape, threshold, side_counts, total_depth_mm, x_length_mm, y_length_mm, iterations, close_ends,
                  add_padding, caps, device):
-        import ctypes
         L = engine._L()
         self.shape = Z, H, W = tuple(int(v) for v in shape)
         self.threshold, self.close_ends, self.add_padding = int(threshold), bool(close_ends), bool(add_padding)
