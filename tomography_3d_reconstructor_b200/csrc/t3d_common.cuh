@@ -9,7 +9,14 @@
 #include <stdint.h>
 #include <stdio.h>
 
-#define T3D_NUM_SMS 148
+// number of SMs of the current device (queried once per device; 148 on a B200); grids of the persistent-style kernels
+// are sized in multiples of it
+int t3d_num_sms(void);
+#define T3D_NUM_SMS (t3d_num_sms())
+// per-device "done once" flags for state that lives per device (constant memory, function attributes): returns true the
+// first time it is called for (slot, current device)
+bool t3d_first_use_on_device(int slot);
+enum { T3D_ONCE_FILL_HOLES_ATTR = 0, T3D_ONCE_MC_LUTS = 1, T3D_ONCE_SORT_ATTR = 2, T3D_ONCE_SLOTS = 8 };
 
 extern "C" void t3d_set_error(const char* fmt, ...);
 extern "C" void t3d_count_launches(int n);  // bookkeeping for bench.py's gpu_launches (our kernels only)
@@ -145,6 +152,19 @@ __device__ __forceinline__ int64_t dev_n(int64_t cap, const unsigned long long* 
     const unsigned long long v = *p;
     return v < (unsigned long long)cap ? (int64_t)v : cap;
 }
+
+// ---- internal launchers shared between translation units (t3d_voxel.cu) -----------------------------------------------
+// one 6-connected erosion / dilation stage: planes [z0, z0 + nz) of the compact volume `in` -> `out` (pointing at the word
+// of plane z0, row 0, word 0) with its own row / plane strides.  ring: the output is the padded-storage layout, the
+// stage also clears the 4 pad words in front of every row it writes and ring_tail (0 / 1) uint4 behind it.
+int t3d_morph_stage(const uint32_t* in, uint32_t* out, int Z, int H, int W, int z0, int nz, int out_rs, long long out_ps,
+                    bool erode, bool ring, int ring_tail, unsigned long long* counts, cudaStream_t st);
+// fused pack + z gap fill + per-slice counts + extrema (see t3d_voxel.cu)
+bool t3d_pack_gap_supported(const void* masks_u8, int Z, int H, int W, int threshold);
+int t3d_pack_gap_launch(const void* masks_u8, int Z, int H, int W, int threshold, void* out, unsigned long long* counts,
+                        unsigned int* bbox_t, int skip_ends, cudaStream_t st);
+int t3d_close_ends_fixup_launch(const void* masks_u8, int Z, int H, int W, int threshold, const void* filled0, const void* filledT,
+                                void* out, unsigned long long* counts, cudaStream_t st);
 
 // rows each thread of the y-marching stencil kernels walks (tunable through the environment for experiments)
 int t3d_rows_per_thread(const char* env_name, int dflt);

@@ -7,8 +7,10 @@
 // padded-occupancy view + exact field evaluation
 // ------------------------------------------------------------------------------------------------
 struct OccView {
-    const uint32_t* bits;  // (Z, H, nw) packed occupancy
+    const uint32_t* bits;  // packed occupancy: word (z, y, w) at bits[z*ps + y*rs + w], w < nw
     int Z, H, W, nw;
+    int rs;                // row stride in words (= nw for a compact volume)
+    long long ps;          // plane stride in words (= H*nw for a compact volume)
     int pad;               // 0 or 1
     int Zp, Hp, Wp;        // padded extents
     int gaussian;          // 1: field = gaussian(sigma 0.5) of padded occupancy; 0: field = occupancy
@@ -31,7 +33,7 @@ __device__ __forceinline__ uint32_t pbit(const OccView& v, int zp, int yp, int x
 {
     const int z = zp - v.pad, y = yp - v.pad, x = xp - v.pad;
     if (z < 0 || z >= v.Z || y < 0 || y >= v.H || x < 0 || x >= v.W) return 0u;
-    return (v.bits[((int64_t)z * v.H + y) * v.nw + (x >> 5)] >> (x & 31)) & 1u;
+    return (v.bits[(z * v.ps + (long long)y * v.rs) + (x >> 5)] >> (x & 31)) & 1u;
 }
 
 // bits of padded row (zp, yp) at padded x = xs .. xs+4 (x reflected at the padded border)
@@ -39,7 +41,7 @@ __device__ __forceinline__ uint32_t get5(const OccView& v, int zp, int yp, int x
 {
     const int z = zp - v.pad, y = yp - v.pad;
     if (z < 0 || z >= v.Z || y < 0 || y >= v.H) return 0u;
-    const uint32_t* row = v.bits + ((int64_t)z * v.H + y) * v.nw;
+    const uint32_t* row = v.bits + (z * v.ps + (long long)y * v.rs);
     if (xs >= 0 && xs + 4 < v.Wp) {
         const int ox = xs - v.pad;
         const int w = ox >> 5, sh = ox & 31;
@@ -102,7 +104,7 @@ __device__ __forceinline__ uint32_t pword(const OccView& v, int zp, int yp, int 
 {
     const int z = zp - v.pad, y = yp - v.pad;
     if (z < 0 || z >= v.Z || y < 0 || y >= v.H || wp < 0) return 0u;
-    const uint32_t* row = v.bits + ((int64_t)z * v.H + y) * v.nw;
+    const uint32_t* row = v.bits + (z * v.ps + (long long)y * v.rs);
     const uint32_t cur = (wp < v.nw) ? row[wp] : 0u;
     if (!v.pad) return cur;
     const uint32_t prev = (wp - 1 >= 0 && wp - 1 < v.nw) ? row[wp - 1] : 0u;
@@ -115,7 +117,7 @@ __device__ __forceinline__ uint32_t get6(const OccView& v, int zp, int yp, int x
 {
     const int z = zp - v.pad, y = yp - v.pad;
     if (z < 0 || z >= v.Z || y < 0 || y >= v.H) return 0u;
-    const uint32_t* row = v.bits + ((int64_t)z * v.H + y) * v.nw;
+    const uint32_t* row = v.bits + (z * v.ps + (long long)y * v.rs);
     if (xs >= 0 && xs + 5 < v.Wp) {
         const int ox = xs - v.pad;
         const int w = ox >> 5, sh = ox & 31;
@@ -166,14 +168,14 @@ __device__ __forceinline__ void edge_field_values(const OccView& v, const double
     if (oz0 >= 0 && oz0 + NZ <= v.Z && oy0 >= 0 && oy0 + NY <= v.H && ox0 >= 0 && ox0 + 6 <= v.W) {
         const int w = ox0 >> 5, sh = ox0 & 31;
         const bool two = sh > 26;  // the 6-bit window straddles two words
-        const uint32_t* p = v.bits + ((int64_t)oz0 * v.H + oy0) * v.nw + w;
-        const int64_t dzs = (int64_t)v.H * v.nw;
+        const uint32_t* p = v.bits + (oz0 * v.ps + (long long)oy0 * v.rs) + w;
+        const long long dzs = v.ps;
 #pragma unroll
         for (int dy = 0; dy < NY; ++dy) {
             unsigned long long c = 0;
 #pragma unroll
             for (int dz = 0; dz < NZ; ++dz) {
-                const uint32_t* q = p + dz * dzs + dy * v.nw;
+                const uint32_t* q = p + dz * dzs + dy * v.rs;
                 const uint32_t lo = q[0], hi = two ? q[1] : 0u;
                 c |= (unsigned long long)(__funnelshift_r(lo, hi, sh) & 63u) << (6 * dz);
             }
@@ -238,6 +240,7 @@ static inline OccView t3d_make_view(const void* occ_bits, int Z, int H, int W, i
     OccView v;
     v.bits = (const uint32_t*)occ_bits;
     v.Z = Z; v.H = H; v.W = W; v.nw = t3d_wpr(W);
+    v.rs = v.nw; v.ps = (long long)H * v.nw;
     v.pad = pad ? 1 : 0;
     v.Zp = Z + 2 * v.pad; v.Hp = H + 2 * v.pad; v.Wp = W + 2 * v.pad;
     v.gaussian = gaussian ? 1 : 0;
@@ -247,3 +250,18 @@ static inline OccView t3d_make_view(const void* occ_bits, int Z, int H, int W, i
     v.w2 = w3 ? w3[2] : 0x1.14aebe6a24088p-12;
     return v;
 }
+
+// the same (Z,H,W) occupancy stored inside a larger buffer: word (z,y,w) at origin[z*plane_stride + y*row_stride + w]
+static inline OccView t3d_make_view_strided(const void* origin, int Z, int H, int W, int row_stride, long long plane_stride, int pad,
+                                            int gaussian, const double* w3)
+{
+    OccView v = t3d_make_view(origin, Z, H, W, pad, gaussian, w3);
+    v.rs = row_stride; v.ps = plane_stride;
+    return v;
+}
+
+// t3d_mc.cu: vertices of a mesh emitted on a sign volume whose x coordinates are shifted by x_off against the padded
+// grid of `view` (the padded-storage layout of the fused pipeline: x_off = 127)
+int t3d_mc_vertices_view_dev(const OccView& view, int x_off, const void* vkeys_u64, const void* sizes_u64, uint32_t cap_verts,
+                             int unpad_shift, int z_offset, const void* cum_f64, const void* adj_f64, int n_cum, double mm_per_pixel_y,
+                             double mm_per_pixel_x, int scale_in_f64, int which_blocks, void* verts_f32, void* stream);

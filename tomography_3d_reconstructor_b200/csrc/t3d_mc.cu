@@ -30,7 +30,6 @@ struct McLuts {
     uint8_t amb[256];
 };
 __constant__ McLuts c_luts;
-static bool g_luts_ready = false;
 
 static int host_is_ambiguous(int idx)
 {
@@ -49,7 +48,7 @@ static int host_is_ambiguous(int idx)
 
 static int ensure_luts()
 {
-    if (g_luts_ready) return 0;
+    if (!t3d_first_use_on_device(T3D_ONCE_MC_LUTS)) return 0;   // __constant__ memory is per device
     McLuts l;
     for (int i = 0; i < 256; ++i) {
         int n = 0;
@@ -58,7 +57,6 @@ static int ensure_luts()
         l.amb[i] = (uint8_t)host_is_ambiguous(i);
     }
     T3D_CUDA(cudaMemcpyToSymbol(c_luts, &l, sizeof(l)));
-    g_luts_ready = true;
     return 0;
 }
 
@@ -147,7 +145,7 @@ __device__ __forceinline__ WordMasks load_masks(const Grid& g, uint32_t row, int
 // ------------------------------------------------------------------------------------------------
 #define GY 16
 
-__global__ void __launch_bounds__(256, 5) k_mc_flags(Grid g, uint32_t* __restrict__ ballots, int lanes_x, int pz_per_block, int gy)
+__global__ void __launch_bounds__(256, 4) k_mc_flags(Grid g, uint32_t* __restrict__ ballots, int lanes_x, int pz_per_block, int gy)
 {
     const int lx = threadIdx.x % lanes_x, pz = threadIdx.x / lanes_x;
     const int nws4 = g.nws >> 2;
@@ -157,21 +155,20 @@ __global__ void __launch_bounds__(256, 5) k_mc_flags(Grid g, uint32_t* __restric
     const bool hx = (4 * w4 + 4 < g.nws);
     const uint4 vm = valid_mask4(w4, g.Ws), em = valid_mask4(w4, g.Ws - 1);
     const uint4 zero = make_uint4(0, 0, 0, 0);
-    auto row4 = [&](int zz, int yy, uint32_t& nxt) -> uint4 {
-        const uint32_t* p = g.sign + ((int64_t)zz * g.Hs + yy) * g.nws + 4 * w4;
-        nxt = hx ? p[4] : 0u;
-        return *reinterpret_cast<const uint4*>(p);
-    };
-    uint32_t n0, n1, m0 = 0, m1 = 0;
-    uint4 c0 = row4(z, y0, n0), c1 = hz ? row4(z + 1, y0, n1) : zero;  // rows (z,y), (z+1,y)
-    if (!hz) n1 = 0;
+    // running pointers: row (z, y) and row (z+1, y) of this uint4 column, the bitmap word of (z, y)
+    const uint32_t* p0 = g.sign + ((long long)z * g.Hs + y0) * g.nws + 4 * w4;
+    const uint32_t* p1 = p0 + (long long)g.Hs * g.nws;
+    uint32_t* pb = ballots + ((long long)z * g.Hs + y0) * g.ncr + (w4 >> 3);
+    const uint32_t bshift = (4 * w4) & 31;
+    uint4 c0 = *reinterpret_cast<const uint4*>(p0), c1 = hz ? *reinterpret_cast<const uint4*>(p1) : zero;  // rows (z,y), (z+1,y)
+    uint32_t n0 = hx ? p0[4] : 0u, n1 = (hx && hz) ? p1[4] : 0u;
     const int y1 = min(g.Hs, y0 + gy);
     for (int y = y0; y < y1; ++y) {
         const bool hy = (y + 1 < g.Hs);
-        const uint4 d0 = hy ? row4(z, y + 1, m0) : zero;                 // rows (z,y+1), (z+1,y+1)
-        const uint4 d1 = (hy && hz) ? row4(z + 1, y + 1, m1) : zero;
-        if (!hy) m0 = 0;
-        if (!(hy && hz)) m1 = 0;
+        p0 += g.nws; p1 += g.nws;
+        const uint4 d0 = hy ? *reinterpret_cast<const uint4*>(p0) : zero;                 // rows (z,y+1), (z+1,y+1)
+        const uint4 d1 = (hy && hz) ? *reinterpret_cast<const uint4*>(p1) : zero;
+        const uint32_t m0 = (hy && hx) ? p0[4] : 0u, m1 = (hy && hz && hx) ? p1[4] : 0u;
         // values at x+1
         const uint4 a0 = shr1_4(c0, n0), a1 = shr1_4(c1, n1), b0 = shr1_4(d0, m0), b1 = shr1_4(d1, m1);
         uint4 f;  // owned cut edges
@@ -184,10 +181,8 @@ __global__ void __launch_bounds__(256, 5) k_mc_flags(Grid g, uint32_t* __restric
             f.x |= (o.x & ~a.x) & em.x; f.y |= (o.y & ~a.y) & em.y; f.z |= (o.z & ~a.z) & em.z; f.w |= (o.w & ~a.w) & em.w;
         }
         const uint32_t nib = (f.x ? 1u : 0u) | (f.y ? 2u : 0u) | (f.z ? 4u : 0u) | (f.w ? 8u : 0u);
-        if (nib) {
-            const int w = 4 * w4;
-            atomicOr(ballots + ((int64_t)z * g.Hs + y) * g.ncr + (w >> 5), nib << (w & 31));
-        }
+        if (nib) atomicOr(pb, nib << bshift);
+        pb += g.ncr;
         c0 = d0; c1 = d1; n0 = m0; n1 = m1;
     }
 }
@@ -396,6 +391,7 @@ struct VertexArgs {
     double level;             // iso level (0.5 for the Gaussian occupancy field)
     const unsigned long long* vkeys;
     uint32_t first, count;    // id range of this axis block
+    int x_off;                // the keys' x minus this = x in the (reference-)padded grid (padded-storage layout: 127)
     int z_offset;             // global padded plane of local padded plane 0 (z-slab sharding; 0 on a single device)
     float shift;              // 1 if manifold else 0 (surface_extractor.py:57-60)
     const double* cum;        // cumulative adjusted depths, n_cum entries (n_cum = 0: no z map)
@@ -410,7 +406,7 @@ template <int AXIS>
 __device__ __forceinline__ void vertex_body(const VertexArgs& p, const double* zlut, uint32_t id)
 {
     const unsigned long long key = p.vkeys[id];
-    const int x = (int)((key >> 2) & 0xfffffu), y = (int)((key >> 22) & 0xfffffu), z = (int)(key >> 42);
+    const int x = (int)((key >> 2) & 0xfffffu) - p.x_off, y = (int)((key >> 22) & 0xfffffu), z = (int)(key >> 42);
     float fa, fb;
     if (p.field) {
         const int64_t i = ((int64_t)z * p.occ.H + y) * p.occ.W + x;
@@ -590,6 +586,7 @@ extern "C" int t3d_mc_vertices(const void* occ_bits, int Z, int H, int W, int pa
     p.vkeys = (const unsigned long long*)vkeys_u64;
     p.field = nullptr;
     p.level = 0.5;
+    p.x_off = 0;
     p.shift = unpad_shift ? 1.0f : 0.0f;
     p.z_offset = z_offset;
     p.cum = (const double*)cum_f64;
@@ -662,19 +659,19 @@ extern "C" int t3d_mc_emit_dev(const void* sign_bits, int Zs, int Hs, int Ws, in
     return 0;
 }
 
-extern "C" int t3d_mc_vertices_dev(const void* occ_bits, int Z, int H, int W, int pad, int gaussian, const double* weights3_host,
-                                   const void* vkeys_u64, const void* sizes_u64, uint32_t cap_verts, int unpad_shift, int z_offset,
-                                   const void* cum_f64, const void* adj_f64, int n_cum, double mm_per_pixel_y,
-                                   double mm_per_pixel_x, int scale_in_f64, int which_blocks, void* verts_f32, void* stream)
+// vertices of a mesh emitted on a sign volume whose x coordinates are shifted by x_off against `view`'s padded grid
+int t3d_mc_vertices_view_dev(const OccView& view, int x_off, const void* vkeys_u64, const void* sizes_u64, uint32_t cap_verts,
+                             int unpad_shift, int z_offset, const void* cum_f64, const void* adj_f64, int n_cum, double mm_per_pixel_y,
+                             double mm_per_pixel_x, int scale_in_f64, int which_blocks, void* verts_f32, void* stream)
 {
-    if (Z <= 0 || H <= 0 || W <= 0) { t3d_set_error("t3d_mc_vertices_dev: empty volume"); return 2; }
     if ((which_blocks & 7) == 0) return 0;
     if (cap_verts == 0) return 0;
     VertexArgs p;
-    p.occ = t3d_make_view(occ_bits, Z, H, W, pad, gaussian, weights3_host);
+    p.occ = view;
     p.vkeys = (const unsigned long long*)vkeys_u64;
     p.field = nullptr;
     p.level = 0.5;
+    p.x_off = x_off;
     p.first = 0; p.count = cap_verts;
     p.shift = unpad_shift ? 1.0f : 0.0f;
     p.z_offset = z_offset;
@@ -690,6 +687,17 @@ extern "C" int t3d_mc_vertices_dev(const void* occ_bits, int Z, int H, int W, in
     T3D_CHECK_LAUNCH("t3d_mc_vertices_dev");
     t3d_count_launches(1);
     return 0;
+}
+
+extern "C" int t3d_mc_vertices_dev(const void* occ_bits, int Z, int H, int W, int pad, int gaussian, const double* weights3_host,
+                                   const void* vkeys_u64, const void* sizes_u64, uint32_t cap_verts, int unpad_shift, int z_offset,
+                                   const void* cum_f64, const void* adj_f64, int n_cum, double mm_per_pixel_y,
+                                   double mm_per_pixel_x, int scale_in_f64, int which_blocks, void* verts_f32, void* stream)
+{
+    if (Z <= 0 || H <= 0 || W <= 0) { t3d_set_error("t3d_mc_vertices_dev: empty volume"); return 2; }
+    return t3d_mc_vertices_view_dev(t3d_make_view(occ_bits, Z, H, W, pad, gaussian, weights3_host), 0, vkeys_u64, sizes_u64, cap_verts,
+                                    unpad_shift, z_offset, cum_f64, adj_f64, n_cum, mm_per_pixel_y, mm_per_pixel_x, scale_in_f64,
+                                    which_blocks, verts_f32, stream);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -734,6 +742,7 @@ extern "C" int t3d_mc_vertices_f32(const void* field_f32, int Z, int H, int W, d
     p.occ = t3d_make_view(nullptr, Z, H, W, 0, 0, nullptr);
     p.field = (const float*)field_f32;
     p.level = level;
+    p.x_off = 0;
     p.vkeys = (const unsigned long long*)vkeys_u64;
     p.shift = unpad_shift ? 1.0f : 0.0f;
     p.z_offset = z_offset;

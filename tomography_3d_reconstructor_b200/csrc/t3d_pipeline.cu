@@ -8,8 +8,10 @@
 // bounding-box reduction run on an internal side stream, forked and joined with events (also capturable).
 #include <stdint.h>
 
+#include <stdlib.h>
+
 #include "t3d.h"
-#include "t3d_common.cuh"
+#include "t3d_field.cuh"
 
 // result block (uint64 slots); keep in sync with include/t3d.h and pipeline.py
 enum {
@@ -22,7 +24,21 @@ enum {
 #define EXC_CAP (1u << 20)  // capacity of the list of sign words that need the exact field evaluation
 #define SURF_HALO 3         // smoothed planes the surface stage reads beyond the owned ones (Gaussian radius 2 + upper cube corner)
 
+#define S_XPAD 128          // zero voxels in front of every row of the padded-storage sign volume (4 words: rows stay 16-byte aligned)
+
 static inline int64_t al(int64_t x) { return (x + 255) & ~(int64_t)255; }
+
+// Opening then closing (stages E,D,D,E) leaves no voxel whose six face neighbours all disagree with it: an opened set is a
+// union of crosses (every member touches another member), closing only adds voxels next to the dilated set, and a cleared
+// voxel with six set neighbours would have survived the closing's erosion.  With the zero pad ring around it the sign of
+// (gaussian(0.5) - 0.5) is then the padded occupancy itself (see t3d_surface.cu), so the last erosion writes the sign
+// volume directly, in a padded STORAGE layout: (Zl+2, H+2, wpr(W + S_XPAD + 1)) with the occupancy at plane 1, row 1,
+// word 4 -- no separate field-sign pass, no separately stored smoothed volume.
+static bool fast_surface(int n_stages, unsigned erode_mask, int pad, int Zx, int H, int W)
+{
+    static const bool off = getenv("T3D_NO_FAST_SIGN") != nullptr;
+    return !off && pad == 1 && n_stages == 4 && (erode_mask & 15u) == 9u && Zx >= 2 && H >= 2 && W >= 2;
+}
 
 struct Layout {
     int64_t bitsA, bitsB, bitsC, morph, fill, sign, exc, ballots, chunkbase, scan1, aw_idx, aw_cnt, aw_base, scan2, vkeys, verts_raw,
@@ -31,16 +47,16 @@ struct Layout {
 
 // Zx: planes of the voxel buffers (own slices + halos); Zl: planes the surface stage reads
 static Layout make_layout(int Zx, int Zl, int H, int W, int pad, uint32_t capNA, uint32_t capV, uint32_t capF, uint32_t capZ,
-                          uint32_t capG0, int n_stages, bool own_bitsA)
+                          uint32_t capG0, int n_stages, bool own_bitsA, bool fast)
 {
     Layout L;
     const int64_t nw = t3d_words_per_row(W), vol = (int64_t)Zx * H * nw * 4;
-    const int Zp = Zl + 2 * pad, Hp = H + 2 * pad, Wp = W + 2 * pad;
+    const int Zp = Zl + 2 * pad, Hp = H + 2 * pad, Wp = fast ? W + S_XPAD + 1 : W + 2 * pad;
     const int64_t nwp = t3d_words_per_row(Wp), n_chunks = t3d_mc_num_chunks(Zp, Hp, Wp);
     int64_t o = 0;
     L.bitsA = o; o += own_bitsA ? al(vol) : 0;
     L.bitsB = o; o += al(vol);
-    L.bitsC = o; o += al(vol);
+    L.bitsC = o; o += fast ? 0 : al(vol);       // smoothed volume (the fast path writes it straight into the sign volume)
     L.morph = o; o += al(t3d_morph_scratch_bytes(Zx, H, W, n_stages));
     L.fill = o; o += al(t3d_fill_holes_scratch_bytes(2, H, W));
     L.sign = o; o += al((int64_t)Zp * Hp * nwp * 4);
@@ -65,7 +81,11 @@ static Layout make_layout(int Zx, int Zl, int H, int W, int pad, uint32_t capNA,
 extern "C" int64_t t3d_reconstruct_workspace_bytes(int Z, int H, int W, int add_padding, int n_stages, uint32_t cap_active,
                                                    uint32_t cap_verts, uint32_t cap_faces, uint32_t cap_zverts, uint32_t cap_g0)
 {
-    return make_layout(Z, Z, H, W, add_padding ? 1 : 0, cap_active, cap_verts, cap_faces, cap_zverts, cap_g0, n_stages, true).total;
+    // (sized for whichever of the two surface paths needs more; which one runs also depends on the erode mask)
+    const int pad = add_padding ? 1 : 0;
+    const int64_t a = make_layout(Z, Z, H, W, pad, cap_active, cap_verts, cap_faces, cap_zverts, cap_g0, n_stages, true, false).total;
+    const int64_t b = make_layout(Z, Z, H, W, pad, cap_active, cap_verts, cap_faces, cap_zverts, cap_g0, n_stages, true, true).total;
+    return a > b ? a : b;
 }
 
 extern "C" int64_t t3d_reconstruct_results_len(int Z) { return R_COUNTS + 2 * (int64_t)Z; }
@@ -77,11 +97,24 @@ extern "C" int64_t t3d_reconstruct_slab_workspace_bytes(int halo_lo, int n_own, 
                                                         uint32_t cap_zverts, uint32_t cap_g0)
 {
     const int Zx = halo_lo + n_own + halo_hi, Zl = imin(SURF_HALO, halo_lo) + n_own + imin(SURF_HALO, halo_hi);
-    return make_layout(Zx, Zl, H, W, add_padding ? 1 : 0, cap_active, cap_verts, cap_faces, cap_zverts, cap_g0, n_stages, false).total;
+    const int pad = add_padding ? 1 : 0;
+    const int64_t a = make_layout(Zx, Zl, H, W, pad, cap_active, cap_verts, cap_faces, cap_zverts, cap_g0, n_stages, false, false).total;
+    const int64_t b = make_layout(Zx, Zl, H, W, pad, cap_active, cap_verts, cap_faces, cap_zverts, cap_g0, n_stages, false, true).total;
+    return a > b ? a : b;
 }
 
-__global__ void k_finalize_sizes(unsigned long long* r, unsigned long long capNA, unsigned long long capV, unsigned long long capF)
+__global__ void k_finalize_sizes(unsigned long long* r, unsigned long long capNA, unsigned long long capV, unsigned long long capF,
+                                 int bbox_transformed)
 {
+    if (bbox_transformed) {   // k_pack_gap accumulates {INT_MAX - min, max + 1}: back to {min (INT_MAX if empty), max (-1 if empty)}
+        unsigned int* t = (unsigned int*)(r + R_BBOX_I32X6);
+        int* b = (int*)(r + R_BBOX_I32X6);
+        for (int k = 0; k < 3; ++k) {
+            const unsigned lo = t[2 * k], hi = t[2 * k + 1];
+            b[2 * k] = 0x7fffffff - (int)lo;
+            b[2 * k + 1] = (int)hi - 1;
+        }
+    }
     unsigned long long of8 = (r[R_NEXC] > EXC_CAP) ? 8ull : 0ull;
     const unsigned long long v = r[R_NX] + r[R_NY] + r[R_NZ];
     r[R_VRAW] = v;
@@ -205,46 +238,98 @@ struct SlabGeom {
     float z_ghost, z_lead;
 };
 
+// zero ring of the padded-storage sign volume: planes 0 and Zs-1, rows 0 and Hs-1 of the planes between them (the pad
+// words of the other rows are written by the morphology stage that fills them)
+__global__ void __launch_bounds__(256) k_zero_ring(uint4* __restrict__ S, int Zs, int Hs, int nws4)
+{
+    const long long plane4 = (long long)Hs * nws4;
+    const long long nA = 2 * plane4, nB = (long long)(Zs - 2) * 2 * nws4;
+    const uint4 zero = make_uint4(0, 0, 0, 0);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nA + nB; i += (long long)gridDim.x * blockDim.x) {
+        if (i < nA) {
+            S[i < plane4 ? i : (long long)(Zs - 1) * plane4 + (i - plane4)] = zero;
+        } else {
+            const long long j = i - nA;
+            const long long z = 1 + j / (2 * nws4);
+            const int r = (int)(j % (2 * nws4));
+            S[z * plane4 + (long long)(r < nws4 ? 0 : Hs - 1) * nws4 + (r % nws4)] = zero;
+        }
+    }
+}
+
 // Everything after the voxel grid exists: smoothing, surface, canonical mesh, measures.  `grid` = bit volume of
 // Zx = hl + n + hh planes after close_ends (bitsB of the layout), counts already in R[R_COUNTS .. +Zx).
+// bbox_state: 0 = compute the bounding box of the owned planes here (side stream), 1 = already in R (int32 x 6),
+// 2 = in R in k_pack_gap's transformed form (converted by k_finalize_sizes).
 static int reconstruct_core(const uint32_t* grid, const SlabGeom& g, int H, int W, int n_stages, unsigned erode_mask, int pad,
                             const double* weights3_host, const void* cum_f64, const void* adj_f64, int n_cum, double mm_y,
                             double mm_x, int scale_in_f64, uint32_t cap_active, uint32_t cap_verts, uint32_t cap_faces,
                             uint32_t cap_zverts, uint32_t cap_g0, int zkey_bits, void* verts_out_f32, void* faces_out_i64,
-                            unsigned long long* R, char* ws, const Layout& L, SideStream* side, cudaStream_t st)
+                            unsigned long long* R, char* ws, const Layout& L, bool fast, int bbox_state, SideStream* side, cudaStream_t st)
 {
     const int Zx = g.hl + g.n + g.hh;
-    const int64_t nw = t3d_words_per_row(W), plane_words = (int64_t)H * nw;
+    const int64_t nw = t3d_words_per_row(W), plane_words = (int64_t)H * nw, vol_words = (int64_t)Zx * plane_words;
     const int sl = imin(SURF_HALO, g.hl), sh = imin(SURF_HALO, g.hh), Zl = sl + g.n + sh;
-    const int Zp = Zl + 2 * pad, Hp = H + 2 * pad, Wp = W + 2 * pad;
+    const int Zp = Zl + 2 * pad, Hp = H + 2 * pad, Wp = fast ? W + S_XPAD + 1 : W + 2 * pad;
     const int64_t n_chunks = t3d_mc_num_chunks(Zp, Hp, Wp);
-    uint32_t* bitsC = (uint32_t*)(ws + L.bitsC);
 
-    // bounding box of the owned planes of the raw grid: side stream, joined before the measures
+    // side stream: bounding box of the owned planes of the raw grid (unless the pack kernel already did it) and the zero
+    // ring of the padded sign volume; joined before the cube flags / the measures
     T3D_CUDA(cudaEventRecord(side->e[2], st));
     T3D_CUDA(cudaStreamWaitEvent(side->s, side->e[2], 0));
-    RUN(t3d_volume_stats(grid + (int64_t)g.hl * plane_words, g.n, H, W, nullptr, R + R_BBOX_I32X6, side->s));
-    T3D_CUDA(cudaEventRecord(side->e[3], side->s));
-
-    // ---- smooth_voxel_data
-    const uint32_t* smoothed = grid;
-    if (n_stages > 0) {
-        RUN(t3d_morph(grid, bitsC, Zx, H, W, n_stages, erode_mask, R + R_COUNTS + Zx, ws + L.morph, st));
-        smoothed = bitsC;
+    if (bbox_state == 0)
+        RUN(t3d_volume_stats(grid + (int64_t)g.hl * plane_words, g.n, H, W, nullptr, R + R_BBOX_I32X6, side->s));
+    OccView view;   // the smoothed occupancy the vertex kernel evaluates the field on
+    int x_off = 0;
+    if (fast) {
+        const int nws = (int)t3d_words_per_row(Wp);
+        uint32_t* S = (uint32_t*)(ws + L.sign);
+        const long long s_ps = (long long)Hp * nws;
+        {
+            const long long items = 2 * (long long)Hp * (nws / 4) + (long long)(Zp - 2) * 2 * (nws / 4);
+            long long blocks = (items + 255) / 256;
+            if (blocks > (long long)T3D_NUM_SMS * 8) blocks = (long long)T3D_NUM_SMS * 8;
+            k_zero_ring<<<(unsigned)(blocks < 1 ? 1 : blocks), 256, 0, side->s>>>((uint4*)S, Zp, Hp, nws / 4);
+            t3d_count_launches(1);
+        }
+        T3D_CUDA(cudaEventRecord(side->e[3], side->s));
+        // ---- smooth_voxel_data: E, D, D on compact scratch volumes, the last E straight into the padded sign volume
+        uint32_t* tA = (uint32_t*)(ws + L.morph);
+        uint32_t* tB = tA + vol_words;
+        RUN(t3d_morph_stage(grid, tA, Zx, H, W, 0, Zx, (int)nw, plane_words, true, false, 0, nullptr, st));
+        RUN(t3d_morph_stage(tA, tB, Zx, H, W, 0, Zx, (int)nw, plane_words, false, false, 0, nullptr, st));
+        RUN(t3d_morph_stage(tB, tA, Zx, H, W, 0, Zx, (int)nw, plane_words, false, false, 0, nullptr, st));
+        uint32_t* S_origin = S + s_ps + nws + S_XPAD / 32;   // word of (plane 1, row 1, x = S_XPAD)
+        const int z0 = g.hl - sl;
+        RUN(t3d_morph_stage(tA, S_origin, Zx, H, W, z0, Zl, nws, s_ps, true, true, (nws - (int)nw - S_XPAD / 32) / 4, R + R_COUNTS + Zx + z0, st));
+        view = t3d_make_view_strided(S_origin, Zl, H, W, nws, s_ps, 1, 1, weights3_host);
+        x_off = S_XPAD - 1;
+        T3D_CUDA(cudaStreamWaitEvent(st, side->e[3], 0));   // ring zeroed
     } else {
-        T3D_CUDA(cudaMemcpyAsync(R + R_COUNTS + Zx, R + R_COUNTS, sizeof(unsigned long long) * Zx, cudaMemcpyDeviceToDevice, st));
+        T3D_CUDA(cudaEventRecord(side->e[3], side->s));
+        uint32_t* bitsC = (uint32_t*)(ws + L.bitsC);
+        // ---- smooth_voxel_data
+        const uint32_t* smoothed = grid;
+        if (n_stages > 0) {
+            RUN(t3d_morph(grid, bitsC, Zx, H, W, n_stages, erode_mask, R + R_COUNTS + Zx, ws + L.morph, st));
+            smoothed = bitsC;
+        } else {
+            T3D_CUDA(cudaMemcpyAsync(R + R_COUNTS + Zx, R + R_COUNTS, sizeof(unsigned long long) * Zx, cudaMemcpyDeviceToDevice, st));
+        }
+        const uint32_t* surf = smoothed + (int64_t)(g.hl - sl) * plane_words;
+        // ---- field sign: pad + gaussian + `> 0.5` (exceptions evaluated exactly)
+        RUN(t3d_field_sign_lean(surf, Zl, H, W, pad, weights3_host, ws + L.sign, R + R_NEXACT, ws + L.exc, EXC_CAP, R + R_NEXC, st));
+        view = t3d_make_view(surf, Zl, H, W, pad, 1, weights3_host);
     }
-    const uint32_t* surf = smoothed + (int64_t)(g.hl - sl) * plane_words;
 
-    // ---- extract_manifold_surface: field sign, two-pass marching cubes, vertices
-    RUN(t3d_field_sign_lean(surf, Zl, H, W, pad, weights3_host, ws + L.sign, R + R_NEXACT, ws + L.exc, EXC_CAP, R + R_NEXC, st));
+    // ---- extract_manifold_surface: two-pass marching cubes, vertices
     RUN(t3d_mc_flags(ws + L.sign, Zp, Hp, Wp, g.z_begin, g.z_end, ws + L.ballots, st));
     RUN(t3d_exclusive_scan_u32(ws + L.ballots, ws + L.chunkbase, n_chunks, 1, 0, 1, R + R_NACTIVE, ws + L.scan1, st));
     RUN(t3d_mc_words_dev(ws + L.sign, Zp, Hp, Wp, g.z_begin, g.z_end, ws + L.ballots, ws + L.chunkbase, cap_active, R + R_NACTIVE,
                          ws + L.aw_idx, ws + L.aw_cnt, R + R_NAMBIGUOUS, st));
     RUN(t3d_exclusive_scan_u32_dev(ws + L.aw_cnt, ws + L.aw_base, cap_active, cap_active, 4, 0, 0, R + R_NACTIVE, R + R_NX,
                                    ws + L.scan2, st));
-    k_finalize_sizes<<<1, 1, 0, st>>>(R, cap_active, cap_verts, cap_faces);
+    k_finalize_sizes<<<1, 1, 0, st>>>(R, cap_active, cap_verts, cap_faces, bbox_state == 2 ? 1 : 0);
     t3d_count_launches(1);
     // The vertex kernel only needs the keys: the faces are emitted on the side stream at the same time (the two kernels
     // have different bottlenecks: dependent loads vs. float64 issue), then the measures run there as before.
@@ -255,8 +340,8 @@ static int reconstruct_core(const uint32_t* grid, const SlabGeom& g, int H, int 
     RUN(t3d_mc_emit_dev(ws + L.sign, Zp, Hp, Wp, g.z_begin, g.z_end, ws + L.ballots, ws + L.chunkbase, ws + L.aw_idx, ws + L.aw_base,
                         cap_active, R + R_NACTIVE, cap_verts, cap_faces, ws + L.vkeys, ws + L.faces_raw, 2, side->s));
     T3D_CUDA(cudaEventRecord(side->e[6], side->s));
-    RUN(t3d_mc_vertices_dev(surf, Zl, H, W, pad, 1, weights3_host, ws + L.vkeys, R + R_NACTIVE, cap_verts, 1, g.z_offset, cum_f64,
-                            adj_f64, n_cum, mm_y, mm_x, scale_in_f64, 7, ws + L.verts_raw, st));
+    RUN(t3d_mc_vertices_view_dev(view, x_off, ws + L.vkeys, R + R_NACTIVE, cap_verts, 1, g.z_offset, cum_f64, adj_f64, n_cum, mm_y, mm_x,
+                                 scale_in_f64, 7, ws + L.verts_raw, st));
     // ---- mesh volume / area on the emitted mesh (side stream, concurrent with the canonical ordering), canonical mesh
     T3D_CUDA(cudaEventRecord(side->e[7], st));
     T3D_CUDA(cudaStreamWaitEvent(side->s, side->e[7], 0));
@@ -290,7 +375,8 @@ extern "C" int t3d_reconstruct(const void* masks_u8, int Z, int H, int W, int th
     if (cap_active == 0 || cap_verts == 0 || cap_faces == 0) { t3d_set_error("t3d_reconstruct: zero capacity"); return 2; }
     cudaStream_t st = (cudaStream_t)stream;
     const int pad = add_padding ? 1 : 0;
-    const Layout L = make_layout(Z, Z, H, W, pad, cap_active, cap_verts, cap_faces, cap_zverts, cap_g0, n_stages, true);
+    const bool fast = fast_surface(n_stages, erode_mask, pad, Z, H, W);
+    const Layout L = make_layout(Z, Z, H, W, pad, cap_active, cap_verts, cap_faces, cap_zverts, cap_g0, n_stages, true, fast);
     char* ws = (char*)workspace;
     unsigned long long* R = (unsigned long long*)results_u64;
     const int64_t nw = t3d_words_per_row(W), plane_words = (int64_t)H * nw, plane_bytes = (int64_t)H * W;
@@ -301,7 +387,7 @@ extern "C" int t3d_reconstruct(const void* masks_u8, int Z, int H, int W, int th
     RUN(side_for_current_device(&side));
     PrezeroGuard zg;
     {
-        const int Zp = Z + 2 * pad, Hp = H + 2 * pad, Wp = W + 2 * pad;
+        const int Zp = Z + 2 * pad, Hp = H + 2 * pad, Wp = fast ? W + S_XPAD + 1 : W + 2 * pad;
         const int64_t n_chunks = t3d_mc_num_chunks(Zp, Hp, Wp);
         zg.add(R, sizeof(unsigned long long) * (R_COUNTS + 2 * (size_t)Z));
         zg.add(ws + L.ballots, (size_t)al(n_chunks * 4));
@@ -316,7 +402,23 @@ extern "C" int t3d_reconstruct(const void* masks_u8, int Z, int H, int W, int th
     }
 
     // ---- create_voxel_data: pack, fill the holes of the end slices (side stream), z gap fill + per-slice counts
-    if (close_ends && Z >= 3) {
+    int bbox_state = 0;
+    if (close_ends && t3d_pack_gap_supported(m, Z, H, W, threshold)) {
+        // one pass over the masks: pack + gap fill + counts + extrema; the two end planes are packed apart, hole-filled on
+        // the side stream meanwhile, and planes 0, 1, Z-2, Z-1 are then rewritten from them
+        uint32_t* f0 = bitsA;
+        uint32_t* fT = bitsA + plane_words;
+        RUN(t3d_pack_masks(m, 1, H, W, threshold, f0, st));
+        RUN(t3d_pack_masks(m + (int64_t)(Z - 1) * plane_bytes, 1, H, W, threshold, fT, st));
+        T3D_CUDA(cudaEventRecord(side->e[0], st));
+        T3D_CUDA(cudaStreamWaitEvent(side->s, side->e[0], 0));
+        RUN(t3d_fill_holes_2d(f0, 2, plane_words, H, W, ws + L.fill, side->s));
+        T3D_CUDA(cudaEventRecord(side->e[1], side->s));
+        RUN(t3d_pack_gap_launch(m, Z, H, W, threshold, bitsB, R + R_COUNTS, (unsigned int*)(R + R_BBOX_I32X6), 1, st));
+        T3D_CUDA(cudaStreamWaitEvent(st, side->e[1], 0));
+        RUN(t3d_close_ends_fixup_launch(m, Z, H, W, threshold, f0, fT, bitsB, R + R_COUNTS, st));
+        bbox_state = 2;
+    } else if (close_ends && Z >= 3) {
         RUN(t3d_pack_masks(m, 1, H, W, threshold, bitsA, st));
         RUN(t3d_pack_masks(m + (int64_t)(Z - 1) * plane_bytes, 1, H, W, threshold, bitsA + (int64_t)(Z - 1) * plane_words, st));
         T3D_CUDA(cudaEventRecord(side->e[0], st));
@@ -338,7 +440,7 @@ extern "C" int t3d_reconstruct(const void* masks_u8, int Z, int H, int W, int th
     SlabGeom g = {0, Z, 0, 0, -1, 0, 0, 0, 0.f, 0.f};
     RUN(reconstruct_core(bitsB, g, H, W, n_stages, erode_mask, pad, weights3_host, cum_f64, adj_f64, n_cum, mm_per_pixel_y,
                          mm_per_pixel_x, scale_in_f64, cap_active, cap_verts, cap_faces, cap_zverts, cap_g0, zkey_bits, verts_out_f32,
-                         faces_out_i64, R, ws, L, side, st));
+                         faces_out_i64, R, ws, L, fast, bbox_state, side, st));
     T3D_CHECK_LAUNCH("t3d_reconstruct");
     t3d_count_launches(1);
     return 0;
@@ -393,14 +495,15 @@ extern "C" int t3d_reconstruct_slab(const void* ext_bits, int halo_lo, int n_own
     cudaStream_t st = (cudaStream_t)stream;
     const int pad = add_padding ? 1 : 0, Zx = halo_lo + n_own + halo_hi;
     const int Zl = imin(SURF_HALO, halo_lo) + n_own + imin(SURF_HALO, halo_hi);
-    const Layout L = make_layout(Zx, Zl, H, W, pad, cap_active, cap_verts, cap_faces, cap_zverts, cap_g0, n_stages, false);
+    const bool fast = fast_surface(n_stages, erode_mask, pad, Zx, H, W);
+    const Layout L = make_layout(Zx, Zl, H, W, pad, cap_active, cap_verts, cap_faces, cap_zverts, cap_g0, n_stages, false, fast);
     char* ws = (char*)workspace;
     unsigned long long* R = (unsigned long long*)results_u64;
     SideStream* side;
     RUN(side_for_current_device(&side));
     PrezeroGuard zg;
     {
-        const int Zp = Zl + 2 * pad, Hp = H + 2 * pad, Wp = W + 2 * pad;
+        const int Zp = Zl + 2 * pad, Hp = H + 2 * pad, Wp = fast ? W + S_XPAD + 1 : W + 2 * pad;
         const int64_t n_chunks = t3d_mc_num_chunks(Zp, Hp, Wp);
         zg.add(R, sizeof(unsigned long long) * (R_COUNTS + 2 * (size_t)Zx));
         zg.add(ws + L.ballots, (size_t)al(n_chunks * 4));
@@ -418,7 +521,7 @@ extern "C" int t3d_reconstruct_slab(const void* ext_bits, int halo_lo, int n_own
     SlabGeom g = {halo_lo, n_own, halo_hi, z_begin, z_end, z_offset, want_ghost, want_lead, z_ghost, z_lead};
     RUN(reconstruct_core((const uint32_t*)(ws + L.bitsB), g, H, W, n_stages, erode_mask, pad, weights3_host, cum_f64, adj_f64, n_cum,
                          mm_per_pixel_y, mm_per_pixel_x, scale_in_f64, cap_active, cap_verts, cap_faces, cap_zverts, cap_g0, zkey_bits,
-                         verts_out_f32, faces_out_i64, R, ws, L, side, st));
+                         verts_out_f32, faces_out_i64, R, ws, L, fast, 0, side, st));
     T3D_CHECK_LAUNCH("t3d_reconstruct_slab");
     t3d_count_launches(1);
     return 0;
@@ -442,7 +545,7 @@ extern "C" int t3d_slab_stitch_faces(void* faces_i64, int64_t cap_faces, const v
 {
     if (rank < 0 || cap_faces < 0) { t3d_set_error("t3d_slab_stitch_faces: bad arguments"); return 2; }
     if (rank == 0 || cap_faces == 0) return 0;
-    k_add_vertex_base<<<148 * 8, 256, 0, (cudaStream_t)stream>>>((long long*)faces_i64, (const unsigned long long*)gathered_results_u64,
+    k_add_vertex_base<<<T3D_NUM_SMS * 8, 256, 0, (cudaStream_t)stream>>>((long long*)faces_i64, (const unsigned long long*)gathered_results_u64,
                                                                stride_u64, rank, 3 * cap_faces);
     T3D_CHECK_LAUNCH("t3d_slab_stitch_faces");
     t3d_count_launches(1);

@@ -43,7 +43,7 @@ __device__ __forceinline__ uint4 prow4(const OccView& v, int zp, int yp, int wp4
 {
     const int z = zp - v.pad, y = yp - v.pad;
     if (z < 0 || z >= v.Z || y < 0 || y >= v.H) { left = right = 0u; return make_uint4(0, 0, 0, 0); }
-    const uint32_t* row = v.bits + ((int64_t)z * v.H + y) * v.nw;
+    const uint32_t* row = v.bits + (z * v.ps + (long long)y * v.rs);
     const int w0 = 4 * wp4;
     const uint4 o = (w0 < v.nw) ? *reinterpret_cast<const uint4*>(row + w0) : make_uint4(0, 0, 0, 0);
     const uint32_t om1 = (w0 >= 1 && w0 - 1 < v.nw) ? row[w0 - 1] : 0u;

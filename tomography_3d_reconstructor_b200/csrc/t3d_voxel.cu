@@ -45,6 +45,31 @@ int t3d_zero_async(void* p, size_t n, cudaStream_t st)
     return 0;
 }
 
+int t3d_num_sms(void)
+{
+    static int sms[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return 148; }
+    int& n = sms[dev & 63];
+    if (n <= 0) {
+        int v = 0;
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) { cudaGetLastError(); v = 148; }
+        n = v;
+    }
+    return n;
+}
+
+bool t3d_first_use_on_device(int slot)
+{
+    static bool done[T3D_ONCE_SLOTS][64] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); dev = 0; }
+    bool& d = done[slot][dev & 63];
+    const bool first = !d;
+    d = true;
+    return first;
+}
+
 int t3d_rows_per_thread(const char* env_name, int dflt)
 {
     const char* e = getenv(env_name);
@@ -378,11 +403,8 @@ extern "C" int t3d_fill_holes_2d(void* bits, int n_planes, int64_t plane_stride_
     if (n_planes <= 0) return 0;
     if (H <= 0 || W <= 0) { t3d_set_error("t3d_fill_holes_2d: empty plane"); return 2; }
     const size_t smem = (size_t)(FH_THREADS / 32) * 2 * 32 * FH_PITCH * sizeof(uint32_t);  // 136 KB
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (t3d_first_use_on_device(T3D_ONCE_FILL_HOLES_ATTR))   // function attributes are per device
         T3D_CUDA(cudaFuncSetAttribute(k_fill_holes, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
-    }
     k_fill_holes<<<n_planes, FH_THREADS, smem, (cudaStream_t)stream>>>((uint32_t*)bits, plane_stride_words,
                                                                       (uint32_t*)scratch, H, W, t3d_wpr(W));
     T3D_CHECK_LAUNCH("t3d_fill_holes_2d");
@@ -452,327 +474,334 @@ extern "C" int t3d_gap_fill(const void* in_bits, void* out_bits, const void* lo_
 }
 
 // ------------------------------------------------------------------------------------------------
+// Fused create_voxel_data: `img >= threshold` + np.stack + the z loop of _close_volume_ends + np.sum per slice + the
+// np.where extrema, in ONE pass over the uint8 stack (voxel_processor.py:46-52, 72-75; volume_calculator.py:62-79).
+// A warp owns 1024 consecutive bytes (32 packed words) of the (y,x) plane and marches along z through a chunk of planes
+// with the packed words of planes z-1, z, z+1 in registers: out[z] = w[z] | (w[z-1] & w[z+1]).  Every mask byte is read
+// once (plus one halo plane per chunk end), the bit volume is written once, nothing is re-read.
+// The two end planes need scipy.ndimage.binary_fill_holes first (voxel_processor.py:60-70): k_pack_gap treats them as
+// raw and k_close_ends_fixup afterwards rewrites planes 0, 1, Z-2, Z-1 from the hole-filled end planes (and counts them).
+// Extrema are accumulated in a form that works on zero-initialised memory: {INT_MAX - min, max + 1} under atomicMax.
+// ------------------------------------------------------------------------------------------------
+#define PG_ZC 128   // most planes a chunk may have
+
+struct PackGapArgs {
+    const uint8_t* src;
+    uint32_t* dst;
+    int Z, nw;                    // nw: words per row (= W/32 on this path)
+    long long plane_words, plane_bytes;
+    uint32_t thr4;
+    int zc;                       // planes per chunk (<= PG_ZC)
+    int skip_ends;                // planes 0, 1, Z-2, Z-1 are not counted here (k_close_ends_fixup counts them)
+    unsigned long long* counts;   // Z per-slice counts (zeroed by the caller) or null
+    unsigned int* bbox_t;         // 6 transformed extrema {z, y, x} x {INT_MAX - min, max + 1} (zeroed by the caller) or null
+};
+
+__global__ void __launch_bounds__(256) k_pack_gap(PackGapArgs a)
+{
+    __shared__ unsigned int s_cnt[PG_ZC];
+    __shared__ unsigned int s_bb[6];
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const uint32_t l = lane_id();
+    if (tid < PG_ZC) s_cnt[tid] = 0;
+    if (tid < 6) s_bb[tid] = 0;
+    __syncthreads();
+    const long long span = (long long)blockIdx.x * 8 + warp;     // 1024 bytes = 32 words of a plane
+    const int za = blockIdx.y * a.zc, zb = min(a.Z, za + a.zc);
+    const long long wi = span * 32 + l;                           // this lane's word of the plane
+    const bool wvalid = wi < a.plane_words;
+    const long long boff = span * 1024 + 16 * l;                  // this lane's first 16 mask bytes
+    const bool va = boff + 16 <= a.plane_bytes, vb = boff + 512 + 16 <= a.plane_bytes;
+    const int s0 = (2 * l) & 31;
+    auto load_word = [&](int z) -> uint32_t {
+        const uint8_t* p = a.src + (long long)z * a.plane_bytes + boff;
+        const uint4 zero = make_uint4(0, 0, 0, 0);
+        const uint4 x = va ? ld_stream_u4(p) : zero;
+        const uint4 y = vb ? ld_stream_u4(p + 512) : zero;
+        const uint32_t ha = ge16(x, a.thr4), hb = ge16(y, a.thr4);
+        const uint32_t a0 = __shfl_sync(0xffffffffu, ha, s0), a1 = __shfl_sync(0xffffffffu, ha, s0 + 1);
+        const uint32_t b0 = __shfl_sync(0xffffffffu, hb, s0), b1 = __shfl_sync(0xffffffffu, hb, s0 + 1);
+        return (l < 16) ? (a0 | (a1 << 16)) : (b0 | (b1 << 16));
+    };
+    uint32_t acc = 0;
+    int zmin = 0x7fffffff, zmax = -1;
+    if (span * 1024 < a.plane_bytes) {   // (warp-uniform)
+        uint32_t prev = za > 0 ? load_word(za - 1) : 0u;
+        uint32_t cur = load_word(za);
+        uint32_t* dp = a.dst + (long long)za * a.plane_words + wi;
+        for (int z = za; z < zb; ++z) {
+            const bool hn = z + 1 < a.Z;
+            const uint32_t next = hn ? load_word(z + 1) : 0u;
+            uint32_t v = cur;
+            if (z > 0 && hn) v |= prev & next;
+            if (wvalid) *dp = v;
+            dp += a.plane_words;
+            acc |= v;
+            const unsigned wc = __reduce_add_sync(0xffffffffu, (unsigned)__popc(v));
+            if (wc) {
+                zmin = min(zmin, z);
+                zmax = z;
+                const bool counted = !(a.skip_ends && (z < 2 || z >= a.Z - 2));
+                if (l == 0 && counted) atomicAdd(&s_cnt[z - za], wc);
+            }
+            prev = cur;
+            cur = next;
+        }
+    }
+    if (a.bbox_t && zmax >= 0) {         // (warp-uniform)
+        int ymin = 0x7fffffff, ymax = -1, xmin = 0x7fffffff, xmax = -1;
+        if (acc) {
+            const int y = (int)(wi / a.nw), w = (int)(wi - (long long)y * a.nw);
+            ymin = ymax = y;
+            xmin = (w << 5) + __ffs(acc) - 1;
+            xmax = (w << 5) + 31 - __clz(acc);
+        }
+        ymin = __reduce_min_sync(0xffffffffu, ymin); ymax = __reduce_max_sync(0xffffffffu, ymax);
+        xmin = __reduce_min_sync(0xffffffffu, xmin); xmax = __reduce_max_sync(0xffffffffu, xmax);
+        if (l == 0) {
+            atomicMax(&s_bb[0], (unsigned)(0x7fffffff - zmin)); atomicMax(&s_bb[1], (unsigned)(zmax + 1));
+            atomicMax(&s_bb[2], (unsigned)(0x7fffffff - ymin)); atomicMax(&s_bb[3], (unsigned)(ymax + 1));
+            atomicMax(&s_bb[4], (unsigned)(0x7fffffff - xmin)); atomicMax(&s_bb[5], (unsigned)(xmax + 1));
+        }
+    }
+    __syncthreads();
+    if (a.counts && tid < zb - za && s_cnt[tid]) atomicAdd(a.counts + za + tid, (unsigned long long)s_cnt[tid]);
+    if (a.bbox_t && tid < 6 && s_bb[tid]) atomicMax(a.bbox_t + tid, s_bb[tid]);
+}
+
+struct EndsFixArgs {
+    const uint8_t* src;
+    const uint32_t* f0;           // hole-filled plane 0
+    const uint32_t* fT;           // hole-filled plane Z-1
+    uint32_t* dst;
+    int Z;
+    long long plane_words, plane_bytes;
+    uint32_t thr4;
+    unsigned long long* counts;
+};
+
+// planes 0, 1, Z-2, Z-1 of the closed grid from the hole-filled end planes (Z >= 3; one thread per word; a word is 32
+// consecutive mask bytes because W % 128 == 0 on this path)
+__global__ void __launch_bounds__(256) k_close_ends_fixup(EndsFixArgs a)
+{
+    const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+    const long long pw = a.plane_words;
+    const int Z = a.Z;
+    unsigned c[4] = {0, 0, 0, 0};   // planes 0, 1, Z-2, Z-1
+    if (i < pw) {
+        auto raw = [&](int z) -> uint32_t {
+            const uint4* p = reinterpret_cast<const uint4*>(a.src + (long long)z * a.plane_bytes + 32 * i);
+            return ge16(p[0], a.thr4) | (ge16(p[1], a.thr4) << 16);
+        };
+        const uint32_t b = a.f0[i], t = a.fT[i];
+        a.dst[i] = b;
+        a.dst[(long long)(Z - 1) * pw + i] = t;
+        c[0] = __popc(b); c[3] = __popc(t);
+        const uint32_t v1 = raw(1) | (b & ((Z - 1 == 2) ? t : raw(2)));
+        a.dst[pw + i] = v1;
+        c[1] = __popc(v1);
+        if (Z - 2 != 1) {
+            const uint32_t vT = raw(Z - 2) | (((Z - 3 == 0) ? b : raw(Z - 3)) & t);
+            a.dst[(long long)(Z - 2) * pw + i] = vT;
+            c[2] = __popc(vT);
+        }
+    }
+    if (!a.counts) return;
+    __shared__ unsigned s[4];
+    if (threadIdx.x < 4) s[threadIdx.x] = 0;
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const unsigned w = __reduce_add_sync(0xffffffffu, c[k]);
+        if (lane_id() == 0 && w) atomicAdd(&s[k], w);
+    }
+    __syncthreads();
+    if (threadIdx.x < 4 && s[threadIdx.x]) {
+        const int zz = threadIdx.x == 0 ? 0 : threadIdx.x == 1 ? 1 : threadIdx.x == 2 ? Z - 2 : Z - 1;
+        atomicAdd(a.counts + zz, (unsigned long long)s[threadIdx.x]);
+    }
+}
+
+bool t3d_pack_gap_supported(const void* masks_u8, int Z, int H, int W, int threshold)
+{
+    static const bool off = getenv("T3D_NO_PACK_GAP") != nullptr;
+    return !off && Z >= 3 && H > 0 && (W & 127) == 0 && ((uintptr_t)masks_u8 & 15) == 0 && threshold >= 1 && threshold <= 255;
+}
+
+// masks -> gap-filled grid `out` (end planes still raw), per-slice counts (zeroed by the caller; planes 0, 1, Z-2, Z-1
+// left out when skip_ends) and transformed extrema (6 uint32 zeroed by the caller, may be null)
+int t3d_pack_gap_launch(const void* masks_u8, int Z, int H, int W, int threshold, void* out, unsigned long long* counts,
+                        unsigned int* bbox_t, int skip_ends, cudaStream_t st)
+{
+    PackGapArgs a;
+    a.src = (const uint8_t*)masks_u8; a.dst = (uint32_t*)out;
+    a.Z = Z; a.nw = t3d_wpr(W);
+    a.plane_words = (long long)H * a.nw; a.plane_bytes = (long long)H * W;
+    a.thr4 = 0x01010101u * (uint32_t)threshold;
+    const long long n_spans = (a.plane_bytes + 1023) / 1024;
+    // about one wave of resident warps (64 per SM); chunks of 16..PG_ZC planes (each chunk re-reads two halo planes)
+    static const int zc_env = t3d_rows_per_thread("T3D_PACK_ZC", 0);
+    long long chunks = ((long long)T3D_NUM_SMS * 64 + n_spans - 1) / n_spans;
+    if (chunks < 1) chunks = 1;
+    int zc = (int)((Z + chunks - 1) / chunks);
+    if (zc < 16) zc = 16;
+    if (zc_env > 0) zc = zc_env;
+    if (zc > PG_ZC) zc = PG_ZC;
+    a.zc = zc;
+    a.skip_ends = skip_ends;
+    a.counts = counts; a.bbox_t = bbox_t;
+    dim3 grid((unsigned)((n_spans + 7) / 8), (unsigned)((Z + zc - 1) / zc));
+    k_pack_gap<<<grid, 256, 0, st>>>(a);
+    T3D_CHECK_LAUNCH("t3d_pack_gap");
+    t3d_count_launches(1);
+    return 0;
+}
+
+int t3d_close_ends_fixup_launch(const void* masks_u8, int Z, int H, int W, int threshold, const void* filled0, const void* filledT,
+                                void* out, unsigned long long* counts, cudaStream_t st)
+{
+    EndsFixArgs a;
+    a.src = (const uint8_t*)masks_u8; a.f0 = (const uint32_t*)filled0; a.fT = (const uint32_t*)filledT; a.dst = (uint32_t*)out;
+    a.Z = Z; a.plane_words = (long long)H * t3d_wpr(W); a.plane_bytes = (long long)H * W;
+    a.thr4 = 0x01010101u * (uint32_t)threshold;
+    a.counts = counts;
+    k_close_ends_fixup<<<(unsigned)((a.plane_words + 255) / 256), 256, 0, st>>>(a);
+    T3D_CHECK_LAUNCH("t3d_close_ends_fixup");
+    t3d_count_launches(1);
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
 // 6-connected binary morphology.  Stage s of a call is an erosion (bit s of erode_mask set; out-of-volume = 1)
 // or a dilation (out-of-volume = 0): exactly skimage's binary_erosion / binary_dilation with the default cross
 // footprint.  opening then closing = stages E,D,D,E = erode_mask 0b1001.
 //
-// One launch per stage.  The packed volume is 1/8 byte per voxel (67 MB at 512x1024x1024: L2 resident on a B200),
-// so a stage is bound by instruction issue and load latency, not HBM.  A thread owns one uint4 column (128 voxels)
-// of one plane and marches down MY rows with the y neighbours in a register window: per 128 output voxels it issues
-// 3 x 128-bit loads (next row, z-1, z+1) + 2 scalar loads (x neighbours, L1 hits), 8 funnel shifts and 12 LOP3.
+// One launch per stage.  A thread owns one uint4 column (128 voxels) of one plane and marches down `my` rows with the
+// y neighbours in a register window; all addresses are running pointers (one add per row and stream), so a row costs
+// 3 x 128-bit loads (next row, z-1, z+1) + 2 scalar loads (x neighbours, L1 hits), 8 funnel shifts, 12 LOP3 and one
+// 128-bit store.  The output may live in a differently strided buffer: the last stage of the fused pipeline writes
+// straight into the padded layout the marching-cubes kernels read (RING: it also clears the pad words of its rows).
 // ------------------------------------------------------------------------------------------------
 #define MY 8
 
-template <bool ER, bool FIX>
-__global__ void __launch_bounds__(256, 5) k_morph4(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, int Z, int H,
-                                                int W, int nw, int lanes_x, int pz_per_block, int my,
-                                                unsigned long long* __restrict__ counts)
+struct MorphArgs {
+    const uint32_t* in;          // compact (Z, H, nw) volume
+    uint32_t* out;               // word (plane z0, row 0, word 0) of the output
+    int Z, H, W, nw;
+    int z0, nz;                  // planes [z0, z0 + nz) are computed
+    int out_rs;                  // output row stride (words)
+    long long out_ps;            // output plane stride (words)
+    int lanes_x, pz_per_block, my;
+    int ring_tail;               // RING: uint4s of zeros appended after the nw real words of every output row (0 or 1)
+    unsigned long long* counts;  // COUNT: counts[z - z0] += set voxels of output plane z
+};
+
+// a row of border values for each kind of stage: neighbours outside the volume are read from here through pointers that
+// do not advance, so the inner loop carries no predicated loads (each would cost four register moves for its default)
+__device__ __align__(16) const uint32_t g_border_row[8] = {0u, 0u, 0u, 0u, 0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+
+template <bool ER, bool FIX, bool COUNT, bool RING>
+__global__ void __launch_bounds__(256, 4) k_morph(MorphArgs a)
 {
-    constexpr uint32_t B = ER ? 0xffffffffu : 0u;
-    const int lx = threadIdx.x % lanes_x, pz = threadIdx.x / lanes_x;
-    const int nw4 = nw >> 2, nwv = (W + 31) >> 5;
-    const int w4 = blockIdx.x * lanes_x + lx, z = blockIdx.z * pz_per_block + pz, y0 = blockIdx.y * my;
+    const int lx = threadIdx.x % a.lanes_x, pz = threadIdx.x / a.lanes_x;
+    const int nw4 = a.nw >> 2, nwv = (a.W + 31) >> 5;
+    const int w4 = blockIdx.x * a.lanes_x + lx, zi = blockIdx.z * a.pz_per_block + pz, y0 = blockIdx.y * a.my;
     extern __shared__ unsigned int s_cnt[];
-    if (counts) {
-        if ((int)threadIdx.x < pz_per_block) s_cnt[threadIdx.x] = 0;
+    if (COUNT) {
+        if ((int)threadIdx.x < a.pz_per_block) s_cnt[threadIdx.x] = 0;
         __syncthreads();
     }
-    uint32_t cnt = 0;
-    if (pz < pz_per_block && w4 < nw4 && z < Z) {
-        const uint4 vm = valid_mask4(w4, W);
+    if (pz < a.pz_per_block && w4 < nw4 && zi < a.nz) {
+        const int z = a.z0 + zi;
+        const uint4 vm = valid_mask4(w4, a.W);
         // words beyond the volume (tail bits, padding words) read as the border value of this stage
-        const bool fix = FIX && ER && (4 * w4 + 4 > (W >> 5));
-        auto row4 = [&](int zz, int yy) -> uint4 {
-            uint4 v = *reinterpret_cast<const uint4*>(in + ((int64_t)zz * H + yy) * nw + 4 * w4);
-            if (fix) v = make_uint4(v.x | ~vm.x, v.y | ~vm.y, v.z | ~vm.z, v.w | ~vm.w);
+        const bool fix = FIX && ER && (4 * w4 + 4 > (a.W >> 5));
+        const uint4 fixm = fix ? make_uint4(~vm.x, ~vm.y, ~vm.z, ~vm.w) : make_uint4(0, 0, 0, 0);
+        auto ld4 = [&](const uint32_t* p) -> uint4 {
+            uint4 v = *reinterpret_cast<const uint4*>(p);
+            if (FIX && ER) v = or4(v, fixm);
             return v;
         };
+        const uint32_t* border = g_border_row + (ER ? 4 : 0);
         const bool has_l = (w4 > 0), has_r = (4 * w4 + 4 < nwv);
-        const uint4 B4 = splat4(B);
-        uint4 prev = (y0 > 0) ? row4(z, y0 - 1) : B4;
-        uint4 cur = row4(z, y0);
-        const int y1 = min(H, y0 + my);
+        const bool fix_r = FIX && ER && has_r && (4 * w4 + 5 >= nwv);   // the right neighbour is the partial last word
+        const uint32_t fix_r_bits = fix_r ? ~valid_mask(4 * w4 + 4, a.W) : 0u;
+        const long long in_ps = (long long)a.H * a.nw;
+        const uint32_t* pc = a.in + (long long)z * in_ps + (long long)y0 * a.nw + 4 * w4;   // row (z, y)
+        // neighbours: running pointers with a step of one row, or the border row with a step of zero
+        const uint32_t* pm = (z > 0) ? pc - in_ps : border;
+        const uint32_t* pp = (z + 1 < a.Z) ? pc + in_ps : border;
+        const uint32_t* pl = has_l ? pc - 1 : border;
+        const uint32_t* pr = has_r ? pc + 4 : border;
+        const int sm = (z > 0) ? a.nw : 0, sp = (z + 1 < a.Z) ? a.nw : 0, sl = has_l ? a.nw : 0, sr = has_r ? a.nw : 0;
+        uint32_t* po = a.out + (long long)zi * a.out_ps + (long long)y0 * a.out_rs + 4 * w4;
+        uint4 prev = ld4(y0 > 0 ? pc - a.nw : border);
+        uint4 cur = ld4(pc);
+        const int y1 = min(a.H, y0 + a.my);
+        uint32_t cnt = 0;
 #pragma unroll 4
         for (int y = y0; y < y1; ++y) {
-            const uint4 next = (y + 1 < H) ? row4(z, y + 1) : B4;
-            const uint4 zm = (z > 0) ? row4(z - 1, y) : B4;
-            const uint4 zp = (z + 1 < Z) ? row4(z + 1, y) : B4;
-            const uint32_t* rowp = in + ((int64_t)z * H + y) * nw + 4 * w4;
-            const uint32_t l = has_l ? rowp[-1] : B;
-            uint32_t r = has_r ? rowp[4] : B;
-            if (FIX && ER && has_r && 4 * w4 + 5 >= nwv) r |= ~valid_mask(4 * w4 + 4, W);  // right neighbour is the partial last word
+            const uint4 next = ld4((y + 1 < a.H) ? pc + a.nw : border);
+            const uint4 zm = ld4(pm);
+            const uint4 zp = ld4(pp);
+            const uint32_t l = *pl;
+            const uint32_t r = *pr | fix_r_bits;
             const uint4 xm = shl1_4(cur, l), xp = shr1_4(cur, r);
             uint4 v;
             if (ER) v = and4(and4(and4(cur, xm), and4(xp, prev)), and4(and4(next, zm), zp));
             else v = or4(or4(or4(cur, xm), or4(xp, prev)), or4(or4(next, zm), zp));
             v = and4(v, vm);
-            *reinterpret_cast<uint4*>(out + ((int64_t)z * H + y) * nw + 4 * w4) = v;
-            cnt += popc4(v);
+            *reinterpret_cast<uint4*>(po) = v;
+            if (RING) {   // pad words of the padded layout: 4 zero words in front of every row, the tail behind it
+                if (w4 == 0) *reinterpret_cast<uint4*>(po - 4) = make_uint4(0, 0, 0, 0);
+                if (w4 == nw4 - 1 && a.ring_tail) *reinterpret_cast<uint4*>(po + 4) = make_uint4(0, 0, 0, 0);
+            }
+            if (COUNT) cnt += popc4(v);
             prev = cur;
             cur = next;
+            pc += a.nw; pm += sm; pp += sp; pl += sl; pr += sr; po += a.out_rs;
         }
-        if (counts && cnt) atomicAdd(&s_cnt[pz], cnt);
+        if (COUNT && cnt) atomicAdd(&s_cnt[pz], cnt);
     }
-    if (counts) {
+    if (COUNT) {
         __syncthreads();
-        const int zz = blockIdx.z * pz_per_block + threadIdx.x;
-        if ((int)threadIdx.x < pz_per_block && zz < Z && s_cnt[threadIdx.x])
-            atomicAdd(counts + zz, (unsigned long long)s_cnt[threadIdx.x]);
+        const int zz = blockIdx.z * a.pz_per_block + threadIdx.x;
+        if ((int)threadIdx.x < a.pz_per_block && zz < a.nz && s_cnt[threadIdx.x])
+            atomicAdd(a.counts + zz, (unsigned long long)s_cnt[threadIdx.x]);
     }
 }
 
-// ------------------------------------------------------------------------------------------------
-// The same stage with the input staged through shared memory.  A CTA owns a tile of MT_Z planes x MT_Y rows x 32 words
-// (1024 voxels) and first copies the tile plus a one-cell halo into shared memory with coalesced 128-bit loads -- cells
-// outside the volume (planes, rows, tail bits, padding words) get the border value of the stage there, so the stencil
-// itself is branch-free.  Every input word is then read from L2 (6*34)/(4*32) = 1.6 times instead of 3 + the x-neighbour
-// words.  EXPERIMENT (T3D_MORPH_TILE=1): despite the lower L2 traffic it is slower than k_morph4 (43 vs 33 us per stage at
-// 512x1024x1024) -- the load / barrier / compute phases overlap worse than the register march's independent loads.
-// ------------------------------------------------------------------------------------------------
-#define MT_Z 4
-#define MT_Y 32
-#define MT_Q 8    // uint4 per tile row
-
-template <bool ER>
-__global__ void __launch_bounds__(256) k_morph_tile(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, int Z, int H, int W,
-                                                    int nw, unsigned long long* __restrict__ counts)
+// one stage: planes [z0, z0 + nz) of the compact volume `in` -> out (see MorphArgs)
+int t3d_morph_stage(const uint32_t* in, uint32_t* out, int Z, int H, int W, int z0, int nz, int out_rs, long long out_ps,
+                    bool erode, bool ring, int ring_tail, unsigned long long* counts, cudaStream_t st)
 {
-    constexpr uint32_t B = ER ? 0xffffffffu : 0u;
-    __shared__ uint4 s_in[MT_Z + 2][MT_Y + 2][MT_Q];
-    __shared__ uint32_t s_l[MT_Z + 2][MT_Y + 2], s_r[MT_Z + 2][MT_Y + 2];
-    __shared__ unsigned int s_cnt[MT_Z];
-    const int nw4 = nw >> 2, nwv = (W + 31) >> 5;
-    const int q0 = blockIdx.x * MT_Q, y0 = blockIdx.y * MT_Y, z0 = blockIdx.z * MT_Z;
-    const int tid = threadIdx.x;
-    if (tid < MT_Z) s_cnt[tid] = 0;
-    // ---- stage the tile + halo
-    constexpr int ROWS = (MT_Z + 2) * (MT_Y + 2);
-    for (int i = tid; i < ROWS * MT_Q; i += 256) {
-        const int q = i % MT_Q, r = i / MT_Q, py = r % (MT_Y + 2), pz = r / (MT_Y + 2);
-        const int z = z0 - 1 + pz, y = y0 - 1 + py, w4 = q0 + q;
-        uint4 v = make_uint4(B, B, B, B);
-        if (z >= 0 && z < Z && y >= 0 && y < H && w4 < nw4) {
-            v = *reinterpret_cast<const uint4*>(in + ((int64_t)z * H + y) * nw + 4 * w4);
-            if (ER) {   // tail bits and padding words read as 1
-                const uint4 vm = valid_mask4(w4, W);
-                v = make_uint4(v.x | ~vm.x, v.y | ~vm.y, v.z | ~vm.z, v.w | ~vm.w);
-            }
-        }
-        s_in[pz][py][q] = v;
+    MorphArgs a;
+    a.in = in; a.out = out; a.Z = Z; a.H = H; a.W = W; a.nw = t3d_wpr(W);
+    a.z0 = z0; a.nz = nz; a.out_rs = out_rs; a.out_ps = out_ps;
+    const int nw4 = a.nw / 4;
+    a.lanes_x = nw4 < 256 ? nw4 : 256;
+    a.pz_per_block = 256 / a.lanes_x;
+    static const int my_env = t3d_rows_per_thread("T3D_MORPH_ROWS", MY);
+    a.my = my_env;
+    a.ring_tail = ring_tail;
+    a.counts = counts;
+    dim3 grid((nw4 + a.lanes_x - 1) / a.lanes_x, (H + a.my - 1) / a.my, (nz + a.pz_per_block - 1) / a.pz_per_block);
+    const size_t smem = counts ? sizeof(unsigned int) * a.pz_per_block : 0;
+    const bool fixw = (W & 127) != 0;
+#define T3D_MORPH_LAUNCH(ER, FIX, COUNT, RING) k_morph<ER, FIX, COUNT, RING><<<grid, 256, smem, st>>>(a)
+    if (ring) {
+        if (erode) { if (fixw) { if (counts) T3D_MORPH_LAUNCH(true, true, true, true); else T3D_MORPH_LAUNCH(true, true, false, true); }
+                     else { if (counts) T3D_MORPH_LAUNCH(true, false, true, true); else T3D_MORPH_LAUNCH(true, false, false, true); } }
+        else { if (counts) T3D_MORPH_LAUNCH(false, false, true, true); else T3D_MORPH_LAUNCH(false, false, false, true); }
+    } else {
+        if (erode) { if (fixw) { if (counts) T3D_MORPH_LAUNCH(true, true, true, false); else T3D_MORPH_LAUNCH(true, true, false, false); }
+                     else { if (counts) T3D_MORPH_LAUNCH(true, false, true, false); else T3D_MORPH_LAUNCH(true, false, false, false); } }
+        else { if (counts) T3D_MORPH_LAUNCH(false, false, true, false); else T3D_MORPH_LAUNCH(false, false, false, false); }
     }
-    for (int r = tid; r < 2 * ROWS; r += 256) {
-        const int side = r / ROWS, rr = r - side * ROWS, py = rr % (MT_Y + 2), pz = rr / (MT_Y + 2);
-        const int z = z0 - 1 + pz, y = y0 - 1 + py;
-        const int w = side ? 4 * (q0 + MT_Q) : 4 * q0 - 1;     // word right of the tile row / left of it
-        uint32_t v = B;
-        if (z >= 0 && z < Z && y >= 0 && y < H && w >= 0 && w < nwv) {
-            v = in[((int64_t)z * H + y) * nw + w];
-            if (ER) v |= ~valid_mask(w, W);
-        }
-        if (side) s_r[pz][py] = v; else s_l[pz][py] = v;
-    }
-    __syncthreads();
-    // ---- stencil: thread = (row py, uint4 q), marching over the MT_Z planes with the z neighbours in registers
-    const int q = tid % MT_Q, py = tid / MT_Q;     // 256 threads = 32 rows x 8 uint4
-    const int y = y0 + py, w4 = q0 + q;
-    const bool live = (y < H) && (w4 < nw4);
-    const uint4 vm = valid_mask4(w4, W);
-    uint4 zm = s_in[0][py + 1][q], cur = s_in[1][py + 1][q];
-#pragma unroll
-    for (int pz = 0; pz < MT_Z; ++pz) {
-        const uint4 zp = s_in[pz + 2][py + 1][q];
-        const uint4 prev = s_in[pz + 1][py][q], next = s_in[pz + 1][py + 2][q];
-        const uint32_t l = q > 0 ? s_in[pz + 1][py + 1][q - 1].w : s_l[pz + 1][py + 1];
-        const uint32_t r = q < MT_Q - 1 ? s_in[pz + 1][py + 1][q + 1].x : s_r[pz + 1][py + 1];
-        const uint4 xm = shl1_4(cur, l), xp = shr1_4(cur, r);
-        uint4 v;
-        if (ER) v = and4(and4(and4(cur, xm), and4(xp, prev)), and4(and4(next, zm), zp));
-        else v = or4(or4(or4(cur, xm), or4(xp, prev)), or4(or4(next, zm), zp));
-        v = and4(v, vm);
-        const int z = z0 + pz;
-        uint32_t c = 0;
-        if (live && z < Z) {
-            *reinterpret_cast<uint4*>(out + ((int64_t)z * H + y) * nw + 4 * w4) = v;
-            c = popc4(v);
-        }
-        if (counts) {
-            c = warp_sum(c);
-            if ((tid & 31) == 0 && c) atomicAdd(&s_cnt[pz], c);
-        }
-        zm = cur;
-        cur = zp;
-    }
-    if (counts) {
-        __syncthreads();
-        if (tid < MT_Z && z0 + tid < Z && s_cnt[tid]) atomicAdd(counts + z0 + tid, (unsigned long long)s_cnt[tid]);
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// Fused multi-stage morphology (up to 4 stages, e.g. opening then closing = E,D,D,E) in ONE pass over the volume.
-// A CTA owns a band of full-width rows and marches through a chunk of planes.  Level 0 = input, level k = output of
-// stage k-1; levels 0..NST-1 live in shared memory as rings of 4 planes, the last level goes to global memory.  Level k
-// lags level k-1 by two planes, so everything a step reads was written in an earlier step: one __syncthreads per
-// plane.  Cells outside the volume (rows, planes, tail bits) hold the border value of the stage that will READ them
-// (1 for an erosion, 0 for a dilation), which makes the inner loop branch-free.
-// The halo is nst rows / planes on each side (recomputed by neighbouring CTAs); band and chunk sizes are chosen so
-// that the grid is about one wave of the 148 SMs.
-// ------------------------------------------------------------------------------------------------
-struct FusedMorph {
-    const uint32_t* in;
-    uint32_t* out;
-    int Z, H, W, nw, nw4;
-    int nst;
-    uint32_t erode_mask;
-    int BY, BZ, RB;            // output rows per band, output planes per chunk, rows held in shared memory
-    unsigned long long* counts;
-};
-
-__global__ void __launch_bounds__(1024, 1) k_morph_fused(FusedMorph p)
-{
-    extern __shared__ uint4 ring[];  // [level][slot 0..3][row 0..RB)[w4]
-    __shared__ unsigned int s_cnt[2];
-    const int R = p.nst, RB = p.RB, nw4 = p.nw4;
-    const int yb0 = blockIdx.y * p.BY, yb1 = min(p.H, yb0 + p.BY);
-    const int zc0 = blockIdx.z * p.BZ, zc1 = min(p.Z, zc0 + p.BZ);
-    const int plane4 = RB * nw4;                  // uint4 per ring plane
-    const int nwv = (p.W + 31) >> 5;
-    const int T = (zc1 - zc0) + R + 2 * p.nst;
-    const int tid = threadIdx.x, nthreads = blockDim.x;
-    auto border = [&](int stage) -> uint32_t { return ((p.erode_mask >> stage) & 1u) ? 0xffffffffu : 0u; };
-    // items of one step: level 0 loads RB rows; level k (1..nst) computes rows [k, RB-k)
-    int first[6];
-    first[0] = 0;
-    first[1] = RB * nw4;
-    for (int k = 1; k <= p.nst; ++k) first[k + 1] = first[k] + (RB - 2 * k) * nw4;
-    const int n_items = first[p.nst + 1];
-    if (tid < 2) s_cnt[tid] = 0;
-    __syncthreads();
-
-    // input staging: every thread owns up to two uint4 of a plane; the global loads for plane zi+1 are issued at the
-    // start of step t and land in shared memory at the start of step t+1, so their latency hides behind the compute
-    const int n_in = first[1];
-    const uint32_t B0 = border(0);
-    auto load_in = [&](int zi, int j) -> uint4 {
-        const int r = j / nw4, w4 = j - r * nw4;
-        const int y = yb0 - R + r;
-        uint4 v = splat4(B0);
-        if (zi >= 0 && zi < p.Z && y >= 0 && y < p.H && zi < zc1 + R) {
-            v = *reinterpret_cast<const uint4*>(p.in + ((int64_t)zi * p.H + y) * p.nw + 4 * w4);
-            if (B0 && 4 * w4 + 4 > (p.W >> 5)) { const uint4 vm = valid_mask4(w4, p.W); v = make_uint4(v.x | ~vm.x, v.y | ~vm.y, v.z | ~vm.z, v.w | ~vm.w); }
-        }
-        return v;
-    };
-    uint4 pre0 = splat4(B0), pre1 = splat4(B0);
-    if (tid < n_in) pre0 = load_in(zc0 - R, tid);
-    if (tid + nthreads < n_in) pre1 = load_in(zc0 - R, tid + nthreads);
-
-    for (int t = 0; t < T; ++t) {
-        const int zi = zc0 - R + t;   // input plane of this step
-        // ---- level 0: plane zi (prefetched) -> ring, then prefetch plane zi + 1
-        {
-            uint4* dst = ring + ((zi + 64) & 3) * plane4;
-            if (tid < n_in) dst[tid] = pre0;
-            if (tid + nthreads < n_in) dst[tid + nthreads] = pre1;
-            if (tid < n_in) pre0 = load_in(zi + 1, tid);
-            if (tid + nthreads < n_in) pre1 = load_in(zi + 1, tid + nthreads);
-        }
-        uint32_t pc = 0;
-        for (int i = n_in + tid; i < n_items; i += nthreads) {
-            int k = 1;
-            while (i >= first[k + 1]) ++k;
-            const int j = i - first[k];
-            {
-                // ---- level k = stage k-1 applied to level k-1, plane z = zi - 2k
-                const int z = zi - 2 * k;
-                const int halo = R - k;
-                if (z < zc0 - halo || z >= zc1 + halo) continue;
-                const int rr = j / nw4, w4 = j - rr * nw4;
-                const int r = k + rr;
-                const int y = yb0 - R + r;
-                const bool er = (p.erode_mask >> (k - 1)) & 1u;
-                const uint32_t B = er ? 0xffffffffu : 0u;
-                const uint4* L = ring + (k - 1) * 4 * plane4;
-                const uint4* pc0 = L + ((z + 64) & 3) * plane4 + r * nw4 + w4;
-                const uint4 c = pc0[0], ym = pc0[-nw4], yp = pc0[nw4];
-                const uint4 zm = L[((z - 1 + 64) & 3) * plane4 + r * nw4 + w4], zq = L[((z + 1 + 64) & 3) * plane4 + r * nw4 + w4];
-                const uint32_t l = (w4 > 0) ? pc0[-1].w : B;
-                const uint32_t rgt = (4 * w4 + 4 < nwv) ? pc0[1].x : B;
-                const uint4 xm = shl1_4(c, l), xp = shr1_4(c, rgt);
-                uint4 v = er ? and4(and4(and4(c, xm), and4(xp, ym)), and4(and4(yp, zm), zq))
-                             : or4(or4(or4(c, xm), or4(xp, ym)), or4(or4(yp, zm), zq));
-                const uint4 vm = valid_mask4(w4, p.W);
-                const bool inside = (z >= 0 && z < p.Z && y >= 0 && y < p.H);
-                if (k < p.nst) {
-                    const uint32_t Bn = border(k);   // what the next stage must see outside the volume / beyond W
-                    if (!inside) v = splat4(Bn);
-                    else v = make_uint4((v.x & vm.x) | (Bn & ~vm.x), (v.y & vm.y) | (Bn & ~vm.y), (v.z & vm.z) | (Bn & ~vm.z), (v.w & vm.w) | (Bn & ~vm.w));
-                    ring[(k * 4 + ((z + 64) & 3)) * plane4 + r * nw4 + w4] = v;
-                } else if (inside && y >= yb0 && y < yb1) {
-                    v = and4(v, vm);
-                    *reinterpret_cast<uint4*>(p.out + ((int64_t)z * p.H + y) * p.nw + 4 * w4) = v;
-                    pc += popc4(v);
-                }
-            }
-        }
-        if (p.counts) {
-            pc = warp_sum(pc);
-            if ((tid & 31) == 0 && pc) atomicAdd(&s_cnt[t & 1], pc);
-        }
-        __syncthreads();
-        if (p.counts && tid == 0) {
-            const int zf = zi - 2 * p.nst;
-            const unsigned int c = s_cnt[t & 1];
-            if (c && zf >= zc0 && zf < zc1) atomicAdd(p.counts + zf, (unsigned long long)c);
-            s_cnt[t & 1] = 0;   // reused at step t+2, after the barrier of step t+1
-        }
-    }
-}
-
-// returns 1 if the fused kernel was launched, 0 if the shape does not fit (caller falls back to one launch per stage)
-static int launch_morph_fused(const uint32_t* in, uint32_t* out, int Z, int H, int W, int n_stages, unsigned erode_mask,
-                              unsigned long long* counts, cudaStream_t st, int* rc)
-{
-    *rc = 0;
-    if (n_stages < 2 || n_stages > 4) return 0;
-    // Correct but shared-memory-bandwidth bound (5 LDS.128 per 128 voxels and stage): 243 us vs 4 x 38 us for the
-    // per-stage kernels at 512x1024x1024, so it is opt-in until the z neighbours are kept in registers.
-    if (!getenv("T3D_FUSED_MORPH")) return 0;
-    const int nw = t3d_wpr(W), nw4 = nw / 4;
-    const int smem_budget = 200 * 1024;
-    const int row_bytes = nw * 4;
-    int RB = smem_budget / (n_stages * 4 * row_bytes);
-    if (RB > 64) RB = 64;
-    if (RB * nw4 > 2048) RB = 2048 / nw4;   // the input plane is staged by at most two uint4 per thread
-    int BY = RB - 2 * n_stages;
-    if (BY < 8) return 0;
-    if (BY > H) { BY = H; RB = BY + 2 * n_stages; }
-    const int n_bands = (H + BY - 1) / BY;
-    // even out the bands, then choose the chunk count so that bands * chunks is about one wave
-    BY = (H + n_bands - 1) / n_bands;
-    RB = BY + 2 * n_stages;
-    int n_chunks = T3D_NUM_SMS / n_bands;
-    if (n_chunks < 1) n_chunks = 1;
-    int BZ = (Z + n_chunks - 1) / n_chunks;
-    if (BZ < 4 * n_stages) BZ = Z < 4 * n_stages ? Z : 4 * n_stages;   // keep the redundant halo work bounded
-    n_chunks = (Z + BZ - 1) / BZ;
-    FusedMorph p;
-    p.in = in; p.out = out; p.Z = Z; p.H = H; p.W = W; p.nw = nw; p.nw4 = nw4; p.nst = n_stages; p.erode_mask = erode_mask;
-    p.BY = BY; p.BZ = BZ; p.RB = RB; p.counts = counts;
-    const size_t smem = (size_t)n_stages * 4 * RB * row_bytes;
-    static size_t attr = 0;
-    if (smem > attr) {
-        if (cudaFuncSetAttribute(k_morph_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
-            cudaGetLastError();
-            return 0;
-        }
-        attr = smem;
-    }
-    dim3 grid(1, n_bands, n_chunks);
-    k_morph_fused<<<grid, 1024, smem, st>>>(p);
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) { t3d_set_error("t3d_morph (fused): launch failed: %s", cudaGetErrorString(e)); *rc = 1; }
-    return 1;
+#undef T3D_MORPH_LAUNCH
+    T3D_CHECK_LAUNCH("t3d_morph_stage");
+    t3d_count_launches(1);
+    return 0;
 }
 
 extern "C" int64_t t3d_morph_scratch_bytes(int Z, int H, int W, int n_stages)
@@ -789,54 +818,18 @@ extern "C" int t3d_morph(const void* in_bits, void* out_bits, int Z, int H, int 
     if (in_bits == out_bits) { t3d_set_error("t3d_morph: in-place is not supported"); return 2; }
     if (n_stages > 1 && !scratch) { t3d_set_error("t3d_morph: scratch required for more than one stage"); return 2; }
     cudaStream_t st = (cudaStream_t)stream;
-    const int nw = t3d_wpr(W), nw4 = nw / 4;
+    const int nw = t3d_wpr(W);
     const int64_t vol_words = (int64_t)Z * H * nw;
     if (slice_counts_u64 && t3d_zero_async(slice_counts_u64, sizeof(unsigned long long) * Z, st)) return 1;
-    {   // all stages in one pass when they fit in shared memory
-        int rc = 0;
-        if (launch_morph_fused((const uint32_t*)in_bits, (uint32_t*)out_bits, Z, H, W, n_stages, erode_mask,
-                               (unsigned long long*)slice_counts_u64, st, &rc)) {
-            if (rc) return rc;
-            t3d_count_launches(1);
-            return 0;
-        }
-    }
-    static const bool use_tile = getenv("T3D_MORPH_TILE") != nullptr;   // measured slower than k_morph4 (43 vs 33 us per C1 stage)
-    if (use_tile) {
-        dim3 tgrid((nw4 + MT_Q - 1) / MT_Q, (H + MT_Y - 1) / MT_Y, (Z + MT_Z - 1) / MT_Z);
-        uint32_t* tmp2[2] = {(uint32_t*)scratch, (uint32_t*)scratch + vol_words};
-        const uint32_t* src2 = (const uint32_t*)in_bits;
-        for (int s = 0; s < n_stages; ++s) {
-            const bool last = (s == n_stages - 1);
-            uint32_t* dst = last ? (uint32_t*)out_bits : tmp2[s & 1];
-            unsigned long long* cnt = last ? (unsigned long long*)slice_counts_u64 : nullptr;
-            if ((erode_mask >> s) & 1u) k_morph_tile<true><<<tgrid, 256, 0, st>>>(src2, dst, Z, H, W, nw, cnt);
-            else k_morph_tile<false><<<tgrid, 256, 0, st>>>(src2, dst, Z, H, W, nw, cnt);
-            src2 = dst;
-        }
-        T3D_CHECK_LAUNCH("t3d_morph");
-        t3d_count_launches(n_stages);
-        return 0;
-    }
-    const int lanes_x = nw4 < 256 ? nw4 : 256;
-    const int pzb = 256 / lanes_x;
-    static const int my = t3d_rows_per_thread("T3D_MORPH_ROWS", MY);
-    dim3 grid((nw4 + lanes_x - 1) / lanes_x, (H + my - 1) / my, (Z + pzb - 1) / pzb);
-    const size_t smem = sizeof(unsigned int) * pzb;
     uint32_t* tmp[2] = {(uint32_t*)scratch, (uint32_t*)scratch + vol_words};
     const uint32_t* src = (const uint32_t*)in_bits;
     for (int s = 0; s < n_stages; ++s) {
         const bool last = (s == n_stages - 1);
         uint32_t* dst = last ? (uint32_t*)out_bits : tmp[s & 1];
         unsigned long long* cnt = last ? (unsigned long long*)slice_counts_u64 : nullptr;
-        const bool er = (erode_mask >> s) & 1u;
-        if (er && (W & 127)) k_morph4<true, true><<<grid, 256, smem, st>>>(src, dst, Z, H, W, nw, lanes_x, pzb, my, cnt);
-        else if (er) k_morph4<true, false><<<grid, 256, smem, st>>>(src, dst, Z, H, W, nw, lanes_x, pzb, my, cnt);
-        else k_morph4<false, false><<<grid, 256, smem, st>>>(src, dst, Z, H, W, nw, lanes_x, pzb, my, cnt);
+        if (int rc = t3d_morph_stage(src, dst, Z, H, W, 0, Z, nw, (long long)H * nw, (erode_mask >> s) & 1u, false, 0, cnt, st)) return rc;
         src = dst;
     }
-    T3D_CHECK_LAUNCH("t3d_morph");
-    t3d_count_launches(n_stages);
     return 0;
 }
 
