@@ -43,22 +43,32 @@ def side_counts(Z):
 # reference arm / CPU baseline: the oracle (CPU restatement of the reference pipeline) on a bounded z-slab sample
 # ----------------------------------------------------------------------------------------------------------------
 def _cpu_sample_job(args):
-    Z, H, W, z0, z1 = args
+    Z, H, W, z0, z1, sides, kind = args
     from oracle import cpu_ref
     u8 = cpu_ref.ellipsoid_phantom_u8(Z, H, W, z0, z1)
+    sides = sides or side_counts(z1 - z0)
     t0 = time.perf_counter()
-    cpu_ref.reference_pipeline(u8, THRESHOLD, side_counts(z1 - z0), PHYS["total_depth_mm"], PHYS["x_length_mm"],
-                               PHYS["y_length_mm"])
+    if kind == "sdf":       # additive stage: smoothing -> scipy's exact EDT (both polarities) -> marching cubes at level 0
+        masks = [u8[z] >= THRESHOLD for z in range(u8.shape[0])]
+        sm = cpu_ref.smooth_voxel_data(cpu_ref.create_voxel_data(masks, True), 3, True)
+        sdf = cpu_ref.signed_distance(sm, (PHYS["total_depth_mm"] / Z, PHYS["y_length_mm"] / H, PHYS["x_length_mm"] / W))
+        cpu_ref.marching_cubes(sdf, 0.0)
+    else:
+        cpu_ref.reference_pipeline(u8, THRESHOLD, sides, PHYS["total_depth_mm"], PHYS["x_length_mm"], PHYS["y_length_mm"])
     return time.perf_counter() - t0, (z1 - z0) * H * W
 
 
-def cpu_sample(Z, H, W, n_slices, workers):
-    """Run the oracle on `workers` disjoint central z-slabs of n_slices each, in parallel processes.
-    Returns (seconds, voxels)."""
+def cpu_sample(Z, H, W, n_slices, workers, sides=None, kind="occupancy"):
+    """Run the oracle on `workers` disjoint central z-slabs of n_slices each, in parallel processes (sides given: every
+    worker runs the WHOLE stack, i.e. `workers` replicas).  Returns (seconds, voxels, slices per worker)."""
     import multiprocessing as mp
-    n_slices = max(4, min(n_slices, Z // max(1, workers)))
-    zc = Z // 2 - (n_slices * workers) // 2
-    jobs = [(Z, H, W, zc + k * n_slices, zc + (k + 1) * n_slices) for k in range(workers)]
+    if sides is not None:
+        n_slices = Z
+        jobs = [(Z, H, W, 0, Z, tuple(sides), kind) for _ in range(workers)]
+    else:
+        n_slices = max(4, min(n_slices, Z // max(1, workers)))
+        zc = Z // 2 - (n_slices * workers) // 2
+        jobs = [(Z, H, W, zc + k * n_slices, zc + (k + 1) * n_slices, None, kind) for k in range(workers)]
     t0 = time.perf_counter()
     if workers == 1:
         res = [_cpu_sample_job(jobs[0])]
@@ -71,7 +81,7 @@ def cpu_sample(Z, H, W, n_slices, workers):
     return wall, sum(r[1] for r in res), n_slices
 
 
-def run_reference(args, Z, H, W):
+def run_reference(args, Z, H, W, cfg):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -79,24 +89,32 @@ def run_reference(args, Z, H, W):
     cpu_ref.build()
     cores = os.cpu_count() or 1
     workers = max(1, min(cores, 16))
+    path = cfg["path"]
+    kind = "sdf" if path == "sdf" else "occupancy"
     budget_per_step = 150.0 / max(1, args.steps + args.warmup)
-    # measured oracle speed is ~2.5 Mvox/s per core (scipy.ndimage is single-threaded)
-    n_slices = int(max(4, min(32, budget_per_step * 2.5e6 / (H * W))))
+    whole = path == "batch" or args.config == "C0"       # volumes small enough to run whole: one per worker
+    sides = (cfg.get("sides") or side_counts(Z)) if whole else None
+    # measured oracle speed is ~2.5 Mvox/s per core (scipy.ndimage is single-threaded); the EDT is ~4x slower
+    n_slices = int(max(4, min(32, budget_per_step * (0.6e6 if kind == "sdf" else 2.5e6) / (H * W))))
     for _ in range(args.warmup):
-        cpu_sample(Z, H, W, n_slices, workers)
+        cpu_sample(Z, H, W, n_slices, workers, sides, kind)
     secs, vox = 0.0, 0
     for _ in range(args.steps):
-        s, v, n_slices = cpu_sample(Z, H, W, n_slices, workers)
+        s, v, n_slices = cpu_sample(Z, H, W, n_slices, workers, sides, kind)
         secs += s
         vox += v
     value = vox / secs / 1e9
-    sample = "%d disjoint central z-slabs of %d slices x %dx%d per step (one per worker process)" % (workers, n_slices, H, W)
+    if whole:
+        sample = "%d whole %dx%dx%d stacks per step (one per worker process)" % (workers, Z, H, W)
+    else:
+        sample = "%d disjoint central z-slabs of %d slices x %dx%d per step (one per worker process)" % (workers, n_slices, H, W)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "Gvoxels/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / max(1, args.steps),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bool/f64 (numpy/scipy)",
         "data": "synthetic",
-        "config": {"workload": "C1 ellipsoid stack %dx%dx%d (bounded sample per step)" % (Z, H, W), "sample": sample},
+        "config": {"workload": "%s, ellipsoid stack %dx%dx%d (bounded sample per step)" % (cfg["name"], Z, H, W), "config": args.config,
+                   "sample": sample},
         "cpu_baseline": {"value": value, "unit": "Gvoxels/s", "cores": workers, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "Gvoxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -113,6 +131,7 @@ class ClockSampler:
 
     def __init__(self, index):
         self.index, self.rows, self.proc = index, [], None
+        self.t0 = self.t1 = None
 
     def __enter__(self):
         try:
@@ -127,7 +146,14 @@ class ClockSampler:
 
     def _read(self):
         for ln in self.proc.stdout:
-            self.rows.append(ln.strip())
+            self.rows.append((time.perf_counter(), ln.strip()))
+
+    def n_rows(self):
+        return len(self.rows)
+
+    def window(self, t0, t1):
+        """Timed region [t0, t1] (perf_counter); samples inside it are counted apart in summary()."""
+        self.t0, self.t1 = t0, t1
 
     def __exit__(self, *a):
         if self.proc:
@@ -139,9 +165,9 @@ class ClockSampler:
                 self.proc.kill()
 
     def summary(self):
-        sm, mx, reasons = [], [], set()
+        sm, mx, reasons, inside = [], [], set(), 0
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for ts, r in self.rows:
             f = [x.strip() for x in r.split(",")]
             if len(f) < 7:
                 continue
@@ -150,12 +176,17 @@ class ClockSampler:
                 mx.append(float(f[1]))
             except ValueError:
                 continue
+            if self.t0 is not None and self.t0 <= ts <= self.t1 + 0.1:
+                inside += 1
             for k, nm in enumerate(names):
                 if f[3 + k].lower().startswith("active"):
                     reasons.add(nm)
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm),
+                "samples_in_timed_region": inside,
+                "note": "sampled every 100 ms while the same step runs back to back (load phase before + timed region + load phase "
+                        "after): the timed region itself can be shorter than one sampling period"}
 
 
 def make_phantom_u8(Z_total, H, W, z0, z1, device):
@@ -180,8 +211,92 @@ STAGE_BYTES = {  # algorithmic bytes per voxel of each volume-sized stage (DESIG
     "pack_close": 1.0 + 0.125 + 0.25, "smooth": 4 * 0.25, "field_sign": 0.25, "mc_flags": 0.125 + 1.0 / 256,
 }
 
+# BASELINE.json configs -> (per-GPU shape, path).  The stack grows with the number of GPUs (weak scaling): C3 / C4 are the
+# full 2048^3 / 4096^3 stacks at N = 8 and one GPU's z-slab of them at N = 1.
+CONFIGS = {
+    "C0": dict(shape=(104, 512, 512), sides=(20, 64, 20), path="occupancy", replicas=True,
+               name="C0 (BASELINE configs[0]): 512x512 masks, Section_0/1/2 = 20+64+20 slices"),
+    "C1": dict(shape=(512, 1024, 1024), path="occupancy", name="C1 (BASELINE configs[1])"),
+    "C2": dict(shape=(256, 256, 256), path="batch", count=256,
+               name="C2 (BASELINE configs[2]): batch of 256 independent 256^3 phantoms, round robin over the GPUs"),
+    "C3": dict(shape=(256, 2048, 2048), path="sdf",
+               name="C3 (BASELINE configs[3]): 2048x2048 slices, exact EDT/SDF + marching cubes on the distance field, "
+                    "256 slices per GPU (the full 2048^3 stack at 8 GPUs)"),
+    "C4": dict(shape=(512, 4096, 4096), path="occupancy",
+               name="C4 (BASELINE configs[4]): 4096x4096 slices, 512 per GPU (the full 4096^3 stack at 8 GPUs)"),
+}
 
-def run_ours(args, Z, H, W):
+
+def mesh_digest(v, f):
+    """sha256 over the float32 vertex bits and the int64 faces of a device mesh (downloaded in chunks)."""
+    import hashlib
+    h = hashlib.sha256()
+    for t in (v, f):
+        t = t.contiguous()
+        flat = t.view(-1)
+        for a in range(0, flat.numel(), 1 << 24):
+            h.update(flat[a:a + (1 << 24)].cpu().numpy().tobytes())
+    return h.hexdigest()[:16]
+
+
+def mesh_topology(v, f):
+    """(closed oriented 2-manifold?, Euler characteristic) of a device mesh: every directed edge once and its twin present."""
+    import torch
+    V = int(v.shape[0])
+    e = torch.cat([f[:, [0, 1]], f[:, [1, 2]], f[:, [2, 0]]])
+    key = e[:, 0] * (V + 1) + e[:, 1]
+    rev = e[:, 1] * (V + 1) + e[:, 0]
+    sk = torch.sort(key)[0]
+    closed = bool((sk[1:] != sk[:-1]).all()) and bool(torch.equal(sk, torch.sort(rev)[0]))
+    return closed, V - int(key.numel()) // 2 + int(f.shape[0])
+
+
+def sharded_check(world, rank, dev, H=512, W=512, per_rank=128):
+    """N > 1: the stitched mesh of a (per_rank*N, H, W) stack sharded over the N ranks against rank 0's own single-GPU run
+    of the same stack: same bits (sha256 of vertices + faces), closed 2-manifold, Euler characteristic 2, consistent
+    ghost/lead stitching, same volumes.  Asserted, and reported in the bench line."""
+    import torch
+    import torch.distributed as dist
+    from tomography_3d_reconstructor_b200 import pipeline, sharded
+    Zc = per_rank * world
+    sides = side_counts(Zc)
+    phys = (PHYS["total_depth_mm"], PHYS["x_length_mm"], PHYS["y_length_mm"])
+    z0, z1 = sharded.slab_range(Zc, rank, world)
+    masks = make_phantom_u8(Zc, H, W, z0, z1, dev)
+    for _ in range(3):     # staged (learns the sizes), fused, fused + graph
+        out = sharded.reconstruct_fused(masks, Zc, z0, THRESHOLD, sides, *phys, use_graph=True)
+    gm = sharded.gather_mesh(out, 0)
+    rep = None
+    if rank == 0:
+        v, f = gm
+        full = make_phantom_u8(Zc, H, W, 0, Zc, dev)
+        for _ in range(2):
+            ref = pipeline.reconstruct_fused(full, THRESHOLD, sides, *phys)
+        rv, rf = ref["mesh"].verts, ref["mesh"].faces
+        closed, euler = mesh_topology(v, f)
+        rep = {"shape": [Zc, H, W], "ranks": world, "vertices": int(v.shape[0]), "faces": int(f.shape[0]),
+               "mesh_sha256_16": mesh_digest(v, f), "single_gpu_sha256_16": mesh_digest(rv, rf),
+               "stitch_consistent": bool(out["stitch_consistent"]), "closed_manifold": closed, "euler": euler,
+               "voxel_volume_equal": out["voxel_volume_mm3"] == ref["voxel_volume_mm3"],
+               "processed_volume_equal": out["processed_voxel_volume_mm3"] == ref["processed_voxel_volume_mm3"],
+               "bbox_equal": out["bbox_index"] == ref["bbox_index"],
+               "mesh_volume_rel_diff": abs(out["mesh_volume_mm3"] - ref["mesh_volume_mm3"]) / ref["mesh_volume_mm3"]}
+        rep["ok"] = bool(rep["mesh_sha256_16"] == rep["single_gpu_sha256_16"] and rep["stitch_consistent"] and closed and euler == 2
+                         and rep["voxel_volume_equal"] and rep["processed_volume_equal"] and rep["bbox_equal"]
+                         and rep["mesh_volume_rel_diff"] <= 1e-9)
+        del full, ref
+    sharded._slab_plans.clear()
+    pipeline._plans.clear()
+    del masks, out, gm
+    torch.cuda.empty_cache()
+    flag = torch.tensor([0 if (rep is None or rep["ok"]) else 1], device=dev)
+    dist.all_reduce(flag)
+    if int(flag.item()):
+        raise AssertionError("sharded mesh differs from the single-GPU mesh: %r" % (rep,))
+    return rep
+
+
+def run_ours(args, Z, H, W, cfg):
     import torch
     import torch.distributed as dist
     rank = int(os.environ.get("RANK", "0"))
@@ -190,64 +305,109 @@ def run_ours(args, Z, H, W):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = os.environ.get("T3D_NCCL_DEBUG", "WARN")  # keep stdout to the one JSON line
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/t3d_nccl.%h.%p.log")
+        # NCCL's own logging is left exactly as the caller set it (NCCL_DEBUG / NCCL_DEBUG_FILE); the JSON line is the LAST
+        # line this program prints to stdout
         dist.init_process_group("nccl", device_id=dev)
     from tomography_3d_reconstructor_b200 import _lib, engine, pipeline
     lib = _lib.load()
+    path = cfg["path"]
+    replicas = bool(cfg.get("replicas")) or path == "batch"
+    phys = (PHYS["total_depth_mm"], PHYS["x_length_mm"], PHYS["y_length_mm"])
 
-    Zg = Z * world                       # weak scaling: the stack grows with the number of GPUs
-    sides = side_counts(Zg)
-    if world > 1:
-        from tomography_3d_reconstructor_b200 import sharded
-        z0, z1 = sharded.slab_range(Zg, rank, world)
+    if replicas:
+        Zg, z0, z1 = Z, 0, Z                 # every rank holds whole volumes: no collective on the data path
     else:
-        z0, z1 = 0, Zg
-    masks = make_phantom_u8(Zg, H, W, z0, z1, dev)
+        Zg = Z * world                       # weak scaling: the stack grows with the number of GPUs
+        if world > 1:
+            from tomography_3d_reconstructor_b200 import sharded
+            z0, z1 = sharded.slab_range(Zg, rank, world)
+        else:
+            z0, z1 = 0, Zg
+    sides = cfg.get("sides") or side_counts(Zg)
+    sharded_run = world > 1 and not replicas
+    if sharded_run:
+        from tomography_3d_reconstructor_b200 import sharded
+
+    if path == "batch":
+        from tomography_3d_reconstructor_b200 import batch
+        count = int(cfg["count"])
+        radii, centres = batch.phantom_params(count, Z)
+        mine = batch.my_items(count, rank, world)
+        stacks = {i: batch.phantom_u8(Z, radii[i], centres[i], dev) for i in mine}
+        masks = None
+        voxels = count * Z * H * W
+        per_gpu_vox = len(mine) * Z * H * W
+    else:
+        masks = make_phantom_u8(Zg, H, W, z0, z1, dev)
+        voxels = Zg * H * W * (world if replicas else 1)
+        per_gpu_vox = (z1 - z0) * H * W
 
     def step(mark=None):
-        if world > 1:
+        if path == "batch":
+            return batch.reconstruct_volumes(stacks, THRESHOLD, sides, *phys)
+        if path == "sdf":
+            if sharded_run:
+                return sharded.reconstruct_sdf(masks, Zg, z0, THRESHOLD, sides, *phys)
+            return pipeline.reconstruct_sdf(masks, THRESHOLD, sides, *phys)
+        if sharded_run:
             if mark is not None or args.staged:
-                return sharded.reconstruct(masks, Zg, z0, THRESHOLD, sides, PHYS["total_depth_mm"], PHYS["x_length_mm"],
-                                           PHYS["y_length_mm"], mark=mark)
+                return sharded.reconstruct(masks, Zg, z0, THRESHOLD, sides, *phys, mark=mark)
             # fused: pack -> NCCL halo exchange -> one t3d_reconstruct_slab enqueue -> all-gather -> stitch, one sync
-            return sharded.reconstruct_fused(masks, Zg, z0, THRESHOLD, sides, PHYS["total_depth_mm"], PHYS["x_length_mm"],
-                                             PHYS["y_length_mm"], use_graph=not args.no_graph)
+            return sharded.reconstruct_fused(masks, Zg, z0, THRESHOLD, sides, *phys, use_graph=not args.no_graph)
         if mark is not None or args.staged:   # staged path: one library call per stage (per-stage event timing)
-            return pipeline.reconstruct(masks, THRESHOLD, sides, PHYS["total_depth_mm"], PHYS["x_length_mm"],
-                                        PHYS["y_length_mm"], mark=mark)
+            return pipeline.reconstruct(masks, THRESHOLD, sides, *phys, mark=mark)
         # fused path: the whole step is one t3d_reconstruct enqueue replayed from a CUDA graph + one D2H copy
-        return pipeline.reconstruct_fused(masks, THRESHOLD, sides, PHYS["total_depth_mm"], PHYS["x_length_mm"],
-                                          PHYS["y_length_mm"], use_graph=not args.no_graph)
+        return pipeline.reconstruct_fused(masks, THRESHOLD, sides, *phys, use_graph=not args.no_graph)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def all_ranks_agree(flag):
+        """True on every rank iff rank 0 says so (steps are collective when sharded: every rank must stop together)."""
+        if world == 1:
+            return flag
+        t = torch.tensor([1 if flag else 0], device=dev)
+        dist.broadcast(t, 0)
+        return bool(t.item())
+
     for _ in range(max(3, args.warmup)):
         res = step()
     barrier()
     # kernels of this library per step: counted on one eager (non-graph) step, a graph replay launches the same ones
     lc0 = lib.t3d_launch_count()
-    if world == 1 and not args.staged:
-        pipeline.reconstruct_fused(masks, THRESHOLD, sides, PHYS["total_depth_mm"], PHYS["x_length_mm"], PHYS["y_length_mm"],
-                                   use_graph=False)
-    elif world > 1 and not args.staged:
-        sharded.reconstruct_fused(masks, Zg, z0, THRESHOLD, sides, PHYS["total_depth_mm"], PHYS["x_length_mm"], PHYS["y_length_mm"],
-                                  use_graph=False)
+    if path == "occupancy" and not args.staged:
+        if sharded_run:
+            sharded.reconstruct_fused(masks, Zg, z0, THRESHOLD, sides, *phys, use_graph=False)
+        else:
+            pipeline.reconstruct_fused(masks, THRESHOLD, sides, *phys, use_graph=False)
     else:
         step()
     launches_per_step = lib.t3d_launch_count() - lc0
     barrier()
-    l0 = lib.t3d_launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local_rank) as clocks:
+        # load phase: the same step back to back until the sampler has delivered a few rows (a C1 step is ~1 ms, the
+        # sampling period 100 ms), then the timed region, then a short load phase again so that samples bracket it
+        t_load = time.perf_counter()
+        while not all_ranks_agree(clocks.n_rows() >= 3 or time.perf_counter() - t_load > 4.0):
+            for _ in range(10 if path == "occupancy" else 1):
+                step()
         barrier()
+        t0 = time.perf_counter()
         ev0.record()
         for _ in range(args.steps):
             res = step()
         ev1.record()
+        barrier()
+        t1 = time.perf_counter()
+        clocks.window(t0, t1)
+        n_before = clocks.n_rows()
+        t_load = time.perf_counter()
+        while not all_ranks_agree(clocks.n_rows() >= n_before + 2 or time.perf_counter() - t_load > 1.0):
+            for _ in range(10 if path == "occupancy" else 1):
+                step()
         barrier()
     ms = ev0.elapsed_time(ev1)
     launches = launches_per_step
@@ -255,26 +415,27 @@ def run_ours(args, Z, H, W):
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-    voxels = Zg * H * W
     value = voxels * args.steps / (ms * 1e-3) / 1e9
 
-    # ---- dominant kernel by bytes, timed alone on the launching stream: k_pack_flat (t3d_pack_masks) streams the whole
-    # u8 stack (larger than L2) and writes the bit volume
-    n_own = z1 - z0
-    kbits = torch.empty((n_own, H, engine.words_per_row(W)), dtype=torch.int32, device=dev)
-    kst = engine._stream()
-    for _ in range(3):
-        lib.t3d_pack_masks(engine._p(masks), n_own, H, W, THRESHOLD, engine._p(kbits), kst)
-    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
-    K_REP = 20
-    k0.record()
-    for _ in range(K_REP):
-        lib.t3d_pack_masks(engine._p(masks), n_own, H, W, THRESHOLD, engine._p(kbits), kst)
-    k1.record()
-    torch.cuda.synchronize()
-    pack_ms = k0.elapsed_time(k1) / K_REP
-    del kbits
+    # ---- the kernel that moves the most bytes, timed alone on the launching stream: the mask decode / bit packing
+    # streams the whole u8 stack (larger than L2) and writes the bit volume
+    pack_ms = None
+    if masks is not None:
+        n_own = z1 - z0
+        kbits = torch.empty((n_own, H, engine.words_per_row(W)), dtype=torch.int32, device=dev)
+        kst = engine._stream()
+        for _ in range(3):
+            lib.t3d_pack_masks(engine._p(masks), n_own, H, W, THRESHOLD, engine._p(kbits), kst)
+        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        K_REP = 20
+        k0.record()
+        for _ in range(K_REP):
+            lib.t3d_pack_masks(engine._p(masks), n_own, H, W, THRESHOLD, engine._p(kbits), kst)
+        k1.record()
+        torch.cuda.synchronize()
+        pack_ms = k0.elapsed_time(k1) / K_REP
+        del kbits
 
     # ---- per-stage device times (one instrumented step, events on the launching stream)
     marks = []
@@ -285,19 +446,21 @@ def run_ours(args, Z, H, W):
         marks.append((name, e))
 
     stage_ms = {}
-    for _ in range(3):
-        marks.clear()
-        barrier()
-        mark("start")
-        step(mark)
-        barrier()
-        for (n0, e0), (n1, e1) in zip(marks[:-1], marks[1:]):
-            stage_ms.setdefault(n1, []).append(e0.elapsed_time(e1))
-    stage_ms = {k: float(np.min(v)) for k, v in stage_ms.items()}
+    if path == "occupancy":
+        for _ in range(3):
+            marks.clear()
+            barrier()
+            mark("start")
+            step(mark)
+            barrier()
+            for (n0, e0), (n1, e1) in zip(marks[:-1], marks[1:]):
+                stage_ms.setdefault(n1, []).append(e0.elapsed_time(e1))
+        stage_ms = {k: float(np.min(v)) for k, v in stage_ms.items()}
 
     # ---- e2e through the reference-facing classes, host buffers in pinned memory
     e2e = e2e_classes = None
-    if world == 1 and not args.no_e2e:
+    want_e2e = path == "occupancy" and not args.no_e2e
+    if want_e2e and not sharded_run:
         from tomography_3d_reconstructor_b200 import VoxelProcessor, SurfaceExtractor, VolumeCalculator
         host_bool = torch.empty((Z, H, W), dtype=torch.bool, pin_memory=True)
         host_bool.copy_(masks >= THRESHOLD)          # image_loader.py:108 happens upstream of the hot path
@@ -331,7 +494,7 @@ def run_ours(args, Z, H, W):
             torch.cuda.synchronize()
             e2e_s = (time.perf_counter() - t0) / n_e2e
         vox, sm, v, f, props = out
-        e2e_classes = {"value": voxels / e2e_s / 1e9, "unit": "Gvoxels/s", "h2d_bytes_per_step": int(hb.nbytes),
+        e2e_classes = {"value": voxels / world / e2e_s / 1e9, "unit": "Gvoxels/s", "h2d_bytes_per_step": int(hb.nbytes),
                        "d2h_bytes_per_step": int(vox.nbytes + sm.nbytes + v.nbytes + f.nbytes), "ms_per_step": 1e3 * e2e_s,
                        "steps": n_e2e, "api": "VoxelProcessor.create_voxel_data -> smooth_voxel_data -> "
                        "SurfaceExtractor.extract_manifold_surface -> calculate_mesh_volume/area -> "
@@ -345,19 +508,22 @@ def run_ours(args, Z, H, W):
         u8_list = [hu[z] for z in range(Z)]
 
         def host_step():
-            return pipeline.reconstruct_host(u8_list, THRESHOLD, sides, PHYS["total_depth_mm"], PHYS["x_length_mm"],
-                                             PHYS["y_length_mm"], use_graph=not args.no_graph)
+            return pipeline.reconstruct_host(u8_list, THRESHOLD, sides, *phys, use_graph=not args.no_graph)
 
         for _ in range(2):
             out = host_step()
-        torch.cuda.synchronize()
+        barrier()
         t0 = time.perf_counter()
         for _ in range(n_e2e):
             out = host_step()
-        torch.cuda.synchronize()
+        barrier()
         e2e_s = (time.perf_counter() - t0) / n_e2e
-        e2e = {"value": voxels / e2e_s / 1e9, "unit": "Gvoxels/s", "h2d_bytes_per_step": int(hu.nbytes),
-               "d2h_bytes_per_step": int(out["vertices"].nbytes + out["faces"].nbytes + 8 * (32 + 2 * Z)),
+        if world > 1:
+            tm = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+            e2e_s = float(tm.item())
+        e2e = {"value": voxels / e2e_s / 1e9, "unit": "Gvoxels/s", "h2d_bytes_per_step": int(hu.nbytes) * world,
+               "d2h_bytes_per_step": int(out["vertices"].nbytes + out["faces"].nbytes + 8 * (32 + 2 * Z)) * world,
                "ms_per_step": 1e3 * e2e_s, "steps": n_e2e,
                "api": "pipeline.reconstruct_host: list of pinned host u8 masks -> H2D -> t3d_reconstruct -> D2H of the mesh "
                "(f32 vertices, int64 faces) and the result block (volumes, area, bbox, per-slice counts)"}
@@ -366,14 +532,15 @@ def run_ours(args, Z, H, W):
     def teardown():
         if world > 1:
             # captured graphs hold NCCL work: release them before the communicator goes away
-            sharded._slab_plans.clear()
+            if sharded_run:
+                sharded._slab_plans.clear()
             import gc
             gc.collect()
             torch.cuda.synchronize()
             dist.barrier()
             dist.destroy_process_group()
 
-    if world > 1 and not args.no_e2e:
+    if want_e2e and sharded_run:
         # sharded e2e: every rank uploads its slab from pinned host memory and downloads its slab of the stitched mesh
         host_u8 = torch.empty((z1 - z0, H, W), dtype=torch.uint8, pin_memory=True)
         host_u8.copy_(masks)
@@ -381,8 +548,7 @@ def run_ours(args, Z, H, W):
         hnp = host_u8.numpy()
 
         def host_step():
-            return sharded.reconstruct_host(hnp, Zg, z0, THRESHOLD, sides, PHYS["total_depth_mm"], PHYS["x_length_mm"],
-                                            PHYS["y_length_mm"], use_graph=not args.no_graph)
+            return sharded.reconstruct_host(hnp, Zg, z0, THRESHOLD, sides, *phys, use_graph=not args.no_graph)
 
         for _ in range(2):
             out = host_step()
@@ -404,6 +570,37 @@ def run_ours(args, Z, H, W):
                "api": "sharded.reconstruct_host: per-rank pinned host u8 slab -> H2D -> sharded step -> D2H of the rank's "
                "slab of the stitched mesh (bytes summed over ranks, time = max over ranks)"}
 
+    # ---- N > 1: the stitched mesh against a single-GPU run of the same stack (asserted)
+    check = None
+    if sharded_run and path == "occupancy" and not args.no_check:
+        del masks
+        masks = None
+        sharded._slab_plans.clear()
+        torch.cuda.empty_cache()
+        check = sharded_check(world, rank, dev)
+
+    # mesh totals
+    if path == "batch":
+        tot = torch.tensor([sum(o["n_vertices"] for o in res.values()), sum(o["n_faces"] for o in res.values()),
+                            sum(o["n_ambiguous"] for o in res.values())], dtype=torch.int64, device=dev)
+        if world > 1:
+            dist.all_reduce(tot)
+        V, F, n_amb = (int(x) for x in tot.tolist())
+        results = {"volumes": count, "first_volume_mesh_volume_mm3": float(res[mine[0]]["mesh_volume_mm3"]) if mine else None}
+    else:
+        mesh = res["mesh"]
+        V = int(res.get("total_vertices", mesh.verts.shape[0]))
+        F = int(res.get("total_faces", mesh.faces.shape[0]))
+        n_amb = int(getattr(mesh, "n_ambiguous", 0))
+        if replicas and world > 1:
+            V, F = V * world, F * world
+        results = {"voxel_volume_mm3": float(res["voxel_volume_mm3"]), "mesh_volume_mm3": float(res["mesh_volume_mm3"]),
+                   "surface_area_mm2": float(res["surface_area_mm2"]), "active_voxels": int(res["active_voxels"])}
+        if "stitch_consistent" in res:
+            results["stitch_consistent"] = bool(res["stitch_consistent"])
+            if not res["stitch_consistent"]:
+                raise AssertionError("sharded step: ghost tail / lead mismatch between neighbouring ranks")
+
     if rank != 0:
         teardown()
         return
@@ -415,62 +612,76 @@ def run_ours(args, Z, H, W):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
-    mesh = res["mesh"]
-    V = int(res.get("total_vertices", mesh.verts.shape[0]))
-    F = int(res.get("total_faces", mesh.faces.shape[0]))
     mesh_bytes = 12 * V + 12 * F
-    # dominant kernel by bytes: the mask decode / bit packing (1 B read + 1/8 B written per voxel)
-    per_gpu_vox = (z1 - z0) * H * W
-    dom = "k_pack_flat (t3d_pack_masks)"
-    dom_bytes = 1.125 * per_gpu_vox
-    achieved = dom_bytes / (pack_ms * 1e-3) / 1e9
-    stage_roofline = {k: {"GB/s": STAGE_BYTES[k] * per_gpu_vox / (stage_ms[k] * 1e-3) / 1e9,
-                          "frac": STAGE_BYTES[k] * per_gpu_vox / (stage_ms[k] * 1e-3) / 1e9 / peak}
-                      for k in STAGE_BYTES if k in stage_ms}
-    bytes_alg = 1.5 * voxels + mesh_bytes
+    # algorithmic bytes per voxel of the whole path + the mesh it writes
+    per_voxel = 17.5 if path == "sdf" else 1.5
+    bytes_alg = per_voxel * voxels + mesh_bytes
+    step_gbs = bytes_alg * args.steps / (ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "scope": "whole step (every kernel of the path, SURVEY.md 8d)", "achieved": step_gbs,
+                "peak": peak * world, "unit": "GB/s", "frac": step_gbs / (peak * world), "traffic": None,
+                "peak_source": peak_src + (" x %d GPUs" % world if world > 1 else ""),
+                "algorithmic_bytes_per_step": bytes_alg,
+                "algorithmic_bytes": "%.3g B/voxel x %d voxels + 12 B x (%d vertices + %d faces)" % (per_voxel, voxels, V, F)}
+    if pack_ms is not None:
+        dom_bytes = 1.125 * per_gpu_vox
+        achieved = dom_bytes / (pack_ms * 1e-3) / 1e9
+        roofline["dominant_kernel"] = {
+            "kernel": "k_pack_flat (t3d_pack_masks): moves the most bytes of any kernel of the step", "achieved": achieved,
+            "peak": peak, "unit": "GB/s", "frac": achieved / peak, "algorithmic_bytes_per_launch": dom_bytes,
+            "us_per_launch": 1e3 * pack_ms, "launches_timed": 20, "share_of_step": pack_ms / (ms / args.steps),
+            "traffic": NCU_PACK_TRAFFIC_BYTES if (Z, H, W) == (512, 1024, 1024) else None,
+            "traffic_source": "profiles/ ncu --set full capture of this kernel at C1: dram__bytes_read.sum + "
+                              "dram__bytes_write.sum per launch (most of the 67 MB bit volume stays in the 126 MB L2)"}
+    if stage_ms:
+        roofline["stages"] = {k: {"GB/s": STAGE_BYTES[k] * per_gpu_vox / (stage_ms[k] * 1e-3) / 1e9,
+                                  "frac": STAGE_BYTES[k] * per_gpu_vox / (stage_ms[k] * 1e-3) / 1e9 / peak}
+                              for k in STAGE_BYTES if k in stage_ms}
+    execution = {
+        "batch": "batch.reconstruct_volumes: all volumes of a rank in one t3d_reconstruct_batch enqueue, replayed from a CUDA graph",
+        "sdf": ("sharded.reconstruct_sdf: z-slab sharded, EDT z pass through an NCCL all-to-all transpose" if sharded_run
+                else "pipeline.reconstruct_sdf"),
+        "occupancy": ("z-slab sharded, staged launches" if sharded_run and args.staged else
+                      "z-slab sharded: pack, NCCL halo exchange, one t3d_reconstruct_slab enqueue, result all-gather, "
+                      "face stitching; one host sync per step" + ("" if args.no_graph else ", replayed from a CUDA graph (NCCL included)")
+                      if sharded_run else "staged launches" if args.staged else
+                      "one t3d_reconstruct enqueue per step" + ("" if args.no_graph else ", replayed from a CUDA graph")
+                      + ("; %d independent replicas, no collective" % world if world > 1 else "")),
+    }[path]
     line = {
         "metric": METRIC, "value": value, "unit": "Gvoxels/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8 -> bit-packed u32 (topology), f64 field taps -> f32 vertices", "data": "synthetic",
-        "config": {"workload": "C1 (BASELINE configs[1]): %d slices of %dx%d analytic ellipsoid masks (u8 0/255), threshold 200, "
-                   "close ends + opening/closing + Gaussian(0.5) marching cubes + volumes%s" %
-                   (Zg, H, W, "" if world == 1 else "; z-slab sharded over %d GPUs" % world),
-                   "shape": [Zg, H, W], "l2": "inputs larger than L2: %.0f MB of u8 masks per GPU per step" % (per_gpu_vox / 1e6),
-                   "mesh": {"vertices": V, "faces": F, "n_ambiguous_cubes": int(mesh.n_ambiguous)},
-                   "execution": ("z-slab sharded, staged launches" if world > 1 and args.staged else
-                                 "z-slab sharded: pack, NCCL halo exchange, one t3d_reconstruct_slab enqueue, result all-gather, "
-                                 "face stitching; one host sync per step" + ("" if args.no_graph else ", replayed from a CUDA graph (NCCL included)")
-                                 if world > 1 else "staged launches" if args.staged else
-                                 "one t3d_reconstruct enqueue per step" + ("" if args.no_graph else ", replayed from a CUDA graph"))},
+        "config": {"workload": "%s: %s analytic ellipsoid masks (u8 0/255), threshold 200, close ends + opening/closing + %s + volumes%s" %
+                   (cfg["name"], "%d volumes of %dx%dx%d" % (cfg["count"], Z, H, W) if path == "batch" else
+                    "%d slices of %dx%d" % (Zg, H, W),
+                    "exact EDT/SDF + marching cubes at level 0" if path == "sdf" else "Gaussian(0.5) marching cubes",
+                    "; z-slab sharded over %d GPUs" % world if sharded_run else ""),
+                   "config": args.config, "shape": [Zg, H, W],
+                   "l2": "inputs larger than L2: %.0f MB of u8 masks per GPU per step" % (per_gpu_vox / 1e6)
+                   if per_gpu_vox > 130e6 else "inputs of one step (%.0f MB of u8 masks) fit the 126 MB L2" % (per_gpu_vox / 1e6),
+                   "mesh": {"vertices": V, "faces": F, "n_ambiguous_cubes": n_amb},
+                   "execution": execution},
         "clocks": clocks.summary(),
         "gpu_launches": int(launches),
         "stages_ms": stage_ms,
-        "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": NCU_PACK_TRAFFIC_BYTES if (Z, H, W) == (512, 1024, 1024) else None,
-                     "traffic_source": "profiles/ ncu --set full capture of this kernel at C1: dram__bytes_read.sum + "
-                     "dram__bytes_write.sum per launch (most of the 67 MB bit volume stays in the 126 MB L2)",
-                     "peak_source": peak_src, "algorithmic_bytes_per_launch": dom_bytes,
-                     "us_per_launch": 1e3 * pack_ms, "launches_timed": K_REP, "share_of_step": pack_ms / (ms / args.steps),
-                     "stages": stage_roofline},
-        "pipeline_roofline": {"bytes_alg_per_step": bytes_alg, "achieved": bytes_alg * args.steps / (ms * 1e-3) / 1e9,
-                              "peak": peak * world, "unit": "GB/s",
-                              "frac": bytes_alg * args.steps / (ms * 1e-3) / 1e9 / (peak * world)},
-        "results": {"voxel_volume_mm3": float(res["voxel_volume_mm3"]), "mesh_volume_mm3": float(res["mesh_volume_mm3"]),
-                    "surface_area_mm2": float(res["surface_area_mm2"]), "active_voxels": int(res["active_voxels"])},
+        "roofline": roofline,
+        "results": results,
     }
+    if check is not None:
+        line["sharded_check"] = check
     if e2e is not None:
         line["e2e"] = e2e
     if e2e_classes is not None:
         line["e2e_classes"] = e2e_classes
-    if world == 1 and not args.no_cpu:
+    if world == 1 and not args.no_cpu and path == "occupancy":
         from oracle import cpu_ref
         cpu_ref.build()
-        secs, vox_s, n_sl = cpu_sample(Z, H, W, 96, 1)
+        secs, vox_s, n_sl = cpu_sample(Z, H, W, 96, 1, sides if args.config == "C0" else None)
         line["cpu_baseline"] = {"value": vox_s / secs / 1e9, "unit": "Gvoxels/s", "cores": 1, "kind": "port",
                                 "sample": "central z-slab of %d slices x %dx%d of the same phantom, oracle/cpu_ref.py "
                                 "(scipy.ndimage is single-threaded), %.1f s" % (n_sl, H, W, secs)}
-    print(json.dumps(line), flush=True)
     teardown()
+    print(json.dumps(line), flush=True)
 
 
 def main():
@@ -479,17 +690,23 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--shape", default="512,1024,1024", help="Z,H,W per GPU")
+    ap.add_argument("--config", default="C1", choices=sorted(CONFIGS), help="BASELINE.json configuration (C1 = configs[1], the headline)")
+    ap.add_argument("--shape", default=None, help="Z,H,W per GPU (overrides the shape of --config; occupancy path)")
+    ap.add_argument("--no-check", action="store_true", help="N>1: skip the stitched-mesh-vs-single-GPU check")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--staged", action="store_true", help="time the staged (one call per stage) path instead of the fused one")
     ap.add_argument("--no-graph", action="store_true", help="fused path without CUDA-graph replay")
     args = ap.parse_args()
-    Z, H, W = (int(v) for v in args.shape.split(","))
+    cfg = dict(CONFIGS[args.config])
+    Z, H, W = (int(v) for v in args.shape.split(",")) if args.shape else cfg["shape"]
+    if args.shape:
+        cfg.pop("sides", None)
+        cfg["name"] = "custom shape"
     if args.impl == "reference":
-        run_reference(args, Z, H, W)
+        run_reference(args, Z, H, W, cfg)
     else:
-        run_ours(args, Z, H, W)
+        run_ours(args, Z, H, W, cfg)
 
 
 if __name__ == "__main__":

@@ -99,7 +99,7 @@ int t3d_field_sign_lean(const void* occ_bits, int Z, int H, int W, int pad, cons
  *                      active cube origin
  *   (caller) exclusive scan of popcount(ballots) -> chunkbase_u32, n_active
  *   t3d_mc_words    -> aw_idx_u32[n_active] (flat word index) and aw_cnt_u32[4][n_active] (owned x/y/z cut edges,
- *                      triangles); n_ambiguous_u64: cubes whose tiling Lewiner's extra tests could change
+ *                      triangles); n_ambiguous_u64: cubes tiled through Lewiner's face / interior tests (mc_field)
  *   (caller) exclusive scan of aw_cnt -> aw_base_u32, totals n_x, n_y, n_z, n_t
  *   t3d_mc_emit     -> vkeys_u64[n_x+n_y+n_z] (edge key per vertex) and faces_i32 (n_t,3): reference cube order,
  *                      reversed winding (gradient_direction='descent')
@@ -108,15 +108,30 @@ int t3d_field_sign_lean(const void* occ_bits, int Z, int H, int W, int pad, cons
  * z_begin/z_end: owned planes of the sign volume ([0, Zs) on one device; -1 = Zs).  With z-slab sharding a rank owns
  * [z_begin, z_end) and additionally emits the x/y-edge vertices of ghost plane z_end; z_offset is the global padded
  * plane index of local padded plane 0. */
+/* The marched field as the ambiguity tests of t3d_mc_words / t3d_mc_emit see it.  Cubes whose index has an ambiguous face
+ * (Lewiner's cases 3, 6, 7, 10, 12, 13) or is case 4 are tiled by the row that Lewiner's face test (asymptotic decider) and
+ * interior test select (csrc/mc33_tables.h; oracle/mc_ref.c restates the same decisions); both need the corner VALUES:
+ *   field_f32 != NULL: dense float32 field of the sign volume's own shape (Z,H,W), marched at `level`;
+ *   else occ_bits != NULL: Gaussian(0.5) (gaussian = 1) of the occupancy (Z,H,W) padded by `pad`, as for t3d_mc_vertices;
+ *   NULL struct: only the signs are known (values level +- 0.5: every face test is a tie -> positive corners joined). */
+typedef struct t3d_mc_field {
+    const void* occ_bits;
+    int Z, H, W, pad, gaussian;
+    const double* weights3_host;
+    const void* field_f32;
+    double level;
+} t3d_mc_field;
+
 int64_t t3d_mc_num_chunks(int Zs, int Hs, int Ws);
 int t3d_mc_flags(const void* sign_bits, int Zs, int Hs, int Ws, int z_begin, int z_end, void* ballots_u32, void* stream);
 int t3d_mc_words(const void* sign_bits, int Zs, int Hs, int Ws, int z_begin, int z_end, const void* ballots_u32,
                  const void* chunkbase_u32,
-                 uint32_t n_active, void* aw_idx_u32, void* aw_cnt_u32, void* n_ambiguous_u64, void* stream);
+                 uint32_t n_active, void* aw_idx_u32, void* aw_cnt_u32, void* n_ambiguous_u64, const t3d_mc_field* mc_field,
+                 void* stream);
 int t3d_mc_emit(const void* sign_bits, int Zs, int Hs, int Ws, int z_begin, int z_end, const void* ballots_u32,
                 const void* chunkbase_u32,
                 const void* aw_idx_u32, const void* aw_base_u32, uint32_t n_active, uint32_t n_x, uint32_t n_y,
-                void* vkeys_u64, void* faces_i32, void* stream);
+                void* vkeys_u64, void* faces_i32, const t3d_mc_field* mc_field, void* stream);
 int t3d_mc_vertices(const void* occ_bits, int Z, int H, int W, int pad, int gaussian, const double* weights3_host,
                     const void* vkeys_u64, uint32_t n_x, uint32_t n_y, uint32_t n_z, int unpad_shift, int z_offset,
                     const void* cum_f64,
@@ -152,11 +167,11 @@ int t3d_exclusive_scan_u32_dev(const void* in, void* out, int64_t n_cap, int64_t
                                int popcount_input, const void* n_dev_u64, void* totals_u64, void* workspace, void* stream);
 int t3d_mc_words_dev(const void* sign_bits, int Zs, int Hs, int Ws, int z_begin, int z_end, const void* ballots_u32,
                      const void* chunkbase_u32, uint32_t cap_active, const void* sizes_u64, void* aw_idx_u32, void* aw_cnt_u32,
-                     void* n_ambiguous_u64, void* stream);
+                     void* n_ambiguous_u64, const t3d_mc_field* mc_field, void* stream);
 int t3d_mc_emit_dev(const void* sign_bits, int Zs, int Hs, int Ws, int z_begin, int z_end, const void* ballots_u32,
                     const void* chunkbase_u32, const void* aw_idx_u32, const void* aw_base_u32, uint32_t cap_active,
                     const void* sizes_u64, uint32_t cap_verts, uint32_t cap_faces, void* vkeys_u64, void* faces_i32,
-                    int parts /* 1: vertex keys, 2: faces, 3: both */, void* stream);
+                    int parts /* 1: vertex keys, 2: faces, 3: both */, const t3d_mc_field* mc_field, void* stream);
 int t3d_mc_vertices_dev(const void* occ_bits, int Z, int H, int W, int pad, int gaussian, const double* weights3_host,
                         const void* vkeys_u64, const void* sizes_u64, uint32_t cap_verts, int unpad_shift, int z_offset,
                         const void* cum_f64, const void* adj_f64, int n_cum, double mm_per_pixel_y, double mm_per_pixel_x,

@@ -33,7 +33,6 @@ from scipy import ndimage
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _REF_DIR = os.path.join(_HERE, "_ref")
 _MC_SO = os.path.join(_REF_DIR, "libmc_ref.so")
-_CSRC = os.path.join(_HERE, "..", "tomography_3d_reconstructor_b200", "csrc")
 
 
 # --------------------------------------------------------------------------------------------
@@ -42,13 +41,12 @@ _CSRC = os.path.join(_HERE, "..", "tomography_3d_reconstructor_b200", "csrc")
 def build(force: bool = False) -> str:
     """Compile oracle/mc_ref.c -> oracle/_ref/libmc_ref.so (gcc, no external dependencies)."""
     src = os.path.join(_HERE, "mc_ref.c")
-    hdr = os.path.join(_CSRC, "mc_tables.h")
+    hdr = os.path.join(_HERE, "mc33_tables_oracle.h")      # the oracle's own tables: nothing under the product tree is included
     os.makedirs(_REF_DIR, exist_ok=True)
     if (not force and os.path.exists(_MC_SO)
             and os.path.getmtime(_MC_SO) >= max(os.path.getmtime(src), os.path.getmtime(hdr))):
         return _MC_SO
-    cmd = ["gcc", "-O2", "-fPIC", "-shared", "-std=c99", "-ffp-contract=off", "-I", _CSRC,
-           src, "-o", _MC_SO, "-lm"]
+    cmd = ["gcc", "-O2", "-fPIC", "-shared", "-std=c99", "-ffp-contract=off", "-I", _HERE, src, "-o", _MC_SO, "-lm"]
     subprocess.check_call(cmd)
     return _MC_SO
 
@@ -67,7 +65,9 @@ def _mc_lib():
             ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double,
             ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64,
             ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int64),
-            ctypes.POINTER(ctypes.c_int64), ctypes.c_void_p]
+            ctypes.POINTER(ctypes.c_int64), ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
+        _lib.t3d_oracle_resolve_cube.restype = ctypes.c_int
+        _lib.t3d_oracle_resolve_cube.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
         _lib.t3d_oracle_cube_cases.restype = ctypes.c_int
         _lib.t3d_oracle_cube_cases.argtypes = [
             ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_void_p]
@@ -185,11 +185,25 @@ def scalar_field(volume_data: np.ndarray, manifold: bool = True, add_padding: bo
     return np.ascontiguousarray(vol, dtype=np.float32)
 
 
-def marching_cubes(vol32: np.ndarray, level: float = 0.5, want_hist: bool = False):
+last_mc33_stats = None   # of the last marching_cubes() call: [ambiguous cubes, resolved row != classic row, tunnels, interior tests]
+
+
+def resolve_cube(values, level: float = 0.0):
+    """Resolved triangle row of one cube (8 corner values): (triangles (n,3) int8 of cube-edge ids, J bits, tunnel, row)."""
+    v = np.ascontiguousarray(np.asarray(values, dtype=np.float64) - level)
+    out = np.full(36, -1, dtype=np.int8)
+    info = np.zeros(3, dtype=np.int32)
+    n = _mc_lib().t3d_oracle_resolve_cube(v.ctypes.data, out.ctypes.data, info.ctypes.data)
+    return out[:3 * n].reshape(-1, 3).copy(), int(info[0]), int(info[1]), int(info[2])
+
+
+def marching_cubes(vol32: np.ndarray, level: float = 0.5, want_hist: bool = False, z_base: int = 0):
     """skimage.measure.marching_cubes(volume, level) restated (oracle/mc_ref.c).
 
     Returns (verts float32 (V,3) [z,y,x], faces int32 (F,3), n_ambiguous[, case histogram]).
     Raises ValueError / RuntimeError exactly where skimage does (level outside range / no surface).
+    z_base (test aid, 0 = skimage): vol32 is a z-slab starting at plane z_base of a larger volume; vertex z coordinates
+    are formed from the global plane index, as a run on the whole volume would.
     """
     vol32 = np.ascontiguousarray(vol32, dtype=np.float32)
     if vol32.ndim != 3:
@@ -204,18 +218,21 @@ def marching_cubes(vol32: np.ndarray, level: float = 0.5, want_hist: bool = Fals
     hist = np.zeros(256, dtype=np.int64) if want_hist else None
     rc = lib.t3d_oracle_marching_cubes(vol32.ctypes.data, nz, ny, nx, float(level), None, 0, None, 0,
                                        ctypes.byref(nv), ctypes.byref(nf), ctypes.byref(na),
-                                       hist.ctypes.data if want_hist else None)
+                                       hist.ctypes.data if want_hist else None, None, int(z_base))
     if rc:
         raise RuntimeError("oracle marching cubes failed (%d)" % rc)
     if nf.value == 0:
         raise RuntimeError("No surface found at the given iso value.")
     verts = np.empty((nv.value, 3), dtype=np.float32)
     faces = np.empty((nf.value, 3), dtype=np.int32)
+    stats = np.zeros(4, dtype=np.int64)
     rc = lib.t3d_oracle_marching_cubes(vol32.ctypes.data, nz, ny, nx, float(level),
                                        verts.ctypes.data, nv.value, faces.ctypes.data, nf.value,
-                                       ctypes.byref(nv), ctypes.byref(nf), ctypes.byref(na), None)
+                                       ctypes.byref(nv), ctypes.byref(nf), ctypes.byref(na), None, stats.ctypes.data, int(z_base))
     if rc:
         raise RuntimeError("oracle marching cubes failed (%d)" % rc)
+    global last_mc33_stats
+    last_mc33_stats = stats.tolist()
     if want_hist:
         return verts, faces, na.value, hist
     return verts, faces, na.value

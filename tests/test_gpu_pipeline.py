@@ -278,6 +278,37 @@ def test_batch_of_independent_phantoms_matches_the_oracle(eng, oracle):
         assert abs(got[i]["mesh_volume_mm3"] - ref["mesh_volume"]) <= 1e-6 * ref["mesh_volume"]
 
 
+def test_many_volumes_in_flight_match_the_one_at_a_time_batch(eng, oracle):
+    """batch.reconstruct_volumes (several plans / streams / captured graphs in flight) against batch.reconstruct_batch and
+    the oracle; the second call is the steady state, a volume larger than any seen before falls back and is re-learned."""
+    from tomography_3d_reconstructor_b200 import batch, pipeline
+    n, count = 40, 7
+    radii, centres = batch.phantom_params(count, n, seed=99)
+    dev = torch.device("cuda", 0)
+    stacks = {i: batch.phantom_u8(n, radii[i], centres[i], dev) for i in range(count)}
+    sides = (5, 30, 5)
+    phys = (6.0, 143.1, 95.03)
+    batch._batch_caps.clear(); batch._batch_slots.clear()
+    small = {i: stacks[i] for i in range(count - 1)}
+    for rep in range(3):          # 1: learns the capacities (staged), 2-3: in flight
+        got = batch.reconstruct_volumes(small, 200, sides, *phys, keep_mesh=True, slots=3)
+        assert sorted(got) == sorted(small)
+        for i in small:
+            ref = oracle.reference_pipeline(stacks[i].cpu().numpy(), 200, sides, *phys)
+            assert np.array_equal(got[i]["vertices"], ref["vertices"]) and np.array_equal(got[i]["faces"], ref["faces"]), (rep, i)
+            assert got[i]["voxel_volume_mm3"] == ref["voxel_volume"] and got[i]["processed_voxel_volume_mm3"] == ref["processed_volume"]
+            assert abs(got[i]["mesh_volume_mm3"] - ref["mesh_volume"]) <= 1e-6 * ref["mesh_volume"]
+    # a much larger object than the learned capacities allow: staged fallback for that item, capacities grow
+    big = torch.zeros((n, n, n), dtype=torch.uint8, device=dev)
+    big[1:-1, 1:-1, 1:-1] = 255
+    big[::2, ::2, 5:35:2] = 0
+    mixed = dict(small)
+    mixed[count] = big
+    got = batch.reconstruct_volumes(mixed, 200, sides, *phys, keep_mesh=True, slots=3)
+    ref = oracle.reference_pipeline(big.cpu().numpy(), 200, sides, *phys)
+    assert np.array_equal(got[count]["vertices"], ref["vertices"]) and np.array_equal(got[count]["faces"], ref["faces"])
+
+
 @pytest.mark.parametrize("shape", [(1, 9, 33), (2, 5, 7), (3, 64, 31), (4, 3, 257), (5, 33, 130), (9, 40, 1)])
 def test_fused_path_on_degenerate_shapes(eng, oracle, shape):
     """Tiny / ragged stacks (one or two slices, rows narrower or slightly wider than a machine word, W = 1) through the
@@ -294,7 +325,7 @@ def test_fused_path_on_degenerate_shapes(eng, oracle, shape):
     pipeline._plans.clear(); pipeline._hints.clear(); pipeline._g0_caps.clear(); pipeline._generic_sort.clear()
     ref = oracle.reference_pipeline(u8, 200, sides, 6.0, 143.1, 95.03)
     for rep in range(3):
-        if ref["vertices"] is None:
+        if ref.get("vertices") is None:      # the oracle found nothing to mesh (reference: extract -> None)
             with pytest.raises((RuntimeError, ValueError)):
                 pipeline.reconstruct_fused(masks, *args, use_graph=False)
             continue

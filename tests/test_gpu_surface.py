@@ -266,3 +266,43 @@ def test_fast_canonicalize_falls_back_when_order_cannot_be_verified(eng, oracle)
     gv, gf = eng.canonicalize(tv, tf, fast=True)               # ... and the synchronous call falls back
     rv, rf = oracle.ensure_manifold_mesh(verts, faces)
     assert np.array_equal(gv.cpu().numpy(), rv) and np.array_equal(gf.cpu().numpy(), rf)
+
+
+@pytest.mark.parametrize("seed,density", [(5, 0.35), (6, 0.5), (7, 0.65)])
+def test_ambiguous_cubes_are_resolved_like_the_oracle(eng, oracle, seed, density):
+    """Raw noise (no smoothing): thousands of cubes with ambiguous faces / case 4.  Lewiner's face and interior tests pick
+    the tiling; GPU and oracle take the same decisions (same corner values, same arithmetic) -> identical faces."""
+    from tomography_3d_reconstructor_b200 import SurfaceExtractor
+    rng = np.random.default_rng(seed)
+    occ = rng.random((12, 30, 70)) < density
+    depths = oracle.calculate_slice_depths(6.0, 2, 8, 2)
+    se = SurfaceExtractor()
+    for add_padding in (True, False):
+        got = se.extract_manifold_surface(occ, depths, 0.31, 0.27, True, True, add_padding)
+        assert got is not None, se.last_error
+        rv, rf, namb = oracle.extract_manifold_surface(occ, depths, 0.31, 0.27, True, True, add_padding, return_diag=True)
+        amb, changed, tunnels, interior = oracle.last_mc33_stats
+        assert namb > 1000 and changed > 100 and tunnels > 10, (namb, changed, tunnels)
+        assert se.last_n_ambiguous == namb
+        check_mesh(got, (rv, rf))
+
+
+def test_ambiguous_cubes_on_a_dense_float_field(eng, oracle):
+    """The dense-field entry (SDF path) resolves ambiguous cubes from the field values themselves."""
+    from tomography_3d_reconstructor_b200 import SurfaceExtractor
+    rng = np.random.default_rng(3)
+    field = np.zeros((11, 21, 40), np.float32)
+    field[1:-1, 1:-1, 1:-1] = rng.random((9, 19, 38)).astype(np.float32)
+    depths = np.full(11, 0.5)
+    se = SurfaceExtractor()
+    got = se.extract_surface_from_sdf(field, depths, 0.3, 0.25, level=0.5)
+    assert got is not None, se.last_error
+    rv, rf, namb = oracle.marching_cubes(field, 0.5)
+    amb, changed, tunnels, interior = oracle.last_mc33_stats
+    assert changed > 100 and tunnels > 10
+    oracle.apply_variable_slice_depths(rv, depths, False)
+    rv[:, 1] *= 0.3
+    rv[:, 2] *= 0.25
+    uv, uf = oracle.ensure_manifold_mesh(rv, rf)
+    assert se.last_n_ambiguous == namb
+    assert np.array_equal(got[0], uv) and np.array_equal(got[1], uf)

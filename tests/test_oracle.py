@@ -196,3 +196,57 @@ def test_config0_real_generator_stack_known_answer(oracle):
     assert np.array_equal(depths, g["slice_depths"])
     vol = oracle.calculate_voxel_volume_variable_depth(vox, 143.1 / 512, 95.03 / 512, depths)
     assert vol == float(g["volume"]) == 28658.498565015263
+
+
+def _closed_oriented(v, f):
+    e = np.concatenate([f[:, [0, 1]], f[:, [1, 2]], f[:, [2, 0]]]).astype(np.int64)
+    key = e[:, 0] * (len(v) + 1) + e[:, 1]
+    rev = e[:, 1] * (len(v) + 1) + e[:, 0]
+    return np.array_equal(np.sort(key), np.sort(rev))
+
+
+def test_face_test_is_the_asymptotic_decider(oracle):
+    """Lewiner's face test on case 3 (corners 0 and 2 positive on the z=0 face): positives joined iff p1*p2 - n1*n2 >= 0."""
+    tris, J, tube, row = oracle.resolve_cube([1.0, -1.0, 0.1, -1.0, -1, -1, -1, -1])       # 0.1 - 1 < 0: separated
+    assert (J, tube) == (0, 0) and tris.tolist() == [[0, 8, 3], [1, 2, 10]]                # = the classic row (Lewiner 3.1)
+    tris, J, tube, row = oracle.resolve_cube([3.0, -1.0, 2.0, -1.0, -1, -1, -1, -1])       # 6 - 1 > 0: joined (3.2)
+    assert (J, tube) == (1, 0) and len(tris) == 4
+    tris, J, tube, row = oracle.resolve_cube([1.0, -1.0, 1.0, -1.0, -1, -1, -1, -1])       # exact tie -> joined
+    assert J == 1
+    # the complement (corners 0, 2 negative): the same face, positives 1 and 3
+    tris, J, tube, row = oracle.resolve_cube([-1.0, 0.1, -1.0, 1.0, 1, 1, 1, 1])
+    assert J == 0 and len(tris) == 4                                                       # negatives joined: the 4-triangle tiling
+    tris, J, tube, row = oracle.resolve_cube([-1.0, 3.0, -1.0, 2.0, 1, 1, 1, 1])
+    assert J == 1 and len(tris) == 2
+
+
+def test_interior_test_decides_the_case4_tunnel(oracle):
+    """Case 4 (corners 0 and 6 positive): strong corners -> the trilinear surface is one tunnel (4.2, 6 triangles);
+    weak corners -> two separate caps (4.1, 2 triangles)."""
+    strong = [10.0, -1, -1, -1, -1, -1, 10.0, -1]
+    tris, J, tube, row = oracle.resolve_cube(strong)
+    assert tube == 1 and len(tris) == 6
+    # the trilinear interpolant is indeed positive at the cube centre for the strong cube (tunnel), negative for the weak one
+    assert sum(strong) / 8 > 0
+    weak = [1.0, -5, -5, -5, -5, -5, 1.0, -5]
+    tris, J, tube, row = oracle.resolve_cube(weak)
+    assert tube == 0 and tris.tolist() == [[0, 8, 3], [5, 10, 6]] and sum(weak) / 8 < 0
+    # complement: the negative corners 0 and 6 joined through the interior
+    tris, J, tube, row = oracle.resolve_cube([-v for v in strong])
+    assert tube == 1 and len(tris) == 6
+
+
+def test_resolved_meshes_are_watertight_on_noise(oracle):
+    """Neighbouring cubes decide a shared ambiguous face from the same four values: no cracks, whatever the field."""
+    for seed in range(3):
+        rng = np.random.default_rng(seed)
+        vol = np.zeros((14, 15, 16), np.float32)
+        vol[1:-1, 1:-1, 1:-1] = rng.random((12, 13, 14)).astype(np.float32)
+        v, f, namb = oracle.marching_cubes(vol, 0.5)
+        amb, changed, tunnels, interior = oracle.last_mc33_stats
+        assert namb == amb > 100 and changed > 50 and tunnels > 5 and interior >= tunnels
+        assert _closed_oriented(v, f)
+        # and through the whole extraction (Gaussian field of a noisy occupancy)
+        occ = rng.random((10, 20, 30)) < 0.35
+        ev, ef, n2 = oracle.extract_manifold_surface(occ, np.ones(10), 1.0, 1.0, True, True, True, return_diag=True)
+        assert n2 > 0 and _closed_oriented(ev, ef)

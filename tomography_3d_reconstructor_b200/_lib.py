@@ -14,6 +14,12 @@ LIB_PATH = os.path.join(_HERE, "libt3d.so")
 _c = ctypes
 _vp, _i, _i64, _u32, _dbl = _c.c_void_p, _c.c_int, _c.c_int64, _c.c_uint32, _c.c_double
 
+class McField(ctypes.Structure):
+    """struct t3d_mc_field (include/t3d.h): the marched field as the ambiguity tests of marching cubes see it."""
+    _fields_ = [("occ_bits", _vp), ("Z", _i), ("H", _i), ("W", _i), ("pad", _i), ("gaussian", _i), ("weights3_host", _vp),
+                ("field_f32", _vp), ("level", _dbl)]
+
+
 # name -> (restype, argtypes); mirrors include/t3d.h one to one (tests/test_abi.py checks both directions)
 SIGNATURES = {
     "t3d_last_error": (_c.c_char_p, []),
@@ -37,8 +43,8 @@ SIGNATURES = {
     "t3d_field_sign_lean": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _u32, _vp, _vp]),
     "t3d_mc_num_chunks": (_i64, [_i, _i, _i]),
     "t3d_mc_flags": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp]),
-    "t3d_mc_words": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _u32, _vp, _vp, _vp, _vp]),
-    "t3d_mc_emit": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _u32, _u32, _u32, _vp, _vp, _vp]),
+    "t3d_mc_words": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _u32, _vp, _vp, _vp, _vp, _vp]),
+    "t3d_mc_emit": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _u32, _u32, _u32, _vp, _vp, _vp, _vp]),
     "t3d_mc_vertices": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _u32, _u32, _u32, _i, _i, _vp, _vp, _i, _dbl, _dbl, _i,
                              _vp, _vp]),
     "t3d_field_dense": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
@@ -50,8 +56,8 @@ SIGNATURES = {
     "t3d_mesh_measure_workspace_bytes": (_i64, []),
     "t3d_mesh_measure": (_i, [_vp, _i64, _vp, _i64, _i, _vp, _vp, _vp]),
     "t3d_exclusive_scan_u32_dev": (_i, [_vp, _vp, _i64, _i64, _i, _i, _i, _vp, _vp, _vp, _vp]),
-    "t3d_mc_words_dev": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _u32, _vp, _vp, _vp, _vp, _vp]),
-    "t3d_mc_emit_dev": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _u32, _vp, _u32, _u32, _vp, _vp, _i, _vp]),
+    "t3d_mc_words_dev": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _u32, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "t3d_mc_emit_dev": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _u32, _vp, _u32, _u32, _vp, _vp, _i, _vp, _vp]),
     "t3d_mc_vertices_dev": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _u32, _i, _i, _vp, _vp, _i, _dbl, _dbl, _i, _i, _vp, _vp]),
     "t3d_mesh_canonicalize_fast_dev": (_i, [_vp, _i64, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "t3d_mesh_measure_dev": (_i, [_vp, _vp, _i64, _vp, _i, _vp, _vp, _vp]),

@@ -265,3 +265,11 @@ static inline OccView t3d_make_view_strided(const void* origin, int Z, int H, in
 int t3d_mc_vertices_view_dev(const OccView& view, int x_off, const void* vkeys_u64, const void* sizes_u64, uint32_t cap_verts,
                              int unpad_shift, int z_offset, const void* cum_f64, const void* adj_f64, int n_cum, double mm_per_pixel_y,
                              double mm_per_pixel_x, int scale_in_f64, int which_blocks, void* verts_f32, void* stream);
+// t3d_mc.cu: counting / emission passes whose ambiguity tests evaluate the field on a strided view (same x_off convention)
+int t3d_mc_words_view_dev(const OccView& view, int x_off, const void* sign_bits, int Zs, int Hs, int Ws, int z_begin, int z_end,
+                          const void* ballots_u32, const void* chunkbase_u32, uint32_t cap_active, const void* sizes_u64,
+                          void* aw_idx_u32, void* aw_cnt_u32, void* n_ambiguous_u64, void* stream);
+int t3d_mc_emit_view_dev(const OccView& view, int x_off, const void* sign_bits, int Zs, int Hs, int Ws, int z_begin, int z_end,
+                         const void* ballots_u32, const void* chunkbase_u32, const void* aw_idx_u32, const void* aw_base_u32,
+                         uint32_t cap_active, const void* sizes_u64, uint32_t cap_verts, uint32_t cap_faces, void* vkeys_u64,
+                         void* faces_i32, int parts, void* stream);

@@ -17,6 +17,8 @@
 // corner).  Faces come out in the reference's order: cubes z-major, y, x fastest, table order inside a cube,
 // winding reversed (gradient_direction='descent').
 #include "mc_tables.h"
+#include "mc33_tables.h"
+#include "t3d.h"
 #include "t3d_field.cuh"
 
 // ------------------------------------------------------------------------------------------------
@@ -26,24 +28,108 @@ __device__ __align__(16) const int8_t g_tri_table[256][T3D_MC_ROW] = {T3D_TRI_TA
 static const int8_t h_tri_table[256][T3D_MC_ROW] = {T3D_TRI_TABLE_ROWS};
 
 struct McLuts {
-    uint8_t ntri[256];
-    uint8_t amb[256];
+    uint8_t ntri[256];   // triangles of the classic row
+    uint8_t amb[256];    // 1: the index has an ambiguous face or is Lewiner's case 4 -> resolved per cube (mc33_resolve)
 };
 __constant__ McLuts c_luts;
 
-static int host_is_ambiguous(int idx)
+// Tilings of the ambiguous configurations (generated, tools/gen_mc33_tables.py): row = base[index] + (J | tube << k), J = bit i
+// set iff the positive corners are joined across the i-th ambiguous face, tube = the interior test asks for a tunnel.
+// These tables are only touched by cubes with an ambiguous index (none on smooth closed surfaces, a few % on noise).
+__device__ const int8_t g33_rows[T3D_MC33_NROWS][T3D_MC33_ROW] = {T3D_MC33_TRI_ROWS};
+__device__ const uint8_t g33_ntri[T3D_MC33_NROWS] = {T3D_MC33_NTRI_VALUES};
+__device__ const uint16_t g33_base[256] = {T3D_MC33_BASE_VALUES};
+__device__ const uint8_t g33_k[256] = {T3D_MC33_K_VALUES};
+__device__ const uint8_t g33_faces[256][6] = {T3D_MC33_FACES_VALUES};
+__device__ const unsigned long long g33_need[256] = {T3D_MC33_NEED_VALUES};
+__device__ const uint8_t g33_pol[256] = {T3D_MC33_POL_VALUES};
+__device__ const int8_t g33_sign[256] = {T3D_MC33_SIGN_VALUES};
+__device__ const uint8_t g33_cyc[6][4] = {T3D_MC33_FACE_CYCLE_VALUES};
+static const uint16_t h33_base[256] = {T3D_MC33_BASE_VALUES};
+
+// The marched field as the ambiguity tests see it (value - level at the 8 corners of a cube).
+//   mode 0: only the sign volume is known: value - level = +-0.5 (every face test is a tie -> positives joined)
+//   mode 1: Gaussian(0.5) of the padded occupancy `occ` (or the occupancy itself), evaluated exactly like the vertex kernel
+//   mode 2: dense float32 field of the sign volume's own shape (SDF path)
+struct McField {
+    OccView occ;
+    const float* field;
+    double level;
+    int x_off;      // sign-volume x minus this = x in occ's padded grid (padded-storage layout of the fused pipeline)
+    int mode;
+};
+
+#define MC33_EPS 2.220446049250313e-16   // np.spacing(1.0): skimage's `FLT_EPSILON` (tie threshold of the face test, vertex weights)
+
+// Lewiner's test_face in the form "are the POSITIVE corners joined across face f" (oracle/mc_ref.c: face_joined)
+__device__ __forceinline__ int mc33_face_joined(const double* v, int f)
 {
-    static const int FC[6][4] = {{0, 1, 2, 3}, {4, 5, 6, 7}, {0, 1, 5, 4}, {3, 2, 6, 7}, {0, 3, 7, 4}, {1, 2, 6, 5}};
-    for (int f = 0; f < 6; ++f) {
-        const int a = (idx >> FC[f][0]) & 1, b = (idx >> FC[f][1]) & 1, c = (idx >> FC[f][2]) & 1, d = (idx >> FC[f][3]) & 1;
-        if (a == c && b == d && a != b) return 1;
+    const double A = v[g33_cyc[f][0]], B = v[g33_cyc[f][1]], C = v[g33_cyc[f][2]], D = v[g33_cyc[f][3]];
+    const double ac = __dmul_rn(A, C), bd = __dmul_rn(B, D);
+    const double det = (A > 0.0) ? __dsub_rn(ac, bd) : __dsub_rn(bd, ac);
+    return det > -MC33_EPS;
+}
+
+// Lewiner's test_interior, z-sweep variant (oracle/mc_ref.c: interior_test): 1 = the s-signed corners are NOT joined inside
+__device__ __forceinline__ int mc33_interior_test(const double* v, int s)
+{
+    const double d40 = __dsub_rn(v[4], v[0]), d62 = __dsub_rn(v[6], v[2]), d73 = __dsub_rn(v[7], v[3]), d51 = __dsub_rn(v[5], v[1]);
+    const double a = __dsub_rn(__dmul_rn(d40, d62), __dmul_rn(d73, d51));
+    const double b = __dsub_rn(__dsub_rn(__dadd_rn(__dmul_rn(v[2], d40), __dmul_rn(v[0], d62)), __dmul_rn(v[1], d73)), __dmul_rn(v[3], d51));
+    const double t = __ddiv_rn(-b, __dmul_rn(2.0, a));
+    if (t < 0.0 || t > 1.0) return s > 0;
+    const double At = __dadd_rn(v[0], __dmul_rn(d40, t)), Bt = __dadd_rn(v[3], __dmul_rn(d73, t));
+    const double Ct = __dadd_rn(v[2], __dmul_rn(d62, t)), Dt = __dadd_rn(v[1], __dmul_rn(d51, t));
+    const int test = (At >= 0.0 ? 1 : 0) | (Bt >= 0.0 ? 2 : 0) | (Ct >= 0.0 ? 4 : 0) | (Dt >= 0.0 ? 8 : 0);
+    const double dec = __dsub_rn(__dmul_rn(At, Ct), __dmul_rn(Bt, Dt));
+    switch (test) {
+    case 5: if (dec < MC33_EPS) return s > 0; break;
+    case 10: if (dec >= MC33_EPS) return s > 0; break;
+    case 7: case 11: case 13: case 14: case 15: return s < 0;
+    default: return s > 0;
     }
-    static const int DG[4][2] = {{0, 6}, {1, 7}, {2, 4}, {3, 5}};
-    for (int k = 0; k < 4; ++k) {
-        const int m = (1 << DG[k][0]) | (1 << DG[k][1]);
-        if (idx == m || idx == (255 ^ m)) return 1;
+    return s < 0;
+}
+
+// row of g33_rows for the cube with origin (z, y, x) of the sign volume and ambiguous index cs
+__device__ __noinline__ int mc33_resolve(const McField& f, int z, int y, int x, int cs)
+{
+    double v[8];
+#pragma unroll 1
+    for (int c = 0; c < 8; ++c) {
+        const int dz = c >> 2, dy = (c >> 1) & 1, dx = (c ^ (c >> 1)) & 1;
+        float val;
+        if (f.mode == 1) val = field_value(f.occ, z + dz, y + dy, x - f.x_off + dx);
+        else if (f.mode == 2) val = f.field[((int64_t)(z + dz) * f.occ.H + (y + dy)) * f.occ.W + (x + dx)];
+        else val = ((cs >> c) & 1) ? 1.0f : 0.0f;
+        v[c] = __dsub_rn((double)val, f.level);
     }
-    return 0;
+    const int k = g33_k[cs];
+    int J = 0, tube = 0;
+    for (int i = 0; i < k; ++i) J |= mc33_face_joined(v, g33_faces[cs][i]) << i;
+    if ((g33_need[cs] >> J) & 1ull) {
+        const int I = mc33_interior_test(v, g33_sign[cs]);
+        tube = g33_pol[cs] ? I : !I;
+    }
+    return (int)g33_base[cs] + (J | (tube << k));
+}
+
+static McField mc_field_from_abi(const t3d_mc_field* a)
+{
+    McField f;
+    f.field = nullptr; f.level = 0.5; f.x_off = 0; f.mode = 0;
+    f.occ = t3d_make_view(nullptr, 1, 1, 1, 0, 0, nullptr);
+    if (!a) return f;
+    f.level = a->level;
+    if (a->field_f32) {
+        f.occ = t3d_make_view(nullptr, a->Z, a->H, a->W, 0, 0, nullptr);
+        f.field = (const float*)a->field_f32;
+        f.mode = 2;
+    } else if (a->occ_bits) {
+        f.occ = t3d_make_view(a->occ_bits, a->Z, a->H, a->W, a->pad, a->gaussian, a->weights3_host);
+        f.mode = 1;
+    }
+    return f;
 }
 
 static int ensure_luts()
@@ -54,7 +140,7 @@ static int ensure_luts()
         int n = 0;
         while (n < T3D_MC_ROW && h_tri_table[i][n] >= 0) n += 3;
         l.ntri[i] = (uint8_t)(n / 3);
-        l.amb[i] = (uint8_t)host_is_ambiguous(i);
+        l.amb[i] = (uint8_t)(h33_base[i] != T3D_MC33_NONE);
     }
     T3D_CUDA(cudaMemcpyToSymbol(c_luts, &l, sizeof(l)));
     return 0;
@@ -210,7 +296,7 @@ __global__ void __launch_bounds__(256) k_mc_compact(Grid g, const uint32_t* __re
     }
 }
 
-__global__ void __launch_bounds__(128) k_mc_words(Grid g, const uint32_t* __restrict__ aw_idx, uint32_t cap_active,
+__global__ void __launch_bounds__(128) k_mc_words(Grid g, McField fld, const uint32_t* __restrict__ aw_idx, uint32_t cap_active,
                                                   const unsigned long long* __restrict__ n_active_dev, uint32_t* __restrict__ aw_cnt,
                                                   unsigned long long* __restrict__ n_ambiguous)
 {
@@ -227,8 +313,12 @@ __global__ void __launch_bounds__(128) k_mc_words(Grid g, const uint32_t* __rest
         const int b = __ffs(a) - 1;
         a &= a - 1;
         const int cs = cube_case(m, b);
-        nt += c_luts.ntri[cs];
-        na += c_luts.amb[cs];
+        if (c_luts.amb[cs]) {     // resolved per cube with Lewiner's face / interior tests (rare)
+            nt += g33_ntri[mc33_resolve(fld, z, y, (w << 5) + b, cs)];
+            ++na;
+        } else {
+            nt += c_luts.ntri[cs];
+        }
     }
     aw_cnt[k] = __popc(m.X00);
     aw_cnt[(int64_t)n_active + k] = __popc(m.Y0);
@@ -242,6 +332,7 @@ __global__ void __launch_bounds__(128) k_mc_words(Grid g, const uint32_t* __rest
 // ------------------------------------------------------------------------------------------------
 struct EmitArgs {
     Grid g;
+    McField fld;
     const uint32_t* ballots;
     const uint32_t* chunkbase;
     const uint32_t* aw_idx;
@@ -360,6 +451,23 @@ __global__ void __launch_bounds__(128) k_mc_emit(EmitArgs a)
         const int cs = cube_case(m, b);
         const uint32_t lb = lt_mask(b), lb1 = lt_mask(b + 1);
         const bool last = (b == 31);
+        auto vertex_id = [&](int e) -> uint32_t {
+            const uint32_t at_next = (0x622u >> e) & 1u;           // edges 1, 5, 9, 10 sit at x + 1
+            uint32_t id = s_base[e][tid] + __popc(s_mask[e][tid] & (at_next ? lb1 : lb));
+            if (last && at_next) id = s_next[((e >> 2) & 1) + 2 * ((e >> 3) & 1) + ((e >> 3) & 1) * ((e >> 1) & 1)][tid];
+            return id;
+        };
+        if (c_luts.amb[cs]) {     // ambiguous index: the row Lewiner's tests select (same decision as in k_mc_words)
+            const int r = mc33_resolve(a.fld, z, y, x0 + b, cs);
+            const int8_t* row = g33_rows[r];
+            const int n3 = 3 * (int)g33_ntri[r];
+            for (int t = 0; t < n3; t += 3) {
+                int32_t* f = a.faces + 3 * (int64_t)pT;
+                f[0] = (int32_t)vertex_id(row[t + 2]); f[1] = (int32_t)vertex_id(row[t + 1]); f[2] = (int32_t)vertex_id(row[t]);
+                ++pT;
+            }
+            continue;
+        }
         const int4 trow = *reinterpret_cast<const int4*>(s_tri[cs]);   // 16 edge ids, -1 terminated
         const uint32_t tw[4] = {(uint32_t)trow.x, (uint32_t)trow.y, (uint32_t)trow.z, (uint32_t)trow.w};
         auto edge_at = [&](int t) -> int { return (int)(int8_t)((tw[t >> 2] >> ((t & 3) * 8)) & 0xffu); };
@@ -368,13 +476,7 @@ __global__ void __launch_bounds__(128) k_mc_emit(EmitArgs a)
             if (e0 < 0) break;
             uint32_t vid[3];
 #pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                const int e = (c == 0) ? e0 : edge_at(t + c);
-                const uint32_t at_next = (0x622u >> e) & 1u;           // edges 1, 5, 9, 10 sit at x + 1
-                uint32_t id = s_base[e][tid] + __popc(s_mask[e][tid] & (at_next ? lb1 : lb));
-                if (last && at_next) id = s_next[((e >> 2) & 1) + 2 * ((e >> 3) & 1) + ((e >> 3) & 1) * ((e >> 1) & 1)][tid];
-                vid[c] = id;
-            }
+            for (int c = 0; c < 3; ++c) vid[c] = vertex_id((c == 0) ? e0 : edge_at(t + c));
             int32_t* f = a.faces + 3 * (int64_t)pT;
             f[0] = (int32_t)vid[2]; f[1] = (int32_t)vid[1]; f[2] = (int32_t)vid[0];
             ++pT;
@@ -415,10 +517,10 @@ __device__ __forceinline__ void vertex_body(const VertexArgs& p, const double* z
     } else {
         edge_field_values<AXIS>(p.occ, zlut, z, y, x, fa, fb);
     }
-    // skimage: strength = 1/(FLT_EPSILON + |v - level|), centre of mass of the two corners, all in double
+    // skimage: strength = 1/(eps + |v - level|), eps = np.spacing(1.0), centre of mass of the two corners, all in double
     const double va = (double)fa - p.level, vb = (double)fb - p.level;
-    const double wa = __ddiv_rn(1.0, __dadd_rn(1.1920928955078125e-07, fabs(va)));
-    const double wb = __ddiv_rn(1.0, __dadd_rn(1.1920928955078125e-07, fabs(vb)));
+    const double wa = __ddiv_rn(1.0, __dadd_rn(MC33_EPS, fabs(va)));
+    const double wb = __ddiv_rn(1.0, __dadd_rn(MC33_EPS, fabs(vb)));
     const double frac = __ddiv_rn(wb, __dadd_rn(wa, wb));
     double pz = (double)(z + p.z_offset), py = (double)y, px = (double)x;
     if (AXIS == 0) pz = __dadd_rn(pz, frac); else if (AXIS == 1) py = __dadd_rn(py, frac); else px = __dadd_rn(px, frac);
@@ -523,10 +625,12 @@ extern "C" int t3d_mc_flags(const void* sign_bits, int Zs, int Hs, int Ws, int z
 // chunkbase_u32: exclusive scan of popcount(ballots); aw_idx_u32: n_active; aw_cnt_u32: 4 arrays of n_active
 extern "C" int t3d_mc_words(const void* sign_bits, int Zs, int Hs, int Ws, int z_begin, int z_end, const void* ballots_u32,
                             const void* chunkbase_u32,
-                            uint32_t n_active, void* aw_idx_u32, void* aw_cnt_u32, void* n_ambiguous_u64, void* stream)
+                            uint32_t n_active, void* aw_idx_u32, void* aw_cnt_u32, void* n_ambiguous_u64, const t3d_mc_field* mc_field,
+                            void* stream)
 {
     Grid g;
     if (int rc = make_grid(g, sign_bits, Zs, Hs, Ws, z_begin, z_end, "t3d_mc_words")) return rc;
+    const McField fld = mc_field_from_abi(mc_field);
     if (ensure_luts()) return 1;
     cudaStream_t st = (cudaStream_t)stream;
     if (t3d_zero_async(n_ambiguous_u64, 8, st)) return 1;
@@ -535,7 +639,7 @@ extern "C" int t3d_mc_words(const void* sign_bits, int Zs, int Hs, int Ws, int z
     k_mc_compact<<<(unsigned)((n_chunks + 255) / 256), 256, 0, st>>>(g, (const uint32_t*)ballots_u32,
                                                                       (const uint32_t*)chunkbase_u32, n_chunks,
                                                                       (uint32_t*)aw_idx_u32, n_active);
-    k_mc_words<<<(n_active + 127) / 128, 128, 0, st>>>(g, (const uint32_t*)aw_idx_u32, n_active, nullptr,
+    k_mc_words<<<(n_active + 127) / 128, 128, 0, st>>>(g, fld, (const uint32_t*)aw_idx_u32, n_active, nullptr,
                                                        (uint32_t*)aw_cnt_u32, (unsigned long long*)n_ambiguous_u64);
     T3D_CHECK_LAUNCH("t3d_mc_words");
     t3d_count_launches(2);
@@ -547,10 +651,11 @@ extern "C" int t3d_mc_words(const void* sign_bits, int Zs, int Hs, int Ws, int z
 extern "C" int t3d_mc_emit(const void* sign_bits, int Zs, int Hs, int Ws, int z_begin, int z_end, const void* ballots_u32,
                            const void* chunkbase_u32,
                            const void* aw_idx_u32, const void* aw_base_u32, uint32_t n_active, uint32_t n_x, uint32_t n_y,
-                           void* vkeys_u64, void* faces_i32, void* stream)
+                           void* vkeys_u64, void* faces_i32, const t3d_mc_field* mc_field, void* stream)
 {
     EmitArgs a;
     if (int rc = make_grid(a.g, sign_bits, Zs, Hs, Ws, z_begin, z_end, "t3d_mc_emit")) return rc;
+    a.fld = mc_field_from_abi(mc_field);
     if (ensure_luts()) return 1;
     if (n_active == 0) return 0;
     a.ballots = (const uint32_t*)ballots_u32;
@@ -609,9 +714,9 @@ extern "C" int t3d_mc_vertices(const void* occ_bits, int Z, int H, int W, int pa
 // device-size variants: every data-dependent size stays in device memory (sizes_u64 = {n_active, n_x, n_y, n_z, n_t}),
 // arrays are capacity-sized, nothing is written beyond the capacities.  No host round trip => graph-capturable.
 // ------------------------------------------------------------------------------------------------
-extern "C" int t3d_mc_words_dev(const void* sign_bits, int Zs, int Hs, int Ws, int z_begin, int z_end, const void* ballots_u32,
-                                const void* chunkbase_u32, uint32_t cap_active, const void* sizes_u64, void* aw_idx_u32,
-                                void* aw_cnt_u32, void* n_ambiguous_u64, void* stream)
+static int mc_words_dev_impl(const McField& fld, const void* sign_bits, int Zs, int Hs, int Ws, int z_begin, int z_end,
+                             const void* ballots_u32, const void* chunkbase_u32, uint32_t cap_active, const void* sizes_u64,
+                             void* aw_idx_u32, void* aw_cnt_u32, void* n_ambiguous_u64, void* stream)
 {
     Grid g;
     if (int rc = make_grid(g, sign_bits, Zs, Hs, Ws, z_begin, z_end, "t3d_mc_words_dev")) return rc;
@@ -622,7 +727,7 @@ extern "C" int t3d_mc_words_dev(const void* sign_bits, int Zs, int Hs, int Ws, i
     const int64_t n_chunks = (int64_t)g.n_rows * g.ncr;
     k_mc_compact<<<(unsigned)((n_chunks + 255) / 256), 256, 0, st>>>(g, (const uint32_t*)ballots_u32, (const uint32_t*)chunkbase_u32,
                                                                       n_chunks, (uint32_t*)aw_idx_u32, cap_active);
-    k_mc_words<<<(cap_active + 127) / 128, 128, 0, st>>>(g, (const uint32_t*)aw_idx_u32, cap_active,
+    k_mc_words<<<(cap_active + 127) / 128, 128, 0, st>>>(g, fld, (const uint32_t*)aw_idx_u32, cap_active,
                                                          (const unsigned long long*)sizes_u64, (uint32_t*)aw_cnt_u32,
                                                          (unsigned long long*)n_ambiguous_u64);
     T3D_CHECK_LAUNCH("t3d_mc_words_dev");
@@ -630,15 +735,24 @@ extern "C" int t3d_mc_words_dev(const void* sign_bits, int Zs, int Hs, int Ws, i
     return 0;
 }
 
-extern "C" int t3d_mc_emit_dev(const void* sign_bits, int Zs, int Hs, int Ws, int z_begin, int z_end, const void* ballots_u32,
-                               const void* chunkbase_u32, const void* aw_idx_u32, const void* aw_base_u32, uint32_t cap_active,
-                               const void* sizes_u64, uint32_t cap_verts, uint32_t cap_faces, void* vkeys_u64, void* faces_i32,
-                               int parts, void* stream)
+extern "C" int t3d_mc_words_dev(const void* sign_bits, int Zs, int Hs, int Ws, int z_begin, int z_end, const void* ballots_u32,
+                                const void* chunkbase_u32, uint32_t cap_active, const void* sizes_u64, void* aw_idx_u32,
+                                void* aw_cnt_u32, void* n_ambiguous_u64, const t3d_mc_field* mc_field, void* stream)
+{
+    return mc_words_dev_impl(mc_field_from_abi(mc_field), sign_bits, Zs, Hs, Ws, z_begin, z_end, ballots_u32, chunkbase_u32, cap_active,
+                             sizes_u64, aw_idx_u32, aw_cnt_u32, n_ambiguous_u64, stream);
+}
+
+static int mc_emit_dev_impl(const McField& fld, const void* sign_bits, int Zs, int Hs, int Ws, int z_begin, int z_end,
+                            const void* ballots_u32, const void* chunkbase_u32, const void* aw_idx_u32, const void* aw_base_u32,
+                            uint32_t cap_active, const void* sizes_u64, uint32_t cap_verts, uint32_t cap_faces, void* vkeys_u64,
+                            void* faces_i32, int parts, void* stream)
 {
     EmitArgs a;
     if (int rc = make_grid(a.g, sign_bits, Zs, Hs, Ws, z_begin, z_end, "t3d_mc_emit_dev")) return rc;
     if (ensure_luts()) return 1;
     if (cap_active == 0) return 0;
+    a.fld = fld;
     a.ballots = (const uint32_t*)ballots_u32;
     a.chunkbase = (const uint32_t*)chunkbase_u32;
     a.aw_idx = (const uint32_t*)aw_idx_u32;
@@ -657,6 +771,37 @@ extern "C" int t3d_mc_emit_dev(const void* sign_bits, int Zs, int Hs, int Ws, in
     T3D_CHECK_LAUNCH("t3d_mc_emit_dev");
     t3d_count_launches(1);
     return 0;
+}
+
+extern "C" int t3d_mc_emit_dev(const void* sign_bits, int Zs, int Hs, int Ws, int z_begin, int z_end, const void* ballots_u32,
+                               const void* chunkbase_u32, const void* aw_idx_u32, const void* aw_base_u32, uint32_t cap_active,
+                               const void* sizes_u64, uint32_t cap_verts, uint32_t cap_faces, void* vkeys_u64, void* faces_i32,
+                               int parts, const t3d_mc_field* mc_field, void* stream)
+{
+    return mc_emit_dev_impl(mc_field_from_abi(mc_field), sign_bits, Zs, Hs, Ws, z_begin, z_end, ballots_u32, chunkbase_u32, aw_idx_u32,
+                            aw_base_u32, cap_active, sizes_u64, cap_verts, cap_faces, vkeys_u64, faces_i32, parts, stream);
+}
+
+// the same on a strided occupancy view (padded-storage layout of the fused pipeline, t3d_pipeline.cu)
+int t3d_mc_words_view_dev(const OccView& view, int x_off, const void* sign_bits, int Zs, int Hs, int Ws, int z_begin, int z_end,
+                          const void* ballots_u32, const void* chunkbase_u32, uint32_t cap_active, const void* sizes_u64,
+                          void* aw_idx_u32, void* aw_cnt_u32, void* n_ambiguous_u64, void* stream)
+{
+    McField f;
+    f.occ = view; f.field = nullptr; f.level = 0.5; f.x_off = x_off; f.mode = 1;
+    return mc_words_dev_impl(f, sign_bits, Zs, Hs, Ws, z_begin, z_end, ballots_u32, chunkbase_u32, cap_active, sizes_u64, aw_idx_u32,
+                             aw_cnt_u32, n_ambiguous_u64, stream);
+}
+
+int t3d_mc_emit_view_dev(const OccView& view, int x_off, const void* sign_bits, int Zs, int Hs, int Ws, int z_begin, int z_end,
+                         const void* ballots_u32, const void* chunkbase_u32, const void* aw_idx_u32, const void* aw_base_u32,
+                         uint32_t cap_active, const void* sizes_u64, uint32_t cap_verts, uint32_t cap_faces, void* vkeys_u64,
+                         void* faces_i32, int parts, void* stream)
+{
+    McField f;
+    f.occ = view; f.field = nullptr; f.level = 0.5; f.x_off = x_off; f.mode = 1;
+    return mc_emit_dev_impl(f, sign_bits, Zs, Hs, Ws, z_begin, z_end, ballots_u32, chunkbase_u32, aw_idx_u32, aw_base_u32, cap_active,
+                            sizes_u64, cap_verts, cap_faces, vkeys_u64, faces_i32, parts, stream);
 }
 
 // vertices of a mesh emitted on a sign volume whose x coordinates are shifted by x_off against `view`'s padded grid

@@ -325,20 +325,20 @@ static int reconstruct_core(const uint32_t* grid, const SlabGeom& g, int H, int 
     // ---- extract_manifold_surface: two-pass marching cubes, vertices
     RUN(t3d_mc_flags(ws + L.sign, Zp, Hp, Wp, g.z_begin, g.z_end, ws + L.ballots, st));
     RUN(t3d_exclusive_scan_u32(ws + L.ballots, ws + L.chunkbase, n_chunks, 1, 0, 1, R + R_NACTIVE, ws + L.scan1, st));
-    RUN(t3d_mc_words_dev(ws + L.sign, Zp, Hp, Wp, g.z_begin, g.z_end, ws + L.ballots, ws + L.chunkbase, cap_active, R + R_NACTIVE,
-                         ws + L.aw_idx, ws + L.aw_cnt, R + R_NAMBIGUOUS, st));
+    RUN(t3d_mc_words_view_dev(view, x_off, ws + L.sign, Zp, Hp, Wp, g.z_begin, g.z_end, ws + L.ballots, ws + L.chunkbase, cap_active,
+                              R + R_NACTIVE, ws + L.aw_idx, ws + L.aw_cnt, R + R_NAMBIGUOUS, st));
     RUN(t3d_exclusive_scan_u32_dev(ws + L.aw_cnt, ws + L.aw_base, cap_active, cap_active, 4, 0, 0, R + R_NACTIVE, R + R_NX,
                                    ws + L.scan2, st));
     k_finalize_sizes<<<1, 1, 0, st>>>(R, cap_active, cap_verts, cap_faces, bbox_state == 2 ? 1 : 0);
     t3d_count_launches(1);
     // The vertex kernel only needs the keys: the faces are emitted on the side stream at the same time (the two kernels
     // have different bottlenecks: dependent loads vs. float64 issue), then the measures run there as before.
-    RUN(t3d_mc_emit_dev(ws + L.sign, Zp, Hp, Wp, g.z_begin, g.z_end, ws + L.ballots, ws + L.chunkbase, ws + L.aw_idx, ws + L.aw_base,
-                        cap_active, R + R_NACTIVE, cap_verts, cap_faces, ws + L.vkeys, ws + L.faces_raw, 1, st));
+    RUN(t3d_mc_emit_view_dev(view, x_off, ws + L.sign, Zp, Hp, Wp, g.z_begin, g.z_end, ws + L.ballots, ws + L.chunkbase, ws + L.aw_idx,
+                             ws + L.aw_base, cap_active, R + R_NACTIVE, cap_verts, cap_faces, ws + L.vkeys, ws + L.faces_raw, 1, st));
     T3D_CUDA(cudaEventRecord(side->e[4], st));
     T3D_CUDA(cudaStreamWaitEvent(side->s, side->e[4], 0));
-    RUN(t3d_mc_emit_dev(ws + L.sign, Zp, Hp, Wp, g.z_begin, g.z_end, ws + L.ballots, ws + L.chunkbase, ws + L.aw_idx, ws + L.aw_base,
-                        cap_active, R + R_NACTIVE, cap_verts, cap_faces, ws + L.vkeys, ws + L.faces_raw, 2, side->s));
+    RUN(t3d_mc_emit_view_dev(view, x_off, ws + L.sign, Zp, Hp, Wp, g.z_begin, g.z_end, ws + L.ballots, ws + L.chunkbase, ws + L.aw_idx,
+                             ws + L.aw_base, cap_active, R + R_NACTIVE, cap_verts, cap_faces, ws + L.vkeys, ws + L.faces_raw, 2, side->s));
     T3D_CUDA(cudaEventRecord(side->e[6], side->s));
     RUN(t3d_mc_vertices_view_dev(view, x_off, ws + L.vkeys, R + R_NACTIVE, cap_verts, 1, g.z_offset, cum_f64, adj_f64, n_cum, mm_y, mm_x,
                                  scale_in_f64, 7, ws + L.verts_raw, st));

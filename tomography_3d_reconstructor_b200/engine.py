@@ -600,8 +600,15 @@ def extract_surface(dv: DeviceVolume, slice_depths, mm_per_pixel_y, mm_per_pixel
     aw_idx = torch.empty(n_active, dtype=torch.int32, device=dev)
     aw_cnt = torch.empty(4 * n_active, dtype=torch.int32, device=dev)
     n_amb = torch.empty(1, dtype=torch.int64, device=dev)
+    # what Lewiner's face / interior tests evaluate on ambiguous cubes: the dense field, or the Gaussian of the occupancy
+    from ._lib import McField
+    if field is not None:
+        mcf = McField(None, Z, H, W, 0, 0, None, _p(field), float(level))
+    else:
+        mcf = McField(_p(dv.bits), Z, H, W, pad, gaussian, ctypes.cast(_W3_C, ctypes.c_void_p), None, 0.5)
+    mcf_p = ctypes.cast(ctypes.pointer(mcf), ctypes.c_void_p)
     check(L.t3d_mc_words(_p(sign), Zs, Hs, Ws, z_begin, z_end, _p(ballots), _p(chunkbase), n_active, _p(aw_idx), _p(aw_cnt), _p(n_amb),
-                         _stream()), "t3d_mc_words")
+                         mcf_p, _stream()), "t3d_mc_words")
     aw_base, totals = exclusive_scan_u32(aw_cnt, n_active, 4)
     mark("mc_words")
     tail = torch.cat([totals, n_amb, n_exact_t if n_exact_t is not None else torch.zeros_like(n_amb)]).cpu().tolist()
@@ -617,7 +624,7 @@ def extract_surface(dv: DeviceVolume, slice_depths, mm_per_pixel_y, mm_per_pixel
     strong = isinstance(mm_per_pixel_y, np.floating) or isinstance(mm_per_pixel_x, np.floating)
     check(L.t3d_mc_emit(_p(sign), Zs, Hs, Ws, z_begin, z_end, _p(ballots), _p(chunkbase), _p(aw_idx), _p(aw_base), n_active,
                         nX, nY,
-                        _p(vkeys), _p(faces), _stream()), "t3d_mc_emit")
+                        _p(vkeys), _p(faces), mcf_p, _stream()), "t3d_mc_emit")
     mark("mc_emit")
     if field is not None:
         check(L.t3d_mc_vertices_f32(_p(field), Z, H, W, float(level), _p(vkeys), nX, nY, nZ, 0, z_offset, _p(cum_d), _p(adj_d),

@@ -199,13 +199,17 @@ class FusedPlan:
         self.graph, self.graph_ptr = g, masks_u8.data_ptr()
         self.res_np = self.res_host.numpy()
 
-    def run(self, masks_u8: torch.Tensor, use_graph: bool = True):
-        """Returns the host result block (numpy int64 view) after one synchronisation."""
+    def launch(self, masks_u8: torch.Tensor, use_graph: bool = True) -> None:
+        """Enqueue one step on the current stream (graph replay when captured for this input buffer); no synchronisation."""
         if use_graph and self.graph is not None and self.graph_ptr == masks_u8.data_ptr():
             self.graph.replay()
         else:
             self.enqueue(masks_u8)
             self.res_host.copy_(self.res, non_blocking=True)
+
+    def run(self, masks_u8: torch.Tensor, use_graph: bool = True):
+        """Returns the host result block (numpy int64 view) after one synchronisation."""
+        self.launch(masks_u8, use_graph)
         torch.cuda.current_stream().synchronize()
         return self.res_np
 
@@ -282,10 +286,18 @@ def reconstruct_fused(masks_u8: torch.Tensor, threshold: int, side_counts, total
         _plans.pop(key, None)
         _hints.pop(key, None)
         return staged()
+    return _result_from_block(plan, r, h, key)
+
+
+def _result_from_block(plan: "FusedPlan", r: np.ndarray, h: list, hints_key=None) -> Dict:
+    """Result dict of reconstruct() from the host result block of a step that neither overflowed nor failed its order
+    check (plain Python on one .tolist() of the header: this runs between two steps, with the GPU idle)."""
+    Z = plan.shape[0]
     sizes = (h[R_NACTIVE], h[R_VRAW], h[R_NT], h[R_NZ], h[R_NG0])
     if sizes != plan.last_sizes:
         # every later call with a slightly larger mesh still fits thanks to the margin; refresh the hints if it grew
-        _hints[key] = tuple(max(a, b) for a, b in zip(_hints[key], _caps_from(*sizes)))
+        if hints_key is not None and hints_key in _hints:
+            _hints[hints_key] = tuple(max(a, b) for a, b in zip(_hints[hints_key], _caps_from(*sizes)))
         plan.last_sizes = sizes
     canon = (h[R_VCANON], h[R_FCANON])
     if plan.last_mesh is None or plan.last_canon != canon:
