@@ -298,6 +298,13 @@ int t3d_layer_colors(const void* verts_f32, int64_t V, int has_first, double fir
  * "v %.6f %.6f %.6f\n" per vertex, one blank line, "f a b c\n" (1-based) per face -- byte-identical to the reference's
  * loop (the two comment lines and the blank line in front of the body stay with the host). */
 int64_t t3d_obj_workspace_bytes(int64_t V, int64_t F);
+/* glb_exporter.py:26-50 (trimesh's GLB export of Trimesh(vertices, faces, vertex_colors) after fix_normals()): the binary
+ * chunk of a glTF 2.0 file assembled on the device: [uint32 indices (3F) | float32 positions (3V) | uint8 RGBA (4V, only
+ * if rgba_u8)]; flip_winding reverses every face (fix_normals() of a closed mesh whose signed volume is negative);
+ * minmax_f32x6 = per-column minima then maxima of the positions (required on the POSITION accessor). */
+int64_t t3d_glb_payload_bytes(int64_t V, int64_t F, int with_colors);
+int t3d_glb_pack(const void* verts_f32, int64_t V, const void* faces, int64_t F, int faces_are_i64, const void* rgba_u8,
+                 int flip_winding, void* bin_out, void* minmax_f32x6, void* stream);
 int t3d_obj_measure(const void* verts_f32, int64_t V, const void* faces, int64_t F, int faces_are_i64, void* total_len_u64,
                     void* workspace, void* stream);
 int t3d_obj_emit(const void* verts_f32, int64_t V, const void* faces, int64_t F, int faces_are_i64, const void* total_len_u64,

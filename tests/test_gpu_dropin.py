@@ -147,3 +147,90 @@ def test_config0_real_generator_stack_through_the_classes(eng, oracle):
     assert np.array_equal(v, ref["vertices"]) and np.array_equal(f, ref["faces"])
     assert abs(mv - ref["mesh_volume"]) <= 1e-6 * ref["mesh_volume"]
     assert se.last_n_ambiguous == ref["n_ambiguous"]
+
+
+def _loader_like_masks(oracle, Z, H, W, hole=True):
+    """What ImageLoader.load_mask_images returns (image_loader.py:97-109): a list of separately allocated pageable bool arrays."""
+    u8 = oracle.ellipsoid_phantom_u8(Z, H, W)
+    if hole:
+        u8[0, H // 2 - 3:H // 2 + 3, W // 2 - 5:W // 2 + 5] = 0
+    masks = [np.array(u8[z] >= 200) for z in range(Z)]
+    assert all(m.flags.owndata for m in masks)
+    return u8, masks
+
+
+def test_image_loader_style_list_goes_through_the_pinned_ring(eng, oracle):
+    """scattered pageable masks are gathered chunk-wise through pinned staging buffers (no np.stack), in both
+    the class API and the one-call host entry, with chunk sizes that do and do not divide Z."""
+    from tomography_3d_reconstructor_b200 import VoxelProcessor, engine, pipeline
+    Z, H, W = 45, 96, 130
+    sides = (5, 35, 5)
+    u8, masks = _loader_like_masks(oracle, Z, H, W)
+    src, z, h, w, pinned = engine.mask_source(masks)
+    assert src is masks and (z, h, w) == (Z, H, W) and not pinned
+    ref = oracle.reference_pipeline(u8, 200, sides, 6.0, 143.1, 95.03)
+    for chunk in (32, 7, 64):
+        dv, host = engine.create_voxel_data_from_host(masks, 1, True, chunk_planes=chunk)
+        assert host.dtype == np.bool_ and np.array_equal(host, ref["voxel_data"])
+    with contextlib.redirect_stdout(io.StringIO()):
+        vox = VoxelProcessor().create_voxel_data(masks, True, *sides)
+    assert np.array_equal(vox, ref["voxel_data"])
+    for _ in range(3):
+        out = pipeline.reconstruct_host(masks, 1, sides, 6.0, 143.1, 95.03)
+        assert np.array_equal(out["vertices"], ref["vertices"]) and np.array_equal(out["faces"], ref["faces"])
+        assert out["voxel_volume_mm3"] == ref["voxel_volume"]
+    # uint8 grey-level masks thresholded on the device, as a scattered list too
+    grey = [np.array(u8[k]) for k in range(Z)]
+    out = pipeline.reconstruct_host(grey, 200, sides, 6.0, 143.1, 95.03)
+    assert np.array_equal(out["vertices"], ref["vertices"]) and np.array_equal(out["faces"], ref["faces"])
+
+
+def test_create_voxel_data_from_u8(eng, oracle):
+    """Additive fast path: grayscale stack thresholded on the device (image_loader.py:108 + voxel_processor.py:36-54)."""
+    import torch
+    from tomography_3d_reconstructor_b200 import VoxelProcessor, VolumeCalculator
+    Z, H, W = 20, 70, 100
+    rng = np.random.default_rng(4)
+    grey = (oracle.ellipsoid_phantom_u8(Z, H, W) // 255 * 180 + rng.integers(0, 76, (Z, H, W))).astype(np.uint8)   # straddles 200
+    grey[0, 30:36, 40:52] = 0
+    masks = [grey[z] >= 200 for z in range(Z)]
+    ref = oracle.create_voxel_data(masks, True)
+    raw = oracle.create_voxel_data(masks, False)
+    with contextlib.redirect_stdout(io.StringIO()) as out:
+        vp = VoxelProcessor()
+        a = vp.create_voxel_data_from_u8(grey, 200, True, 2, 16, 2)
+        b = VoxelProcessor().create_voxel_data_from_u8(torch.from_numpy(grey).cuda(), 200, False)
+    assert a.dtype == np.bool_ and np.array_equal(a, ref) and np.array_equal(b, raw)
+    assert (vp.side_0_count, vp.side_1_count, vp.side_2_count) == (2, 16, 2) and vp.voxel_data is a
+    assert "Voxels: (20, 70, 100), active: %s" % format(int(ref.sum()), ",") in out.getvalue()
+    depths = vp.calculate_slice_depths(6.0)
+    vol = VolumeCalculator().calculate_voxel_volume_variable_depth(a, 0.3, 0.2, depths)
+    assert vol == oracle.calculate_voxel_volume_variable_depth(ref, 0.3, 0.2, depths)
+    with pytest.raises(ValueError):
+        VoxelProcessor().create_voxel_data_from_u8(np.zeros((0, 4, 4), np.uint8))
+
+
+def test_writable_outputs_flag(eng, oracle):
+    """Default: returned arrays are read-only mirrors of cached device objects.  engine.WRITABLE_OUTPUTS: ordinary writable
+    arrays like the reference's; later calls see what the caller wrote into them."""
+    from tomography_3d_reconstructor_b200 import VoxelProcessor, SurfaceExtractor, engine
+    Z, H, W = 16, 48, 64
+    u8, masks = _loader_like_masks(oracle, Z, H, W, hole=False)
+    depths = np.full(Z, 0.4)
+    with contextlib.redirect_stdout(io.StringIO()):
+        vox = VoxelProcessor().create_voxel_data(masks, True, 0, Z, 0)
+        with pytest.raises(ValueError):
+            vox[0, 0, 0] = True
+        engine.WRITABLE_OUTPUTS = True
+        try:
+            vp, se = VoxelProcessor(), SurfaceExtractor()
+            vox = vp.create_voxel_data(masks, True, 0, Z, 0)
+            sm = vp.smooth_voxel_data(vox, 3, True)
+            v, f = se.extract_manifold_surface(sm, depths, 0.3, 0.25)
+            vol0 = se.calculate_mesh_volume(v, f)
+            v[:, 0] *= 2.0                                     # the caller edits the mesh in place ...
+            assert abs(se.calculate_mesh_volume(v, f) / vol0 - 2.0) < 1e-5      # ... and the next call sees the edit
+            sm[:] = False                                      # the caller empties the volume: extraction fails -> None
+            assert se.extract_manifold_surface(sm, depths, 0.3, 0.25) is None
+        finally:
+            engine.WRITABLE_OUTPUTS = False

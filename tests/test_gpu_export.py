@@ -100,3 +100,37 @@ def test_exporters_through_dropin_modules_use_the_device_mesh(eng, oracle, tmp_p
         sys.path.remove(shim)
         for m in ("obj_exporter", "glb_exporter", "surface_extractor", "voxel_processor"):
             sys.modules.pop(m, None)
+
+
+def test_glb_writer_reparses_to_the_mesh(eng, oracle, tmp_path):
+    """glb_exporter.py:26-50 without trimesh: the binary glTF file written from the device mesh re-parses to exactly the
+    vertices, faces (wound outwards, as trimesh's fix_normals() leaves them) and colours it was given."""
+    import json
+    from tomography_3d_reconstructor_b200 import SurfaceExtractor
+    from tomography_3d_reconstructor_b200.glb_exporter import GLBExporter, parse_glb
+    vol = oracle.smooth_voxel_data(oracle.ellipsoid_phantom_u8(24, 56, 72) >= 200, 3, True)
+    depths = oracle.calculate_slice_depths(6.0, 3, 18, 3)
+    se, ex = SurfaceExtractor(), GLBExporter()
+    v, f = se.extract_manifold_surface(vol, depths, 0.3, 0.25, True, True, True)
+    colors = ex.create_layer_colors(v, depths, 3, 20, 1.0)
+    path = str(tmp_path / "model.glb")
+    assert ex.export_to_glb(v, f, path, colors) is True
+    data = open(path, "rb").read()
+    pos, idx, col, doc = parse_glb(data)
+    assert np.array_equal(pos.view(np.uint32), v.view(np.uint32)) and np.array_equal(col, colors)
+    # winding: outward (positive signed volume in the file's own coordinates), every face the same triangle as given
+    p64 = pos.astype(np.float64)
+    a, b, c = p64[idx[:, 0]], p64[idx[:, 1]], p64[idx[:, 2]]
+    assert np.einsum("ij,ij->i", a, np.cross(b, c)).sum() > 0
+    same = np.array_equal(idx.astype(np.int64), f)
+    flipped = np.array_equal(idx.astype(np.int64), f[:, [0, 2, 1]])
+    assert same or flipped
+    acc = doc["accessors"][doc["meshes"][0]["primitives"][0]["attributes"]["POSITION"]]
+    assert np.array_equal(np.float32(acc["min"]), v.min(axis=0)) and np.array_equal(np.float32(acc["max"]), v.max(axis=0))
+    assert doc["asset"]["version"] == "2.0" and len(data) % 4 == 0
+    # host arrays that did not come from this package (fresh copies, int32 faces) and no colours
+    assert ex.export_to_glb(v.copy(), f.astype(np.int32), path, None) is True
+    pos2, idx2, col2, _ = parse_glb(open(path, "rb").read())
+    assert col2 is None and np.array_equal(pos2, v) and np.array_equal(idx2, idx)
+    # failures keep the reference's convention: message + False
+    assert ex.export_to_glb(v[:0], f[:0], path, None) is False

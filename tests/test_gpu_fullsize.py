@@ -85,7 +85,7 @@ def test_config1_full_size_against_oracle_slabs_and_invariants(eng, oracle):
         t = np.array([[float(k), 0.0, 0.0]], dtype=np.float32)
         oracle.apply_variable_slice_depths(t, depths, True)
         return t[0, 0]
-    for za in (28, Z // 2 - 3, Z - 40):              # near the lower pole, the equator, near the upper pole
+    for za in (44, Z // 2 - 3, Z - 50):              # the lower polar cap (the object spans planes 41..470), the equator, the upper cap
         zb = za + n
         a, b = za - halo, zb + halo
         u8 = oracle.ellipsoid_phantom_u8(Z, H, W, a, b)

@@ -83,6 +83,8 @@ SIGNATURES = {
     "t3d_mc_vertices_f32": (_i, [_vp, _i, _i, _i, _dbl, _vp, _u32, _u32, _u32, _i, _i, _vp, _vp, _i, _dbl, _dbl, _i, _vp, _vp]),
     "t3d_layer_colors": (_i, [_vp, _i64, _i, _dbl, _dbl, _i, _dbl, _dbl, _vp, _vp]),
     "t3d_obj_workspace_bytes": (_i64, [_i64, _i64]),
+    "t3d_glb_payload_bytes": (_i64, [_i64, _i64, _i]),
+    "t3d_glb_pack": (_i, [_vp, _i64, _vp, _i64, _i, _vp, _i, _vp, _vp, _vp]),
     "t3d_obj_measure": (_i, [_vp, _i64, _vp, _i64, _i, _vp, _vp, _vp]),
     "t3d_obj_emit": (_i, [_vp, _i64, _vp, _i64, _i, _vp, _vp, _vp, _vp]),
     "t3d_vertex_normals": (_i, [_vp, _i64, _vp, _i64, _i, _vp, _vp]),

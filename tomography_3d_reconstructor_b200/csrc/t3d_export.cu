@@ -201,3 +201,96 @@ extern "C" int t3d_obj_emit(const void* verts_f32, int64_t V, const void* faces,
     t3d_count_launches(2);
     return 0;
 }
+
+// ------------------------------------------------------------------------------------------------
+// GLB (binary glTF 2.0) payload: what trimesh's exporter writes for Trimesh(vertices, faces, vertex_colors) after
+// fix_normals() (glb_exporter.py:36-43) -- one buffer = [uint32 indices | float32 positions | uint8 RGBA colours], plus the
+// per-axis minima / maxima glTF requires on the POSITION accessor.  fix_normals() on a closed, consistently wound mesh
+// amounts to reversing every face when the enclosed (signed) volume is negative: `flip`.
+// ------------------------------------------------------------------------------------------------
+template <typename IdxT>
+__global__ void __launch_bounds__(256) k_glb_pack(const float* __restrict__ verts, int64_t V, const IdxT* __restrict__ faces, int64_t F,
+                                                  const uchar4* __restrict__ rgba, int flip, uint32_t* __restrict__ idx_out,
+                                                  float* __restrict__ pos_out, uchar4* __restrict__ col_out,
+                                                  unsigned int* __restrict__ minmax /* 3 x min, 3 x max as ordered uints */)
+{
+    const int64_t n_idx = 3 * F, n_pos = 3 * V;
+    float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_idx + V; i += (int64_t)gridDim.x * blockDim.x) {
+        if (i < n_idx) {
+            const int64_t f = i / 3;
+            int c = (int)(i - 3 * f);
+            if (flip && c) c = 3 - c;          // (a, b, c) -> (a, c, b)
+            idx_out[i] = (uint32_t)faces[3 * f + c];
+        } else {
+            const int64_t v = i - n_idx;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const float x = verts[3 * v + k];
+                pos_out[3 * v + k] = x;
+                lo[k] = fminf(lo[k], x);
+                hi[k] = fmaxf(hi[k], x);
+            }
+            if (rgba) col_out[v] = rgba[v];
+        }
+    }
+    (void)n_pos;
+    // order-preserving float -> uint map, warp tree, one atomic per warp and axis
+    auto enc = [](float x) -> unsigned int { const unsigned int u = __float_as_uint(x); return (u & 0x80000000u) ? ~u : (u | 0x80000000u); };
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        unsigned int a = enc(lo[k]), b = enc(hi[k]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            a = min(a, __shfl_xor_sync(0xffffffffu, a, o));
+            b = max(b, __shfl_xor_sync(0xffffffffu, b, o));
+        }
+        if ((threadIdx.x & 31) == 0) {
+            atomicMin(&minmax[k], a);
+            atomicMax(&minmax[3 + k], b);
+        }
+    }
+}
+
+__global__ void k_glb_minmax_init(unsigned int* m)
+{
+    if (threadIdx.x < 3) m[threadIdx.x] = 0xffffffffu;
+    else if (threadIdx.x < 6) m[threadIdx.x] = 0u;
+}
+
+__global__ void k_glb_minmax_decode(unsigned int* m)
+{
+    if (threadIdx.x < 6) {
+        const unsigned int u = m[threadIdx.x];
+        m[threadIdx.x] = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
+    }
+}
+
+extern "C" int64_t t3d_glb_payload_bytes(int64_t V, int64_t F, int with_colors) { return 12 * F + 12 * V + (with_colors ? 4 * V : 0); }
+
+// bin_out: t3d_glb_payload_bytes bytes; minmax_f32x6: {min x3, max x3} of the vertex columns (device, float32)
+extern "C" int t3d_glb_pack(const void* verts_f32, int64_t V, const void* faces, int64_t F, int faces_are_i64, const void* rgba_u8,
+                            int flip_winding, void* bin_out, void* minmax_f32x6, void* stream)
+{
+    if (V <= 0 || F <= 0 || V > 0xffffffffll) { t3d_set_error("t3d_glb_pack: bad sizes"); return 2; }
+    cudaStream_t st = (cudaStream_t)stream;
+    char* out = (char*)bin_out;
+    uint32_t* idx_out = (uint32_t*)out;
+    float* pos_out = (float*)(out + 12 * F);
+    uchar4* col_out = (uchar4*)(out + 12 * F + 12 * V);
+    unsigned int* mm = (unsigned int*)minmax_f32x6;
+    k_glb_minmax_init<<<1, 32, 0, st>>>(mm);
+    const int64_t items = 3 * F + V;
+    int64_t blocks = (items + 255) / 256;
+    if (blocks > (int64_t)T3D_NUM_SMS * 16) blocks = (int64_t)T3D_NUM_SMS * 16;
+    if (faces_are_i64)
+        k_glb_pack<long long><<<(unsigned)blocks, 256, 0, st>>>((const float*)verts_f32, V, (const long long*)faces, F, (const uchar4*)rgba_u8,
+                                                                flip_winding, idx_out, pos_out, col_out, mm);
+    else
+        k_glb_pack<int><<<(unsigned)blocks, 256, 0, st>>>((const float*)verts_f32, V, (const int*)faces, F, (const uchar4*)rgba_u8,
+                                                          flip_winding, idx_out, pos_out, col_out, mm);
+    k_glb_minmax_decode<<<1, 32, 0, st>>>(mm);
+    T3D_CHECK_LAUNCH("t3d_glb_pack");
+    t3d_count_launches(3);
+    return 0;
+}

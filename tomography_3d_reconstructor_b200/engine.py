@@ -222,6 +222,22 @@ class _Registry:
 volumes = _Registry()
 meshes = _Registry()
 
+# Host arrays handed to the caller mirror a device object that later calls recognise by array identity (smooth -> extract
+# -> volume never re-uploads).  That only holds while the array cannot change, so by default it is read-only; the
+# reference returns ordinary writable arrays.  T3D_WRITABLE_OUTPUTS=1 (or engine.WRITABLE_OUTPUTS = True) hands out
+# writable arrays instead and does not register them: every later call uploads what the array then contains.
+import os as _os
+WRITABLE_OUTPUTS = bool(_os.environ.get("T3D_WRITABLE_OUTPUTS"))
+
+
+def publish(registry: "_Registry", arr: np.ndarray, obj) -> np.ndarray:
+    if WRITABLE_OUTPUTS:
+        arr.setflags(write=True)
+        return arr
+    arr.setflags(write=False)
+    registry.register(arr, obj)
+    return arr
+
 
 # ----------------------------------------------------------------------------------------------------------
 # host -> device
@@ -318,6 +334,133 @@ def pack_and_close(masks_u8_dev: torch.Tensor, threshold: int = 1, close_ends: b
 
 
 _copy_streams = {}
+_stage_pool = None
+
+
+def _pool():
+    global _stage_pool
+    if _stage_pool is None:
+        from concurrent.futures import ThreadPoolExecutor
+        _stage_pool = ThreadPoolExecutor(max_workers=min(8, (_os.cpu_count() or 2)))
+    return _stage_pool
+
+
+class PinnedRing:
+    """Staging ring for mask lists as ImageLoader returns them (image_loader.py:97-109): Z separately allocated, pageable
+    (H,W) bool / uint8 arrays.  A chunk of slices is copied into one of `slots` pinned buffers by a few host threads
+    (numpy copies release the GIL) while the previous chunk's buffer is on its way to the device: the H2D copies run at
+    PCIe speed from pinned memory and overlap the host-side gathering, and no (Z,H,W) host copy (np.stack) is made."""
+
+    def __init__(self, H: int, W: int, chunk_planes: int, slots: int = 3):
+        self.H, self.W, self.chunk = H, W, chunk_planes
+        self.bufs = [torch.empty((chunk_planes, H, W), dtype=torch.uint8, pin_memory=True) for _ in range(slots)]
+        self.views = [b.numpy() for b in self.bufs]
+        self.events = [None] * slots
+        self.k = 0
+
+    def stage(self, source, a: int, b: int) -> torch.Tensor:
+        """Slices [a, b) of `source` (list of arrays or a (Z,H,W) array) -> a pinned (b-a,H,W) uint8 tensor.  The caller
+        records an event after its H2D copy with release()."""
+        slot = self.k % len(self.bufs)
+        self.k += 1
+        if self.events[slot] is not None:
+            self.events[slot].synchronize()        # the copy that last read this buffer has finished
+        dst = self.views[slot]
+
+        def one(z):
+            m = np.asarray(source[z])
+            if m.dtype == np.bool_:
+                m = m.view(np.uint8)
+            elif m.dtype != np.uint8:
+                m = (m != 0).view(np.uint8)
+            np.copyto(dst[z - a], m)
+
+        n = b - a
+        if n >= 4:
+            list(_pool().map(one, range(a, b)))
+        else:
+            for z in range(a, b):
+                one(z)
+        self._slot = slot
+        return self.bufs[slot][:n]
+
+    def release(self, stream) -> None:
+        ev = torch.cuda.Event()
+        ev.record(stream)
+        self.events[self._slot] = ev
+
+
+_rings = {}
+
+
+def _ring_for(H: int, W: int, chunk_planes: int) -> PinnedRing:
+    key = (H, W, chunk_planes)
+    r = _rings.get(key)
+    if r is None:
+        _rings.clear()                 # one shape at a time: pinned memory is a scarce resource
+        r = _rings[key] = PinnedRing(H, W, chunk_planes)
+    return r
+
+
+def _is_pinned_stack(x) -> bool:
+    if isinstance(x, torch.Tensor):
+        return x.is_pinned()
+    if isinstance(x, np.ndarray) and x.ndim == 3 and x.flags.c_contiguous and x.dtype.itemsize == 1:
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore", UserWarning)
+            return torch.from_numpy(x.view(np.uint8)).is_pinned()
+    return False
+
+
+def mask_source(mask_images):
+    """(source, Z, H, W, pinned): `source[z]` is slice z; pinned = one contiguous pinned (Z,H,W) byte array (no staging)."""
+    if isinstance(mask_images, (np.ndarray, torch.Tensor)):
+        if mask_images.ndim != 3:
+            raise ValueError("expected a (Z,H,W) stack")
+        Z, H, W = (int(v) for v in mask_images.shape)
+        return mask_images, Z, H, W, _is_pinned_stack(mask_images)
+    # a list whose slices already lie back to back in memory is one array (e.g. views of a pinned stack)
+    first = np.asarray(mask_images[0])
+    if first.ndim != 2:
+        raise ValueError("expected a list of (H,W) masks")
+    n = len(mask_images)
+    if first.flags.c_contiguous and first.dtype.itemsize == 1:
+        step, base = first.nbytes, first.__array_interface__["data"][0]
+        if all(isinstance(m, np.ndarray) and m.shape == first.shape and m.dtype == first.dtype and m.flags.c_contiguous
+               and m.__array_interface__["data"][0] == base + k * step for k, m in enumerate(mask_images)):
+            arr = _as_stack(mask_images)
+            return arr, n, int(first.shape[0]), int(first.shape[1]), _is_pinned_stack(arr)
+    return mask_images, n, int(first.shape[0]), int(first.shape[1]), False
+
+
+def upload_masks(mask_images, out: Optional[torch.Tensor] = None, chunk_planes: int = 32) -> torch.Tensor:
+    """Host masks (list or stack) -> uint8 (Z,H,W) on the device, enqueued on the current stream's timeline.  Pinned
+    contiguous input: one async copy.  Anything else goes through the pinned staging ring in z-chunks."""
+    dev = _require_cuda()
+    src, Z, H, W, pinned = mask_source(mask_images)
+    if out is None:
+        out = torch.empty((Z, H, W), dtype=torch.uint8, device=dev)
+    if pinned:
+        t = src if isinstance(src, torch.Tensor) else torch.from_numpy(src.view(np.uint8))
+        out.copy_(t.view(torch.uint8) if t.dtype != torch.uint8 else t, non_blocking=True)
+        return out
+    ring = _ring_for(H, W, chunk_planes)
+    main = torch.cuda.current_stream()
+    s_in, _ = _copy_stream_pair(dev)
+    start = torch.cuda.Event()
+    start.record(main)
+    s_in.wait_event(start)
+    for a in range(0, Z, chunk_planes):
+        b = min(Z, a + chunk_planes)
+        buf = ring.stage(src, a, b)
+        with torch.cuda.stream(s_in):
+            out[a:b].copy_(buf, non_blocking=True)
+            ring.release(s_in)
+    done = torch.cuda.Event()
+    done.record(s_in)
+    main.wait_event(done)
+    return out
 
 
 def _copy_stream_pair(dev: torch.device):
@@ -329,8 +472,8 @@ def _copy_stream_pair(dev: torch.device):
     return st
 
 
-def create_voxel_data_from_host(stack_u8: np.ndarray, threshold: int = 1, close_ends: bool = True, chunk_planes: int = 32):
-    """create_voxel_data (voxel_processor.py:36-54) for a host stack, pipelined in z-chunks so that the upload of the
+def create_voxel_data_from_host(stack_u8, threshold: int = 1, close_ends: bool = True, chunk_planes: int = 32):
+    """create_voxel_data (voxel_processor.py:36-54) for a host stack or list of masks, pipelined in z-chunks so that the upload of the
     masks (H2D), the kernels and the download of the resulting bool grid (D2H) overlap: PCIe is full duplex and the
     two directions use different copy engines.  Returns (DeviceVolume, numpy bool array in pinned memory).
 
@@ -339,9 +482,13 @@ def create_voxel_data_from_host(stack_u8: np.ndarray, threshold: int = 1, close_
     reads them, so the result is identical to the unpipelined path."""
     L = _L()
     dev = _require_cuda()
-    Z, H, W = (int(v) for v in stack_u8.shape)
+    source, Z, H, W, pinned = mask_source(stack_u8)
     wpr = words_per_row(W)
-    src = torch.from_numpy(np.ascontiguousarray(stack_u8)) if not isinstance(stack_u8, torch.Tensor) else stack_u8
+    if pinned:
+        src = source if isinstance(source, torch.Tensor) else torch.from_numpy(source.view(np.uint8))
+        ring = None
+    else:           # pageable and / or scattered slices (what ImageLoader returns): pinned staging ring, no np.stack
+        src, ring = None, _ring_for(H, W, chunk_planes)
     masks_dev = torch.empty((Z, H, W), dtype=torch.uint8, device=dev)
     bits = torch.empty((Z, H, wpr), dtype=torch.int32, device=dev)
     out_bits = torch.empty_like(bits)
@@ -373,10 +520,13 @@ def create_voxel_data_from_host(stack_u8: np.ndarray, threshold: int = 1, close_
             host_u8[a:b].copy_(out_u8[a:b], non_blocking=True)
 
     for c, (a, b) in enumerate(bounds):
+        chunk = src[a:b] if ring is None else ring.stage(source, a, b)
         with torch.cuda.stream(s_in):
-            masks_dev[a:b].copy_(src[a:b], non_blocking=True)
+            masks_dev[a:b].copy_(chunk, non_blocking=True)
             up = torch.cuda.Event()
             up.record(s_in)
+            if ring is not None:
+                ring.release(s_in)
         main.wait_event(up)
         dst = bits if close_ends else out_bits
         check(L.t3d_pack_masks(_p(masks_dev[a]), b - a, H, W, int(threshold), _p(dst[a]), _stream()), "t3d_pack_masks")

@@ -334,16 +334,14 @@ def reconstruct_host(mask_images, threshold: int, side_counts, total_depth_mm: f
     image_loader.py:97-109) or a (Z,H,W) array -> one host->device copy -> reconstruct_fused -> the mesh as numpy arrays
     (out["vertices"] f32 (V,3) [z,y,x] mm, out["faces"] int64 (F,3)) + the scalars of reconstruct().  bool masks:
     pass threshold=1.  The intermediate voxel grids stay on the device (the class API has to return them as arrays)."""
-    a = engine._as_stack(mask_images)
+    _src, Z, H, W, _pinned = engine.mask_source(mask_images)
     dev = engine._require_cuda()
-    key = (a.shape, torch.cuda.current_device())
+    key = ((Z, H, W), torch.cuda.current_device())
     buf = _device_inputs.get(key)
     if buf is None:                                  # persistent input buffer: keeps the captured graph valid
-        buf = _device_inputs[key] = torch.empty(a.shape, dtype=torch.uint8, device=dev)
-    import warnings
-    with warnings.catch_warnings():
-        warnings.simplefilter("ignore", UserWarning)
-        buf.copy_(torch.from_numpy(np.ascontiguousarray(a)), non_blocking=True)
+        buf = _device_inputs[key] = torch.empty((Z, H, W), dtype=torch.uint8, device=dev)
+    # one async copy from a pinned stack; a list of pageable masks is gathered through the pinned staging ring
+    engine.upload_masks(mask_images, buf)
     out = reconstruct_fused(buf, threshold, side_counts, total_depth_mm, x_length_mm, y_length_mm, iterations, close_ends,
                             add_padding, use_graph)
     v, f = out["mesh"].verts.contiguous(), out["mesh"].faces.contiguous()

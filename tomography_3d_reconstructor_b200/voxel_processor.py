@@ -5,7 +5,8 @@ names/order, defaults, prints and error behaviour follow the reference; see INTE
 
 Differences a caller can observe:
   * returned voxel arrays are real `np.ndarray[bool]` but read-only (the device copy they mirror is cached by
-    array identity so smooth -> extract -> volume never re-uploads);
+    array identity so smooth -> extract -> volume never re-uploads); T3D_WRITABLE_OUTPUTS=1 returns writable,
+    unregistered arrays instead (every later call then uploads the array's current content);
   * with scikit-image absent the reference degrades to an identity smooth (voxel_processor.py:81-82); this
     class always applies the skimage semantics (6-connected opening, then closing).
 """
@@ -27,10 +28,7 @@ class VoxelProcessor:
 
     # ------------------------------------------------------------------------------------------------
     def _publish(self, dv: engine.DeviceVolume) -> np.ndarray:
-        host = dv.to_host()
-        host.setflags(write=False)
-        engine.volumes.register(host, dv)
-        return host
+        return engine.publish(engine.volumes, dv.to_host(), dv)
 
     def create_voxel_data(self, mask_images: list, close_ends: bool = True,
                           side_0_count: int = 0, side_1_count: int = 0, side_2_count: int = 0) -> np.ndarray:
@@ -43,9 +41,9 @@ class VoxelProcessor:
         self.side_2_count = side_2_count
 
         # upload, pack/close and download pipelined in z-chunks (H2D and D2H overlap)
-        dv, host = engine.create_voxel_data_from_host(engine._as_stack(mask_images), 1, close_ends)
-        host.setflags(write=False)
-        engine.volumes.register(host, dv)
+        # (a list of separately allocated pageable masks -- what ImageLoader returns -- is gathered through a pinned ring)
+        dv, host = engine.create_voxel_data_from_host(mask_images, 1, close_ends)
+        engine.publish(engine.volumes, host, dv)
         active = int(dv.slice_counts().sum())
         self.voxel_data = host
         print(f"Voxels: {self.voxel_data.shape}, active: {active:,}")
