@@ -274,6 +274,25 @@ int t3d_edt_z(const void* dy_i16, const void* dx_i16, int Z, int H, int W, const
 int t3d_edt(const void* occ_bits, int Z, int H, int W, int invert, const double* sampling_host, float sign, int accumulate,
             void* dist_f32, void* workspace, void* stream);
 
+/* Half-ellipsoid end-cap slices (ellipsoid_slice_generator.py:61-77): out_u8 (n,H,W), slice k = cv2.warpAffine(base, M_k,
+ * INTER_LINEAR, constant border 0) in OpenCV's own fixed-point arithmetic (bit-identical; csrc/t3d_generator.cu);
+ * inv_matrices_f64 = 6 float64 per slice (device), already inverted the way cv::warpAffine inverts its argument; an all-zero
+ * matrix gives an all-zero slice. */
+int t3d_endcap_slices(const void* base_u8, int H, int W, const void* inv_matrices_f64, int n, void* out_u8, void* stream);
+
+/* Signed distance in one sweep per axis (csrc/t3d_edt.cu): sdf_f32 (Z,H,W) = edt(occ) - edt(~occ) -- +distance to the nearest
+ * unset voxel at set voxels, -distance to the nearest set voxel at unset ones (scipy's arithmetic, bit-equal at unit sampling),
+ * +-inf if only one kind exists.  t3d_sdf_xy / t3d_sdf_z are its two halves for z-slab sharding: dyx_i16 = two (Z,H,W) int16
+ * arrays, [0] = (y offset << 1) | occupancy bit, [1] = x offset of the nearest opposite-kind voxel in the voxel's own plane;
+ * the z pass runs on full columns (after the all-to-all transpose).  Extents up to 16382 per axis. */
+int64_t t3d_sdf_xy_workspace_bytes(int Z, int H, int W);
+int t3d_sdf_xy(const void* occ_bits, int Z, int H, int W, const double* sampling_host, void* dyx_i16, void* workspace, void* stream);
+int64_t t3d_sdf_z_workspace_bytes(int Z, int H, int W);
+int t3d_sdf_z(const void* dy_i16, const void* dx_i16, int Z, int H, int W, const double* sampling_host, void* sdf_f32, void* workspace,
+              void* stream);
+int64_t t3d_sdf_workspace_bytes(int Z, int H, int W);
+int t3d_sdf(const void* occ_bits, int Z, int H, int W, const double* sampling_host, void* sdf_f32, void* workspace, void* stream);
+
 /* Marching a dense float32 field directly (e.g. the SDF): sign bits = (field > level) packed like an occupancy volume,
  * then t3d_mc_flags/words/emit on them, and vertices interpolated on the field itself. */
 int t3d_sign_from_f32(const void* field_f32, int Z, int H, int W, double level, void* sign_bits, void* stream);

@@ -110,12 +110,49 @@ def test_sharded_edt_matches_single_device(eng, shape, sampling, world):
     ref = edt.signed_distance(dv, sampling).cpu().numpy()
     ranges = [sharded.slab_range(Z, r, world) for r in range(world)]
     ts = [edt.SlabTransform(dv.bits[a:b].contiguous(), Z, a, H, W, sampling, r, world) for r, (a, b) in enumerate(ranges)]
-    for k, invert in enumerate((0, 1)):
-        sends = [t.xy_pass(invert) for t in ts]
-        for c in range(2):
-            _emulated_all_to_all([s[c] for s in sends], [t.send_sizes for t in ts], [t.cols[c] for t in ts], [t.recv_sizes for t in ts])
-        for t in ts:
-            t.z_pass(invert, k)
+    sends = [t.sdf_xy_pass() for t in ts]             # both polarities in one sweep: one offset pair per voxel is exchanged
+    for c in range(2):
+        _emulated_all_to_all([s[c] for s in sends], [t.send_sizes for t in ts], [t.cols[c] for t in ts], [t.recv_sizes for t in ts])
+    for t in ts:
+        t.sdf_z_pass()
     _emulated_all_to_all([t.dist_cols for t in ts], [t.recv_sizes for t in ts], [t.back for t in ts], [t.send_sizes for t in ts])
     out = torch.cat([t.result() for t in ts]).cpu().numpy()
     assert np.array_equal(out.view(np.uint32), ref.view(np.uint32))
+    # the one-sided transform (edt(occ) only) still goes through the two-component exchange of t3d_edt_xy / t3d_edt_z
+    ts = [edt.SlabTransform(dv.bits[a:b].contiguous(), Z, a, H, W, sampling, r, world) for r, (a, b) in enumerate(ranges)]
+    sends = [t.xy_pass(0) for t in ts]
+    for c in range(2):
+        _emulated_all_to_all([s[c] for s in sends], [t.send_sizes for t in ts], [t.cols[c] for t in ts], [t.recv_sizes for t in ts])
+    for t in ts:
+        t.z_pass(0, 0)
+    _emulated_all_to_all([t.dist_cols for t in ts], [t.recv_sizes for t in ts], [t.back for t in ts], [t.send_sizes for t in ts])
+    one_sided = torch.cat([t.result() for t in ts]).cpu().numpy()
+    assert np.array_equal(one_sided, edt.distance(dv, sampling).cpu().numpy())
+
+
+@pytest.mark.parametrize("shape", [(1, 1, 1), (2, 3, 4), (9, 17, 33), (12, 40, 70), (20, 33, 130), (5, 6, 1100), (40, 8, 9)])
+@pytest.mark.parametrize("sampling", [(1.0, 1.0, 1.0), (0.09375, 0.31, 0.28)])
+@pytest.mark.parametrize("kind", ["blobs", "noise", "sparse"])
+def test_one_sweep_sdf_matches_scipy_and_the_two_transforms(eng, oracle, shape, sampling, kind):
+    """t3d_sdf (both polarities in one sweep per axis, run-end zero-cost sites, float32-estimated take-over positions with an
+    exact float64 check) against scipy's distance_transform_edt and against the two one-sided transforms."""
+    from tomography_3d_reconstructor_b200 import edt
+    rng = np.random.default_rng(sum(shape) + len(kind))
+    if kind == "blobs":
+        vol = random_blobs(rng, shape, 0.45, 1.5) if min(shape) > 1 else rng.random(shape) < 0.5
+    elif kind == "noise":
+        vol = rng.random(shape) < 0.5
+    else:
+        vol = rng.random(shape) < 0.02
+    dv = dev_volume(eng, vol)
+    got = edt.signed_distance(dv, sampling).cpu().numpy()
+    two = edt.signed_distance_two_transforms(dv, sampling).cpu().numpy()
+    ref = oracle.signed_distance(vol, sampling)
+    if sampling == (1.0, 1.0, 1.0):
+        assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))       # squared distances are exact integers
+        assert np.array_equal(got.view(np.uint32), two.view(np.uint32))
+    else:
+        fin = np.isfinite(ref)
+        assert np.array_equal(np.isfinite(got), fin)
+        assert np.allclose(got[fin], ref[fin], rtol=1e-6, atol=0) and np.allclose(got[fin], two[fin], rtol=1e-6, atol=0)
+        assert np.array_equal(got[~fin], ref[~fin])

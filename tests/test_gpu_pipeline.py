@@ -230,12 +230,11 @@ def test_sharded_sdf_pipeline_stitches_to_the_single_gpu_mesh(eng, oracle, world
             s.ext[s.hl + s.n:] = hi.ext[hi.hl:hi.hl + s.hh]
     sms = [sharded.sdf_slab_smooth(s) for s in slabs]
     ts = [edt.SlabTransform(sm.bits, Z, a, H, W, samp, r, world) for r, (sm, (a, b)) in enumerate(zip(sms, ranges))]
-    for k, invert in enumerate((0, 1)):
-        sends = [t.xy_pass(invert) for t in ts]
-        for c in range(2):
-            _emulated_all_to_all([x[c] for x in sends], [t.send_sizes for t in ts], [t.cols[c] for t in ts], [t.recv_sizes for t in ts])
-        for t in ts:
-            t.z_pass(invert, k)
+    sends = [t.sdf_xy_pass() for t in ts]
+    for c in range(2):
+        _emulated_all_to_all([x[c] for x in sends], [t.send_sizes for t in ts], [t.cols[c] for t in ts], [t.recv_sizes for t in ts])
+    for t in ts:
+        t.sdf_z_pass()
     _emulated_all_to_all([t.dist_cols for t in ts], [t.recv_sizes for t in ts], [t.back for t in ts], [t.send_sizes for t in ts])
     sdfs = [t.result() for t in ts]
     assert torch.equal(torch.cat(sdfs), ref["sdf"])

@@ -79,6 +79,13 @@ SIGNATURES = {
     "t3d_edt_z_workspace_bytes": (_i64, [_i, _i, _i]),
     "t3d_edt_z": (_i, [_vp, _vp, _i, _i, _i, _vp, _c.c_float, _i, _vp, _vp, _vp]),
     "t3d_edt": (_i, [_vp, _i, _i, _i, _i, _vp, _c.c_float, _i, _vp, _vp, _vp]),
+    "t3d_endcap_slices": (_i, [_vp, _i, _i, _vp, _i, _vp, _vp]),
+    "t3d_sdf_xy_workspace_bytes": (_i64, [_i, _i, _i]),
+    "t3d_sdf_xy": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "t3d_sdf_z_workspace_bytes": (_i64, [_i, _i, _i]),
+    "t3d_sdf_z": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "t3d_sdf_workspace_bytes": (_i64, [_i, _i, _i]),
+    "t3d_sdf": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "t3d_sign_from_f32": (_i, [_vp, _i, _i, _i, _dbl, _vp, _vp]),
     "t3d_mc_vertices_f32": (_i, [_vp, _i, _i, _i, _dbl, _vp, _u32, _u32, _u32, _i, _i, _vp, _vp, _i, _dbl, _dbl, _i, _vp, _vp]),
     "t3d_layer_colors": (_i, [_vp, _i64, _i, _dbl, _dbl, _i, _dbl, _dbl, _vp, _vp]),

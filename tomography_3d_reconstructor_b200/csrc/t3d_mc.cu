@@ -28,9 +28,10 @@ __device__ __align__(16) const int8_t g_tri_table[256][T3D_MC_ROW] = {T3D_TRI_TA
 static const int8_t h_tri_table[256][T3D_MC_ROW] = {T3D_TRI_TABLE_ROWS};
 
 struct McLuts {
-    uint8_t ntri[256];   // triangles of the classic row
-    uint8_t amb[256];    // 1: the index has an ambiguous face or is Lewiner's case 4 -> resolved per cube (mc33_resolve)
+    uint8_t ntri[256];   // triangles of the classic row; bit 7 (MC_AMB): the index has an ambiguous face or is Lewiner's case 4
+                         // -> resolved per cube (mc33_resolve).  One byte, one (divergent) constant load per cube.
 };
+#define MC_AMB 0x80u
 __constant__ McLuts c_luts;
 
 // Tilings of the ambiguous configurations (generated, tools/gen_mc33_tables.py): row = base[index] + (J | tube << k), J = bit i
@@ -139,8 +140,7 @@ static int ensure_luts()
     for (int i = 0; i < 256; ++i) {
         int n = 0;
         while (n < T3D_MC_ROW && h_tri_table[i][n] >= 0) n += 3;
-        l.ntri[i] = (uint8_t)(n / 3);
-        l.amb[i] = (uint8_t)(h33_base[i] != T3D_MC33_NONE);
+        l.ntri[i] = (uint8_t)(n / 3) | (uint8_t)(h33_base[i] != T3D_MC33_NONE ? MC_AMB : 0u);
     }
     T3D_CUDA(cudaMemcpyToSymbol(c_luts, &l, sizeof(l)));
     return 0;
@@ -313,11 +313,12 @@ __global__ void __launch_bounds__(128) k_mc_words(Grid g, McField fld, const uin
         const int b = __ffs(a) - 1;
         a &= a - 1;
         const int cs = cube_case(m, b);
-        if (c_luts.amb[cs]) {     // resolved per cube with Lewiner's face / interior tests (rare)
+        const uint32_t n = c_luts.ntri[cs];
+        if (n & MC_AMB) {     // resolved per cube with Lewiner's face / interior tests (rare)
             nt += g33_ntri[mc33_resolve(fld, z, y, (w << 5) + b, cs)];
             ++na;
         } else {
-            nt += c_luts.ntri[cs];
+            nt += n;
         }
     }
     aw_cnt[k] = __popc(m.X00);
@@ -373,7 +374,10 @@ __global__ void __launch_bounds__(128) k_mc_emit(EmitArgs a)
     if (PARTS & 2) {
         const int4* src = reinterpret_cast<const int4*>(&g_tri_table[0][0]);
         int4* dst = reinterpret_cast<int4*>(&s_tri[0][0]);
-        for (int i = threadIdx.x; i < 256; i += blockDim.x) dst[i] = src[i];
+        for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+            dst[i] = src[i];
+            if (c_luts.ntri[i] & MC_AMB) s_tri[i][T3D_MC_ROW - 1] = -2;   // (classic rows end at or before entry 15)
+        }
         __syncthreads();
     }
     const uint32_t tid = threadIdx.x;
@@ -457,7 +461,8 @@ __global__ void __launch_bounds__(128) k_mc_emit(EmitArgs a)
             if (last && at_next) id = s_next[((e >> 2) & 1) + 2 * ((e >> 3) & 1) + ((e >> 3) & 1) * ((e >> 1) & 1)][tid];
             return id;
         };
-        if (c_luts.amb[cs]) {     // ambiguous index: the row Lewiner's tests select (same decision as in k_mc_words)
+        const int4 trow = *reinterpret_cast<const int4*>(s_tri[cs]);   // 16 edge ids, -1 terminated; byte 15 = -2: ambiguous index
+        if ((int8_t)((uint32_t)trow.w >> 24) == -2) {     // the row Lewiner's tests select (same decision as in k_mc_words)
             const int r = mc33_resolve(a.fld, z, y, x0 + b, cs);
             const int8_t* row = g33_rows[r];
             const int n3 = 3 * (int)g33_ntri[r];
@@ -468,7 +473,6 @@ __global__ void __launch_bounds__(128) k_mc_emit(EmitArgs a)
             }
             continue;
         }
-        const int4 trow = *reinterpret_cast<const int4*>(s_tri[cs]);   // 16 edge ids, -1 terminated
         const uint32_t tw[4] = {(uint32_t)trow.x, (uint32_t)trow.y, (uint32_t)trow.z, (uint32_t)trow.w};
         auto edge_at = [&](int t) -> int { return (int)(int8_t)((tw[t >> 2] >> ((t & 3) * 8)) & 0xffu); };
         for (int t = 0; t < 15; t += 3) {

@@ -10,8 +10,19 @@
 
 #include <stdlib.h>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "t3d.h"
 #include "t3d_field.cuh"
+
+// NVTX ranges per stage of the enqueue (host side: they bracket the launches of a stage, and show up in an Nsight Systems
+// trace of a step next to the kernels they enqueue; header-only NVTX3, a no-op without an attached tool)
+struct NvtxRange {
+    bool open;
+    explicit NvtxRange(const char* name) : open(true) { nvtxRangePushA(name); }
+    void end() { if (open) { nvtxRangePop(); open = false; } }
+    ~NvtxRange() { end(); }
+};
 
 // result block (uint64 slots); keep in sync with include/t3d.h and pipeline.py
 enum {
@@ -275,6 +286,7 @@ static int reconstruct_core(const uint32_t* grid, const SlabGeom& g, int H, int 
 
     // side stream: bounding box of the owned planes of the raw grid (unless the pack kernel already did it) and the zero
     // ring of the padded sign volume; joined before the cube flags / the measures
+    NvtxRange r_smooth("t3d:smooth_voxel_data");
     T3D_CUDA(cudaEventRecord(side->e[2], st));
     T3D_CUDA(cudaStreamWaitEvent(side->s, side->e[2], 0));
     if (bbox_state == 0)
@@ -322,7 +334,9 @@ static int reconstruct_core(const uint32_t* grid, const SlabGeom& g, int H, int 
         view = t3d_make_view(surf, Zl, H, W, pad, 1, weights3_host);
     }
 
+    r_smooth.end();
     // ---- extract_manifold_surface: two-pass marching cubes, vertices
+    NvtxRange r_mc("t3d:extract_manifold_surface");
     RUN(t3d_mc_flags(ws + L.sign, Zp, Hp, Wp, g.z_begin, g.z_end, ws + L.ballots, st));
     RUN(t3d_exclusive_scan_u32(ws + L.ballots, ws + L.chunkbase, n_chunks, 1, 0, 1, R + R_NACTIVE, ws + L.scan1, st));
     RUN(t3d_mc_words_view_dev(view, x_off, ws + L.sign, Zp, Hp, Wp, g.z_begin, g.z_end, ws + L.ballots, ws + L.chunkbase, cap_active,
@@ -343,6 +357,8 @@ static int reconstruct_core(const uint32_t* grid, const SlabGeom& g, int H, int 
     RUN(t3d_mc_vertices_view_dev(view, x_off, ws + L.vkeys, R + R_NACTIVE, cap_verts, 1, g.z_offset, cum_f64, adj_f64, n_cum, mm_y, mm_x,
                                  scale_in_f64, 7, ws + L.verts_raw, st));
     // ---- mesh volume / area on the emitted mesh (side stream, concurrent with the canonical ordering), canonical mesh
+    r_mc.end();
+    NvtxRange r_canon("t3d:ensure_manifold_mesh+measures");
     T3D_CUDA(cudaEventRecord(side->e[7], st));
     T3D_CUDA(cudaStreamWaitEvent(side->s, side->e[7], 0));
     RUN(t3d_mesh_measure_dev(ws + L.verts_raw, ws + L.faces_raw, cap_faces, R + R_NT, 0, R + R_VOLUME_F64, ws + L.measure, side->s));
@@ -403,6 +419,7 @@ extern "C" int t3d_reconstruct(const void* masks_u8, int Z, int H, int W, int th
 
     // ---- create_voxel_data: pack, fill the holes of the end slices (side stream), z gap fill + per-slice counts
     int bbox_state = 0;
+    NvtxRange r_create("t3d:create_voxel_data");
     if (close_ends && t3d_pack_gap_supported(m, Z, H, W, threshold)) {
         // one pass over the masks: pack + gap fill + counts + extrema; the two end planes are packed apart, hole-filled on
         // the side stream meanwhile, and planes 0, 1, Z-2, Z-1 are then rewritten from them
@@ -437,6 +454,7 @@ extern "C" int t3d_reconstruct(const void* masks_u8, int Z, int H, int W, int th
         RUN(t3d_pack_masks(m, Z, H, W, threshold, bitsB, st));
         RUN(t3d_volume_stats(bitsB, Z, H, W, R + R_COUNTS, nullptr, st));
     }
+    r_create.end();
     SlabGeom g = {0, Z, 0, 0, -1, 0, 0, 0, 0.f, 0.f};
     RUN(reconstruct_core(bitsB, g, H, W, n_stages, erode_mask, pad, weights3_host, cum_f64, adj_f64, n_cum, mm_per_pixel_y,
                          mm_per_pixel_x, scale_in_f64, cap_active, cap_verts, cap_faces, cap_zverts, cap_g0, zkey_bits, verts_out_f32,

@@ -232,7 +232,10 @@ WRITABLE_OUTPUTS = bool(_os.environ.get("T3D_WRITABLE_OUTPUTS"))
 
 def publish(registry: "_Registry", arr: np.ndarray, obj) -> np.ndarray:
     if WRITABLE_OUTPUTS:
-        arr.setflags(write=True)
+        try:
+            arr.setflags(write=True)
+        except ValueError:            # a view of memory numpy does not own (pinned staging buffer): hand out a copy
+            arr = np.array(arr)
         return arr
     arr.setflags(write=False)
     registry.register(arr, obj)

@@ -47,8 +47,8 @@ class SurfaceExtractor:
                     dv.memo[key] = mesh
             vertices = engine.download(mesh.verts)      # fresh host arrays on every call, read-only: the device copy
             faces = engine.download(mesh.faces)         # is recognised by array identity (volume / area / export)
-            engine.publish(engine.meshes, vertices, mesh)
-            engine.publish(engine.meshes, faces, mesh)
+            vertices = engine.publish(engine.meshes, vertices, mesh)
+            faces = engine.publish(engine.meshes, faces, mesh)
             self.last_mesh = mesh
             self.last_n_ambiguous = mesh.n_ambiguous
 
@@ -91,8 +91,8 @@ class SurfaceExtractor:
             mesh = engine.extract_surface(None, slice_depths, mm_per_pixel_y, mm_per_pixel_x, False, False, field=f.contiguous(),
                                           level=level)
             vertices, faces = engine.download(mesh.verts), engine.download(mesh.faces)
-            engine.publish(engine.meshes, vertices, mesh)
-            engine.publish(engine.meshes, faces, mesh)
+            vertices = engine.publish(engine.meshes, vertices, mesh)
+            faces = engine.publish(engine.meshes, faces, mesh)
             self.last_mesh, self.last_n_ambiguous = mesh, mesh.n_ambiguous
             return vertices, faces
         except engine.T3DUnavailable:

@@ -43,7 +43,7 @@ class VoxelProcessor:
         # upload, pack/close and download pipelined in z-chunks (H2D and D2H overlap)
         # (a list of separately allocated pageable masks -- what ImageLoader returns -- is gathered through a pinned ring)
         dv, host = engine.create_voxel_data_from_host(mask_images, 1, close_ends)
-        engine.publish(engine.volumes, host, dv)
+        host = engine.publish(engine.volumes, host, dv)
         active = int(dv.slice_counts().sum())
         self.voxel_data = host
         print(f"Voxels: {self.voxel_data.shape}, active: {active:,}")

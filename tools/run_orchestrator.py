@@ -46,13 +46,19 @@ class _Recorder:
         return self
 
     def __getattr__(self, item):
+        if item.startswith("__"):
+            raise AttributeError(item)
         return _Recorder(self._name + "." + item)
 
 
 def stub_module(name, **attrs):
     m = types.ModuleType(name)
     m.__dict__.update(attrs)
-    m.__getattr__ = lambda item, _n=name: _Recorder(_n + "." + item)
+    def _getattr(item, _n=name):
+        if item.startswith("__"):
+            raise AttributeError(item)
+        return _Recorder(_n + "." + item)
+    m.__getattr__ = _getattr
     sys.modules[name] = m
     return m
 
@@ -119,7 +125,8 @@ def main():
                  for m in (orch, voxel_processor, surface_extractor, volume_calculator, glb_exporter, sys.modules["image_loader"],
                            sys.modules["visualizer"], config)}
         print("[harness] modules:", bound)
-        assert bound["voxel_processor"].startswith("tomography_3d_reconstructor_b200") and orch.__file__.startswith(args.reference)
+        assert bound["voxel_processor"].startswith("tomography_3d_reconstructor_b200")
+        assert os.path.abspath(orch.__file__).startswith(os.path.abspath(args.reference))
         import torch
         torch.cuda.synchronize()
         t0 = time.perf_counter()
