@@ -375,6 +375,22 @@ def run_ours(args, Z, H, W, cfg):
     for _ in range(max(3, args.warmup)):
         res = step()
     barrier()
+    partition = None
+    if sharded_run and path == "occupancy" and not args.no_balance:
+        # Equal slice counts are equal voxel work but unequal surface work (polar slabs carry less mesh than equatorial ones),
+        # and the step ends with a collective: re-cut the slabs by estimated cost, learned from the equal-split step above
+        hist = torch.from_numpy(sharded.vertices_per_slice(res, Zg)).to(dev)
+        dist.all_reduce(hist)
+        partition = sharded.balanced_ranges(sharded.slice_cost(hist.cpu().numpy()), world, sharded.HALO)
+        sharded.set_partition(Zg, world, partition)
+        z0, z1 = partition[rank]
+        del masks
+        torch.cuda.empty_cache()
+        masks = make_phantom_u8(Zg, H, W, z0, z1, dev)
+        per_gpu_vox = (z1 - z0) * H * W
+        for _ in range(max(3, args.warmup)):
+            res = step()
+        barrier()
     # kernels of this library per step: counted on one eager (non-graph) step, a graph replay launches the same ones
     lc0 = lib.t3d_launch_count()
     if path == "occupancy" and not args.staged:
@@ -458,7 +474,7 @@ def run_ours(args, Z, H, W, cfg):
         stage_ms = {k: float(np.min(v)) for k, v in stage_ms.items()}
 
     # ---- e2e through the reference-facing classes, host buffers in pinned memory
-    e2e = e2e_classes = None
+    e2e = e2e_classes = e2e_bits = None
     want_e2e = path == "occupancy" and not args.no_e2e
     if want_e2e and not sharded_run:
         from tomography_3d_reconstructor_b200 import VoxelProcessor, SurfaceExtractor, VolumeCalculator
@@ -528,6 +544,30 @@ def run_ours(args, Z, H, W, cfg):
                "api": "pipeline.reconstruct_host: list of pinned host u8 masks -> H2D -> t3d_reconstruct -> D2H of the mesh "
                "(f32 vertices, int64 faces) and the result block (volumes, area, bbox, per-slice counts)"}
         assert np.array_equal(out["vertices"], v) and np.array_equal(out["faces"], f)
+        # additive entry: the same masks already bit-packed on the host (1 bit per voxel over PCIe)
+        if world == 1:
+            from tomography_3d_reconstructor_b200 import sharded as _sh
+            wpr = engine.words_per_row(W)
+            host_bits = torch.empty((Z, H, wpr), dtype=torch.int32, pin_memory=True)
+            packed = torch.empty((Z, H, wpr), dtype=torch.int32, device=dev)
+            lib.t3d_pack_masks(engine._p(masks), Z, H, W, THRESHOLD, engine._p(packed), engine._stream())
+            host_bits.copy_(packed)
+            torch.cuda.synchronize()
+            del packed
+            hbits = host_bits.numpy().view(np.uint32)
+            for _ in range(3):
+                ob = _sh.reconstruct_host_bits(hbits, W, sides, *phys, use_graph=not args.no_graph)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(n_e2e):
+                ob = _sh.reconstruct_host_bits(hbits, W, sides, *phys, use_graph=not args.no_graph)
+            torch.cuda.synchronize()
+            eb_s = (time.perf_counter() - t0) / n_e2e
+            assert np.array_equal(ob["vertices"], v) and np.array_equal(ob["faces"], f)
+            e2e_bits = {"value": voxels / eb_s / 1e9, "unit": "Gvoxels/s", "h2d_bytes_per_step": int(hbits.nbytes),
+                        "d2h_bytes_per_step": int(ob["vertices"].nbytes + ob["faces"].nbytes + 8 * (32 + 2 * Z)), "ms_per_step": 1e3 * eb_s,
+                        "steps": n_e2e, "api": "sharded.reconstruct_host_bits: pinned host masks ALREADY bit-packed (1 bit per voxel) -> H2D -> "
+                        "t3d_reconstruct_slab -> D2H of the mesh and the result block (additive input format; not the headline e2e)"}
 
     def teardown():
         if world > 1:
@@ -657,6 +697,8 @@ def run_ours(args, Z, H, W, cfg):
                     "exact EDT/SDF + marching cubes at level 0" if path == "sdf" else "Gaussian(0.5) marching cubes",
                     "; z-slab sharded over %d GPUs" % world if sharded_run else ""),
                    "config": args.config, "shape": [Zg, H, W],
+                   "partition": ("cost-balanced z-slabs (slices per GPU: %s), learned from one equal-split step" %
+                                 [b - a for a, b in partition]) if partition else ("equal z-slabs" if sharded_run else None),
                    "l2": "inputs larger than L2: %.0f MB of u8 masks per GPU per step" % (per_gpu_vox / 1e6)
                    if per_gpu_vox > 130e6 else "inputs of one step (%.0f MB of u8 masks) fit the 126 MB L2" % (per_gpu_vox / 1e6),
                    "mesh": {"vertices": V, "faces": F, "n_ambiguous_cubes": n_amb},
@@ -673,6 +715,8 @@ def run_ours(args, Z, H, W, cfg):
         line["e2e"] = e2e
     if e2e_classes is not None:
         line["e2e_classes"] = e2e_classes
+    if e2e_bits is not None:
+        line["e2e_bits"] = e2e_bits
     if world == 1 and not args.no_cpu and path == "occupancy":
         from oracle import cpu_ref
         cpu_ref.build()
@@ -693,6 +737,7 @@ def main():
     ap.add_argument("--config", default="C1", choices=sorted(CONFIGS), help="BASELINE.json configuration (C1 = configs[1], the headline)")
     ap.add_argument("--shape", default=None, help="Z,H,W per GPU (overrides the shape of --config; occupancy path)")
     ap.add_argument("--no-check", action="store_true", help="N>1: skip the stitched-mesh-vs-single-GPU check")
+    ap.add_argument("--no-balance", action="store_true", help="N>1: equal slice counts per GPU instead of cost-balanced z-slabs")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--staged", action="store_true", help="time the staged (one call per stage) path instead of the fused one")

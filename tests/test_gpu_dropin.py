@@ -234,3 +234,22 @@ def test_writable_outputs_flag(eng, oracle):
             assert se.extract_manifold_surface(sm, depths, 0.3, 0.25) is None
         finally:
             engine.WRITABLE_OUTPUTS = False
+
+
+def test_bit_packed_host_input_matches_the_byte_path(eng, oracle):
+    """Additive entry for masks that are already bit-packed on the host (1 bit per voxel over PCIe): same mesh and volumes as
+    reconstruct_host / the oracle; learning call, fused call, graph replay; a hole in the first slice is still filled."""
+    from tomography_3d_reconstructor_b200 import sharded
+    Z, H, W = 37, 70, 130
+    sides = (4, 29, 4)
+    u8, masks = _loader_like_masks(oracle, Z, H, W)
+    ref = oracle.reference_pipeline(u8, 200, sides, 6.0, 143.1, 95.03)
+    bits = sharded.pack_bits_host(masks)
+    assert bits.shape == (Z, H, eng.words_per_row(W)) and bits.dtype.itemsize == 4
+    assert int(np.unpackbits(bits.view(np.uint8), bitorder="little").sum()) == int(sum(m.sum() for m in masks))
+    sharded._bits_plans.clear()
+    for rep in range(4):
+        out = sharded.reconstruct_host_bits(bits, W, sides, 6.0, 143.1, 95.03, use_graph=rep != 1)
+        assert np.array_equal(out["vertices"], ref["vertices"]) and np.array_equal(out["faces"], ref["faces"]), rep
+        assert out["voxel_volume_mm3"] == ref["voxel_volume"] and out["processed_voxel_volume_mm3"] == ref["processed_volume"]
+        assert abs(out["mesh_volume_mm3"] - ref["mesh_volume"]) <= 1e-6 * ref["mesh_volume"]

@@ -132,3 +132,37 @@ def test_halo_exchange_and_gathers_world_size_2_gloo():
     for rank, ok_halo, bases, ok, ok_gather in out:
         assert ok_halo and ok and ok_gather
         assert bases == [0, 97]
+
+
+def test_balanced_ranges_tile_the_stack_with_equal_cost():
+    import numpy as np
+    from tomography_3d_reconstructor_b200 import sharded
+    Z, world = 4096, 8
+    z = np.arange(Z)
+    verts = 4000.0 * np.sqrt(np.clip(1 - ((z - Z / 2) / (0.42 * Z)) ** 2, 0, None))     # an ellipsoid's vertices per slice
+    cost = sharded.slice_cost(verts)
+    ranges = sharded.balanced_ranges(cost, world, sharded.HALO)
+    assert ranges[0][0] == 0 and ranges[-1][1] == Z and all(ranges[r][1] == ranges[r + 1][0] for r in range(world - 1))
+    assert all(b - a >= sharded.HALO for a, b in ranges)
+    sums = np.array([cost[a:b].sum() for a, b in ranges])
+    assert sums.max() / sums.mean() < 1.01                       # equal slices would give 1.19 on this profile
+    eq = np.array([cost[a:b].sum() for a, b in [sharded.slab_range(Z, r, world) for r in range(world)]])
+    assert eq.max() / eq.mean() > 1.1
+    # the end slabs (polar caps, little surface) get more slices than the equatorial ones
+    assert ranges[0][1] - ranges[0][0] > ranges[world // 2][1] - ranges[world // 2][0]
+    # registering the partition redirects slab_range for exactly this (Z, world)
+    try:
+        sharded.set_partition(Z, world, ranges)
+        assert [sharded.slab_range(Z, r, world) for r in range(world)] == ranges
+        assert sharded.slab_range(Z, 0, 4) == (0, Z // 4)
+        with pytest.raises(ValueError):
+            sharded.set_partition(Z, world, ranges[:-1])
+    finally:
+        sharded.set_partition(Z, world, None)
+    assert sharded.slab_range(Z, 1, world) == (Z // 8, Z // 4)
+    # degenerate: everything in one slice still leaves every rank its minimum
+    spike = np.zeros(64); spike[10] = 1.0
+    r2 = sharded.balanced_ranges(spike, 4, 8)
+    assert all(b - a >= 8 for a, b in r2) and r2[-1][1] == 64
+    with pytest.raises(ValueError):
+        sharded.balanced_ranges(np.ones(20), 4, 8)

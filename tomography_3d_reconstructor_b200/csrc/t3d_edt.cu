@@ -431,8 +431,8 @@ struct SdfPass {
     int n;
     int bulk;             // 1: every 128-line tile is one contiguous, 16-byte aligned row segment per sample -> bulk-async tiles
     double w_new, w0, w1, s_new, s0, s1;
-    uint2* stack;         // [total threads][2 * n]: a thread's two stacks are contiguous (envelope 0 in [0, n), envelope 1 in [n, 2n)):
-                          // threads are not in lockstep on the slot index, so thread-major keeps each thread's accesses sequential
+    uint2* stack;         // [total threads][n]: a thread's stack is contiguous -- threads are not in lockstep on the slot index, so
+                          // thread-major keeps each thread's accesses sequential (4 entries per 32-byte sector)
 };
 
 // ---- bulk-async (TMA engine, 1-D form) tile pipeline: raw PTX, sm_90+ ---------------------------------------------------
@@ -466,91 +466,17 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
 }
 
 #define SDF_ROWS 16     // samples per pipeline stage (one bulk copy of 256 bytes per row and component)
-#define SDF_STAGES 4    // stages in flight (bulk-async path)
+#define SDF_STAGES 3    // stages in flight (bulk-async path)
 
-// one lower envelope being built: the top entry lives in registers, entries below it in the global stack
-struct SdfEnv {
-    int k, vk, bk, ak, ck;
-    double gk;
-    uint2* base;
-    uint2* top;
-};
-
-template <int NCOMP>
-__device__ __forceinline__ void sdf_push(SdfEnv& e, int q, int a, int c, int n, double w_new, double w0, double w1)
-{
-    const double qd = (double)q;
-    double gq = (double)(a * a) * w0 + qd * qd * w_new;
-    if (NCOMP > 1) gq += (double)(c * c) * w1;
-    int b = 0;
-    while (e.k >= 0) {
-        // first sample that site q takes from the top site vk: the smallest integer p with num < den * p
-        const double num = gq - e.gk, den = (2.0 * w_new) * (qd - (double)e.vk);
-        const float est = fminf(fmaxf(__fdividef((float)num, (float)den), -1.0f), (float)n);   // (also tames +-inf)
-        b = max(0, min((int)floorf(est) + 1, n));
-        while (b > 0 && num < den * (double)(b - 1)) --b;
-        while (b < n && !(num < den * (double)b)) ++b;
-        if (b > e.bk) break;
-        --e.k;
-        --e.top;
-        if (e.k >= 0) {
-            const uint2 t = *e.top;
-            e.vk = (int)(t.x & 0xffffu); e.bk = (int)(t.x >> 16);
-            e.ak = (int)(short)(t.y & 0xffffu); e.ck = (int)(short)(t.y >> 16);
-            const double vd = (double)e.vk;
-            e.gk = (double)(e.ak * e.ak) * w0 + vd * vd * w_new;
-            if (NCOMP > 1) e.gk += (double)(e.ck * e.ck) * w1;
-        }
-    }
-    if (e.k >= 0) { *e.top = make_uint2((uint32_t)e.vk | ((uint32_t)e.bk << 16), ((uint32_t)e.ak & 0xffffu) | ((uint32_t)e.ck << 16)); ++e.top; }
-    else { b = 0; e.top = e.base; }
-    ++e.k;
-    e.vk = q; e.bk = b; e.ak = a; e.ck = c; e.gk = gq;
-}
-
-__device__ __forceinline__ void sdf_flush(SdfEnv& e)
-{
-    if (e.k >= 0) *e.top = make_uint2((uint32_t)e.vk | ((uint32_t)e.bk << 16), ((uint32_t)e.ak & 0xffffu) | ((uint32_t)e.ck << 16));
-}
-
-// cursor of the evaluation sweep over one envelope
-struct SdfCur {
-    int j, k, v, a, c, next_start;
-    uint2 e_next;
-    const uint2* nx;
-    double a2, c2;
-    bool fresh;
-};
-
-__device__ __forceinline__ void sdf_cur_init(SdfCur& u, const SdfEnv& e, int n)
-{
-    u.j = 0; u.k = e.k; u.v = 0; u.a = 0; u.c = 0; u.next_start = n; u.e_next = make_uint2(0, 0); u.nx = e.base + 1;
-    u.a2 = u.c2 = 0.0; u.fresh = true;
-    if (e.k >= 0) {
-        const uint2 t = e.base[0];
-        u.v = (int)(t.x & 0xffffu); u.a = (int)(short)(t.y & 0xffffu); u.c = (int)(short)(t.y >> 16);
-        if (e.k >= 1) { u.e_next = *u.nx; u.next_start = (int)(u.e_next.x >> 16); }
-    }
-}
-
-__device__ __forceinline__ void sdf_cur_seek(SdfCur& u, int q, int n)
-{
-    while (q >= u.next_start) {
-        ++u.j;
-        u.v = (int)(u.e_next.x & 0xffffu); u.a = (int)(short)(u.e_next.y & 0xffffu); u.c = (int)(short)(u.e_next.y >> 16);
-        ++u.nx;
-        if (u.j < u.k) { u.e_next = *u.nx; u.next_start = (int)(u.e_next.x >> 16); }
-        else u.next_start = n;
-        u.fresh = true;
-    }
-}
-
-// Two sweeps per 128-line tile: (1) build both envelopes, (2) evaluate every voxel on the envelope of the other kind.  The
-// samples stream through a shared-memory ring of [SDF_ROWS][128] int16 tiles: with p.bulk the rows of a tile are contiguous
-// 256-byte segments fetched by cp.async.bulk (one lane per row, completion on an mbarrier, SDF_STAGES tiles in flight); else
-// every thread fills its own column with plain loads (same layout, no barriers needed: a thread only reads its own column).
+// Per 128-line tile: for K = 0, 1 (the envelope "distance to the nearest K-voxel") a build sweep, then an evaluation sweep
+// at the voxels of the other kind -- ONE straight-line code body for both kinds (the kernel is instruction-bound: a version
+// that built both envelopes in one sweep paid more in register moves, selects and divergence than it saved in loads; ncu:
+// 240-380 instructions per sample, 25 % IMAD moves, 9 % BSSY/BSYNC).  The samples stream through a shared-memory ring of
+// [SDF_ROWS][128] int16 tiles: with p.bulk the rows of a tile are contiguous 256-byte segments fetched by cp.async.bulk (one
+// lane per row, completion on an mbarrier, SDF_STAGES tiles in flight); else every thread fills its own column with plain
+// loads (same layout; a thread only ever reads its own column).
 template <int NCOMP, bool FINAL>
-__global__ void __launch_bounds__(SDF_THREADS, 6) k_sdf_envelope(SdfPass p)
+__global__ void __launch_bounds__(SDF_THREADS, 8) k_sdf_envelope(SdfPass p)
 {
     __shared__ __align__(128) int16_t s_t0[SDF_STAGES][SDF_ROWS][SDF_THREADS];
     __shared__ __align__(128) int16_t s_t1[NCOMP > 1 ? SDF_STAGES : 1][SDF_ROWS][SDF_THREADS];
@@ -559,7 +485,7 @@ __global__ void __launch_bounds__(SDF_THREADS, 6) k_sdf_envelope(SdfPass p)
     const int64_t t = (int64_t)blockIdx.x * SDF_THREADS + tid;
     const int n = p.n;
     const int64_t stride = p.stride;
-    const double w_new = p.w_new, w0 = p.w0, w1 = p.w1;
+    const double w_new = p.w_new, w0 = p.w0, w1 = p.w1, two_w = 2.0 * p.w_new;
     const int n_chunks = (n + SDF_ROWS - 1) / SDF_ROWS;
     const bool bulk = p.bulk != 0;
     if (bulk && tid == 0) {
@@ -569,6 +495,7 @@ __global__ void __launch_bounds__(SDF_THREADS, 6) k_sdf_envelope(SdfPass p)
     __syncthreads();
     uint32_t uses = 0;      // chunks consumed so far by this CTA (stage = uses % STAGES, parity = (uses / STAGES) & 1)
     uint32_t issued = 0;    // chunks issued so far (warp 0)
+    uint2* const st = p.stack + t * (int64_t)n;     // this thread's stack: n entries, contiguous (see SdfPass::stack)
     const int64_t n_tiles = (p.n_lines + SDF_THREADS - 1) / SDF_THREADS;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int64_t line0 = tile * SDF_THREADS, line = line0 + tid;
@@ -576,27 +503,74 @@ __global__ void __launch_bounds__(SDF_THREADS, 6) k_sdf_envelope(SdfPass p)
         const int tile_lines = (int)min((int64_t)SDF_THREADS, p.n_lines - line0);
         const int64_t base0 = (line0 / p.inner) * p.outer_stride + (line0 % p.inner);     // first line of the tile
         const int64_t base = live ? (line / p.inner) * p.outer_stride + (line % p.inner) : 0;
-        SdfEnv E0, E1;
-        E0.k = E1.k = -1; E0.vk = E0.bk = E0.ak = E0.ck = 0; E1.vk = E1.bk = E1.ak = E1.ck = 0; E0.gk = E1.gk = 0.0;
-        E0.base = E0.top = p.stack + t * (2 * (int64_t)n);
-        E1.base = E1.top = E0.base + n;
-        SdfCur U0, U1;
+        int k = -1;                                   // index of the top entry of the envelope being built / evaluated
 #pragma unroll 1
-        for (int sweep = 0; sweep < 2; ++sweep) {
-            int prev_kind = -1, run_start = 0;
-            if (sweep == 1) { sdf_cur_init(U0, E0, n); sdf_cur_init(U1, E1, n); }
+        for (int pass = 0; pass < 4; ++pass) {
+            const int K = pass >> 1;
+            const bool build = (pass & 1) == 0;
+            const bool need1 = NCOMP > 1 && build;
+            // state of a build sweep: the top entry in registers (site, first sample it serves, its offsets, its cost)
+            int vk = 0, bk = 0, ak = 0, ck = 0, prev_kind = -1, run_start = 0;
+            double gk = 0.0;
+            uint2* top = st;
+            // state of an evaluation sweep
+            int j = 0, v = 0, ea = 0, ec = 0, next_start = n;
+            uint2 e_next = make_uint2(0, 0);
+            const uint2* nx = st + 1;
+            double a2 = 0.0, c2 = 0.0;
+            bool fresh = true;
+            if (build) k = -1;
+            else if (k >= 0) {
+                const uint2 e0 = st[0];
+                v = (int)(e0.x & 0xffffu); ea = (int)(short)(e0.y & 0xffffu); ec = (int)(short)(e0.y >> 16);
+                if (k >= 1) { e_next = *nx; next_start = (int)(e_next.x >> 16); }
+            }
+            // one site: pop the entries it takes over completely, then push it
+            auto push = [&](int q, int a, int c) {
+                const double qd = (double)q;
+                double gq = (double)(a * a) * w0 + qd * qd * w_new;
+                if (NCOMP > 1) gq += (double)(c * c) * w1;
+                int b = 0;
+                while (k >= 0) {
+                    // first sample that site q takes from the top site vk: the smallest integer s with num < den * s
+                    const double num = gq - gk, den = two_w * (qd - (double)vk);
+                    const float est = fminf(fmaxf(__fdividef((float)num, (float)den), -1.0f), (float)n);   // (also tames +-inf)
+                    const float fl = floorf(est);
+                    b = max(0, min((int)fl + 1, n));
+                    const float fr = est - fl;
+                    if (fr < 0.02f || fr > 0.98f) {        // the float32 estimate is too close to an integer to be trusted
+                        while (b > 0 && num < den * (double)(b - 1)) --b;
+                        while (b < n && !(num < den * (double)b)) ++b;
+                    }
+                    if (b > bk) break;
+                    --k;
+                    --top;
+                    if (k >= 0) {
+                        const uint2 e = *top;
+                        vk = (int)(e.x & 0xffffu); bk = (int)(e.x >> 16);
+                        ak = (int)(short)(e.y & 0xffffu); ck = (int)(short)(e.y >> 16);
+                        const double vd = (double)vk;
+                        gk = (double)(ak * ak) * w0 + vd * vd * w_new;
+                        if (NCOMP > 1) gk += (double)(ck * ck) * w1;
+                    }
+                }
+                if (k >= 0) { *top = make_uint2((uint32_t)vk | ((uint32_t)bk << 16), ((uint32_t)ak & 0xffffu) | ((uint32_t)ck << 16)); ++top; }
+                else { b = 0; top = st; }
+                ++k;
+                vk = q; bk = b; ak = a; ck = c; gk = gq;
+            };
             // chunk loader: rows [c*ROWS, ...) of this tile into stage (issued % STAGES)
             auto issue = [&](int c) {
-                const int st = (int)(issued % SDF_STAGES);
+                const int sg = (int)(issued % SDF_STAGES);
                 const int rows = min(SDF_ROWS, n - c * SDF_ROWS);
                 if (tid < 32) {
                     const uint32_t row_bytes = (uint32_t)tile_lines * 2u;
-                    if (tid == 0) mbar_expect_tx(&s_full[st], row_bytes * rows * (NCOMP > 1 && sweep == 0 ? 2u : 1u));
+                    if (tid == 0) mbar_expect_tx(&s_full[sg], row_bytes * rows * (need1 ? 2u : 1u));
                     __syncwarp();
                     if (tid < rows) {
                         const int64_t off = base0 + (int64_t)(c * SDF_ROWS + tid) * stride;
-                        bulk_g2s(&s_t0[st][tid][0], p.in0 + off, row_bytes, &s_full[st]);
-                        if (NCOMP > 1 && sweep == 0) bulk_g2s(&s_t1[st][tid][0], p.in1 + off, row_bytes, &s_full[st]);
+                        bulk_g2s(&s_t0[sg][tid][0], p.in0 + off, row_bytes, &s_full[sg]);
+                        if (need1) bulk_g2s(&s_t1[sg][tid][0], p.in1 + off, row_bytes, &s_full[sg]);
                     }
                 }
                 ++issued;
@@ -605,88 +579,78 @@ __global__ void __launch_bounds__(SDF_THREADS, 6) k_sdf_envelope(SdfPass p)
                 for (int c = 0; c < SDF_STAGES - 1 && c < n_chunks; ++c) issue(c);
             }
             for (int c = 0; c < n_chunks; ++c) {
-                const int st = (int)(uses % SDF_STAGES);
+                const int sg = (int)(uses % SDF_STAGES);
                 const int rows = min(SDF_ROWS, n - c * SDF_ROWS);
                 if (bulk) {
                     if (c + SDF_STAGES - 1 < n_chunks) issue(c + SDF_STAGES - 1);   // (its stage was released by the barrier below)
-                    mbar_wait(&s_full[st], (uses / SDF_STAGES) & 1u);
+                    mbar_wait(&s_full[sg], (uses / SDF_STAGES) & 1u);
                 } else if (live) {
                     const int64_t off = base + (int64_t)c * SDF_ROWS * stride;
 #pragma unroll 8
-                    for (int r = 0; r < rows; ++r) s_t0[st][r][tid] = p.in0[off + (int64_t)r * stride];
-                    if (NCOMP > 1 && sweep == 0) {
+                    for (int r = 0; r < rows; ++r) s_t0[sg][r][tid] = p.in0[off + (int64_t)r * stride];
+                    if (need1) {
 #pragma unroll 8
-                        for (int r = 0; r < rows; ++r) s_t1[st][r][tid] = p.in1[off + (int64_t)r * stride];
+                        for (int r = 0; r < rows; ++r) s_t1[sg][r][tid] = p.in1[off + (int64_t)r * stride];
                     }
                 }
-                if (live) {
-                    if (sweep == 0) {
-                        // ---- build: a voxel is a site with its stored offsets for the envelope of the OTHER kind; for its own
-                        // kind only the two ends of a run of equal voxels are (zero-cost) sites
-                        for (int r = 0; r < rows; ++r) {
-                            const int q = c * SDF_ROWS + r;
-                            const int cur = s_t0[st][r][tid];
-                            const int kind = cur & 1;
+                if (live && build) {
+                    // a K-voxel is a zero-cost site, but only the two ends of a run of K-voxels can serve a voxel of the other
+                    // kind; a voxel of the other kind is a site with its stored offsets
+                    for (int r = 0; r < rows; ++r) {
+                        const int q = c * SDF_ROWS + r;
+                        const int cur = s_t0[sg][r][tid];
+                        const int kind = cur & 1;
+                        if (kind == K) {
+                            if (prev_kind != K) { push(q, 0, 0); run_start = q; }      // start of a run
+                        } else {
+                            if (prev_kind == K && q - 1 > run_start) push(q - 1, 0, 0);  // the run that just ended
                             const int a = sdf_dec(cur);
-                            const int cc = NCOMP > 1 ? (int)s_t1[st][r][tid] : 0;
-                            const bool change = kind != prev_kind;
-                            // up to three pushes, in this order (positions must ascend within an envelope): the end of the previous
-                            // run (zero cost, envelope prev_kind), this voxel's stored offsets (envelope of the other kind), the
-                            // start of a new run (zero cost, envelope kind).  ONE push body, the target envelope swapped in.
-#pragma unroll 1
-                            for (int op = 0; op < 3; ++op) {
-                                int target, pq, pa, pc;
-                                if (op == 0) { if (!(change && prev_kind >= 0 && q - 1 > run_start)) continue; target = prev_kind; pq = q - 1; pa = 0; pc = 0; }
-                                else if (op == 1) { if (a == SDF_NONE) continue; target = kind ^ 1; pq = q; pa = a; pc = cc; }
-                                else { if (!change) continue; target = kind; pq = q; pa = 0; pc = 0; }
-                                if (target) { const SdfEnv tmp = E0; E0 = E1; E1 = tmp; }
-                                sdf_push<NCOMP>(E0, pq, pa, pc, n, w_new, w0, w1);
-                                if (target) { const SdfEnv tmp = E0; E0 = E1; E1 = tmp; }
-                            }
-                            if (change) { run_start = q; prev_kind = kind; }
+                            if (a != SDF_NONE) push(q, a, NCOMP > 1 ? (int)s_t1[sg][r][tid] : 0);
                         }
-                    } else {
-                        // ---- evaluate: one-voxels on envelope 0 (+), zero-voxels on envelope 1 (-)
-                        int64_t off = base + (int64_t)c * SDF_ROWS * stride;
-                        for (int r = 0; r < rows; ++r, off += stride) {
-                            const int q = c * SDF_ROWS + r;
-                            const int kind = s_t0[st][r][tid] & 1;
-                            SdfCur& u = kind ? U0 : U1;
-                            if (u.k < 0) {
-                                if (FINAL) p.sdf[off] = kind ? INFINITY : -INFINITY;
-                                else { p.out0[off] = (int16_t)((SDF_NONE << 1) | kind); p.out1[off] = 0; }
-                                continue;
+                        prev_kind = kind;
+                    }
+                } else if (live) {
+                    int64_t off = base + (int64_t)c * SDF_ROWS * stride;
+                    for (int r = 0; r < rows; ++r, off += stride) {
+                        const int kind = s_t0[sg][r][tid] & 1;
+                        if (kind == K) continue;
+                        if (k < 0) {        // no K-voxel reachable from this line
+                            if (FINAL) p.sdf[off] = K ? -INFINITY : INFINITY;
+                            else { p.out0[off] = (int16_t)((SDF_NONE << 1) | kind); p.out1[off] = 0; }
+                            continue;
+                        }
+                        const int q = c * SDF_ROWS + r;
+                        while (q >= next_start) {
+                            ++j;
+                            v = (int)(e_next.x & 0xffffu); ea = (int)(short)(e_next.y & 0xffffu); ec = (int)(short)(e_next.y >> 16);
+                            ++nx;
+                            if (j < k) { e_next = *nx; next_start = (int)(e_next.x >> 16); }
+                            else next_start = n;
+                            fresh = true;
+                        }
+                        const int dnew = v - q;
+                        if (FINAL) {
+                            if (fresh) {
+                                const double t1 = __dmul_rn((double)ea, p.s0), t2 = __dmul_rn((double)ec, p.s1);
+                                a2 = __dmul_rn(t1, t1); c2 = __dmul_rn(t2, t2);
+                                fresh = false;
                             }
-                            sdf_cur_seek(u, q, n);
-                            const int dnew = u.v - q;
-                            if (FINAL) {
-                                if (u.fresh) {
-                                    const double t1 = __dmul_rn((double)u.a, p.s0), t2 = __dmul_rn((double)u.c, p.s1);
-                                    u.a2 = __dmul_rn(t1, t1); u.c2 = __dmul_rn(t2, t2);
-                                    u.fresh = false;
-                                }
-                                // scipy: dt = (ft - indices) * sampling; sqrt(add.reduce(dt*dt, axis=0)) -- axis order z, y, x
-                                const double t0 = __dmul_rn((double)dnew, p.s_new);
-                                const float d = (float)sqrt(__dadd_rn(__dadd_rn(__dmul_rn(t0, t0), u.a2), u.c2));
-                                p.sdf[off] = kind ? d : -d;
-                            } else {
-                                p.out0[off] = (int16_t)((dnew << 1) | kind);
-                                p.out1[off] = (int16_t)u.a;
-                            }
+                            // scipy: dt = (ft - indices) * sampling; sqrt(add.reduce(dt*dt, axis=0)) -- axis order z, y, x
+                            const double t0 = __dmul_rn((double)dnew, p.s_new);
+                            const float d = (float)sqrt(__dadd_rn(__dadd_rn(__dmul_rn(t0, t0), a2), c2));
+                            p.sdf[off] = K ? -d : d;          // distance to the nearest 0 (inside): +, to the nearest 1: -
+                        } else {
+                            p.out0[off] = (int16_t)((dnew << 1) | kind);
+                            p.out1[off] = (int16_t)ea;
                         }
                     }
                 }
                 ++uses;
                 if (bulk) __syncthreads();     // every thread is done with this stage: it may be refilled
             }
-            if (sweep == 0 && live) {
-                if (prev_kind >= 0 && n - 1 > run_start) {                       // end of the last run
-                    if (prev_kind) { const SdfEnv tmp = E0; E0 = E1; E1 = tmp; }
-                    sdf_push<NCOMP>(E0, n - 1, 0, 0, n, w_new, w0, w1);
-                    if (prev_kind) { const SdfEnv tmp = E0; E0 = E1; E1 = tmp; }
-                }
-                sdf_flush(E0);
-                sdf_flush(E1);
+            if (live && build) {
+                if (prev_kind == K && n - 1 > run_start) push(n - 1, 0, 0);       // end of the last run
+                if (k >= 0) *top = make_uint2((uint32_t)vk | ((uint32_t)bk << 16), ((uint32_t)ak & 0xffffu) | ((uint32_t)ck << 16));
             }
         }
     }
@@ -720,7 +684,7 @@ static int sdf_grid_blocks(int64_t n_lines)
     return (int)(want < cap ? want : cap);
 }
 
-static int64_t sdf_stack_bytes(int n, int64_t n_lines) { return a256(2 * (int64_t)n * sdf_grid_blocks(n_lines) * SDF_THREADS * 8); }
+static int64_t sdf_stack_bytes(int n, int64_t n_lines) { return a256((int64_t)n * sdf_grid_blocks(n_lines) * SDF_THREADS * 8); }
 
 static int sdf_bulk_ok(const void* a, const void* b, int64_t n_lines, int64_t inner, int64_t outer_stride, int64_t stride)
 {

@@ -15,6 +15,8 @@
 // disagree with them; only those are evaluated exactly.  All topology (cube cases, vertex ownership,
 // counts, ranks) is therefore pure bit arithmetic on a packed sign volume; float64 arithmetic in scipy's
 // exact summation order is spent only on the two end points of each cut edge (vertex interpolation).
+#include <stdlib.h>
+
 #include <cub/device/device_radix_sort.cuh>
 
 #include "t3d_field.cuh"
@@ -953,6 +955,156 @@ __global__ void __launch_bounds__(256) k_canon_zkeys(CanonS c)
     c.zval[i] = i;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Ordering of the z-edge vertices without a library sort.  They are emitted in raster order of their owning grid point,
+// so the vertices of one cube layer are contiguous: the (layer, z float) order is a SEGMENTED sort, one independent
+// segment per layer, by the 32-bit (or narrower) layer-relative z key alone.  One CTA per layer runs a stable LSD radix
+// sort (8-bit digits) over its segment, ping-ponging between two global buffers:
+//   count   : every warp histograms its contiguous sub-range of the segment into its own 256 shared-memory bins;
+//   offsets : digit-major exclusive scan over (digit, warp) -> where each warp's elements of each digit start;
+//   scatter : every warp walks its sub-range in order, 32 elements per step; lanes with equal digits find each other with
+//             match.any, rank themselves by lane order and advance the warp's offset for that digit -> stable.
+// Layers are independent (no grid-wide synchronisation, no library), a typical layer (a few thousand vertices) costs a few
+// microseconds and all layers run at once; keys are generated on the fly in pass 0.  The result is the permutation
+// k_canon_positions expects (zperm[rank in the z block] = index in the z block).
+// ------------------------------------------------------------------------------------------------
+#define ZS_WARPS 16
+#define ZS_THREADS (32 * ZS_WARPS)
+
+__device__ __forceinline__ uint32_t canon_zkey(const CanonS& c, uint32_t i, uint32_t nx, uint32_t ny, uint32_t gZ)
+{
+    if (i < gZ) return 0u;     // clamp group: ordered elsewhere (k_canon_gkeys); keep raster order here
+    const uint32_t raw = nx + ny + i;
+    const int k = (int)(c.vkeys[raw] >> 42);
+    uint32_t zk = float_key(c.verts[3 * (int64_t)raw]);
+    if (c.zkey_bits < 32) {
+        // relative to the layer's lower plane; anything outside the promised span saturates (and fails the order check)
+        const uint32_t base = float_key(plane_z(c, k));
+        zk = zk >= base ? zk - base : 0u;
+        const uint32_t lim = (1u << c.zkey_bits) - 1u;
+        zk = zk > lim ? lim : zk;
+    }
+    return zk;
+}
+
+// Stable LSD radix sort (8-bit digits) of ONE segment by ONE CTA of ZS_THREADS threads.  key_of(i) generates the key of
+// element i in pass 0 (keys are materialised in keyA); out[rank] = value_of(i).  keyA/keyB/idxA/idxB: the segment's slices
+// of the ping-pong buffers.  `passes` digits are sorted, least significant first.
+template <typename KeyT, typename KeyFn, typename ValFn>
+__device__ __forceinline__ void cta_radix_sort(uint32_t n, int passes, KeyFn key_of, ValFn value_of, KeyT* keyA, KeyT* keyB, uint32_t* idxA,
+                                               uint32_t* idxB, uint32_t* out)
+{
+    __shared__ uint32_t s_hist[ZS_WARPS][256];
+    __shared__ uint32_t s_tot[256];
+    __shared__ uint32_t s_carry[8];
+    const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
+    // contiguous sub-range of every warp, a multiple of 32 elements long
+    const uint32_t per = (((n + ZS_WARPS - 1) / ZS_WARPS) + 31u) & ~31u;
+    const uint32_t ws = min(n, (uint32_t)w * per), we = min(n, ws + per);
+    const KeyT* kin = keyA; const uint32_t* iin = idxA;
+    KeyT* kout = keyB; uint32_t* iout = idxB;
+    for (int p = 0; p < passes; ++p) {
+        const int shift = 8 * p;
+        const bool first = p == 0, last = p == passes - 1;
+        for (int i = tid; i < ZS_WARPS * 256; i += ZS_THREADS) (&s_hist[0][0])[i] = 0;
+        __syncthreads();
+        // ---- count (pass 0 also materialises the keys)
+        for (uint32_t i = ws + lane; i < we; i += 32) {
+            KeyT key;
+            if (first) { key = key_of(i); keyA[i] = key; }
+            else key = kin[i];
+            atomicAdd(&s_hist[w][(uint32_t)(key >> shift) & 255u], 1u);
+        }
+        __syncthreads();
+        // ---- offsets: digit-major exclusive scan over (digit, warp)
+        if (tid < 256) {
+            uint32_t t = 0;
+            for (int ww = 0; ww < ZS_WARPS; ++ww) t += s_hist[ww][tid];
+            s_tot[tid] = t;
+        }
+        __syncthreads();
+        if (tid < 256) {       // the first 8 warps: exclusive scan of the 256 digit totals (named barrier 1)
+            const uint32_t v = s_tot[tid];
+            const uint32_t incl = warp_incl_scan(v);
+            if (lane == 31) s_carry[w] = incl;
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            uint32_t carry = 0;
+            for (int ww = 0; ww < w; ++ww) carry += s_carry[ww];
+            uint32_t run = carry + incl - v;
+            for (int ww = 0; ww < ZS_WARPS; ++ww) { const uint32_t h = s_hist[ww][tid]; s_hist[ww][tid] = run; run += h; }
+        }
+        __syncthreads();
+        // ---- stable scatter
+        for (uint32_t i0 = ws; i0 < we; i0 += 32) {
+            const uint32_t i = i0 + lane;
+            const bool ok = i < we;
+            KeyT key = 0;
+            uint32_t idx = 0, d = 0xffffffffu;
+            if (ok) {
+                key = first ? keyA[i] : kin[i];
+                idx = first ? value_of(i) : iin[i];
+                d = (uint32_t)(key >> shift) & 255u;
+            }
+            const uint32_t peers = __match_any_sync(0xffffffffu, d);
+            const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
+            uint32_t pos = 0;
+            if (ok) pos = s_hist[w][d] + rank;
+            __syncwarp();
+            if (ok && rank == 0) s_hist[w][d] += __popc(peers);      // the lowest lane of each digit group advances the offset
+            __syncwarp();
+            if (ok) {
+                if (last) out[pos] = idx;
+                else { kout[pos] = key; iout[pos] = idx; }
+            }
+        }
+        __syncthreads();
+        // ping-pong (pass 0 read keyA / implicit values and wrote B)
+        const KeyT* tk = kin; const uint32_t* ti = iin;
+        kin = kout; iin = iout;
+        kout = (KeyT*)tk; iout = (uint32_t*)ti;
+    }
+}
+
+__global__ void __launch_bounds__(ZS_THREADS) k_zsort_layers(CanonS c, uint32_t* __restrict__ keyA, uint32_t* __restrict__ keyB,
+                                                            uint32_t* __restrict__ idxA, uint32_t* __restrict__ idxB,
+                                                            uint32_t* __restrict__ zperm)
+{
+    const uint32_t nx = (uint32_t)c.sizes[1], ny = (uint32_t)c.sizes[2], nz = (uint32_t)c.sizes[3];
+    if ((unsigned long long)nx + ny + nz > c.cap_verts || nz > c.cap_z) return;
+    const int layer = blockIdx.x;
+    uint32_t s = before_row<2>(c, (int64_t)layer * c.Hs), e = before_row<2>(c, (int64_t)(layer + 1) * c.Hs);
+    if (e > nz) e = nz;
+    if (s >= e) return;
+    const uint32_t n = e - s;
+    uint32_t gX, gY, gZ;
+    g0_sizes(c, gX, gY, gZ);
+    if (n == 1 || e <= gZ) {       // nothing to order (single vertex, or a layer of the clamp group)
+        for (uint32_t i = s + threadIdx.x; i < e; i += ZS_THREADS) zperm[i] = i;
+        return;
+    }
+    cta_radix_sort<uint32_t>(n, (c.zkey_bits + 7) / 8, [&](uint32_t i) { return canon_zkey(c, s + i, nx, ny, gZ); },
+                             [&](uint32_t i) { return s + i; }, keyA + s, keyB + s, idxA + s, idxB + s, zperm + s);
+}
+
+// the clamp group (vertices the z map clamps onto z = 0, see above): one CTA orders it by its 64-bit (y, x) key;
+// gperm[rank] = raw vertex id.  A group larger than cap_g0 is left alone (the order check then fails, the caller retries).
+__global__ void __launch_bounds__(ZS_THREADS) k_gsort(CanonS c, unsigned long long* __restrict__ keyA, unsigned long long* __restrict__ keyB,
+                                                     uint32_t* __restrict__ idxA, uint32_t* __restrict__ idxB, uint32_t* __restrict__ gperm)
+{
+    const uint32_t nx = (uint32_t)c.sizes[1], ny = (uint32_t)c.sizes[2], nz = (uint32_t)c.sizes[3];
+    if ((unsigned long long)nx + ny + nz > c.cap_verts) return;
+    uint32_t gX, gY, gZ;
+    g0_sizes(c, gX, gY, gZ);
+    const uint32_t n = gX + gY + gZ;
+    if (n == 0 || n > c.cap_g0) return;
+    auto raw_of = [&](uint32_t t) -> uint32_t { return t < gX ? t : t < gX + gY ? nx + (t - gX) : nx + ny + (t - gX - gY); };
+    if (n == 1) { if (threadIdx.x == 0) gperm[0] = raw_of(0); return; }
+    cta_radix_sort<unsigned long long>(n, 8, [&](uint32_t t) {
+        const float* v = c.verts + 3 * (int64_t)raw_of(t);
+        return ((unsigned long long)float_key(v[1]) << 32) | float_key(v[2]);
+    }, raw_of, keyA, keyB, idxA, idxB, gperm);
+}
+
 __global__ void __launch_bounds__(256) k_canon_gkeys(CanonS c)
 {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1030,7 +1182,9 @@ extern "C" int64_t t3d_canonicalize_structured_workspace_bytes(int64_t V, int64_
     b += align256(4 * V);                                                          // perm
     b += 2 * align256(4 * n);                                                      // flags, positions
     b += align256(4 * V);                                                          // newid
-    const int64_t tz = (int64_t)sort64_temp_bytes(cap_z > 0 ? cap_z : 1), tg = (int64_t)sort64_temp_bytes(cap_g0 > 0 ? cap_g0 : 1);
+    const int64_t tz = (int64_t)sort64_temp_bytes(cap_z > 0 ? cap_z : 1);
+    int64_t tg = (int64_t)sort64_temp_bytes(cap_g0 > 0 ? cap_g0 : 1);
+    if (tg < 4 * (int64_t)cap_g0 + 256) tg = 4 * (int64_t)cap_g0 + 256;     // k_gsort's second value buffer
     b += align256(tz > tg ? tz : tg);
     b += 2 * align256(t3d_scan_workspace_bytes(n, 1)) + 256;   // zero tail: unique descriptors, face-scan workspace, totals
     return b;
@@ -1093,7 +1247,9 @@ extern "C" int t3d_mesh_canonicalize_structured_dev(const void* verts_in, const 
     uint32_t* flags = (uint32_t*)ws; ws += align256(4 * n);
     uint32_t* pos = (uint32_t*)ws; ws += align256(4 * n);
     uint32_t* newid = (uint32_t*)ws; ws += align256(4 * V);
-    const size_t tz = sort64_temp_bytes(cap_z), tg = sort64_temp_bytes(cap_g0 > 0 ? cap_g0 : 1);
+    const size_t tz = sort64_temp_bytes(cap_z);
+    size_t tg = sort64_temp_bytes(cap_g0 > 0 ? cap_g0 : 1);
+    if (tg < 4 * (size_t)cap_g0 + 256) tg = 4 * (size_t)cap_g0 + 256;       // k_gsort's second value buffer
     void* temp = ws; ws += align256((int64_t)(tz > tg ? tz : tg));
     void* scan_ws = ws; ws += align256(t3d_scan_workspace_bytes(n, 1));
     void* scan_ws_f = ws; ws += align256(t3d_scan_workspace_bytes(n, 1));
@@ -1102,20 +1258,37 @@ extern "C" int t3d_mesh_canonicalize_structured_dev(const void* verts_in, const 
     c.zperm = zperm; c.gperm = gperm;
     c.n_g0_out = (unsigned long long*)n_g0_u64;
     if (phases & 1) {
-        k_canon_zkeys<<<(cap_z + 255) / 256, 256, 0, st>>>(c);
-        size_t tb = tz;
-        T3D_CUDA(cub::DeviceRadixSort::SortPairs(temp, tb, (const unsigned long long*)c.zkeys, zkeys_b, (const uint32_t*)c.zval, zperm,
-                                                 (int)cap_z, 0, zkey_bits + bits_for((unsigned)Zs + 1), st));
-        t3d_count_launches(2);
+        static const bool lib_sort = getenv("T3D_ZSORT_LIBRARY") != nullptr;     // A/B switch: the previous library radix sort
+        if (lib_sort) {
+            k_canon_zkeys<<<(cap_z + 255) / 256, 256, 0, st>>>(c);
+            size_t tb = tz;
+            T3D_CUDA(cub::DeviceRadixSort::SortPairs(temp, tb, (const unsigned long long*)c.zkeys, zkeys_b, (const uint32_t*)c.zval, zperm,
+                                                     (int)cap_z, 0, zkey_bits + bits_for((unsigned)Zs + 1), st));
+            t3d_count_launches(2);
+        } else {
+            // one CTA per cube layer: segmented stable radix sort of the layer's z-edge vertices (no library)
+            uint32_t* keyA = (uint32_t*)c.zkeys;
+            uint32_t* keyB = keyA + cap_z;
+            uint32_t* idxA = (uint32_t*)zkeys_b;
+            uint32_t* idxB = idxA + cap_z;
+            k_zsort_layers<<<Zs, ZS_THREADS, 0, st>>>(c, keyA, keyB, idxA, idxB, zperm);
+            t3d_count_launches(1);
+        }
     }
     if (phases & 2) {
         if (t3d_zero_async(counts + 2, 8, st)) return 1;
         if (cap_g0 > 0) {
-            // (shares the radix sort's temporary storage with the z sort: phase 2 must be ordered after phase 1)
-            k_canon_gkeys<<<(cap_g0 + 255) / 256, 256, 0, st>>>(c);
-            size_t tb = tg;
-            T3D_CUDA(cub::DeviceRadixSort::SortPairs(temp, tb, (const unsigned long long*)c.gkeys, gkeys_b, (const uint32_t*)c.gval, gperm,
-                                                     (int)cap_g0, 0, 64, st));
+            static const bool lib_sort = getenv("T3D_ZSORT_LIBRARY") != nullptr;
+            if (lib_sort) {
+                // (shares the radix sort's temporary storage with the z sort: phase 2 must be ordered after phase 1)
+                k_canon_gkeys<<<(cap_g0 + 255) / 256, 256, 0, st>>>(c);
+                size_t tb = tg;
+                T3D_CUDA(cub::DeviceRadixSort::SortPairs(temp, tb, (const unsigned long long*)c.gkeys, gkeys_b, (const uint32_t*)c.gval, gperm,
+                                                         (int)cap_g0, 0, 64, st));
+            } else {
+                // one CTA: stable radix sort of the clamp group by (y, x); gval / `temp` serve as the second value / key buffers
+                k_gsort<<<1, ZS_THREADS, 0, st>>>(c, c.gkeys, gkeys_b, c.gval, (uint32_t*)temp, gperm);
+            }
         }
         k_canon_positions<<<(unsigned)((V + 255) / 256), 256, 0, st>>>(c);
         if (canonical_tail(c.verts, c.perm, V, (const unsigned long long*)V_dev_u64, faces_in, F, (const unsigned long long*)F_dev_u64,

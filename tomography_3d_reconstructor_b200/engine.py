@@ -423,18 +423,32 @@ def mask_source(mask_images):
             raise ValueError("expected a (Z,H,W) stack")
         Z, H, W = (int(v) for v in mask_images.shape)
         return mask_images, Z, H, W, _is_pinned_stack(mask_images)
-    # a list whose slices already lie back to back in memory is one array (e.g. views of a pinned stack)
-    first = np.asarray(mask_images[0])
+    # a list whose slices already lie back to back in memory is one array (e.g. views of a pinned stack): one pass over the
+    # list (this runs per call on the host: ~1 us per slice)
+    first = mask_images[0]
+    if not isinstance(first, np.ndarray):
+        first = np.asarray(first)
     if first.ndim != 2:
         raise ValueError("expected a list of (H,W) masks")
     n = len(mask_images)
-    if first.flags.c_contiguous and first.dtype.itemsize == 1:
-        step, base = first.nbytes, first.__array_interface__["data"][0]
-        if all(isinstance(m, np.ndarray) and m.shape == first.shape and m.dtype == first.dtype and m.flags.c_contiguous
-               and m.__array_interface__["data"][0] == base + k * step for k, m in enumerate(mask_images)):
-            arr = _as_stack(mask_images)
-            return arr, n, int(first.shape[0]), int(first.shape[1]), _is_pinned_stack(arr)
-    return mask_images, n, int(first.shape[0]), int(first.shape[1]), False
+    H, W = int(first.shape[0]), int(first.shape[1])
+    base_obj = first.base
+    if (first.flags.c_contiguous and first.dtype.itemsize == 1 and isinstance(base_obj, np.ndarray) and base_obj.ndim == 3
+            and base_obj.shape == (n, H, W) and base_obj.flags.c_contiguous and base_obj.dtype == first.dtype):
+        # views of one (n,H,W) array: in order iff every slice sits at its own offset
+        step, addr = first.nbytes, first.ctypes.data
+        if addr == base_obj.ctypes.data:
+            ok = True
+            for k in range(1, n):
+                m = mask_images[k]
+                if m.base is not base_obj or m.shape != first.shape or m.ctypes.data != addr + k * step:
+                    ok = False
+                    break
+            if ok:
+                arr = base_obj.view(np.uint8) if base_obj.dtype == np.bool_ else base_obj
+                if arr.dtype == np.uint8:
+                    return arr, n, H, W, _is_pinned_stack(arr)
+    return mask_images, n, H, W, False
 
 
 def upload_masks(mask_images, out: Optional[torch.Tensor] = None, chunk_planes: int = 32) -> torch.Tensor:
@@ -793,13 +807,22 @@ def extract_surface(dv: DeviceVolume, slice_depths, mm_per_pixel_y, mm_per_pixel
     if not canonical:
         return DeviceMesh(verts, faces, n_ambiguous, n_exact)
     if canonical == "async":
-        v2, f2, counts = canonicalize(verts, faces, sync=False, fast=True)
+        unpad = 1 if (manifold and field is None) else 0
+        res = canonicalize_structured(verts, vkeys, faces, (n_active, nX, nY, nZ, nT), (Zs, Hs, Ws), chunkbase, aw_base, n_active,
+                                      z_offset, unpad, cum_d, adj_d, n_cum, zkey_bits(slice_depths, add_padding, Zs, z_offset, unpad),
+                                      sync=False)
+        v2, f2, counts = res if res is not None else canonicalize(verts, faces, sync=False, fast=True)
         mark("canonicalize")
         m = DeviceMesh(v2, f2, n_ambiguous, n_exact, counts_dev=counts)
         m.raw = (verts, faces)
         m.n_active, m.n_raw, m.n_z = n_active, (V, nT), nZ
         return m
-    v2, f2 = canonicalize(verts, faces, fast=True)
+    # structured ordering (no global sort: x-edge vertices are in place, y-edge vertices ranked per row gap, z-edge vertices
+    # ordered per cube layer); the generic sort-based path only if its device-side order check fails
+    unpad = 1 if (manifold and field is None) else 0
+    res = canonicalize_structured(verts, vkeys, faces, (n_active, nX, nY, nZ, nT), (Zs, Hs, Ws), chunkbase, aw_base, n_active,
+                                  z_offset, unpad, cum_d, adj_d, n_cum, zkey_bits(slice_depths, add_padding, Zs, z_offset, unpad))
+    v2, f2 = res if res is not None else canonicalize(verts, faces, fast=True)
     mark("canonicalize")
     m = DeviceMesh(v2, f2, n_ambiguous, n_exact)
     m.n_active, m.n_raw, m.n_z = n_active, (V, nT), nZ
@@ -834,6 +857,43 @@ def canonicalize(verts: torch.Tensor, faces_i32: torch.Tensor, faces_i64: bool =
     if bad:
         return canonicalize(verts, faces_i32, faces_i64, True, False)
     return vout[:v2], fout[:f2]
+
+
+def canonicalize_structured(verts, vkeys, faces_i32, sizes, sign_dims, chunkbase, aw_base, aw_stride, z_offset, unpad_shift, cum_d,
+                            adj_d, n_cum, zkey_bits_, sync: bool = True):
+    """_ensure_manifold_mesh for a mesh straight out of t3d_mc_emit (t3d_mesh_canonicalize_structured_dev).
+    sync=True: returns (verts, int64 faces) or None when the structured order could not be verified (the caller then sorts
+    generically); the clamp group (vertices under slice 0) is provisioned on a second attempt when the first one reports it.
+    sync=False: one attempt, returns capacity-sized (verts, faces, device counts (V', F', unverified flag))."""
+    import os
+    if os.environ.get("T3D_NO_STRUCTURED"):
+        return None
+    L = _L()
+    n_active, nX, nY, nZ, nT = (int(v) for v in sizes)
+    V = nX + nY + nZ
+    Zs, Hs, Ws = sign_dims
+    dev = verts.device
+    sizes_d = torch.tensor([n_active, nX, nY, nZ, nT, V], dtype=torch.int64, device=dev)
+    vout = torch.empty((V, 3), dtype=torch.float32, device=dev)
+    fout = torch.empty((nT, 3), dtype=torch.int64, device=dev)
+    counts = torch.zeros(4, dtype=torch.int64, device=dev)
+    cap_z, cap_g0 = max(nZ, 1), 0
+    for _attempt in range(2):
+        ws = torch.zeros(int(L.t3d_canonicalize_structured_workspace_bytes(V, nT, cap_z, cap_g0, Zs)) // 8 + 1, dtype=torch.int64, device=dev)
+        check(L.t3d_mesh_canonicalize_structured_dev(
+            _p(verts), _p(vkeys), V, _p(sizes_d), _p(sizes_d[5:]), Zs, Hs, Ws, _p(chunkbase), _p(aw_base), int(aw_stride), int(z_offset),
+            int(unpad_shift), _p(cum_d), _p(adj_d), int(n_cum), int(zkey_bits_), cap_z, cap_g0, _p(faces_i32), nT, _p(sizes_d[4:]),
+            _p(vout), _p(fout), None, _p(counts), _p(counts[3:]), _p(ws), 3, _stream()), "t3d_mesh_canonicalize_structured_dev")
+        if not sync:
+            return vout, fout, counts[:3]
+        v2, f2, bad, n_g0 = (int(c) for c in counts.cpu().tolist())
+        if not bad:
+            return vout[:v2], fout[:f2]
+        if n_g0 > cap_g0:
+            cap_g0 = n_g0 + 16
+            continue
+        break
+    return None
 
 
 def mesh_measure_async(verts: torch.Tensor, faces: torch.Tensor) -> torch.Tensor:

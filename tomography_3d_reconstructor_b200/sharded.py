@@ -32,11 +32,74 @@ HALO = 8          # bit-planes exchanged per side
 SURF_HALO = 3     # smoothed planes the surface stage needs beyond the owned ones
 
 
+_partitions: Dict = {}      # (Z, world) -> [(z0, z1)] set by set_partition(); every rank must set the same one
+
+
 def slab_range(Z: int, rank: int, world: int) -> Tuple[int, int]:
-    """Contiguous, balanced slice range [z0, z1) of `rank`."""
+    """Contiguous slice range [z0, z1) of `rank`: the registered partition of this (Z, world), else equal slices."""
+    part = _partitions.get((int(Z), int(world)))
+    if part is not None:
+        return part[rank]
     base, rem = divmod(Z, world)
     z0 = rank * base + min(rank, rem)
     return z0, z0 + base + (1 if rank < rem else 0)
+
+
+def balanced_ranges(per_slice_cost, world: int, min_slices: int = 8) -> List[Tuple[int, int]]:
+    """Contiguous z-slabs of (nearly) equal summed cost.  Equal slice counts give equal voxel work but not equal surface
+    work: the slabs that hold the polar caps of an object carry less mesh than the ones through its equator, and the
+    step ends with a collective, so every rank waits for the heaviest slab.  per_slice_cost[z] = estimated cost of slice z
+    (e.g. slice_cost()).  Every slab gets at least `min_slices` slices (the halo width)."""
+    c = np.asarray(per_slice_cost, dtype=np.float64)
+    Z = len(c)
+    if Z < world * min_slices:
+        raise ValueError("stack too thin for %d slabs of at least %d slices" % (world, min_slices))
+    cum = np.concatenate([[0.0], np.cumsum(c)])
+    cuts = [0]
+    for r in range(1, world):
+        target = cum[-1] * r / world
+        z = int(np.searchsorted(cum, target))
+        if z > 0 and abs(cum[z - 1] - target) <= abs(cum[min(z, Z)] - target):
+            z -= 1
+        z = max(z, cuts[-1] + min_slices)
+        z = min(z, Z - (world - r) * min_slices)
+        cuts.append(z)
+    cuts.append(Z)
+    return [(cuts[r], cuts[r + 1]) for r in range(world)]
+
+
+def set_partition(Z: int, world: int, ranges) -> None:
+    """Register the z-slab partition of a (Z, world) job (None: back to equal slices).  Collective by convention: all ranks
+    must register the same ranges before the next step; plans built for another partition are dropped."""
+    key = (int(Z), int(world))
+    if ranges is None:
+        _partitions.pop(key, None)
+    else:
+        ranges = [(int(a), int(b)) for a, b in ranges]
+        if len(ranges) != world or ranges[0][0] != 0 or ranges[-1][1] != Z or any(ranges[r][1] != ranges[r + 1][0] for r in range(world - 1)):
+            raise ValueError("ranges must tile [0, Z) in rank order")
+        _partitions[key] = ranges
+    _slab_plans.clear()
+    _slab_hints.clear()
+
+
+def slice_cost(vertices_per_slice, slice_equivalent_vertices: float = 2900.0) -> np.ndarray:
+    """Cost model of one slice for balanced_ranges(): the volume passes cost the same for every slice (about as much as
+    ~2900 mesh vertices at 1024x1024: 0.35 ms / 512 slices against 0.5 ms / 2.06 M vertices), the surface passes scale
+    with the vertices the slice contributes."""
+    return slice_equivalent_vertices + np.asarray(vertices_per_slice, dtype=np.float64)
+
+
+def vertices_per_slice(res: Dict, Zg: int, add_padding: bool = True) -> np.ndarray:
+    """Vertices of this rank's slab of the stitched mesh (result dict of reconstruct*) per global slice index, as a length-Zg
+    histogram: a vertex with z between the map values of planes k and k+1 belongs to slice k (learning step only)."""
+    depths = res["slice_depths"]
+    cum, adj = engine.z_map_arrays(depths, add_padding)
+    knots = np.array([z_map_value(k, cum, adj) for k in range(Zg + 1)], dtype=np.float64)
+    vz = res["verts"][:, 0].double()
+    idx = torch.bucketize(vz, torch.from_numpy(knots).to(vz.device), right=True) - 1
+    idx = idx.clamp_(0, Zg - 1)
+    return torch.bincount(idx, minlength=Zg).cpu().numpy().astype(np.float64)
 
 
 def owned_padded_planes(Zg: int, z0: int, z1: int, pad: int = 1) -> Tuple[int, int]:
@@ -454,6 +517,94 @@ def reconstruct_host(masks_host: np.ndarray, Zg: int, z0: int, threshold: int, s
     hf.copy_(f, non_blocking=True)
     torch.cuda.current_stream().synchronize()
     out["vertices_host"], out["faces_host"] = hv.numpy(), hf.numpy()
+    return out
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# bit-packed host input (additive API): 1 bit per voxel over PCIe instead of 1 byte
+# ----------------------------------------------------------------------------------------------------------------
+def pack_bits_host(mask_images) -> np.ndarray:
+    """(Z,H,W) bool / 0-1 masks (array or list) -> the library's packed layout on the host: uint32 (Z,H,words_per_row(W)), bit i of
+    word w = voxel x = 32*w + i, zero beyond W.  For callers whose masks already live packed (or that can pack while decoding)."""
+    a = engine._as_stack(mask_images)
+    Z, H, W = a.shape
+    wpr = engine.words_per_row(W)
+    out = np.zeros((Z, H, wpr * 4), dtype=np.uint8)
+    out[:, :, :(W + 7) // 8] = np.packbits(a != 0, axis=-1, bitorder="little")
+    return out.view("<u4")
+
+
+_bits_plans: Dict = {}
+
+
+def reconstruct_host_bits(bits_host: np.ndarray, W: int, side_counts, total_depth_mm: float, x_length_mm: float, y_length_mm: float,
+                          iterations: int = 3, add_padding: bool = True, use_graph: bool = True) -> Dict:
+    """pipeline.reconstruct_host for masks that are already bit-packed on the host (pack_bits_host layout; ideally pinned):
+    the upload is W/8 bytes per row instead of W -- the host->device copy is what bounds reconstruct_host (537 MB of the
+    14 ms at 512 x 1024 x 1024).  Same results (out["vertices"], out["faces"], volumes)."""
+    b = np.ascontiguousarray(bits_host)
+    if b.dtype.itemsize != 4 or b.ndim != 3 or b.shape[2] != engine.words_per_row(W):
+        raise ValueError("bits_host must be (Z, H, words_per_row(W)) 32-bit words")
+    Z, H = int(b.shape[0]), int(b.shape[1])
+    dev = engine._require_cuda()
+    L = engine._L()
+    key = (Z, H, int(W), tuple(side_counts), float(total_depth_mm), float(x_length_mm), float(y_length_mm), int(iterations),
+           bool(add_padding), torch.cuda.current_device())
+    src = torch.from_numpy(b.view(np.int32))
+    st = _bits_plans.get(key)
+    if st is None:
+        # learning step: unpack on the device and run the staged path once for the mesh sizes
+        bits_d = src.to(dev)
+        u8 = torch.empty((Z, H, W), dtype=torch.uint8, device=dev)
+        engine.check(L.t3d_unpack_bits(engine._p(bits_d), Z, H, W, engine._p(u8), engine._stream()), "t3d_unpack_bits")
+        out = pipeline.reconstruct(u8, 1, side_counts, total_depth_mm, x_length_mm, y_length_mm, iterations, True, add_padding)
+        m = out["mesh"]
+        caps = pipeline._caps_from(m.n_active, *m.n_raw, m.n_z)
+        plan = FusedSlabPlan(Z, H, W, Z, 0, 1, side_counts, total_depth_mm, x_length_mm, y_length_mm, iterations, add_padding,
+                             pipeline._tuned_caps(("bits",) + key, caps), dev, 0, 1)
+        st = _bits_plans[key] = {"plan": plan, "graph": None}
+        out["vertices"], out["faces"] = engine.download(m.verts), engine.download(m.faces)
+        return out
+    plan = st["plan"]
+
+    def enqueue():
+        p = engine._p
+        if Z >= 1:
+            ends = [0] if Z == 1 else [0, Z - 1]
+            for e in ends:
+                engine.check(L.t3d_fill_holes_2d(p(plan.ext[e]), 1, 0, H, W, p(plan.fill), engine._stream()), "t3d_fill_holes_2d")
+        plan.compute()
+        plan.gathered[0].copy_(plan.res)
+        plan.host.copy_(plan.gathered, non_blocking=True)
+
+    plan.ext.copy_(src, non_blocking=True)
+    if use_graph:
+        if st["graph"] is None:
+            enqueue()
+            torch.cuda.current_stream().synchronize()
+            plan.ext.copy_(src, non_blocking=True)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                enqueue()
+            st["graph"] = g
+        st["graph"].replay()
+    else:
+        enqueue()
+    torch.cuda.current_stream().synchronize()
+    h = plan.host_np
+    R = pipeline
+    if h[0, R.R_OVERFLOW] or h[0, R.R_UNVERIFIED] or h[0, R.R_NT] == 0:
+        _bits_plans.pop(key, None)          # sizes changed beyond the margin (or an unverifiable ordering): learn again
+        return reconstruct_host_bits(bits_host, W, side_counts, total_depth_mm, x_length_mm, y_length_mm, iterations, add_padding,
+                                     use_graph)
+    out = assemble(plan, h)
+    v, f = out["verts"].contiguous(), out["faces"].contiguous()
+    hv = torch.empty(v.shape, dtype=v.dtype, pin_memory=True)
+    hf = torch.empty(f.shape, dtype=f.dtype, pin_memory=True)
+    hv.copy_(v, non_blocking=True)
+    hf.copy_(f, non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    out["vertices"], out["faces"] = hv.numpy(), hf.numpy()
     return out
 
 

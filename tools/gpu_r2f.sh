@@ -32,7 +32,7 @@ for (Z, H, W) in shapes:
 PY
 python /tmp/sdf_time.py > gpurun_out/r2f_sdf.log 2>&1; cat gpurun_out/r2f_sdf.log
 T3D_SDF_NO_BULK=1 python /tmp/sdf_time.py > gpurun_out/r2f_sdf_nobulk.log 2>&1; echo "--- no bulk"; cat gpurun_out/r2f_sdf_nobulk.log
-ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,sm__throughput.avg.pct_of_peak_sustained_elapsed,sm__warps_active.avg.pct_of_peak_sustained_active --clock-control none -k regex:k_sdf -c 12 --csv --log-file gpurun_out/r2f_sdf_ncu.csv python /tmp/sdf_time.py c1 > /dev/null 2>&1
+ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,smsp__inst_executed.sum,smsp__issue_active.avg.pct_of_peak_sustained_active,sm__throughput.avg.pct_of_peak_sustained_elapsed,sm__warps_active.avg.pct_of_peak_sustained_active --clock-control none -k regex:k_sdf -c 12 --csv --log-file gpurun_out/r2f_sdf_ncu.csv python /tmp/sdf_time.py c1 > /dev/null 2>&1
 python - <<'PY'
 import csv
 rows=[r for r in csv.DictReader(l for l in open("gpurun_out/r2f_sdf_ncu.csv") if not l.startswith("=="))]
