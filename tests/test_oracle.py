@@ -199,10 +199,11 @@ def test_config0_real_generator_stack_known_answer(oracle):
 
 
 def _closed_oriented(v, f):
+    """Every directed edge exactly once and its twin present: closed, oriented, no edge with more than two triangles."""
     e = np.concatenate([f[:, [0, 1]], f[:, [1, 2]], f[:, [2, 0]]]).astype(np.int64)
     key = e[:, 0] * (len(v) + 1) + e[:, 1]
     rev = e[:, 1] * (len(v) + 1) + e[:, 0]
-    return np.array_equal(np.sort(key), np.sort(rev))
+    return len(np.unique(key)) == len(key) and np.array_equal(np.sort(key), np.sort(rev))
 
 
 def test_face_test_is_the_asymptotic_decider(oracle):

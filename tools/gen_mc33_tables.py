@@ -21,7 +21,9 @@ For every cube index with an ambiguous face (or case 4) and every outcome of the
     13.5): the two loops bounding the tunnel are joined by a triangle strip (m + n triangles, see tube()), other loops
     get disks.
     No additional (centre) vertex is used anywhere: Lewiner's 13th vertex (sub-cases 6.1.2, 7.3, 10.2, 12.2, 13.3, 13.4)
-    is the known deviation -- same topology, different triangle count in those sub-cases.
+    is the known deviation -- same topology, different triangle count in those sub-cases.  Where a triangulation without
+    a diagonal inside a cube face does not exist, only diagonals owned by this cube are used (diagonal_allowed), which keeps
+    the mesh free of edges with more than two triangles.
 
 Outputs (identical tables, separately stored so that the CPU oracle does not include product sources):
     tomography_3d_reconstructor_b200/csrc/mc33_tables.h     (+ per-index decision metadata for the kernels)
@@ -164,6 +166,32 @@ def same_face(a, b):
     return any(all(c in FACE_CYCLE[f] for c in EDGES[a] + EDGES[b]) for f in range(6))
 
 
+def face_label(f, e):
+    """Face-local label of cube edge e lying in face f, the same for the two cubes that share the face: 0 / 1 = the edge runs
+    along the first in-face axis at the low / high end of the second, 2 / 3 = along the second axis at the low / high end of
+    the first."""
+    ax, _val = FACES[f]
+    u, w = [a for a in range(3) if a != ax]
+    pa, pb = CORN[EDGES[e][0]], CORN[EDGES[e][1]]
+    return pa[w] if pa[u] != pb[u] else 2 + pa[u]
+
+
+def diagonal_allowed(a, b):
+    """A mesh edge between two vertices of one cube face that is not a boundary segment runs INSIDE that face.  Two cubes
+    share the face; if both used the same such diagonal the mesh edge would carry four triangles.  Ownership rule: a
+    diagonal joining OPPOSITE edges of the face belongs to the cube on the LOW side of the face (the one that sees it as its
+    x=1 / y=1 / z=1 face), a diagonal joining ADJACENT edges to the cube on the high side.  Of the 64 possible assignments
+    of the six kinds of diagonal, four let every loop and every tunnel of every sub-case be triangulated with owned
+    diagonals only (exhaustive search; this is one of them), so no mesh edge is ever used by more than two triangles --
+    without Lewiner's 13th vertex.  The generator asserts it, tools/validate_mc33.py re-checks it independently."""
+    for f in range(6):
+        if all(c in FACE_CYCLE[f] for c in EDGES[a] + EDGES[b]):
+            low_side_owns = (face_label(f, a) < 2) == (face_label(f, b) < 2)
+            if low_side_owns != (FACES[f][1] == 1):
+                return False
+    return True
+
+
 def dist2(a, b):
     return sum((p - q) ** 2 for p, q in zip(mid2(a), mid2(b)))
 
@@ -185,17 +213,20 @@ def disk(loop):
     """Triangulation of the loop (v0 = lowest edge id) without additional vertices.  A diagonal joining two loop vertices
     that lie in one cube face would run inside that face: such diagonals are avoided where a triangulation without them
     exists (it does not for the 9-loops of 7.3 / 13.3, the 8-loops of 10.2 and the 12-loops of 13.4 -- the sub-cases
-    where Lewiner inserts a 13th vertex); cost = (face diagonals, summed squared diagonal length), first minimum in
-    enumeration order.  Returns (triangles, number of face diagonals)."""
+    where Lewiner inserts a 13th vertex) and otherwise restricted to the diagonals this cube OWNS (diagonal_allowed: the
+    neighbour across the face can never use the same one); cost = (diagonals not owned [always 0], face diagonals, summed
+    squared diagonal length), first minimum in enumeration order.  Returns (triangles, number of face diagonals)."""
     n = len(loop)
     best = None
     for tr in polygon_triangulations(n):
         chords = {(min(p, q), max(p, q)) for t in tr for p, q in ((t[0], t[1]), (t[1], t[2]), (t[0], t[2]))
                   if (q - p) % n not in (1, n - 1)}
-        cost = (sum(same_face(loop[p], loop[q]) for p, q in chords), sum(dist2(loop[p], loop[q]) for p, q in chords))
+        cost = (sum(not diagonal_allowed(loop[p], loop[q]) for p, q in chords), sum(same_face(loop[p], loop[q]) for p, q in chords),
+                sum(dist2(loop[p], loop[q]) for p, q in chords))
         if best is None or cost < best[0]:
             best = (cost, tr)
-    (bad, _), tr = best
+    (forbidden, bad, _), tr = best
+    assert forbidden == 0, loop
     # every triangle (i, k, j) with i < k < j follows the loop direction
     return [(loop[i], loop[k], loop[j]) for (i, k, j) in tr], bad
 
@@ -224,10 +255,12 @@ def tube(A, B):
                 inner = {(min(d), max(d)) for d in directed if d not in on_a and d not in on_b}
                 if any((d[1], d[0]) in on_a or (d[1], d[0]) in on_b for d in directed):
                     continue                   # a boundary edge used backwards
-                cost = (sum(same_face(p, q) for p, q in inner), sum(dist2(p, q) for p, q in inner))
+                cost = (sum(not diagonal_allowed(p, q) for p, q in inner), sum(same_face(p, q) for p, q in inner),
+                        sum(dist2(p, q) for p, q in inner))
                 if best is None or cost < best[0]:
                     best = (cost, tris)
-    return best[1], best[0][0]
+    assert best[0][0] == 0, (A, B)
+    return best[1], best[0][1]
 
 
 def classify(idx):

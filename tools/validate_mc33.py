@@ -7,8 +7,9 @@ extended entry, every outcome J of the face tests and both values of the tunnel 
   1. built from all and only the sign-changing cube edges, no degenerate triangle;
   2. an oriented 2-manifold patch: every directed mesh edge at most once, every edge without a twin lies in a cube face
      (it is a boundary edge), all others have their twin.  An INTERIOR edge lying in a cube face (a diagonal between two
-     vertices of one face) is a blemish that cannot be avoided without Lewiner's 13th vertex in sub-cases 7.3, 7.4.2,
-     10.1.2 / 12.1.2, 10.2, 13.3, 13.4: such rows are counted ("face_diagonal_rows", pinned by tests/test_mc_table.py);
+     vertices of one face) cannot be avoided without Lewiner's 13th vertex in sub-cases 7.3, 7.4.2, 10.1.2 / 12.1.2, 10.2,
+     13.3, 13.4: such rows are counted ("face_diagonal_rows", pinned by tests/test_mc_table.py) and must obey the ownership
+     rule (owns_face_diagonal) that keeps two neighbouring cubes from ever using the same diagonal;
   3. bounded exactly by the face polylines (index, J) prescribe: on an ambiguous face whose positive corners are joined
      (bit of J set) the two boundary segments cut off the two NEGATIVE corners, otherwise the two POSITIVE corners -- this
      is what makes two cubes sharing a face agree (the face test only sees the four shared corner values);
@@ -72,6 +73,18 @@ def face_of_edge_pair(a, b):
     return None
 
 
+def owns_face_diagonal(a, b, f):
+    """Ownership of a diagonal inside face f (written independently of the generator): classify the two cube edges by their
+    direction inside the face; a diagonal between two PARALLEL (opposite) edges belongs to the cube that has the face on
+    its high side (x=1 / y=1 / z=1), a diagonal between two PERPENDICULAR (adjacent) edges to the cube that has it on its
+    low side."""
+    ax, v = FACE[f]
+    da = np.abs(P[E[a][0]] - P[E[a][1]])
+    db = np.abs(P[E[b][0]] - P[E[b][1]])
+    parallel = bool((da == db).all())
+    return parallel == (v == 1)
+
+
 def ambiguous_faces(idx):
     out = []
     for f, (ax, v) in enumerate(FACE):
@@ -103,7 +116,11 @@ def check_row(idx, faces, Jbits, tunnel_expected, tris, ref_side):
         f = face_of_edge_pair(a, b)
         twin = (b, a) in directed
         if f is not None and twin:
-            ref_side["face_diagonal"] = True     # tolerated where unavoidable without a 13th vertex; counted by validate()
+            # an interior edge inside a cube face: tolerated where unavoidable without a 13th vertex, but only if THIS cube owns
+            # the diagonal (the neighbour across the face then cannot use it: no mesh edge with four triangles)
+            if not owns_face_diagonal(a, b, f):
+                return "edge %d-%d runs inside face %d, which this cube does not own for that diagonal" % (a, b, f)
+            ref_side["face_diagonal"] = True
             continue
         if f is None and not twin:
             return "interior edge %d-%d has no twin" % (a, b)
