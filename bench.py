@@ -500,7 +500,7 @@ def run_ours(args, Z, H, W, cfg):
 
         sink = io.StringIO()
         with contextlib.redirect_stdout(sink):
-            for _ in range(2):
+            for _ in range(4):      # (the first calls also populate torch's pinned-host allocator cache: 3 x 537 MB blocks)
                 out = api_step()
             n_e2e = max(2, min(args.steps, 5))
             torch.cuda.synchronize()

@@ -308,18 +308,20 @@ __global__ void __launch_bounds__(128) k_mc_words(Grid g, McField fld, const uin
     const int w = (int)(i - row * (uint32_t)g.nws);
     int z, y;
     const WordMasks m = load_masks(g, row, w, z, y);
-    uint32_t nt = 0, na = 0;
-    for (uint32_t a = m.act; a;) {
+    uint32_t nt = 0, na = 0, ambmask = 0;
+    for (uint32_t a = m.act; a;) {        // branch-free common loop: classic triangle counts, ambiguous cubes only noted
+        const int b = __ffs(a) - 1;
+        a &= a - 1;
+        const uint32_t n = c_luts.ntri[cube_case(m, b)];
+        nt += n & 0x7fu;
+        ambmask |= (n >> 7) << b;
+    }
+    for (uint32_t a = ambmask; a;) {      // rare: replace the classic count by the count of the row Lewiner's tests select
         const int b = __ffs(a) - 1;
         a &= a - 1;
         const int cs = cube_case(m, b);
-        const uint32_t n = c_luts.ntri[cs];
-        if (n & MC_AMB) {     // resolved per cube with Lewiner's face / interior tests (rare)
-            nt += g33_ntri[mc33_resolve(fld, z, y, (w << 5) + b, cs)];
-            ++na;
-        } else {
-            nt += n;
-        }
+        nt += g33_ntri[mc33_resolve(fld, z, y, (w << 5) + b, cs)] - (c_luts.ntri[cs] & 0x7fu);
+        ++na;
     }
     aw_cnt[k] = __popc(m.X00);
     aw_cnt[(int64_t)n_active + k] = __popc(m.Y0);
@@ -449,30 +451,22 @@ __global__ void __launch_bounds__(128) k_mc_emit(EmitArgs a)
     s_next[0][tid] = nY0; s_next[1][tid] = nY1; s_next[2][tid] = nZ0; s_next[3][tid] = nZ1;
     // (each thread reads back only its own column: no barrier needed)
 
+    // does this word hold a cube with an ambiguous index?  (word-level split: the common loop below carries no call)
+    uint32_t ambmask = 0;
     for (uint32_t q = m.act; q;) {
         const int b = __ffs(q) - 1;
         q &= q - 1;
-        const int cs = cube_case(m, b);
-        const uint32_t lb = lt_mask(b), lb1 = lt_mask(b + 1);
-        const bool last = (b == 31);
-        auto vertex_id = [&](int e) -> uint32_t {
-            const uint32_t at_next = (0x622u >> e) & 1u;           // edges 1, 5, 9, 10 sit at x + 1
-            uint32_t id = s_base[e][tid] + __popc(s_mask[e][tid] & (at_next ? lb1 : lb));
-            if (last && at_next) id = s_next[((e >> 2) & 1) + 2 * ((e >> 3) & 1) + ((e >> 3) & 1) * ((e >> 1) & 1)][tid];
-            return id;
-        };
-        const int4 trow = *reinterpret_cast<const int4*>(s_tri[cs]);   // 16 edge ids, -1 terminated; byte 15 = -2: ambiguous index
-        if ((int8_t)((uint32_t)trow.w >> 24) == -2) {     // the row Lewiner's tests select (same decision as in k_mc_words)
-            const int r = mc33_resolve(a.fld, z, y, x0 + b, cs);
-            const int8_t* row = g33_rows[r];
-            const int n3 = 3 * (int)g33_ntri[r];
-            for (int t = 0; t < n3; t += 3) {
-                int32_t* f = a.faces + 3 * (int64_t)pT;
-                f[0] = (int32_t)vertex_id(row[t + 2]); f[1] = (int32_t)vertex_id(row[t + 1]); f[2] = (int32_t)vertex_id(row[t]);
-                ++pT;
-            }
-            continue;
-        }
+        ambmask |= (uint32_t)((uint8_t)s_tri[cube_case(m, b)][T3D_MC_ROW - 1] == 0xfeu) << b;     // byte 15 = -2: ambiguous index
+    }
+    // corner -> vertex id of the cube at bit b, through the per-thread tables above
+    auto vertex_id = [&](int b, int e) -> uint32_t {
+        const uint32_t at_next = (0x622u >> e) & 1u;           // edges 1, 5, 9, 10 sit at x + 1
+        uint32_t id = s_base[e][tid] + __popc(s_mask[e][tid] & (at_next ? lt_mask(b + 1) : lt_mask(b)));
+        if (b == 31 && at_next) id = s_next[((e >> 2) & 1) + 2 * ((e >> 3) & 1) + ((e >> 3) & 1) * ((e >> 1) & 1)][tid];
+        return id;
+    };
+    auto emit_classic = [&](int b, int cs) {
+        const int4 trow = *reinterpret_cast<const int4*>(s_tri[cs]);   // 16 edge ids, -1 terminated
         const uint32_t tw[4] = {(uint32_t)trow.x, (uint32_t)trow.y, (uint32_t)trow.z, (uint32_t)trow.w};
         auto edge_at = [&](int t) -> int { return (int)(int8_t)((tw[t >> 2] >> ((t & 3) * 8)) & 0xffu); };
         for (int t = 0; t < 15; t += 3) {
@@ -480,9 +474,32 @@ __global__ void __launch_bounds__(128) k_mc_emit(EmitArgs a)
             if (e0 < 0) break;
             uint32_t vid[3];
 #pragma unroll
-            for (int c = 0; c < 3; ++c) vid[c] = vertex_id((c == 0) ? e0 : edge_at(t + c));
+            for (int c = 0; c < 3; ++c) vid[c] = vertex_id(b, (c == 0) ? e0 : edge_at(t + c));
             int32_t* f = a.faces + 3 * (int64_t)pT;
             f[0] = (int32_t)vid[2]; f[1] = (int32_t)vid[1]; f[2] = (int32_t)vid[0];
+            ++pT;
+        }
+    };
+    if (!ambmask) {                       // the common word: no call, no extra test inside the loop
+        for (uint32_t q = m.act; q;) {
+            const int b = __ffs(q) - 1;
+            q &= q - 1;
+            emit_classic(b, cube_case(m, b));
+        }
+        return;
+    }
+    for (uint32_t q = m.act; q;) {        // a word with at least one ambiguous cube
+        const int b = __ffs(q) - 1;
+        q &= q - 1;
+        const int cs = cube_case(m, b);
+        if (!((ambmask >> b) & 1u)) { emit_classic(b, cs); continue; }
+        // the row Lewiner's tests select (same decision as in k_mc_words)
+        const int r = mc33_resolve(a.fld, z, y, x0 + b, cs);
+        const int8_t* row = g33_rows[r];
+        const int n3 = 3 * (int)g33_ntri[r];
+        for (int t = 0; t < n3; t += 3) {
+            int32_t* f = a.faces + 3 * (int64_t)pT;
+            f[0] = (int32_t)vertex_id(b, row[t + 2]); f[1] = (int32_t)vertex_id(b, row[t + 1]); f[2] = (int32_t)vertex_id(b, row[t]);
             ++pT;
         }
     }

@@ -513,11 +513,16 @@ __global__ void __launch_bounds__(256) k_pack_gap(PackGapArgs a)
     const long long boff = span * 1024 + 16 * l;                  // this lane's first 16 mask bytes
     const bool va = boff + 16 <= a.plane_bytes, vb = boff + 512 + 16 <= a.plane_bytes;
     const int s0 = (2 * l) & 31;
-    auto load_word = [&](int z) -> uint32_t {
+    // raw 2 x 16 mask bytes of this lane for plane z, and their conversion to the lane's packed word: split so that the
+    // loads of plane z+2 are in flight while plane z+1 is converted (two planes of loads per warp instead of one: the loop
+    // was bound by the latency of its single outstanding load pair)
+    auto load_raw = [&](int z, uint4& x, uint4& y) {
         const uint8_t* p = a.src + (long long)z * a.plane_bytes + boff;
         const uint4 zero = make_uint4(0, 0, 0, 0);
-        const uint4 x = va ? ld_stream_u4(p) : zero;
-        const uint4 y = vb ? ld_stream_u4(p + 512) : zero;
+        x = va ? ld_stream_u4(p) : zero;
+        y = vb ? ld_stream_u4(p + 512) : zero;
+    };
+    auto to_word = [&](const uint4& x, const uint4& y) -> uint32_t {
         const uint32_t ha = ge16(x, a.thr4), hb = ge16(y, a.thr4);
         const uint32_t a0 = __shfl_sync(0xffffffffu, ha, s0), a1 = __shfl_sync(0xffffffffu, ha, s0 + 1);
         const uint32_t b0 = __shfl_sync(0xffffffffu, hb, s0), b1 = __shfl_sync(0xffffffffu, hb, s0 + 1);
@@ -526,12 +531,20 @@ __global__ void __launch_bounds__(256) k_pack_gap(PackGapArgs a)
     uint32_t acc = 0;
     int zmin = 0x7fffffff, zmax = -1;
     if (span * 1024 < a.plane_bytes) {   // (warp-uniform)
-        uint32_t prev = za > 0 ? load_word(za - 1) : 0u;
-        uint32_t cur = load_word(za);
+        uint4 rx, ry, qx, qy;
+        const uint4 zero = make_uint4(0, 0, 0, 0);
+        uint32_t prev = 0u;
+        if (za > 0) { load_raw(za - 1, rx, ry); prev = to_word(rx, ry); }
+        load_raw(za, rx, ry);
+        if (za + 1 < a.Z) load_raw(za + 1, qx, qy); else { qx = zero; qy = zero; }
+        uint32_t cur = to_word(rx, ry);
         uint32_t* dp = a.dst + (long long)za * a.plane_words + wi;
         for (int z = za; z < zb; ++z) {
             const bool hn = z + 1 < a.Z;
-            const uint32_t next = hn ? load_word(z + 1) : 0u;
+            // issue the loads of plane z+2 before plane z+1 is consumed
+            if (z + 2 < a.Z && z + 1 < zb) load_raw(z + 2, rx, ry); else { rx = zero; ry = zero; }
+            const uint32_t next = hn ? to_word(qx, qy) : 0u;
+            qx = rx; qy = ry;
             uint32_t v = cur;
             if (z > 0 && hn) v |= prev & next;
             if (wvalid) *dp = v;

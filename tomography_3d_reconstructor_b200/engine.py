@@ -432,22 +432,22 @@ def mask_source(mask_images):
         raise ValueError("expected a list of (H,W) masks")
     n = len(mask_images)
     H, W = int(first.shape[0]), int(first.shape[1])
-    base_obj = first.base
-    if (first.flags.c_contiguous and first.dtype.itemsize == 1 and isinstance(base_obj, np.ndarray) and base_obj.ndim == 3
-            and base_obj.shape == (n, H, W) and base_obj.flags.c_contiguous and base_obj.dtype == first.dtype):
-        # views of one (n,H,W) array: in order iff every slice sits at its own offset
-        step, addr = first.nbytes, first.ctypes.data
-        if addr == base_obj.ctypes.data:
-            ok = True
+    if first.flags.c_contiguous and first.dtype.itemsize == 1 and first.dtype in (np.bool_, np.uint8):
+        # in order and back to back iff every slice sits at its own offset from the first one
+        step, addr, shape0, strides0, dt0 = first.nbytes, first.ctypes.data, first.shape, first.strides, first.dtype
+        ok = True
+        try:
             for k in range(1, n):
                 m = mask_images[k]
-                if m.base is not base_obj or m.shape != first.shape or m.ctypes.data != addr + k * step:
+                if m.ctypes.data != addr + k * step or m.strides != strides0 or m.shape != shape0 or m.dtype != dt0:
                     ok = False
                     break
-            if ok:
-                arr = base_obj.view(np.uint8) if base_obj.dtype == np.bool_ else base_obj
-                if arr.dtype == np.uint8:
-                    return arr, n, H, W, _is_pinned_stack(arr)
+        except AttributeError:        # not an ndarray
+            ok = False
+        if ok:
+            buf = (ctypes.c_uint8 * (step * n)).from_address(addr)
+            arr = np.frombuffer(buf, dtype=np.uint8).reshape((n, H, W))
+            return arr, n, H, W, _is_pinned_stack(arr)
     return mask_images, n, H, W, False
 
 

@@ -372,6 +372,8 @@ class FusedSlabPlan:
             np.concatenate([r * self.stride + np.arange(a_, b_) for r, (a_, b_) in enumerate(spans)])
             for spans in (self.raw_spans, self.sm_spans)])
         self.last_view, self.last_view_key = None, None
+        # compute() joins the library's side stream when pack() started the hole filling of a global end slice there
+        self.join_fill = self.z0 == 0 or self.z1 == self.Zg
 
     def pack(self, masks_u8: torch.Tensor) -> None:
         """Own slices -> planes [hl, hl+n) of the extended buffer; the holes of the global end slices are filled on the
@@ -387,7 +389,7 @@ class FusedSlabPlan:
         engine.check(engine._L().t3d_reconstruct_slab(
             p(self.ext), self.hl, self.n, self.hh, self.H, self.W, self.n_stages, self.erode_mask, 1 if self.add_padding else 0,
             self.z_begin, self.z_end, self.z_offset, self.want_ghost, self.z_ghost, self.want_lead, self.z_lead,
-            int(self.z0 == 0 or self.z1 == self.Zg), engine._W3_C,
+            int(self.join_fill), engine._W3_C,
             p(self.cum_d), p(self.adj_d), self.n_cum, float(self.mm_y), float(self.mm_x), 0, self.caps[0], self.caps[1],
             self.caps[2], self.caps[3], self.caps[4], self.zkey_bits, p(self.verts), p(self.faces), p(self.res), p(self.ws), engine._stream()), "t3d_reconstruct_slab")
 
@@ -562,6 +564,7 @@ def reconstruct_host_bits(bits_host: np.ndarray, W: int, side_counts, total_dept
         caps = pipeline._caps_from(m.n_active, *m.n_raw, m.n_z)
         plan = FusedSlabPlan(Z, H, W, Z, 0, 1, side_counts, total_depth_mm, x_length_mm, y_length_mm, iterations, add_padding,
                              pipeline._tuned_caps(("bits",) + key, caps), dev, 0, 1)
+        plan.join_fill = False          # the end slices are hole-filled on the main stream here (no t3d_slab_pack)
         st = _bits_plans[key] = {"plan": plan, "graph": None}
         out["vertices"], out["faces"] = engine.download(m.verts), engine.download(m.faces)
         return out
