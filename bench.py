@@ -381,7 +381,9 @@ def run_ours(args, Z, H, W, cfg):
         # and the step ends with a collective: re-cut the slabs by estimated cost, learned from the equal-split step above
         hist = torch.from_numpy(sharded.vertices_per_slice(res, Zg)).to(dev)
         dist.all_reduce(hist)
-        partition = sharded.balanced_ranges(sharded.slice_cost(hist.cpu().numpy()), world, sharded.HALO)
+        # (the volume passes of a slice cost about as much as ~2900 mesh vertices at 1024x1024, in proportion to the slice area)
+        partition = sharded.balanced_ranges(sharded.slice_cost(hist.cpu().numpy(), 2900.0 * (H * W) / (1024.0 * 1024.0)), world,
+                                            sharded.HALO)
         sharded.set_partition(Zg, world, partition)
         z0, z1 = partition[rank]
         del masks

@@ -332,3 +332,27 @@ def test_fused_path_on_degenerate_shapes(eng, oracle, shape):
         v, f = out["mesh"].verts.cpu().numpy(), out["mesh"].faces.cpu().numpy()
         assert np.array_equal(v.view(np.uint32), ref["vertices"].view(np.uint32)) and np.array_equal(f, ref["faces"]), rep
         assert out["voxel_volume_mm3"] == ref["voxel_volume"] and out["processed_voxel_volume_mm3"] == ref["processed_volume"]
+
+
+def test_second_device_in_one_process(eng, oracle):
+    """State that lives per device (constant-memory tables, function attributes, side streams) is initialised per device: the
+    whole path on cuda:1 after cuda:0 in ONE process (needs two GPUs; skipped otherwise)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from tomography_3d_reconstructor_b200 import pipeline
+    Z, H, W = 24, 64, 96
+    u8 = oracle.ellipsoid_phantom_u8(Z, H, W)
+    u8[0, 30:34, 40:44] = 0
+    sides = (3, 18, 3)
+    ref = oracle.reference_pipeline(u8, 200, sides, 6.0, 143.1, 95.03)
+    try:
+        for d in (0, 1, 0):
+            torch.cuda.set_device(d)
+            masks = torch.from_numpy(u8).to("cuda:%d" % d)
+            for _ in range(3):      # staged, fused, fused + graph
+                out = pipeline.reconstruct_fused(masks, 200, sides, 6.0, 143.1, 95.03)
+                assert out["mesh"].verts.device.index == d
+                assert np.array_equal(out["mesh"].verts.cpu().numpy(), ref["vertices"]) and np.array_equal(out["mesh"].faces.cpu().numpy(), ref["faces"])
+                assert out["voxel_volume_mm3"] == ref["voxel_volume"]
+    finally:
+        torch.cuda.set_device(0)

@@ -249,12 +249,24 @@ __global__ void __launch_bounds__(256, 4) k_mc_flags(Grid g, uint32_t* __restric
     uint4 c0 = *reinterpret_cast<const uint4*>(p0), c1 = hz ? *reinterpret_cast<const uint4*>(p1) : zero;  // rows (z,y), (z+1,y)
     uint32_t n0 = hx ? p0[4] : 0u, n1 = (hx && hz) ? p1[4] : 0u;
     const int y1 = min(g.Hs, y0 + gy);
+    // rows (z,y+1), (z+1,y+1) are loaded one iteration ahead of their use (two rows of loads in flight per thread: the loop
+    // was bound by the latency of its single outstanding row at volumes beyond L2)
+    auto load_row = [&](int y, uint4& d0, uint4& d1, uint32_t& m0, uint32_t& m1) {
+        const bool hy = (y < g.Hs);
+        d0 = hy ? *reinterpret_cast<const uint4*>(p0) : zero;
+        d1 = (hy && hz) ? *reinterpret_cast<const uint4*>(p1) : zero;
+        m0 = (hy && hx) ? p0[4] : 0u;
+        m1 = (hy && hz && hx) ? p1[4] : 0u;
+    };
+    uint4 e0, e1; uint32_t q0, q1;           // the prefetched row
+    p0 += g.nws; p1 += g.nws;
+    load_row(y0 + 1, e0, e1, q0, q1);
     for (int y = y0; y < y1; ++y) {
         const bool hy = (y + 1 < g.Hs);
+        const uint4 d0 = e0, d1 = e1;
+        const uint32_t m0 = q0, m1 = q1;
         p0 += g.nws; p1 += g.nws;
-        const uint4 d0 = hy ? *reinterpret_cast<const uint4*>(p0) : zero;                 // rows (z,y+1), (z+1,y+1)
-        const uint4 d1 = (hy && hz) ? *reinterpret_cast<const uint4*>(p1) : zero;
-        const uint32_t m0 = (hy && hx) ? p0[4] : 0u, m1 = (hy && hz && hx) ? p1[4] : 0u;
+        if (y + 1 < y1) load_row(y + 2, e0, e1, q0, q1);
         // values at x+1
         const uint4 a0 = shr1_4(c0, n0), a1 = shr1_4(c1, n1), b0 = shr1_4(d0, m0), b1 = shr1_4(d1, m1);
         uint4 f;  // owned cut edges

@@ -337,7 +337,19 @@ def pack_and_close(masks_u8_dev: torch.Tensor, threshold: int = 1, close_ends: b
 
 
 _copy_streams = {}
+_capture_streams = {}
 _stage_pool = None
+
+
+def capture_stream(dev=None) -> "torch.cuda.Stream":
+    """Stream for CUDA-graph capture ON THE GIVEN DEVICE.  torch.cuda.graph() otherwise captures on a class-level default
+    stream created on whichever device used graphs first: on a second device of the same process the step would be
+    captured (and its kernels launched) on the first device's stream."""
+    idx = torch.cuda.current_device() if dev is None or getattr(dev, "index", None) is None else dev.index
+    st = _capture_streams.get(idx)
+    if st is None:
+        st = _capture_streams[idx] = torch.cuda.Stream(device=idx)
+    return st
 
 
 def _pool():
@@ -679,7 +691,8 @@ def zkey_bits(slice_depths, add_padding: bool, n_planes: int, z_offset: int = 0,
     return nb if nb < 31 else 32
 
 
-EXC_CAP = 1 << 18  # list capacity of the lean field-sign kernel (words needing the exact float64 evaluation)
+EXC_CAP = 1 << 20  # list capacity of the lean field-sign kernel (words needing the exact float64 evaluation); the same
+                   # constant as EXC_CAP in csrc/t3d_pipeline.cu, so the staged and the fused path switch over at the same input
 
 
 def field_sign(dv: DeviceVolume, pad: int, lean: bool = False):

@@ -193,7 +193,7 @@ class FusedPlan:
         self.enqueue(masks_u8)
         torch.cuda.current_stream().synchronize()
         g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
+        with torch.cuda.graph(g, stream=engine.capture_stream()):
             self.enqueue(masks_u8)
             self.res_host.copy_(self.res, non_blocking=True)      # the read-back of the result block is a node of the graph
         self.graph, self.graph_ptr = g, masks_u8.data_ptr()

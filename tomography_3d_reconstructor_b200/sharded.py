@@ -415,7 +415,7 @@ class FusedSlabPlan:
         self.enqueue(masks_u8)
         torch.cuda.current_stream().synchronize()
         g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
+        with torch.cuda.graph(g, stream=engine.capture_stream()):
             self.enqueue(masks_u8)
             self.host.copy_(self.gathered, non_blocking=True)     # the read-back of the result blocks is a node of the graph
         self.graph, self.graph_ptr = g, masks_u8.data_ptr()
@@ -587,7 +587,7 @@ def reconstruct_host_bits(bits_host: np.ndarray, W: int, side_counts, total_dept
             torch.cuda.current_stream().synchronize()
             plan.ext.copy_(src, non_blocking=True)
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
+            with torch.cuda.graph(g, stream=engine.capture_stream()):
                 enqueue()
             st["graph"] = g
         st["graph"].replay()
