@@ -137,32 +137,57 @@ __device__ __forceinline__ uint32_t get6(const OccView& v, int zp, int yp, int x
 
 // z-pass lookup: the first (z) pass of the separable filter sees only 0/1 samples, so its result is one of 18
 // values indexed by (centre c, n2 = a[-2]+a[+2], n1 = a[-1]+a[+1]):  c*w0 + n2*w2 + n1*w1 in scipy's order.
-__device__ __forceinline__ void fill_zlut(const OccView& v, double* zlut)  // zlut[18], one entry per calling thread
+// SWAR form: the six x columns of one (plane, row) fetch are six bits; spread[] moves bit k to bit 5k, and the five planes
+// of a z pass add up -- centre << 4, outer pair << 2, inner pair << 0 -- to six 5-bit indices (c << 4 | n2 << 2 | n1) at once.
+struct ZLut {
+    double z[32];           // indexed by c << 4 | n2 << 2 | n1 (n1, n2 in 0..2)
+    uint32_t spread[64];    // 6 bits -> one bit per 5-bit field
+};
+
+__device__ __forceinline__ void fill_zlut(const OccView& v, ZLut& L)   // by the first 64 threads of the block; __syncthreads() after it
 {
     const int i = threadIdx.x;
-    if (i < 18) {
-        const int c = i / 9, n2 = (i / 3) % 3, n1 = i % 3;
+    if (i < 32) {
+        const int c = i >> 4, n2 = (i >> 2) & 3, n1 = i & 3;
         double t = __dmul_rn((double)c, v.w0);
         t = __dadd_rn(t, __dmul_rn((double)n2, v.w2));
         t = __dadd_rn(t, __dmul_rn((double)n1, v.w1));
-        zlut[i] = t;
+        L.z[i] = t;
+    }
+    if (i < 64) {
+        uint32_t r = 0;
+        for (int k = 0; k < 6; ++k) r |= ((uint32_t)(i >> k) & 1u) << (5 * k);
+        L.spread[i] = r;
     }
 }
 
 // float32 field at both end points of the grid edge (z,y,x) -> +1 along AXIS (0 = z, 1 = y, 2 = x), sharing one
-// neighbourhood fetch: NY rows of (NZ planes x 6 x-bits) packed into one 64-bit word each.  Same arithmetic as
-// field_value() (the z pass comes from zlut, see fill_zlut).
+// neighbourhood fetch of NY rows x NZ planes x 6 x-bits.  Same arithmetic as field_value().
 template <int AXIS>
-__device__ __forceinline__ void edge_field_values(const OccView& v, const double* __restrict__ zlut, int z, int y, int x,
-                                                  float& fa, float& fb)
+__device__ __forceinline__ void edge_field_values(const OccView& v, const ZLut& L, int z, int y, int x, float& fa, float& fb)
 {
     if (!v.gaussian) {
         fa = pbit(v, z, y, x) ? 1.0f : 0.0f;
         fb = pbit(v, z + (AXIS == 0), y + (AXIS == 1), x + (AXIS == 2)) ? 1.0f : 0.0f;
         return;
     }
-    constexpr int NZ = 5 + (AXIS == 0), NY = 5 + (AXIS == 1);
-    unsigned long long col[NY];
+    constexpr int NZ = 5 + (AXIS == 0), NY = 5 + (AXIS == 1), NE = 1 + (AXIS == 0);
+    // idx[e][dy]: six 5-bit z-pass indices (one per x column) of row dy for the five planes e .. e+4
+    uint32_t idx[NE][NY];
+#pragma unroll
+    for (int e = 0; e < NE; ++e)
+#pragma unroll
+        for (int dy = 0; dy < NY; ++dy) idx[e][dy] = 0u;
+    // plane j of a z pass contributes: outer pair (j = 0, 4) << 2, inner pair (j = 1, 3) << 0, centre (j = 2) << 4
+    auto add_plane = [&](int dy, int dz, uint32_t six) {
+        const uint32_t s = L.spread[six];
+#pragma unroll
+        for (int e = 0; e < NE; ++e) {
+            const int j = dz - e;
+            if (j < 0 || j > 4) continue;
+            idx[e][dy] += s << (j == 2 ? 4 : (j == 0 || j == 4) ? 2 : 0);
+        }
+    };
     // un-padded coordinates of the first fetched voxel; interior = the whole fetch lies inside the occupancy volume
     const int oz0 = z - 2 - v.pad, oy0 = y - 2 - v.pad, ox0 = x - 2 - v.pad;
     if (oz0 >= 0 && oz0 + NZ <= v.Z && oy0 >= 0 && oy0 + NY <= v.H && ox0 >= 0 && ox0 + 6 <= v.W) {
@@ -172,34 +197,23 @@ __device__ __forceinline__ void edge_field_values(const OccView& v, const double
         const long long dzs = v.ps;
 #pragma unroll
         for (int dy = 0; dy < NY; ++dy) {
-            unsigned long long c = 0;
 #pragma unroll
             for (int dz = 0; dz < NZ; ++dz) {
                 const uint32_t* q = p + dz * dzs + dy * v.rs;
                 const uint32_t lo = q[0], hi = two ? q[1] : 0u;
-                c |= (unsigned long long)(__funnelshift_r(lo, hi, sh) & 63u) << (6 * dz);
+                add_plane(dy, dz, __funnelshift_r(lo, hi, sh) & 63u);
             }
-            col[dy] = c;
         }
     } else {
 #pragma unroll
         for (int dy = 0; dy < NY; ++dy) {
             const int yr = reflect_idx(y - 2 + dy, v.Hp);
-            unsigned long long c = 0;
 #pragma unroll
-            for (int dz = 0; dz < NZ; ++dz)
-                c |= (unsigned long long)get6(v, reflect_idx(z - 2 + dz, v.Zp), yr, x - 2) << (6 * dz);
-            col[dy] = c;
+            for (int dz = 0; dz < NZ; ++dz) add_plane(dy, dz, get6(v, reflect_idx(z - 2 + dz, v.Zp), yr, x - 2));
         }
     }
-    // z pass of column (dy, k): bit 6*plane + k of col[dy]; `oz` selects which five planes are the taps
-    auto zpass = [&](int dy, int k, int oz) -> double {
-        const uint32_t q = (uint32_t)(col[dy] >> (6 * oz + k));  // bit 6j = plane j of this column
-        const uint32_t c = (q >> 12) & 1u;
-        const uint32_t n1 = ((q >> 6) & 1u) + ((q >> 18) & 1u);
-        const uint32_t n2 = (q & 1u) + ((q >> 24) & 1u);
-        return zlut[c * 9 + n2 * 3 + n1];
-    };
+    // z pass of column (dy, k) for end point e
+    auto zpass = [&](int dy, int k, int e) -> double { return L.z[(idx[e][dy] >> (5 * k)) & 31u]; };
     if (AXIS == 2) {
         // end points differ by one in x: the z and y passes of the six x columns are shared
         double Y[6];

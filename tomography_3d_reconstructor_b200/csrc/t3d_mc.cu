@@ -308,38 +308,57 @@ __global__ void __launch_bounds__(256) k_mc_compact(Grid g, const uint32_t* __re
     }
 }
 
-__global__ void __launch_bounds__(128) k_mc_words(Grid g, McField fld, const uint32_t* __restrict__ aw_idx, uint32_t cap_active,
+#define AW_AMB 0x80000000u     // bit 31 of an aw_idx entry: the word holds a cube with an ambiguous index (set by k_mc_words<0>)
+#define AW_MASK 0x7fffffffu
+
+// AMB = 0: every active word -- counts with the CLASSIC triangle counts, words holding an ambiguous cube are flagged in aw_idx.
+// AMB = 1: the flagged words only -- the classic count of every ambiguous cube is replaced by the count of the row Lewiner's
+//          tests select.  Two kernels so that the common one carries neither the call nor its registers / stack frame
+//          (with the tests inlined behind a branch it ran at 28 us instead of 17 at 512 x 1024 x 1024).
+template <int AMB>
+__global__ void __launch_bounds__(128) k_mc_words(Grid g, McField fld, uint32_t* __restrict__ aw_idx, uint32_t cap_active,
                                                   const unsigned long long* __restrict__ n_active_dev, uint32_t* __restrict__ aw_cnt,
                                                   unsigned long long* __restrict__ n_ambiguous)
 {
     const uint32_t n_active = cap_active;  // array stride
     const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     if ((int64_t)k >= dev_n(cap_active, n_active_dev)) return;
-    const uint32_t i = aw_idx[k];
+    const uint32_t iraw = aw_idx[k];
+    if (AMB && !(iraw & AW_AMB)) return;
+    const uint32_t i = iraw & AW_MASK;
     const uint32_t row = i / (uint32_t)g.nws;
     const int w = (int)(i - row * (uint32_t)g.nws);
     int z, y;
     const WordMasks m = load_masks(g, row, w, z, y);
-    uint32_t nt = 0, na = 0, ambmask = 0;
-    for (uint32_t a = m.act; a;) {        // branch-free common loop: classic triangle counts, ambiguous cubes only noted
-        const int b = __ffs(a) - 1;
-        a &= a - 1;
-        const uint32_t n = c_luts.ntri[cube_case(m, b)];
-        nt += n & 0x7fu;
-        ambmask |= (n >> 7) << b;
+    if (!AMB) {
+        uint32_t nt = 0, amb = 0;
+        for (uint32_t a = m.act; a;) {        // branch-free: classic triangle counts, ambiguous cubes only noted
+            const int b = __ffs(a) - 1;
+            a &= a - 1;
+            const uint32_t n = c_luts.ntri[cube_case(m, b)];
+            nt += n & 0x7fu;
+            amb |= n;
+        }
+        aw_cnt[k] = __popc(m.X00);
+        aw_cnt[(int64_t)n_active + k] = __popc(m.Y0);
+        aw_cnt[2 * (int64_t)n_active + k] = __popc(m.Z0);
+        aw_cnt[3 * (int64_t)n_active + k] = nt;
+        if (amb & MC_AMB) aw_idx[k] = i | AW_AMB;
+    } else {
+        int delta = 0;
+        uint32_t na = 0;
+        for (uint32_t a = m.act; a;) {
+            const int b = __ffs(a) - 1;
+            a &= a - 1;
+            const int cs = cube_case(m, b);
+            const uint32_t n = c_luts.ntri[cs];
+            if (!(n & MC_AMB)) continue;
+            delta += (int)g33_ntri[mc33_resolve(fld, z, y, (w << 5) + b, cs)] - (int)(n & 0x7fu);
+            ++na;
+        }
+        aw_cnt[3 * (int64_t)n_active + k] += (uint32_t)delta;
+        if (na) atomicAdd(n_ambiguous, (unsigned long long)na);
     }
-    for (uint32_t a = ambmask; a;) {      // rare: replace the classic count by the count of the row Lewiner's tests select
-        const int b = __ffs(a) - 1;
-        a &= a - 1;
-        const int cs = cube_case(m, b);
-        nt += g33_ntri[mc33_resolve(fld, z, y, (w << 5) + b, cs)] - (c_luts.ntri[cs] & 0x7fu);
-        ++na;
-    }
-    aw_cnt[k] = __popc(m.X00);
-    aw_cnt[(int64_t)n_active + k] = __popc(m.Y0);
-    aw_cnt[2 * (int64_t)n_active + k] = __popc(m.Z0);
-    aw_cnt[3 * (int64_t)n_active + k] = nt;
-    if (na) atomicAdd(n_ambiguous, (unsigned long long)na);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -376,7 +395,9 @@ __device__ __forceinline__ unsigned long long vkey(int axis, int z, int y, int x
 
 // PARTS: 1 = vertex keys only, 2 = faces only, 3 = both (the keys are all the vertex kernel needs, so the faces can be
 // emitted concurrently with it on another stream)
-template <int PARTS>
+// AMB = 0: faces of the words WITHOUT an ambiguous cube only (the common kernel: no call, no stack frame); AMB = 1: faces of the
+// flagged words only; AMB = 2: all words in one kernel (staged path).  Vertex keys (PARTS & 1) are written for every word.
+template <int PARTS, int AMB>
 __global__ void __launch_bounds__(128) k_mc_emit(EmitArgs a)
 {
     // per-thread tables indexed by cube edge (0..11), thread-major => bank-conflict free; the corner -> vertex id
@@ -385,6 +406,12 @@ __global__ void __launch_bounds__(128) k_mc_emit(EmitArgs a)
     __shared__ uint32_t s_base[12][128];
     __shared__ uint32_t s_mask[12][128];
     __shared__ uint32_t s_next[4][128];   // ids of the y/z-edge vertices at bit 0 of the next word (edges 1, 5, 9, 10 at b = 31)
+    if (AMB == 1) {                       // nearly every CTA of this launch has nothing to do: leave before the table copy
+        const uint32_t k0 = blockIdx.x * blockDim.x + threadIdx.x;
+        const unsigned long long n0 = a.sizes ? a.sizes[0] : (unsigned long long)a.n_active;
+        const int flagged = k0 < n0 && k0 < a.n_active && (a.aw_idx[k0] & AW_AMB);
+        if (!__syncthreads_or(flagged)) return;
+    }
     if (PARTS & 2) {
         const int4* src = reinterpret_cast<const int4*>(&g_tri_table[0][0]);
         int4* dst = reinterpret_cast<int4*>(&s_tri[0][0]);
@@ -403,7 +430,9 @@ __global__ void __launch_bounds__(128) k_mc_emit(EmitArgs a)
         if (a.sizes[1] + a.sizes[2] + a.sizes[3] > a.cap_verts || a.sizes[4] > a.cap_faces) return;  // overflow: flagged by the caller
     }
     if (k >= a.n_active) return;
-    const uint32_t i = a.aw_idx[k];
+    const uint32_t iraw = a.aw_idx[k];
+    if (AMB == 1 && !(iraw & AW_AMB)) return;
+    const uint32_t i = iraw & AW_MASK;
     const uint32_t row = i / (uint32_t)a.g.nws;
     const int w = (int)(i - row * (uint32_t)a.g.nws);
     int z, y;
@@ -423,6 +452,7 @@ __global__ void __launch_bounds__(128) k_mc_emit(EmitArgs a)
         for (uint32_t q = m.Z0; q;) { const int b = __ffs(q) - 1; q &= q - 1; a.vkeys[id++] = vkey(0, z, y, x0 + b); }
     }
     if (!(PARTS & 2) || !m.act) return;
+    if (AMB == 0 && (iraw & AW_AMB)) return;       // its faces come from the AMB = 1 launch
 
     // ---- bases of the neighbouring words whose vertices our cubes use (looked up only when they own any)
     const uint32_t Hs = (uint32_t)a.g.Hs;
@@ -463,13 +493,6 @@ __global__ void __launch_bounds__(128) k_mc_emit(EmitArgs a)
     s_next[0][tid] = nY0; s_next[1][tid] = nY1; s_next[2][tid] = nZ0; s_next[3][tid] = nZ1;
     // (each thread reads back only its own column: no barrier needed)
 
-    // does this word hold a cube with an ambiguous index?  (word-level split: the common loop below carries no call)
-    uint32_t ambmask = 0;
-    for (uint32_t q = m.act; q;) {
-        const int b = __ffs(q) - 1;
-        q &= q - 1;
-        ambmask |= (uint32_t)((uint8_t)s_tri[cube_case(m, b)][T3D_MC_ROW - 1] == 0xfeu) << b;     // byte 15 = -2: ambiguous index
-    }
     // corner -> vertex id of the cube at bit b, through the per-thread tables above
     auto vertex_id = [&](int b, int e) -> uint32_t {
         const uint32_t at_next = (0x622u >> e) & 1u;           // edges 1, 5, 9, 10 sit at x + 1
@@ -492,7 +515,7 @@ __global__ void __launch_bounds__(128) k_mc_emit(EmitArgs a)
             ++pT;
         }
     };
-    if (!ambmask) {                       // the common word: no call, no extra test inside the loop
+    if (AMB == 0) {                       // the common kernel: classic rows only
         for (uint32_t q = m.act; q;) {
             const int b = __ffs(q) - 1;
             q &= q - 1;
@@ -500,12 +523,12 @@ __global__ void __launch_bounds__(128) k_mc_emit(EmitArgs a)
         }
         return;
     }
-    for (uint32_t q = m.act; q;) {        // a word with at least one ambiguous cube
+    for (uint32_t q = m.act; q;) {        // words that may hold ambiguous cubes
         const int b = __ffs(q) - 1;
         q &= q - 1;
         const int cs = cube_case(m, b);
-        if (!((ambmask >> b) & 1u)) { emit_classic(b, cs); continue; }
-        // the row Lewiner's tests select (same decision as in k_mc_words)
+        if ((uint8_t)s_tri[cs][T3D_MC_ROW - 1] != 0xfeu) { emit_classic(b, cs); continue; }     // byte 15 = -2: ambiguous index
+        // the row Lewiner's tests select (same decision as in k_mc_words<1>)
         const int r = mc33_resolve(a.fld, z, y, x0 + b, cs);
         const int8_t* row = g33_rows[r];
         const int n3 = 3 * (int)g33_ntri[r];
@@ -538,7 +561,7 @@ struct VertexArgs {
 };
 
 template <int AXIS>
-__device__ __forceinline__ void vertex_body(const VertexArgs& p, const double* zlut, uint32_t id)
+__device__ __forceinline__ void vertex_body(const VertexArgs& p, const ZLut& zlut, uint32_t id)
 {
     const unsigned long long key = p.vkeys[id];
     const int x = (int)((key >> 2) & 0xfffffu) - p.x_off, y = (int)((key >> 22) & 0xfffffu), z = (int)(key >> 42);
@@ -587,7 +610,7 @@ __device__ __forceinline__ void vertex_body(const VertexArgs& p, const double* z
 template <int AXIS>
 __global__ void __launch_bounds__(128) k_mc_vertices(VertexArgs p)
 {
-    __shared__ double zlut[18];
+    __shared__ ZLut zlut;
     fill_zlut(p.occ, zlut);
     __syncthreads();
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -600,7 +623,7 @@ __global__ void __launch_bounds__(128) k_mc_vertices(VertexArgs p)
 __global__ void __launch_bounds__(128) k_mc_vertices_all(VertexArgs p, const unsigned long long* __restrict__ sizes, uint32_t cap_verts,
                                                          int which)
 {
-    __shared__ double zlut[18];
+    __shared__ ZLut zlut;
     fill_zlut(p.occ, zlut);
     __syncthreads();
     const unsigned long long nx = sizes[1], ny = sizes[2], nz = sizes[3];
@@ -631,7 +654,7 @@ static int make_grid(Grid& g, const void* sign_bits, int Zs, int Hs, int Ws, int
     g.ncr = (g.nws + 31) >> 5;
     g.n_rows = (uint32_t)((int64_t)Zs * Hs);
     g.n_words = (int64_t)Zs * Hs * g.nws;
-    if (g.n_words >= ((int64_t)1 << 32)) { t3d_set_error("%s: more than 2^32 words in one device slab", who); return 2; }
+    if (g.n_words >= ((int64_t)1 << 31)) { t3d_set_error("%s: more than 2^31 words in one device slab", who); return 2; }
     return 0;
 }
 
@@ -672,10 +695,12 @@ extern "C" int t3d_mc_words(const void* sign_bits, int Zs, int Hs, int Ws, int z
     k_mc_compact<<<(unsigned)((n_chunks + 255) / 256), 256, 0, st>>>(g, (const uint32_t*)ballots_u32,
                                                                       (const uint32_t*)chunkbase_u32, n_chunks,
                                                                       (uint32_t*)aw_idx_u32, n_active);
-    k_mc_words<<<(n_active + 127) / 128, 128, 0, st>>>(g, fld, (const uint32_t*)aw_idx_u32, n_active, nullptr,
-                                                       (uint32_t*)aw_cnt_u32, (unsigned long long*)n_ambiguous_u64);
+    k_mc_words<0><<<(n_active + 127) / 128, 128, 0, st>>>(g, fld, (uint32_t*)aw_idx_u32, n_active, nullptr, (uint32_t*)aw_cnt_u32,
+                                                          (unsigned long long*)n_ambiguous_u64);
+    k_mc_words<1><<<(n_active + 127) / 128, 128, 0, st>>>(g, fld, (uint32_t*)aw_idx_u32, n_active, nullptr, (uint32_t*)aw_cnt_u32,
+                                                          (unsigned long long*)n_ambiguous_u64);
     T3D_CHECK_LAUNCH("t3d_mc_words");
-    t3d_count_launches(2);
+    t3d_count_launches(3);
     return 0;
 }
 
@@ -702,7 +727,7 @@ extern "C" int t3d_mc_emit(const void* sign_bits, int Zs, int Hs, int Ws, int z_
     a.faces = (int32_t*)faces_i32;
     a.sizes = nullptr;
     a.cap_verts = a.cap_faces = 0xffffffffu;
-    k_mc_emit<3><<<(n_active + 127) / 128, 128, 0, (cudaStream_t)stream>>>(a);
+    k_mc_emit<3, 2><<<(n_active + 127) / 128, 128, 0, (cudaStream_t)stream>>>(a);
     T3D_CHECK_LAUNCH("t3d_mc_emit");
     t3d_count_launches(1);
     return 0;
@@ -760,11 +785,12 @@ static int mc_words_dev_impl(const McField& fld, const void* sign_bits, int Zs, 
     const int64_t n_chunks = (int64_t)g.n_rows * g.ncr;
     k_mc_compact<<<(unsigned)((n_chunks + 255) / 256), 256, 0, st>>>(g, (const uint32_t*)ballots_u32, (const uint32_t*)chunkbase_u32,
                                                                       n_chunks, (uint32_t*)aw_idx_u32, cap_active);
-    k_mc_words<<<(cap_active + 127) / 128, 128, 0, st>>>(g, fld, (const uint32_t*)aw_idx_u32, cap_active,
-                                                         (const unsigned long long*)sizes_u64, (uint32_t*)aw_cnt_u32,
-                                                         (unsigned long long*)n_ambiguous_u64);
+    k_mc_words<0><<<(cap_active + 127) / 128, 128, 0, st>>>(g, fld, (uint32_t*)aw_idx_u32, cap_active, (const unsigned long long*)sizes_u64,
+                                                            (uint32_t*)aw_cnt_u32, (unsigned long long*)n_ambiguous_u64);
+    k_mc_words<1><<<(cap_active + 127) / 128, 128, 0, st>>>(g, fld, (uint32_t*)aw_idx_u32, cap_active, (const unsigned long long*)sizes_u64,
+                                                            (uint32_t*)aw_cnt_u32, (unsigned long long*)n_ambiguous_u64);
     T3D_CHECK_LAUNCH("t3d_mc_words_dev");
-    t3d_count_launches(2);
+    t3d_count_launches(3);
     return 0;
 }
 
@@ -798,11 +824,15 @@ static int mc_emit_dev_impl(const McField& fld, const void* sign_bits, int Zs, i
     a.vkeys = (unsigned long long*)vkeys_u64;
     a.faces = (int32_t*)faces_i32;
     const unsigned ge = (cap_active + 127) / 128;
-    if ((parts & 3) == 1) k_mc_emit<1><<<ge, 128, 0, (cudaStream_t)stream>>>(a);
-    else if ((parts & 3) == 2) k_mc_emit<2><<<ge, 128, 0, (cudaStream_t)stream>>>(a);
-    else k_mc_emit<3><<<ge, 128, 0, (cudaStream_t)stream>>>(a);
+    int launches = 1;
+    if ((parts & 3) == 1) k_mc_emit<1, 0><<<ge, 128, 0, (cudaStream_t)stream>>>(a);
+    else if ((parts & 3) == 2) {        // the common words, then the (rare) words holding ambiguous cubes
+        k_mc_emit<2, 0><<<ge, 128, 0, (cudaStream_t)stream>>>(a);
+        k_mc_emit<2, 1><<<ge, 128, 0, (cudaStream_t)stream>>>(a);
+        launches = 2;
+    } else k_mc_emit<3, 2><<<ge, 128, 0, (cudaStream_t)stream>>>(a);
     T3D_CHECK_LAUNCH("t3d_mc_emit_dev");
-    t3d_count_launches(1);
+    t3d_count_launches(launches);
     return 0;
 }
 
