@@ -16,7 +16,7 @@ int t3d_num_sms(void);
 // per-device "done once" flags for state that lives per device (constant memory, function attributes): returns true the
 // first time it is called for (slot, current device)
 bool t3d_first_use_on_device(int slot);
-enum { T3D_ONCE_FILL_HOLES_ATTR = 0, T3D_ONCE_MC_LUTS = 1, T3D_ONCE_SORT_ATTR = 2, T3D_ONCE_SLOTS = 8 };
+enum { T3D_ONCE_FILL_HOLES_ATTR = 0, T3D_ONCE_MC_LUTS = 1, T3D_ONCE_SORT_ATTR = 2, T3D_ONCE_MORPH4_ATTR = 3, T3D_ONCE_SLOTS = 8 };
 
 extern "C" void t3d_set_error(const char* fmt, ...);
 extern "C" void t3d_count_launches(int n);  // bookkeeping for bench.py's gpu_launches (our kernels only)
@@ -159,6 +159,11 @@ __device__ __forceinline__ int64_t dev_n(int64_t cap, const unsigned long long* 
 // stage also clears the 4 pad words in front of every row it writes and ring_tail (0 / 1) uint4 behind it.
 int t3d_morph_stage(const uint32_t* in, uint32_t* out, int Z, int H, int W, int z0, int nz, int out_rs, long long out_ps,
                     bool erode, bool ring, int ring_tail, unsigned long long* counts, cudaStream_t st);
+// the four stages E, D, D, E in one pass (k_morph4, t3d_voxel.cu): eligibility of a volume and the launch; arguments as for a
+// ring + counts t3d_morph_stage
+bool t3d_morph4_eligible(int Z, int H, int W);
+int t3d_morph4_launch(const uint32_t* in, uint32_t* out, int Z, int H, int W, int z0, int nz, int out_rs, long long out_ps, int ring_tail,
+                      unsigned long long* counts, cudaStream_t st);
 // fused pack + z gap fill + per-slice counts + extrema (see t3d_voxel.cu)
 bool t3d_pack_gap_supported(const void* masks_u8, int Z, int H, int W, int threshold);
 int t3d_pack_gap_launch(const void* masks_u8, int Z, int H, int W, int threshold, void* out, unsigned long long* counts,

@@ -333,6 +333,9 @@ static int reconstruct_core(const uint32_t* grid, const SlabGeom& g, int H, int 
                 RUN(t3d_morph_stage(tA, S_origin + (int64_t)(a - z0) * s_ps, hi3 - lo3, H, W, a - lo3, b - a, nws, s_ps, true, true, ring_tail,
                                     R + R_COUNTS + Zx + a, st));
             }
+        } else if (t3d_morph4_eligible(Zx, H, W)) {
+            // the four stages in one pass: grid read once, sign volume written once
+            RUN(t3d_morph4_launch(grid, S_origin, Zx, H, W, z0, Zl, nws, s_ps, ring_tail, R + R_COUNTS + Zx + z0, st));
         } else {
             RUN(t3d_morph_stage(grid, tA, Zx, H, W, 0, Zx, (int)nw, plane_words, true, false, 0, nullptr, st));
             RUN(t3d_morph_stage(tA, tB, Zx, H, W, 0, Zx, (int)nw, plane_words, false, false, 0, nullptr, st));

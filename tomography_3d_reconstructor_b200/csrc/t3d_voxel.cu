@@ -817,6 +817,274 @@ int t3d_morph_stage(const uint32_t* in, uint32_t* out, int Z, int H, int W, int 
     return 0;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Opening + closing (stages E, D, D, E) in ONE pass over the volume: the grid is read once and the result written once,
+// instead of four reads and four writes (the four-launch chain above moves 8 x the volume through DRAM).
+//
+// A CTA owns a band of `ty` rows (full row width) and marches along z through a chunk of planes.  A thread owns M4_R
+// consecutive rows of one uint4 column (128 voxels) and carries, for every stage s, two registers per row:
+//     Xp_s = the stage's input at the previous plane,   Q_s = op_s(in-plane cross of the previous plane, input two planes back)
+// so that when input plane t arrives
+//     stage 0 output (t-1) = op_0(Q_0, I(t))   -> is stage 1's input plane t-1
+//     stage 1 output (t-2) = op_1(Q_1, that)   -> stage 2's input ...          stage 3 output (t-4) goes to global memory
+// entirely in registers.  Only the in-plane neighbours (rows above / below the thread's rows; the x neighbours come from
+// warp shuffles) need another thread's data: the four new input planes are exchanged through shared memory, double
+// buffered, ONE barrier per plane.  Input planes arrive through a cp.async ring M4_PF deep.
+// Halo: 4 rows above / below the band and 4 planes before / after the chunk are recomputed; rows / planes outside the
+// volume hold the neutral element of the stage that reads them (skimage's border rule: erosion sees 1, dilation 0).
+// Requires W % 128 == 0 and a row of nw4 = W / 128 uint4 with 32 % nw4 == 0 (W = 128 .. 4096 in powers of two).
+// ------------------------------------------------------------------------------------------------
+#define M4_R 2
+#define M4_PF 4
+#define M4_ZC_MAX 128
+#define M4_EM 9u          // stage s is an erosion when bit s is set: E, D, D, E
+
+struct Morph4Args {
+    const uint32_t* in;          // compact (Z, H, 4 * nw4) volume
+    uint32_t* out;               // word (plane z0, row 0, word 0) of the output
+    int Z, H, nw4;
+    int z0, nz;                  // planes [z0, z0 + nz) are written
+    int out_rs;
+    long long out_ps;
+    int ty, zc;                  // band height, planes per chunk
+    int ring_tail;
+    unsigned long long* counts;  // counts[z - z0] += set voxels of output plane z (or null)
+};
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
+__device__ __forceinline__ uint4 lds128(uint32_t addr)
+{
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];\n" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, uint4 v)
+{
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};\n" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void cp_async16s(uint32_t saddr, const void* gsrc)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(saddr), "l"(gsrc) : "memory");
+}
+
+__global__ void __launch_bounds__(512, 1) k_morph4(Morph4Args a)
+{
+    extern __shared__ __align__(16) uint32_t m4_smem[];
+    __shared__ unsigned int s_cnt[M4_ZC_MAX];
+    const int nw4 = a.nw4;
+    const uint32_t row_b = 16u * nw4;                            // bytes of a tile row
+    const int tid = threadIdx.x, x4 = tid % nw4, rg = tid / nw4;
+    const int rows = a.ty + 8;
+    const int yl0 = rg * M4_R;                                   // first tile row of this thread
+    const int y0 = blockIdx.x * a.ty - 4;                        // volume row of tile row 0
+    const int za = a.z0 + blockIdx.y * a.zc, zb = min(a.z0 + a.nz, za + a.zc);
+    const uint32_t tile_b = (uint32_t)rows * row_b;
+    // shared memory (byte addresses of this thread's first uint4): ring [M4_PF] input planes, xbuf [2][3] inputs of stages 1..3
+    const uint32_t me = (uint32_t)__cvta_generic_to_shared(m4_smem) + (uint32_t)yl0 * row_b + 16u * x4;
+    const uint32_t xb0 = me + M4_PF * tile_b;
+    for (int i = tid; i < M4_ZC_MAX; i += blockDim.x) s_cnt[i] = 0;
+    __syncthreads();
+
+    const uint4 ones = splat4(0xffffffffu), zeros = splat4(0u);
+    bool rowin[M4_R], rowst[M4_R];
+    uint32_t rowout[M4_R];                                       // all ones: the row lies outside the volume
+#pragma unroll
+    for (int r = 0; r < M4_R; ++r) {
+        const int yl = yl0 + r, y = y0 + yl;
+        rowin[r] = y >= 0 && y < a.H;
+        rowst[r] = rowin[r] && yl >= 4 && yl < 4 + a.ty;
+        rowout[r] = rowin[r] ? 0u : 0xffffffffu;
+    }
+    const long long in_ps = (long long)a.H * 4 * nw4;
+    const int t0 = za - 4, t_last = zb + 3;
+    const uint32_t* gnext = a.in + (long long)t0 * in_ps + (long long)(y0 + yl0) * 4 * nw4 + 4 * x4;   // this thread's rows of the next plane to fetch
+    int pnext = t0;
+    const int p_hi = min(a.Z - 1, t_last);
+
+    auto issue = [&](uint32_t saddr) {                           // input plane pnext -> ring slot at saddr
+        const bool need = pnext >= 0 && pnext <= p_hi;
+#pragma unroll
+        for (int r = 0; r < M4_R; ++r) {
+            if (need && rowin[r]) cp_async16s(saddr + r * row_b, gnext + r * 4 * nw4);
+            else sts128(saddr + r * row_b, (M4_EM & 1u) ? ones : zeros);
+        }
+        cp_async_commit();
+        gnext += in_ps;
+        ++pnext;
+    };
+
+    uint4 Q[4][M4_R], Xp[4][M4_R];
+#pragma unroll
+    for (int s = 0; s < 4; ++s)
+#pragma unroll
+        for (int r = 0; r < M4_R; ++r) { Q[s][r] = zeros; Xp[s][r] = zeros; }
+
+#pragma unroll
+    for (int k = 0; k < M4_PF - 1; ++k) issue(me + k * tile_b);
+    uint32_t slot_a = me;                                        // ring slot of plane t
+    uint32_t slot_w = me + (M4_PF - 1) * tile_b;                 // ring slot the next fetch goes to
+    uint32_t xb = xb0, xb_other = xb0 + 3 * tile_b;
+    const bool up_ok = yl0 > 0, dn_ok = yl0 + M4_R < rows;
+    const unsigned full = 0xffffffffu;
+    const uint32_t lfix = x4 == 0 ? 0x80000000u : 0u, rfix = x4 == nw4 - 1 ? 1u : 0u;   // the bit an x neighbour outside the row supplies
+    // output pointers of this thread's rows at plane t0 - 4 (advanced every step; dereferenced inside [za, zb) only)
+    uint32_t* po = a.out + (long long)(t0 - 4 - a.z0) * a.out_ps + (long long)(y0 + yl0) * a.out_rs + 4 * x4;
+    const bool pad_l = x4 == 0, pad_r = x4 == nw4 - 1 && a.ring_tail;
+#pragma unroll 2
+    for (int t = t0; t <= t_last; ++t) {
+        cp_async_wait<M4_PF - 2>();                              // this thread's part of plane t has landed
+        uint4 Xn[4][M4_R];
+#pragma unroll
+        for (int r = 0; r < M4_R; ++r) Xn[0][r] = lds128(slot_a + r * row_b);
+        // the chain along z, in registers: stage s turns its new input plane t - s into its output plane t - s - 1
+        const int zo = t - 4;
+        const bool st_plane = zo >= za && zo < zb;
+        uint32_t cnt = 0;
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+            const bool er = (M4_EM >> s) & 1u;
+            const int q = t - s - 1;                             // plane of this stage's output = next stage's input
+            const uint32_t pout = (q >= 0 && q < a.Z) ? 0u : 0xffffffffu;
+#pragma unroll
+            for (int r = 0; r < M4_R; ++r) {
+                uint4 y = er ? and4(Q[s][r], Xn[s][r]) : or4(Q[s][r], Xn[s][r]);
+                if (s < 3) {
+                    // outside the volume: the neutral element of the stage that reads it (one LOP3 with the line above)
+                    const uint32_t o = pout | rowout[r];
+                    const bool ern = (M4_EM >> (s + 1)) & 1u;
+                    if (ern) y = or4(y, splat4(o)); else y = and4(y, splat4(~o));
+                    Xn[s < 3 ? s + 1 : 3][r] = y;
+                } else if (st_plane && rowst[r]) {
+                    uint32_t* pr = po + (long long)r * a.out_rs;
+                    *reinterpret_cast<uint4*>(pr) = y;
+                    if (pad_l) *reinterpret_cast<uint4*>(pr - 4) = zeros;                 // pad words of the padded layout
+                    if (pad_r) *reinterpret_cast<uint4*>(pr + 4) = zeros;
+                    cnt += popc4(y);
+                }
+            }
+        }
+        po += a.out_ps;
+        if (a.counts && st_plane) {
+            cnt = __reduce_add_sync(full, cnt);
+            if ((tid & 31) == 0 && cnt) atomicAdd(&s_cnt[zo - za], cnt);
+        }
+        // exchange: the new input planes of stages 1..3 (stage 0's is the ring slot itself)
+#pragma unroll
+        for (int s = 1; s < 4; ++s)
+#pragma unroll
+            for (int r = 0; r < M4_R; ++r) sts128(xb + (s - 1) * tile_b + r * row_b, Xn[s][r]);
+        __syncthreads();
+        issue(slot_w);                                           // into the slot read one step ago
+        // in-plane cross of the new planes, folded with the previous plane into Q
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+            const bool er = (M4_EM >> s) & 1u;
+            const uint4 nt = er ? ones : zeros;
+            const uint32_t base = s == 0 ? slot_a : xb + (s - 1) * tile_b;
+            const uint4 up = up_ok ? lds128(base - row_b) : nt;
+            const uint4 dn = dn_ok ? lds128(base + M4_R * row_b) : nt;
+#pragma unroll
+            for (int r = 0; r < M4_R; ++r) {
+                const uint4 c = Xn[s][r];
+                uint32_t l = __shfl_up_sync(full, c.w, 1), rr = __shfl_down_sync(full, c.x, 1);
+                if (er) { l |= lfix; rr |= rfix; } else { l &= ~lfix; rr &= ~rfix; }
+                const uint4 above = r == 0 ? up : Xn[s][r > 0 ? r - 1 : 0];
+                const uint4 below = r == M4_R - 1 ? dn : Xn[s][r < M4_R - 1 ? r + 1 : 0];
+                const uint4 xm = shl1_4(c, l), xp = shr1_4(c, rr);
+                uint4 P;
+                if (er) P = and4(and4(and4(c, xm), and4(xp, above)), and4(below, Xp[s][r]));
+                else P = or4(or4(or4(c, xm), or4(xp, above)), or4(below, Xp[s][r]));
+                Q[s][r] = P;
+                Xp[s][r] = c;
+            }
+        }
+        slot_w = slot_a;
+        slot_a = slot_a == me + (M4_PF - 1) * tile_b ? me : slot_a + tile_b;
+        const uint32_t tmp = xb; xb = xb_other; xb_other = tmp;
+    }
+    cp_async_wait<0>();
+    if (a.counts) {
+        __syncthreads();
+        for (int i = tid; i < zb - za; i += blockDim.x)
+            if (s_cnt[i]) atomicAdd(a.counts + (za - a.z0) + i, (unsigned long long)s_cnt[i]);
+    }
+}
+
+static int m4_env(const char* name, int dflt) { const char* e = getenv(name); return e && atoi(e) > 0 ? atoi(e) : dflt; }
+
+// can the one-pass kernel take this volume?  (else the four-launch chain runs)
+bool t3d_morph4_eligible(int Z, int H, int W)
+{
+    static const bool off = getenv("T3D_NO_MORPH4") != nullptr;
+    if (off || (W & 127) || W > 4096 || W < 512) return false;
+    const int nw4 = W / 128;
+    return (32 % nw4) == 0 && Z >= 1 && H >= 1;
+}
+
+// E, D, D, E of planes [z0, z0 + nz) of the compact volume `in` (Z planes) -> out (row stride out_rs, plane stride out_ps words),
+// with the pad words of the padded layout cleared (see k_morph RING) and per-plane counts accumulated
+int t3d_morph4_launch(const uint32_t* in, uint32_t* out, int Z, int H, int W, int z0, int nz, int out_rs, long long out_ps, int ring_tail,
+                      unsigned long long* counts, cudaStream_t st)
+{
+    Morph4Args a;
+    a.in = in; a.out = out; a.Z = Z; a.H = H; a.nw4 = W / 128;
+    a.z0 = z0; a.nz = nz; a.out_rs = out_rs; a.out_ps = out_ps; a.ring_tail = ring_tail; a.counts = counts;
+    const int nw = 4 * a.nw4;
+    // Tile rows: at most 512 threads (rows / M4_R row groups x nw4 columns) and (M4_PF + 6) tiles in ~200 KB of shared memory,
+    // a multiple of the rows one warp covers.  Band height and chunk length are picked by a small cost model: a CTA runs
+    // zc + 8 steps whose duration grows with the tile rows (throughput) but not below a per-step latency floor; the CTAs of
+    // one SM share its throughput.  Tall bands / long chunks waste less halo, short ones fill the machine.
+    const int warp_rows = M4_R * (32 / a.nw4);
+    int rows_max = 512 / a.nw4 * M4_R;
+    const int by_smem = (200 * 1024) / ((M4_PF + 6) * nw * 4);
+    if (rows_max > by_smem) rows_max = by_smem;
+    rows_max -= rows_max % warp_rows;
+    if (rows_max < 9 || rows_max < warp_rows) { t3d_set_error("t3d_morph4: tile does not fit"); return 2; }
+    static const int ty_env = m4_env("T3D_MORPH4_TY", 0), zc_env = m4_env("T3D_MORPH4_ZC", 0);
+    const int sms = T3D_NUM_SMS;
+    int rows = 0, zc = 0;
+    double best = 1e300;
+    for (int rr = rows_max; rr >= 16 && rr >= warp_rows; rr -= warp_rows) {
+        if (ty_env && rr != ((ty_env + 8 + warp_rows - 1) / warp_rows) * warp_rows && rr != rows_max) continue;
+        const int ty = rr - 8, bands = (H + ty - 1) / ty, thr = rr / M4_R * a.nw4;
+        int per_sm = 512 / thr;
+        const int smem_fit = (int)((220 * 1024) / ((size_t)(M4_PF + 6) * rr * nw * 4));
+        if (per_sm > smem_fit) per_sm = smem_fit;
+        if (per_sm < 1) continue;
+        static const int zcs[] = {16, 24, 32, 48, 64, 96, 128};
+        for (int zi = 0; zi < 7; ++zi) {
+            const int c = zc_env ? zc_env : zcs[zi];
+            if (c > M4_ZC_MAX) continue;
+            const long long ctas = (long long)bands * ((nz + c - 1) / c);
+            const double load = (double)((ctas + sms - 1) / sms) * rr;                                   // tile rows per SM per step
+            const double floor_ = 48.0 * (double)((ctas + (long long)sms * per_sm - 1) / ((long long)sms * per_sm));
+            const double cost = (load > floor_ ? load : floor_) * (c + 8);
+            if (cost < best) { best = cost; rows = rr; zc = c; }
+        }
+    }
+    if (ty_env) { rows = ((ty_env + 8 + warp_rows - 1) / warp_rows) * warp_rows; if (rows > rows_max) rows = rows_max; }
+    if (rows == 0) { t3d_set_error("t3d_morph4: no tile configuration"); return 2; }
+    a.ty = rows - 8;
+    const int bands = (H + a.ty - 1) / a.ty;
+    a.zc = zc;
+    const int threads = rows / M4_R * a.nw4;
+    const size_t smem = (size_t)(M4_PF + 6) * rows * nw * 4;
+    if (t3d_first_use_on_device(T3D_ONCE_MORPH4_ATTR))
+        T3D_CUDA(cudaFuncSetAttribute(k_morph4, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    dim3 grid(bands, (nz + zc - 1) / zc);
+    k_morph4<<<grid, threads, smem, st>>>(a);
+    T3D_CHECK_LAUNCH("t3d_morph4");
+    t3d_count_launches(1);
+    return 0;
+}
+
 extern "C" int64_t t3d_morph_scratch_bytes(int Z, int H, int W, int n_stages)
 {
     return n_stages > 1 ? (int64_t)Z * H * t3d_wpr(W) * 4 * (n_stages > 2 ? 2 : 1) : 0;
