@@ -39,6 +39,15 @@ void t3d_count_launches(int n);
  * masks use threshold = 1.  bits: (Z,H,wpr) uint32. */
 int t3d_pack_masks(const void* masks_u8, int Z, int H, int W, int threshold, void* bits, void* stream);
 
+/* The same threshold + stack fused with the z loop of _close_volume_ends (voxel_processor.py:72-75: out[z] = v[z] | (v[z-1] & v[z+1])
+ * for 1 <= z <= Z-2) and with np.sum per slice / the np.where extrema of volume_calculator.py:62-79, in one pass over the
+ * masks (the kernel of the single-enqueue path that streams the uint8 stack).  The end planes are written raw: the caller
+ * hole-fills them and rewrites planes 0, 1, Z-2, Z-1 (what t3d_reconstruct does).  Requires Z >= 3, W % 128 == 0, a 16-byte
+ * aligned stack and 1 <= threshold <= 255 (returns 2 otherwise).  counts_u64: Z per-slice counts or NULL; bbox_u32x6:
+ * {INT_MAX - zmin, zmax + 1, INT_MAX - ymin, ymax + 1, INT_MAX - xmin, xmax + 1} or NULL; both are zeroed by the call. */
+int t3d_pack_gap(const void* masks_u8, int Z, int H, int W, int threshold, void* bits, void* counts_u64, void* bbox_u32x6,
+                 void* stream);
+
 /* inverse: numpy-bool view of a packed volume (the ndarray the reference API returns). out: uint8 (Z,H,W) 0/1 */
 int t3d_unpack_bits(const void* bits, int Z, int H, int W, void* out_u8, void* stream);
 

@@ -32,6 +32,43 @@ def test_pack_unpack(eng, shape, thr):
     assert np.array_equal(bits, refw.reshape(bits.shape))
 
 
+@pytest.mark.parametrize("shape", [(3, 1, 128), (5, 8, 128), (9, 3, 384), (70, 16, 256), (4, 33, 1024), (131, 5, 128)])
+@pytest.mark.parametrize("thr", [1, 2, 127, 128, 129, 200, 254, 255])
+def test_pack_gap_fused_kernel(eng, shape, thr):
+    """t3d_pack_gap: threshold + stack + z gap fill (voxel_processor.py:46, 72-75) + per-slice counts + extrema in one pass;
+    every byte value against every class of threshold (the byte compare is a hand-written carry trick, not a SIMD intrinsic)."""
+    from tomography_3d_reconstructor_b200 import _lib
+    lib = _lib.load()
+    Z, H, W = shape
+    rng = np.random.default_rng(hash((shape, thr)) % 2**32)
+    u8 = rng.integers(0, 256, size=shape, dtype=np.uint8)
+    u8[:, 0, :] = np.arange(W, dtype=np.int64).astype(np.uint8)[None, :] + np.arange(Z, dtype=np.uint8)[:, None]   # all byte values
+    if Z > 4:
+        u8[Z // 2] = 0                                  # a slice the gap fill has to bridge
+    t = eng.upload_u8(u8)
+    nw = eng.words_per_row(W)
+    bits = torch.empty((Z, H, nw), dtype=torch.int32, device="cuda")
+    cnt = torch.full((Z,), -1, dtype=torch.int64, device="cuda")
+    bb = torch.full((6,), -1, dtype=torch.int32, device="cuda")
+    rc = lib.t3d_pack_gap(eng._p(t), Z, H, W, thr, eng._p(bits), eng._p(cnt), eng._p(bb), eng._stream())
+    assert rc == 0, lib.t3d_last_error()
+    torch.cuda.synchronize()
+    v = u8 >= thr
+    ref = v.copy()
+    ref[1:-1] |= v[:-2] & v[2:]
+    got = np.unpackbits(bits.cpu().numpy().view(np.uint8).reshape(Z, H, nw * 4), axis=-1, bitorder="little")[..., :W].astype(bool)
+    assert np.array_equal(got, ref)
+    assert np.array_equal(cnt.cpu().numpy(), ref.reshape(Z, -1).sum(axis=1))
+    b = bb.cpu().numpy().view(np.uint32).astype(np.int64)
+    if ref.any():
+        zz, yy, xx = np.nonzero(ref)
+        want = [zz.min(), zz.max(), yy.min(), yy.max(), xx.min(), xx.max()]
+        have = [0x7fffffff - b[0], b[1] - 1, 0x7fffffff - b[2], b[3] - 1, 0x7fffffff - b[4], b[5] - 1]
+        assert have == [int(x) for x in want]
+    # unsupported stacks are refused, not mangled
+    assert lib.t3d_pack_gap(eng._p(t), 2, H, W, thr, eng._p(bits), None, None, eng._stream()) == 2
+
+
 def test_pack_unaligned_input(eng):
     rng = np.random.default_rng(5)
     big = rng.integers(0, 2, size=(4 * 8 * 64 + 3,), dtype=np.uint8)

@@ -28,6 +28,7 @@ SIGNATURES = {
     "t3d_launch_count": (_i64, []),
     "t3d_count_launches": (None, [_i]),
     "t3d_pack_masks": (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
+    "t3d_pack_gap": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "t3d_unpack_bits": (_i, [_vp, _i, _i, _i, _vp, _vp]),
     "t3d_fill_holes_scratch_bytes": (_i64, [_i, _i, _i]),
     "t3d_fill_holes_2d": (_i, [_vp, _i, _i64, _i, _i, _vp, _vp]),

@@ -267,16 +267,30 @@ __global__ void __launch_bounds__(256, 4) k_mc_flags(Grid g, uint32_t* __restric
         const uint32_t m0 = q0, m1 = q1;
         p0 += g.nws; p1 += g.nws;
         if (y + 1 < y1) load_row(y + 2, e0, e1, q0, q1);
-        // values at x+1
-        const uint4 a0 = shr1_4(c0, n0), a1 = shr1_4(c1, n1), b0 = shr1_4(d0, m0), b1 = shr1_4(d1, m1);
-        uint4 f;  // owned cut edges
-        f.x = ((c0.x ^ a0.x) & em.x); f.y = ((c0.y ^ a0.y) & em.y); f.z = ((c0.z ^ a0.z) & em.z); f.w = ((c0.w ^ a0.w) & em.w);
-        if (hy) { f.x |= (c0.x ^ d0.x) & vm.x; f.y |= (c0.y ^ d0.y) & vm.y; f.z |= (c0.z ^ d0.z) & vm.z; f.w |= (c0.w ^ d0.w) & vm.w; }
-        if (hz) { f.x |= (c0.x ^ c1.x) & vm.x; f.y |= (c0.y ^ c1.y) & vm.y; f.z |= (c0.z ^ c1.z) & vm.z; f.w |= (c0.w ^ c1.w) & vm.w; }
-        if (hy && hz) {  // active cube origins: the 8 corners are neither all set nor all clear
-            const uint4 o = or4(or4(or4(c0, c1), or4(d0, d1)), or4(or4(a0, a1), or4(b0, b1)));
-            const uint4 a = and4(and4(and4(c0, c1), and4(d0, d1)), and4(and4(a0, a1), and4(b0, b1)));
-            f.x |= (o.x & ~a.x) & em.x; f.y |= (o.y & ~a.y) & em.y; f.z |= (o.z & ~a.z) & em.z; f.w |= (o.w & ~a.w) & em.w;
+        uint4 f;  // owned cut edges | active cube origins
+        if (hy && hz) {
+            // The common row.  A cube is active iff its 8 corners are not all equal: iff one of its two x slices (the four
+            // values at x, the four at x+1) is non-uniform, or the slices differ at one corner.  u = non-uniformity of the
+            // slice at x costs two operations per word and its value at x+1 is one funnel shift -- 2 shifts + 5 logic
+            // operations per word where OR / AND over the eight shifted corners took 4 + 14.  The owned y / z edges are
+            // yz = (c0^d0)|(c0^c1) (they matter beyond `em` only, in the last valid column); the owned x edge c0^a0 is
+            // part of the cube test.
+            const uint32_t un = (n0 ^ n1) | (n0 ^ m0) | (m0 ^ m1);            // slice non-uniformity of the next word (bit 0 used)
+            uint4 yz, u;
+            yz.x = (c0.x ^ d0.x) | (c0.x ^ c1.x); yz.y = (c0.y ^ d0.y) | (c0.y ^ c1.y);
+            yz.z = (c0.z ^ d0.z) | (c0.z ^ c1.z); yz.w = (c0.w ^ d0.w) | (c0.w ^ c1.w);
+            u.x = yz.x | (d0.x ^ d1.x); u.y = yz.y | (d0.y ^ d1.y); u.z = yz.z | (d0.z ^ d1.z); u.w = yz.w | (d0.w ^ d1.w);
+            const uint4 us = shr1_4(u, un), a0 = shr1_4(c0, n0);
+            f.x = ((u.x | us.x | (c0.x ^ a0.x)) & em.x) | (yz.x & vm.x);
+            f.y = ((u.y | us.y | (c0.y ^ a0.y)) & em.y) | (yz.y & vm.y);
+            f.z = ((u.z | us.z | (c0.z ^ a0.z)) & em.z) | (yz.z & vm.z);
+            f.w = ((u.w | us.w | (c0.w ^ a0.w)) & em.w) | (yz.w & vm.w);
+        } else {
+            // last row of a plane / last or ghost plane: owned edges only (no cube starts here)
+            const uint4 a0 = shr1_4(c0, n0);
+            f.x = ((c0.x ^ a0.x) & em.x); f.y = ((c0.y ^ a0.y) & em.y); f.z = ((c0.z ^ a0.z) & em.z); f.w = ((c0.w ^ a0.w) & em.w);
+            if (hy) { f.x |= (c0.x ^ d0.x) & vm.x; f.y |= (c0.y ^ d0.y) & vm.y; f.z |= (c0.z ^ d0.z) & vm.z; f.w |= (c0.w ^ d0.w) & vm.w; }
+            if (hz) { f.x |= (c0.x ^ c1.x) & vm.x; f.y |= (c0.y ^ c1.y) & vm.y; f.z |= (c0.z ^ c1.z) & vm.z; f.w |= (c0.w ^ c1.w) & vm.w; }
         }
         const uint32_t nib = (f.x ? 1u : 0u) | (f.y ? 2u : 0u) | (f.z ? 4u : 0u) | (f.w ? 8u : 0u);
         if (nib) atomicOr(pb, nib << bshift);
@@ -321,23 +335,22 @@ __global__ void __launch_bounds__(128) k_mc_words(Grid g, McField fld, uint32_t*
                                                   unsigned long long* __restrict__ n_ambiguous)
 {
     const uint32_t n_active = cap_active;  // array stride
-    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-    if ((int64_t)k >= dev_n(cap_active, n_active_dev)) return;
-    const uint32_t iraw = aw_idx[k];
-    if (AMB && !(iraw & AW_AMB)) return;
-    const uint32_t i = iraw & AW_MASK;
-    const uint32_t row = i / (uint32_t)g.nws;
-    const int w = (int)(i - row * (uint32_t)g.nws);
-    int z, y;
-    const WordMasks m = load_masks(g, row, w, z, y);
+    const int64_t n = dev_n(cap_active, n_active_dev);
     if (!AMB) {
+        const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+        if ((int64_t)k >= n) return;
+        const uint32_t i = aw_idx[k];
+        const uint32_t row = i / (uint32_t)g.nws;
+        const int w = (int)(i - row * (uint32_t)g.nws);
+        int z, y;
+        const WordMasks m = load_masks(g, row, w, z, y);
         uint32_t nt = 0, amb = 0;
         for (uint32_t a = m.act; a;) {        // branch-free: classic triangle counts, ambiguous cubes only noted
             const int b = __ffs(a) - 1;
             a &= a - 1;
-            const uint32_t n = c_luts.ntri[cube_case(m, b)];
-            nt += n & 0x7fu;
-            amb |= n;
+            const uint32_t c = c_luts.ntri[cube_case(m, b)];
+            nt += c & 0x7fu;
+            amb |= c;
         }
         aw_cnt[k] = __popc(m.X00);
         aw_cnt[(int64_t)n_active + k] = __popc(m.Y0);
@@ -345,21 +358,35 @@ __global__ void __launch_bounds__(128) k_mc_words(Grid g, McField fld, uint32_t*
         aw_cnt[3 * (int64_t)n_active + k] = nt;
         if (amb & MC_AMB) aw_idx[k] = i | AW_AMB;
     } else {
-        int delta = 0;
+        // a fixed, small grid striding over the word list: nearly every entry is skipped (a capacity-sized launch of
+        // threads that return at once cost 10 us of CTA launches at 512 x 1024 x 1024)
         uint32_t na = 0;
-        for (uint32_t a = m.act; a;) {
-            const int b = __ffs(a) - 1;
-            a &= a - 1;
-            const int cs = cube_case(m, b);
-            const uint32_t n = c_luts.ntri[cs];
-            if (!(n & MC_AMB)) continue;
-            delta += (int)g33_ntri[mc33_resolve(fld, z, y, (w << 5) + b, cs)] - (int)(n & 0x7fu);
-            ++na;
+        for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) {
+            const uint32_t iraw = aw_idx[k];
+            if (!(iraw & AW_AMB)) continue;
+            const uint32_t i = iraw & AW_MASK;
+            const uint32_t row = i / (uint32_t)g.nws;
+            const int w = (int)(i - row * (uint32_t)g.nws);
+            int z, y;
+            const WordMasks m = load_masks(g, row, w, z, y);
+            int delta = 0;
+            for (uint32_t a = m.act; a;) {
+                const int b = __ffs(a) - 1;
+                a &= a - 1;
+                const int cs = cube_case(m, b);
+                const uint32_t c = c_luts.ntri[cs];
+                if (!(c & MC_AMB)) continue;
+                delta += (int)g33_ntri[mc33_resolve(fld, z, y, (w << 5) + b, cs)] - (int)(c & 0x7fu);
+                ++na;
+            }
+            aw_cnt[3 * (int64_t)n_active + k] += (uint32_t)delta;
         }
-        aw_cnt[3 * (int64_t)n_active + k] += (uint32_t)delta;
         if (na) atomicAdd(n_ambiguous, (unsigned long long)na);
     }
 }
+
+// grid of the launches that stride over the word list looking for flagged words
+static unsigned amb_grid(uint32_t n) { const unsigned want = (n + 127) / 128, cap = (unsigned)T3D_NUM_SMS * 8; return want < cap ? (want ? want : 1) : cap; }
 
 // ------------------------------------------------------------------------------------------------
 // 5. emit: one thread per active word
@@ -406,12 +433,6 @@ __global__ void __launch_bounds__(128) k_mc_emit(EmitArgs a)
     __shared__ uint32_t s_base[12][128];
     __shared__ uint32_t s_mask[12][128];
     __shared__ uint32_t s_next[4][128];   // ids of the y/z-edge vertices at bit 0 of the next word (edges 1, 5, 9, 10 at b = 31)
-    if (AMB == 1) {                       // nearly every CTA of this launch has nothing to do: leave before the table copy
-        const uint32_t k0 = blockIdx.x * blockDim.x + threadIdx.x;
-        const unsigned long long n0 = a.sizes ? a.sizes[0] : (unsigned long long)a.n_active;
-        const int flagged = k0 < n0 && k0 < a.n_active && (a.aw_idx[k0] & AW_AMB);
-        if (!__syncthreads_or(flagged)) return;
-    }
     if (PARTS & 2) {
         const int4* src = reinterpret_cast<const int4*>(&g_tri_table[0][0]);
         int4* dst = reinterpret_cast<int4*>(&s_tri[0][0]);
@@ -422,16 +443,15 @@ __global__ void __launch_bounds__(128) k_mc_emit(EmitArgs a)
         __syncthreads();
     }
     const uint32_t tid = threadIdx.x;
-    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t n_words = a.n_active;
     if (a.sizes) {
-        if ((unsigned long long)k >= a.sizes[0]) return;
+        if (a.sizes[0] < n_words) n_words = (uint32_t)a.sizes[0];
         a.offY = (uint32_t)a.sizes[1];
         a.offZ = (uint32_t)(a.sizes[1] + a.sizes[2]);
         if (a.sizes[1] + a.sizes[2] + a.sizes[3] > a.cap_verts || a.sizes[4] > a.cap_faces) return;  // overflow: flagged by the caller
     }
-    if (k >= a.n_active) return;
-    const uint32_t iraw = a.aw_idx[k];
-    if (AMB == 1 && !(iraw & AW_AMB)) return;
+    // one active word (the tables above are per thread: a thread may take several words in turn)
+    auto emit_word = [&](const uint32_t k, const uint32_t iraw) {
     const uint32_t i = iraw & AW_MASK;
     const uint32_t row = i / (uint32_t)a.g.nws;
     const int w = (int)(i - row * (uint32_t)a.g.nws);
@@ -537,6 +557,17 @@ __global__ void __launch_bounds__(128) k_mc_emit(EmitArgs a)
             f[0] = (int32_t)vertex_id(b, row[t + 2]); f[1] = (int32_t)vertex_id(b, row[t + 1]); f[2] = (int32_t)vertex_id(b, row[t]);
             ++pT;
         }
+    }
+    };
+    if (AMB == 1) {
+        // a fixed, small grid striding over the word list for the flagged words (nearly every entry is skipped)
+        for (uint32_t k = blockIdx.x * blockDim.x + tid; k < n_words; k += gridDim.x * blockDim.x) {
+            const uint32_t iraw = a.aw_idx[k];
+            if (iraw & AW_AMB) emit_word(k, iraw);
+        }
+    } else {
+        const uint32_t k = blockIdx.x * blockDim.x + tid;
+        if (k < n_words) emit_word(k, a.aw_idx[k]);
     }
 }
 
@@ -697,7 +728,7 @@ extern "C" int t3d_mc_words(const void* sign_bits, int Zs, int Hs, int Ws, int z
                                                                       (uint32_t*)aw_idx_u32, n_active);
     k_mc_words<0><<<(n_active + 127) / 128, 128, 0, st>>>(g, fld, (uint32_t*)aw_idx_u32, n_active, nullptr, (uint32_t*)aw_cnt_u32,
                                                           (unsigned long long*)n_ambiguous_u64);
-    k_mc_words<1><<<(n_active + 127) / 128, 128, 0, st>>>(g, fld, (uint32_t*)aw_idx_u32, n_active, nullptr, (uint32_t*)aw_cnt_u32,
+    k_mc_words<1><<<amb_grid(n_active), 128, 0, st>>>(g, fld, (uint32_t*)aw_idx_u32, n_active, nullptr, (uint32_t*)aw_cnt_u32,
                                                           (unsigned long long*)n_ambiguous_u64);
     T3D_CHECK_LAUNCH("t3d_mc_words");
     t3d_count_launches(3);
@@ -787,7 +818,7 @@ static int mc_words_dev_impl(const McField& fld, const void* sign_bits, int Zs, 
                                                                       n_chunks, (uint32_t*)aw_idx_u32, cap_active);
     k_mc_words<0><<<(cap_active + 127) / 128, 128, 0, st>>>(g, fld, (uint32_t*)aw_idx_u32, cap_active, (const unsigned long long*)sizes_u64,
                                                             (uint32_t*)aw_cnt_u32, (unsigned long long*)n_ambiguous_u64);
-    k_mc_words<1><<<(cap_active + 127) / 128, 128, 0, st>>>(g, fld, (uint32_t*)aw_idx_u32, cap_active, (const unsigned long long*)sizes_u64,
+    k_mc_words<1><<<amb_grid(cap_active), 128, 0, st>>>(g, fld, (uint32_t*)aw_idx_u32, cap_active, (const unsigned long long*)sizes_u64,
                                                             (uint32_t*)aw_cnt_u32, (unsigned long long*)n_ambiguous_u64);
     T3D_CHECK_LAUNCH("t3d_mc_words_dev");
     t3d_count_launches(3);
@@ -828,7 +859,7 @@ static int mc_emit_dev_impl(const McField& fld, const void* sign_bits, int Zs, i
     if ((parts & 3) == 1) k_mc_emit<1, 0><<<ge, 128, 0, (cudaStream_t)stream>>>(a);
     else if ((parts & 3) == 2) {        // the common words, then the (rare) words holding ambiguous cubes
         k_mc_emit<2, 0><<<ge, 128, 0, (cudaStream_t)stream>>>(a);
-        k_mc_emit<2, 1><<<ge, 128, 0, (cudaStream_t)stream>>>(a);
+        k_mc_emit<2, 1><<<amb_grid(a.n_active), 128, 0, (cudaStream_t)stream>>>(a);
         launches = 2;
     } else k_mc_emit<3, 2><<<ge, 128, 0, (cudaStream_t)stream>>>(a);
     T3D_CHECK_LAUNCH("t3d_mc_emit_dev");

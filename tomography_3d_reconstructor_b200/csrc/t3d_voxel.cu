@@ -497,6 +497,37 @@ struct PackGapArgs {
     unsigned int* bbox_t;         // 6 transformed extrema {z, y, x} x {INT_MAX - min, max + 1} (zeroed by the caller) or null
 };
 
+// `byte >= threshold` for the 16 bytes of a uint4 -> 16 bits, threshold 1..255, with the constants of ThrK:
+// low 7 bits by a carry that cannot leave the byte ((v & 0x7f) + (0x80 - (t & 0x7f)) sets bit 7 iff low7(v) >= low7(t)), then
+// bit 7 of the result is MAJ(carry, v, ~t) at bit 7 (t < 128: carry | v7, t >= 128: carry & v7) -- four ALU operations per
+// four bytes where the emulated SIMD compare took about ten; the four result bits are gathered by one multiply and the four
+// nibbles of the uint4 are chained by funnel shifts.
+struct ThrK { uint32_t add7, n7; };
+__device__ __forceinline__ ThrK make_thrk(uint32_t thr4)
+{
+    ThrK k;
+    k.add7 = 0x80808080u - (thr4 & 0x7f7f7f7fu);
+    k.n7 = ~thr4 & 0x80808080u;
+    return k;
+}
+__device__ __forceinline__ uint32_t ge4_top(uint32_t v, const ThrK& k)      // result nibble in bits 28..31 (garbage below)
+{
+    const uint32_t c = (v & 0x7f7f7f7fu) + k.add7;
+    uint32_t r;
+    asm("lop3.b32 %0, %1, %2, %3, 0xE8;" : "=r"(r) : "r"(c), "r"(v), "r"(k.n7));   // MAJ(c, v, n7) (kept as ONE operation)
+    return (r & 0x80808080u) * 0x00204081u;
+}
+__device__ __forceinline__ uint32_t ge16k(const uint4& v, const ThrK& k)
+{
+    uint32_t acc = ge4_top(v.w, k) >> 28;
+    acc = __funnelshift_l(ge4_top(v.z, k), acc, 4);
+    acc = __funnelshift_l(ge4_top(v.y, k), acc, 4);
+    acc = __funnelshift_l(ge4_top(v.x, k), acc, 4);
+    return acc;
+}
+
+// FULL: the plane is a whole number of 1024-byte spans (no partial span: no validity predicates in the loop)
+template <bool FULL>
 __global__ void __launch_bounds__(256) k_pack_gap(PackGapArgs a)
 {
     __shared__ unsigned int s_cnt[PG_ZC];
@@ -509,13 +540,14 @@ __global__ void __launch_bounds__(256) k_pack_gap(PackGapArgs a)
     const long long span = (long long)blockIdx.x * 8 + warp;     // 1024 bytes = 32 words of a plane
     const int za = blockIdx.y * a.zc, zb = min(a.Z, za + a.zc);
     const long long wi = span * 32 + l;                           // this lane's word of the plane
-    const bool wvalid = wi < a.plane_words;
+    const bool wvalid = FULL || wi < a.plane_words;
     const long long boff = span * 1024 + 16 * l;                  // this lane's first 16 mask bytes
-    const bool va = boff + 16 <= a.plane_bytes, vb = boff + 512 + 16 <= a.plane_bytes;
+    const bool va = FULL || boff + 16 <= a.plane_bytes, vb = FULL || boff + 512 + 16 <= a.plane_bytes;
+    const ThrK tk = make_thrk(a.thr4);
     const int s0 = (2 * l) & 31;
+    const uint32_t sel = l < 16 ? 0x5410u : 0x7632u;             // which halves of the two shuffled words make this lane's word
     // raw 2 x 16 mask bytes of this lane for plane z, and their conversion to the lane's packed word: split so that the
-    // loads of plane z+2 are in flight while plane z+1 is converted (two planes of loads per warp instead of one: the loop
-    // was bound by the latency of its single outstanding load pair)
+    // loads of later planes are in flight while an earlier one is converted (three planes of loads per warp)
     auto load_raw = [&](int z, uint4& x, uint4& y) {
         const uint8_t* p = a.src + (long long)z * a.plane_bytes + boff;
         const uint4 zero = make_uint4(0, 0, 0, 0);
@@ -523,28 +555,28 @@ __global__ void __launch_bounds__(256) k_pack_gap(PackGapArgs a)
         y = vb ? ld_stream_u4(p + 512) : zero;
     };
     auto to_word = [&](const uint4& x, const uint4& y) -> uint32_t {
-        const uint32_t ha = ge16(x, a.thr4), hb = ge16(y, a.thr4);
-        const uint32_t a0 = __shfl_sync(0xffffffffu, ha, s0), a1 = __shfl_sync(0xffffffffu, ha, s0 + 1);
-        const uint32_t b0 = __shfl_sync(0xffffffffu, hb, s0), b1 = __shfl_sync(0xffffffffu, hb, s0 + 1);
-        return (l < 16) ? (a0 | (a1 << 16)) : (b0 | (b1 << 16));
+        const uint32_t hab = ge16k(x, tk) | (ge16k(y, tk) << 16);                // bits of bytes [16l, 16l+16) and [512+16l, ...)
+        const uint32_t x0 = __shfl_sync(0xffffffffu, hab, s0), x1 = __shfl_sync(0xffffffffu, hab, s0 + 1);
+        return __byte_perm(x0, x1, sel);
     };
     uint32_t acc = 0;
     int zmin = 0x7fffffff, zmax = -1;
-    if (span * 1024 < a.plane_bytes) {   // (warp-uniform)
-        uint4 rx, ry, qx, qy;
-        const uint4 zero = make_uint4(0, 0, 0, 0);
+    if (span * 1024 < a.plane_bytes) {   // (warp-uniform; the last CTA of a plane may hold warps beyond it)
+        uint4 r0x, r0y, r1x, r1y, r2x, r2y;      // raw planes z+1, z+2, z+3 (a ring, rotated by the 3-way unrolled loop)
+        const int p_hi = min(zb, a.Z - 1);        // last plane this chunk reads
         uint32_t prev = 0u;
-        if (za > 0) { load_raw(za - 1, rx, ry); prev = to_word(rx, ry); }
-        load_raw(za, rx, ry);
-        if (za + 1 < a.Z) load_raw(za + 1, qx, qy); else { qx = zero; qy = zero; }
-        uint32_t cur = to_word(rx, ry);
+        if (za > 0) { load_raw(za - 1, r0x, r0y); prev = to_word(r0x, r0y); }
+        load_raw(za, r0x, r0y);
+        uint32_t cur = to_word(r0x, r0y);
+        if (za + 1 <= p_hi) load_raw(za + 1, r0x, r0y);
+        if (za + 2 <= p_hi) load_raw(za + 2, r1x, r1y);
+        if (za + 3 <= p_hi) load_raw(za + 3, r2x, r2y);
         uint32_t* dp = a.dst + (long long)za * a.plane_words + wi;
-        for (int z = za; z < zb; ++z) {
+        // one plane: rx/ry hold raw plane z+1 on entry and raw plane z+4 on exit
+        auto step = [&](int z, uint4& rx, uint4& ry) {
             const bool hn = z + 1 < a.Z;
-            // issue the loads of plane z+2 before plane z+1 is consumed
-            if (z + 2 < a.Z && z + 1 < zb) load_raw(z + 2, rx, ry); else { rx = zero; ry = zero; }
-            const uint32_t next = hn ? to_word(qx, qy) : 0u;
-            qx = rx; qy = ry;
+            const uint32_t next = hn ? to_word(rx, ry) : 0u;
+            if (z + 4 <= p_hi) load_raw(z + 4, rx, ry);
             uint32_t v = cur;
             if (z > 0 && hn) v |= prev & next;
             if (wvalid) *dp = v;
@@ -559,6 +591,11 @@ __global__ void __launch_bounds__(256) k_pack_gap(PackGapArgs a)
             }
             prev = cur;
             cur = next;
+        };
+        for (int z = za; z < zb; z += 3) {
+            step(z, r0x, r0y);
+            if (z + 1 < zb) step(z + 1, r1x, r1y);
+            if (z + 2 < zb) step(z + 2, r2x, r2y);
         }
     }
     if (a.bbox_t && zmax >= 0) {         // (warp-uniform)
@@ -664,10 +701,24 @@ int t3d_pack_gap_launch(const void* masks_u8, int Z, int H, int W, int threshold
     a.skip_ends = skip_ends;
     a.counts = counts; a.bbox_t = bbox_t;
     dim3 grid((unsigned)((n_spans + 7) / 8), (unsigned)((Z + zc - 1) / zc));
-    k_pack_gap<<<grid, 256, 0, st>>>(a);
+    if (a.plane_bytes % 1024 == 0) k_pack_gap<true><<<grid, 256, 0, st>>>(a);
+    else k_pack_gap<false><<<grid, 256, 0, st>>>(a);
     T3D_CHECK_LAUNCH("t3d_pack_gap");
     t3d_count_launches(1);
     return 0;
+}
+
+extern "C" int t3d_pack_gap(const void* masks_u8, int Z, int H, int W, int threshold, void* bits, void* counts_u64, void* bbox_u32x6,
+                            void* stream)
+{
+    if (!t3d_pack_gap_supported(masks_u8, Z, H, W, threshold)) {
+        t3d_set_error("t3d_pack_gap: needs Z >= 3, W %% 128 == 0, a 16-byte aligned stack and 1 <= threshold <= 255");
+        return 2;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    if (counts_u64 && t3d_zero_async(counts_u64, sizeof(unsigned long long) * Z, st)) return 1;
+    if (bbox_u32x6 && t3d_zero_async(bbox_u32x6, 6 * sizeof(unsigned int), st)) return 1;
+    return t3d_pack_gap_launch(masks_u8, Z, H, W, threshold, bits, (unsigned long long*)counts_u64, (unsigned int*)bbox_u32x6, 0, st);
 }
 
 int t3d_close_ends_fixup_launch(const void* masks_u8, int Z, int H, int W, int threshold, const void* filled0, const void* filledT,
