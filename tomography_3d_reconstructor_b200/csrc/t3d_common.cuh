@@ -164,6 +164,9 @@ int t3d_morph_stage(const uint32_t* in, uint32_t* out, int Z, int H, int W, int 
 bool t3d_morph4_eligible(int Z, int H, int W);
 int t3d_morph4_launch(const uint32_t* in, uint32_t* out, int Z, int H, int W, int z0, int nz, int out_rs, long long out_ps, int ring_tail,
                       unsigned long long* counts, cudaStream_t st);
+// one-shot: the next canonicalisation of this thread waits for `e` before its first kernel that reads the faces (t3d_surface.cu)
+void t3d_canon_faces_ready_event(cudaEvent_t e);
+bool t3d_canon_faces_ready_pending();
 // fused pack + z gap fill + per-slice counts + extrema (see t3d_voxel.cu)
 bool t3d_pack_gap_supported(const void* masks_u8, int Z, int H, int W, int threshold);
 int t3d_pack_gap_launch(const void* masks_u8, int Z, int H, int W, int threshold, void* out, unsigned long long* counts,

@@ -268,6 +268,44 @@ __global__ void __launch_bounds__(256) k_zero_ring(uint4* __restrict__ S, int Zs
     }
 }
 
+// Debug timeline (T3D_STAGE_EVENTS=1, eager launches only): events on the main stream at the stage boundaries of
+// reconstruct_core; the elapsed times between them (which include every wait on the side stream) go to stderr after a
+// stream synchronize.  Off by default; never active while the stream is being captured.
+struct StageMarks {
+    enum { N = 12 };
+    cudaEvent_t ev[N];
+    const char* name[N];
+    int n = 0;
+    bool on = false;
+    void begin(cudaStream_t st)
+    {
+        static const bool want = getenv("T3D_STAGE_EVENTS") != nullptr;
+        on = false;
+        if (!want) return;
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) return;
+        on = true; n = 0;
+    }
+    void mark(const char* what, cudaStream_t st)
+    {
+        if (!on || n >= N) return;
+        static thread_local cudaEvent_t pool[N] = {};
+        if (!pool[n]) cudaEventCreate(&pool[n]);
+        ev[n] = pool[n]; name[n] = what;
+        cudaEventRecord(ev[n], st);
+        ++n;
+    }
+    void report(cudaStream_t st)
+    {
+        if (!on) return;
+        cudaStreamSynchronize(st);
+        fprintf(stderr, "[t3d stages]");
+        for (int i = 1; i < n; ++i) { float ms = 0; cudaEventElapsedTime(&ms, ev[i - 1], ev[i]); fprintf(stderr, " %s %.1f us |", name[i], 1e3f * ms); }
+        float tot = 0; if (n > 1) cudaEventElapsedTime(&tot, ev[0], ev[n - 1]);
+        fprintf(stderr, " total %.1f us\n", 1e3f * tot);
+    }
+};
+
 // Everything after the voxel grid exists: smoothing, surface, canonical mesh, measures.  `grid` = bit volume of
 // Zx = hl + n + hh planes after close_ends (bitsB of the layout), counts already in R[R_COUNTS .. +Zx).
 // bbox_state: 0 = compute the bounding box of the owned planes here (side stream), 1 = already in R (int32 x 6),
@@ -287,6 +325,10 @@ static int reconstruct_core(const uint32_t* grid, const SlabGeom& g, int H, int 
     // side stream: bounding box of the owned planes of the raw grid (unless the pack kernel already did it) and the zero
     // ring of the padded sign volume; joined before the cube flags / the measures
     NvtxRange r_smooth("t3d:smooth_voxel_data");
+    StageMarks marks;
+    marks.begin(st);
+    marks.mark("start", st);
+    (void)t3d_canon_faces_ready_pending();   // (nothing registered by an earlier, failed step)
     T3D_CUDA(cudaEventRecord(side->e[2], st));
     T3D_CUDA(cudaStreamWaitEvent(side->s, side->e[2], 0));
     if (bbox_state == 0)
@@ -363,9 +405,11 @@ static int reconstruct_core(const uint32_t* grid, const SlabGeom& g, int H, int 
     }
 
     r_smooth.end();
+    marks.mark("smooth", st);
     // ---- extract_manifold_surface: two-pass marching cubes, vertices
     NvtxRange r_mc("t3d:extract_manifold_surface");
     RUN(t3d_mc_flags(ws + L.sign, Zp, Hp, Wp, g.z_begin, g.z_end, ws + L.ballots, st));
+    marks.mark("flags", st);
     RUN(t3d_exclusive_scan_u32(ws + L.ballots, ws + L.chunkbase, n_chunks, 1, 0, 1, R + R_NACTIVE, ws + L.scan1, st));
     RUN(t3d_mc_words_view_dev(view, x_off, ws + L.sign, Zp, Hp, Wp, g.z_begin, g.z_end, ws + L.ballots, ws + L.chunkbase, cap_active,
                               R + R_NACTIVE, ws + L.aw_idx, ws + L.aw_cnt, R + R_NAMBIGUOUS, st));
@@ -373,25 +417,29 @@ static int reconstruct_core(const uint32_t* grid, const SlabGeom& g, int H, int 
                                    ws + L.scan2, st));
     k_finalize_sizes<<<1, 1, 0, st>>>(R, cap_active, cap_verts, cap_faces, bbox_state == 2 ? 1 : 0);
     t3d_count_launches(1);
-    // The vertex kernel only needs the keys: the faces are emitted on the side stream at the same time (the two kernels
-    // have different bottlenecks: dependent loads vs. float64 issue), then the measures run there as before.
+    marks.mark("scan+words+scan", st);
+    // Keys, then the vertices on the main stream.  The faces are emitted on the side stream AFTER the vertex kernel (run side
+    // by side the two took longer than one after the other: 1.70 ms against 0.77 + 0.76 at 512 x 4096 x 4096) and
+    // concurrently with the ordering of the vertices (layer sort, positions, unique: latency-bound kernels that only need the
+    // vertices); the canonicalisation waits for the faces right before its face kernels.  The measures follow the faces on
+    // the side stream and are joined at the end.
     RUN(t3d_mc_emit_view_dev(view, x_off, ws + L.sign, Zp, Hp, Wp, g.z_begin, g.z_end, ws + L.ballots, ws + L.chunkbase, ws + L.aw_idx,
                              ws + L.aw_base, cap_active, R + R_NACTIVE, cap_verts, cap_faces, ws + L.vkeys, ws + L.faces_raw, 1, st));
+    marks.mark("keys", st);
+    RUN(t3d_mc_vertices_view_dev(view, x_off, ws + L.vkeys, R + R_NACTIVE, cap_verts, 1, g.z_offset, cum_f64, adj_f64, n_cum, mm_y, mm_x,
+                                 scale_in_f64, 7, ws + L.verts_raw, st));
+    r_mc.end();
+    marks.mark("vertices", st);
+    NvtxRange r_canon("t3d:ensure_manifold_mesh+measures");
     T3D_CUDA(cudaEventRecord(side->e[4], st));
     T3D_CUDA(cudaStreamWaitEvent(side->s, side->e[4], 0));
     RUN(t3d_mc_emit_view_dev(view, x_off, ws + L.sign, Zp, Hp, Wp, g.z_begin, g.z_end, ws + L.ballots, ws + L.chunkbase, ws + L.aw_idx,
                              ws + L.aw_base, cap_active, R + R_NACTIVE, cap_verts, cap_faces, ws + L.vkeys, ws + L.faces_raw, 2, side->s));
     T3D_CUDA(cudaEventRecord(side->e[6], side->s));
-    RUN(t3d_mc_vertices_view_dev(view, x_off, ws + L.vkeys, R + R_NACTIVE, cap_verts, 1, g.z_offset, cum_f64, adj_f64, n_cum, mm_y, mm_x,
-                                 scale_in_f64, 7, ws + L.verts_raw, st));
-    // ---- mesh volume / area on the emitted mesh (side stream, concurrent with the canonical ordering), canonical mesh
-    r_mc.end();
-    NvtxRange r_canon("t3d:ensure_manifold_mesh+measures");
-    T3D_CUDA(cudaEventRecord(side->e[7], st));
-    T3D_CUDA(cudaStreamWaitEvent(side->s, side->e[7], 0));
+    // ---- mesh volume / area on the emitted mesh (side stream), canonical mesh
     RUN(t3d_mesh_measure_dev(ws + L.verts_raw, ws + L.faces_raw, cap_faces, R + R_NT, 0, R + R_VOLUME_F64, ws + L.measure, side->s));
     T3D_CUDA(cudaEventRecord(side->e[5], side->s));
-    T3D_CUDA(cudaStreamWaitEvent(st, side->e[6], 0));   // faces emitted (and, earlier on that stream, the bbox reduction)
+    t3d_canon_faces_ready_event(side->e[6]);            // (also orders the earlier work of that stream: the bbox reduction)
     if (cap_zverts)
         RUN(t3d_mesh_canonicalize_structured_dev(ws + L.verts_raw, ws + L.vkeys, cap_verts, R + R_NACTIVE, R + R_VRAW, Zp, Hp, Wp,
                                                  ws + L.chunkbase, ws + L.aw_base, cap_active, g.z_offset, 1, cum_f64, adj_f64, n_cum,
@@ -400,11 +448,15 @@ static int reconstruct_core(const uint32_t* grid, const SlabGeom& g, int H, int 
     else
         RUN(t3d_mesh_canonicalize_fast_dev(ws + L.verts_raw, cap_verts, R + R_VRAW, ws + L.faces_raw, cap_faces, R + R_NT,
                                            verts_out_f32, faces_out_i64, nullptr, R + R_VCANON, ws + L.canon, st));
+    if (t3d_canon_faces_ready_pending()) T3D_CUDA(cudaStreamWaitEvent(st, side->e[6], 0));   // (a path without face kernels)
     if (g.want_ghost || g.want_lead)
         k_count_plane_vertices<<<1, 64, 0, st>>>((const float*)verts_out_f32, R + R_VCANON, g.z_ghost, g.z_lead, g.want_ghost,
                                                  g.want_lead, R + R_NGHOST, R + R_NLEAD);
     if (g.want_ghost || g.want_lead) t3d_count_launches(1);
+    marks.mark("canonicalize", st);
     T3D_CUDA(cudaStreamWaitEvent(st, side->e[5], 0));
+    marks.mark("wait measures", st);
+    marks.report(st);
     return 0;
 }
 

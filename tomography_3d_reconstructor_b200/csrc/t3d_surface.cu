@@ -761,6 +761,14 @@ __global__ void __launch_bounds__(SC_THREADS) k_unique_fused(const float* __rest
 }
 
 // everything after the sorted permutation is known: head flags + order check, unique scatter, face remap
+// The single-enqueue pipeline emits the faces on its side stream while the vertices are being ordered here: it registers
+// the event "faces emitted" and the tail waits for it right before the first kernel that reads the faces (the kernels before
+// that -- layer sort, positions, unique -- only need the vertices).  One-shot: consumed by the next canonical_tail of this thread.
+static thread_local cudaEvent_t g_faces_ready = nullptr;
+void t3d_canon_faces_ready_event(cudaEvent_t e) { g_faces_ready = e; }
+// true if the registered event was not consumed (the caller then waits for it itself); clears it
+bool t3d_canon_faces_ready_pending() { const bool p = g_faces_ready != nullptr; g_faces_ready = nullptr; return p; }
+
 static int canonical_tail(const float* vin, const uint32_t* perm, int64_t V, const unsigned long long* V_dev, const void* faces_in,
                           int64_t F, const unsigned long long* F_dev, void* verts_out, void* faces_out_i64, void* faces_out_i32,
                           unsigned long long* counts, uint32_t* flags, uint32_t* pos, uint32_t* newid, void* scan_ws,
@@ -774,6 +782,10 @@ static int canonical_tail(const float* vin, const uint32_t* perm, int64_t V, con
         if (t3d_zero_async(scan_ws, desc_bytes + 64, st)) return 1;
         k_unique_fused<<<(unsigned)nb, SC_THREADS, 0, st>>>(vin, perm, V, V_dev, (float*)verts_out, newid, (unsigned long long*)scan_ws,
                                                            (int)nb, (unsigned int*)((char*)scan_ws + desc_bytes), counts + 2, counts);
+    }
+    if (g_faces_ready) {
+        T3D_CUDA(cudaStreamWaitEvent(st, g_faces_ready, 0));
+        g_faces_ready = nullptr;
     }
     if (F > 0) {
         // totals[1] = invalid faces, totals[2] = faces the compaction has to look at (0 when nothing is invalid)
@@ -990,6 +1002,7 @@ __device__ __forceinline__ uint32_t canon_zkey(const CanonS& c, uint32_t i, uint
 // Stable LSD radix sort (8-bit digits) of ONE segment by ONE CTA of ZS_THREADS threads.  key_of(i) generates the key of
 // element i in pass 0 (keys are materialised in keyA); out[rank] = value_of(i).  keyA/keyB/idxA/idxB: the segment's slices
 // of the ping-pong buffers.  `passes` digits are sorted, least significant first.
+#define ZS_U 8
 template <typename KeyT, typename KeyFn, typename ValFn>
 __device__ __forceinline__ void cta_radix_sort(uint32_t n, int passes, KeyFn key_of, ValFn value_of, KeyT* keyA, KeyT* keyB, uint32_t* idxA,
                                                uint32_t* idxB, uint32_t* out)
@@ -1009,11 +1022,18 @@ __device__ __forceinline__ void cta_radix_sort(uint32_t n, int passes, KeyFn key
         for (int i = tid; i < ZS_WARPS * 256; i += ZS_THREADS) (&s_hist[0][0])[i] = 0;
         __syncthreads();
         // ---- count (pass 0 also materialises the keys)
-        for (uint32_t i = ws + lane; i < we; i += 32) {
-            KeyT key;
-            if (first) { key = key_of(i); keyA[i] = key; }
-            else key = kin[i];
-            atomicAdd(&s_hist[w][(uint32_t)(key >> shift) & 255u], 1u);
+        // (ZS_U elements per lane are fetched before any is consumed: one exposed memory latency per ZS_U elements -- with one
+        // element per trip both loops of a pass ran at one global-memory round trip per 32 elements per warp)
+        for (uint32_t i0 = ws + lane; i0 < we; i0 += 32 * ZS_U) {
+            KeyT kk[ZS_U];
+#pragma unroll
+            for (int u = 0; u < ZS_U; ++u) {
+                const uint32_t i = i0 + 32 * u;
+                if (i < we) { if (first) { kk[u] = key_of(i); keyA[i] = kk[u]; } else kk[u] = kin[i]; }
+            }
+#pragma unroll
+            for (int u = 0; u < ZS_U; ++u)
+                if (i0 + 32 * u < we) atomicAdd(&s_hist[w][(uint32_t)(kk[u] >> shift) & 255u], 1u);
         }
         __syncthreads();
         // ---- offsets: digit-major exclusive scan over (digit, warp)
@@ -1035,26 +1055,37 @@ __device__ __forceinline__ void cta_radix_sort(uint32_t n, int passes, KeyFn key
         }
         __syncthreads();
         // ---- stable scatter
-        for (uint32_t i0 = ws; i0 < we; i0 += 32) {
-            const uint32_t i = i0 + lane;
-            const bool ok = i < we;
-            KeyT key = 0;
-            uint32_t idx = 0, d = 0xffffffffu;
-            if (ok) {
-                key = first ? keyA[i] : kin[i];
-                idx = first ? value_of(i) : iin[i];
-                d = (uint32_t)(key >> shift) & 255u;
+        for (uint32_t c0 = ws; c0 < we; c0 += 32 * ZS_U) {
+            KeyT kk[ZS_U];
+            uint32_t ii[ZS_U];
+#pragma unroll
+            for (int u = 0; u < ZS_U; ++u) {
+                const uint32_t i = c0 + 32 * u + lane;
+                kk[u] = 0; ii[u] = 0;
+                if (i < we) {
+                    kk[u] = first ? keyA[i] : kin[i];
+                    ii[u] = first ? value_of(i) : iin[i];
+                }
             }
-            const uint32_t peers = __match_any_sync(0xffffffffu, d);
-            const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
-            uint32_t pos = 0;
-            if (ok) pos = s_hist[w][d] + rank;
-            __syncwarp();
-            if (ok && rank == 0) s_hist[w][d] += __popc(peers);      // the lowest lane of each digit group advances the offset
-            __syncwarp();
-            if (ok) {
-                if (last) out[pos] = idx;
-                else { kout[pos] = key; iout[pos] = idx; }
+#pragma unroll
+            for (int u = 0; u < ZS_U; ++u) {
+                if (c0 + 32 * u >= we) break;                      // (warp-uniform)
+                const uint32_t i = c0 + 32 * u + lane;
+                const bool ok = i < we;
+                const KeyT key = kk[u];
+                const uint32_t idx = ii[u];
+                const uint32_t d = ok ? ((uint32_t)(key >> shift) & 255u) : 0xffffffffu;
+                const uint32_t peers = __match_any_sync(0xffffffffu, d);
+                const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
+                uint32_t pos = 0;
+                if (ok) pos = s_hist[w][d] + rank;
+                __syncwarp();
+                if (ok && rank == 0) s_hist[w][d] += __popc(peers);      // the lowest lane of each digit group advances the offset
+                __syncwarp();
+                if (ok) {
+                    if (last) out[pos] = idx;
+                    else { kout[pos] = key; iout[pos] = idx; }
+                }
             }
         }
         __syncthreads();
