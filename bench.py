@@ -444,7 +444,8 @@ def run_ours(args, Z, H, W, cfg):
         kst = engine._stream()
         # the kernel the single-enqueue step streams the masks with: threshold + stack + z gap fill + per-slice counts
         # (k_pack_gap); stacks it does not take (W % 128 != 0, fewer than 3 slices) go through the plain pack kernel
-        pack_gap = n_own >= 3 and W % 128 == 0 and not sharded_run   # (the sharded step packs with t3d_slab_pack: k_pack_flat)
+        # (a sharded step runs the same kernel over the interior planes of its slab when the slab has >= 16 slices: t3d_slab_pack)
+        pack_gap = n_own >= 3 and W % 128 == 0 and (not sharded_run or n_own >= 16)
         kcnt = torch.empty(n_own, dtype=torch.int64, device=dev)
         kbb = torch.empty(6, dtype=torch.int32, device=dev)
 

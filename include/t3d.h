@@ -246,9 +246,16 @@ int t3d_reconstruct(const void* masks_u8, int Z, int H, int W, int threshold, in
  *   [19] lead: canonical vertices with z == z_lead (this rank's first plane), if want_lead.
  * t3d_slab_pack packs the own slices (uint8, n_own x H x W) into ext_bits and fills the holes of the global end slices
  * (fill_first / fill_last; fill_scratch = t3d_fill_holes_scratch_bytes(2, H, W)) on an internal side stream, which
- * t3d_reconstruct_slab joins when join_fill != 0 -- the halo exchange in between does not wait for it. */
+ * t3d_reconstruct_slab joins when join_fill != 0 -- the halo exchange in between does not wait for it.
+ * Pre-filled mode (pre_grid_bits and pre_stats_u64 non-NULL in BOTH calls; allowed when t3d_slab_pack_gap_ok returns 1: at
+ * least 16 own slices, W % 128 == 0, 16-byte aligned masks, 1 <= threshold <= 255): the own planes [4, n_own - 4) depend on
+ * no neighbour, so t3d_slab_pack sends them through the one-pass kernel of t3d_pack_gap straight into pre_grid_bits (a
+ * halo_lo + n_own + halo_hi plane bit volume) with their counts / extrema in pre_stats_u64 (that many + 3 uint64), and packs
+ * only the 8 own planes at either end raw into ext_bits (what the halo exchange sends); t3d_reconstruct_slab then gap-fills
+ * just the two ends into pre_grid_bits.  Same results as the plain mode; the uint8 stack is read once. */
+int t3d_slab_pack_gap_ok(const void* masks_u8, int n_own, int H, int W, int threshold);
 int t3d_slab_pack(const void* masks_u8, int n_own, int H, int W, int threshold, int halo_lo, int halo_hi, int fill_first,
-                  int fill_last, void* ext_bits, void* fill_scratch, void* stream);
+                  int fill_last, void* ext_bits, void* fill_scratch, void* pre_grid_bits, void* pre_stats_u64, void* stream);
 int64_t t3d_reconstruct_slab_workspace_bytes(int halo_lo, int n_own, int halo_hi, int H, int W, int add_padding, int n_stages,
                                              uint32_t cap_active, uint32_t cap_verts, uint32_t cap_faces, uint32_t cap_zverts,
                                              uint32_t cap_g0);
@@ -257,7 +264,8 @@ int t3d_reconstruct_slab(const void* ext_bits, int halo_lo, int n_own, int halo_
                          int want_lead, float z_lead, int join_fill, const double* weights3_host, const void* cum_f64, const void* adj_f64,
                          int n_cum, double mm_per_pixel_y, double mm_per_pixel_x, int scale_in_f64, uint32_t cap_active,
                          uint32_t cap_verts, uint32_t cap_faces, uint32_t cap_zverts, uint32_t cap_g0, int zkey_bits,
-                         void* verts_out_f32, void* faces_out_i64, void* results_u64, void* workspace, void* stream);
+                         void* verts_out_f32, void* faces_out_i64, void* results_u64, void* workspace, void* pre_grid_bits,
+                         const void* pre_stats_u64, void* stream);
 /* faces_i64[0 .. 3*F'[rank]) += sum over lower ranks of (V' - ghost tail), read from the all-gathered result blocks
  * (world x stride_u64 uint64 on the device): local vertex ids -> ids in the stitched mesh. */
 int t3d_slab_stitch_faces(void* faces_i64, int64_t cap_faces, const void* gathered_results_u64, int64_t stride_u64, int rank,

@@ -74,7 +74,7 @@ def test_sharded_slabs_stitch_to_the_single_gpu_mesh(eng, oracle, shape, world):
 
 
 @pytest.mark.parametrize("world", [1, 2, 3])
-@pytest.mark.parametrize("shape", [(40, 64, 96), (53, 70, 130)])
+@pytest.mark.parametrize("shape", [(40, 64, 96), (53, 70, 130), (72, 40, 128), (50, 37, 256)])
 def test_fused_slab_path_stitches_to_the_single_gpu_mesh(eng, oracle, shape, world):
     """t3d_reconstruct_slab + t3d_slab_stitch_faces (the sharded step without host synchronisation), all ranks emulated on
     ONE GPU: device copies stand in for the NCCL halo exchange and the all-gather of the result blocks."""
@@ -92,6 +92,8 @@ def test_fused_slab_path_stitches_to_the_single_gpu_mesh(eng, oracle, shape, wor
              for r, (a, b) in enumerate(ranges)]
     for pl, (a, b) in zip(plans, ranges):
         pl.pack(full[a:b].contiguous())
+    # slabs the one-pass pack kernel takes (W % 128 == 0, >= 16 slices) run in the pre-filled mode, the others in the plain one
+    assert [pl.pre_active for pl in plans] == [W % 128 == 0 and (b - a) >= 16 for a, b in ranges]
     for r, s in enumerate(plans):
         if s.hl:
             lo = plans[r - 1]

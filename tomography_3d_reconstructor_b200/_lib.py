@@ -70,9 +70,10 @@ SIGNATURES = {
     "t3d_reconstruct": (_i, [_vp, _i, _i, _i, _i, _i, _i, _c.c_uint, _i, _vp, _vp, _vp, _i, _dbl, _dbl, _i, _u32, _u32, _u32,
                              _u32, _u32, _i, _vp, _vp, _vp, _vp, _vp]),
     "t3d_reconstruct_slab_workspace_bytes": (_i64, [_i, _i, _i, _i, _i, _i, _i, _u32, _u32, _u32, _u32, _u32]),
-    "t3d_slab_pack": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "t3d_slab_pack_gap_ok": (_i, [_vp, _i, _i, _i, _i]),
+    "t3d_slab_pack": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "t3d_reconstruct_slab": (_i, [_vp, _i, _i, _i, _i, _i, _i, _c.c_uint, _i, _i, _i, _i, _i, _c.c_float, _i, _c.c_float, _i, _vp, _vp,
-                                  _vp, _i, _dbl, _dbl, _i, _u32, _u32, _u32, _u32, _u32, _i, _vp, _vp, _vp, _vp, _vp]),
+                                  _vp, _i, _dbl, _dbl, _i, _u32, _u32, _u32, _u32, _u32, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "t3d_slab_stitch_faces": (_i, [_vp, _i64, _vp, _i64, _i, _vp]),
     "t3d_edt_workspace_bytes": (_i64, [_i, _i, _i]),
     "t3d_edt_xy_workspace_bytes": (_i64, [_i, _i, _i]),

@@ -170,7 +170,9 @@ bool t3d_canon_faces_ready_pending();
 // fused pack + z gap fill + per-slice counts + extrema (see t3d_voxel.cu)
 bool t3d_pack_gap_supported(const void* masks_u8, int Z, int H, int W, int threshold);
 int t3d_pack_gap_launch(const void* masks_u8, int Z, int H, int W, int threshold, void* out, unsigned long long* counts,
-                        unsigned int* bbox_t, int skip_ends, cudaStream_t st);
+                        unsigned int* bbox_t, int skip_ends, cudaStream_t st, int z_bias = 0);
+// extrema of a few planes in the same transformed form (plane p of the call = plane z_bias + p)
+int t3d_bbox_t_planes_launch(const uint32_t* bits, int n_planes, int H, int W, int z_bias, unsigned int* bbox_t, cudaStream_t st);
 int t3d_close_ends_fixup_launch(const void* masks_u8, int Z, int H, int W, int threshold, const void* filled0, const void* filledT,
                                 void* out, unsigned long long* counts, cudaStream_t st);
 

@@ -548,16 +548,58 @@ extern "C" int t3d_reconstruct(const void* masks_u8, int Z, int H, int W, int th
 // fill_last) are packed first and hole-filled on the side stream while the other slices are packed; t3d_reconstruct_slab
 // joins the side stream (join_fill), so the halo exchange in between does not wait for the fill.  (The filled slice is
 // part of a halo only if the slab is thinner than the halo; then the fill is joined here.)
+// counts of the interior planes [za, zb) and the transformed extrema of the pack kernel -> the result block (zeroed before)
+__global__ void k_merge_pre_stats(unsigned long long* __restrict__ r, const unsigned long long* __restrict__ pre, int Zx, int za, int zb)
+{
+    const int z = blockIdx.x * blockDim.x + threadIdx.x;
+    if (z >= za && z < zb) r[R_COUNTS + z] = pre[z];
+    if (z < 6) atomicMax((unsigned int*)(r + R_BBOX_I32X6) + z, ((const unsigned int*)(pre + Zx))[z]);
+}
+
+// Pre-filled mode (pre_grid_bits / pre_stats_u64 given; t3d_slab_pack_gap_ok says when it applies): the interior of the slab
+// -- own planes [SLAB_EDGE, n_own - SLAB_EDGE) -- does not depend on any neighbour's data, so it goes through the one-pass
+// kernel of the single-device path (k_pack_gap: threshold + stack + z gap fill + slice counts + extrema, masks read once)
+// straight into pre_grid_bits, a (halo_lo + n_own + halo_hi)-plane buffer, with its counts / extrema in pre_stats_u64
+// (Zx + 3 uint64).  Only the SLAB_RAW own planes at either end are packed raw into ext_bits: those are what the halo exchange
+// sends and what t3d_reconstruct_slab gap-fills together with the received halo planes.
+#define SLAB_EDGE 4     // own planes at either end of a slab whose gap fill is left to t3d_reconstruct_slab
+#define SLAB_RAW 8      // own planes at either end packed raw into the exchange buffer (>= the halo depth and > SLAB_EDGE)
+
+extern "C" int t3d_slab_pack_gap_ok(const void* masks_u8, int n_own, int H, int W, int threshold)
+{
+    static const bool off = getenv("T3D_NO_SLAB_PACK_GAP") != nullptr;
+    if (off || n_own < 2 * SLAB_RAW || H <= 0 || W <= 0) return 0;
+    const uint8_t* sub = (const uint8_t*)masks_u8 + (int64_t)(SLAB_EDGE - 2) * H * W;
+    return t3d_pack_gap_supported(sub, n_own - 2 * SLAB_EDGE + 4, H, W, threshold) ? 1 : 0;
+}
+
 extern "C" int t3d_slab_pack(const void* masks_u8, int n_own, int H, int W, int threshold, int halo_lo, int halo_hi, int fill_first,
-                             int fill_last, void* ext_bits, void* fill_scratch, void* stream)
+                             int fill_last, void* ext_bits, void* fill_scratch, void* pre_grid_bits, void* pre_stats_u64, void* stream)
 {
     if (n_own <= 0 || H <= 0 || W <= 0 || halo_lo < 0) { t3d_set_error("t3d_slab_pack: bad slab"); return 2; }
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t nw = t3d_words_per_row(W), plane_words = (int64_t)H * nw, plane_bytes = (int64_t)H * W;
     const uint8_t* m = (const uint8_t*)masks_u8;
     uint32_t* own = (uint32_t*)ext_bits + (int64_t)halo_lo * plane_words;
+    const bool pre = pre_grid_bits != nullptr;
+    if (pre) {
+        if (!pre_stats_u64 || !t3d_slab_pack_gap_ok(masks_u8, n_own, H, W, threshold)) {
+            t3d_set_error("t3d_slab_pack: pre-filled mode needs pre_stats_u64 and a slab t3d_slab_pack_gap_ok accepts");
+            return 2;
+        }
+        const int Zx = halo_lo + n_own + halo_hi, a0 = SLAB_EDGE - 2, zsub = n_own - 2 * SLAB_EDGE + 4;
+        unsigned long long* ps = (unsigned long long*)pre_stats_u64;
+        T3D_CUDA(cudaMemsetAsync(ps, 0, sizeof(unsigned long long) * ((size_t)Zx + 3), st));
+        RUN(t3d_pack_gap_launch(m + (int64_t)a0 * plane_bytes, zsub, H, W, threshold,
+                                (uint32_t*)pre_grid_bits + (int64_t)(halo_lo + a0) * plane_words, ps + halo_lo + a0,
+                                (unsigned int*)(ps + Zx), 1, st, a0));
+    }
     if (fill_last && n_own == 1 && fill_first) fill_last = 0;   // one slice: filled once
-    if (!fill_first && !fill_last) return t3d_pack_masks(m, n_own, H, W, threshold, own, st);
+    if (!fill_first && !fill_last) {
+        if (!pre) return t3d_pack_masks(m, n_own, H, W, threshold, own, st);
+        RUN(t3d_pack_masks(m, SLAB_RAW, H, W, threshold, own, st));
+        return t3d_pack_masks(m + (int64_t)(n_own - SLAB_RAW) * plane_bytes, SLAB_RAW, H, W, threshold, own + (int64_t)(n_own - SLAB_RAW) * plane_words, st);
+    }
     SideStream* side;
     RUN(side_for_current_device(&side));
     const int lo = fill_first ? 1 : 0, hi = fill_last ? n_own - 1 : n_own;   // [lo, hi) = slices that are not filled
@@ -572,7 +614,11 @@ extern "C" int t3d_slab_pack(const void* masks_u8, int n_own, int H, int W, int 
         RUN(t3d_fill_holes_2d(fill_first ? own : own + (int64_t)(n_own - 1) * plane_words, 1, 0, H, W, scratch, side->s));
     }
     T3D_CUDA(cudaEventRecord(side->e[1], side->s));
-    if (hi > lo) RUN(t3d_pack_masks(m + (int64_t)lo * plane_bytes, hi - lo, H, W, threshold, own + (int64_t)lo * plane_words, st));
+    if (pre) {      // only the raw end ranges [lo, SLAB_RAW) and [n_own - SLAB_RAW, hi)
+        RUN(t3d_pack_masks(m + (int64_t)lo * plane_bytes, SLAB_RAW - lo, H, W, threshold, own + (int64_t)lo * plane_words, st));
+        const int b0 = n_own - SLAB_RAW;
+        RUN(t3d_pack_masks(m + (int64_t)b0 * plane_bytes, hi - b0, H, W, threshold, own + (int64_t)b0 * plane_words, st));
+    } else if (hi > lo) RUN(t3d_pack_masks(m + (int64_t)lo * plane_bytes, hi - lo, H, W, threshold, own + (int64_t)lo * plane_words, st));
     const int halo = halo_lo > halo_hi ? halo_lo : halo_hi;
     if (n_own <= halo) T3D_CUDA(cudaStreamWaitEvent(st, side->e[1], 0));
     return 0;
@@ -586,9 +632,10 @@ extern "C" int t3d_reconstruct_slab(const void* ext_bits, int halo_lo, int n_own
                                     const void* adj_f64, int n_cum, double mm_per_pixel_y, double mm_per_pixel_x, int scale_in_f64,
                                     uint32_t cap_active, uint32_t cap_verts, uint32_t cap_faces, uint32_t cap_zverts, uint32_t cap_g0,
                                     int zkey_bits, void* verts_out_f32, void* faces_out_i64, void* results_u64, void* workspace,
-                                    void* stream)
+                                    void* pre_grid_bits, const void* pre_stats_u64, void* stream)
 {
     if (n_own <= 0 || H <= 0 || W <= 0 || halo_lo < 0 || halo_hi < 0) { t3d_set_error("t3d_reconstruct_slab: bad slab"); return 2; }
+    if (pre_grid_bits && (!pre_stats_u64 || n_own < 2 * SLAB_RAW)) { t3d_set_error("t3d_reconstruct_slab: bad pre-filled slab"); return 2; }
     if (cap_active == 0 || cap_verts == 0 || cap_faces == 0) { t3d_set_error("t3d_reconstruct_slab: zero capacity"); return 2; }
     cudaStream_t st = (cudaStream_t)stream;
     const int pad = add_padding ? 1 : 0, Zx = halo_lo + n_own + halo_hi;
@@ -615,11 +662,31 @@ extern "C" int t3d_reconstruct_slab(const void* ext_bits, int halo_lo, int n_own
         RUN(zg.launch(st));
     }
     if (join_fill) T3D_CUDA(cudaStreamWaitEvent(st, side->e[1], 0));   // hole filling started by t3d_slab_pack
-    RUN(t3d_gap_fill(ext_bits, ws + L.bitsB, nullptr, nullptr, Zx, H, W, R + R_COUNTS, st));
     SlabGeom g = {halo_lo, n_own, halo_hi, z_begin, z_end, z_offset, want_ghost, want_lead, z_ghost, z_lead};
-    RUN(reconstruct_core((const uint32_t*)(ws + L.bitsB), g, H, W, n_stages, erode_mask, pad, weights3_host, cum_f64, adj_f64, n_cum,
+    const uint32_t* grid = (const uint32_t*)(ws + L.bitsB);
+    int bbox_state = 0;
+    if (pre_grid_bits) {
+        // the interior own planes are final in pre_grid_bits (t3d_slab_pack): gap-fill the two ends -- halo planes + SLAB_EDGE own
+        // planes each, with the raw plane beyond as the outer neighbour -- and merge the pack kernel's counts / extrema
+        const int64_t pw = (int64_t)H * t3d_words_per_row(W);
+        const uint32_t* ext = (const uint32_t*)ext_bits;
+        uint32_t* pg = (uint32_t*)pre_grid_bits;
+        const int zl = halo_lo + SLAB_EDGE, p0 = halo_lo + n_own - SLAB_EDGE;
+        RUN(t3d_gap_fill(ext, pg, nullptr, ext + (int64_t)zl * pw, zl, H, W, R + R_COUNTS, st));
+        RUN(t3d_gap_fill(ext + (int64_t)p0 * pw, pg + (int64_t)p0 * pw, ext + (int64_t)(p0 - 1) * pw, nullptr, Zx - p0, H, W, R + R_COUNTS + p0, st));
+        k_merge_pre_stats<<<(Zx + 255) / 256, 256, 0, st>>>(R, (const unsigned long long*)pre_stats_u64, Zx, zl, p0);
+        t3d_count_launches(1);
+        unsigned int* bb = (unsigned int*)(R + R_BBOX_I32X6);
+        RUN(t3d_bbox_t_planes_launch(pg + (int64_t)halo_lo * pw, SLAB_EDGE, H, W, 0, bb, st));
+        RUN(t3d_bbox_t_planes_launch(pg + (int64_t)p0 * pw, SLAB_EDGE, H, W, n_own - SLAB_EDGE, bb, st));
+        grid = pg;
+        bbox_state = 2;
+    } else {
+        RUN(t3d_gap_fill(ext_bits, ws + L.bitsB, nullptr, nullptr, Zx, H, W, R + R_COUNTS, st));
+    }
+    RUN(reconstruct_core(grid, g, H, W, n_stages, erode_mask, pad, weights3_host, cum_f64, adj_f64, n_cum,
                          mm_per_pixel_y, mm_per_pixel_x, scale_in_f64, cap_active, cap_verts, cap_faces, cap_zverts, cap_g0, zkey_bits,
-                         verts_out_f32, faces_out_i64, R, ws, L, fast, 0, side, st));
+                         verts_out_f32, faces_out_i64, R, ws, L, fast, bbox_state, side, st));
     T3D_CHECK_LAUNCH("t3d_reconstruct_slab");
     t3d_count_launches(1);
     return 0;

@@ -493,6 +493,7 @@ struct PackGapArgs {
     uint32_t thr4;
     int zc;                       // planes per chunk (<= PG_ZC)
     int skip_ends;                // planes 0, 1, Z-2, Z-1 are not counted here (k_close_ends_fixup counts them)
+    int z_bias;                   // added to the z extrema (a sub-stack of a z-slab reports planes of the slab)
     unsigned long long* counts;   // Z per-slice counts (zeroed by the caller) or null
     unsigned int* bbox_t;         // 6 transformed extrema {z, y, x} x {INT_MAX - min, max + 1} (zeroed by the caller) or null
 };
@@ -609,7 +610,7 @@ __global__ void __launch_bounds__(256) k_pack_gap(PackGapArgs a)
         ymin = __reduce_min_sync(0xffffffffu, ymin); ymax = __reduce_max_sync(0xffffffffu, ymax);
         xmin = __reduce_min_sync(0xffffffffu, xmin); xmax = __reduce_max_sync(0xffffffffu, xmax);
         if (l == 0) {
-            atomicMax(&s_bb[0], (unsigned)(0x7fffffff - zmin)); atomicMax(&s_bb[1], (unsigned)(zmax + 1));
+            atomicMax(&s_bb[0], (unsigned)(0x7fffffff - (zmin + a.z_bias))); atomicMax(&s_bb[1], (unsigned)(zmax + a.z_bias + 1));
             atomicMax(&s_bb[2], (unsigned)(0x7fffffff - ymin)); atomicMax(&s_bb[3], (unsigned)(ymax + 1));
             atomicMax(&s_bb[4], (unsigned)(0x7fffffff - xmin)); atomicMax(&s_bb[5], (unsigned)(xmax + 1));
         }
@@ -681,9 +682,10 @@ bool t3d_pack_gap_supported(const void* masks_u8, int Z, int H, int W, int thres
 // masks -> gap-filled grid `out` (end planes still raw), per-slice counts (zeroed by the caller; planes 0, 1, Z-2, Z-1
 // left out when skip_ends) and transformed extrema (6 uint32 zeroed by the caller, may be null)
 int t3d_pack_gap_launch(const void* masks_u8, int Z, int H, int W, int threshold, void* out, unsigned long long* counts,
-                        unsigned int* bbox_t, int skip_ends, cudaStream_t st)
+                        unsigned int* bbox_t, int skip_ends, cudaStream_t st, int z_bias)
 {
     PackGapArgs a;
+    a.z_bias = z_bias;
     a.src = (const uint8_t*)masks_u8; a.dst = (uint32_t*)out;
     a.Z = Z; a.nw = t3d_wpr(W);
     a.plane_words = (long long)H * a.nw; a.plane_bytes = (long long)H * W;
@@ -719,6 +721,43 @@ extern "C" int t3d_pack_gap(const void* masks_u8, int Z, int H, int W, int thres
     if (counts_u64 && t3d_zero_async(counts_u64, sizeof(unsigned long long) * Z, st)) return 1;
     if (bbox_u32x6 && t3d_zero_async(bbox_u32x6, 6 * sizeof(unsigned int), st)) return 1;
     return t3d_pack_gap_launch(masks_u8, Z, H, W, threshold, bits, (unsigned long long*)counts_u64, (unsigned int*)bbox_u32x6, 0, st);
+}
+
+// extrema of the set voxels of `n_planes` planes in k_pack_gap's transformed form ({INT_MAX - min, max + 1} under atomicMax on
+// zero-initialised memory); plane p of the call is plane z_bias + p of the slab.  One CTA per (plane, band of rows).
+__global__ void __launch_bounds__(256) k_bbox_t_planes(const uint32_t* __restrict__ bits, int H, int nw, int z_bias, unsigned int* __restrict__ bbox_t)
+{
+    const int z = blockIdx.y;
+    const uint32_t* p = bits + (long long)z * H * nw;
+    const int rows_per = (H + gridDim.x - 1) / gridDim.x;
+    const int ya = blockIdx.x * rows_per, yb = min(H, ya + rows_per);
+    int ymin = 0x7fffffff, ymax = -1, xmin = 0x7fffffff, xmax = -1;
+    for (long long i = (long long)ya * nw + threadIdx.x; i < (long long)yb * nw; i += 256) {
+        const uint32_t v = p[i];
+        if (v) {
+            const int y = (int)(i / nw), w = (int)(i - (long long)y * nw);
+            ymin = min(ymin, y); ymax = max(ymax, y);
+            xmin = min(xmin, (w << 5) + __ffs(v) - 1);
+            xmax = max(xmax, (w << 5) + 31 - __clz(v));
+        }
+    }
+    ymin = __reduce_min_sync(0xffffffffu, ymin); ymax = __reduce_max_sync(0xffffffffu, ymax);
+    xmin = __reduce_min_sync(0xffffffffu, xmin); xmax = __reduce_max_sync(0xffffffffu, xmax);
+    if ((threadIdx.x & 31) == 0 && ymax >= 0) {
+        atomicMax(bbox_t + 0, (unsigned)(0x7fffffff - (z + z_bias))); atomicMax(bbox_t + 1, (unsigned)(z + z_bias + 1));
+        atomicMax(bbox_t + 2, (unsigned)(0x7fffffff - ymin)); atomicMax(bbox_t + 3, (unsigned)(ymax + 1));
+        atomicMax(bbox_t + 4, (unsigned)(0x7fffffff - xmin)); atomicMax(bbox_t + 5, (unsigned)(xmax + 1));
+    }
+}
+
+int t3d_bbox_t_planes_launch(const uint32_t* bits, int n_planes, int H, int W, int z_bias, unsigned int* bbox_t, cudaStream_t st)
+{
+    if (n_planes <= 0) return 0;
+    dim3 grid((unsigned)min(8, H), (unsigned)n_planes);
+    k_bbox_t_planes<<<grid, 256, 0, st>>>(bits, H, t3d_wpr(W), z_bias, bbox_t);
+    T3D_CHECK_LAUNCH("t3d_bbox_t_planes");
+    t3d_count_launches(1);
+    return 0;
 }
 
 int t3d_close_ends_fixup_launch(const void* masks_u8, int Z, int H, int W, int threshold, const void* filled0, const void* filledT,

@@ -372,16 +372,27 @@ class FusedSlabPlan:
             np.concatenate([r * self.stride + np.arange(a_, b_) for r, (a_, b_) in enumerate(spans)])
             for spans in (self.raw_spans, self.sm_spans)])
         self.last_view, self.last_view_key = None, None
+        # pre-filled mode (see pack()): interior planes of the gap-filled grid written by the pack kernel itself
+        self.grid, self.pre, self.pre_active = None, None, False
         # compute() joins the library's side stream when pack() started the hole filling of a global end slice there
         self.join_fill = self.z0 == 0 or self.z1 == self.Zg
 
     def pack(self, masks_u8: torch.Tensor) -> None:
         """Own slices -> planes [hl, hl+n) of the extended buffer; the holes of the global end slices are filled on the
-        library's side stream (joined by compute())."""
+        library's side stream (joined by compute()).  Slabs the one-pass kernel takes (t3d_slab_pack_gap_ok) go through the
+        pre-filled mode: the interior own planes are thresholded, gap-filled and counted in ONE pass over the masks into
+        self.grid, only the 8 planes at either end are packed raw for the halo exchange (include/t3d.h, t3d_slab_pack)."""
         p = engine._p
-        engine.check(engine._L().t3d_slab_pack(p(masks_u8), self.n, self.H, self.W, self.threshold, self.hl, self.hh,
-                                               int(self.z0 == 0), int(self.z1 == self.Zg), p(self.ext), p(self.fill),
-                                               engine._stream()), "t3d_slab_pack")
+        L = engine._L()
+        self.pre_active = bool(L.t3d_slab_pack_gap_ok(p(masks_u8), self.n, self.H, self.W, self.threshold))
+        if self.pre_active and self.grid is None:
+            Zx = self.hl + self.n + self.hh
+            self.grid = torch.empty((Zx, self.H, engine.words_per_row(self.W)), dtype=torch.int32, device=self.dev)
+            self.pre = torch.empty(Zx + 3, dtype=torch.int64, device=self.dev)
+        engine.check(L.t3d_slab_pack(p(masks_u8), self.n, self.H, self.W, self.threshold, self.hl, self.hh,
+                                     int(self.z0 == 0), int(self.z1 == self.Zg), p(self.ext), p(self.fill),
+                                     p(self.grid) if self.pre_active else None, p(self.pre) if self.pre_active else None,
+                                     engine._stream()), "t3d_slab_pack")
 
     def compute(self) -> None:
         """Everything between the halo exchange and the result gather: one t3d_reconstruct_slab enqueue."""
@@ -391,7 +402,8 @@ class FusedSlabPlan:
             self.z_begin, self.z_end, self.z_offset, self.want_ghost, self.z_ghost, self.want_lead, self.z_lead,
             int(self.join_fill), engine._W3_C,
             p(self.cum_d), p(self.adj_d), self.n_cum, float(self.mm_y), float(self.mm_x), 0, self.caps[0], self.caps[1],
-            self.caps[2], self.caps[3], self.caps[4], self.zkey_bits, p(self.verts), p(self.faces), p(self.res), p(self.ws), engine._stream()), "t3d_reconstruct_slab")
+            self.caps[2], self.caps[3], self.caps[4], self.zkey_bits, p(self.verts), p(self.faces), p(self.res), p(self.ws),
+            p(self.grid) if self.pre_active else None, p(self.pre) if self.pre_active else None, engine._stream()), "t3d_reconstruct_slab")
 
     def stitch(self) -> None:
         """Local face ids -> ids in the stitched mesh, from the gathered result blocks (device side)."""
