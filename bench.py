@@ -400,6 +400,14 @@ def run_ours(args, Z, H, W, cfg):
             sharded.reconstruct_fused(masks, Zg, z0, THRESHOLD, sides, *phys, use_graph=False)
         else:
             pipeline.reconstruct_fused(masks, THRESHOLD, sides, *phys, use_graph=False)
+    elif path == "batch":
+        # every volume of the batch is one t3d_reconstruct enqueue replayed from its slot's graph: count one eager enqueue of one
+        # volume of this shape (after a staged call that learns its capacities) and multiply
+        one = next(iter(stacks.values()))
+        pipeline.reconstruct_fused(one, THRESHOLD, sides, *phys, use_graph=False)
+        lc0 = lib.t3d_launch_count()
+        pipeline.reconstruct_fused(one, THRESHOLD, sides, *phys, use_graph=False)
+        lc0 -= (lib.t3d_launch_count() - lc0) * (len(stacks) - 1)
     else:
         step()
     launches_per_step = lib.t3d_launch_count() - lc0
