@@ -382,7 +382,12 @@ def run_ours(args, Z, H, W, cfg):
         hist = torch.from_numpy(sharded.vertices_per_slice(res, Zg)).to(dev)
         dist.all_reduce(hist)
         # (the volume passes of a slice cost about as much as ~2900 mesh vertices at 1024x1024, in proportion to the slice area)
-        partition = sharded.balanced_ranges(sharded.slice_cost(hist.cpu().numpy(), 2900.0 * (H * W) / (1024.0 * 1024.0)), world,
+        # cost of a slice in units of one surface vertex.  Kernel times alone say ~1950 (volume kernels ~0.38 us per 1024 x 1024
+        # slice, mesh kernels ~0.19 us per 1000 vertices), but the end ranks also fill the holes of an end slice and sort the
+        # large polar layers: measured at N = 8, 2900 beats 1950 (C1 0.750 against 0.783 ms per step, 4096^3 5.32 against 5.51 ms;
+        # profiles/r02_balance_constant_n8.txt).  T3D_BALANCE_SLICE_COST overrides it.
+        slice_units = float(os.environ.get("T3D_BALANCE_SLICE_COST", "2900")) * (H * W) / (1024.0 * 1024.0)
+        partition = sharded.balanced_ranges(sharded.slice_cost(hist.cpu().numpy(), slice_units), world,
                                             sharded.HALO)
         sharded.set_partition(Zg, world, partition)
         z0, z1 = partition[rank]
