@@ -646,10 +646,12 @@ __global__ void __launch_bounds__(SC_THREADS) k_unique_fused(const float* __rest
                                                              const unsigned long long* __restrict__ V_dev, float* __restrict__ out_verts,
                                                              uint32_t* __restrict__ newid, unsigned long long* __restrict__ desc, int n_tiles,
                                                              unsigned int* __restrict__ ticket, unsigned long long* __restrict__ bad,
-                                                             unsigned long long* __restrict__ n_unique_out)
+                                                             unsigned long long* __restrict__ n_unique_out,
+                                                             const unsigned long long* __restrict__ skip_unless)
 {
     // striped arrangement: element e = k * SC_THREADS + tid of the tile, so a warp always touches 32 consecutive sorted
     // positions (coalesced perm reads, neighbouring vertices); keys go through shared memory for the neighbour compare
+    if (skip_unless && *skip_unless == 0) return;      // the optimistic pass (k_unique_optimistic) already wrote everything
     const int64_t n = dev_n(V_cap, V_dev);
     volatile unsigned long long* d = desc;
     __shared__ int s_tile;
@@ -760,6 +762,41 @@ __global__ void __launch_bounds__(SC_THREADS) k_unique_fused(const float* __rest
     }
 }
 
+// The same np.unique under the assumption that NO two vertices coincide (the rule on a marching-cubes mesh: duplicates need a
+// field value of exactly 0.5 at a grid point): then the unique index of a vertex is its sorted position and there is nothing
+// to scan -- one streaming pass: gather the vertex, write it and its new id, compare it with its predecessor.  Any equal pair
+// raises *dup and the exact kernel above (enqueued right behind, returning at once while *dup == 0) redoes the step.
+__global__ void __launch_bounds__(256) k_unique_optimistic(const float* __restrict__ verts, const uint32_t* __restrict__ perm, int64_t V_cap,
+                                                           const unsigned long long* __restrict__ V_dev, float* __restrict__ out_verts,
+                                                           uint32_t* __restrict__ newid, unsigned long long* __restrict__ bad,
+                                                           unsigned long long* __restrict__ n_unique_out, unsigned long long* __restrict__ dup)
+{
+    const int64_t n = dev_n(V_cap, V_dev);
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) *n_unique_out = (unsigned long long)n;
+    const bool ok = i < n;
+    uint32_t src = 0, kz = 0, ky = 0, kx = 0;
+    if (ok) {
+        src = perm[i];
+        const float* a = verts + 3 * (int64_t)src;
+        const float z = a[0], y = a[1], x = a[2];
+        float* o = out_verts + 3 * i;
+        o[0] = z; o[1] = y; o[2] = x;
+        newid[src] = (uint32_t)i;
+        kz = float_key(z); ky = float_key(y); kx = float_key(x);
+    }
+    // predecessor: the lane below, or (lane 0) one more gather
+    uint32_t pz = __shfl_up_sync(0xffffffffu, kz, 1), py = __shfl_up_sync(0xffffffffu, ky, 1), px = __shfl_up_sync(0xffffffffu, kx, 1);
+    if ((threadIdx.x & 31) == 0 && ok && i > 0) {
+        const float* b = verts + 3 * (int64_t)perm[i - 1];
+        pz = float_key(b[0]); py = float_key(b[1]); px = float_key(b[2]);
+    }
+    if (ok && i > 0) {
+        if (kz == pz && ky == py && kx == px) atomicOr(dup, 1ull);
+        else if ((kz < pz) || (kz == pz && (ky < py || (ky == py && kx < px)))) atomicOr(bad, 1ull);
+    }
+}
+
 // everything after the sorted permutation is known: head flags + order check, unique scatter, face remap
 // The single-enqueue pipeline emits the faces on its side stream while the vertices are being ordered here: it registers
 // the event "faces emitted" and the tail waits for it right before the first kernel that reads the faces (the kernels before
@@ -780,8 +817,16 @@ static int canonical_tail(const float* vin, const uint32_t* perm, int64_t V, con
         const int64_t nb = (V + UQ_TILE - 1) / UQ_TILE;
         const size_t desc_bytes = (size_t)nb * 8;
         if (t3d_zero_async(scan_ws, desc_bytes + 64, st)) return 1;
+        static const bool optimistic = getenv("T3D_NO_OPTIMISTIC_UNIQUE") == nullptr;
+        unsigned long long* dup = nullptr;
+        if (optimistic) {
+            dup = totals + 8;
+            if (t3d_zero_async(dup, 8, st)) return 1;
+            k_unique_optimistic<<<(unsigned)((V + 255) / 256), 256, 0, st>>>(vin, perm, V, V_dev, (float*)verts_out, newid, counts + 2, counts, dup);
+            t3d_count_launches(1);
+        }
         k_unique_fused<<<(unsigned)nb, SC_THREADS, 0, st>>>(vin, perm, V, V_dev, (float*)verts_out, newid, (unsigned long long*)scan_ws,
-                                                           (int)nb, (unsigned int*)((char*)scan_ws + desc_bytes), counts + 2, counts);
+                                                           (int)nb, (unsigned int*)((char*)scan_ws + desc_bytes), counts + 2, counts, dup);
     }
     if (g_faces_ready) {
         T3D_CUDA(cudaStreamWaitEvent(st, g_faces_ready, 0));
