@@ -205,7 +205,7 @@ def make_phantom_u8(Z_total, H, W, z0, z1, device):
     return out
 
 
-NCU_PACK_TRAFFIC_BYTES = 570400000   # k_pack_gap at C1: 555.6 MB read + 14.8 MB written (profiles/r02_ncu_full_fused_step_c1.txt)
+NCU_PACK_TRAFFIC_BYTES = 567000000   # k_pack_gap at C1: 552.3 MB read + 14.7 MB written (profiles/r02_ncu_full_pack_gap_and_staged_path_c1.txt)
 
 STAGE_BYTES = {  # algorithmic bytes per voxel of each volume-sized stage
     "pack_close": 1.0 + 0.125 + 0.25, "smooth": 4 * 0.25, "field_sign": 0.25, "mc_flags": 0.125 + 1.0 / 256,
@@ -459,8 +459,8 @@ def run_ours(args, Z, H, W, cfg):
         # (k_pack_gap); stacks it does not take (W % 128 != 0, fewer than 3 slices) go through the plain pack kernel
         # (a sharded step runs the same kernel over the interior planes of its slab when the slab has >= 16 slices: t3d_slab_pack)
         pack_gap = n_own >= 3 and W % 128 == 0 and (not sharded_run or n_own >= 16)
-        kcnt = torch.empty(n_own, dtype=torch.int64, device=dev)
-        kbb = torch.empty(6, dtype=torch.int32, device=dev)
+        kstat = torch.empty(n_own + 3, dtype=torch.int64, device=dev)      # per-slice counts, then the 6 extrema (zeroed by one memset)
+        kcnt, kbb = kstat[:n_own], kstat[n_own:].view(torch.int32)
 
         def pack_launch():
             if pack_gap:
@@ -702,8 +702,9 @@ def run_ours(args, Z, H, W, cfg):
             "peak": peak, "unit": "GB/s", "frac": achieved / peak, "algorithmic_bytes_per_launch": dom_bytes,
             "us_per_launch": 1e3 * pack_ms, "launches_timed": 20, "share_of_step": pack_ms / (ms / args.steps),
             "traffic": NCU_PACK_TRAFFIC_BYTES if (Z, H, W) == (512, 1024, 1024) and pack_gap else None,
-            "traffic_source": "profiles/ ncu --set full capture of this kernel at C1: dram__bytes_read.sum + "
-                              "dram__bytes_write.sum per launch (most of the 67 MB bit volume stays in the 126 MB L2)"}
+            "traffic_source": "profiles/r02_ncu_full_pack_gap_and_staged_path_c1.txt: ncu --set full of this kernel at C1, "
+                              "dram__bytes_read.sum + dram__bytes_write.sum per launch (most of the 67 MB bit volume it writes "
+                              "stays in the 126 MB L2)"}
     if stage_ms:
         roofline["stages"] = {k: {"GB/s": STAGE_BYTES[k] * per_gpu_vox / (stage_ms[k] * 1e-3) / 1e9,
                                   "frac": STAGE_BYTES[k] * per_gpu_vox / (stage_ms[k] * 1e-3) / 1e9 / peak}

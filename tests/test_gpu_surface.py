@@ -268,6 +268,27 @@ def test_fast_canonicalize_falls_back_when_order_cannot_be_verified(eng, oracle)
     assert np.array_equal(gv.cpu().numpy(), rv) and np.array_equal(gf.cpu().numpy(), rf)
 
 
+@pytest.mark.parametrize("dup_every", [0, 7, 1])
+def test_unique_pass_with_and_without_coinciding_vertices(eng, oracle, dup_every):
+    """The np.unique step runs an optimistic streaming pass (no two vertices coincide => index = sorted position) and falls
+    back on the device to the exact scan kernel when it meets an equal pair: both against numpy on vertex lists that are in
+    sorted order already (so the fast ordering is verified and the result of the unique kernels is what comes back)."""
+    rng = np.random.default_rng(23 + dup_every)
+    pts = np.unique(rng.integers(-40, 41, size=(6000, 3)).astype(np.float32) * np.float32(0.173), axis=0)   # sorted by (z, y, x)
+    if dup_every:
+        reps = np.where(np.arange(len(pts)) % dup_every == 0, 1 + (np.arange(len(pts)) % 3), 1)
+        pts = np.repeat(pts, reps, axis=0)                   # runs of 1..3 equal vertices, still sorted
+    V, F = len(pts), 2 * len(pts)
+    faces = rng.integers(0, V, size=(F, 3)).astype(np.int32)
+    tv, tf = torch.from_numpy(pts).cuda(), torch.from_numpy(faces).cuda()
+    vout, fout, counts = eng.canonicalize(tv, tf, sync=False, fast=True)
+    v2, f2, bad = (int(c) for c in counts.cpu().tolist())
+    assert bad == 0                                          # order verified on the device: no generic fallback involved
+    rv, rf = oracle.ensure_manifold_mesh(pts, faces)
+    assert v2 == len(rv) and f2 == len(rf)
+    assert np.array_equal(vout[:v2].cpu().numpy(), rv) and np.array_equal(fout[:f2].cpu().numpy(), rf)
+
+
 @pytest.mark.parametrize("seed,density", [(5, 0.35), (6, 0.5), (7, 0.65)])
 def test_ambiguous_cubes_are_resolved_like_the_oracle(eng, oracle, seed, density):
     """Raw noise (no smoothing): thousands of cubes with ambiguous faces / case 4.  Lewiner's face and interior tests pick
