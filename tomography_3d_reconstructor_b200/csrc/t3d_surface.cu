@@ -1140,17 +1140,11 @@ __device__ __forceinline__ void cta_radix_sort_u(uint32_t n, int passes, KeyFn k
     }
 }
 
-// Long segments fetch 8 elements per lane before consuming any (one exposed memory latency per 8 elements: 2.2x faster on the
-// 30..60 thousand z-edge vertices of a 4096 x 4096 layer); short ones (a few thousand elements: 1024 x 1024) are faster with
-// the plain one-element loop.  (n is uniform over the CTA.)
-template <typename KeyT, typename KeyFn, typename ValFn>
-__device__ __forceinline__ void cta_radix_sort(uint32_t n, int passes, KeyFn key_of, ValFn value_of, KeyT* keyA, KeyT* keyB, uint32_t* idxA,
-                                               uint32_t* idxB, uint32_t* out)
-{
-    if (n >= 16384u) cta_radix_sort_u<8, KeyT>(n, passes, key_of, value_of, keyA, keyB, idxA, idxB, out);
-    else cta_radix_sort_u<1, KeyT>(n, passes, key_of, value_of, keyA, keyB, idxA, idxB, out);
-}
-
+// ZS_U = elements per lane fetched before any is consumed.  Long segments want 8 (one exposed memory latency per 8 elements: the
+// 30..60 thousand z-edge vertices of a 4096 x 4096 layer sort 1.3x faster), short ones 1 (a few thousand elements per layer at
+// 1024 x 1024: the batched variant needs 64 registers instead of 40 and loses occupancy: 57 against 41 us).  Picked per launch
+// from the average layer length.
+template <int ZS_U>
 __global__ void __launch_bounds__(ZS_THREADS) k_zsort_layers(CanonS c, uint32_t* __restrict__ keyA, uint32_t* __restrict__ keyB,
                                                             uint32_t* __restrict__ idxA, uint32_t* __restrict__ idxB,
                                                             uint32_t* __restrict__ zperm)
@@ -1168,8 +1162,8 @@ __global__ void __launch_bounds__(ZS_THREADS) k_zsort_layers(CanonS c, uint32_t*
         for (uint32_t i = s + threadIdx.x; i < e; i += ZS_THREADS) zperm[i] = i;
         return;
     }
-    cta_radix_sort<uint32_t>(n, (c.zkey_bits + 7) / 8, [&](uint32_t i) { return canon_zkey(c, s + i, nx, ny, gZ); },
-                             [&](uint32_t i) { return s + i; }, keyA + s, keyB + s, idxA + s, idxB + s, zperm + s);
+    cta_radix_sort_u<ZS_U, uint32_t>(n, (c.zkey_bits + 7) / 8, [&](uint32_t i) { return canon_zkey(c, s + i, nx, ny, gZ); },
+                                     [&](uint32_t i) { return s + i; }, keyA + s, keyB + s, idxA + s, idxB + s, zperm + s);
 }
 
 // the clamp group (vertices the z map clamps onto z = 0, see above): one CTA orders it by its 64-bit (y, x) key;
@@ -1185,7 +1179,7 @@ __global__ void __launch_bounds__(ZS_THREADS) k_gsort(CanonS c, unsigned long lo
     if (n == 0 || n > c.cap_g0) return;
     auto raw_of = [&](uint32_t t) -> uint32_t { return t < gX ? t : t < gX + gY ? nx + (t - gX) : nx + ny + (t - gX - gY); };
     if (n == 1) { if (threadIdx.x == 0) gperm[0] = raw_of(0); return; }
-    cta_radix_sort<unsigned long long>(n, 8, [&](uint32_t t) {
+    cta_radix_sort_u<1, unsigned long long>(n, 8, [&](uint32_t t) {
         const float* v = c.verts + 3 * (int64_t)raw_of(t);
         return ((unsigned long long)float_key(v[1]) << 32) | float_key(v[2]);
     }, raw_of, keyA, keyB, idxA, idxB, gperm);
@@ -1357,7 +1351,10 @@ extern "C" int t3d_mesh_canonicalize_structured_dev(const void* verts_in, const 
             uint32_t* keyB = keyA + cap_z;
             uint32_t* idxA = (uint32_t*)zkeys_b;
             uint32_t* idxB = idxA + cap_z;
-            k_zsort_layers<<<Zs, ZS_THREADS, 0, st>>>(c, keyA, keyB, idxA, idxB, zperm);
+            static const int force_u = getenv("T3D_ZSORT_U") ? atoi(getenv("T3D_ZSORT_U")) : 0;      // A/B switch: 1 or 8
+            const bool batched = force_u ? force_u == 8 : (int64_t)cap_z >= 4096 * (int64_t)Zs;
+            if (batched) k_zsort_layers<8><<<Zs, ZS_THREADS, 0, st>>>(c, keyA, keyB, idxA, idxB, zperm);
+            else k_zsort_layers<1><<<Zs, ZS_THREADS, 0, st>>>(c, keyA, keyB, idxA, idxB, zperm);
             t3d_count_launches(1);
         }
     }
