@@ -213,6 +213,13 @@ def test_classes_vs_oracle(eng, oracle):
     fresh = ref.copy()
     assert vc.calculate_voxel_volume_variable_depth(fresh, mm_x, mm_y, depths) == \
         oracle.calculate_voxel_volume_variable_depth(ref, mm_x, mm_y, depths)
+    # occupancies in another dtype (0 / 1 values): accepted like the reference's np.sum / np.where accept them
+    for dt in (np.uint8, np.int32, np.float32):
+        other = ref.astype(dt)
+        assert vc.calculate_voxel_volume(other, mm_x, mm_y, 0.1) == oracle.calculate_voxel_volume(ref, mm_x, mm_y, 0.1)
+        assert vc.calculate_bounding_box(other, mm_x, mm_y, 0.1) == oracle.calculate_bounding_box(ref, mm_x, mm_y, 0.1)
+    with pytest.raises(TypeError, match="only 0 and 1"):      # 0 / 255 masks are not occupancies: refused, not reinterpreted
+        vc.calculate_voxel_volume(ref.astype(np.uint8) * 255, mm_x, mm_y, 0.1)
     sm = vp.smooth_voxel_data(fresh, 3, True)
     assert np.array_equal(sm, oracle.smooth_voxel_data(ref, 3, True))
     pc = vp.generate_point_cloud(sm, mm_x, mm_y, depths, 2)

@@ -449,9 +449,15 @@ _slab_retuned: Dict = {}
 
 def reconstruct_fused(masks_u8: torch.Tensor, Zg: int, z0: int, threshold: int, side_counts, total_depth_mm: float,
                       x_length_mm: float, y_length_mm: float, iterations: int = 3, add_padding: bool = True, group=None,
-                      use_graph: bool = False) -> Dict:
+                      use_graph: bool = False, collective_capture: bool = False) -> Dict:
     """Same contract and results as reconstruct(); the step is enqueued without any host synchronisation (use_graph:
     replayed from a CUDA graph that includes the NCCL operations; all ranks must pass the same value).
+
+    A captured graph is bound to the input buffer it was captured on, and (re)capturing runs the step's collectives, so
+    with use_graph EVERY rank has to (re)capture in the same call.  That holds when all ranks pass persistent buffers (what
+    reconstruct_host and bench.py do) or all pass fresh ones.  A caller that cannot promise it sets collective_capture=True:
+    the ranks then agree on "somebody needs a capture" with one small all-reduce per call (a host synchronisation, ~50 us:
+    not the default).
 
     The first call for a given (slab, parameters) runs the staged path to learn the mesh sizes; if any rank reports a
     capacity overflow, an unverifiable fast ordering or an empty slab, every rank re-runs the staged path."""
@@ -476,8 +482,14 @@ def reconstruct_fused(masks_u8: torch.Tensor, Zg: int, z0: int, threshold: int, 
         plan = FusedSlabPlan(n, H, W, Zg, z0, threshold, side_counts, total_depth_mm, x_length_mm, y_length_mm, iterations,
                              add_padding, caps, masks_u8.device, rank, world, group)
         _slab_plans[key] = plan
-    if use_graph and plan.graph_ptr != masks_u8.data_ptr():
-        plan.capture(masks_u8)
+    if use_graph:
+        need = plan.graph_ptr != masks_u8.data_ptr()
+        if collective_capture and world > 1:
+            flag = torch.tensor([1 if need else 0], dtype=torch.int32, device=masks_u8.device)
+            dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=group)
+            need = bool(int(flag.item()))
+        if need:
+            plan.capture(masks_u8)
     h = plan.run(masks_u8, use_graph)
     me = h[rank]
     bad = h[:, R.R_UNVERIFIED] != 0
@@ -489,7 +501,7 @@ def reconstruct_fused(masks_u8: torch.Tensor, Zg: int, z0: int, threshold: int, 
             pipeline._retune(("slab",) + key, int(me[R.R_NG0]), plan.caps[4])
         _slab_plans.pop(key, None)
         return reconstruct_fused(masks_u8, Zg, z0, threshold, side_counts, total_depth_mm, x_length_mm, y_length_mm, iterations,
-                                 add_padding, group, use_graph)
+                                 add_padding, group, use_graph, collective_capture)
     if (h[:, R.R_OVERFLOW] != 0).any() or bad.any() or (h[:, R.R_NT] == 0).any():
         _slab_plans.pop(key, None)
         _slab_hints.pop(key, None)

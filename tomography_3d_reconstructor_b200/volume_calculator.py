@@ -19,8 +19,18 @@ class VolumeCalculator:
 
     @staticmethod
     def _dv(voxel_data: np.ndarray) -> engine.DeviceVolume:
-        if not isinstance(voxel_data, np.ndarray) or voxel_data.dtype != np.bool_:
-            raise TypeError("voxel_data must be a numpy bool array (Z,H,W)")
+        """The device volume of a (Z,H,W) occupancy array.  bool arrays are what the pipeline produces; like the reference
+        (np.sum / np.where work on any dtype, volume_calculator.py:20,34,40) other numeric dtypes are accepted as long as
+        they are occupancies, i.e. hold only 0 and 1 -- then np.sum IS the voxel count the device computes.  Anything else
+        (say 0/255 masks, where the reference would return 255 x the volume) is refused rather than silently reinterpreted."""
+        if not isinstance(voxel_data, np.ndarray) or voxel_data.ndim != 3:
+            raise TypeError("voxel_data must be a numpy array (Z,H,W)")
+        if voxel_data.dtype != np.bool_:
+            known = engine.volumes.lookup(voxel_data)
+            if known is not None:
+                return known
+            if voxel_data.dtype.kind not in "uif" or not bool(np.logical_or(voxel_data == 0, voxel_data == 1).all()):
+                raise TypeError("voxel_data must be a bool array or a numeric array holding only 0 and 1")
         return engine.volume_from_host(voxel_data)
 
     def calculate_voxel_volume(self, voxel_data: np.ndarray, mm_per_pixel_x: float,
