@@ -535,14 +535,13 @@ __global__ void __launch_bounds__(128) k_mc_emit(EmitArgs a)
             ++pT;
         }
     };
-    if (AMB == 0) {                       // the common kernel: classic rows only
+    if constexpr (AMB == 0) {             // the common kernel: classic rows only
         for (uint32_t q = m.act; q;) {
             const int b = __ffs(q) - 1;
             q &= q - 1;
             emit_classic(b, cube_case(m, b));
         }
-        return;
-    }
+    } else {
     for (uint32_t q = m.act; q;) {        // words that may hold ambiguous cubes
         const int b = __ffs(q) - 1;
         q &= q - 1;
@@ -557,6 +556,7 @@ __global__ void __launch_bounds__(128) k_mc_emit(EmitArgs a)
             f[0] = (int32_t)vertex_id(b, row[t + 2]); f[1] = (int32_t)vertex_id(b, row[t + 1]); f[2] = (int32_t)vertex_id(b, row[t]);
             ++pT;
         }
+    }
     }
     };
     if (AMB == 1) {

@@ -353,29 +353,9 @@ static int reconstruct_core(const uint32_t* grid, const SlabGeom& g, int H, int 
         uint32_t* S_origin = S + s_ps + nws + S_XPAD / 32;   // word of (plane 1, row 1, x = S_XPAD)
         const int z0 = g.hl - sl;
         const int ring_tail = (nws - (int)nw - S_XPAD / 32) / 4;
-        // Opt-in experiment (T3D_MORPH_ZTILE=n planes per chunk): L2-tiled temporal blocking -- the four stages run chunk by
-        // chunk over z with the intermediate chunks in reused ping-pong buffers that stay in L2, so DRAM would see the grid
-        // read once and the sign volume written once instead of 4 reads + 4 writes.  Measured at 512x4096x4096: SLOWER
-        // (8.54 ms per step with 32-plane chunks, 9.10 with 8, against 7.99 untiled): 4 x Z/n short dependent launches with
-        // (n+6)/n of the work each cost more than the DRAM traffic they save.  Off by default.
-        static const int tile_env = getenv("T3D_MORPH_ZTILE") ? atoi(getenv("T3D_MORPH_ZTILE")) : 0;
-        const int ztile = tile_env > 0 ? tile_env : 0;
-        if (ztile > 0 && ztile < Zl) {
-            for (int a = z0; a < z0 + Zl; a += ztile) {
-                const int b = imin(a + ztile, z0 + Zl);
-                // output ranges of the four stages (global planes), clamped to the volume: each stage needs one plane more
-                const int lo1 = a - 3 < 0 ? 0 : a - 3, hi1 = imin(Zx, b + 3);
-                const int lo2 = a - 2 < 0 ? 0 : a - 2, hi2 = imin(Zx, b + 2);
-                const int lo3 = a - 1 < 0 ? 0 : a - 1, hi3 = imin(Zx, b + 1);
-                // chunk buffers hold planes [lo, hi) of a stage at local index 0..: a stage reads its input as a volume of
-                // (hi - lo) planes whose ends are either true volume ends (border rules apply) or planes it does not compute
-                RUN(t3d_morph_stage(grid, tA, Zx, H, W, lo1, hi1 - lo1, (int)nw, plane_words, true, false, 0, nullptr, st));
-                RUN(t3d_morph_stage(tA, tB, hi1 - lo1, H, W, lo2 - lo1, hi2 - lo2, (int)nw, plane_words, false, false, 0, nullptr, st));
-                RUN(t3d_morph_stage(tB, tA, hi2 - lo2, H, W, lo3 - lo2, hi3 - lo3, (int)nw, plane_words, false, false, 0, nullptr, st));
-                RUN(t3d_morph_stage(tA, S_origin + (int64_t)(a - z0) * s_ps, hi3 - lo3, H, W, a - lo3, b - a, nws, s_ps, true, true, ring_tail,
-                                    R + R_COUNTS + Zx + a, st));
-            }
-        } else if (t3d_morph4_eligible(Zx, H, W)) {
+        // (An L2-tiled variant of the four-launch chain -- chunks of planes with the intermediate stages kept in L2 -- was
+        // measured slower than the untiled chain at 512x4096x4096, profiles/r02_morph_ztile_sweep_c4slab.txt, and removed.)
+        if (t3d_morph4_eligible(Zx, H, W)) {
             // the four stages in one pass: grid read once, sign volume written once
             RUN(t3d_morph4_launch(grid, S_origin, Zx, H, W, z0, Zl, nws, s_ps, ring_tail, R + R_COUNTS + Zx + z0, st));
         } else {
