@@ -690,6 +690,7 @@ def run_ours(args, Z, H, W, cfg):
     roofline = {"bound": "hbm", "scope": "whole step (every kernel of the path, SURVEY.md 8d)", "achieved": step_gbs,
                 "peak": peak * world, "unit": "GB/s", "frac": step_gbs / (peak * world), "traffic": None,
                 "peak_source": peak_src + (" x %d GPUs" % world if world > 1 else ""),
+                "frac_of_nominal_8TBs": step_gbs / (8000.0 * world),     # also against the nominal 8 TB/s
                 "algorithmic_bytes_per_step": bytes_alg,
                 "algorithmic_bytes": "%.3g B/voxel x %d voxels + 12 B x (%d vertices + %d faces)" % (per_voxel, voxels, V, F)}
     if pack_ms is not None:
