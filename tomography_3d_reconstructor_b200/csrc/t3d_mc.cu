@@ -361,9 +361,7 @@ __global__ void __launch_bounds__(128) k_mc_words(Grid g, McField fld, uint32_t*
         // a fixed, small grid striding over the word list: nearly every entry is skipped (a capacity-sized launch of
         // threads that return at once cost 10 us of CTA launches at 512 x 1024 x 1024)
         uint32_t na = 0;
-        for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) {
-            const uint32_t iraw = aw_idx[k];
-            if (!(iraw & AW_AMB)) continue;
+        auto fix_word = [&](int64_t k, uint32_t iraw) {
             const uint32_t i = iraw & AW_MASK;
             const uint32_t row = i / (uint32_t)g.nws;
             const int w = (int)(i - row * (uint32_t)g.nws);
@@ -380,6 +378,20 @@ __global__ void __launch_bounds__(128) k_mc_words(Grid g, McField fld, uint32_t*
                 ++na;
             }
             aw_cnt[3 * (int64_t)n_active + k] += (uint32_t)delta;
+        };
+        // four list entries per load (the list is 16-byte aligned): the scan for flag bits is what this launch spends its time on
+        const int64_t n4 = ((uintptr_t)aw_idx & 15) ? 0 : (n >> 2), stride = (int64_t)gridDim.x * blockDim.x, t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        for (int64_t c = t0; c < n4; c += stride) {
+            const uint4 v = reinterpret_cast<const uint4*>(aw_idx)[c];
+            if (!((v.x | v.y | v.z | v.w) & AW_AMB)) continue;
+            if (v.x & AW_AMB) fix_word(4 * c, v.x);
+            if (v.y & AW_AMB) fix_word(4 * c + 1, v.y);
+            if (v.z & AW_AMB) fix_word(4 * c + 2, v.z);
+            if (v.w & AW_AMB) fix_word(4 * c + 3, v.w);
+        }
+        for (int64_t k = 4 * n4 + t0; k < n; k += stride) {      // (the last n % 4 entries)
+            const uint32_t iraw = aw_idx[k];
+            if (iraw & AW_AMB) fix_word(k, iraw);
         }
         if (na) atomicAdd(n_ambiguous, (unsigned long long)na);
     }
@@ -433,6 +445,13 @@ __global__ void __launch_bounds__(128) k_mc_emit(EmitArgs a)
     __shared__ uint32_t s_base[12][128];
     __shared__ uint32_t s_mask[12][128];
     __shared__ uint32_t s_next[4][128];   // ids of the y/z-edge vertices at bit 0 of the next word (edges 1, 5, 9, 10 at b = 31)
+    if (AMB == 1) {                       // nearly every CTA of this launch finds no flagged word in its share of the list:
+        int any = 0;                      // leave before the table copy (the second look at the list comes from L2)
+        uint32_t nw_ = a.n_active;
+        if (a.sizes && a.sizes[0] < nw_) nw_ = (uint32_t)a.sizes[0];
+        for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < nw_; k += gridDim.x * blockDim.x) any |= (int)(a.aw_idx[k] >> 31);
+        if (!__syncthreads_or(any)) return;
+    }
     if (PARTS & 2) {
         const int4* src = reinterpret_cast<const int4*>(&g_tri_table[0][0]);
         int4* dst = reinterpret_cast<int4*>(&s_tri[0][0]);
