@@ -109,3 +109,21 @@ def test_z_map_value_and_zkey_bits_follow_the_reference_z_map(oracle):
             span = int(np.diff(z.view(np.uint32).astype(np.int64)).max())
             assert nb == 32 or span < (1 << nb)
     assert engine.zkey_bits(np.array([]), True, 10) == 32
+
+
+def test_pack_bits_host_layout():
+    """Host-side bit packing for the bit-packed entry point (sharded.reconstruct_host_bits): LSB-first along x, 32 voxels per
+    word, rows padded to a multiple of 4 words, zero beyond W -- the layout t3d_pack_masks produces on the device."""
+    import numpy as np
+    from tomography_3d_reconstructor_b200 import engine, sharded
+    rng = np.random.default_rng(3)
+    for W in (1, 31, 32, 33, 70, 128, 200):
+        m = rng.integers(0, 2, size=(3, 5, W)).astype(bool)
+        bits = sharded.pack_bits_host([m[z] for z in range(3)])            # a list of slices, like ImageLoader's
+        wpr = engine.words_per_row(W)
+        assert bits.shape == (3, 5, wpr) and bits.dtype.itemsize == 4 and wpr % 4 == 0 and wpr * 32 >= W
+        for x in range(W):
+            assert np.array_equal((bits[:, :, x // 32] >> np.uint32(x % 32)) & 1, m[:, :, x].astype(np.uint32))
+        full = np.unpackbits(bits.view(np.uint8), axis=-1, bitorder="little")
+        assert not full[:, :, W:].any()
+        assert np.array_equal(sharded.pack_bits_host(m.astype(np.uint8)), bits)   # 0/1 arrays of another dtype
