@@ -470,6 +470,7 @@ def run_ours(args, Z, H, W, cfg):
             if rc:
                 raise RuntimeError("pack kernel failed: rc=%d" % rc)
 
+        kstat.zero_()      # (t3d_pack_gap accumulates its counts / extrema: zeroed once, the timed launches are the kernel alone)
         for _ in range(3):
             pack_launch()
         k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

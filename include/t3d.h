@@ -44,7 +44,8 @@ int t3d_pack_masks(const void* masks_u8, int Z, int H, int W, int threshold, voi
  * masks (the kernel of the single-enqueue path that streams the uint8 stack).  The end planes are written raw: the caller
  * hole-fills them and rewrites planes 0, 1, Z-2, Z-1 (what t3d_reconstruct does).  Requires Z >= 3, W % 128 == 0, a 16-byte
  * aligned stack and 1 <= threshold <= 255 (returns 2 otherwise).  counts_u64: Z per-slice counts or NULL; bbox_u32x6:
- * {INT_MAX - zmin, zmax + 1, INT_MAX - ymin, ymax + 1, INT_MAX - xmin, xmax + 1} or NULL; both are zeroed by the call. */
+ * {INT_MAX - zmin, zmax + 1, INT_MAX - ymin, ymax + 1, INT_MAX - xmin, xmax + 1} or NULL.  Both are accumulated into with
+ * atomics (add / max): the CALLER zeroes them beforehand (the call itself is this one kernel and nothing else). */
 int t3d_pack_gap(const void* masks_u8, int Z, int H, int W, int threshold, void* bits, void* counts_u64, void* bbox_u32x6,
                  void* stream);
 

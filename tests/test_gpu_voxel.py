@@ -48,8 +48,8 @@ def test_pack_gap_fused_kernel(eng, shape, thr):
     t = eng.upload_u8(u8)
     nw = eng.words_per_row(W)
     bits = torch.empty((Z, H, nw), dtype=torch.int32, device="cuda")
-    cnt = torch.full((Z,), -1, dtype=torch.int64, device="cuda")
-    bb = torch.full((6,), -1, dtype=torch.int32, device="cuda")
+    cnt = torch.zeros((Z,), dtype=torch.int64, device="cuda")      # accumulated into: zeroed by the caller
+    bb = torch.zeros((6,), dtype=torch.int32, device="cuda")
     rc = lib.t3d_pack_gap(eng._p(t), Z, H, W, thr, eng._p(bits), eng._p(cnt), eng._p(bb), eng._stream())
     assert rc == 0, lib.t3d_last_error()
     torch.cuda.synchronize()

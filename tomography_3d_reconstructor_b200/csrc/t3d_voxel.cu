@@ -718,12 +718,7 @@ extern "C" int t3d_pack_gap(const void* masks_u8, int Z, int H, int W, int thres
         return 2;
     }
     cudaStream_t st = (cudaStream_t)stream;
-    if (counts_u64 && bbox_u32x6 && (char*)bbox_u32x6 == (char*)counts_u64 + sizeof(unsigned long long) * Z) {
-        if (t3d_zero_async(counts_u64, sizeof(unsigned long long) * Z + 6 * sizeof(unsigned int), st)) return 1;   // adjacent: one memset
-    } else {
-        if (counts_u64 && t3d_zero_async(counts_u64, sizeof(unsigned long long) * Z, st)) return 1;
-        if (bbox_u32x6 && t3d_zero_async(bbox_u32x6, 6 * sizeof(unsigned int), st)) return 1;
-    }
+    // counts / extrema are ACCUMULATED (atomics): the caller zeroes them, as t3d_reconstruct does with its one up-front zeroing kernel
     return t3d_pack_gap_launch(masks_u8, Z, H, W, threshold, bits, (unsigned long long*)counts_u64, (unsigned int*)bbox_u32x6, 0, st);
 }
 
